@@ -1,0 +1,24 @@
+"""bayesloop_b200 -- B200-native grid forward-backward inference engine with the bayesloop API.
+
+    import bayesloop_b200 as bl
+    S = bl.HyperStudy()
+    S.loadData(counts)
+    S.set(bl.om.Poisson('rate', bl.oint(0, 12, 1000)),
+          bl.tm.GaussianRandomWalk('sigma', bl.cint(0, 0.2, 512), target='rate'))
+    S.fit()
+
+Same names as the reference package (bayesloop/__init__.py:4-18) for everything on the hot path; the probability
+parser, plotting, Jeffreys-prior derivation and file I/O of the reference are outside this engine's scope
+(DESIGN.md "Out of scope").
+"""
+from . import observationModels
+from . import observationModels as om
+from . import transitionModels
+from . import transitionModels as tm
+from .core import ChangepointStudy, HyperStudy, OnlineStudy, Study
+from .exceptions import ConfigurationError, PostProcessingError
+from .helper import cint, oint
+
+__all__ = ['Study', 'HyperStudy', 'ChangepointStudy', 'OnlineStudy', 'observationModels', 'om', 'transitionModels',
+           'tm', 'cint', 'oint', 'ConfigurationError', 'PostProcessingError']
+__version__ = '0.1.0'

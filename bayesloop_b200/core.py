@@ -1,0 +1,1185 @@
+"""Study classes of the B200 engine: same public API as bayesloop/core.py, different machine underneath.
+
+The reference runs `Study.fit` as a Python loop over time steps (core.py:372-470) and `HyperStudy.fit` as a Python
+loop over hyper-parameter combinations that calls it (core.py:1349-1366).  Here the combinations are the BATCH: the
+transition-model tree is lowered once into a flat per-combo program (transitionModels.lower), and one
+`blg_forward` + one `blg_backward` call (include/blgrid.h) run the whole time loop for a wave of combinations
+inside persistent sm_100a kernels.  Host code below only prepares inputs (grid, prior, hyper-grid, windows) and
+post-processes O(B) / O(T x G) results; nothing here touches a grid cell per time step.
+"""
+import math
+from collections.abc import Iterable
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+from . import transitionModels as _tm
+from .exceptions import ConfigurationError, PostProcessingError
+from .helper import assignNestedItem, flatten, is_regular, recursiveIndex
+from .observationModels import KIND_GAUSSIAN_MEAN, KIND_TABLE, ObservationModel
+from .preprocessing import movingWindow
+from .transitionModels import TransitionModel
+
+COAL_MINING_DISASTERS = (  # UK coal mining disasters per year, 1852-1961 (the series of core.py:82-86)
+    "5410434063340263354531441553425223421322111130010110031032201110"
+    "1010002100011023311211112330001400010000010010")
+
+
+def _is_sympy_rv(obj):
+    try:
+        import sympy.stats.rv
+        return isinstance(obj, sympy.stats.rv.RandomSymbol)
+    except Exception:
+        return False
+
+
+def _sympy_density(rv, symbol):
+    from scipy.special import beta as beta_func
+    from scipy.special import factorial
+    from sympy import lambdify
+    from sympy.stats import density
+    return lambdify([symbol], density(rv)(symbol), modules=['numpy', {'factorial': factorial, 'beta': beta_func}])
+
+
+def _free_symbols(rv):
+    for arg in rv._sorted_args:
+        dist = getattr(arg, 'distribution', None)
+        if dist is not None:
+            return list(dist.free_symbols)
+    return []
+
+
+class _Session:
+    """Device-side constants of one fit: plan, data series, prior, likelihood table."""
+
+    def __init__(self, study, eng):
+        om = study.observationModel
+        self.eng = eng
+        self.T = len(study.formattedData)
+        self.gridSize = list(study.gridSize)
+        self.G = int(np.prod(self.gridSize))
+        raw = np.asarray(study.rawData, dtype=float)
+        self.nCols = 1 if raw.ndim == 1 else int(raw.shape[1])
+        if raw.ndim > 2:
+            raise ConfigurationError('Data with more than two dimensions is not supported.')
+        kind = getattr(om, 'deviceKind', KIND_TABLE)
+        if type(om).pdf is not ObservationModel.pdf:  # a subclass that brings its own pdf wins over the op-code
+            kind = KIND_TABLE
+        if len(self.gridSize) > 2:
+            raise NotImplementedError('The engine supports observation models with one or two parameters.')
+        if kind == KIND_GAUSSIAN_MEAN and self.nCols != 2:
+            raise ConfigurationError('GaussianMean expects data rows of the form [value, std].')
+        self.kind = kind
+        self.plan = eng.plan(study.marginalGrid, study.latticeConstant, kind, om.segmentLength, self.nCols)
+        self.data = eng.to_device(raw.reshape(len(raw), self.nCols), pinned=True)
+        self.likTable = None
+        if kind == KIND_TABLE:  # plugin without op-code: one host evaluation per time step, shared by all combos
+            table = np.empty((self.T, self.G))
+            for i in range(self.T):
+                table[i] = np.asarray(om.processedPdf(study.grid, study.formattedData[i]), dtype=float).ravel()
+            self.likTable = eng.to_device(table, pinned=True)
+        self.prior = eng.to_device(np.asarray(study._computePrior(silent=True), dtype=float).reshape(-1))
+        self.resetBase = None
+        self._study = study
+
+    def reset_base(self):
+        """Observation-model prior on the grid, normalised to sum 1 (what ChangePoint / Independent restore:
+        transitionModels.py:300-310, :350-359)."""
+        if self.resetBase is None:
+            study = self._study
+            prior = study.observationModel.prior
+            if callable(prior):
+                values = np.asarray(prior(*study.grid), dtype=float) * np.ones(study.gridSize)
+            elif isinstance(prior, np.ndarray):
+                values = np.array(prior, dtype=float)
+            else:
+                values = np.ones(study.gridSize)
+            values = values / np.sum(values)
+            self.resetBase = self.eng.to_device(values.reshape(-1))
+        return self.resetBase
+
+
+class Study(object):
+    """Fit with fixed hyper-parameter values (reference: core.py:39-486)."""
+
+    def __init__(self, silent=False, engine=None):
+        self.observationModel = None
+        self.transitionModel = None
+        self.gridSize = []
+        self.boundaries = []
+        self.marginalGrid = []
+        self.grid = []
+        self.latticeConstant = []
+        self.rawData = np.array([])
+        self.formattedData = np.array([])
+        self.rawTimestamps = None
+        self.formattedTimestamps = None
+        self.posteriorSequence = []
+        self.posteriorMeanValues = []
+        self.logEvidence = 0
+        self.localEvidence = []
+        self.selectedHyperParameters = []
+        self.fitWarningCounter = 0
+        self._engineOverride = engine
+        if not silent:
+            print('+ Created new study.')
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    def _engine(self):
+        return self._engineOverride if self._engineOverride is not None else _engine.default_engine()
+
+    @property
+    def log10Evidence(self):
+        return self.logEvidence / np.log(10)
+
+    def loadExampleData(self, silent=False):
+        self.rawData = np.array([int(c) for c in COAL_MINING_DISASTERS])
+        self.rawTimestamps = np.arange(1852, 1962)
+        if not silent:
+            print('+ Successfully imported example data.')
+
+    def loadData(self, array, timestamps=None, silent=False):
+        if isinstance(array, np.ndarray):
+            self.rawData = array
+        elif isinstance(array, list):
+            if not silent:
+                print('! WARNING: Data supplied as list, not as Numpy array. Converting list to Numpy array '
+                      '(dtype=float).')
+            self.rawData = np.array(array, dtype=float)
+        else:
+            raise ConfigurationError('Data type not supported. Please provide data as Numpy array.')
+        self.rawTimestamps = np.arange(len(self.rawData))
+        if timestamps is not None:
+            if len(timestamps) == len(array):
+                self.rawTimestamps = np.array(timestamps)
+            elif not silent:
+                print('! WARNING: Number of timestamps does not match number of data points. Omitting timestamps.')
+        if not silent:
+            print('+ Successfully imported array.')
+
+    def load(self, array, timestamps=None, silent=False):
+        self.loadData(array, timestamps=timestamps, silent=silent)
+
+    def setObservationModel(self, L, silent=False):
+        """Attach the likelihood plugin and build the parameter grid from its parameter values."""
+        self.observationModel = L
+        self.marginalGrid, self.gridSize, self.boundaries, self.latticeConstant = [], [], [], []
+        for values, name in zip(L.parameterValues, L.parameterNames):
+            if values is None:
+                try:
+                    values = L.estimateParameterValues(name, self.rawData)
+                except Exception:
+                    raise ConfigurationError('Could not estimate parameter values for "{}".'.format(name))
+                print('+ Estimated parameter interval for "{}": [{}, {}] ({} values).'
+                      .format(name, values[0], values[-1], len(values)))
+            values = np.array(values, dtype=float)
+            self.marginalGrid.append(values)
+            self.gridSize.append(len(values))
+            self.boundaries.append([values[0], values[-1]])
+            if is_regular(values):
+                self.latticeConstant.append(np.abs(values[0] - values[1]))
+            else:
+                print('! WARNING: Supplied parameter values for "{}" are not equally spaced. Assuming categorical '
+                      'parameter.'.format(name))
+                self.latticeConstant.append(1.)
+        self.grid = list(np.meshgrid(*self.marginalGrid, indexing='ij'))
+        if self.transitionModel is not None:
+            self.transitionModel.latticeConstant = self.latticeConstant
+        if not silent:
+            print('+ Observation model: {}. Parameter(s): {}'.format(L, L.parameterNames))
+
+    def setOM(self, L, silent=False):
+        self.setObservationModel(L, silent=silent)
+
+    def setTransitionModel(self, T, silent=False):
+        if str(T) == 'Break-point':
+            raise ConfigurationError('The "BreakPoint" transition model can only be used with the '
+                                     '"SerialTransitionModel" class.')
+        self.transitionModel = T
+        T.study = self
+        T.latticeConstant = self.latticeConstant
+        if not silent:
+            print('+ Transition model: {}. Hyper-Parameter(s): {}'
+                  .format(T, self._unpackAllHyperParameters(values=False)))
+
+    def setTM(self, T, silent=False):
+        self.setTransitionModel(T, silent=silent)
+
+    def set(self, *args, **kwargs):
+        for key in kwargs:
+            if key != 'silent':
+                raise TypeError("set() got an unexpected keyword argument '{}'".format(key))
+        silent = kwargs.get('silent', False)
+        seen = set()
+        for model in args:
+            if isinstance(model, ObservationModel):
+                role, setter = 'observation', self.setObservationModel
+            elif isinstance(model, TransitionModel):
+                role, setter = 'transition', self.setTransitionModel
+            else:
+                raise ConfigurationError('Expected observation model or transition model instance as first argument.')
+            if role in seen:
+                raise ConfigurationError('More than one {} model supplied.'.format(role))
+            seen.add(role)
+            setter(model, silent=silent)
+
+    def _computePrior(self, silent=False):
+        """Initial parameter distribution on the grid with the reference's normalisation conventions
+        (core.py:184-265): flat / array / callable priors end up summing to 1/prod(latticeConstant) -- arrays are
+        normalised IN PLACE like the reference does -- SymPy random variables are taken as densities as they are."""
+        prior = self.observationModel.prior
+        cell = np.prod(self.latticeConstant)
+        if prior is None:
+            flat = np.ones(self.gridSize)
+            return flat / np.sum(flat) / cell
+        if isinstance(prior, np.ndarray):
+            if prior.shape != tuple(self.gridSize):
+                raise ConfigurationError('Prior array does not match parameter grid size.')
+            total = np.sum(prior)
+            if total != 1.:
+                prior /= total
+                prior /= cell
+            return prior
+        if callable(prior):
+            values = prior(*self.grid) * np.ones(self.gridSize)
+            total = np.sum(values)
+            if total != 1.:
+                values = values / total / cell
+            return values
+        rvs = [prior] if _is_sympy_rv(prior) else prior
+        if isinstance(rvs, (list, tuple)):
+            import string
+
+            import sympy
+            if len(rvs) != len(self.observationModel.parameterNames):
+                raise ConfigurationError('Observation model contains {} parameters, but {} priors were provided.'
+                                         .format(len(self.observationModel.parameterNames), len(rvs)))
+            values = 1.
+            for letter, rv, axisGrid in zip(string.ascii_lowercase, rvs, self.grid):
+                if not _is_sympy_rv(rv):
+                    raise ConfigurationError('Only lambda functions or SymPy random variables can be used as a prior.')
+                if len(_free_symbols(rv)) > 0:
+                    raise ConfigurationError('Prior distribution must not contain free parameters.')
+                values = values * _sympy_density(rv, sympy.Symbol(letter))(axisGrid)
+            return np.asarray(values, dtype=float) * np.ones(self.gridSize)
+        raise ConfigurationError('Unsupported prior specification.')
+
+    # ------------------------------------------------------------------------ hyper-parameter tree plumbing
+    def _unpackHyperParameters(self, transitionModel, values=False):
+        out = [self._unpackHyperParameters(m, values=values) for m in getattr(transitionModel, 'models', [])]
+        if hasattr(transitionModel, 'hyperParameterNames'):
+            out.extend(transitionModel.hyperParameterValues if values else transitionModel.hyperParameterNames)
+        return out
+
+    def _unpackAllHyperParameters(self, values=True):
+        return list(flatten(self._unpackHyperParameters(self.transitionModel, values=values)))
+
+    def _locate(self, nameTree, name):
+        path = recursiveIndex(nameTree, name)
+        if len(path) == 0:
+            raise ConfigurationError('Could not find any hyper-parameter named {}.'.format(name))
+        model = self.transitionModel
+        for pos in path[:-1]:
+            model = model.models[pos]
+        assignNestedItem(nameTree, path, ' ')  # a name listed twice addresses consecutive occurrences
+        return model, model.hyperParameterNames.index(name)
+
+    def _unpackSelectedHyperParameters(self):
+        if not self.selectedHyperParameters:
+            return self._unpackAllHyperParameters()
+        tree = self._unpackHyperParameters(self.transitionModel)
+        out = []
+        for name in self.selectedHyperParameters:
+            model, pos = self._locate(tree, name)
+            out.append(model.hyperParameterValues[pos])
+        return out
+
+    def _setAllHyperParameters(self, x):
+        tree = self._unpackHyperParameters(self.transitionModel)
+        names = list(flatten(self._unpackHyperParameters(self.transitionModel)))
+        for name, value in zip(names, list(x)):
+            model, pos = self._locate(tree, name)
+            model.hyperParameterValues[pos] = value
+
+    def _setSelectedHyperParameters(self, x):
+        if not self.selectedHyperParameters:
+            self._setAllHyperParameters(x)
+            return 1
+        tree = self._unpackHyperParameters(self.transitionModel)
+        for name, value in zip(self.selectedHyperParameters, list(x)):
+            model, pos = self._locate(tree, name)
+            model.hyperParameterValues[pos] = value
+        return 1
+
+    def _unpackLabelled(self, transitionModel, label):
+        out = [self._unpackLabelled(m, label) for m in getattr(transitionModel, 'models', [])]
+        if hasattr(transitionModel, 'hyperParameterNames') and str(transitionModel) == label:
+            out.extend(transitionModel.hyperParameterNames)
+        return out
+
+    def _unpackChangepointNames(self, transitionModel):
+        return self._unpackLabelled(transitionModel, 'Change-point')
+
+    def _unpackBreakpointNames(self, transitionModel):
+        return self._unpackLabelled(transitionModel, 'Serial transition model')
+
+    def _getHyperParameterIndex(self, transitionModel, name):
+        names = list(flatten(self._unpackHyperParameters(transitionModel, values=False)))
+        if name not in names:
+            raise PostProcessingError('Could not find any hyper-parameter with name: {}.'.format(name))
+        return names.index(name)
+
+    def getHyperParameterValue(self, name):
+        return self._unpackAllHyperParameters(values=True)[self._getHyperParameterIndex(self.transitionModel, name)]
+
+    def _checkConsistency(self):
+        if len(self.rawData) == 0:
+            raise ConfigurationError('No data loaded.')
+        if not self.observationModel:
+            raise ConfigurationError('No observation model chosen.')
+        if not self.transitionModel:
+            raise ConfigurationError('No transition model chosen.')
+        names = self._unpackAllHyperParameters(values=False)
+        twice = sorted({n for n in names if names.count(n) > 1})
+        if twice:
+            raise ConfigurationError('Detected duplicate hyper-parameter names: {}.'.format(twice))
+
+    def _formatData(self):
+        seg = self.observationModel.segmentLength
+        self.formattedData = movingWindow(self.rawData, seg)
+        self.formattedTimestamps = self.rawTimestamps[seg - 1:]
+
+    # ---------------------------------------------------------------------------------------- device sweep
+    def _lower(self, hyperRows, timestamps, online=False, model=None):
+        model = self.transitionModel if model is None else model
+        _tm.assign_columns(model)
+        ctx = _tm.LoweringContext(self.observationModel.parameterNames, self.latticeConstant, hyperRows, timestamps,
+                                  online=online)
+        model.lower(ctx, _tm.Window.everything(ctx.B))
+        return ctx
+
+    def _warnZeroNorm(self, backward):
+        if self.fitWarningCounter < 5:
+            print('    ! WARNING: {} distribution contains only zeros, check parameter boundaries!'
+                  .format('Posterior' if backward else 'Forward pass'))
+            print('      Stopping inference process. Setting model evidence to zero.')
+        elif self.fitWarningCounter == 5:
+            print('    ! WARNING: Will omit further warnings about parameter boundaries.')
+        self.fitWarningCounter += 1
+
+    def _fitSingle(self, forwardOnly, evidenceOnly, silent):
+        """One combination of hyper-parameter values: forward filter, backward smoother, means (core.py:330-486)."""
+        eng = self._engine()
+        ses = _Session(self, eng)
+        T, G = ses.T, ses.G
+        values = self._unpackAllHyperParameters()
+        for v in values:
+            if isinstance(v, (Iterable, str)) and not np.isscalar(v):
+                raise ConfigurationError('Study.fit needs scalar hyper-parameter values; use HyperStudy for lists.')
+        ctx = self._lower(np.array([values], dtype=float).reshape(1, len(values)), self.formattedTimestamps)
+        program = _engine.Program(eng, ctx.ops, 1)
+        logE, local = eng.zeros(1), eng.zeros((1, T))
+        alive = eng.zeros(1, dtype=torch.int32)
+        seq = None if evidenceOnly else eng.empty((1, T, G))
+        common = dict(T=T, B=1, data=ses.data, prior=ses.prior, lik_table=ses.likTable, program=program,
+                      reset_base=ses.reset_base() if ctx.usesReset else None, log_evidence=logE,
+                      local_evidence=local, alive=alive, alpha_seq=seq)
+        eng.run('forward', ses.plan, _engine.F_EVIDENCE_ONLY if evidenceOnly else 0, **common)
+        state = int(eng.to_host(alive)[0])
+        if state == 1 and not (forwardOnly or evidenceOnly):
+            eng.run('backward', ses.plan, 0, **common)
+            state = int(eng.to_host(alive)[0])
+        self.localEvidence = eng.to_host(local)[0]
+        self.logEvidence = float(eng.to_host(logE)[0])
+        if not silent and state != 0:
+            print('    + Finished forward pass.')
+            print('    + Log10-evidence: {:.5f}'.format(self.logEvidence / np.log(10)))
+        if state != 1:
+            self._warnZeroNorm(backward=(state == -1))
+            self.logEvidence = -np.inf
+            if not evidenceOnly:
+                self.posteriorSequence = eng.to_host(seq).reshape([T] + self.gridSize)
+            return
+        if evidenceOnly:
+            self.posteriorMeanValues = []
+            return
+        means = eng.empty((len(self.gridSize), T))
+        eng.finalize(ses.plan, seq, T, means, 0)
+        self.posteriorSequence = eng.to_host(seq).reshape([T] + self.gridSize)
+        self.posteriorMeanValues = eng.to_host(means)
+        if not silent:
+            if not forwardOnly:
+                print('    + Finished backward pass.')
+            print('    + Computed mean parameter values.')
+
+    def fit(self, forwardOnly=False, evidenceOnly=False, silent=False):
+        """Sequence of posterior distributions and the model evidence (same contract as core.py:330-343)."""
+        self._checkConsistency()
+        if not silent:
+            print('+ Started new fit:')
+        self._formatData()
+        if not silent:
+            print('    + Formatted data.')
+        self.logEvidence = 0
+        self._fitSingle(forwardOnly, evidenceOnly, silent)
+
+    # -------------------------------------------------------------------------------------------- optimize
+    def optimize(self, parameterList=[], forwardOnly=False, **kwargs):
+        """Maximise the log-evidence over hyper-parameters with SciPy's COBYLA (core.py:488-565); every
+        evaluation is one evidence-only device pass."""
+        from scipy.optimize import minimize
+        self.selectedHyperParameters = [parameterList] if isinstance(parameterList, str) else parameterList
+        print('+ Starting optimization...')
+        self._checkConsistency()
+        if self.selectedHyperParameters:
+            print('  --> Parameter(s) to optimize:', self.selectedHyperParameters)
+        else:
+            print('  --> All model parameters are optimized (except change/break-points).')
+            everything = list(flatten(self._unpackHyperParameters(self.transitionModel)))
+            points = list(flatten(self._unpackChangepointNames(self.transitionModel))) + \
+                list(flatten(self._unpackBreakpointNames(self.transitionModel)))
+            self.selectedHyperParameters = [x for x in everything if x not in points]
+        x0 = self._unpackSelectedHyperParameters()
+        if len(x0) == 0:
+            self.selectedHyperParameters = []
+            raise ConfigurationError('No parameters to optimize. Check parameter names.')
+        result = minimize(self._optimizationStep, x0, method='COBYLA', **kwargs)
+        print('+ Finished optimization.')
+        self._setSelectedHyperParameters(result.x)
+        self.fit(forwardOnly=forwardOnly)
+        self.selectedHyperParameters = []
+
+    def _optimizationStep(self, x):
+        self._setSelectedHyperParameters(x)
+        self.fit(evidenceOnly=True, silent=True)
+        print('    + Log10-evidence: {:.5f}'.format(self.logEvidence / np.log(10)), '- Parameter values:', x)
+        return -self.logEvidence
+
+    # ------------------------------------------------------------------------------------------- accessors
+    def _parameterIndex(self, name):
+        names = list(self.observationModel.parameterNames)
+        if name not in names:
+            raise PostProcessingError('Wrong parameter name. Available options: {0}'.format(names))
+        return names.index(name)
+
+    def _hasPosterior(self):
+        return isinstance(self.posteriorSequence, np.ndarray) and self.posteriorSequence.size > 0
+
+    def getParameterMeanValues(self, name):
+        return self.posteriorMeanValues[self._parameterIndex(name)]
+
+    def getParameterDistribution(self, t, name, plot=False, density=True, **kwargs):
+        """Marginal distribution of one parameter at time stamp `t` (or 'avg')."""
+        if not self._hasPosterior():
+            raise PostProcessingError('Cannot plot posterior sequence as it has not yet been computed. '
+                                      'Run complete fit.')
+        if isinstance(t, str) and t == 'avg':
+            dist = np.sum(self.posteriorSequence, axis=0) / len(self.posteriorSequence)
+        else:
+            stamps = list(self.formattedTimestamps)
+            if t not in stamps:
+                raise PostProcessingError('Supplied time ({}) does not exist in data or is out of range.'.format(t))
+            dist = self.posteriorSequence[stamps.index(t)]
+        axis = self._parameterIndex(name)
+        others = tuple(a for a in range(dist.ndim) if a != axis)
+        marginal = np.sum(dist, axis=others) if others else dist.copy()
+        if density:
+            marginal = marginal / self.latticeConstant[axis]
+        return self.marginalGrid[axis], marginal
+
+    def getPD(self, t, name, plot=False, density=True, **kwargs):
+        return self.getParameterDistribution(t, name, plot=plot, density=density, **kwargs)
+
+    def getParameterDistributions(self, name, plot=False, density=True, **kwargs):
+        """Time series of marginal distributions of one parameter: array [T, n_axis]."""
+        if not self._hasPosterior():
+            raise PostProcessingError('Cannot plot posterior sequence as it has not yet been computed. '
+                                      'Run complete fit.')
+        axis = self._parameterIndex(name)
+        seq = np.asarray(self.posteriorSequence)
+        others = tuple(a + 1 for a in range(seq.ndim - 1) if a != axis)
+        marginal = np.sum(seq, axis=others) if others else seq.copy()
+        if density:
+            marginal = marginal / self.latticeConstant[axis]
+        return self.marginalGrid[axis], marginal
+
+    def getPDs(self, name, plot=False, density=True, **kwargs):
+        return self.getParameterDistributions(name, plot=plot, density=density, **kwargs)
+
+
+class HyperStudy(Study):
+    """Sweep over a grid of hyper-parameter values with evidence-weighted model averaging
+    (reference: core.py:1118-1495).  The sweep is the batch axis of the device kernels and, under
+    torch.distributed, is sharded across ranks/GPUs (bayesloop_b200/distributed.py)."""
+
+    def __init__(self, silent=False, engine=None):
+        super(HyperStudy, self).__init__(silent=silent, engine=engine)
+        self.hyperGrid = []
+        self.hyperGridValues = []
+        self.hyperGridConstant = []
+        self.flatHyperParameters = []
+        self.flatHyperParameterNames = []
+        self.flatHyperPriors = []
+        self.flatHyperPriorValues = []
+        self.hyperParameterDistribution = None
+        self.averagePosteriorSequence = None
+        self.logEvidenceList = []
+        self.localEvidenceList = []
+        self.sweepStats = {}
+        if not silent:
+            print('  --> Hyper-study')
+
+    def _unpackHyperPriors(self, transitionModel):
+        out = [self._unpackHyperPriors(m) for m in getattr(transitionModel, 'models', [])]
+        if hasattr(transitionModel, 'prior'):
+            if len(getattr(transitionModel, 'hyperParameterNames', [])) > 0 or str(transitionModel) == 'Break-point':
+                out.append(transitionModel.prior)
+        return out
+
+    def _unpackAllHyperPriors(self):
+        return list(flatten(self._unpackHyperPriors(self.transitionModel)))
+
+    def _createHyperGrid(self, silent=False):
+        """Cartesian grid of hyper-parameter values, its lattice constants and the joint hyper-prior
+        (semantics of core.py:1142-1245)."""
+        self.flatHyperParameters = self._unpackAllHyperParameters()
+        self.flatHyperParameterNames = self._unpackAllHyperParameters(values=False)
+        self.flatHyperPriors = self._unpackAllHyperPriors()
+        for i, v in enumerate(self.flatHyperParameters):
+            if isinstance(v, str) and v == 'all':
+                self.flatHyperParameters[i] = self.formattedTimestamps[:-1]
+
+        if len(self.flatHyperParameterNames) > 0:
+            mesh = np.meshgrid(*self.flatHyperParameters, indexing='ij')
+            self.hyperGridValues = np.array([m.ravel() for m in mesh]).T
+        else:
+            self.hyperGridValues = np.array([])
+
+        constants = []
+        for values in self.flatHyperParameters:
+            step = 1
+            if isinstance(values, Iterable) and len(values) > 1:
+                arr = np.array(values)
+                if is_regular(arr, tol=1e-10) and not np.any(np.abs(np.diff(arr, 2)) >= 1e-10):
+                    step = np.abs(arr[1] - arr[0])
+            constants.append(step)
+        self.hyperGridConstant = np.array(constants)
+
+        perAxis, labels = [], []
+        for prior, values, const, name in zip(self.flatHyperPriors, self.flatHyperParameters,
+                                              self.hyperGridConstant, self.flatHyperParameterNames):
+            if prior is None:
+                p = np.ones_like(values, dtype=float)
+                p = p / np.sum(p) / const
+                labels.append('uniform')
+            elif callable(prior):
+                try:
+                    p = np.array([prior(v) for v in values])
+                    total = np.sum(p)
+                    p = p / total / const
+                except Exception:
+                    raise ConfigurationError('Failed to set hyper-prior for "{}" from function "{}".'
+                                             .format(name, getattr(prior, '__name__', prior)))
+                labels.append(prior.__name__ + (' (re-normalized)' if total != 1. else ''))
+            elif isinstance(prior, Iterable):
+                if len(prior) != len(values):
+                    raise ConfigurationError('Failed to set hyper-prior for "{}" from list/array.'.format(name))
+                total = np.sum(prior)
+                if isinstance(prior, np.ndarray) and prior.dtype.kind == 'f':
+                    prior /= total  # in place, like the reference (core.py:1210-1213)
+                    prior /= const
+                    p = prior
+                else:
+                    p = np.array(prior, dtype=float) / total / const
+                labels.append('list/array' + (' (re-normalized)' if total != 1. else ''))
+            else:  # SymPy random variable: density evaluated as is
+                import sympy.abc
+                if len(_free_symbols(prior)) > 0:
+                    raise ConfigurationError('Hyper-prior for "{}" must not contain free parameters.'.format(name))
+                p = _sympy_density(prior, sympy.abc.x)(values)
+                labels.append('sympy')
+            perAxis.append(p)
+
+        if len(self.flatHyperParameterNames) > 0:
+            mesh = np.meshgrid(*perAxis, indexing='ij')
+            self.flatHyperPriorValues = np.prod(np.array([m.ravel() for m in mesh]).T, axis=1)
+            if not silent and len(self.hyperGridValues) > 1:
+                print('+ Set hyper-prior(s): {}'.format(labels))
+        else:
+            self.flatHyperPriorValues = np.array([1])
+
+    def _sweep(self, forwardOnly, evidenceOnly, exclude=None):
+        """Run all rows of self.hyperGridValues on the device, in waves sized to HBM, sharded across ranks.
+        Returns host arrays (logE[B], localEvidence[T]) and device tensors (avg [T,G] normalised, means)."""
+        from . import distributed as dist
+        eng = self._engine()
+        ses = _Session(self, eng)
+        T, G = ses.T, ses.G
+        Ball = len(self.hyperGridValues)
+        lo, hi = dist.shard_bounds(Ball)
+        B = hi - lo
+        hyper = np.asarray(self.hyperGridValues, dtype=float)[lo:hi]
+        hp = np.asarray(self.flatHyperPriorValues, dtype=float)[lo:hi]
+        ctx = self._lower(hyper, self.formattedTimestamps)
+        program = _engine.Program(eng, ctx.ops, B)
+        resetBase = ses.reset_base() if ctx.usesReset else None
+        logE, local = eng.zeros(max(B, 1)), eng.zeros((max(B, 1), T))
+        alive = eng.zeros(max(B, 1), dtype=torch.int32)
+        avg = None if evidenceOnly else eng.zeros((T, G))
+
+        if evidenceOnly:
+            wave = max(B, 1)
+            buf = None
+        else:
+            budget = int(eng.free_bytes() * 0.80) - 2 * T * G * 8
+            wave = int(max(1, min(B, budget // max(1, T * G * 8))))
+            buf = eng.empty((wave, T, G)) if B > 0 else None
+        with np.errstate(divide='ignore'):
+            logHp = np.log(hp)
+        shift = -np.inf
+        logEHost = np.zeros(B)
+        waves = 0
+        for w0 in range(0, B, wave):
+            w1 = min(B, w0 + wave)
+            nb = w1 - w0
+            common = dict(T=T, B=nb, data=ses.data, prior=ses.prior, lik_table=ses.likTable, program=program, lo=w0,
+                          reset_base=resetBase, log_evidence=logE[w0:w1], local_evidence=local[w0:w1],
+                          alive=alive[w0:w1], alpha_seq=buf)
+            eng.run('forward', ses.plan, _engine.F_EVIDENCE_ONLY if evidenceOnly else 0, **common)
+            waves += 1
+            if evidenceOnly:
+                logEHost[w0:w1] = eng.to_host(logE[w0:w1])
+                continue
+            le = eng.to_host(logE[w0:w1])  # the evidences fix the averaging weights of this wave
+            logEHost[w0:w1] = le
+            lw = le + logHp[w0:w1]
+            if exclude is not None:
+                lw = np.where(exclude[lo + w0:lo + w1], -np.inf, lw)
+            finite = np.isfinite(lw)
+            if finite.any():
+                top = float(np.max(lw[finite]))
+                if top > shift:
+                    if np.isfinite(shift):
+                        eng.scale(ses.plan, avg, T * G, math.exp(shift - top))
+                    shift = top
+            weights = eng.to_device(np.where(finite, lw - (shift if np.isfinite(shift) else 0.), -np.inf))
+            if forwardOnly:
+                eng.run('accumulate', ses.plan, 0, log_weight=weights, avg=avg, **common)
+            else:
+                eng.run('backward', ses.plan, _engine.F_ACCUMULATE, log_weight=weights, avg=avg, **common)
+        aliveHost = eng.to_host(alive)[:B]
+        logEHost = np.where(aliveHost == 1, logEHost, -np.inf)
+
+        # averaged local evidence: sum_b localEvidence_b * hyperprior_b (core.py:1410)
+        part = eng.zeros(T)
+        if B > 0:
+            eng.mix(ses.plan, local, eng.to_device(hp), B, T, part)
+        logEAll, aliveAll = dist.gather_rows(eng, logEHost, aliveHost, Ball)
+        localEv = dist.reduce_sum(eng, part)
+        died = aliveAll == -1
+        if exclude is not None:
+            died = died & ~exclude
+        if (not evidenceOnly) and died.any():
+            # A combo whose backward pass hit a zero norm is dropped from the average as a whole
+            # (core.py:1358): redo the sweep with its weight forced to zero.
+            return self._sweep(forwardOnly, evidenceOnly, exclude=(died if exclude is None else (exclude | died)))
+        means = None
+        if not evidenceOnly:
+            shift = dist.rebase_and_reduce(eng, ses.plan, avg, shift, T * G)
+            means = eng.empty((len(self.gridSize), T))
+            eng.finalize(ses.plan, avg, T, means, _engine.F_NORMALIZE_ROWS)
+        self.sweepStats = dict(waves=waves, wave=wave, shard=(lo, hi), launches=eng.launch_count())
+        return eng, logEAll, aliveAll, eng.to_host(localEv), avg, means
+
+    def fit(self, forwardOnly=False, evidenceOnly=False, silent=False, nJobs=1, customHyperGrid=False):
+        """Fit every combination of hyper-parameter values and average the models by their evidence (contract of
+        core.py:1247-1264).  `nJobs` is accepted for compatibility; device parallelism comes from the batch
+        kernels and from torch.distributed ranks (one per GPU), not from a process pool."""
+        self.fitWarningCounter = 0
+        self._formatData()
+        if not customHyperGrid:
+            self._createHyperGrid(silent=silent)
+            points = list(flatten(self._unpackChangepointNames(self.transitionModel))) + \
+                list(flatten(self._unpackBreakpointNames(self.transitionModel)))
+            if len(points) > 1:
+                cols = [self.flatHyperParameterNames.index(p) for p in points]
+                sub = np.sort(np.asarray(self.hyperGridValues)[:, cols], axis=1)
+                if np.any(np.diff(sub, axis=1) == 0):
+                    raise ConfigurationError('Detected multiple change-/break-points with identical values and/or '
+                                             'overlapping value intervals. Use "ChangepointStudy" instead of '
+                                             '"HyperStudy" for such cases.')
+        self._checkConsistency()
+        self.logEvidenceList = []
+        self.localEvidenceList = []
+
+        if len(self.hyperGridValues) <= 1:
+            if not silent:
+                if len(self.hyperGridValues) == 1:
+                    print('+ Only one combination of hyper-parameter values, switching to standard fit method.')
+                else:
+                    print('+ Transition model contains no hyper-parameters, switching to standard fit method.')
+            if not evidenceOnly:
+                self.averagePosteriorSequence = None
+            if len(self.hyperGridValues) == 1:  # single-element lists -> scalars for the duration of the fit
+                self._setAllHyperParameters(list(self.hyperGridValues[0]))
+                try:
+                    Study.fit(self, forwardOnly=forwardOnly, evidenceOnly=evidenceOnly, silent=silent)
+                finally:
+                    self._setAllHyperParameters(self.flatHyperParameters)
+            else:
+                Study.fit(self, forwardOnly=forwardOnly, evidenceOnly=evidenceOnly, silent=silent)
+            return
+
+        if not silent:
+            print('+ Started new fit.')
+            print('    + {} analyses to run.'.format(len(self.hyperGridValues)))
+        eng, logE, alive, localEv, avg, means = self._sweep(forwardOnly, evidenceOnly)
+        for state in alive[alive != 1][:6]:
+            self._warnZeroNorm(backward=(state == -1))
+        self.logEvidenceList = list(logE)
+        T = len(self.formattedData)
+        if not evidenceOnly:
+            self.averagePosteriorSequence = eng.to_host(avg).reshape([T] + self.gridSize)
+            self.posteriorSequence = self.averagePosteriorSequence
+            if not silent:
+                print('    + Computed average posterior sequence')
+
+        # hyper-parameter distribution and evidence of the average model (core.py:1391-1410)
+        with np.errstate(divide='ignore'):
+            logDist = logE + np.log(self.flatHyperPriorValues) + np.sum(np.log(self.hyperGridConstant))
+        top = np.amax(logDist)
+        dist = np.exp(logDist - top)
+        self.hyperParameterDistribution = dist / np.sum(dist) / np.prod(self.hyperGridConstant)
+        self.logEvidence = float(top + np.log(np.sum(dist))) if np.isfinite(top) else -np.inf
+        self.localEvidence = localEv
+        if not silent:
+            print('    + Computed hyper-parameter distribution')
+            print('    + Log10-evidence of average model: {:.5f}'.format(self.logEvidence / np.log(10)))
+            print('    + Computed local evidence of average model')
+        if not evidenceOnly:
+            self.posteriorMeanValues = eng.to_host(means)
+            if not silent:
+                print('    + Computed mean parameter values.')
+        self.localEvidenceList = []
+        self._setAllHyperParameters(self.flatHyperParameters)
+        if not silent:
+            print('+ Finished fit.')
+
+    def optimize(self, *args, **kwargs):
+        raise NotImplementedError('HyperStudy object has no optimizing method.')
+
+    # ------------------------------------------------------------------------------------------- accessors
+    def _hyperShape(self):
+        return [len(x) if isinstance(x, Iterable) else 1 for x in self.flatHyperParameters]
+
+    def getHyperParameterDistribution(self, name, plot=False, **kwargs):
+        """Marginal probability of one hyper-parameter over its value grid."""
+        if len(self.hyperGridValues) < 2:
+            raise PostProcessingError('At least two combinations of hyper-parameter values need to be fitted to '
+                                      'evaluate a hyper-parameter distribution. Check transition model.')
+        axis = self._getHyperParameterIndex(self.transitionModel, name)
+        cube = np.asarray(self.hyperParameterDistribution).reshape(self._hyperShape(), order='C')
+        others = tuple(a for a in range(cube.ndim) if a != axis)
+        marginal = (np.sum(cube, axis=others) if others else cube) * np.prod(self.hyperGridConstant)
+        return self.flatHyperParameters[axis], marginal
+
+    def getHPD(self, name, plot=False, **kwargs):
+        return self.getHyperParameterDistribution(name, plot=plot, **kwargs)
+
+    def getJointHyperParameterDistribution(self, names, plot=False, figure=None, subplot=111, **kwargs):
+        """Joint probability of two hyper-parameters (rows follow names[0], columns names[1])."""
+        if len(self.hyperGridValues) < 2:
+            raise PostProcessingError('At least two combinations of hyper-parameter values need to be fitted to '
+                                      'evaluate a hyper-parameter distribution. Check transition model.')
+        if not isinstance(names, Iterable) or len(names) != 2:
+            raise PostProcessingError('A list of exactly two hyper-parameters has to be provided.')
+        a, b = [self._getHyperParameterIndex(self.transitionModel, n) for n in names]
+        cube = np.asarray(self.hyperParameterDistribution).reshape(self._hyperShape(), order='C')
+        others = tuple(ax for ax in range(cube.ndim) if ax not in (a, b))
+        joint = (np.sum(cube, axis=others) if others else cube) * np.prod(self.hyperGridConstant)
+        if a > b:
+            joint = joint.T
+        return self.flatHyperParameters[a], self.flatHyperParameters[b], joint
+
+    def getJHPD(self, names, plot=False, figure=None, subplot=111, **kwargs):
+        return self.getJointHyperParameterDistribution(names, plot=plot, figure=figure, subplot=subplot, **kwargs)
+
+
+class ChangepointStudy(HyperStudy):
+    """Sweep over all ORDERED combinations of change-/break-point times (reference: core.py:1743-1930)."""
+
+    def __init__(self, silent=False, engine=None):
+        super(ChangepointStudy, self).__init__(silent=silent, engine=engine)
+        self.allHyperGridValues = []
+        self.allHyperPriorValues = []
+        self.mask = []
+        self.userDefinedGrid = False
+        self.hyperGridBackup = []
+        if not silent:
+            print('  --> Change-point analysis')
+
+    def _unpackSerialTransitionModels(self, transitionModel):
+        out = [self._unpackSerialTransitionModels(m) for m in getattr(transitionModel, 'models', [])]
+        if hasattr(transitionModel, 'hyperParameterNames') and str(transitionModel) == 'Serial transition model':
+            out.append(transitionModel)
+        return out
+
+    def fit(self, forwardOnly=False, evidenceOnly=False, silent=False, nJobs=1):
+        self._formatData()
+        if len(list(flatten(self._unpackSerialTransitionModels(self.transitionModel)))) > 1:
+            raise NotImplementedError('Multiple instances of SerialTransition models are currently not supported by '
+                                      'ChangepointStudy.')
+        changepoints = list(flatten(self._unpackChangepointNames(self.transitionModel)))
+        breakpoints = list(flatten(self._unpackBreakpointNames(self.transitionModel)))
+        if changepoints and breakpoints:
+            raise NotImplementedError('Detected both change-points (Changepoint transition model) and break-points '
+                                      '(SerialTransitionModel). Currently, only one type is supported in a single '
+                                      'transition model.')
+        if not changepoints and not breakpoints:
+            raise ConfigurationError('No change-points or break-points detected in transition model. Check transition '
+                                     'model.')
+        self.flatHyperParameters = self._unpackAllHyperParameters()
+        self.flatHyperParameterNames = self._unpackAllHyperParameters(values=False)
+        points = changepoints if changepoints else breakpoints
+        if not silent:
+            print('+ Detected {} {}-point(s) in transition model: {}'
+                  .format(len(points), 'change' if changepoints else 'break', points))
+
+        self._createHyperGrid(silent=silent)
+        self.allHyperGridValues = self.hyperGridValues[:]
+        self.allHyperPriorValues = self.flatHyperPriorValues[:]
+        cols = np.isin(np.array(self.flatHyperParameterNames), points)
+        times = self.allHyperGridValues[:, cols]
+        # keep strictly increasing tuples only (core.py:1826-1834), then restore the prior mass of the full grid
+        self.mask = np.all(times[:, :-1] < times[:, 1:], axis=1) if times.shape[1] > 1 else \
+            np.ones(len(times), dtype=bool)
+        self.hyperGridValues = self.allHyperGridValues[self.mask]
+        self.flatHyperPriorValues = self.allHyperPriorValues[self.mask]
+        self.flatHyperPriorValues = self.flatHyperPriorValues * (np.sum(self.allHyperPriorValues) /
+                                                                 np.sum(self.allHyperPriorValues[self.mask]))
+        HyperStudy.fit(self, forwardOnly=forwardOnly, evidenceOnly=evidenceOnly, silent=silent, nJobs=nJobs,
+                       customHyperGrid=True)
+        full = np.zeros(len(self.allHyperGridValues))
+        full[self.mask] = self.hyperParameterDistribution
+        self.hyperParameterDistribution = full
+        full = np.zeros(len(self.allHyperPriorValues))
+        full[self.mask] = self.flatHyperPriorValues
+        self.flatHyperPriorValues = full
+
+    def getDurationDistribution(self, names, plot=False, **kwargs):
+        """Distribution of the time between two change-/break-points (reference: core.py:1875-1924)."""
+        if not isinstance(names, Iterable) or len(names) != 2:
+            raise PostProcessingError('A list of exactly two hyper-parameters has to be provided.')
+        a, b = sorted(self._getHyperParameterIndex(self.transitionModel, n) for n in names)
+        allValues = np.asarray(self.allHyperGridValues)
+        delta = allValues[:, b] - allValues[:, a]
+        keep = delta > 0
+        duration = np.unique(np.asarray(self.hyperGridValues)[:, b] - np.asarray(self.hyperGridValues)[:, a])
+        idx = np.searchsorted(duration.round(10), delta[keep].round(10))
+        out = np.zeros(len(duration))
+        np.add.at(out, idx, np.asarray(self.hyperParameterDistribution)[keep])
+        return duration, out / np.sum(out)
+
+    def getDD(self, names, plot=False, **kwargs):
+        return self.getDurationDistribution(names, plot=plot, **kwargs)
+
+
+class OnlineStudy(HyperStudy):
+    """Streaming forward filter over many transition-model hypotheses (reference: core.py:1933-2226).
+
+    All hypotheses -- every hyper-parameter combination of every added transition model -- live in ONE device
+    batch: their programs are concatenated and masked per hypothesis, the per-hypothesis posteriors stay resident
+    in HBM between `step` calls, and each `step` is one batched kernel launch plus O(#hypotheses) host arithmetic.
+    """
+
+    def __init__(self, storeHistory=False, silent=False, engine=None):
+        super(OnlineStudy, self).__init__(silent=silent, engine=engine)
+        self.firstStep = True
+        self.transitionModels = []
+        self.transitionModelNames = []
+        self.tmCount = None
+        self.tmCounts = []
+        self.hyperParameterValues = []
+        self.allFlatHyperParameterValues = []
+        self.hyperParameterNames = []
+        self.hyperGridConstants = []
+        self.logEvidenceList = None
+        self.hyperLogEvidenceList = None
+        self.hyperPrior = []
+        self.hyperPriorValues = []
+        self.transitionModelPrior = None
+        self.hyperParameterDistribution = None
+        self.transitionModelDistribution = None
+        self.localTransitionModelDistribution = None
+        self.storeHistory = storeHistory
+        self.posteriorMeanValues = []
+        self.posteriorSequence = []
+        self.hyperParameterSequence = []
+        self.transitionModelSequence = []
+        self.localTransitionModelSequence = []
+        self._dev = None
+        if not silent:
+            print('  --> Online study')
+
+    def addTransitionModel(self, name, transitionModel):
+        self.setTransitionModel(transitionModel, silent=True)
+        self._createHyperGrid(silent=True)
+        self.transitionModels.append(transitionModel)
+        self.transitionModelNames.append(name)
+        self.hyperParameterValues.append(self.hyperGridValues[:])
+        self.allFlatHyperParameterValues.append(self.flatHyperParameters)
+        self.hyperParameterNames.append(self.flatHyperParameterNames[:])
+        self.hyperGridConstants.append(self.hyperGridConstant[:])
+        self.hyperPrior.append(self.flatHyperPriors[:])
+        self.hyperPriorValues.append(self.flatHyperPriorValues[:])
+        self.tmCounts = [len(h) if len(h) > 0 else 1 for h in self.hyperParameterValues]
+        self.tmCount = int(np.sum(self.tmCounts))
+        if len(self.hyperGridValues) > 0:
+            print('+ Added transition model: {} ({} combination(s) of the following hyper-parameters: {})'
+                  .format(name, len(self.hyperGridValues), self.hyperParameterNames[-1]))
+        else:
+            print('+ Added transition model: {} (no hyper-parameters)'.format(name))
+
+    def addTM(self, name, transitionModel):
+        self.addTransitionModel(name, transitionModel)
+
+    def add(self, name, transitionModel):
+        self.addTransitionModel(name, transitionModel)
+
+    def setTransitionModelPrior(self, transitionModelPrior, silent=False):
+        if not (isinstance(transitionModelPrior, Iterable) and
+                len(transitionModelPrior) == len(self.transitionModels)):
+            raise ConfigurationError('Length of transition model prior ({}) does not fit number of transition models '
+                                     '({})'.format(len(transitionModelPrior), len(self.transitionModels)))
+        self.transitionModelPrior = np.array(transitionModelPrior, dtype=float)
+        if not np.sum(transitionModelPrior) == 1.:
+            print('+ WARNING: Transition model prior does not sum up to one. Will re-normalize.')
+            self.transitionModelPrior /= np.sum(self.transitionModelPrior)
+        if not silent:
+            print('+ Set custom transition model prior.')
+
+    def _setupDevice(self):
+        """Concatenate the programs of all transition models; hypothesis h only sees the operators of its own
+        model (all other windows are empty).  t = -1 is what the reference hands to the models (core.py:2167)."""
+        eng = self._engine()
+        om = self.observationModel
+        seg = om.segmentLength
+        first = np.asarray(self.rawData[-seg:], dtype=float)
+        nCols = 1 if first.ndim == 1 else int(first.shape[1])
+        kind = getattr(om, 'deviceKind', KIND_TABLE)
+        if type(om).pdf is not ObservationModel.pdf:
+            kind = KIND_TABLE
+        plan = eng.plan(self.marginalGrid, self.latticeConstant, kind, seg, nCols)
+        H = self.tmCount
+        ops, usesReset, row = [], False, 0
+        for tm, rows, count in zip(self.transitionModels, self.hyperParameterValues, self.tmCounts):
+            hyper = np.asarray(rows, dtype=float).reshape(count, -1) if len(rows) > 0 else np.zeros((1, 0))
+            self.setTransitionModel(tm, silent=True)
+            ctx = self._lower(hyper, np.array([-1.]), online=True, model=tm)
+            usesReset |= ctx.usesReset
+            for op in ctx.ops:
+                full = dict(kind=op['kind'], axis=op['axis'], param=np.zeros(H), radius=np.zeros(H, dtype=np.int32),
+                            window=np.zeros((H, 4), dtype=np.int32))
+                full['param'][row:row + count] = op['param']
+                full['radius'][row:row + count] = op['radius']
+                full['window'][row:row + count] = op['window']
+                ops.append(full)
+            row += count
+        G = int(np.prod(self.gridSize))
+        dev = dict(eng=eng, plan=plan, kind=kind, nCols=nCols, G=G, H=H,
+                   program=_engine.Program(eng, ops, H), state=eng.empty((H, G)), step=eng.zeros(H),
+                   alive=eng.zeros(H, dtype=torch.int32), mixed=eng.empty(G), tmPost=None,
+                   prior=eng.to_device(np.asarray(self._computePrior(silent=False), dtype=float).reshape(-1)),
+                   resetBase=None)
+        if usesReset:
+            dev['resetBase'] = _Session.reset_base(_ResetShim(self, eng))
+        self._dev = dev
+
+    def step(self, dataPoint):
+        """Include one new data point (contract of core.py:2062-2226)."""
+        if self.tmCount is None and self.transitionModel is None:
+            raise ConfigurationError('No transition model set or added.')
+        if self.tmCount is None:
+            self.addTransitionModel('transition model', self.transitionModel)
+        if not isinstance(dataPoint, list):
+            dataPoint = [dataPoint]
+        if len(self.rawData) == 0:
+            print('+ Start model fit')
+            names = list(flatten(self.hyperParameterNames))
+            if len(names) != len(set(names)):
+                raise ConfigurationError('Detected duplicate hyper-parameter names. Choose unique identifiers.')
+            self.rawData = np.array(dataPoint)
+            Study._checkConsistency(self)
+            self.rawTimestamps = np.array([0])
+            self.formattedTimestamps = []
+        else:
+            self.rawData = np.append(self.rawData, np.array(dataPoint), axis=0)
+            self.rawTimestamps = np.append(self.rawTimestamps, self.rawTimestamps[-1] + 1)
+        seg = self.observationModel.segmentLength
+        if len(self.rawData) < seg:
+            print('+ Not enough data points to start analysis. Will wait for more data.')
+            return
+        self.formattedTimestamps.append(self.rawTimestamps[-1])
+
+        nTM = len(self.transitionModels)
+        if self.firstStep:
+            self._setupDevice()
+            if self.transitionModelPrior is None:
+                self.transitionModelPrior = np.ones(nTM) / nTM
+                if nTM > 1:
+                    print('    + Set flat transition model prior.')
+            self.logEvidenceList = [np.zeros(c) for c in self.tmCounts]
+            self.hyperLogEvidenceList = np.zeros(nTM)
+            self.hyperParameterDistribution = [np.zeros(c) for c in self.tmCounts]
+            self.transitionModelDistribution = np.zeros(nTM)
+            self.localTransitionModelDistribution = np.zeros(nTM)
+        dev = self._dev
+        eng, plan, H, G = dev['eng'], dev['plan'], dev['H'], dev['G']
+
+        segment = np.asarray(self.rawData[-seg:], dtype=float).reshape(seg, dev['nCols'])
+        likTable = None
+        if dev['kind'] == KIND_TABLE:
+            seg1 = self.rawData[-seg:]
+            likTable = eng.to_device(np.asarray(self.observationModel.processedPdf(self.grid, seg1),
+                                                dtype=float).reshape(1, G))
+        flags = _engine.F_EVIDENCE_ONLY | _engine.F_SAVE_STATE
+        if not self.firstStep:
+            flags |= _engine.F_INIT_STATE | _engine.F_TRANSITION_FIRST
+        eng.run('forward', plan, flags, T=1, B=H, data=eng.to_device(segment), prior=dev['prior'],
+                reset_base=dev['resetBase'], lik_table=likTable, program=dev['program'], init_state=dev['state'],
+                log_evidence=dev['step'], alive=dev['alive'], final_state=dev['state'])
+        inc = eng.to_host(dev['step'])  # log n_i per hypothesis (+ log prod(latticeConstant) on the first step)
+
+        # O(H) bookkeeping of core.py:2171-2215
+        weights = np.zeros(H)
+        row = 0
+        for i, count in enumerate(self.tmCounts):
+            self.logEvidenceList[i] = self.logEvidenceList[i] + inc[row:row + count]
+            with np.errstate(divide='ignore'):
+                logPost = self.logEvidenceList[i] + np.log(self.hyperPriorValues[i])
+            old = self.hyperLogEvidenceList[i]
+            top = np.amax(logPost)
+            self.hyperLogEvidenceList[i] = top + np.log(np.sum(np.exp(logPost - top)))
+            self.transitionModelDistribution[i] = self.hyperLogEvidenceList[i]
+            self.localTransitionModelDistribution[i] = self.hyperLogEvidenceList[i] - old + \
+                np.log(self.transitionModelPrior[i])
+            hpd = np.exp(logPost - top)
+            hpd /= np.sum(hpd)
+            if len(self.hyperGridConstants[i]) > 0:
+                hpd /= np.prod(self.hyperGridConstants[i])
+            self.hyperParameterDistribution[i] = hpd
+            weights[row:row + count] = hpd * np.prod(self.hyperGridConstants[i])
+            row += count
+        for attr in ('transitionModelDistribution', 'localTransitionModelDistribution'):
+            d = getattr(self, attr)
+            d = np.exp(d - np.amax(d))
+            setattr(self, attr, d / np.sum(d))
+        self.logEvidence = float(_logsumexp(self.hyperLogEvidenceList + np.log(self.transitionModelPrior)))
+
+        # marginalisation over hyper-parameters and transition models: one weighted row-sum on the device
+        row = 0
+        for i, count in enumerate(self.tmCounts):
+            weights[row:row + count] *= self.transitionModelDistribution[i]
+            row += count
+        dev['weights'] = weights
+        dev['mixedValid'] = False
+        if self.storeHistory:
+            post = self.marginalizedPosterior
+            self.posteriorMeanValues.append(np.array([np.sum(post * g) for g in self.grid]))
+            self.posteriorSequence.append(post.copy())
+            self.hyperParameterSequence.append([h.copy() for h in self.hyperParameterDistribution])
+            self.transitionModelSequence.append(self.transitionModelDistribution.copy())
+            self.localTransitionModelSequence.append(self.localTransitionModelDistribution.copy())
+        self.firstStep = False
+
+    # device-resident results, copied to the host when somebody looks at them
+    @property
+    def marginalizedPosterior(self):
+        dev = self._dev
+        if dev is None:
+            return None
+        if not dev.get('mixedValid'):
+            eng = dev['eng']
+            eng.mix(dev['plan'], dev['state'], eng.to_device(dev['weights']), dev['H'], dev['G'], dev['mixed'])
+            dev['mixedHost'] = eng.to_host(dev['mixed']).reshape(self.gridSize)
+            dev['mixedValid'] = True
+        return dev['mixedHost']
+
+    @marginalizedPosterior.setter
+    def marginalizedPosterior(self, value):
+        pass
+
+    @property
+    def parameterPosterior(self):
+        dev = self._dev
+        if dev is None:
+            return None
+        flat = dev['eng'].to_host(dev['state'])
+        out, row = [], 0
+        for count in self.tmCounts:
+            out.append(flat[row:row + count].reshape([count] + self.gridSize))
+            row += count
+        return out
+
+    @parameterPosterior.setter
+    def parameterPosterior(self, value):
+        pass
+
+    @property
+    def transitionModelPosterior(self):
+        posts = self.parameterPosterior
+        if posts is None:
+            return None
+        out = np.zeros([len(posts)] + self.gridSize)
+        for i, (p, hpd) in enumerate(zip(posts, self.hyperParameterDistribution)):
+            w = (hpd * np.prod(self.hyperGridConstants[i])).reshape([-1] + [1] * len(self.gridSize))
+            out[i] = np.sum(p * w, axis=0)
+        return out
+
+    @transitionModelPosterior.setter
+    def transitionModelPosterior(self, value):
+        pass
+
+    def fit(self, *args, **kwargs):
+        raise NotImplementedError('OnlineStudy object has no "fit" method. Use "step" instead.')
+
+    # ------------------------------------------------------------------------------------------- accessors
+    def getCurrentParameterDistribution(self, name, plot=False, density=True, **kwargs):
+        axis = self._parameterIndex(name)
+        post = self.marginalizedPosterior
+        others = tuple(a for a in range(post.ndim) if a != axis)
+        marginal = np.sum(post, axis=others) if others else post.copy()
+        if density:
+            marginal = marginal / self.latticeConstant[axis]
+        return self.marginalGrid[axis], marginal
+
+    def getCurrentTransitionModelDistribution(self, local=False, plot=False, **kwargs):
+        dist = self.localTransitionModelDistribution if local else self.transitionModelDistribution
+        return self.transitionModelNames, dist
+
+    def getCurrentHyperParameterDistribution(self, name, plot=False, **kwargs):
+        for i, names in enumerate(self.hyperParameterNames):
+            if name in names:
+                axis = list(names).index(name)
+                shape = [len(x) if isinstance(x, Iterable) else 1 for x in self.allFlatHyperParameterValues[i]]
+                cube = np.asarray(self.hyperParameterDistribution[i]).reshape(shape, order='C')
+                others = tuple(a for a in range(cube.ndim) if a != axis)
+                marginal = (np.sum(cube, axis=others) if others else cube) * np.prod(self.hyperGridConstants[i])
+                return self.allFlatHyperParameterValues[i][axis], marginal
+        raise PostProcessingError('Could not find any hyper-parameter named {}.'.format(name))
+
+
+class _ResetShim:
+    """Minimal stand-in so OnlineStudy can reuse _Session.reset_base without opening a full session."""
+
+    def __init__(self, study, eng):
+        self._study, self.eng, self.resetBase = study, eng, None
+
+
+def _logsumexp(x):
+    x = np.asarray(x, dtype=float)
+    top = np.amax(x)
+    if not np.isfinite(top):
+        return top
+    return top + np.log(np.sum(np.exp(x - top)))

@@ -1,0 +1,261 @@
+"""ctypes binding of the C ABI in include/blgrid.h.
+
+The product engine is `bayesloop_b200/csrc/libblgrid.so` (hand-written sm_100a CUDA kernels) driving `cuda`
+tensors.  There is NO CPU fallback: if the shared library or a CUDA device is missing, `default_engine()` raises.
+PyTorch is used for device memory, streams and torch.distributed only -- every kernel launched on the hot path
+comes from libblgrid.so.
+
+`Engine(lib_path, device)` is also the seam the test-suite uses to check the host-side logic of this package on a
+machine without a GPU: tests/ build an Engine around the CPU oracle (oracle/libblgrid_oracle.so exports the same
+symbols and takes host pointers) and pass it explicitly to the studies.  Nothing in this package refers to oracle/.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+import torch
+
+MAX_OPS = 16
+
+F_EVIDENCE_ONLY = 1 << 0
+F_INIT_STATE = 1 << 1
+F_TRANSITION_FIRST = 1 << 2
+F_SAVE_STATE = 1 << 3
+F_ACCUMULATE = 1 << 4
+F_NORMALIZE_ROWS = 1 << 5
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+
+
+class _Problem(ctypes.Structure):
+    _fields_ = [('ndim', ctypes.c_int32), ('n', ctypes.c_int32 * 2), ('coords', _dp * 2),
+                ('lattice', ctypes.c_double * 2), ('om_kind', ctypes.c_int32), ('seg_len', ctypes.c_int32),
+                ('n_cols', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class _Program(ctypes.Structure):
+    _fields_ = [('n_ops', ctypes.c_int32), ('kind', ctypes.c_int32 * MAX_OPS), ('axis', ctypes.c_int32 * MAX_OPS),
+                ('max_radius', ctypes.c_int32 * MAX_OPS), ('param', ctypes.c_void_p), ('radius', ctypes.c_void_p), ('window', ctypes.c_void_p)]
+
+
+class _Inputs(ctypes.Structure):
+    _fields_ = [('T', ctypes.c_int64), ('B', ctypes.c_int64), ('data', ctypes.c_void_p), ('prior', ctypes.c_void_p),
+                ('reset_base', ctypes.c_void_p), ('lik_table', ctypes.c_void_p), ('prog', _Program),
+                ('log_weight', ctypes.c_void_p), ('init_state', ctypes.c_void_p)]
+
+
+class _Outputs(ctypes.Structure):
+    _fields_ = [('log_evidence', ctypes.c_void_p), ('local_evidence', ctypes.c_void_p), ('alive', ctypes.c_void_p),
+                ('alpha_seq', ctypes.c_void_p), ('avg', ctypes.c_void_p), ('final_state', ctypes.c_void_p)]
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Program:
+    """Flat transition program on the engine's device (see transitionModels.LoweringContext)."""
+
+    def __init__(self, engine, ops, B):
+        if len(ops) > MAX_OPS:
+            raise EngineError('transition program has {} operators, the engine supports {}'.format(len(ops), MAX_OPS))
+        self.n_ops = len(ops)
+        self.B = B
+        self.kinds = [int(o['kind']) for o in ops]
+        self.axes = [int(o['axis']) for o in ops]
+        K = max(self.n_ops, 1)
+        param = np.zeros((B, K))
+        radius = np.zeros((B, K), dtype=np.int32)
+        window = np.zeros((B, K, 4), dtype=np.int32)
+        for k, o in enumerate(ops):
+            param[:, k], radius[:, k], window[:, k, :] = o['param'], o['radius'], o['window']
+        self.host = dict(param=param, radius=radius, window=window)
+        self.param = engine.to_device(param)
+        self.radius = engine.to_device(radius)
+        self.window = engine.to_device(window)
+
+    def struct(self, lo=0, hi=None):
+        hi = self.B if hi is None else hi
+        p = _Program()
+        p.n_ops = self.n_ops
+        for k in range(self.n_ops):
+            p.kind[k], p.axis[k] = self.kinds[k], self.axes[k]
+            p.max_radius[k] = int(self.host['radius'][lo:hi, k].max()) if hi > lo else 0
+        K = max(self.n_ops, 1)
+        p.param = self.param.data_ptr() + lo * K * 8
+        p.radius = self.radius.data_ptr() + lo * K * 4
+        p.window = self.window.data_ptr() + lo * K * 16
+        return p
+
+
+class Plan:
+    def __init__(self, engine, handle, ndim, n, G):
+        self.engine, self.handle, self.ndim, self.n, self.G = engine, handle, ndim, n, G
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.engine.lib.blg_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Engine:
+    """One loaded implementation of include/blgrid.h plus the torch device its pointers live on."""
+
+    def __init__(self, lib_path, device):
+        if not os.path.exists(lib_path):
+            raise EngineError('engine library not found: {} (run `python -c "import __graft_entry__ as g; g.build()"`)'
+                              .format(lib_path))
+        self.lib_path = lib_path
+        self.device = torch.device(device)
+        self.lib = ctypes.CDLL(lib_path)
+        L = self.lib
+        L.blg_version.restype = ctypes.c_int
+        L.blg_last_error.restype = ctypes.c_char_p
+        L.blg_backend.restype = ctypes.c_char_p
+        L.blg_launch_count.restype = ctypes.c_int64
+        L.blg_plan_create.argtypes = [ctypes.POINTER(_Problem), ctypes.POINTER(ctypes.c_void_p)]
+        L.blg_plan_destroy.argtypes = [ctypes.c_void_p]
+        L.blg_plan_destroy.restype = None
+        for name in ('blg_forward', 'blg_backward', 'blg_accumulate'):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.POINTER(_Inputs), ctypes.POINTER(_Outputs),
+                                         ctypes.c_uint32, ctypes.c_void_p]
+        L.blg_finalize.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                   ctypes.c_uint32, ctypes.c_void_p]
+        L.blg_mix.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                              ctypes.c_void_p, ctypes.c_void_p]
+        L.blg_scale.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p]
+        if L.blg_version() != 1:
+            raise EngineError('ABI version mismatch in {}'.format(lib_path))
+        self.backend = L.blg_backend().decode()
+
+    # ---------------------------------------------------------------------------------------------- memory
+    def to_device(self, array, pinned=False):
+        t = torch.from_numpy(np.ascontiguousarray(array))
+        if self.device.type == 'cuda':
+            if pinned:
+                t = t.pin_memory()
+            return t.to(self.device, non_blocking=pinned)
+        return t.clone()
+
+    def empty(self, shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype=torch.float64):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def to_host(self, tensor):
+        return tensor.detach().cpu().numpy()
+
+    def free_bytes(self):
+        if self.device.type == 'cuda':
+            return torch.cuda.mem_get_info(self.device)[0]
+        return 8 << 30
+
+    def stream(self):
+        if self.device.type == 'cuda':
+            return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return ctypes.c_void_p(0)
+
+    def synchronize(self):
+        if self.device.type == 'cuda':
+            torch.cuda.synchronize(self.device)
+
+    def launch_count(self):
+        return int(self.lib.blg_launch_count())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError('{}: {}'.format(self.backend, self.lib.blg_last_error().decode()))
+
+    # ---------------------------------------------------------------------------------------------- calls
+    def plan(self, coords, lattice, om_kind, seg_len, n_cols):
+        ndim = len(coords)
+        hostCoords = [np.ascontiguousarray(c, dtype=np.float64) for c in coords]
+        pb = _Problem()
+        pb.ndim = ndim
+        for a in range(2):
+            pb.n[a] = len(hostCoords[a]) if a < ndim else 1
+            pb.lattice[a] = float(lattice[a]) if a < ndim else 1.0
+            pb.coords[a] = hostCoords[a].ctypes.data_as(_dp) if a < ndim else None
+        pb.om_kind, pb.seg_len, pb.n_cols = int(om_kind), int(seg_len), int(n_cols)
+        handle = ctypes.c_void_p()
+        if self.device.type == 'cuda':
+            with torch.cuda.device(self.device):
+                self._check(self.lib.blg_plan_create(ctypes.byref(pb), ctypes.byref(handle)))
+        else:
+            self._check(self.lib.blg_plan_create(ctypes.byref(pb), ctypes.byref(handle)))
+        n = [pb.n[0], pb.n[1]]
+        return Plan(self, handle, ndim, n, n[0] * n[1])
+
+    def _io(self, T, B, data, prior, reset_base, lik_table, program, lo, log_weight, init_state, log_evidence,
+            local_evidence, alive, alpha_seq, avg, final_state):
+        i = _Inputs()
+        i.T, i.B = int(T), int(B)
+        i.data, i.prior, i.reset_base, i.lik_table = _ptr(data), _ptr(prior), _ptr(reset_base), _ptr(lik_table)
+        i.prog = program.struct(lo, lo + B)
+        i.log_weight, i.init_state = _ptr(log_weight), _ptr(init_state)
+        o = _Outputs()
+        o.log_evidence, o.local_evidence, o.alive = _ptr(log_evidence), _ptr(local_evidence), _ptr(alive)
+        o.alpha_seq, o.avg, o.final_state = _ptr(alpha_seq), _ptr(avg), _ptr(final_state)
+        return i, o
+
+    def run(self, which, plan, flags, **kw):
+        """which in {'forward', 'backward', 'accumulate'}; keyword arguments are the fields of blg_inputs/outputs
+        (tensors on self.device) plus `program` and `lo` (first combo row of the program used by this call)."""
+        names = ('T', 'B', 'data', 'prior', 'reset_base', 'lik_table', 'program', 'lo', 'log_weight', 'init_state',
+                 'log_evidence', 'local_evidence', 'alive', 'alpha_seq', 'avg', 'final_state')
+        args = [kw.get(k) for k in names]
+        args[7] = args[7] or 0
+        i, o = self._io(*args)
+        fn = getattr(self.lib, 'blg_' + which)
+        self._check(fn(plan.handle, ctypes.byref(i), ctypes.byref(o), ctypes.c_uint32(flags), self.stream()))
+
+    def finalize(self, plan, seq, T, means, flags):
+        self._check(self.lib.blg_finalize(plan.handle, _ptr(seq), int(T), _ptr(means), ctypes.c_uint32(flags),
+                                          self.stream()))
+
+    def mix(self, plan, state, weight, K, n, out):
+        self._check(self.lib.blg_mix(plan.handle, _ptr(state), _ptr(weight), int(K), int(n), _ptr(out),
+                                     self.stream()))
+
+    def scale(self, plan, x, count, factor):
+        self._check(self.lib.blg_scale(plan.handle, _ptr(x), int(count), float(factor), self.stream()))
+
+
+_lock = threading.Lock()
+_default = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libblgrid.so')
+
+
+def default_engine():
+    """The CUDA engine on the current device (LOCAL_RANK aware).  Raises if it cannot be had -- by design."""
+    global _default
+    with _lock:
+        if _default is None:
+            if not torch.cuda.is_available():
+                raise EngineError('bayesloop_b200 needs a CUDA device (sm_100a); there is no CPU fallback.')
+            index = int(os.environ.get('LOCAL_RANK', torch.cuda.current_device()))
+            torch.cuda.set_device(index)
+            _default = Engine(library_path(), 'cuda:{}'.format(index))
+            if not _default.backend.startswith('cuda'):
+                raise EngineError('unexpected engine backend {!r}'.format(_default.backend))
+        return _default
+
+
+def set_default_engine(engine):
+    """Install `engine` as the process-wide default (used by multi-process launchers and by the test-suite)."""
+    global _default
+    with _lock:
+        _default = engine

@@ -46,7 +46,13 @@ class _Anything:
 
 def _stub_module(name):
     m = types.ModuleType(name)
-    m.__getattr__ = lambda attr: _Anything  # type: ignore[attr-defined]
+
+    def _getattr(attr):
+        if attr.startswith("__"):  # keep inspect / importlib machinery honest (torch walks sys.modules)
+            raise AttributeError(attr)
+        return _Anything
+
+    m.__getattr__ = _getattr  # type: ignore[attr-defined]
     m.__path__ = []  # behave like a package
     return m
 
