@@ -609,9 +609,9 @@ class HyperStudy(Study):
         else:
             self.flatHyperPriorValues = np.array([1])
 
-    def _sweep(self, forwardOnly, evidenceOnly, exclude=None):
-        """Run all rows of self.hyperGridValues on the device, in waves sized to HBM, sharded across ranks.
-        Returns host arrays (logE[B], localEvidence[T]) and device tensors (avg [T,G] normalised, means)."""
+    def _prepareSweep(self, forwardOnly, evidenceOnly):
+        """Device-resident inputs and work buffers of a sweep over this rank's rows of self.hyperGridValues:
+        session (data, prior, tables), lowered transition program, wave buffer sized to the free HBM."""
         from . import distributed as dist
         eng = self._engine()
         ses = _Session(self, eng)
@@ -622,40 +622,53 @@ class HyperStudy(Study):
         hyper = np.asarray(self.hyperGridValues, dtype=float)[lo:hi]
         hp = np.asarray(self.flatHyperPriorValues, dtype=float)[lo:hi]
         ctx = self._lower(hyper, self.formattedTimestamps)
-        program = _engine.Program(eng, ctx.ops, B)
-        resetBase = ses.reset_base() if ctx.usesReset else None
-        logE, local = eng.zeros(max(B, 1)), eng.zeros((max(B, 1), T))
-        alive = eng.zeros(max(B, 1), dtype=torch.int32)
-        avg = None if evidenceOnly else eng.zeros((T, G))
-
+        sw = dict(eng=eng, ses=ses, T=T, G=G, Ball=Ball, lo=lo, hi=hi, B=B, hp=hp, ops=ctx.ops,
+                  forwardOnly=forwardOnly, evidenceOnly=evidenceOnly)
+        sw['program'] = _engine.Program(eng, ctx.ops, B)
+        sw['resetBase'] = ses.reset_base() if ctx.usesReset else None
+        sw['logE'], sw['local'] = eng.zeros(max(B, 1)), eng.zeros((max(B, 1), T))
+        sw['alive'] = eng.zeros(max(B, 1), dtype=torch.int32)
+        sw['hpDev'] = eng.to_device(hp) if B > 0 else None
+        sw['part'] = eng.zeros(T)
         if evidenceOnly:
-            wave = max(B, 1)
-            buf = None
+            sw['wave'], sw['buf'], sw['avg'], sw['means'] = max(B, 1), None, None, None
         else:
-            budget = int(eng.free_bytes() * 0.80) - 2 * T * G * 8
-            wave = int(max(1, min(B, budget // max(1, T * G * 8))))
-            buf = eng.empty((wave, T, G)) if B > 0 else None
+            sw['avg'] = eng.zeros((T, G))
+            sw['means'] = eng.empty((len(self.gridSize), T))
+            budget = int(eng.free_bytes() * 0.85) - T * G * 8
+            sw['wave'] = int(max(1, min(B, budget // max(1, T * G * 8))))
+            sw['buf'] = eng.empty((sw['wave'], T, G)) if B > 0 else None
         with np.errstate(divide='ignore'):
-            logHp = np.log(hp)
+            sw['logHp'] = np.log(hp)
+        return sw
+
+    def _executeSweep(self, sw, exclude=None):
+        """Kernels of one sweep (inputs already resident): per wave one forward pass, the evidences fix the
+        averaging weights, one backward(+accumulate) pass; then local-evidence mix, cross-rank merge, finalize."""
+        from . import distributed as dist
+        eng, ses, T, G, B = sw['eng'], sw['ses'], sw['T'], sw['G'], sw['B']
+        evidenceOnly, forwardOnly = sw['evidenceOnly'], sw['forwardOnly']
+        logE, local, alive, avg, buf, wave = sw['logE'], sw['local'], sw['alive'], sw['avg'], sw['buf'], sw['wave']
+        if avg is not None:
+            avg.zero_()
         shift = -np.inf
         logEHost = np.zeros(B)
         waves = 0
         for w0 in range(0, B, wave):
             w1 = min(B, w0 + wave)
             nb = w1 - w0
-            common = dict(T=T, B=nb, data=ses.data, prior=ses.prior, lik_table=ses.likTable, program=program, lo=w0,
-                          reset_base=resetBase, log_evidence=logE[w0:w1], local_evidence=local[w0:w1],
+            common = dict(T=T, B=nb, data=ses.data, prior=ses.prior, lik_table=ses.likTable, program=sw['program'],
+                          lo=w0, reset_base=sw['resetBase'], log_evidence=logE[w0:w1], local_evidence=local[w0:w1],
                           alive=alive[w0:w1], alpha_seq=buf)
             eng.run('forward', ses.plan, _engine.F_EVIDENCE_ONLY if evidenceOnly else 0, **common)
             waves += 1
-            if evidenceOnly:
-                logEHost[w0:w1] = eng.to_host(logE[w0:w1])
-                continue
             le = eng.to_host(logE[w0:w1])  # the evidences fix the averaging weights of this wave
             logEHost[w0:w1] = le
-            lw = le + logHp[w0:w1]
+            if evidenceOnly:
+                continue
+            lw = le + sw['logHp'][w0:w1]
             if exclude is not None:
-                lw = np.where(exclude[lo + w0:lo + w1], -np.inf, lw)
+                lw = np.where(exclude[sw['lo'] + w0:sw['lo'] + w1], -np.inf, lw)
             finite = np.isfinite(lw)
             if finite.any():
                 top = float(np.max(lw[finite]))
@@ -670,12 +683,12 @@ class HyperStudy(Study):
                 eng.run('backward', ses.plan, _engine.F_ACCUMULATE, log_weight=weights, avg=avg, **common)
         aliveHost = eng.to_host(alive)[:B]
         logEHost = np.where(aliveHost == 1, logEHost, -np.inf)
-
         # averaged local evidence: sum_b localEvidence_b * hyperprior_b (core.py:1410)
-        part = eng.zeros(T)
+        part = sw['part']
+        part.zero_()
         if B > 0:
-            eng.mix(ses.plan, local, eng.to_device(hp), B, T, part)
-        logEAll, aliveAll = dist.gather_rows(eng, logEHost, aliveHost, Ball)
+            eng.mix(ses.plan, local, sw['hpDev'], B, T, part)
+        logEAll, aliveAll = dist.gather_rows(eng, logEHost, aliveHost, sw['Ball'])
         localEv = dist.reduce_sum(eng, part)
         died = aliveAll == -1
         if exclude is not None:
@@ -683,14 +696,16 @@ class HyperStudy(Study):
         if (not evidenceOnly) and died.any():
             # A combo whose backward pass hit a zero norm is dropped from the average as a whole
             # (core.py:1358): redo the sweep with its weight forced to zero.
-            return self._sweep(forwardOnly, evidenceOnly, exclude=(died if exclude is None else (exclude | died)))
-        means = None
+            return self._executeSweep(sw, exclude=(died if exclude is None else (exclude | died)))
         if not evidenceOnly:
-            shift = dist.rebase_and_reduce(eng, ses.plan, avg, shift, T * G)
-            means = eng.empty((len(self.gridSize), T))
-            eng.finalize(ses.plan, avg, T, means, _engine.F_NORMALIZE_ROWS)
-        self.sweepStats = dict(waves=waves, wave=wave, shard=(lo, hi), launches=eng.launch_count())
-        return eng, logEAll, aliveAll, eng.to_host(localEv), avg, means
+            dist.rebase_and_reduce(eng, ses.plan, avg, shift, T * G)
+            eng.finalize(ses.plan, avg, T, sw['means'], _engine.F_NORMALIZE_ROWS)
+        self.sweepStats = dict(waves=waves, wave=wave, shard=(sw['lo'], sw['hi']), launches=eng.launch_count())
+        return eng, logEAll, aliveAll, localEv, avg, sw['means']
+
+    def _sweep(self, forwardOnly, evidenceOnly):
+        eng, logE, alive, localEv, avg, means = self._executeSweep(self._prepareSweep(forwardOnly, evidenceOnly))
+        return eng, logE, alive, eng.to_host(localEv), avg, means
 
     def fit(self, forwardOnly=False, evidenceOnly=False, silent=False, nJobs=1, customHyperGrid=False):
         """Fit every combination of hyper-parameter values and average the models by their evidence (contract of

@@ -1,0 +1,419 @@
+// api.cu -- host side of libblgrid.so: the C ABI of include/blgrid.h on top of the sm_100a kernels.
+//
+// Boundary replaced (reference file:line): the per-time-step Python loops of Study.fit (bayesloop/core.py:372-411,
+// :434-470), the per-combination loop and averaging of HyperStudy.fit (core.py:1349-1366, :1379-1382, :1410) and
+// the per-hypothesis loop of OnlineStudy.step (core.py:2157-2175, :2195-2212).  No torch types cross this file; the
+// caller hands raw device pointers and a cudaStream_t.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "aux.cuh"
+#include "resident.cuh"
+
+using namespace blg;
+
+namespace {
+
+thread_local char g_err[512];
+std::atomic<long long> g_launches{0};
+
+int fail(const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof g_err, fmt, detail);
+    return -1;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            snprintf(g_err, sizeof g_err, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+            return -1;                                                                      \
+        }                                                                                   \
+    } while (0)
+
+inline int even_up(int x) { return (x + 1) & ~1; }
+
+constexpr int kMiscDoubles = 192;  // reduction scratch (128) + params (16) + radius/window ints (40) + 2 mbarriers
+constexpr size_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+
+}  // namespace
+
+struct blg_plan {
+    blg_problem pb;
+    DevProblem dev;
+    int device;
+    int num_sms;
+    double *d_tables;  // c0[n0] c1[n1] A0 A1 A2 [n0 each] B0 B1 [n1 each]
+    StepC *d_steps;
+    long long steps_cap;
+    double *d_w;
+    long long w_cap;
+    int serpentine;
+};
+
+extern "C" {
+
+int blg_version(void) { return BLG_ABI_VERSION; }
+const char *blg_last_error(void) { return g_err; }
+const char *blg_backend(void) { return "cuda:sm_100a"; }
+int64_t blg_launch_count(void) { return g_launches.load(); }
+
+int blg_plan_create(const blg_problem *p, blg_plan **out) {
+    if (!p || !out) return fail("null argument");
+    if (p->ndim < 1 || p->ndim > 2) return fail("ndim must be 1 or 2");
+    const int n0 = p->n[0], n1 = p->ndim == 2 ? p->n[1] : 1;
+    if (n0 < 1 || n1 < 1) return fail("bad grid size");
+    if (!p->coords[0] || (p->ndim == 2 && !p->coords[1])) return fail("coords missing");
+    const int om = p->om_kind;
+    const bool twoD = (om == BLG_OM_GAUSSIAN || om == BLG_OM_SCALED_AR1 || om == BLG_OM_AR1 || om == BLG_OM_LAPLACE);
+    if (om != BLG_OM_TABLE && twoD != (p->ndim == 2)) return fail("observation model / grid dimension mismatch");
+    if ((om == BLG_OM_AR1 || om == BLG_OM_SCALED_AR1) ? p->seg_len != 2 : (om != BLG_OM_TABLE && p->seg_len != 1))
+        return fail("segment length does not match the observation model");
+    if (om == BLG_OM_GAUSSIAN_MEAN && p->n_cols != 2) return fail("GAUSSIAN_MEAN needs 2 data columns");
+    if (p->n_cols < 1) return fail("n_cols must be >= 1");
+
+    blg_plan *pl = new blg_plan();
+    pl->pb = *p;
+    pl->pb.n[1] = n1;
+    CUDA_TRY(cudaGetDevice(&pl->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, pl->device));
+    pl->num_sms = prop.multiProcessorCount;
+    const char *env = getenv("BLG_SERPENTINE");
+    pl->serpentine = env ? atoi(env) : 1;
+
+    // host tables (see lik_column in common.cuh)
+    std::vector<double> h((size_t)(4 * n0 + 3 * n1), 0.0);
+    double *c0 = h.data(), *c1 = c0 + n0, *A0 = c1 + n1, *A1 = A0 + n0, *A2 = A1 + n0, *B0 = A2 + n0, *B1 = B0 + n1;
+    for (int i = 0; i < n0; ++i) c0[i] = p->coords[0][i];
+    for (int j = 0; j < n1; ++j) c1[j] = p->ndim == 2 ? p->coords[1][j] : 0.0;
+    bool useA[3] = {false, false, false}, useB[2] = {false, false};
+    for (int i = 0; i < n0; ++i) {
+        const double x = c0[i];
+        switch (om) {
+            case BLG_OM_POISSON:
+                A0[i] = x;
+                A1[i] = log(x);
+                useA[0] = useA[1] = true;
+                break;
+            case BLG_OM_GAUSSIAN:
+            case BLG_OM_AR1:
+            case BLG_OM_GAUSSIAN_MEAN:
+            case BLG_OM_LAPLACE:
+                A0[i] = x;
+                useA[0] = true;
+                break;
+            case BLG_OM_SCALED_AR1:
+                A0[i] = x;
+                A1[i] = 1.0 / (1.0 - x * x);
+                A2[i] = -0.5 * log(1.0 - x * x);
+                useA[0] = useA[1] = useA[2] = true;
+                break;
+            case BLG_OM_WHITE_NOISE:
+                A0[i] = 1.0 / (2.0 * x * x);
+                A1[i] = -0.5 * log(2.0 * M_PI * x * x);
+                useA[0] = useA[1] = true;
+                break;
+            case BLG_OM_BERNOULLI:
+                A0[i] = (x > 1.0 || x < 0.0) ? 0.0 : x;
+                useA[0] = true;
+                break;
+            default:
+                break;
+        }
+    }
+    for (int j = 0; j < n1; ++j) {
+        const double y = c1[j];
+        switch (om) {
+            case BLG_OM_GAUSSIAN:
+            case BLG_OM_AR1:
+            case BLG_OM_SCALED_AR1:
+                B0[j] = 1.0 / (2.0 * y * y);
+                B1[j] = -0.5 * log(2.0 * M_PI * y * y);
+                useB[0] = useB[1] = true;
+                break;
+            case BLG_OM_LAPLACE:
+                B0[j] = 1.0 / y;
+                B1[j] = -log(2.0 * y);
+                useB[0] = useB[1] = true;
+                break;
+            default:
+                break;
+        }
+    }
+    if (cudaMalloc(&pl->d_tables, h.size() * sizeof(double)) != cudaSuccess) {
+        delete pl;
+        return fail("cudaMalloc of plan tables failed");
+    }
+    if (cudaMemcpy(pl->d_tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(pl->d_tables);
+        delete pl;
+        return fail("upload of plan tables failed");
+    }
+    DevProblem &d = pl->dev;
+    d.ndim = p->ndim;
+    d.n0 = n0;
+    d.n1 = n1;
+    d.G = n0 * n1;
+    d.om_kind = om;
+    d.seg = p->seg_len;
+    d.ncols = p->n_cols;
+    d.ncols_eff = om == BLG_OM_GAUSSIAN_MEAN ? 1 : p->n_cols;
+    d.lc_prod = p->lattice[0] * (p->ndim == 2 ? p->lattice[1] : 1.0);
+    double *base = pl->d_tables;
+    d.c0 = base;
+    d.c1 = base + n0;
+    double *dA0 = base + n0 + n1;
+    d.tabA[0] = useA[0] ? dA0 : nullptr;
+    d.tabA[1] = useA[1] ? dA0 + n0 : nullptr;
+    d.tabA[2] = useA[2] ? dA0 + 2 * n0 : nullptr;
+    d.tabB[0] = useB[0] ? dA0 + 3 * n0 : nullptr;
+    d.tabB[1] = useB[1] ? dA0 + 3 * n0 + n1 : nullptr;
+    pl->d_steps = nullptr;
+    pl->steps_cap = 0;
+    pl->d_w = nullptr;
+    pl->w_cap = 0;
+    *out = pl;
+    return 0;
+}
+
+void blg_plan_destroy(blg_plan *pl) {
+    if (!pl) return;
+    cudaFree(pl->d_tables);
+    if (pl->d_steps) cudaFree(pl->d_steps);
+    if (pl->d_w) cudaFree(pl->d_w);
+    delete pl;
+}
+
+}  // extern "C"
+
+namespace {
+
+int ensure_steps(blg_plan *pl, long long count) {
+    if (count <= pl->steps_cap) return 0;
+    if (pl->d_steps) CUDA_TRY(cudaFree(pl->d_steps));
+    pl->d_steps = nullptr;
+    pl->steps_cap = 0;
+    CUDA_TRY(cudaMalloc(&pl->d_steps, (size_t)count * sizeof(StepC)));
+    pl->steps_cap = count;
+    return 0;
+}
+
+int ensure_w(blg_plan *pl, long long count) {
+    if (count <= pl->w_cap) return 0;
+    if (pl->d_w) CUDA_TRY(cudaFree(pl->d_w));
+    pl->d_w = nullptr;
+    pl->w_cap = 0;
+    CUDA_TRY(cudaMalloc(&pl->d_w, (size_t)count * sizeof(double)));
+    pl->w_cap = count;
+    return 0;
+}
+
+int prep_steps(blg_plan *pl, const blg_inputs *in, cudaStream_t st) {
+    const DevProblem &d = pl->dev;
+    if (d.om_kind == BLG_OM_TABLE) return ensure_steps(pl, 1);
+    if (!in->data) return fail("data pointer missing");
+    const long long count = in->T * d.ncols_eff;
+    if (ensure_steps(pl, count > 0 ? count : 1)) return -1;
+    if (count > 0) {
+        const int nt = 256;
+        prep_steps_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(in->data, pl->d_steps, in->T, d.om_kind,
+                                                                             d.ncols, d.ncols_eff);
+        ++g_launches;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+struct Layout {
+    size_t bytes;
+    int nt;
+};
+
+// Shared-memory layout of the resident kernels; returns false if the grid does not fit.
+bool resident_layout(const blg_plan *pl, const blg_program &pg, bool backward, bool want_stage, PassArgs &a, Layout &lay) {
+    const DevProblem &d = pl->dev;
+    a.Gp = even_up(d.G);
+    a.n0p = even_up(d.n0);
+    a.n1p = even_up(d.n1);
+    int off = 2 * a.Gp;
+    a.off_stage = -1;
+    if (backward && want_stage) {
+        a.off_stage = off;
+        off += 2 * a.Gp;
+    }
+    a.off_tab = off;
+    off += 3 * a.n0p + 2 * a.n1p;
+    a.off_w = off;
+    int woff = 0;
+    for (int k = 0; k < pg.n_ops; ++k) {
+        a.pg.w_off[k] = woff;
+        a.pg.w_len[k] = 0;
+        if (pg.kind[k] == BLG_OP_GRW) {
+            const int taps = 2 * pg.max_radius[k] + 1;
+            const int len = ((taps + kConvM - 1) / kConvM) * kConvM + kConvM;
+            a.pg.w_len[k] = even_up(len);
+            woff += a.pg.w_len[k];
+        }
+    }
+    off += woff;
+    a.off_misc = even_up(off);
+    lay.bytes = (size_t)(a.off_misc + kMiscDoubles) * sizeof(double);
+    int nt = ((d.G + 3) / 4 + 31) / 32 * 32;
+    if (nt < 128) nt = 128;
+    if (nt > 256 && nt <= 512) nt = 512;
+    if (nt > 512) nt = 1024;
+    lay.nt = nt;
+    return lay.bytes <= kSmemLimit;
+}
+
+template <typename K>
+int launch_resident(K kernel, const PassArgs &a, const Layout &lay, long long B, cudaStream_t st) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+    kernel<<<(unsigned)B, lay.nt, lay.bytes, st>>>(a);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int fill_args(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, PassArgs &a) {
+    const blg_program &pg = in->prog;
+    if (pg.n_ops < 0 || pg.n_ops > BLG_MAX_OPS) return fail("n_ops out of range");
+    if (pg.n_ops > 0 && (!pg.param || !pg.radius || !pg.window)) return fail("program arrays missing");
+    a.pb = pl->dev;
+    a.pg.n_ops = pg.n_ops;
+    bool hasReset = false;
+    for (int k = 0; k < pg.n_ops; ++k) {
+        a.pg.kind[k] = pg.kind[k];
+        a.pg.axis[k] = pg.axis[k];
+        if (pg.kind[k] == BLG_OP_GRW && (pg.axis[k] < 0 || pg.axis[k] >= pl->dev.ndim)) return fail("GRW axis out of range");
+        if (pg.kind[k] == BLG_OP_RESET) hasReset = true;
+        if (pg.kind[k] < BLG_OP_GRW || pg.kind[k] > BLG_OP_NOTEQUAL) return fail("unknown operator kind");
+    }
+    if (hasReset && !in->reset_base) return fail("reset_base required by a RESET operator");
+    a.pg.param = pg.param;
+    a.pg.radius = pg.radius;
+    a.pg.window = pg.window;
+    a.T = in->T;
+    a.B = in->B;
+    a.prior = in->prior;
+    a.reset_base = in->reset_base;
+    a.lik_table = in->lik_table;
+    a.log_weight = in->log_weight;
+    a.init_state = in->init_state;
+    a.logE = out->log_evidence;
+    a.local = out->local_evidence;
+    a.alive = out->alive;
+    a.alpha_seq = out->alpha_seq;
+    a.avg = out->avg;
+    a.final_state = out->final_state;
+    a.steps = pl->d_steps;
+    a.flags = flags;
+    a.num_sms = pl->num_sms;
+    a.serpentine = (pl->serpentine && in->B > pl->num_sms) ? 1 : 0;
+    if (pl->dev.om_kind == BLG_OM_TABLE && !in->lik_table) return fail("lik_table required for BLG_OM_TABLE");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {
+    if (!pl || !in || !out) return fail("null argument");
+    if (!out->log_evidence) return fail("log_evidence output missing");
+    if (in->B <= 0 || in->T <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool store = !(flags & BLG_F_EVIDENCE_ONLY);
+    if (store && !out->alpha_seq) return fail("alpha_seq required unless EVIDENCE_ONLY");
+    if ((flags & BLG_F_INIT_STATE) ? !in->init_state : !in->prior) return fail("initial state missing");
+    if ((flags & BLG_F_SAVE_STATE) && !out->final_state) return fail("final_state missing");
+    PassArgs a;
+    memset(&a, 0, sizeof a);
+    if (prep_steps(pl, in, st)) return -1;
+    if (fill_args(pl, in, out, flags, a)) return -1;
+    Layout lay;
+    if (!resident_layout(pl, in->prog, false, false, a, lay))
+        return fail("grid / kernel radius too large for the shared-memory resident forward kernel");
+    a.use_bulk = (store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0)) ? 1 : 0;
+    if (getenv("BLG_NO_BULK")) a.use_bulk = 0;
+    if (lay.nt <= 256) return launch_resident(fwd_resident_kernel<256, 4>, a, lay, in->B, st);
+    if (lay.nt <= 512) return launch_resident(fwd_resident_kernel<512, 2>, a, lay, in->B, st);
+    return launch_resident(fwd_resident_kernel<1024, 1>, a, lay, in->B, st);
+}
+
+int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {
+    if (!pl || !in || !out) return fail("null argument");
+    if (!out->alpha_seq || !out->log_evidence) return fail("alpha_seq / log_evidence missing");
+    if (in->B <= 0 || in->T <= 0) return 0;
+    const bool acc = (flags & BLG_F_ACCUMULATE) != 0;
+    if (acc && (!out->avg || !in->log_weight)) return fail("avg and log_weight required with ACCUMULATE");
+    cudaStream_t st = (cudaStream_t)stream;
+    PassArgs a;
+    memset(&a, 0, sizeof a);
+    if (prep_steps(pl, in, st)) return -1;
+    if (fill_args(pl, in, out, flags, a)) return -1;
+    Layout lay;
+    const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
+    bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
+    if (!fits) {
+        if (!resident_layout(pl, in->prog, true, false, a, lay))
+            return fail("grid / kernel radius too large for the shared-memory resident backward kernel");
+    }
+    a.use_bulk = (fits && a.off_stage >= 0) ? 1 : 0;
+    if (lay.nt <= 256) return launch_resident(bwd_resident_kernel<256, 4>, a, lay, in->B, st);
+    if (lay.nt <= 512) return launch_resident(bwd_resident_kernel<512, 2>, a, lay, in->B, st);
+    return launch_resident(bwd_resident_kernel<1024, 1>, a, lay, in->B, st);
+}
+
+int blg_accumulate(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {
+    (void)flags;
+    if (!pl || !in || !out || !out->alpha_seq || !out->avg || !in->log_weight) return fail("null argument");
+    if (in->B <= 0 || in->T <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ensure_w(pl, in->B)) return -1;
+    const int nt = 256;
+    weights_kernel<<<(unsigned)((in->B + nt - 1) / nt), nt, 0, st>>>(in->log_weight, out->alive, in->B, pl->d_w);
+    const long long count = in->T * (long long)pl->dev.G;
+    accumulate_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(out->alpha_seq, pl->d_w, in->B, count, out->avg);
+    g_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int blg_scale(blg_plan *pl, double *x, int64_t count, double factor, void *stream) {
+    if (!pl || !x) return fail("null argument");
+    if (count <= 0) return 0;
+    const int nt = 256;
+    scale_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(x, count, factor);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int blg_finalize(blg_plan *pl, double *seq, int64_t T, double *means, uint32_t flags, void *stream) {
+    if (!pl || !seq) return fail("null argument");
+    if (T <= 0) return 0;
+    const DevProblem &d = pl->dev;
+    long long blocks = T < (long long)pl->num_sms * 8 ? T : (long long)pl->num_sms * 8;
+    finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(seq, T, d.G, d.n1, d.ndim, d.c0, d.c1, means,
+                                                                         (flags & BLG_F_NORMALIZE_ROWS) ? 1 : 0);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int blg_mix(blg_plan *pl, const double *state, const double *weight, int64_t K, int64_t n, double *out, void *stream) {
+    if (!pl || !state || !weight || !out) return fail("null argument");
+    if (n <= 0) return 0;
+    const int nt = 256;
+    mix_kernel<<<(unsigned)((n + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(state, weight, K, n, out);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

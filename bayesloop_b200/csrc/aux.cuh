@@ -1,0 +1,119 @@
+// aux.cuh -- small streaming kernels around the persistent passes: per-step data constants, weighted row sums,
+// row normalisation + posterior means, running-average maintenance.  All are HBM/L2-bound elementwise or row
+// reductions with coalesced 8-byte accesses; none sits on the critical path of a sweep (O(T*G) once per sweep
+// against O(B*T*G) for the passes).
+#pragma once
+
+#include "common.cuh"
+
+namespace blg {
+
+// Per (time step, data column) constants: removes lgamma/log/div and the NaN test from the per-cell loops.
+// Implements the segment handling of preprocessing.py:14-26 (two-point segments) and the missing-data rule of
+// observationModels.py:53-54.
+__global__ void prep_steps_kernel(const double *__restrict__ data, StepC *__restrict__ out, long long T, int om, int nc,
+                                  int nce) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * nce) return;
+    const long long t = e / nce;
+    const int c = (int)(e - t * nce);
+    StepC s;
+    s.d0 = 0.0;
+    s.d1 = 0.0;
+    s.c = 0.0;
+    s.skip = 0.0;
+    if (om == BLG_OM_GAUSSIAN_MEAN) {
+        const double v = data[t * nc + 0], err = data[t * nc + 1];
+        if (isnan(v) || isnan(err)) s.skip = 1.0;
+        s.d0 = v;
+        s.d1 = 1.0 / (2.0 * err * err);
+        s.c = -0.5 * log(2.0 * M_PI * err * err);
+    } else if (om == BLG_OM_AR1 || om == BLG_OM_SCALED_AR1) {
+        s.d0 = data[t * nc + c];
+        s.d1 = data[(t + 1) * nc + c];
+        if (isnan(s.d0) || isnan(s.d1)) s.skip = 1.0;
+    } else {
+        s.d0 = data[t * nc + c];
+        if (isnan(s.d0)) s.skip = 1.0;
+        if (om == BLG_OM_POISSON) s.c = lgamma(s.d0 + 1.0);  // log(k!)  (observationModels.py:502)
+    }
+    out[e] = s;
+}
+
+// out[j] = sum_k weight[k] * state[k][j]   (core.py:1410, :2195-2197, :2212); fixed summation order
+__global__ void mix_kernel(const double *__restrict__ state, const double *__restrict__ weight, long long K, long long n,
+                           double *__restrict__ out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double s = 0.0;
+    for (long long k = 0; k < K; ++k) s = fma(__ldg(weight + k), __ldg(state + k * n + j), s);
+    out[j] = s;
+}
+
+__global__ void scale_kernel(double *__restrict__ x, long long count, double f) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) x[i] *= f;
+}
+
+__global__ void weights_kernel(const double *__restrict__ logw, const int *__restrict__ alive, long long B,
+                               double *__restrict__ w) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) w[b] = (!alive || alive[b] == 1) ? exp(logw[b]) : 0.0;
+}
+
+// avg[e] += sum_b w[b] * max(seq[b][e], 1e-300)   (core.py:1362-1366 applied to stored sequences)
+__global__ void accumulate_kernel(const double *__restrict__ seq, const double *__restrict__ w, long long B,
+                                  long long count, double *__restrict__ avg) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    double s = 0.0;
+    for (long long b = 0; b < B; ++b) {
+        const double wb = __ldg(w + b);
+        if (wb > 0.0) {
+            const double v = __ldcs(seq + b * count + e);
+            s = fma(wb, v < kTiny ? kTiny : v, s);
+        }
+    }
+    avg[e] += s;
+}
+
+// One CTA per row t: optional normalisation by the row sum (core.py:1379-1382) and posterior means
+// mean_p[t] = sum_g post[t][g] * coord_p[g]  (core.py:480-483, :1416-1419)
+__global__ void __launch_bounds__(256) finalize_kernel(double *__restrict__ seq, long long T, int G, int n1, int ndim,
+                                                       const double *__restrict__ c0, const double *__restrict__ c1,
+                                                       double *__restrict__ means, int normalize) {
+    __shared__ double scratch[6 * kMaxWarps];
+    RedScratch rs;
+    rs.buf = scratch;
+    rs.phase = 0;
+    for (long long t = blockIdx.x; t < T; t += gridDim.x) {
+        double *row = seq + t * (long long)G;
+        double inv = 1.0;
+        if (normalize) {
+            double part = 0.0;
+            for (int g = threadIdx.x; g < G; g += blockDim.x) part += row[g];
+            inv = 1.0 / block_sum(part, rs);
+        }
+        double m0 = 0.0, m1 = 0.0;
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            double v = row[g];
+            if (normalize) {
+                v *= inv;
+                row[g] = v;
+            }
+            const int i0 = g / n1;
+            m0 = fma(v, __ldg(c0 + i0), m0);
+            if (ndim == 2) m1 = fma(v, __ldg(c1 + (g - i0 * n1)), m1);
+        }
+        if (means) {
+            block_sum2(m0, m1, rs);
+            if (threadIdx.x == 0) {
+                means[t] = m0;
+                if (ndim == 2) means[T + t] = m1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace blg

@@ -1,0 +1,67 @@
+"""The C-ABI libraries load and export every symbol include/blgrid.h declares (no compute calls, no GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ORACLE_SO, ROOT, build_oracle
+
+HEADER = os.path.join(ROOT, 'include', 'blgrid.h')
+CUDA_SO = os.path.join(ROOT, 'bayesloop_b200', 'csrc', 'libblgrid.so')
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(blg_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_symbols()
+    for must in ('blg_version', 'blg_last_error', 'blg_backend', 'blg_plan_create', 'blg_plan_destroy', 'blg_forward',
+                 'blg_backward', 'blg_accumulate', 'blg_scale', 'blg_finalize', 'blg_mix', 'blg_launch_count'):
+        assert must in names
+
+
+def _ensure_cuda_lib():
+    if not os.path.exists(CUDA_SO):
+        import sys
+        subprocess.check_call([sys.executable, os.path.join(ROOT, '__graft_entry__.py')])
+    return CUDA_SO
+
+
+@pytest.mark.parametrize('which', ['cuda', 'oracle'])
+def test_library_exports_every_declared_symbol(which):
+    path = _ensure_cuda_lib() if which == 'cuda' else build_oracle()
+    lib = ctypes.CDLL(path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), '{} does not export {}'.format(os.path.basename(path), name)
+    lib.blg_version.restype = ctypes.c_int
+    lib.blg_backend.restype = ctypes.c_char_p
+    assert lib.blg_version() == 1
+    backend = lib.blg_backend().decode()
+    assert backend == ('cuda:sm_100a' if which == 'cuda' else 'cpu-oracle')
+
+
+def test_cuda_library_contains_sm100a_sass_with_bulk_copies():
+    """SASS evidence that the hot path is Blackwell-native: sm_100a cubin with UBLKCP (cp.async.bulk) in the
+    resident kernels, and no PTX-only fallback."""
+    cuobjdump = '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    out = subprocess.run([cuobjdump, '-sass', _ensure_cuda_lib()], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+    assert 'UBLKCP' in out, 'bulk-async copy instructions missing from the SASS'
+    assert 'fwd_resident_kernel' in out and 'bwd_resident_kernel' in out
+
+
+def test_product_fails_loudly_without_cuda(monkeypatch):
+    import torch
+    from bayesloop_b200 import engine
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    engine.set_default_engine(None)
+    with pytest.raises(engine.EngineError):
+        engine.default_engine()

@@ -1,0 +1,64 @@
+"""N > 1 path on CPU: two gloo ranks shard a HyperStudy's combinations, run them through the CPU oracle engine and
+merge (all-gather of evidences, max + sum all-reduce of the running average).  Result must equal the golden."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, name, out_dir):
+    import torch.distributed as td
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    td.init_process_group('gloo', rank=rank, world_size=world)
+    import bayesloop_b200 as bl
+    import parity
+    from bayesloop_b200 import engine
+    from conftest import ORACLE_SO
+    engine.set_default_engine(engine.Engine(ORACLE_SO, 'cpu'))
+    S, got = parity.run_case(name, bl)
+    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), shard=np.array(S.sweepStats['shard']), **got)
+    td.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _run(name, tmp_path, world=2):
+    from conftest import build_oracle
+    build_oracle()
+    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    return [dict(np.load(os.path.join(str(tmp_path), 'rank%d.npz' % r))) for r in range(world)]
+
+
+def test_two_ranks_reproduce_the_golden_hyperstudy(tmp_path):
+    import parity
+    from conftest import load_golden
+    name = 'syn_hyper_poisson_sweep'
+    ranks = _run(name, tmp_path)
+    want = load_golden(name)
+    assert [tuple(r['shard']) for r in ranks] == [(0, 6), (6, 12)]
+    for r in ranks:
+        r.pop('shard')
+        parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)
+
+
+def test_two_ranks_changepoint_study_with_uneven_shards(tmp_path):
+    import parity
+    from conftest import load_golden
+    name = 'ref_cps_coal_all'  # 109 combos -> 55 + 54
+    ranks = _run(name, tmp_path)
+    want = load_golden(name)
+    assert [tuple(r['shard']) for r in ranks] == [(0, 55), (55, 109)]
+    for r in ranks:
+        r.pop('shard')
+        parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)

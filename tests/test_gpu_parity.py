@@ -1,0 +1,121 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA library, reached through the public API and the
+C ABI, against (1) the golden vectors of the unmodified reference, (2) the CPU oracle on seeded mid-size inputs,
+(3) size-independent properties at larger sizes.
+
+Tolerances (BASELINE.json north_star: 1e-6 relative in fp64): log-evidences 1e-9 relative; posterior grids 1e-6
+relative with an absolute floor of 1e-12 x the per-time-step maximum (cells far in the tails carry rounding noise of
+different summation orders)."""
+import numpy as np
+import pytest
+
+import cases
+import helpers
+import parity
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('name', sorted(cases.CASES))
+def test_case_matches_reference_golden(name, use_cuda):
+    import bayesloop_b200 as bl
+    before = use_cuda.launch_count()
+    S, got = parity.run_case(name, bl)
+    assert use_cuda.launch_count() > before, 'no CUDA kernel was launched'
+    parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)
+    want = float(load_golden(name)['logEvidence'])
+    if np.isfinite(want):
+        assert abs(float(got['logEvidence']) - want) <= 1e-9 * abs(want)
+
+
+def _poisson(bl, engine, B, T, G, smax, seed=1, extra=None):
+    rng = np.random.default_rng(seed)
+    lam = 3 + 2 * np.sin(2 * np.pi * np.arange(T) / 200.)
+    S = bl.HyperStudy(silent=True, engine=engine)
+    S.loadData(rng.poisson(lam).astype(float), silent=True)
+    T_ = bl.tm.GaussianRandomWalk('sigma', bl.cint(0, smax, B), target='rate')
+    if extra is not None:
+        T_ = bl.tm.CombinedTransitionModel(T_, extra(bl))
+    S.set(bl.om.Poisson('rate', bl.oint(0, 12, G)), T_, silent=True)
+    return S
+
+
+def _gauss2d(bl, engine, n0, n1, T, hb, seed=2):
+    rng = np.random.default_rng(seed)
+    mu = np.cumsum(rng.normal(0, 0.03, T))
+    S = bl.HyperStudy(silent=True, engine=engine)
+    S.loadData(rng.normal(mu, 1.0), silent=True)
+    S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, n0), 'std', bl.oint(0, 3, n1)),
+          bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.3, hb), target='mean'),
+                                        bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.2, hb), target='std')),
+          silent=True)
+    return S
+
+
+CONFIGS = {
+    'poisson_c2_small': lambda bl, e: _poisson(bl, e, B=24, T=300, G=1000, smax=0.2),
+    'poisson_wide_kernels': lambda bl, e: _poisson(bl, e, B=6, T=60, G=1000, smax=1.0),
+    'poisson_regime': lambda bl, e: _poisson(bl, e, B=8, T=200, G=500, smax=0.1,
+                                             extra=lambda bl: bl.tm.RegimeSwitch('p', -5)),
+    'poisson_odd_grid': lambda bl, e: _poisson(bl, e, B=5, T=100, G=333, smax=0.3),
+    'gauss_2d_64x48': lambda bl, e: _gauss2d(bl, e, 64, 48, T=80, hb=3),
+    'gauss_2d_100x100': lambda bl, e: _gauss2d(bl, e, 100, 100, T=30, hb=2),
+}
+
+
+@pytest.mark.parametrize('name', sorted(CONFIGS))
+@pytest.mark.parametrize('mode', ['full', 'forwardOnly', 'evidenceOnly'])
+def test_cuda_matches_cpu_oracle(name, mode, cuda_engine, oracle_engine):
+    import bayesloop_b200 as bl
+    kw = dict(forwardOnly=(mode == 'forwardOnly'), evidenceOnly=(mode == 'evidenceOnly'))
+    got = helpers.abi_sweep(cuda_engine, CONFIGS[name](bl, cuda_engine), **kw)
+    want = helpers.abi_sweep(oracle_engine, CONFIGS[name](bl, oracle_engine), **kw)
+    np.testing.assert_array_equal(got['alive'], want['alive'])
+    np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-10)
+    np.testing.assert_allclose(got['local'], want['local'], rtol=1e-7)
+    np.testing.assert_allclose(got['localEvidence'], want['localEvidence'], rtol=1e-7)
+    if mode != 'evidenceOnly':
+        rowmax = want['avg'].max(axis=1, keepdims=True)
+        assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-6 * np.abs(want['avg']) + 1e-12 * rowmax)
+        np.testing.assert_allclose(got['means'], want['means'], rtol=1e-8)
+
+
+def test_study_fit_matches_oracle_on_long_series(cuda_engine, oracle_engine):
+    """Study.fit (B = 1, smoothed posteriors stored in place) on T = 2000."""
+    import bayesloop_b200 as bl
+    rng = np.random.default_rng(5)
+    data = rng.poisson(3 + 2 * np.sin(np.arange(2000) / 40.)).astype(float)
+    out = []
+    for eng in (cuda_engine, oracle_engine):
+        S = bl.Study(silent=True, engine=eng)
+        S.loadData(data, silent=True)
+        S.set(bl.om.Poisson('rate', bl.oint(0, 12, 400)), bl.tm.GaussianRandomWalk('sigma', 0.08, target='rate'),
+              silent=True)
+        S.fit(silent=True)
+        out.append(S)
+    got, want = out
+    assert abs(got.logEvidence - want.logEvidence) <= 1e-10 * abs(want.logEvidence)
+    np.testing.assert_allclose(got.posteriorMeanValues, want.posteriorMeanValues, rtol=1e-9)
+    rowmax = want.posteriorSequence.max(axis=1, keepdims=True)
+    assert np.all(np.abs(got.posteriorSequence - want.posteriorSequence)
+                  <= 1e-6 * want.posteriorSequence + 1e-12 * rowmax)
+    np.testing.assert_allclose(got.localEvidence, want.localEvidence, rtol=1e-7)
+
+
+def test_properties_at_scale(cuda_engine):
+    """C2-shaped sweep (G = 1000, 256 combos, T = 1500) too big for the CPU oracle in seconds: size-independent
+    properties.  (a) averaged posterior rows are distributions; (b) evidence-only and full sweeps agree on every
+    log-evidence; (c) a combo's evidence does not depend on the batch it runs in; (d) deterministic re-run."""
+    import bayesloop_b200 as bl
+    S = _poisson(bl, cuda_engine, B=256, T=1500, G=1000, smax=0.2)
+    full = helpers.abi_sweep(cuda_engine, S)
+    assert np.all(full['alive'] == 1)
+    np.testing.assert_allclose(full['avg'].sum(axis=1), 1.0, rtol=1e-12)
+    assert np.all(full['avg'] >= 0)
+    evo = helpers.abi_sweep(cuda_engine, _poisson(bl, cuda_engine, B=256, T=1500, G=1000, smax=0.2), evidenceOnly=True)
+    np.testing.assert_array_equal(full['logE'], evo['logE'])
+    sub = helpers.abi_sweep(cuda_engine, _poisson(bl, cuda_engine, B=2, T=1500, G=1000, smax=0.2), evidenceOnly=True)
+    np.testing.assert_allclose([full['logE'][0], full['logE'][-1]], sub['logE'], rtol=1e-13)
+    again = helpers.abi_sweep(cuda_engine, _poisson(bl, cuda_engine, B=256, T=1500, G=1000, smax=0.2))
+    np.testing.assert_array_equal(full['logE'], again['logE'])
+    np.testing.assert_allclose(full['avg'], again['avg'], rtol=1e-12, atol=1e-300)  # fp64 atomics: order may vary
