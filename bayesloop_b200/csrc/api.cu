@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "aux.cuh"
+#include "fast1d.cuh"
 #include "resident.cuh"
 
 using namespace blg;
@@ -270,9 +271,51 @@ bool resident_layout(const blg_plan *pl, const blg_program &pg, bool backward, b
     return lay.bytes <= kSmemLimit;
 }
 
+// Fast path (fast1d.cuh): 1-D grid, program = one GaussianRandomWalk, halo <= n, one work item per thread.
+bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, PassArgs &a, Layout &lay) {
+    const DevProblem &d = pl->dev;
+    if (getenv("BLG_NO_FAST1D")) return false;
+    if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
+    const int halo = even_up(pg.max_radius[0] + 2 * kConvM);
+    const int items = (d.G + kConvM - 1) / kConvM;
+    if (halo > d.G || items > 1024) return false;
+    a.halo = halo;
+    a.Gp = even_up(d.G);
+    a.n0p = even_up(d.n0);
+    a.n1p = 2;
+    const int pitch = a.Gp + 2 * halo;
+    int off = 2 * pitch;
+    a.off_stage = -1;
+    if (backward) {
+        a.off_stage = off;
+        off += a.Gp;
+    }
+    a.off_tab = off;
+    off += 3 * a.n0p;
+    a.off_w = off;
+    const int taps = 2 * pg.max_radius[0] + 1;
+    a.pg.w_off[0] = 0;
+    a.pg.w_len[0] = even_up(((taps + kConvM - 1) / kConvM) * kConvM + kConvM);
+    off += a.pg.w_len[0];
+    a.off_misc = even_up(off);
+    lay.bytes = (size_t)(a.off_misc + kMiscDoubles) * sizeof(double);
+    int nt = (items + 31) / 32 * 32;
+    if (nt < 64) nt = 64;
+    lay.nt = nt;
+    return lay.bytes <= kSmemLimit;
+}
+
 template <typename K>
-int launch_resident(K kernel, const PassArgs &a, const Layout &lay, long long B, cudaStream_t st) {
+int launch_resident(K kernel, const PassArgs &a, const Layout &lay, long long B, cudaStream_t st, const char *name) {
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+    // several CTAs (combos) must share an SM: ask for the full shared-memory carveout
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (getenv("BLG_VERBOSE")) {
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, lay.nt, lay.bytes);
+        fprintf(stderr, "[blgrid] %s: grid %lld x %d threads, %zu B smem/CTA, %d CTA/SM, halo %d, bulk %d\n", name, B,
+                lay.nt, lay.bytes, occ, a.halo, a.use_bulk);
+    }
     kernel<<<(unsigned)B, lay.nt, lay.bytes, st>>>(a);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -336,13 +379,21 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
     Layout lay;
+    const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
+    if (fast1d_layout(pl, in->prog, false, a, lay)) {
+        a.use_bulk = bulkOk ? 1 : 0;
+        a.serpentine = 0;
+        if (lay.nt <= 256) return launch_resident(fwd_fast1d_kernel<256, 4>, a, lay, in->B, st, "fwd_fast1d");
+        if (lay.nt <= 512) return launch_resident(fwd_fast1d_kernel<512, 2>, a, lay, in->B, st, "fwd_fast1d");
+        return launch_resident(fwd_fast1d_kernel<1024, 1>, a, lay, in->B, st, "fwd_fast1d");
+    }
+    a.halo = 0;
     if (!resident_layout(pl, in->prog, false, false, a, lay))
         return fail("grid / kernel radius too large for the shared-memory resident forward kernel");
-    a.use_bulk = (store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0)) ? 1 : 0;
-    if (getenv("BLG_NO_BULK")) a.use_bulk = 0;
-    if (lay.nt <= 256) return launch_resident(fwd_resident_kernel<256, 4>, a, lay, in->B, st);
-    if (lay.nt <= 512) return launch_resident(fwd_resident_kernel<512, 2>, a, lay, in->B, st);
-    return launch_resident(fwd_resident_kernel<1024, 1>, a, lay, in->B, st);
+    a.use_bulk = bulkOk ? 1 : 0;
+    if (lay.nt <= 256) return launch_resident(fwd_resident_kernel<256, 4>, a, lay, in->B, st, "fwd_resident");
+    if (lay.nt <= 512) return launch_resident(fwd_resident_kernel<512, 2>, a, lay, in->B, st, "fwd_resident");
+    return launch_resident(fwd_resident_kernel<1024, 1>, a, lay, in->B, st, "fwd_resident");
 }
 
 int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {
@@ -358,15 +409,23 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     if (fill_args(pl, in, out, flags, a)) return -1;
     Layout lay;
     const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
+    if (fast1d_layout(pl, in->prog, true, a, lay)) {
+        a.use_bulk = alignedRows ? 1 : 0;
+        a.serpentine = 0;
+        if (lay.nt <= 256) return launch_resident(bwd_fast1d_kernel<256, 4>, a, lay, in->B, st, "bwd_fast1d");
+        if (lay.nt <= 512) return launch_resident(bwd_fast1d_kernel<512, 2>, a, lay, in->B, st, "bwd_fast1d");
+        return launch_resident(bwd_fast1d_kernel<1024, 1>, a, lay, in->B, st, "bwd_fast1d");
+    }
+    a.halo = 0;
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
     if (!fits) {
         if (!resident_layout(pl, in->prog, true, false, a, lay))
             return fail("grid / kernel radius too large for the shared-memory resident backward kernel");
     }
     a.use_bulk = (fits && a.off_stage >= 0) ? 1 : 0;
-    if (lay.nt <= 256) return launch_resident(bwd_resident_kernel<256, 4>, a, lay, in->B, st);
-    if (lay.nt <= 512) return launch_resident(bwd_resident_kernel<512, 2>, a, lay, in->B, st);
-    return launch_resident(bwd_resident_kernel<1024, 1>, a, lay, in->B, st);
+    if (lay.nt <= 256) return launch_resident(bwd_resident_kernel<256, 4>, a, lay, in->B, st, "bwd_resident");
+    if (lay.nt <= 512) return launch_resident(bwd_resident_kernel<512, 2>, a, lay, in->B, st, "bwd_resident");
+    return launch_resident(bwd_resident_kernel<1024, 1>, a, lay, in->B, st, "bwd_resident");
 }
 
 int blg_accumulate(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {

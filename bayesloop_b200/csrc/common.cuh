@@ -72,6 +72,7 @@ struct PassArgs {
     int use_bulk;        // 1: bulk-async copies allowed (G even, 16-byte aligned rows)
     int serpentine;      // 1: blockIdx -> combo mapping alternates direction per 148-block wave
     int num_sms;
+    int halo;            // fast 1-D kernels: reflected halo cells on each side of the state (0 = generic kernels)
 };
 
 // ------------------------------------------------------------------------------------------------ reductions

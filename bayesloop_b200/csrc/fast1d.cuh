@@ -1,0 +1,318 @@
+// fast1d.cuh -- K1f/K2f: specialisation of the resident kernels for the headline shape of the sweep: a 1-D grid and
+// a transition program that is ONE GaussianRandomWalk (BASELINE.json configs[0], configs[1]).
+//
+// Differences to the generic resident kernels (resident.cuh):
+//   * the state lives in shared memory WITH a reflected halo on both sides (every writer mirrors the cells near
+//     the edges), so the convolution inner loop is one LDS + M FMAs per tap with no boundary logic at all;
+//   * each thread owns M consecutive cells for the whole kernel; the convolution outputs stay in REGISTERS and are
+//     consumed in place by the likelihood multiply (forward) / the posterior product (backward), so a time step
+//     needs two CTA barriers only (reduction; state visible) instead of four to six;
+//   * forward: alpha[t] leaves through one bulk-async (TMA) store per step that overlaps the next convolution;
+//     backward: alpha[t] arrives through a double-buffered bulk-async prefetch (mbarrier complete_tx);
+//   * backward: the normalisation of beta rides on the same reduction as sum(alpha*beta) (block_sum2).
+// Semantics are identical (core.py:372-417, :424-470; transitionModels.py:96-115).
+#pragma once
+
+#include "common.cuh"
+
+namespace blg {
+
+// write v to cell i of a haloed line and to its mirror images inside the halo (valid for halo <= n)
+__device__ __forceinline__ void store_mirrored(double *line, int i, int n, int halo, double v) {
+    line[i] = v;
+    if (i < halo) line[-1 - i] = v;
+    if (i >= n - halo) line[2 * n - 1 - i] = v;
+}
+
+template <int M>
+__device__ __forceinline__ void conv_item(const double *__restrict__ line, int i0, int R, const double *__restrict__ W,
+                                          double (&acc)[M]) {
+    const double *p = line + (i0 - R);
+    double win[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        win[m] = p[m];
+        acc[m] = 0.0;
+    }
+    p += M;
+    const int taps = 2 * R + 1;
+    for (int j0 = 0; j0 < taps; j0 += M) {
+#pragma unroll
+        for (int u = 0; u < M; ++u) {
+            const double wt = W[j0 + u];
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc[m] = fma(wt, win[(u + m) % M], acc[m]);
+            win[u] = p[u];
+        }
+        p += M;
+    }
+}
+
+struct Fast1dSetup {
+    double *buf0, *buf1;  // interior pointers of the two haloed state buffers
+    double *W;
+    LikTables tb;
+    RedScratch rs;
+    double sigma;
+    int R, f_lo, f_hi, b_lo, b_hi;
+};
+
+__device__ __forceinline__ void fast1d_setup(const PassArgs &a, double *sm, long long b, Fast1dSetup &s) {
+    const DevProblem &pb = a.pb;
+    const int halo = a.halo, pitch = a.Gp + 2 * halo;
+    s.buf0 = sm + halo;
+    s.buf1 = sm + pitch + halo;
+    double *tab = sm + a.off_tab;
+    double *A0 = tab, *A1 = A0 + a.n0p, *A2 = A1 + a.n0p;
+    for (int i = threadIdx.x; i < pb.n0; i += blockDim.x) {
+        A0[i] = pb.tabA[0] ? pb.tabA[0][i] : 0.0;
+        A1[i] = pb.tabA[1] ? pb.tabA[1][i] : 0.0;
+        A2[i] = pb.tabA[2] ? pb.tabA[2][i] : 0.0;
+    }
+    s.tb.A0 = A0;
+    s.tb.A1 = A1;
+    s.tb.A2 = A2;
+    s.tb.B0 = A0;
+    s.tb.B1 = A0;
+    s.rs.buf = sm + a.off_misc;
+    s.rs.phase = 0;
+    s.W = sm + a.off_w;
+    s.sigma = a.pg.param[b];
+    s.R = a.pg.radius[b];
+    const int *win = a.pg.window + b * 4;
+    s.f_lo = win[0];
+    s.f_hi = win[1];
+    s.b_lo = win[2];
+    s.b_hi = win[3];
+    if (!(s.sigma > 0.0) || s.R <= 0) {  // transitionModels.py:110-113: identity
+        s.R = 0;
+        for (int j = threadIdx.x; j < a.pg.w_len[0]; j += blockDim.x) s.W[j] = j == 0 ? 1.0 : 0.0;
+        __syncthreads();
+    } else {
+        build_weights(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1f forward
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) {
+    constexpr int M = kConvM;
+    extern __shared__ __align__(16) double sm[];
+    const DevProblem &pb = a.pb;
+    const long long b = blockIdx.x;
+    const int n = pb.G, halo = a.halo;
+    const long long T = a.T;
+    Fast1dSetup s;
+    fast1d_setup(a, sm, b, s);
+    if (2 * s.R + 1 + M > a.pg.w_len[0]) {  // radius beyond blg_program.max_radius
+        if (threadIdx.x == 0) {
+            a.logE[b] = NAN;
+            if (a.alive) a.alive[b] = -2;
+        }
+        return;
+    }
+    const int i0 = threadIdx.x * M;
+    const bool owner = i0 < n;
+    const bool service = threadIdx.x == blockDim.x - 1;
+    double *cur = s.buf0, *nxt = s.buf1;
+    {
+        const double *init = (a.flags & BLG_F_INIT_STATE) ? a.init_state + b * (long long)n : a.prior;
+        for (int g = threadIdx.x; g < n; g += blockDim.x) store_mirrored(cur, g, n, halo, init[g]);
+    }
+    __syncthreads();
+
+    const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
+    const bool bulk = store && a.use_bulk;
+    double *seq = store ? a.alpha_seq + b * T * (long long)n : nullptr;
+    const int nce = pb.ncols_eff;
+    double logE = 0.0;
+    bool dead = false;
+
+    for (long long t = 0; t < T; ++t) {
+        double v[M];
+        const bool trans = (t > 0 || (a.flags & BLG_F_TRANSITION_FIRST)) && (t - 1 >= s.f_lo) && (t - 1 < s.f_hi);
+        if (owner) {
+            if (trans && s.R > 0) {
+                conv_item<M>(cur, i0, s.R, s.W, v);  // transitionModels.py:111
+            } else {
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[m] = cur[i0 + m];
+            }
+        }
+        // alpha <- prior * likelihood; norm = sum(alpha)          core.py:375-385
+        double part = 0.0;
+        if (owner) {
+            const StepC *sc = a.steps + t * nce;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int li = i0 + m;
+                if (li < n) {
+                    const double lik = pb.om_kind == BLG_OM_TABLE ? __ldg(a.lik_table + t * (long long)n + li)
+                                                                  : lik_cell(pb, s.tb, sc, li, 0);
+                    v[m] *= lik;
+                    part += v[m];
+                } else {
+                    v[m] = 0.0;
+                }
+            }
+        }
+        if (bulk && service && t >= 2) bulk_wait_read<1>();  // the store of step t-2 has released `nxt`
+        const double norm = block_sum(part, s.rs);
+        if (!(norm > 0.0)) {  // core.py:388-400
+            dead = true;
+            break;
+        }
+        const double inv = 1.0 / norm;
+        if (owner) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int li = i0 + m;
+                if (li < n) {
+                    const double x = v[m] * inv;
+                    store_mirrored(nxt, li, n, halo, x);
+                    if (store && !bulk) __stcs(seq + t * (long long)n + li, x);  // core.py:408
+                }
+            }
+        }
+        if (service) {
+            logE += log(norm);                                    // core.py:403
+            if (a.local) a.local[b * T + t] = norm * pb.lc_prod;  // core.py:404
+        }
+        if (bulk) fence_proxy_async();
+        __syncthreads();
+        if (bulk && service) bulk_store(seq + t * (long long)n, nxt, (uint32_t)(n * sizeof(double)));  // core.py:408
+        double *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+    if (bulk && service) bulk_wait_all();
+    if (!dead && (a.flags & BLG_F_SAVE_STATE) && a.final_state) {
+        double *fs = a.final_state + b * (long long)n;
+        for (int g = threadIdx.x; g < n; g += blockDim.x) fs[g] = cur[g];
+    }
+    if (service) {
+        if (dead)
+            logE = -INFINITY;
+        else if (!(a.flags & BLG_F_INIT_STATE))
+            logE += log(pb.lc_prod);  // core.py:417
+        a.logE[b] = logE;
+        if (a.alive) a.alive[b] = dead ? 0 : 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K2f backward
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) {
+    constexpr int M = kConvM;
+    extern __shared__ __align__(16) double sm[];
+    const DevProblem &pb = a.pb;
+    const long long b = blockIdx.x;
+    if (a.alive && a.alive[b] != 1) return;  // the forward pass aborted (core.py:400)
+    const int n = pb.G, halo = a.halo;
+    const long long T = a.T;
+    Fast1dSetup s;
+    fast1d_setup(a, sm, b, s);
+    if (2 * s.R + 1 + M > a.pg.w_len[0]) return;
+    const int i0 = threadIdx.x * M;
+    const bool owner = i0 < n;
+    const bool service = threadIdx.x == blockDim.x - 1;
+    const bool acc = (a.flags & BLG_F_ACCUMULATE) != 0;
+    const double wgt = acc ? exp(a.log_weight[b]) : 0.0;
+    double *cur = s.buf0;
+    double *seq = a.alpha_seq + b * T * (long long)n;
+    const bool staged = a.use_bulk != 0;
+    double *S[2] = {s.buf1, sm + a.off_stage};  // staging buffers (the second state buffer is free in this pass)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
+    uint32_t ph[2] = {0u, 0u};
+    const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
+    if (staged) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            fence_proxy_async();
+        }
+        __syncthreads();
+        if (service) {
+            bulk_load(S[(T - 1) & 1], seq + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) & 1]);
+            if (T >= 2) bulk_load(S[(T - 2) & 1], seq + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) & 1]);
+        }
+    }
+    const int nce = pb.ncols_eff;
+    double beta[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) beta[m] = (owner && i0 + m < n) ? 1.0 / (double)n : 0.0;  // core.py:424-425
+    bool dead = false;
+    long long i = T - 1;
+
+    for (; i >= 0; --i) {
+        const int sb = (int)(i & 1);
+        const double *A;
+        if (staged) {
+            mbar_wait(&bars[sb], ph[sb]);
+            ph[sb] ^= 1u;
+            A = S[sb];
+        } else {
+            A = seq + i * (long long)n;
+        }
+        double al[M];
+        double pab = 0.0, pb_ = 0.0;
+        if (owner) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int li = i0 + m;
+                al[m] = li < n ? A[li] : 0.0;
+                pab = fma(al[m], beta[m], pab);
+                pb_ += beta[m];
+            }
+        }
+        block_sum2(pab, pb_, s.rs);       // sum(alpha*beta) and sum(beta) in one barrier
+        const double binv = 1.0 / pb_;     // core.py:470 (normalisation of beta, applied lazily)
+        if (!(pab * binv > 0.0)) {         // core.py:440-452
+            dead = true;
+            break;
+        }
+        const double inv = 1.0 / pab;      // posterior = alpha*beta / sum(alpha*beta): the scale of beta cancels
+        double q = 0.0;
+        if (owner) {
+            const StepC *sc = a.steps + i * nce;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int li = i0 + m;
+                if (li < n) {
+                    const double p = al[m] * beta[m] * inv;                                     // core.py:436-441
+                    const double lik = pb.om_kind == BLG_OM_TABLE ? __ldg(a.lik_table + i * (long long)n + li)
+                                                                  : lik_cell(pb, s.tb, sc, li, 0);  // core.py:455
+                    q += p / lik;                                                               // core.py:463
+                    if (acc) {
+                        if (wgt > 0.0) atomicAdd(a.avg + i * (long long)n + li, wgt * (p < kTiny ? kTiny : p));
+                    } else {
+                        __stcs(seq + i * (long long)n + li, p);
+                    }
+                    store_mirrored(cur, li, n, halo, beta[m] * binv * lik);  // core.py:467: beta*likelihood
+                }
+            }
+        }
+        q = block_sum(q, s.rs);  // also publishes the new state for the convolution
+        if (staged && service && i >= 2) bulk_load(S[sb], seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
+        if (service && a.local) a.local[b * T + i] = 1.0 / (q * pb.lc_prod);
+        const bool trans = (i >= s.b_lo) && (i < s.b_hi);
+        if (owner) {
+            if (trans && s.R > 0) {
+                conv_item<M>(cur, i0, s.R, s.W, beta);  // transitionModels.py:117-118
+            } else {
+#pragma unroll
+                for (int m = 0; m < M; ++m) beta[m] = i0 + m < n ? cur[i0 + m] : 0.0;
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                if (i0 + m >= n) beta[m] = 0.0;
+        }
+    }
+    if (dead && staged && i >= 1) mbar_wait(&bars[(i - 1) & 1], ph[(i - 1) & 1]);  // drain the prefetch in flight
+    if (dead && service) {
+        a.logE[b] = -INFINITY;
+        if (a.alive) a.alive[b] = -1;
+    }
+}
+
+}  // namespace blg
