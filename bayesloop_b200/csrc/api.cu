@@ -272,12 +272,12 @@ bool resident_layout(const blg_plan *pl, const blg_program &pg, bool backward, b
 }
 
 // Fast path (fast1d.cuh): 1-D grid, program = one GaussianRandomWalk, halo <= n, one work item per thread.
-bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, PassArgs &a, Layout &lay) {
+bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int M, PassArgs &a, Layout &lay) {
     const DevProblem &d = pl->dev;
     if (getenv("BLG_NO_FAST1D")) return false;
     if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
-    const int halo = even_up(pg.max_radius[0] + 2 * kConvM);
-    const int items = (d.G + kConvM - 1) / kConvM;
+    const int halo = even_up(pg.max_radius[0] + 2 * M);
+    const int items = (d.G + M - 1) / M;
     if (halo > d.G || items > 1024) return false;
     a.halo = halo;
     a.Gp = even_up(d.G);
@@ -295,7 +295,7 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, Pas
     a.off_w = off;
     const int taps = 2 * pg.max_radius[0] + 1;
     a.pg.w_off[0] = 0;
-    a.pg.w_len[0] = even_up(((taps + kConvM - 1) / kConvM) * kConvM + kConvM);
+    a.pg.w_len[0] = ((taps + M - 1) / M + 1) * (M + 1);  // chunk-padded layout of conv_item (fast1d.cuh)
     off += a.pg.w_len[0];
     a.off_misc = even_up(off);
     lay.bytes = (size_t)(a.off_misc + kMiscDoubles) * sizeof(double);
@@ -303,6 +303,12 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, Pas
     if (nt < 64) nt = 64;
     lay.nt = nt;
     return lay.bytes <= kSmemLimit;
+}
+
+int fast_m() {
+    const char *e = getenv("BLG_FAST_M");
+    const int m = e ? atoi(e) : 7;
+    return (m == 5 || m == 9) ? m : 7;
 }
 
 template <typename K>
@@ -340,6 +346,7 @@ int fill_args(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32
     a.pg.param = pg.param;
     a.pg.radius = pg.radius;
     a.pg.window = pg.window;
+    a.order = getenv("BLG_NO_ORDER") ? nullptr : pg.order;
     a.T = in->T;
     a.B = in->B;
     a.prior = in->prior;
@@ -380,12 +387,19 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     if (fill_args(pl, in, out, flags, a)) return -1;
     Layout lay;
     const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
-    if (fast1d_layout(pl, in->prog, false, a, lay)) {
+    const int M = fast_m();
+    if (fast1d_layout(pl, in->prog, false, M, a, lay)) {
         a.use_bulk = bulkOk ? 1 : 0;
-        a.serpentine = 0;
-        if (lay.nt <= 256) return launch_resident(fwd_fast1d_kernel<256, 4>, a, lay, in->B, st, "fwd_fast1d");
-        if (lay.nt <= 512) return launch_resident(fwd_fast1d_kernel<512, 2>, a, lay, in->B, st, "fwd_fast1d");
-        return launch_resident(fwd_fast1d_kernel<1024, 1>, a, lay, in->B, st, "fwd_fast1d");
+#define BLG_FWD_FAST(MM)                                                                                           \
+    if (M == MM) {                                                                                                 \
+        if (lay.nt <= 160) return launch_resident(fwd_fast1d_kernel<MM, 160, 4>, a, lay, in->B, st, "fwd_fast1d"); \
+        if (lay.nt <= 256) return launch_resident(fwd_fast1d_kernel<MM, 256, 4>, a, lay, in->B, st, "fwd_fast1d"); \
+        return launch_resident(fwd_fast1d_kernel<MM, 1024, 1>, a, lay, in->B, st, "fwd_fast1d");                   \
+    }
+        BLG_FWD_FAST(5)
+        BLG_FWD_FAST(7)
+        BLG_FWD_FAST(9)
+#undef BLG_FWD_FAST
     }
     a.halo = 0;
     if (!resident_layout(pl, in->prog, false, false, a, lay))
@@ -409,12 +423,19 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     if (fill_args(pl, in, out, flags, a)) return -1;
     Layout lay;
     const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
-    if (fast1d_layout(pl, in->prog, true, a, lay)) {
+    const int M = fast_m();
+    if (fast1d_layout(pl, in->prog, true, M, a, lay)) {
         a.use_bulk = alignedRows ? 1 : 0;
-        a.serpentine = 0;
-        if (lay.nt <= 256) return launch_resident(bwd_fast1d_kernel<256, 4>, a, lay, in->B, st, "bwd_fast1d");
-        if (lay.nt <= 512) return launch_resident(bwd_fast1d_kernel<512, 2>, a, lay, in->B, st, "bwd_fast1d");
-        return launch_resident(bwd_fast1d_kernel<1024, 1>, a, lay, in->B, st, "bwd_fast1d");
+#define BLG_BWD_FAST(MM)                                                                                           \
+    if (M == MM) {                                                                                                 \
+        if (lay.nt <= 160) return launch_resident(bwd_fast1d_kernel<MM, 160, 4>, a, lay, in->B, st, "bwd_fast1d"); \
+        if (lay.nt <= 256) return launch_resident(bwd_fast1d_kernel<MM, 256, 4>, a, lay, in->B, st, "bwd_fast1d"); \
+        return launch_resident(bwd_fast1d_kernel<MM, 1024, 1>, a, lay, in->B, st, "bwd_fast1d");                   \
+    }
+        BLG_BWD_FAST(5)
+        BLG_BWD_FAST(7)
+        BLG_BWD_FAST(9)
+#undef BLG_BWD_FAST
     }
     a.halo = 0;
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);

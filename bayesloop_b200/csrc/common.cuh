@@ -72,8 +72,22 @@ struct PassArgs {
     int use_bulk;        // 1: bulk-async copies allowed (G even, 16-byte aligned rows)
     int serpentine;      // 1: blockIdx -> combo mapping alternates direction per 148-block wave
     int num_sms;
+    const int *order;    // device [B] launch order (descending cost) or NULL
     int halo;            // fast 1-D kernels: reflected halo cells on each side of the state (0 = generic kernels)
 };
+
+__device__ __forceinline__ long long combo_of_block(const PassArgs &a) {
+    long long j = blockIdx.x;
+    if (a.serpentine) {  // alternate direction per wave of num_sms blocks so cheap and expensive combos share an SM
+        const long long S = a.num_sms, wave = j / S, pos = j - wave * S;
+        if (wave & 1) {
+            const long long left = a.B - wave * S;
+            const long long cnt = left < S ? left : S;
+            j = wave * S + (cnt - 1 - pos);
+        }
+    }
+    return j;
+}
 
 // ------------------------------------------------------------------------------------------------ reductions
 struct RedScratch {

@@ -24,9 +24,15 @@ __device__ __forceinline__ void store_mirrored(double *line, int i, int n, int h
     if (i >= n - halo) line[2 * n - 1 - i] = v;
 }
 
+// Weights are stored in chunks of M taps padded to MP = M+1 doubles (16-byte aligned chunks), so one chunk is
+// fetched with (M-1)/2 LDS.128 + 1 LDS.64 broadcast loads instead of M LDS.64: the shared-memory pipe (one per SM,
+// 128 B/clk) stays below the FP64 pipe (64 FMA/clk/SM): per chunk 2*M wavefronts for the inputs + (M+1)/2 for the
+// weights against M*M/2 cycles of DFMA.
 template <int M>
 __device__ __forceinline__ void conv_item(const double *__restrict__ line, int i0, int R, const double *__restrict__ W,
                                           double (&acc)[M]) {
+    static_assert(M % 2 == 1, "M must be odd: lanes stride M doubles => conflict-free 64-bit shared loads");
+    constexpr int MP = M + 1;
     const double *p = line + (i0 - R);
     double win[M];
 #pragma unroll
@@ -35,17 +41,52 @@ __device__ __forceinline__ void conv_item(const double *__restrict__ line, int i
         acc[m] = 0.0;
     }
     p += M;
-    const int taps = 2 * R + 1;
-    for (int j0 = 0; j0 < taps; j0 += M) {
+    const int chunks = (2 * R + M) / M;  // ceil((2R+1)/M)
+    const double *wc = W;
+    for (int c = 0; c < chunks; ++c) {
+        double w[M];
+#pragma unroll
+        for (int k = 0; k < M / 2; ++k) {
+            const double2 t = reinterpret_cast<const double2 *>(wc)[k];
+            w[2 * k] = t.x;
+            w[2 * k + 1] = t.y;
+        }
+        w[M - 1] = wc[M - 1];
 #pragma unroll
         for (int u = 0; u < M; ++u) {
-            const double wt = W[j0 + u];
 #pragma unroll
-            for (int m = 0; m < M; ++m) acc[m] = fma(wt, win[(u + m) % M], acc[m]);
+            for (int m = 0; m < M; ++m) acc[m] = fma(w[u], win[(u + m) % M], acc[m]);
             win[u] = p[u];
         }
         p += M;
+        wc += MP;
     }
+}
+
+// Gaussian weights in the chunk-padded layout of conv_item (see build_weights in common.cuh for the formula).
+template <int M>
+__device__ __forceinline__ void build_weights_chunked(double *W, int len, double sigma, int R, RedScratch &rs) {
+    constexpr int MP = M + 1;
+    double part = 0.0;
+    if (!(sigma > 0.0) || R <= 0) {  // transitionModels.py:110-113: identity
+        for (int q = threadIdx.x; q < len; q += blockDim.x) W[q] = q == 0 ? 1.0 : 0.0;
+        __syncthreads();
+        return;
+    }
+    const double h = -0.5 / (sigma * sigma);
+    for (int q = threadIdx.x; q < len; q += blockDim.x) {
+        const int c = q / MP, u = q - c * MP, j = c * M + u;
+        double v = 0.0;
+        if (u < M && j <= 2 * R) {
+            const double x = (double)(j - R);
+            v = exp(h * x * x);
+        }
+        W[q] = v;
+        part += v;
+    }
+    const double inv = 1.0 / block_sum(part, rs);
+    for (int q = threadIdx.x; q < len; q += blockDim.x) W[q] *= inv;
+    __syncthreads();
 }
 
 struct Fast1dSetup {
@@ -57,6 +98,7 @@ struct Fast1dSetup {
     int R, f_lo, f_hi, b_lo, b_hi;
 };
 
+template <int M>
 __device__ __forceinline__ void fast1d_setup(const PassArgs &a, double *sm, long long b, Fast1dSetup &s) {
     const DevProblem &pb = a.pb;
     const int halo = a.halo, pitch = a.Gp + 2 * halo;
@@ -84,27 +126,21 @@ __device__ __forceinline__ void fast1d_setup(const PassArgs &a, double *sm, long
     s.f_hi = win[1];
     s.b_lo = win[2];
     s.b_hi = win[3];
-    if (!(s.sigma > 0.0) || s.R <= 0) {  // transitionModels.py:110-113: identity
-        s.R = 0;
-        for (int j = threadIdx.x; j < a.pg.w_len[0]; j += blockDim.x) s.W[j] = j == 0 ? 1.0 : 0.0;
-        __syncthreads();
-    } else {
-        build_weights(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
-    }
+    if (!(s.sigma > 0.0) || s.R <= 0) s.R = 0;
+    if ((2 * s.R + M) / M * (M + 1) <= a.pg.w_len[0]) build_weights_chunked<M>(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
 }
 
 // ------------------------------------------------------------------------------------------------ K1f forward
-template <int NT, int MINB>
+template <int M, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) {
-    constexpr int M = kConvM;
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    const long long b = blockIdx.x;
+    const long long b = a.order ? a.order[combo_of_block(a)] : combo_of_block(a);
     const int n = pb.G, halo = a.halo;
     const long long T = a.T;
     Fast1dSetup s;
-    fast1d_setup(a, sm, b, s);
-    if (2 * s.R + 1 + M > a.pg.w_len[0]) {  // radius beyond blg_program.max_radius
+    fast1d_setup<M>(a, sm, b, s);
+    if ((2 * s.R + M) / M * (M + 1) > a.pg.w_len[0]) {  // radius beyond blg_program.max_radius
         if (threadIdx.x == 0) {
             a.logE[b] = NAN;
             if (a.alive) a.alive[b] = -2;
@@ -201,18 +237,17 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------ K2f backward
-template <int NT, int MINB>
+template <int M, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) {
-    constexpr int M = kConvM;
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    const long long b = blockIdx.x;
+    const long long b = a.order ? a.order[combo_of_block(a)] : combo_of_block(a);
     if (a.alive && a.alive[b] != 1) return;  // the forward pass aborted (core.py:400)
     const int n = pb.G, halo = a.halo;
     const long long T = a.T;
     Fast1dSetup s;
-    fast1d_setup(a, sm, b, s);
-    if (2 * s.R + 1 + M > a.pg.w_len[0]) return;
+    fast1d_setup<M>(a, sm, b, s);
+    if ((2 * s.R + M) / M * (M + 1) > a.pg.w_len[0]) return;
     const int i0 = threadIdx.x * M;
     const bool owner = i0 < n;
     const bool service = threadIdx.x == blockDim.x - 1;

@@ -44,19 +44,6 @@ struct Resident {
     bool pending;           // a bulk store is still reading `cur`
 };
 
-__device__ __forceinline__ long long combo_of_block(const PassArgs &a) {
-    long long j = blockIdx.x;
-    if (a.serpentine) {  // alternate direction per wave of num_sms blocks so cheap and expensive combos share an SM
-        const long long S = a.num_sms, wave = j / S, pos = j - wave * S;
-        if (wave & 1) {
-            const long long left = a.B - wave * S;
-            const long long cnt = left < S ? left : S;
-            j = wave * S + (cnt - 1 - pos);
-        }
-    }
-    return j;
-}
-
 // Transition program of one step (forward: index of the step just processed; backward: current step).
 // Every branch is CTA-uniform.  Returns with all threads synchronised on the new state in r.cur.
 __device__ __forceinline__ void apply_ops(const PassArgs &a, Resident &r, long long idx, bool backward, long long b) {
@@ -201,7 +188,7 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) fwd_resident_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    const long long b = combo_of_block(a);
+    const long long b = a.order ? a.order[combo_of_block(a)] : combo_of_block(a);
     if (b >= a.B) return;
     const int G = pb.G, n1 = pb.n1;
     const long long T = a.T;
@@ -309,7 +296,7 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    const long long b = combo_of_block(a);
+    const long long b = a.order ? a.order[combo_of_block(a)] : combo_of_block(a);
     if (b >= a.B) return;
     if (a.alive && a.alive[b] != 1) return;  // the forward pass aborted (core.py:400)
     const int G = pb.G, n1 = pb.n1;

@@ -37,7 +37,8 @@ class _Problem(ctypes.Structure):
 
 class _Program(ctypes.Structure):
     _fields_ = [('n_ops', ctypes.c_int32), ('kind', ctypes.c_int32 * MAX_OPS), ('axis', ctypes.c_int32 * MAX_OPS),
-                ('max_radius', ctypes.c_int32 * MAX_OPS), ('param', ctypes.c_void_p), ('radius', ctypes.c_void_p), ('window', ctypes.c_void_p)]
+                ('max_radius', ctypes.c_int32 * MAX_OPS), ('param', ctypes.c_void_p), ('radius', ctypes.c_void_p),
+                ('window', ctypes.c_void_p), ('order', ctypes.c_void_p)]
 
 
 class _Inputs(ctypes.Structure):
@@ -79,6 +80,8 @@ class Program:
         self.param = engine.to_device(param)
         self.radius = engine.to_device(radius)
         self.window = engine.to_device(window)
+        self._engine = engine
+        self._orders = {}
 
     def struct(self, lo=0, hi=None):
         hi = self.B if hi is None else hi
@@ -91,7 +94,17 @@ class Program:
         p.param = self.param.data_ptr() + lo * K * 8
         p.radius = self.radius.data_ptr() + lo * K * 4
         p.window = self.window.data_ptr() + lo * K * 16
+        p.order = self._order(lo, hi).data_ptr() if hi - lo > 1 else None
         return p
+
+    def _order(self, lo, hi):
+        """Launch order of the combos of one call: most expensive first (cost ~ total convolution radius), so that
+        the hardware block scheduler packs heavy and light combinations onto the same SM."""
+        if (lo, hi) not in self._orders:
+            cost = self.host['radius'][lo:hi].sum(axis=1)
+            order = np.argsort(-cost, kind='stable').astype(np.int32)
+            self._orders[(lo, hi)] = self._engine.to_device(order)
+        return self._orders[(lo, hi)]
 
 
 class Plan:

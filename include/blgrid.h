@@ -93,6 +93,8 @@ typedef struct blg_program {
                                /*   10^log10pMin * prod(lattice); RESET scale (prod(lattice) or 1)               */
     const int32_t *radius;     /* device [B][n_ops]: GRW radius int(4*sigma_n+0.5) (scipy _filters.py:747); else 0 */
     const int32_t *window;     /* device [B][n_ops][4]: f_lo, f_hi, b_lo, b_hi                                   */
+    const int32_t *order;      /* device [B] or NULL: permutation of the combos in descending cost (sum of radii); */
+                               /*   scheduling hint only -- results do not depend on it                           */
 } blg_program;
 
 typedef struct blg_inputs {
