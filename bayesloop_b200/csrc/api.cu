@@ -300,9 +300,63 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int
     a.off_misc = even_up(off);
     lay.bytes = (size_t)(a.off_misc + kMiscDoubles) * sizeof(double);
     int nt = (items + 31) / 32 * 32;
-    if (nt < 64) nt = 64;
     lay.nt = nt;
     return lay.bytes <= kSmemLimit;
+}
+
+// Stream kernels (grids that do not fit in shared memory): state in global scratch, convolution tiles in smem.
+bool stream_layout(const blg_plan *pl, const blg_program &pg, PassArgs &a, Layout &lay) {
+    const DevProblem &d = pl->dev;
+    a.halo = 0;
+    a.Gp = even_up(d.G);
+    a.n0p = even_up(d.n0);
+    a.n1p = even_up(d.n1);
+    a.off_stage = -1;
+    int off = 0;
+    a.off_tab = off;
+    off += 3 * a.n0p + 2 * a.n1p;
+    a.off_w = off;
+    int woff = 0;
+    for (int k = 0; k < pg.n_ops; ++k) {
+        a.pg.w_off[k] = woff;
+        a.pg.w_len[k] = 0;
+        if (pg.kind[k] == BLG_OP_GRW) {
+            const int taps = 2 * pg.max_radius[k] + 1;
+            a.pg.w_len[k] = even_up(((taps + kConvM - 1) / kConvM) * kConvM + kConvM);
+            woff += a.pg.w_len[k];
+        }
+    }
+    off += woff;
+    a.off_misc = even_up(off);
+    off = a.off_misc + kMiscDoubles;
+    a.off_tile = off;
+    const long long room = (long long)(kSmemLimit / sizeof(double)) - off;
+    long long tile = room < 20480 ? room : 20480;  // 160 KB is plenty; leaves L1 for the streamed state
+    const int longest = d.n0 > d.n1 ? d.n0 : d.n1;
+    if (tile < longest) return false;  // one complete line of the convolution axis must fit
+    a.tile_doubles = (int)tile;
+    lay.bytes = (size_t)(off + tile) * sizeof(double);
+    lay.nt = 1024;
+    return true;
+}
+
+template <typename K>
+int launch_stream(K kernel, blg_plan *pl, PassArgs &a, const Layout &lay, long long B, cudaStream_t st, const char *name) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    long long grid = B < pl->num_sms ? B : pl->num_sms;  // one persistent CTA per SM, looping over combos
+    double *scratch = nullptr;
+    CUDA_TRY(cudaMallocAsync(&scratch, (size_t)grid * 2 * a.Gp * sizeof(double), st));
+    a.scratch = scratch;
+    a.use_bulk = 0;
+    if (getenv("BLG_VERBOSE"))
+        fprintf(stderr, "[blgrid] %s: grid %lld x %d threads, %zu B smem/CTA, tile %d doubles, scratch %.1f MB\n", name,
+                grid, lay.nt, lay.bytes, a.tile_doubles, grid * 2.0 * a.Gp * 8 / 1e6);
+    kernel<<<(unsigned)grid, lay.nt, lay.bytes, st>>>(a);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(scratch, st));
+    return 0;
 }
 
 int fast_m() {
@@ -402,12 +456,14 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
 #undef BLG_FWD_FAST
     }
     a.halo = 0;
-    if (!resident_layout(pl, in->prog, false, false, a, lay))
-        return fail("grid / kernel radius too large for the shared-memory resident forward kernel");
+    if (!resident_layout(pl, in->prog, false, false, a, lay) || getenv("BLG_FORCE_STREAM")) {
+        if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream forward kernel");
+        return launch_stream(fwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "fwd_stream");
+    }
     a.use_bulk = bulkOk ? 1 : 0;
-    if (lay.nt <= 256) return launch_resident(fwd_resident_kernel<256, 4>, a, lay, in->B, st, "fwd_resident");
-    if (lay.nt <= 512) return launch_resident(fwd_resident_kernel<512, 2>, a, lay, in->B, st, "fwd_resident");
-    return launch_resident(fwd_resident_kernel<1024, 1>, a, lay, in->B, st, "fwd_resident");
+    if (lay.nt <= 256) return launch_resident(fwd_resident_kernel<256, 4, false>, a, lay, in->B, st, "fwd_resident");
+    if (lay.nt <= 512) return launch_resident(fwd_resident_kernel<512, 2, false>, a, lay, in->B, st, "fwd_resident");
+    return launch_resident(fwd_resident_kernel<1024, 1, false>, a, lay, in->B, st, "fwd_resident");
 }
 
 int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {
@@ -439,14 +495,15 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     }
     a.halo = 0;
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
-    if (!fits) {
-        if (!resident_layout(pl, in->prog, true, false, a, lay))
-            return fail("grid / kernel radius too large for the shared-memory resident backward kernel");
+    if (!fits) fits = false;
+    if (getenv("BLG_FORCE_STREAM") || (!fits && !resident_layout(pl, in->prog, true, false, a, lay))) {
+        if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream backward kernel");
+        return launch_stream(bwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "bwd_stream");
     }
     a.use_bulk = (fits && a.off_stage >= 0) ? 1 : 0;
-    if (lay.nt <= 256) return launch_resident(bwd_resident_kernel<256, 4>, a, lay, in->B, st, "bwd_resident");
-    if (lay.nt <= 512) return launch_resident(bwd_resident_kernel<512, 2>, a, lay, in->B, st, "bwd_resident");
-    return launch_resident(bwd_resident_kernel<1024, 1>, a, lay, in->B, st, "bwd_resident");
+    if (lay.nt <= 256) return launch_resident(bwd_resident_kernel<256, 4, false>, a, lay, in->B, st, "bwd_resident");
+    if (lay.nt <= 512) return launch_resident(bwd_resident_kernel<512, 2, false>, a, lay, in->B, st, "bwd_resident");
+    return launch_resident(bwd_resident_kernel<1024, 1, false>, a, lay, in->B, st, "bwd_resident");
 }
 
 int blg_accumulate(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {

@@ -73,6 +73,9 @@ struct PassArgs {
     int serpentine;      // 1: blockIdx -> combo mapping alternates direction per 148-block wave
     int num_sms;
     const int *order;    // device [B] launch order (descending cost) or NULL
+    double *scratch;     // stream kernels: [gridDim.x][2][Gp] state buffers in global memory (L2 resident)
+    int off_tile;        // stream kernels: offset (doubles) and size of the shared-memory convolution tile
+    int tile_doubles;
     int halo;            // fast 1-D kernels: reflected halo cells on each side of the state (0 = generic kernels)
 };
 
@@ -153,6 +156,25 @@ __device__ __forceinline__ double block_max(double v, RedScratch &rs) {
     return s;
 }
 
+// ------------------------------------------------------------------------------------------------ log-evidence
+// logE = sum_t log(norm_t) (core.py:403) without a log() on the per-step critical path: the product of the norms is
+// carried as mantissa * 2^exponent (two frexp per step, ~10 instructions) and one log() is taken at the end.
+struct LogProduct {
+    double mant;
+    long long expo;
+    __device__ __forceinline__ void init() {
+        mant = 1.0;
+        expo = 0;
+    }
+    __device__ __forceinline__ void mul(double x) {
+        int e1, e2;
+        const double m = frexp(x, &e1);
+        mant = frexp(mant * m, &e2);
+        expo += e1 + e2;
+    }
+    __device__ __forceinline__ double log_value() const { return log(mant) + (double)expo * 0.693147180559945309417232121458; }
+};
+
 // ------------------------------------------------------------------------------------------------ likelihood
 // Likelihood of ONE data column at grid point (i0, i1).  Tables (shared memory):
 //   POISSON        A0 = lambda, A1 = log(lambda)                      arg = k*A1 - A0 - lgamma(k+1)
@@ -231,7 +253,11 @@ __device__ __forceinline__ int reflect_once(int i, int n) {  // valid while -n <
 template <int M, bool SIMPLE>
 __device__ __forceinline__ void conv_lines(const double *__restrict__ src, double *__restrict__ dst,
                                            const double *__restrict__ W, int R, int n, int elemStride, int nLines,
-                                           int lineStride) {
+                                           int lineStride, int dElemStride = -1, int dLineStride = -1) {
+    if (dElemStride < 0) {
+        dElemStride = elemStride;
+        dLineStride = lineStride;
+    }
     const int S = (n + M - 1) / M;
     const int nItems = S * nLines;
     const int taps = 2 * R + 1;
@@ -266,10 +292,10 @@ __device__ __forceinline__ void conv_lines(const double *__restrict__ src, doubl
                 ++idx;
             }
         }
-        double *out = dst + (size_t)l * lineStride;
+        double *out = dst + (size_t)l * dLineStride;
 #pragma unroll
         for (int m = 0; m < M; ++m)
-            if (i0 + m < n) out[(size_t)(i0 + m) * elemStride] = acc[m];
+            if (i0 + m < n) out[(size_t)(i0 + m) * dElemStride] = acc[m];
     }
 }
 

@@ -89,6 +89,59 @@ __device__ __forceinline__ void build_weights_chunked(double *W, int len, double
     __syncthreads();
 }
 
+// Likelihood of the thread's M consecutive cells for one time step: the observation-model switch is outside the
+// cell loop and the M exponentials are independent instruction streams (ILP hides the ~25-DFMA chain of exp()).
+template <int M>
+__device__ __forceinline__ void lik_cells(const PassArgs &a, const LikTables &tb, const StepC &s0, const StepC *sc,
+                                          long long t, int i0, int n, double (&lk)[M]) {
+    const DevProblem &pb = a.pb;
+    if (pb.om_kind == BLG_OM_TABLE) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? __ldg(a.lik_table + t * (long long)n + i0 + m) : 0.0;
+        return;
+    }
+    if (pb.ncols_eff == 1) {
+        if (s0.skip != 0.0) {  // missing data: likelihood of ones (observationModels.py:53-54)
+#pragma unroll
+            for (int m = 0; m < M; ++m) lk[m] = 1.0;
+            return;
+        }
+        double arg[M];
+        if (pb.om_kind == BLG_OM_POISSON) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int li = min(i0 + m, n - 1);
+                arg[m] = fma(s0.d0, tb.A1[li], -tb.A0[li]) - s0.c;
+            }
+        } else if (pb.om_kind == BLG_OM_WHITE_NOISE) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int li = min(i0 + m, n - 1);
+                arg[m] = fma(-s0.d0 * s0.d0, tb.A0[li], tb.A1[li]);
+            }
+        } else if (pb.om_kind == BLG_OM_GAUSSIAN_MEAN) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int li = min(i0 + m, n - 1);
+                const double r = s0.d0 - tb.A0[li];
+                arg[m] = fma(-r * r, s0.d1, s0.c);
+            }
+        } else {  // BERNOULLI
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int li = min(i0 + m, n - 1);
+                lk[m] = s0.d0 != 0.0 ? tb.A0[li] : 1.0 - tb.A0[li];
+            }
+            return;
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) lk[m] = exp(arg[m]);
+        return;
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) lk[m] = lik_cell(pb, tb, sc, min(i0 + m, n - 1), 0);
+}
+
 struct Fast1dSetup {
     double *buf0, *buf1;  // interior pointers of the two haloed state buffers
     double *W;
@@ -161,11 +214,15 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
     const bool bulk = store && a.use_bulk;
     double *seq = store ? a.alpha_seq + b * T * (long long)n : nullptr;
     const int nce = pb.ncols_eff;
-    double logE = 0.0;
+    LogProduct lp;
+    lp.init();
     bool dead = false;
 
     for (long long t = 0; t < T; ++t) {
         double v[M];
+        const StepC *sc = a.steps + t * nce;
+        StepC s0;
+        if (pb.om_kind != BLG_OM_TABLE) s0 = sc[0];  // issued before the convolution, consumed after it
         const bool trans = (t > 0 || (a.flags & BLG_F_TRANSITION_FIRST)) && (t - 1 >= s.f_lo) && (t - 1 < s.f_hi);
         if (owner) {
             if (trans && s.R > 0) {
@@ -178,18 +235,12 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
         // alpha <- prior * likelihood; norm = sum(alpha)          core.py:375-385
         double part = 0.0;
         if (owner) {
-            const StepC *sc = a.steps + t * nce;
+            double lk[M];
+            lik_cells<M>(a, s.tb, s0, sc, t, i0, n, lk);
 #pragma unroll
             for (int m = 0; m < M; ++m) {
-                const int li = i0 + m;
-                if (li < n) {
-                    const double lik = pb.om_kind == BLG_OM_TABLE ? __ldg(a.lik_table + t * (long long)n + li)
-                                                                  : lik_cell(pb, s.tb, sc, li, 0);
-                    v[m] *= lik;
-                    part += v[m];
-                } else {
-                    v[m] = 0.0;
-                }
+                v[m] = i0 + m < n ? v[m] * lk[m] : 0.0;
+                part += v[m];
             }
         }
         if (bulk && service && t >= 2) bulk_wait_read<1>();  // the store of step t-2 has released `nxt`
@@ -211,7 +262,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
             }
         }
         if (service) {
-            logE += log(norm);                                    // core.py:403
+            lp.mul(norm);                                         // core.py:403
             if (a.local) a.local[b * T + t] = norm * pb.lc_prod;  // core.py:404
         }
         if (bulk) fence_proxy_async();
@@ -227,6 +278,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
         for (int g = threadIdx.x; g < n; g += blockDim.x) fs[g] = cur[g];
     }
     if (service) {
+        double logE = lp.log_value();
         if (dead)
             logE = -INFINITY;
         else if (!(a.flags & BLG_F_INIT_STATE))
@@ -289,6 +341,9 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
         } else {
             A = seq + i * (long long)n;
         }
+        const StepC *sc = a.steps + i * nce;
+        StepC s0;
+        if (pb.om_kind != BLG_OM_TABLE) s0 = sc[0];
         double al[M];
         double pab = 0.0, pb_ = 0.0;
         if (owner) {
@@ -309,15 +364,15 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
         const double inv = 1.0 / pab;      // posterior = alpha*beta / sum(alpha*beta): the scale of beta cancels
         double q = 0.0;
         if (owner) {
-            const StepC *sc = a.steps + i * nce;
+            double lk[M];
+            lik_cells<M>(a, s.tb, s0, sc, i, i0, n, lk);  // core.py:455
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 const int li = i0 + m;
                 if (li < n) {
-                    const double p = al[m] * beta[m] * inv;                                     // core.py:436-441
-                    const double lik = pb.om_kind == BLG_OM_TABLE ? __ldg(a.lik_table + i * (long long)n + li)
-                                                                  : lik_cell(pb, s.tb, sc, li, 0);  // core.py:455
-                    q += p / lik;                                                               // core.py:463
+                    const double p = al[m] * beta[m] * inv;  // core.py:436-441
+                    const double lik = lk[m];
+                    q += p / lik;                            // core.py:463
                     if (acc) {
                         if (wgt > 0.0) atomicAdd(a.avg + i * (long long)n + li, wgt * (p < kTiny ? kTiny : p));
                     } else {

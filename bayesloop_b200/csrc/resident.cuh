@@ -44,9 +44,51 @@ struct Resident {
     bool pending;           // a bulk store is still reading `cur`
 };
 
+// Convolution for grids that do not fit in shared memory (stream kernels): the state lives in global memory (L2),
+// tiles that contain COMPLETE lines of the convolution axis are staged in shared memory, so no halo is exchanged:
+//   axis 1 (contiguous): tile = a band of rows;   axis 0: tile = a strip of columns (all n0 rows).
+template <int M>
+__device__ __forceinline__ void conv_global(const double *src, double *dst, const double *W, int R, int n0, int n1,
+                                            int axis, double *tile, int tileDoubles) {
+    if (axis == 1 || n1 == 1) {
+        const int n = n1 == 1 ? n0 : n1, rowsAll = n1 == 1 ? 1 : n0;
+        const int rowsPerTile = max(1, tileDoubles / n);
+        for (int r0 = 0; r0 < rowsAll; r0 += rowsPerTile) {
+            const int rows = min(rowsPerTile, rowsAll - r0);
+            const double *g = src + (size_t)r0 * n;
+            for (int e = threadIdx.x; e < rows * n; e += blockDim.x) tile[e] = g[e];
+            __syncthreads();
+            if (R + 2 * M <= n)
+                conv_lines<M, true>(tile, dst + (size_t)r0 * n, W, R, n, 1, rows, n);
+            else
+                conv_lines<M, false>(tile, dst + (size_t)r0 * n, W, R, n, 1, rows, n);
+            __syncthreads();
+        }
+    } else {
+        int cols = tileDoubles / n0;
+        if (cols > 32) cols = cols / 32 * 32;
+        cols = max(1, min(cols, n1));
+        for (int c0 = 0; c0 < n1; c0 += cols) {
+            const int w = min(cols, n1 - c0);
+            for (int e = threadIdx.x; e < n0 * w; e += blockDim.x) {
+                const int rr = e / w, cc = e - rr * w;
+                tile[e] = src[(size_t)rr * n1 + c0 + cc];
+            }
+            __syncthreads();
+            if (R + 2 * M <= n0)
+                conv_lines<M, true>(tile, dst + c0, W, R, n0, w, w, 1, n1, 1);
+            else
+                conv_lines<M, false>(tile, dst + c0, W, R, n0, w, w, 1, n1, 1);
+            __syncthreads();
+        }
+    }
+}
+
 // Transition program of one step (forward: index of the step just processed; backward: current step).
 // Every branch is CTA-uniform.  Returns with all threads synchronised on the new state in r.cur.
-__device__ __forceinline__ void apply_ops(const PassArgs &a, Resident &r, long long idx, bool backward, long long b) {
+template <bool STREAM>
+__device__ __forceinline__ void apply_ops(const PassArgs &a, Resident &r, long long idx, bool backward, long long b,
+                                          double *sm) {
     const DevProblem &pb = a.pb;
     const int G = pb.G;
     int applied = 0;
@@ -62,7 +104,9 @@ __device__ __forceinline__ void apply_ops(const PassArgs &a, Resident &r, long l
             const int n = ax == 0 ? pb.n0 : pb.n1;
             const int es = ax == 0 ? pb.n1 : 1, nl = ax == 0 ? pb.n1 : pb.n0, ls = ax == 0 ? 1 : pb.n1;
             const double *W = r.W + a.pg.w_off[k];
-            if (R + 2 * kConvM <= n)
+            if (STREAM)
+                conv_global<kConvM>(r.cur, r.oth, W, R, pb.n0, pb.n1, ax, sm + a.off_tile, a.tile_doubles);
+            else if (R + 2 * kConvM <= n)
                 conv_lines<kConvM, true>(r.cur, r.oth, W, R, n, es, nl, ls);
             else
                 conv_lines<kConvM, false>(r.cur, r.oth, W, R, n, es, nl, ls);
@@ -184,24 +228,25 @@ __device__ __forceinline__ bool resident_setup(const PassArgs &a, double *sm, lo
 }
 
 // ------------------------------------------------------------------------------------------------ K1 forward
-template <int NT, int MINB>
+template <int NT, int MINB, bool STREAM>
 __global__ void __launch_bounds__(NT, MINB) fwd_resident_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    const long long b = a.order ? a.order[combo_of_block(a)] : combo_of_block(a);
-    if (b >= a.B) return;
+  for (long long slot = STREAM ? blockIdx.x : combo_of_block(a); slot < a.B; slot += STREAM ? gridDim.x : a.B) {
+    const long long b = a.order ? a.order[slot] : slot;
     const int G = pb.G, n1 = pb.n1;
     const long long T = a.T;
     Resident r;
-    r.cur = sm;
-    r.oth = sm + a.Gp;
+    r.cur = STREAM ? a.scratch + (size_t)blockIdx.x * 2 * a.Gp : sm;
+    r.oth = r.cur + a.Gp;
+    if (STREAM) __syncthreads();  // previous combo of this CTA is completely done with shared memory
     const bool ok = resident_setup(a, sm, b, r);
     if (!ok) {
         if (threadIdx.x == 0) {
             a.logE[b] = NAN;
             if (a.alive) a.alive[b] = -2;
         }
-        return;
+        continue;
     }
     {
         const double *init = (a.flags & BLG_F_INIT_STATE) ? a.init_state + b * (long long)G : a.prior;
@@ -217,7 +262,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_resident_kernel(const PassArgs a
     bool dead = false;
 
     for (long long t = 0; t < T; ++t) {
-        if (t > 0 || (a.flags & BLG_F_TRANSITION_FIRST)) apply_ops(a, r, t - 1, false, b);
+        if (t > 0 || (a.flags & BLG_F_TRANSITION_FIRST)) apply_ops<STREAM>(a, r, t - 1, false, b, sm);
 
         // alpha <- prior * likelihood, norm = sum(alpha)          core.py:375-385
         const StepC *sc = a.steps + t * nce;
@@ -289,29 +334,31 @@ __global__ void __launch_bounds__(NT, MINB) fwd_resident_kernel(const PassArgs a
         a.logE[b] = logE;
         if (a.alive) a.alive[b] = dead ? 0 : 1;
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K2 backward
-template <int NT, int MINB>
+template <int NT, int MINB, bool STREAM>
 __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    const long long b = a.order ? a.order[combo_of_block(a)] : combo_of_block(a);
-    if (b >= a.B) return;
-    if (a.alive && a.alive[b] != 1) return;  // the forward pass aborted (core.py:400)
+  for (long long slot = STREAM ? blockIdx.x : combo_of_block(a); slot < a.B; slot += STREAM ? gridDim.x : a.B) {
+    const long long b = a.order ? a.order[slot] : slot;
+    if (a.alive && a.alive[b] != 1) continue;  // the forward pass aborted (core.py:400)
     const int G = pb.G, n1 = pb.n1;
     const long long T = a.T;
     Resident r;
-    r.cur = sm;
-    r.oth = sm + a.Gp;
-    if (!resident_setup(a, sm, b, r)) return;
+    r.cur = STREAM ? a.scratch + (size_t)blockIdx.x * 2 * a.Gp : sm;
+    r.oth = r.cur + a.Gp;
+    if (STREAM) __syncthreads();
+    if (!resident_setup(a, sm, b, r)) continue;
     const bool acc = (a.flags & BLG_F_ACCUMULATE) != 0;
     const double wgt = acc ? exp(a.log_weight[b]) : 0.0;
     const double beta0 = 1.0 / (double)G;  // core.py:424-425
     for (int g = threadIdx.x; g < G; g += blockDim.x) r.cur[g] = beta0;
 
     double *seq = a.alpha_seq + b * T * (long long)G;
-    const bool staged = a.off_stage >= 0 && a.use_bulk;
+    const bool staged = !STREAM && a.off_stage >= 0 && a.use_bulk;
     double *S[2] = {sm + (staged ? a.off_stage : 0), sm + (staged ? a.off_stage + a.Gp : 0)};
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
     uint32_t ph[2] = {0u, 0u};
@@ -375,7 +422,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
         if (staged && threadIdx.x == 0 && i >= 2)  // everybody is past the barrier: S[sb] is free again
             bulk_load(S[sb], seq + (i - 2) * (long long)G, rowBytes, &bars[sb]);
         if (threadIdx.x == 0 && a.local) a.local[b * T + i] = 1.0 / (q * pb.lc_prod);
-        apply_ops(a, r, i, true, b);
+        apply_ops<STREAM>(a, r, i, true, b, sm);
         part = 0.0;
         for (int g = threadIdx.x; g < G; g += blockDim.x) part += r.cur[g];
         const double binv = 1.0 / block_sum(part, r.rs);  // core.py:470
@@ -386,6 +433,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
         a.logE[b] = -INFINITY;
         if (a.alive) a.alive[b] = -1;
     }
+  }
 }
 
 }  // namespace blg

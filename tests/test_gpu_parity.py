@@ -60,6 +60,8 @@ CONFIGS = {
     'poisson_odd_grid': lambda bl, e: _poisson(bl, e, B=5, T=100, G=333, smax=0.3),
     'gauss_2d_64x48': lambda bl, e: _gauss2d(bl, e, 64, 48, T=80, hb=3),
     'gauss_2d_100x100': lambda bl, e: _gauss2d(bl, e, 100, 100, T=30, hb=2),
+    'gauss_2d_200x200_stream': lambda bl, e: _gauss2d(bl, e, 200, 200, T=16, hb=2),
+    'gauss_2d_256x96_stream': lambda bl, e: _gauss2d(bl, e, 256, 96, T=12, hb=2, seed=3),
 }
 
 
@@ -119,3 +121,14 @@ def test_properties_at_scale(cuda_engine):
     again = helpers.abi_sweep(cuda_engine, _poisson(bl, cuda_engine, B=256, T=1500, G=1000, smax=0.2))
     np.testing.assert_array_equal(full['logE'], again['logE'])
     np.testing.assert_allclose(full['avg'], again['avg'], rtol=1e-12, atol=1e-300)  # fp64 atomics: order may vary
+
+
+@pytest.mark.parametrize('name', ['ref_tm_nested', 'ref_cps_1cp_1bp_2hp', 'syn_hyper_gauss_2d', 'syn_study_scaledar1_2d',
+                                  'syn_study_2d_axis0_wide', 'syn_hyper_poisson_sweep', 'syn_online_mixed',
+                                  'syn_study_multicolumn', 'ref_om_gaussianmean'])
+def test_stream_kernels_on_golden_cases(name, use_cuda, monkeypatch):
+    """The large-grid (global-memory streamed) kernels forced onto small cases: same goldens."""
+    import bayesloop_b200 as bl
+    monkeypatch.setenv('BLG_FORCE_STREAM', '1')
+    S, got = parity.run_case(name, bl)
+    parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)
