@@ -642,7 +642,7 @@ class HyperStudy(Study):
             sw['logHp'] = np.log(hp)
         return sw
 
-    def _executeSweep(self, sw, exclude=None):
+    def _executeSweep(self, sw):
         """Kernels of one sweep (inputs already resident): per wave one forward pass, the evidences fix the
         averaging weights, one backward(+accumulate) pass; then local-evidence mix, cross-rank merge, finalize."""
         from . import distributed as dist
@@ -667,8 +667,6 @@ class HyperStudy(Study):
             if evidenceOnly:
                 continue
             lw = le + sw['logHp'][w0:w1]
-            if exclude is not None:
-                lw = np.where(exclude[sw['lo'] + w0:sw['lo'] + w1], -np.inf, lw)
             finite = np.isfinite(lw)
             if finite.any():
                 top = float(np.max(lw[finite]))
@@ -676,11 +674,13 @@ class HyperStudy(Study):
                     if np.isfinite(shift):
                         eng.scale(ses.plan, avg, T * G, math.exp(shift - top))
                     shift = top
+            if not forwardOnly:
+                # smoothed posteriors overwrite the stored sequences in place; combos whose backward pass hits a
+                # zero norm flag themselves (alive = -1) and are dropped from the average as a whole (core.py:1358)
+                eng.run('backward', ses.plan, 0, **common)
             weights = eng.to_device(np.where(finite, lw - (shift if np.isfinite(shift) else 0.), -np.inf))
-            if forwardOnly:
-                eng.run('accumulate', ses.plan, 0, log_weight=weights, avg=avg, **common)
-            else:
-                eng.run('backward', ses.plan, _engine.F_ACCUMULATE, log_weight=weights, avg=avg, **common)
+            # evidence-weighted sum over the combos of this wave, fixed summation order (deterministic)
+            eng.run('accumulate', ses.plan, 0, log_weight=weights, avg=avg, **common)
         aliveHost = eng.to_host(alive)[:B]
         logEHost = np.where(aliveHost == 1, logEHost, -np.inf)
         # averaged local evidence: sum_b localEvidence_b * hyperprior_b (core.py:1410)
@@ -690,13 +690,6 @@ class HyperStudy(Study):
             eng.mix(ses.plan, local, sw['hpDev'], B, T, part)
         logEAll, aliveAll = dist.gather_rows(eng, logEHost, aliveHost, sw['Ball'])
         localEv = dist.reduce_sum(eng, part)
-        died = aliveAll == -1
-        if exclude is not None:
-            died = died & ~exclude
-        if (not evidenceOnly) and died.any():
-            # A combo whose backward pass hit a zero norm is dropped from the average as a whole
-            # (core.py:1358): redo the sweep with its weight forced to zero.
-            return self._executeSweep(sw, exclude=(died if exclude is None else (exclude | died)))
         if not evidenceOnly:
             dist.rebase_and_reduce(eng, ses.plan, avg, shift, T * G)
             eng.finalize(ses.plan, avg, T, sw['means'], _engine.F_NORMALIZE_ROWS)

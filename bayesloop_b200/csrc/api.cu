@@ -359,10 +359,12 @@ int launch_stream(K kernel, blg_plan *pl, PassArgs &a, const Layout &lay, long l
     return 0;
 }
 
-int fast_m() {
-    const char *e = getenv("BLG_FAST_M");
-    const int m = e ? atoi(e) : 7;
-    return (m == 5 || m == 9) ? m : 7;
+// outputs per thread of the fast 1-D kernels: 9 in the forward pass (4 full warps per 1000-cell combo, one per SM
+// sub-partition), 7 in the backward pass (more live registers per cell); measured on B200, see profiles/
+int fast_m(bool backward) {
+    const char *e = getenv(backward ? "BLG_FAST_M_BWD" : "BLG_FAST_M");
+    const int m = e ? atoi(e) : (backward ? 7 : 9);
+    return (m == 5 || m == 7 || m == 9) ? m : 7;
 }
 
 template <typename K>
@@ -441,7 +443,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     if (fill_args(pl, in, out, flags, a)) return -1;
     Layout lay;
     const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
-    const int M = fast_m();
+    const int M = fast_m(false);
     if (fast1d_layout(pl, in->prog, false, M, a, lay)) {
         a.use_bulk = bulkOk ? 1 : 0;
 #define BLG_FWD_FAST(MM)                                                                                           \
@@ -479,7 +481,7 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     if (fill_args(pl, in, out, flags, a)) return -1;
     Layout lay;
     const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
-    const int M = fast_m();
+    const int M = fast_m(true);
     if (fast1d_layout(pl, in->prog, true, M, a, lay)) {
         a.use_bulk = alignedRows ? 1 : 0;
 #define BLG_BWD_FAST(MM)                                                                                           \

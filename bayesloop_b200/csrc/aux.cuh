@@ -67,12 +67,21 @@ __global__ void accumulate_kernel(const double *__restrict__ seq, const double *
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count) return;
     double s = 0.0;
-    for (long long b = 0; b < B; ++b) {
-        const double wb = __ldg(w + b);
-        if (wb > 0.0) {
-            const double v = __ldcs(seq + b * count + e);
-            s = fma(wb, v < kTiny ? kTiny : v, s);
+    long long b = 0;
+    for (; b + 8 <= B; b += 8) {  // 8 independent streaming loads in flight per thread
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(seq + (b + u) * count + e);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double wb = __ldg(w + b + u);
+            if (wb > 0.0) s = fma(wb, v[u] < kTiny ? kTiny : v[u], s);  // wb == 0: combo not alive (rows may hold NaN)
         }
+    }
+    for (; b < B; ++b) {
+        const double wb = __ldg(w + b);
+        const double v = __ldcs(seq + b * count + e);
+        if (wb > 0.0) s = fma(wb, v < kTiny ? kTiny : v, s);
     }
     avg[e] += s;
 }

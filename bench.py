@@ -238,7 +238,7 @@ def main():
     updates = 2.0 * n_total * T * G
 
     # ---- per-kernel event timing (live, on the launching stream) ---------------------------------------------
-    kernel_ms = {'forward': [], 'backward': []}
+    kernel_ms = {'forward': [], 'backward': [], 'accumulate': []}
     recording = {'on': False, 'events': []}
     plain_run = eng.run
 
@@ -306,19 +306,27 @@ def main():
     if rank == 0:
         peak, peak_src = hbm_peak()
         n_loc = n_total // world
-        fwd_ms = float(np.mean(kernel_ms['forward'])) if kernel_ms['forward'] else float('nan')
-        bwd_ms = float(np.mean(kernel_ms['backward'])) if kernel_ms['backward'] else float('nan')
+        # algorithmic HBM bytes per (combo, time step, cell): forward stores alpha[t] (8 B); backward reads alpha[t] and
+        # stores the posterior (16 B); the averaging pass reads every posterior once (8 B)  ->  32 B per cell for the
+        # two passes = 16 B per grid-cell update (forward 8 B + backward 24 B in HyperStudy mode)
+        bytes_per_cell = {'forward': 8.0, 'backward': 16.0, 'accumulate': 8.0}
+        names = {'forward': 'fwd_fast1d_kernel', 'backward': 'bwd_fast1d_kernel', 'accumulate': 'accumulate_kernel'}
         per_launch_cells = n_loc * T * G / max(1, waves)
-        fwd_gbs = 8.0 * per_launch_cells / (fwd_ms * 1e-3) / 1e9
-        bwd_gbs = 24.0 * per_launch_cells / (bwd_ms * 1e-3) / 1e9
-        dominant = 'bwd_resident_kernel' if bwd_ms >= fwd_ms else 'fwd_resident_kernel'
-        ach = bwd_gbs if bwd_ms >= fwd_ms else fwd_gbs
-        roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                    'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
-                    'algorithmic_bytes_per_update': {'forward': 8, 'backward_hyper': 24},
-                    'kernels': {'fwd_resident_kernel': {'ms': fwd_ms, 'GBps': fwd_gbs, 'frac': fwd_gbs / peak},
-                                'bwd_resident_kernel': {'ms': bwd_ms, 'GBps': bwd_gbs, 'frac': bwd_gbs / peak}},
-                    'kernel_share_of_step': (fwd_ms + bwd_ms) * waves / dev_ms}
+        kern = {}
+        for which, samples in kernel_ms.items():
+            if samples:
+                ms = float(np.mean(samples))
+                gbs = bytes_per_cell[which] * per_launch_cells / (ms * 1e-3) / 1e9
+                kern[names[which]] = {'ms': ms, 'GBps': gbs, 'frac': gbs / peak, 'bytes_per_cell': bytes_per_cell[which]}
+        dominant = max(kern, key=lambda k: kern[k]['ms'])
+        total_kernel_ms = sum(v['ms'] for v in kern.values()) * waves
+        sweep_gbs = 32.0 * n_loc * T * G / (total_kernel_ms * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': kern[dominant]['GBps'], 'peak': peak, 'unit': 'GB/s',
+                    'frac': kern[dominant]['frac'], 'traffic': None, 'peak_source': peak_src,
+                    'kernels': kern, 'all_kernels_GBps': sweep_gbs, 'all_kernels_frac': sweep_gbs / peak,
+                    'kernel_share_of_step': total_kernel_ms / dev_ms,
+                    'note': 'reference-like sigma sweep (kernel radius <= 67): the convolution makes the passes FP64-FMA '
+                            'bound, not HBM bound (SURVEY.md 8d); see profiles/ for the FP64 pipe utilisation'}
         line = {
             'metric': 'grid_cell_updates_per_s', 'value': updates / (dev_ms * 1e-3), 'unit': 'cell-updates/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms,

@@ -44,8 +44,13 @@ def run(B, sigma_lo, sigma_hi, full=False):
           % (B, sigma_lo, sigma_hi, full, f, 1e3 * f / T, b, 1e3 * b / T), flush=True)
 
 
-for B in (148, 592):
-    for s in (0.0, 0.05, 0.2):
-        run(B, s, s + 1e-9, full=True)
+print('env:', {k: v for k, v in os.environ.items() if k.startswith('BLG_')}, flush=True)
+if os.environ.get('EXP_MODE', 'all') == 'all':
+    for B in (148, 592):
+        for s in (0.0, 0.05, 0.2):
+            run(B, s, s + 1e-9, full=True)
+else:
+    run(148, 0.0, 1e-9, full=True)
+    run(148, 0.2, 0.2 + 1e-9, full=True)
 run(512, 0.0, 0.2, full=True)
 run(512, 0.0, 0.05, full=True)
