@@ -52,6 +52,8 @@ struct blg_plan {
     long long steps_cap;
     double *d_w;
     long long w_cap;
+    double *d_lik;  // internal likelihood table [T][G] shared by the combos of a call
+    long long lik_cap;
     int serpentine;
 };
 
@@ -177,6 +179,8 @@ int blg_plan_create(const blg_problem *p, blg_plan **out) {
     pl->steps_cap = 0;
     pl->d_w = nullptr;
     pl->w_cap = 0;
+    pl->d_lik = nullptr;
+    pl->lik_cap = 0;
     *out = pl;
     return 0;
 }
@@ -186,6 +190,7 @@ void blg_plan_destroy(blg_plan *pl) {
     cudaFree(pl->d_tables);
     if (pl->d_steps) cudaFree(pl->d_steps);
     if (pl->d_w) cudaFree(pl->d_w);
+    if (pl->d_lik) cudaFree(pl->d_lik);
     delete pl;
 }
 
@@ -210,6 +215,31 @@ int ensure_w(blg_plan *pl, long long count) {
     pl->w_cap = 0;
     CUDA_TRY(cudaMalloc(&pl->d_w, (size_t)count * sizeof(double)));
     pl->w_cap = count;
+    return 0;
+}
+
+// Shared likelihood table: worth it as soon as a few combos share it; bounded so it never competes with alpha_seq.
+int prep_lik_table(blg_plan *pl, const blg_inputs *in, PassArgs &a, cudaStream_t st) {
+    const DevProblem &d = pl->dev;
+    if (d.om_kind == BLG_OM_TABLE || getenv("BLG_NO_LIK_TABLE")) return 0;
+    const long long count = in->T * (long long)d.G;
+    if (in->B < 4 || count * 8 > (6LL << 30)) return 0;
+    if (count > pl->lik_cap) {
+        if (pl->d_lik) CUDA_TRY(cudaFree(pl->d_lik));
+        pl->d_lik = nullptr;
+        pl->lik_cap = 0;
+        if (cudaMalloc(&pl->d_lik, (size_t)count * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;  // no room: keep evaluating the likelihood in the passes
+        }
+        pl->lik_cap = count;
+    }
+    const int nt = 256;
+    lik_table_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(d, pl->d_steps, in->T, pl->d_lik);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    a.pb.om_kind = BLG_OM_TABLE;
+    a.lik_table = pl->d_lik;
     return 0;
 }
 
@@ -441,6 +471,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     memset(&a, 0, sizeof a);
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
+    if (prep_lik_table(pl, in, a, st)) return -1;
     Layout lay;
     const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
     const int M = fast_m(false);
@@ -448,6 +479,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
         a.use_bulk = bulkOk ? 1 : 0;
 #define BLG_FWD_FAST(MM)                                                                                           \
     if (M == MM) {                                                                                                 \
+        if (lay.nt <= 128) return launch_resident(fwd_fast1d_kernel<MM, 128, 4>, a, lay, in->B, st, "fwd_fast1d"); \
         if (lay.nt <= 160) return launch_resident(fwd_fast1d_kernel<MM, 160, 4>, a, lay, in->B, st, "fwd_fast1d"); \
         if (lay.nt <= 256) return launch_resident(fwd_fast1d_kernel<MM, 256, 4>, a, lay, in->B, st, "fwd_fast1d"); \
         return launch_resident(fwd_fast1d_kernel<MM, 1024, 1>, a, lay, in->B, st, "fwd_fast1d");                   \
@@ -479,6 +511,7 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     memset(&a, 0, sizeof a);
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
+    if (prep_lik_table(pl, in, a, st)) return -1;
     Layout lay;
     const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
     const int M = fast_m(true);
@@ -486,6 +519,7 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
         a.use_bulk = alignedRows ? 1 : 0;
 #define BLG_BWD_FAST(MM)                                                                                           \
     if (M == MM) {                                                                                                 \
+        if (lay.nt <= 128) return launch_resident(bwd_fast1d_kernel<MM, 128, 4>, a, lay, in->B, st, "bwd_fast1d"); \
         if (lay.nt <= 160) return launch_resident(bwd_fast1d_kernel<MM, 160, 4>, a, lay, in->B, st, "bwd_fast1d"); \
         if (lay.nt <= 256) return launch_resident(bwd_fast1d_kernel<MM, 256, 4>, a, lay, in->B, st, "bwd_fast1d"); \
         return launch_resident(bwd_fast1d_kernel<MM, 1024, 1>, a, lay, in->B, st, "bwd_fast1d");                   \

@@ -40,6 +40,24 @@ __global__ void prep_steps_kernel(const double *__restrict__ data, StepC *__rest
     out[e] = s;
 }
 
+// Likelihood table lik[t][g] = processedPdf(grid, segment_t) evaluated ONCE per sweep: the likelihood does not depend
+// on the hyper-parameter combination (core.py:375 recomputes it per combo), so the B combos of a call share one
+// table through L2 instead of each evaluating T*G exponentials.
+__global__ void lik_table_kernel(DevProblem pb, const StepC *__restrict__ steps, long long T, double *__restrict__ table) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * pb.G) return;
+    const long long t = e / pb.G;
+    const int g = (int)(e - t * pb.G);
+    const int i0 = g / pb.n1, i1 = g - i0 * pb.n1;
+    LikTables tb;
+    tb.A0 = pb.tabA[0];
+    tb.A1 = pb.tabA[1];
+    tb.A2 = pb.tabA[2];
+    tb.B0 = pb.tabB[0];
+    tb.B1 = pb.tabB[1];
+    table[e] = lik_cell(pb, tb, steps + t * pb.ncols_eff, i0, i1);
+}
+
 // out[j] = sum_k weight[k] * state[k][j]   (core.py:1410, :2195-2197, :2212); fixed summation order
 __global__ void mix_kernel(const double *__restrict__ state, const double *__restrict__ weight, long long K, long long n,
                            double *__restrict__ out) {

@@ -156,6 +156,23 @@ __device__ __forceinline__ double block_max(double v, RedScratch &rs) {
     return s;
 }
 
+// ------------------------------------------------------------------------------------------------ reciprocal
+// 1/x without the IEEE division subroutine (a serial ~60-instruction call per use): hardware seed (>= 20 bits) plus
+// two Newton steps, <= 2 ulp.  Subnormal x is flushed by the seed, so callers guard tiny operands.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// a / b; exact division only when b is too small for the fast reciprocal (keeps 0/tiny = 0, x/0 = inf semantics)
+__device__ __forceinline__ double fast_div(double a, double b) {
+    return fabs(b) > 1e-290 ? a * fast_rcp(b) : a / b;
+}
+
 // ------------------------------------------------------------------------------------------------ log-evidence
 // logE = sum_t log(norm_t) (core.py:403) without a log() on the per-step critical path: the product of the norms is
 // carried as mantissa * 2^exponent (two frexp per step, ~10 instructions) and one log() is taken at the end.

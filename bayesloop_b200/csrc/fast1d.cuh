@@ -222,7 +222,13 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
         double v[M];
         const StepC *sc = a.steps + t * nce;
         StepC s0;
-        if (pb.om_kind != BLG_OM_TABLE) s0 = sc[0];  // issued before the convolution, consumed after it
+        double lk[M];
+        if (pb.om_kind != BLG_OM_TABLE) {
+            s0 = sc[0];  // issued before the convolution, consumed after it
+        } else if (owner) {  // likelihood row of this step (shared by all combos, L2 resident): in flight during the convolution
+#pragma unroll
+            for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? __ldg(a.lik_table + t * (long long)n + i0 + m) : 0.0;
+        }
         const bool trans = (t > 0 || (a.flags & BLG_F_TRANSITION_FIRST)) && (t - 1 >= s.f_lo) && (t - 1 < s.f_hi);
         if (owner) {
             if (trans && s.R > 0) {
@@ -235,8 +241,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
         // alpha <- prior * likelihood; norm = sum(alpha)          core.py:375-385
         double part = 0.0;
         if (owner) {
-            double lk[M];
-            lik_cells<M>(a, s.tb, s0, sc, t, i0, n, lk);
+            if (pb.om_kind != BLG_OM_TABLE) lik_cells<M>(a, s.tb, s0, sc, t, i0, n, lk);
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 v[m] = i0 + m < n ? v[m] * lk[m] : 0.0;
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
             dead = true;
             break;
         }
-        const double inv = 1.0 / norm;
+        const double inv = fast_rcp(norm);
         if (owner) {
 #pragma unroll
             for (int m = 0; m < M; ++m) {
@@ -343,7 +348,13 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
         }
         const StepC *sc = a.steps + i * nce;
         StepC s0;
-        if (pb.om_kind != BLG_OM_TABLE) s0 = sc[0];
+        double lk[M];
+        if (pb.om_kind != BLG_OM_TABLE) {
+            s0 = sc[0];
+        } else if (owner) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? __ldg(a.lik_table + i * (long long)n + i0 + m) : 0.0;
+        }
         double al[M];
         double pab = 0.0, pb_ = 0.0;
         if (owner) {
@@ -356,23 +367,22 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
             }
         }
         block_sum2(pab, pb_, s.rs);       // sum(alpha*beta) and sum(beta) in one barrier
-        const double binv = 1.0 / pb_;     // core.py:470 (normalisation of beta, applied lazily)
+        const double binv = fast_rcp(pb_);  // core.py:470 (normalisation of beta, applied lazily)
         if (!(pab * binv > 0.0)) {         // core.py:440-452
             dead = true;
             break;
         }
-        const double inv = 1.0 / pab;      // posterior = alpha*beta / sum(alpha*beta): the scale of beta cancels
+        const double inv = fast_rcp(pab);   // posterior = alpha*beta / sum(alpha*beta): the scale of beta cancels
         double q = 0.0;
         if (owner) {
-            double lk[M];
-            lik_cells<M>(a, s.tb, s0, sc, i, i0, n, lk);  // core.py:455
+            if (pb.om_kind != BLG_OM_TABLE) lik_cells<M>(a, s.tb, s0, sc, i, i0, n, lk);  // core.py:455
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 const int li = i0 + m;
                 if (li < n) {
                     const double p = al[m] * beta[m] * inv;  // core.py:436-441
                     const double lik = lk[m];
-                    q += p / lik;                            // core.py:463
+                    q += fast_div(p, lik);                   // core.py:463
                     if (acc) {
                         if (wgt > 0.0) atomicAdd(a.avg + i * (long long)n + li, wgt * (p < kTiny ? kTiny : p));
                     } else {
@@ -384,7 +394,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
         }
         q = block_sum(q, s.rs);  // also publishes the new state for the convolution
         if (staged && service && i >= 2) bulk_load(S[sb], seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
-        if (service && a.local) a.local[b * T + i] = 1.0 / (q * pb.lc_prod);
+        if (service && a.local) a.local[b * T + i] = fast_div(1.0, q * pb.lc_prod);
         const bool trans = (i >= s.b_lo) && (i < s.b_hi);
         if (owner) {
             if (trans && s.R > 0) {

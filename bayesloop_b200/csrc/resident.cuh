@@ -135,7 +135,7 @@ __device__ __forceinline__ void apply_ops(const PassArgs &a, Resident &r, long l
                 r.cur[g] = v;
                 part += v;
             }
-            const double inv = 1.0 / block_sum(part, r.rs);
+            const double inv = fast_rcp(block_sum(part, r.rs));
             for (int g = threadIdx.x; g < G; g += blockDim.x) r.cur[g] *= inv;
             __syncthreads();
         } else if (kind == BLG_OP_RESET) {  // transitionModels.py:300-312, :350-360, :801-813
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_resident_kernel(const PassArgs a
             dead = true;
             break;
         }
-        const double inv = 1.0 / norm;
+        const double inv = fast_rcp(norm);
         if (store && !bulk) {
             double *row = seq + t * (long long)G;
             for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
             dead = true;
             break;
         }
-        const double inv = 1.0 / norm;
+        const double inv = fast_rcp(norm);
         const StepC *sc = a.steps + i * nce;
         double *row = seq + i * (long long)G;
         double *av = acc ? a.avg + i * (long long)G : nullptr;
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
             const double p = A[c.g] * beta * inv;
             const double lik = pb.om_kind == BLG_OM_TABLE ? __ldg(a.lik_table + i * (long long)G + c.g)
                                                           : lik_cell(pb, r.tb, sc, c.i0, c.i1);  // core.py:455
-            q += p / lik;                                                                        // core.py:463
+            q += fast_div(p, lik);                                                               // core.py:463
             if (acc) {
                 if (wgt > 0.0) atomicAdd(av + c.g, wgt * (p < kTiny ? kTiny : p));  // core.py:1362-1366
             } else {
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
         apply_ops<STREAM>(a, r, i, true, b, sm);
         part = 0.0;
         for (int g = threadIdx.x; g < G; g += blockDim.x) part += r.cur[g];
-        const double binv = 1.0 / block_sum(part, r.rs);  // core.py:470
+        const double binv = fast_rcp(block_sum(part, r.rs));  // core.py:470
         for (int g = threadIdx.x; g < G; g += blockDim.x) r.cur[g] *= binv;
     }
     if (dead && staged && i >= 1) mbar_wait(&bars[(i - 1) & 1], ph[(i - 1) & 1]);  // drain the prefetch in flight
