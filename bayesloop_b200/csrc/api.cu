@@ -37,7 +37,8 @@ int fail(const char *fmt, const char *detail = "") {
 
 inline int even_up(int x) { return (x + 1) & ~1; }
 
-constexpr int kMiscDoubles = 192;  // reduction scratch (128) + params (16) + radius/window ints (40) + 2 mbarriers
+constexpr int kMiscDoubles = 384;  // reduction scratch (128) + params (16) + radius/window ints (40) + 2 mbarriers
+                                   // + per-warp partial sums of the fast 1-D kernels (192)
 constexpr size_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 
 }  // namespace
@@ -303,7 +304,7 @@ bool resident_layout(const blg_plan *pl, const blg_program &pg, bool backward, b
 
 // Fast path (fast1d.cuh): 1-D grid, program = one GaussianRandomWalk, halo <= n, one work item per thread.
 bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int M, PassArgs &a, Layout &lay) {
-    const DevProblem &d = pl->dev;
+    const DevProblem &d = a.pb;  // om_kind is TABLE when the shared likelihood table is in use
     if (getenv("BLG_NO_FAST1D")) return false;
     if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
     const int halo = even_up(pg.max_radius[0] + 2 * M);
@@ -318,10 +319,13 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int
     a.off_stage = -1;
     if (backward) {
         a.off_stage = off;
-        off += a.Gp;
+        off += 2 * a.Gp;
     }
-    a.off_tab = off;
-    off += 3 * a.n0p;
+    a.off_tab = -1;
+    if (d.om_kind != BLG_OM_TABLE) {
+        a.off_tab = off;
+        off += 3 * a.n0p;
+    }
     a.off_w = off;
     const int taps = 2 * pg.max_radius[0] + 1;
     a.pg.w_off[0] = 0;
@@ -393,7 +397,7 @@ int launch_stream(K kernel, blg_plan *pl, PassArgs &a, const Layout &lay, long l
 // sub-partition), 7 in the backward pass (more live registers per cell); measured on B200, see profiles/
 int fast_m(bool backward) {
     const char *e = getenv(backward ? "BLG_FAST_M_BWD" : "BLG_FAST_M");
-    const int m = e ? atoi(e) : (backward ? 7 : 9);
+    const int m = e ? atoi(e) : 9;
     return (m == 5 || m == 7 || m == 9) ? m : 7;
 }
 

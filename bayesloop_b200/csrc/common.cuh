@@ -27,6 +27,7 @@ constexpr double kTiny = 1e-300; // clip of core.py:1362
 // "misc" region of the resident kernels (doubles): [0,128) reduction scratch, [128,144) per-op parameters,
 // [144,152) radii (16 ints), [152,184) windows (64 ints), [184,186) two mbarriers
 constexpr int kMiscBarrierOffset = 184;
+constexpr int kMiscPartialOffset = 192;  // fast 1-D kernels: [2][3][kMaxWarps] partial sums (192 doubles)
 
 // ------------------------------------------------------------------------------------------------ structures
 struct DevProblem {

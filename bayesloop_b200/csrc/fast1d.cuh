@@ -1,16 +1,22 @@
 // fast1d.cuh -- K1f/K2f: specialisation of the resident kernels for the headline shape of the sweep: a 1-D grid and
 // a transition program that is ONE GaussianRandomWalk (BASELINE.json configs[0], configs[1]).
 //
-// Differences to the generic resident kernels (resident.cuh):
+// The time recursion is a chain of T dependent steps per combo, and a sweep only has a few hundred combos, so the
+// kernels are built to minimise the LATENCY of one step (measured on B200, see profiles/):
 //   * the state lives in shared memory WITH a reflected halo on both sides (every writer mirrors the cells near
-//     the edges), so the convolution inner loop is one LDS + M FMAs per tap with no boundary logic at all;
-//   * each thread owns M consecutive cells for the whole kernel; the convolution outputs stay in REGISTERS and are
-//     consumed in place by the likelihood multiply (forward) / the posterior product (backward), so a time step
-//     needs two CTA barriers only (reduction; state visible) instead of four to six;
-//   * forward: alpha[t] leaves through one bulk-async (TMA) store per step that overlaps the next convolution;
-//     backward: alpha[t] arrives through a double-buffered bulk-async prefetch (mbarrier complete_tx);
-//   * backward: the normalisation of beta rides on the same reduction as sum(alpha*beta) (block_sum2).
-// Semantics are identical (core.py:372-417, :424-470; transitionModels.py:96-115).
+//     the edges): the convolution inner loop is one LDS + M FMAs per tap, no boundary logic;
+//   * each thread owns M consecutive cells for the whole kernel; convolution outputs stay in REGISTERS and are
+//     consumed in place by the likelihood multiply (forward) / the posterior product (backward);
+//   * ONE CTA barrier per step: the state is kept UNNORMALISED in shared memory and double buffered; its sum (the
+//     evidence increment) is reduced with warp shuffles + one shared-memory exchange that rides on that barrier,
+//     and the normaliser is applied lazily in the next step's multiply -- the reduction, the reciprocal and the
+//     log-evidence bookkeeping leave the critical path.  Rows written to HBM are normalised exactly as before
+//     (from registers, after the barrier);
+//   * the likelihood row lik[t][.] (shared by all combos of the call, L2 resident) is fetched before the
+//     convolution and consumed after it; backward: alpha[t] arrives through a double-buffered bulk-async (TMA)
+//     prefetch with mbarrier completion, two steps ahead.
+// Semantics are identical (core.py:372-417, :424-470; transitionModels.py:96-115): every quantity the reference
+// normalises is either scale-free downstream (beta, alpha inside the backward product) or normalised on output.
 #pragma once
 
 #include "common.cuh"
@@ -145,6 +151,7 @@ __device__ __forceinline__ void lik_cells(const PassArgs &a, const LikTables &tb
 struct Fast1dSetup {
     double *buf0, *buf1;  // interior pointers of the two haloed state buffers
     double *W;
+    double *P;            // per-warp partial sums: [2 parities][3 values][kMaxWarps]
     LikTables tb;
     RedScratch rs;
     double sigma;
@@ -157,20 +164,23 @@ __device__ __forceinline__ void fast1d_setup(const PassArgs &a, double *sm, long
     const int halo = a.halo, pitch = a.Gp + 2 * halo;
     s.buf0 = sm + halo;
     s.buf1 = sm + pitch + halo;
-    double *tab = sm + a.off_tab;
-    double *A0 = tab, *A1 = A0 + a.n0p, *A2 = A1 + a.n0p;
-    for (int i = threadIdx.x; i < pb.n0; i += blockDim.x) {
-        A0[i] = pb.tabA[0] ? pb.tabA[0][i] : 0.0;
-        A1[i] = pb.tabA[1] ? pb.tabA[1][i] : 0.0;
-        A2[i] = pb.tabA[2] ? pb.tabA[2][i] : 0.0;
+    if (a.off_tab >= 0) {  // per-cell tables only when the likelihood is evaluated in the pass (no shared table)
+        double *tab = sm + a.off_tab;
+        double *A0 = tab, *A1 = A0 + a.n0p, *A2 = A1 + a.n0p;
+        for (int i = threadIdx.x; i < pb.n0; i += blockDim.x) {
+            A0[i] = pb.tabA[0] ? pb.tabA[0][i] : 0.0;
+            A1[i] = pb.tabA[1] ? pb.tabA[1][i] : 0.0;
+            A2[i] = pb.tabA[2] ? pb.tabA[2][i] : 0.0;
+        }
+        s.tb.A0 = A0;
+        s.tb.A1 = A1;
+        s.tb.A2 = A2;
+        s.tb.B0 = A0;
+        s.tb.B1 = A0;
     }
-    s.tb.A0 = A0;
-    s.tb.A1 = A1;
-    s.tb.A2 = A2;
-    s.tb.B0 = A0;
-    s.tb.B1 = A0;
     s.rs.buf = sm + a.off_misc;
     s.rs.phase = 0;
+    s.P = sm + a.off_misc + kMiscPartialOffset;
     s.W = sm + a.off_w;
     s.sigma = a.pg.param[b];
     s.R = a.pg.radius[b];
@@ -181,6 +191,18 @@ __device__ __forceinline__ void fast1d_setup(const PassArgs &a, double *sm, long
     s.b_hi = win[3];
     if (!(s.sigma > 0.0) || s.R <= 0) s.R = 0;
     if ((2 * s.R + M) / M * (M + 1) <= a.pg.w_len[0]) build_weights_chunked<M>(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
+}
+
+template <int M>
+__device__ __forceinline__ double tree_sum(const double (&x)[M]) {
+    double t[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) t[m] = x[m];
+#pragma unroll
+    for (int w = 1; w < M; w *= 2)
+#pragma unroll
+        for (int m = 0; m + w < M; m += 2 * w) t[m] += t[m + w];
+    return t[0];
 }
 
 // ------------------------------------------------------------------------------------------------ K1f forward
@@ -203,6 +225,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
     const int i0 = threadIdx.x * M;
     const bool owner = i0 < n;
     const bool service = threadIdx.x == blockDim.x - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     double *cur = s.buf0, *nxt = s.buf1;
     {
         const double *init = (a.flags & BLG_F_INIT_STATE) ? a.init_state + b * (long long)n : a.prior;
@@ -211,25 +234,26 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
     __syncthreads();
 
     const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
-    const bool bulk = store && a.use_bulk;
     double *seq = store ? a.alpha_seq + b * T * (long long)n : nullptr;
     const int nce = pb.ncols_eff;
+    const bool table = pb.om_kind == BLG_OM_TABLE;
     LogProduct lp;
     lp.init();
     bool dead = false;
+    double kappa = 1.0;  // 1 / sum of the state in `cur` (the normaliser of the previous step, applied lazily)
 
     for (long long t = 0; t < T; ++t) {
-        double v[M];
+        double v[M], lk[M];
         const StepC *sc = a.steps + t * nce;
         StepC s0;
-        double lk[M];
-        if (pb.om_kind != BLG_OM_TABLE) {
+        if (!table) {
             s0 = sc[0];  // issued before the convolution, consumed after it
-        } else if (owner) {  // likelihood row of this step (shared by all combos, L2 resident): in flight during the convolution
+        } else if (owner) {  // likelihood row of this step (shared by all combos, L2 resident)
 #pragma unroll
             for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? __ldg(a.lik_table + t * (long long)n + i0 + m) : 0.0;
         }
         const bool trans = (t > 0 || (a.flags & BLG_F_TRANSITION_FIRST)) && (t - 1 >= s.f_lo) && (t - 1 < s.f_hi);
+        double part = 0.0;
         if (owner) {
             if (trans && s.R > 0) {
                 conv_item<M>(cur, i0, s.R, s.W, v);  // transitionModels.py:111
@@ -237,50 +261,43 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
 #pragma unroll
                 for (int m = 0; m < M; ++m) v[m] = cur[i0 + m];
             }
-        }
-        // alpha <- prior * likelihood; norm = sum(alpha)          core.py:375-385
-        double part = 0.0;
-        if (owner) {
-            if (pb.om_kind != BLG_OM_TABLE) lik_cells<M>(a, s.tb, s0, sc, t, i0, n, lk);
+            if (!table) lik_cells<M>(a, s.tb, s0, sc, t, i0, n, lk);
+            // alpha <- prior * likelihood (core.py:375-382); prior = T(alpha[t-1]) carries the lazy normaliser kappa
 #pragma unroll
             for (int m = 0; m < M; ++m) {
-                v[m] = i0 + m < n ? v[m] * lk[m] : 0.0;
-                part += v[m];
+                v[m] = i0 + m < n ? v[m] * kappa * lk[m] : 0.0;
+                if (i0 + m < n) store_mirrored(nxt, i0 + m, n, halo, v[m]);
             }
+            part = tree_sum<M>(v);
         }
-        if (bulk && service && t >= 2) bulk_wait_read<1>();  // the store of step t-2 has released `nxt`
-        const double norm = block_sum(part, s.rs);
+        part = warp_sum(part);
+        double *P = s.P + (t & 1) * 3 * kMaxWarps;
+        if (lane == 0) P[warp] = part;
+        __syncthreads();  // the only barrier of the step: new state and its partial sums are visible
+        double norm = 0.0;  // core.py:385
+        for (int w = 0; w < nw; ++w) norm += P[w];
         if (!(norm > 0.0)) {  // core.py:388-400
             dead = true;
             break;
         }
-        const double inv = fast_rcp(norm);
-        if (owner) {
+        kappa = fast_rcp(norm);
+        if (store && owner) {  // core.py:389, :408 -- normalised filtering distribution, straight from registers
+            double *row = seq + t * (long long)n;
 #pragma unroll
-            for (int m = 0; m < M; ++m) {
-                const int li = i0 + m;
-                if (li < n) {
-                    const double x = v[m] * inv;
-                    store_mirrored(nxt, li, n, halo, x);
-                    if (store && !bulk) __stcs(seq + t * (long long)n + li, x);  // core.py:408
-                }
-            }
+            for (int m = 0; m < M; ++m)
+                if (i0 + m < n) __stcs(row + i0 + m, v[m] * kappa);
         }
         if (service) {
             lp.mul(norm);                                         // core.py:403
             if (a.local) a.local[b * T + t] = norm * pb.lc_prod;  // core.py:404
         }
-        if (bulk) fence_proxy_async();
-        __syncthreads();
-        if (bulk && service) bulk_store(seq + t * (long long)n, nxt, (uint32_t)(n * sizeof(double)));  // core.py:408
         double *tmp = cur;
         cur = nxt;
         nxt = tmp;
     }
-    if (bulk && service) bulk_wait_all();
     if (!dead && (a.flags & BLG_F_SAVE_STATE) && a.final_state) {
         double *fs = a.final_state + b * (long long)n;
-        for (int g = threadIdx.x; g < n; g += blockDim.x) fs[g] = cur[g];
+        for (int g = threadIdx.x; g < n; g += blockDim.x) fs[g] = cur[g] * kappa;
     }
     if (service) {
         double logE = lp.log_value();
@@ -308,12 +325,13 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
     const int i0 = threadIdx.x * M;
     const bool owner = i0 < n;
     const bool service = threadIdx.x == blockDim.x - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     const bool acc = (a.flags & BLG_F_ACCUMULATE) != 0;
     const double wgt = acc ? exp(a.log_weight[b]) : 0.0;
-    double *cur = s.buf0;
+    double *cur = s.buf0, *nxt = s.buf1;
     double *seq = a.alpha_seq + b * T * (long long)n;
     const bool staged = a.use_bulk != 0;
-    double *S[2] = {s.buf1, sm + a.off_stage};  // staging buffers (the second state buffer is free in this pass)
+    double *S[2] = {sm + a.off_stage, sm + a.off_stage + a.Gp};  // alpha[t] staging ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
     uint32_t ph[2] = {0u, 0u};
     const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
@@ -330,14 +348,25 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
         }
     }
     const int nce = pb.ncols_eff;
+    const bool table = pb.om_kind == BLG_OM_TABLE;
     double beta[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) beta[m] = (owner && i0 + m < n) ? 1.0 / (double)n : 0.0;  // core.py:424-425
+    double kb = 1.0;  // keeps the (scale-free) beta recursion in range: 1 / sum(beta) of the previous step
     bool dead = false;
     long long i = T - 1;
 
     for (; i >= 0; --i) {
         const int sb = (int)(i & 1);
+        const StepC *sc = a.steps + i * nce;
+        StepC s0;
+        double lk[M];
+        if (!table) {
+            s0 = sc[0];
+        } else if (owner) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? __ldg(a.lik_table + i * (long long)n + i0 + m) : 0.0;
+        }
         const double *A;
         if (staged) {
             mbar_wait(&bars[sb], ph[sb]);
@@ -346,55 +375,67 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
         } else {
             A = seq + i * (long long)n;
         }
-        const StepC *sc = a.steps + i * nce;
-        StepC s0;
-        double lk[M];
-        if (pb.om_kind != BLG_OM_TABLE) {
-            s0 = sc[0];
-        } else if (owner) {
-#pragma unroll
-            for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? __ldg(a.lik_table + i * (long long)n + i0 + m) : 0.0;
-        }
-        double al[M];
-        double pab = 0.0, pb_ = 0.0;
+        double pu[M];
+        double spu = 0.0, sbeta = 0.0, sql = 0.0;
         if (owner) {
+            if (!table) lik_cells<M>(a, s.tb, s0, sc, i, i0, n, lk);  // core.py:455
+            double ql[M];
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 const int li = i0 + m;
-                al[m] = li < n ? A[li] : 0.0;
-                pab = fma(al[m], beta[m], pab);
-                pb_ += beta[m];
+                const double al = li < n ? A[li] : 0.0;
+                pu[m] = al * beta[m];                                      // posterior ~ alpha*beta   core.py:436
+                ql[m] = li < n ? fast_div(pu[m], lk[m]) : 0.0;             // core.py:463
+                if (li < n) store_mirrored(nxt, li, n, halo, beta[m] * kb * lk[m]);  // beta*likelihood  core.py:467
             }
+            spu = tree_sum<M>(pu);
+            sbeta = tree_sum<M>(beta);
+            sql = tree_sum<M>(ql);
         }
-        block_sum2(pab, pb_, s.rs);       // sum(alpha*beta) and sum(beta) in one barrier
-        const double binv = fast_rcp(pb_);  // core.py:470 (normalisation of beta, applied lazily)
-        if (!(pab * binv > 0.0)) {         // core.py:440-452
+        spu = warp_sum(spu);
+        sbeta = warp_sum(sbeta);
+        sql = warp_sum(sql);
+        double *P = s.P + (i & 1) * 3 * kMaxWarps;
+        if (lane == 0) {
+            P[warp] = spu;
+            P[kMaxWarps + warp] = sbeta;
+            P[2 * kMaxWarps + warp] = sql;
+        }
+        __syncthreads();  // the only barrier of the step
+        spu = 0.0;
+        sbeta = 0.0;
+        sql = 0.0;
+        for (int w = 0; w < nw; ++w) {
+            spu += P[w];
+            sbeta += P[kMaxWarps + w];
+            sql += P[2 * kMaxWarps + w];
+        }
+        if (!(spu > 0.0) || !(sbeta > 0.0)) {  // core.py:440-452
             dead = true;
             break;
         }
-        const double inv = fast_rcp(pab);   // posterior = alpha*beta / sum(alpha*beta): the scale of beta cancels
-        double q = 0.0;
+        if (staged && service && i >= 2)  // everybody is past the barrier: the staging slot is free again
+            bulk_load(S[sb], seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
+        const double inv = fast_rcp(spu);  // posterior = alpha*beta / sum(alpha*beta)   core.py:439-441
+        kb = fast_rcp(sbeta);              // core.py:470, applied lazily (beta only enters scale-free expressions)
         if (owner) {
-            if (pb.om_kind != BLG_OM_TABLE) lik_cells<M>(a, s.tb, s0, sc, i, i0, n, lk);  // core.py:455
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 const int li = i0 + m;
                 if (li < n) {
-                    const double p = al[m] * beta[m] * inv;  // core.py:436-441
-                    const double lik = lk[m];
-                    q += fast_div(p, lik);                   // core.py:463
+                    const double p = pu[m] * inv;
                     if (acc) {
                         if (wgt > 0.0) atomicAdd(a.avg + i * (long long)n + li, wgt * (p < kTiny ? kTiny : p));
                     } else {
                         __stcs(seq + i * (long long)n + li, p);
                     }
-                    store_mirrored(cur, li, n, halo, beta[m] * binv * lik);  // core.py:467: beta*likelihood
                 }
             }
         }
-        q = block_sum(q, s.rs);  // also publishes the new state for the convolution
-        if (staged && service && i >= 2) bulk_load(S[sb], seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
-        if (service && a.local) a.local[b * T + i] = fast_div(1.0, q * pb.lc_prod);
+        if (service && a.local) a.local[b * T + i] = fast_div(spu, sql * pb.lc_prod);  // 1/(sum(post/lik)*lc)  core.py:463
+        double *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
         const bool trans = (i >= s.b_lo) && (i < s.b_hi);
         if (owner) {
             if (trans && s.R > 0) {
