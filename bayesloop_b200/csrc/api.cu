@@ -319,16 +319,12 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int
     a.off_stage = -1;
     if (backward) {
         a.off_stage = off;
-        off += 3 * a.Gp;
+        off += 2 * a.Gp;
     }
     a.off_tab = -1;
-    a.off_lik = -1;
     if (d.om_kind != BLG_OM_TABLE) {
         a.off_tab = off;
         off += 3 * a.n0p;
-    } else {
-        a.off_lik = off;
-        off += 2 * a.Gp;
     }
     a.off_w = off;
     const int taps = 2 * pg.max_radius[0] + 1;
@@ -484,7 +480,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
     const int M = fast_m(false);
     if (fast1d_layout(pl, in->prog, false, M, a, lay)) {
-        a.use_bulk = ((pl->dev.G % 2 == 0) && !getenv("BLG_NO_BULK")) ? 1 : 0;  // 16-byte aligned likelihood rows
+        a.use_bulk = bulkOk ? 1 : 0;
 #define BLG_FWD_FAST(MM)                                                                                           \
     if (M == MM) {                                                                                                 \
         if (lay.nt <= 128) return launch_resident(fwd_fast1d_kernel<MM, 128, 4>, a, lay, in->B, st, "fwd_fast1d"); \

@@ -25,7 +25,7 @@ constexpr int kConvM = 5;        // outputs per work item of the convolution; od
 constexpr int kMaxWarps = 32;
 constexpr double kTiny = 1e-300; // clip of core.py:1362
 // "misc" region of the resident kernels (doubles): [0,128) reduction scratch, [128,144) per-op parameters,
-// [144,152) radii (16 ints), [152,184) windows (64 ints), [184,189) up to five mbarriers
+// [144,152) radii (16 ints), [152,184) windows (64 ints), [184,186) two mbarriers
 constexpr int kMiscBarrierOffset = 184;
 constexpr int kMiscPartialOffset = 192;  // fast 1-D kernels: [2][3][kMaxWarps] partial sums (192 doubles)
 
@@ -77,7 +77,6 @@ struct PassArgs {
     double *scratch;     // stream kernels: [gridDim.x][2][Gp] state buffers in global memory (L2 resident)
     int off_tile;        // stream kernels: offset (doubles) and size of the shared-memory convolution tile
     int tile_doubles;
-    int off_lik;         // fast 1-D kernels: offset (doubles) of the 2-slot likelihood-row ring, or -1
     int halo;            // fast 1-D kernels: reflected halo cells on each side of the state (0 = generic kernels)
 };
 

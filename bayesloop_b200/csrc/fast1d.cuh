@@ -237,24 +237,6 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
     double *seq = store ? a.alpha_seq + b * T * (long long)n : nullptr;
     const int nce = pb.ncols_eff;
     const bool table = pb.om_kind == BLG_OM_TABLE;
-    // likelihood rows lik[t][.] (shared by all combos, L2 resident) arrive through a 2-slot bulk-async (TMA) ring
-    const bool ring = table && a.use_bulk;
-    double *const Lbase = sm + a.off_lik;
-    uint64_t *lbar = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
-    uint32_t lphbits = 0u;
-    const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
-    if (ring) {
-        if (threadIdx.x == 0) {
-            mbar_init(&lbar[0], 1);
-            mbar_init(&lbar[1], 1);
-            fence_proxy_async();
-        }
-        __syncthreads();
-        if (service) {
-            bulk_load(Lbase, a.lik_table, rowBytes, &lbar[0]);
-            if (T >= 2) bulk_load(Lbase + a.Gp, a.lik_table + n, rowBytes, &lbar[1]);
-        }
-    }
     LogProduct lp;
     lp.init();
     bool dead = false;
@@ -266,7 +248,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
         StepC s0;
         if (!table) {
             s0 = sc[0];  // issued before the convolution, consumed after it
-        } else if (!ring && owner) {
+        } else if (owner) {  // likelihood row of this step (shared by all combos, L2 resident)
 #pragma unroll
             for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? __ldg(a.lik_table + t * (long long)n + i0 + m) : 0.0;
         }
@@ -280,12 +262,6 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
                 for (int m = 0; m < M; ++m) v[m] = cur[i0 + m];
             }
             if (!table) lik_cells<M>(a, s.tb, s0, sc, t, i0, n, lk);
-            if (ring) {
-                mbar_wait(&lbar[t & 1], (lphbits >> (t & 1)) & 1u);
-                const double *Lr = Lbase + (t & 1) * a.Gp;
-#pragma unroll
-                for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? Lr[i0 + m] : 0.0;
-            }
             // alpha <- prior * likelihood (core.py:375-382); prior = T(alpha[t-1]) carries the lazy normaliser kappa
 #pragma unroll
             for (int m = 0; m < M; ++m) {
@@ -305,14 +281,11 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
             break;
         }
         kappa = fast_rcp(norm);
-        if (ring) {
-            lphbits ^= 1u << (t & 1);  // every thread consumed (or skipped) this phase of slot t&1
-            if (service && t + 2 < T)
-                bulk_load(Lbase + (t & 1) * a.Gp, a.lik_table + (t + 2) * (long long)n, rowBytes, &lbar[t & 1]);
-        }
-        if (store) {  // core.py:389, :408 -- normalised filtering distribution, coalesced rows out of shared memory
+        if (store && owner) {  // core.py:389, :408 -- normalised filtering distribution, straight from registers
             double *row = seq + t * (long long)n;
-            for (int g = threadIdx.x; g < n; g += blockDim.x) __stcs(row + g, nxt[g] * kappa);
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                if (i0 + m < n) __stcs(row + i0 + m, v[m] * kappa);
         }
         if (service) {
             lp.mul(norm);                                         // core.py:403
@@ -358,33 +331,24 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
     double *cur = s.buf0, *nxt = s.buf1;
     double *seq = a.alpha_seq + b * T * (long long)n;
     const bool staged = a.use_bulk != 0;
-    // alpha[t] ring: 3 slots, slot(i) = i % 3.  The thread's cells of the slot are overwritten in place by the
-    // unnormalised posterior, which leaves after the barrier as coalesced rows; the slot is refilled two steps later.
-    double *const Sbase = sm + a.off_stage;
+    double *S[2] = {sm + a.off_stage, sm + a.off_stage + a.Gp};  // alpha[t] staging ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
-    uint32_t phbits = 0u;  // bit k: phase parity of mbarrier k (0-2 alpha slots, 3-4 likelihood slots)
+    uint32_t ph[2] = {0u, 0u};
     const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
-    const int nce = pb.ncols_eff;
-    const bool table = pb.om_kind == BLG_OM_TABLE;
-    const bool ring = table && staged;  // likelihood rows through a 2-slot bulk-async ring as well
-    double *const Lbase = sm + a.off_lik;
-    uint64_t *lbar = bars + 3;
     if (staged) {
         if (threadIdx.x == 0) {
-            for (int k = 0; k < 5; ++k) mbar_init(&bars[k], 1);
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
             fence_proxy_async();
         }
         __syncthreads();
         if (service) {
-            bulk_load(Sbase + ((T - 1) % 3) * a.Gp, seq + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) % 3]);
-            if (T >= 2) bulk_load(Sbase + ((T - 2) % 3) * a.Gp, seq + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) % 3]);
-            if (ring) {
-                bulk_load(Lbase + ((T - 1) & 1) * a.Gp, a.lik_table + (T - 1) * (long long)n, rowBytes, &lbar[(T - 1) & 1]);
-                if (T >= 2)
-                    bulk_load(Lbase + ((T - 2) & 1) * a.Gp, a.lik_table + (T - 2) * (long long)n, rowBytes, &lbar[(T - 2) & 1]);
-            }
+            bulk_load(S[(T - 1) & 1], seq + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) & 1]);
+            if (T >= 2) bulk_load(S[(T - 2) & 1], seq + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) & 1]);
         }
     }
+    const int nce = pb.ncols_eff;
+    const bool table = pb.om_kind == BLG_OM_TABLE;
     double beta[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) beta[m] = (owner && i0 + m < n) ? 1.0 / (double)n : 0.0;  // core.py:424-425
@@ -393,33 +357,28 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
     long long i = T - 1;
 
     for (; i >= 0; --i) {
-        const int sb = (int)(i % 3), lb = (int)(i & 1);
+        const int sb = (int)(i & 1);
         const StepC *sc = a.steps + i * nce;
         StepC s0;
         double lk[M];
         if (!table) {
             s0 = sc[0];
-        } else if (!ring && owner) {
+        } else if (owner) {
 #pragma unroll
             for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? __ldg(a.lik_table + i * (long long)n + i0 + m) : 0.0;
         }
-        double *A = Sbase + sb * a.Gp;
+        const double *A;
         if (staged) {
-            if (owner) mbar_wait(&bars[sb], (phbits >> sb) & 1u);
-        } else {  // rows not 16-byte aligned: plain (coalesced) copy of alpha[t] into the slot
-            for (int g = threadIdx.x; g < n; g += blockDim.x) A[g] = seq[i * (long long)n + g];
-            __syncthreads();
+            mbar_wait(&bars[sb], ph[sb]);
+            ph[sb] ^= 1u;
+            A = S[sb];
+        } else {
+            A = seq + i * (long long)n;
         }
         double pu[M];
         double spu = 0.0, sbeta = 0.0, sql = 0.0;
         if (owner) {
             if (!table) lik_cells<M>(a, s.tb, s0, sc, i, i0, n, lk);  // core.py:455
-            if (ring) {
-                mbar_wait(&lbar[lb], (phbits >> (3 + lb)) & 1u);
-                const double *Lr = Lbase + lb * a.Gp;
-#pragma unroll
-                for (int m = 0; m < M; ++m) lk[m] = i0 + m < n ? Lr[i0 + m] : 0.0;
-            }
             double ql[M];
 #pragma unroll
             for (int m = 0; m < M; ++m) {
@@ -427,10 +386,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
                 const double al = li < n ? A[li] : 0.0;
                 pu[m] = al * beta[m];                                      // posterior ~ alpha*beta   core.py:436
                 ql[m] = li < n ? fast_div(pu[m], lk[m]) : 0.0;             // core.py:463
-                if (li < n) {
-                    A[li] = pu[m];                                         // own cells only: no cross-thread hazard
-                    store_mirrored(nxt, li, n, halo, beta[m] * kb * lk[m]);  // beta*likelihood  core.py:467
-                }
+                if (li < n) store_mirrored(nxt, li, n, halo, beta[m] * kb * lk[m]);  // beta*likelihood  core.py:467
             }
             spu = tree_sum<M>(pu);
             sbeta = tree_sum<M>(beta);
@@ -458,24 +414,21 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
             dead = true;
             break;
         }
-        if (staged) {
-            phbits ^= (1u << sb) | (1u << (3 + lb));
-            if (service && i >= 2) {  // slot (i-2)%3 was drained by the coalesced pass of step i+1, one barrier ago
-                const int s2 = (int)((i - 2) % 3);
-                bulk_load(Sbase + s2 * a.Gp, seq + (i - 2) * (long long)n, rowBytes, &bars[s2]);
-                if (ring) bulk_load(Lbase + lb * a.Gp, a.lik_table + (i - 2) * (long long)n, rowBytes, &lbar[lb]);
-            }
-        }
+        if (staged && service && i >= 2)  // everybody is past the barrier: the staging slot is free again
+            bulk_load(S[sb], seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
         const double inv = fast_rcp(spu);  // posterior = alpha*beta / sum(alpha*beta)   core.py:439-441
         kb = fast_rcp(sbeta);              // core.py:470, applied lazily (beta only enters scale-free expressions)
-        {  // smoothed posterior of step i leaves as coalesced rows (core.py:441) / joins the running average
-            double *row = seq + i * (long long)n;
-            for (int g = threadIdx.x; g < n; g += blockDim.x) {
-                const double p = A[g] * inv;
-                if (acc) {
-                    if (wgt > 0.0) atomicAdd(a.avg + i * (long long)n + g, wgt * (p < kTiny ? kTiny : p));
-                } else {
-                    __stcs(row + g, p);
+        if (owner) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int li = i0 + m;
+                if (li < n) {
+                    const double p = pu[m] * inv;
+                    if (acc) {
+                        if (wgt > 0.0) atomicAdd(a.avg + i * (long long)n + li, wgt * (p < kTiny ? kTiny : p));
+                    } else {
+                        __stcs(seq + i * (long long)n + li, p);
+                    }
                 }
             }
         }
@@ -496,10 +449,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
                 if (i0 + m >= n) beta[m] = 0.0;
         }
     }
-    if (dead && staged && i >= 1) {  // drain the prefetches in flight before the CTA (and its shared memory) goes away
-        mbar_wait(&bars[(i - 1) % 3], (phbits >> ((i - 1) % 3)) & 1u);
-        if (ring) mbar_wait(&lbar[(i - 1) & 1], (phbits >> (3 + ((i - 1) & 1))) & 1u);
-    }
+    if (dead && staged && i >= 1) mbar_wait(&bars[(i - 1) & 1], ph[(i - 1) & 1]);  // drain the prefetch in flight
     if (dead && service) {
         a.logE[b] = -INFINITY;
         if (a.alive) a.alive[b] = -1;
