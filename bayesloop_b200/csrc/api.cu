@@ -55,6 +55,8 @@ struct blg_plan {
     long long w_cap;
     double *d_lik;  // internal likelihood table [T][G] shared by the combos of a call
     long long lik_cap;
+    int *d_sm_state;  // per-SM arrival counters + per-combo claim flags (fast 1-D kernels with sm_assign)
+    long long sm_state_cap;
     int serpentine;
 };
 
@@ -182,6 +184,8 @@ int blg_plan_create(const blg_problem *p, blg_plan **out) {
     pl->w_cap = 0;
     pl->d_lik = nullptr;
     pl->lik_cap = 0;
+    pl->d_sm_state = nullptr;
+    pl->sm_state_cap = 0;
     *out = pl;
     return 0;
 }
@@ -192,6 +196,7 @@ void blg_plan_destroy(blg_plan *pl) {
     if (pl->d_steps) cudaFree(pl->d_steps);
     if (pl->d_w) cudaFree(pl->d_w);
     if (pl->d_lik) cudaFree(pl->d_lik);
+    if (pl->d_sm_state) cudaFree(pl->d_sm_state);
     delete pl;
 }
 
@@ -395,6 +400,33 @@ int launch_stream(K kernel, blg_plan *pl, PassArgs &a, const Layout &lay, long l
 
 // outputs per thread of the fast 1-D kernels: 9 in the forward pass (4 full warps per 1000-cell combo, one per SM
 // sub-partition), 7 in the backward pass (more live registers per cell); measured on B200, see profiles/
+// Per-SM assignment (blg_program.sm_assign): zeroed counters / claim flags and a grid of sm_count*sm_slots CTAs.
+int prep_sm_assign(blg_plan *pl, const blg_inputs *in, PassArgs &a, long long &grid, cudaStream_t st) {
+    const blg_program &pg = in->prog;
+    a.sm_assign = nullptr;
+    a.sm_state = nullptr;
+    a.sm_count = 0;
+    a.sm_slots = 0;
+    grid = in->B;
+    if (!pg.sm_assign || pg.sm_count != pl->num_sms || pg.sm_slots < 1 || getenv("BLG_NO_SM_ASSIGN")) return 0;
+    if ((long long)pg.sm_count * pg.sm_slots < in->B) return 0;
+    const long long need = pg.sm_count + in->B;
+    if (need > pl->sm_state_cap) {
+        if (pl->d_sm_state) CUDA_TRY(cudaFree(pl->d_sm_state));
+        pl->d_sm_state = nullptr;
+        pl->sm_state_cap = 0;
+        CUDA_TRY(cudaMalloc(&pl->d_sm_state, (size_t)need * sizeof(int)));
+        pl->sm_state_cap = need;
+    }
+    CUDA_TRY(cudaMemsetAsync(pl->d_sm_state, 0, (size_t)need * sizeof(int), st));
+    a.sm_assign = pg.sm_assign;
+    a.sm_state = pl->d_sm_state;
+    a.sm_count = pg.sm_count;
+    a.sm_slots = pg.sm_slots;
+    grid = (long long)pg.sm_count * pg.sm_slots;
+    return 0;
+}
+
 int fast_m(bool backward) {
     const char *e = getenv(backward ? "BLG_FAST_M_BWD" : "BLG_FAST_M");
     const int m = e ? atoi(e) : 9;
@@ -481,12 +513,14 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     const int M = fast_m(false);
     if (fast1d_layout(pl, in->prog, false, M, a, lay)) {
         a.use_bulk = bulkOk ? 1 : 0;
+        long long grid = in->B;
+        if (prep_sm_assign(pl, in, a, grid, st)) return -1;
 #define BLG_FWD_FAST(MM)                                                                                           \
     if (M == MM) {                                                                                                 \
-        if (lay.nt <= 128) return launch_resident(fwd_fast1d_kernel<MM, 128, 4>, a, lay, in->B, st, "fwd_fast1d"); \
-        if (lay.nt <= 160) return launch_resident(fwd_fast1d_kernel<MM, 160, 4>, a, lay, in->B, st, "fwd_fast1d"); \
-        if (lay.nt <= 256) return launch_resident(fwd_fast1d_kernel<MM, 256, 4>, a, lay, in->B, st, "fwd_fast1d"); \
-        return launch_resident(fwd_fast1d_kernel<MM, 1024, 1>, a, lay, in->B, st, "fwd_fast1d");                   \
+        if (lay.nt <= 128) return launch_resident(fwd_fast1d_kernel<MM, 128, 4>, a, lay, grid, st, "fwd_fast1d"); \
+        if (lay.nt <= 160) return launch_resident(fwd_fast1d_kernel<MM, 160, 4>, a, lay, grid, st, "fwd_fast1d"); \
+        if (lay.nt <= 256) return launch_resident(fwd_fast1d_kernel<MM, 256, 4>, a, lay, grid, st, "fwd_fast1d"); \
+        return launch_resident(fwd_fast1d_kernel<MM, 1024, 1>, a, lay, grid, st, "fwd_fast1d");                   \
     }
         BLG_FWD_FAST(5)
         BLG_FWD_FAST(7)
@@ -521,12 +555,14 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     const int M = fast_m(true);
     if (fast1d_layout(pl, in->prog, true, M, a, lay)) {
         a.use_bulk = alignedRows ? 1 : 0;
+        long long grid = in->B;
+        if (prep_sm_assign(pl, in, a, grid, st)) return -1;
 #define BLG_BWD_FAST(MM)                                                                                           \
     if (M == MM) {                                                                                                 \
-        if (lay.nt <= 128) return launch_resident(bwd_fast1d_kernel<MM, 128, 4>, a, lay, in->B, st, "bwd_fast1d"); \
-        if (lay.nt <= 160) return launch_resident(bwd_fast1d_kernel<MM, 160, 4>, a, lay, in->B, st, "bwd_fast1d"); \
-        if (lay.nt <= 256) return launch_resident(bwd_fast1d_kernel<MM, 256, 4>, a, lay, in->B, st, "bwd_fast1d"); \
-        return launch_resident(bwd_fast1d_kernel<MM, 1024, 1>, a, lay, in->B, st, "bwd_fast1d");                   \
+        if (lay.nt <= 128) return launch_resident(bwd_fast1d_kernel<MM, 128, 4>, a, lay, grid, st, "bwd_fast1d"); \
+        if (lay.nt <= 160) return launch_resident(bwd_fast1d_kernel<MM, 160, 4>, a, lay, grid, st, "bwd_fast1d"); \
+        if (lay.nt <= 256) return launch_resident(bwd_fast1d_kernel<MM, 256, 4>, a, lay, grid, st, "bwd_fast1d"); \
+        return launch_resident(bwd_fast1d_kernel<MM, 1024, 1>, a, lay, grid, st, "bwd_fast1d");                   \
     }
         BLG_BWD_FAST(5)
         BLG_BWD_FAST(7)

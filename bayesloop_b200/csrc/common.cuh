@@ -74,6 +74,9 @@ struct PassArgs {
     int serpentine;      // 1: blockIdx -> combo mapping alternates direction per 148-block wave
     int num_sms;
     const int *order;    // device [B] launch order (descending cost) or NULL
+    const int *sm_assign;  // device [sm_count][sm_slots] per-SM combo table or NULL
+    int *sm_state;       // device [sm_count + B]: per-SM arrival counters, then per-combo claim flags (zeroed per launch)
+    int sm_count, sm_slots;
     double *scratch;     // stream kernels: [gridDim.x][2][Gp] state buffers in global memory (L2 resident)
     int off_tile;        // stream kernels: offset (doubles) and size of the shared-memory convolution tile
     int tile_doubles;
@@ -91,6 +94,43 @@ __device__ __forceinline__ long long combo_of_block(const PassArgs &a) {
         }
     }
     return j;
+}
+
+// Combo of this CTA when the caller supplied a per-SM assignment (blg_program.sm_assign): the CTA looks up the SM it
+// runs on, takes the next slot of that SM's list, and claims the combo.  CTAs that arrive after an SM's list is
+// exhausted (only possible if the hardware did not co-schedule the whole grid) adopt any combo still unclaimed, so
+// every combo is processed exactly once whatever the placement.  Returns -1 when there is nothing to do.
+__device__ __forceinline__ long long combo_of_sm(const PassArgs &a, int *shared_slot) {
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        int b = -1;
+        int *counters = a.sm_state, *claimed = a.sm_state + a.sm_count;
+        if ((int)smid < a.sm_count) {
+            const int k = atomicAdd(&counters[smid], 1);
+            if (k < a.sm_slots) {
+                b = a.sm_assign[smid * a.sm_slots + k];
+                if (b >= 0 && atomicCAS(&claimed[b], 0, 1) != 0) b = -1;
+            } else {
+                b = -2;  // late arrival: adopt an orphan
+            }
+        } else {
+            b = -2;
+        }
+        if (b == -2) {
+            b = -1;
+            for (long long j = 0; j < a.B; ++j) {
+                const int cand = a.order ? a.order[j] : (int)j;
+                if (atomicCAS(&claimed[cand], 0, 1) == 0) {
+                    b = cand;
+                    break;
+                }
+            }
+        }
+        *shared_slot = b;
+    }
+    __syncthreads();
+    return *shared_slot;
 }
 
 // ------------------------------------------------------------------------------------------------ reductions

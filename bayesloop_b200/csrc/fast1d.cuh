@@ -210,7 +210,9 @@ template <int M, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    const long long b = a.order ? a.order[combo_of_block(a)] : combo_of_block(a);
+    const long long b = a.sm_assign ? combo_of_sm(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6))
+                                    : (a.order ? a.order[combo_of_block(a)] : combo_of_block(a));
+    if (b < 0) return;
     const int n = pb.G, halo = a.halo;
     const long long T = a.T;
     Fast1dSetup s;
@@ -315,7 +317,9 @@ template <int M, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    const long long b = a.order ? a.order[combo_of_block(a)] : combo_of_block(a);
+    const long long b = a.sm_assign ? combo_of_sm(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6))
+                                    : (a.order ? a.order[combo_of_block(a)] : combo_of_block(a));
+    if (b < 0) return;
     if (a.alive && a.alive[b] != 1) return;  // the forward pass aborted (core.py:400)
     const int n = pb.G, halo = a.halo;
     const long long T = a.T;

@@ -38,7 +38,8 @@ class _Problem(ctypes.Structure):
 class _Program(ctypes.Structure):
     _fields_ = [('n_ops', ctypes.c_int32), ('kind', ctypes.c_int32 * MAX_OPS), ('axis', ctypes.c_int32 * MAX_OPS),
                 ('max_radius', ctypes.c_int32 * MAX_OPS), ('param', ctypes.c_void_p), ('radius', ctypes.c_void_p),
-                ('window', ctypes.c_void_p), ('order', ctypes.c_void_p)]
+                ('window', ctypes.c_void_p), ('order', ctypes.c_void_p), ('sm_assign', ctypes.c_void_p),
+                ('sm_count', ctypes.c_int32), ('sm_slots', ctypes.c_int32)]
 
 
 class _Inputs(ctypes.Structure):
@@ -95,7 +96,35 @@ class Program:
         p.radius = self.radius.data_ptr() + lo * K * 4
         p.window = self.window.data_ptr() + lo * K * 16
         p.order = self._order(lo, hi).data_ptr() if hi - lo > 1 else None
+        sms = self._engine.sm_count()
+        p.sm_assign, p.sm_count, p.sm_slots = None, 0, 0
+        if sms > 0 and hi - lo > sms:
+            table = self._assignment(lo, hi, sms)
+            if table is not None:
+                p.sm_assign, p.sm_count, p.sm_slots = table.data_ptr(), sms, table.shape[1]
         return p
+
+    def _assignment(self, lo, hi, sms, slots=4):
+        """Combos of one call pre-assigned to SMs: longest-processing-time-first into `sms` bins of `slots`
+        entries.  Cost per time step of a chain ~ fixed bookkeeping + taps of its convolutions (measured on B200:
+        1.6 us + 0.0105 us per tap for a 1000-cell grid); heavy chains end up with fewer / lighter neighbours."""
+        if hi - lo > sms * slots:
+            return None
+        key = (lo, hi, sms, slots)
+        if key not in self._orders:
+            taps = (2 * self.host['radius'][lo:hi] + 1).sum(axis=1).astype(float)
+            cost = 1.6 + 0.0105 * taps
+            table = np.full((sms, slots), -1, dtype=np.int32)
+            load = np.zeros(sms)
+            fill = np.zeros(sms, dtype=np.int64)
+            for b in np.argsort(-cost, kind='stable'):
+                open_bins = np.flatnonzero(fill < slots)
+                sm = open_bins[np.argmin(load[open_bins])]
+                table[sm, fill[sm]] = b
+                fill[sm] += 1
+                load[sm] += cost[b]
+            self._orders[key] = self._engine.to_device(table)
+        return self._orders[key]
 
     def _order(self, lo, hi):
         """Launch order of the combos of one call: most expensive first (cost ~ total convolution radius), so that
@@ -167,6 +196,11 @@ class Engine:
 
     def to_host(self, tensor):
         return tensor.detach().cpu().numpy()
+
+    def sm_count(self):
+        if self.device.type == 'cuda':
+            return torch.cuda.get_device_properties(self.device).multi_processor_count
+        return 0
 
     def free_bytes(self):
         if self.device.type == 'cuda':

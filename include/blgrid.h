@@ -95,6 +95,9 @@ typedef struct blg_program {
     const int32_t *window;     /* device [B][n_ops][4]: f_lo, f_hi, b_lo, b_hi                                   */
     const int32_t *order;      /* device [B] or NULL: permutation of the combos in descending cost (sum of radii); */
                                /*   scheduling hint only -- results do not depend on it                           */
+    const int32_t *sm_assign;  /* device [sm_count][sm_slots] or NULL: combos pre-assigned to each SM (-1 = empty),  */
+    int32_t sm_count;          /*   balanced by the caller; persistent CTAs claim the slots of the SM they run on.   */
+    int32_t sm_slots;          /*   Scheduling hint only; every combo must appear exactly once.                     */
 } blg_program;
 
 typedef struct blg_inputs {
