@@ -617,12 +617,12 @@ class HyperStudy(Study):
         ses = _Session(self, eng)
         T, G = ses.T, ses.G
         Ball = len(self.hyperGridValues)
-        lo, hi = dist.shard_bounds(Ball)
-        B = hi - lo
-        hyper = np.asarray(self.hyperGridValues, dtype=float)[lo:hi]
-        hp = np.asarray(self.flatHyperPriorValues, dtype=float)[lo:hi]
+        rows = dist.shard_rows(Ball)
+        B = len(rows)
+        hyper = np.asarray(self.hyperGridValues, dtype=float).reshape(Ball, -1)[rows]
+        hp = np.asarray(self.flatHyperPriorValues, dtype=float)[rows]
         ctx = self._lower(hyper, self.formattedTimestamps)
-        sw = dict(eng=eng, ses=ses, T=T, G=G, Ball=Ball, lo=lo, hi=hi, B=B, hp=hp, ops=ctx.ops,
+        sw = dict(eng=eng, ses=ses, T=T, G=G, Ball=Ball, rows=rows, B=B, hp=hp, ops=ctx.ops,
                   forwardOnly=forwardOnly, evidenceOnly=evidenceOnly)
         sw['program'] = _engine.Program(eng, ctx.ops, B)
         sw['resetBase'] = ses.reset_base() if ctx.usesReset else None
@@ -693,7 +693,7 @@ class HyperStudy(Study):
         if not evidenceOnly:
             dist.rebase_and_reduce(eng, ses.plan, avg, shift, T * G)
             eng.finalize(ses.plan, avg, T, sw['means'], _engine.F_NORMALIZE_ROWS)
-        self.sweepStats = dict(waves=waves, wave=wave, shard=(sw['lo'], sw['hi']), launches=eng.launch_count())
+        self.sweepStats = dict(waves=waves, wave=wave, rows=sw['rows'], launches=eng.launch_count())
         return eng, logEAll, aliveAll, localEv, avg, sw['means']
 
     def _sweep(self, forwardOnly, evidenceOnly):
