@@ -13,6 +13,7 @@
 #include "aux.cuh"
 #include "fast1d.cuh"
 #include "resident.cuh"
+#include "stream2d.cuh"
 
 using namespace blg;
 
@@ -530,6 +531,8 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     a.halo = 0;
     if (!resident_layout(pl, in->prog, false, false, a, lay) || getenv("BLG_FORCE_STREAM")) {
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream forward kernel");
+        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D"))
+            return launch_stream(fwd_stream2d_kernel, pl, a, lay, in->B, st, "fwd_stream2d");
         return launch_stream(fwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "fwd_stream");
     }
     a.use_bulk = bulkOk ? 1 : 0;
@@ -574,6 +577,8 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     if (!fits) fits = false;
     if (getenv("BLG_FORCE_STREAM") || (!fits && !resident_layout(pl, in->prog, true, false, a, lay))) {
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream backward kernel");
+        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D"))
+            return launch_stream(bwd_stream2d_kernel, pl, a, lay, in->B, st, "bwd_stream2d");
         return launch_stream(bwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "bwd_stream");
     }
     a.use_bulk = (fits && a.off_stage >= 0) ? 1 : 0;

@@ -308,10 +308,16 @@ __device__ __forceinline__ int reflect_once(int i, int n) {  // valid while -n <
 // of M (+M).  Work item = M consecutive outputs of one line; the M+2R inputs stream through a register window, so
 // each tap costs one shared-memory load and M FMAs.  Lane->item mapping keeps 64-bit accesses conflict-free:
 // consecutive segments of a line when the axis is contiguous (stride M, M odd), consecutive lines otherwise.
-template <int M, bool SIMPLE>
+struct EpiIdentity {
+    __device__ __forceinline__ double operator()(int, int, double v) const { return v; }
+};
+
+// `epi(line, index, value)` is applied to every output before it is stored (likelihood multiply + partial sums of
+// the 2-D stream kernels).
+template <int M, bool SIMPLE, typename Epi = EpiIdentity>
 __device__ __forceinline__ void conv_lines(const double *__restrict__ src, double *__restrict__ dst,
                                            const double *__restrict__ W, int R, int n, int elemStride, int nLines,
-                                           int lineStride, int dElemStride = -1, int dLineStride = -1) {
+                                           int lineStride, int dElemStride = -1, int dLineStride = -1, Epi epi = Epi()) {
     if (dElemStride < 0) {
         dElemStride = elemStride;
         dLineStride = lineStride;
@@ -353,7 +359,7 @@ __device__ __forceinline__ void conv_lines(const double *__restrict__ src, doubl
         double *out = dst + (size_t)l * dLineStride;
 #pragma unroll
         for (int m = 0; m < M; ++m)
-            if (i0 + m < n) out[(size_t)(i0 + m) * dElemStride] = acc[m];
+            if (i0 + m < n) out[(size_t)(i0 + m) * dElemStride] = epi(l, i0 + m, acc[m]);
     }
 }
 

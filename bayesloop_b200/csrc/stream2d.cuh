@@ -1,0 +1,404 @@
+// stream2d.cuh -- K3f/K4f: forward / backward passes for 2-D grids that do not fit in shared memory (200^2, 256^2,
+// 512^2 ...) when the transition program consists of GaussianRandomWalks (at most one per axis) and prior resets
+// (BASELINE.json configs[2], [3], [4]: Gaussian / ScaledAR1 grids, GRW on both parameters, change-points).
+//
+// One persistent CTA per SM loops over combos.  The state lives in a global scratch that stays in L2 and is kept
+// UNNORMALISED; per time step it is touched by at most two fused tile phases:
+//   phase 1  tiles with complete lines of the first convolution axis are staged in shared memory; on the way in the
+//            previous normaliser is applied (lazily) and the normalised row of the PREVIOUS step is flushed to HBM
+//            (forward) / the smoothed posterior is written and beta*likelihood formed (backward); convolution -> B
+//   phase 2  tiles along the second axis; the epilogue multiplies with the likelihood row of this step, accumulates
+//            the evidence increment (forward) or sum(alpha*beta), sum(beta) for the NEXT step (backward) and writes
+//            the new state.
+// So the only full-grid traffic is: state read/write per phase (L2), the likelihood row (L2, shared by all
+// combos), and the compulsory HBM rows (forward: one store; backward: one load + one store).  Semantics are the
+// same as the generic kernels (core.py:372-417, :434-470; transitionModels.py:96-115, :300-312).
+#pragma once
+
+#include "common.cuh"
+
+namespace blg {
+
+struct Stream2dOps {
+    int k0, k1;        // program index of the GRW acting on axis 0 / axis 1 (-1: none)
+    int pre, post;     // program index of a RESET before all / after all GRWs (-1: none)
+    bool ok;
+};
+
+// Host and device share this classification: which programs the fused 2-D kernels understand.
+__host__ __device__ inline Stream2dOps classify2d(int n_ops, const int *kind, const int *axis) {
+    Stream2dOps o;
+    o.k0 = o.k1 = o.pre = o.post = -1;
+    o.ok = true;
+    int firstGrw = -1, lastGrw = -1;
+    for (int k = 0; k < n_ops; ++k)
+        if (kind[k] == BLG_OP_GRW) {
+            if (firstGrw < 0) firstGrw = k;
+            lastGrw = k;
+            if (axis[k] == 0 && o.k0 < 0)
+                o.k0 = k;
+            else if (axis[k] == 1 && o.k1 < 0)
+                o.k1 = k;
+            else
+                o.ok = false;
+        }
+    for (int k = 0; k < n_ops; ++k) {
+        if (kind[k] == BLG_OP_GRW) continue;
+        if (kind[k] != BLG_OP_RESET) {
+            o.ok = false;
+            continue;
+        }
+        if (firstGrw < 0 || k > lastGrw) {
+            if (o.post < 0)
+                o.post = k;
+            else
+                o.ok = false;
+        } else if (k < firstGrw) {
+            if (o.pre < 0)
+                o.pre = k;
+            else
+                o.ok = false;
+        } else {
+            o.ok = false;
+        }
+    }
+    return o;
+}
+
+struct S2d {
+    double *A, *Bf, *tile, *W0, *W1;
+    RedScratch rs;
+    double sig0, sig1, parPre, parPost;
+    int R0, R1;
+    int w0[4], w1[4], wPre[4], wPost[4];
+    Stream2dOps ops;
+};
+
+__device__ __forceinline__ bool s2d_setup(const PassArgs &a, double *sm, long long b, S2d &s) {
+    s.A = a.scratch + (size_t)blockIdx.x * 2 * a.Gp;
+    s.Bf = s.A + a.Gp;
+    s.tile = sm + a.off_tile;
+    s.rs.buf = sm + a.off_misc;
+    s.rs.phase = 0;
+    s.ops = classify2d(a.pg.n_ops, a.pg.kind, a.pg.axis);
+    const int K = a.pg.n_ops;
+    auto load = [&](int k, double &par, int &rad, int *w) {
+        par = 0.0;
+        rad = 0;
+        for (int q = 0; q < 4; ++q) w[q] = 0;
+        if (k < 0) return;
+        par = a.pg.param[b * K + k];
+        rad = a.pg.radius[b * K + k];
+        for (int q = 0; q < 4; ++q) w[q] = a.pg.window[(b * K + k) * 4 + q];
+    };
+    int dummy;
+    load(s.ops.k0, s.sig0, s.R0, s.w0);
+    load(s.ops.k1, s.sig1, s.R1, s.w1);
+    load(s.ops.pre, s.parPre, dummy, s.wPre);
+    load(s.ops.post, s.parPost, dummy, s.wPost);
+    if (!(s.sig0 > 0.0) || s.R0 <= 0) s.R0 = 0;
+    if (!(s.sig1 > 0.0) || s.R1 <= 0) s.R1 = 0;
+    bool ok = true;
+    s.W0 = sm + a.off_w + (s.ops.k0 >= 0 ? a.pg.w_off[s.ops.k0] : 0);
+    s.W1 = sm + a.off_w + (s.ops.k1 >= 0 ? a.pg.w_off[s.ops.k1] : 0);
+    __syncthreads();  // previous combo is done with the weight tables
+    if (s.ops.k0 >= 0) {
+        if (2 * s.R0 + 1 + kConvM > a.pg.w_len[s.ops.k0])
+            ok = false;
+        else if (s.R0 > 0)
+            build_weights(s.W0, a.pg.w_len[s.ops.k0], s.sig0, s.R0, s.rs);
+    }
+    if (s.ops.k1 >= 0) {
+        if (2 * s.R1 + 1 + kConvM > a.pg.w_len[s.ops.k1])
+            ok = false;
+        else if (s.R1 > 0)
+            build_weights(s.W1, a.pg.w_len[s.ops.k1], s.sig1, s.R1, s.rs);
+    }
+    return ok;
+}
+
+__device__ __forceinline__ bool in_window(const int *w, long long idx, bool backward) {
+    return idx >= (long long)w[backward ? 2 : 0] && idx < (long long)w[backward ? 3 : 1];
+}
+
+// One convolution stage over the whole grid.  `fill(g)` produces the input value of cell g (and may have side
+// effects such as flushing a row to HBM); `epi(g, value)` is applied to every output, result stored to dst[g].
+template <typename Fill, typename Epi>
+__device__ __forceinline__ void conv_stage(const PassArgs &a, const S2d &s, int axis, int R, const double *W, double *dst,
+                                           Fill fill, Epi epi) {
+    const int n0 = a.pb.n0, n1 = a.pb.n1;
+    double *tile = s.tile;
+    if (axis == 1) {
+        const int rowsPer = max(1, a.tile_doubles / n1);
+        for (int r0 = 0; r0 < n0; r0 += rowsPer) {
+            const int rows = min(rowsPer, n0 - r0);
+            const int base = r0 * n1;
+            for (int e = threadIdx.x; e < rows * n1; e += blockDim.x) tile[e] = fill(base + e);
+            __syncthreads();
+            auto ep = [&](int l, int i, double v) { return epi(base + l * n1 + i, v); };
+            if (R + 2 * kConvM <= n1)
+                conv_lines<kConvM, true>(tile, dst + base, W, R, n1, 1, rows, n1, 1, n1, ep);
+            else
+                conv_lines<kConvM, false>(tile, dst + base, W, R, n1, 1, rows, n1, 1, n1, ep);
+            __syncthreads();
+        }
+    } else {
+        int cols = a.tile_doubles / n0;
+        if (cols > 32) cols = cols / 32 * 32;
+        cols = max(1, min(cols, n1));
+        for (int c0 = 0; c0 < n1; c0 += cols) {
+            const int w = min(cols, n1 - c0);
+            for (int e = threadIdx.x; e < n0 * w; e += blockDim.x) {
+                const int rr = e / w, cc = e - rr * w;
+                tile[e] = fill(rr * n1 + c0 + cc);
+            }
+            __syncthreads();
+            auto ep = [&](int l, int i, double v) { return epi(i * n1 + c0 + l, v); };
+            if (R + 2 * kConvM <= n0)
+                conv_lines<kConvM, true>(tile, dst + c0, W, R, n0, w, w, 1, n1, 1, ep);
+            else
+                conv_lines<kConvM, false>(tile, dst + c0, W, R, n0, w, w, 1, n1, 1, ep);
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ double lik_at(const PassArgs &a, const LikTables &tb, long long t, int g) {
+    if (a.pb.om_kind == BLG_OM_TABLE) return __ldg(a.lik_table + t * (long long)a.pb.G + g);
+    const int i0 = g / a.pb.n1, i1 = g - i0 * a.pb.n1;
+    return lik_cell(a.pb, tb, a.steps + t * a.pb.ncols_eff, i0, i1);
+}
+
+// ------------------------------------------------------------------------------------------------ K3f forward
+__global__ void __launch_bounds__(1024, 1) fwd_stream2d_kernel(const PassArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const DevProblem &pb = a.pb;
+    const int G = pb.G;
+    const long long T = a.T;
+    LikTables tb;  // only used when the likelihood is not tabulated (few combos): tables straight from global memory
+    tb.A0 = pb.tabA[0];
+    tb.A1 = pb.tabA[1];
+    tb.A2 = pb.tabA[2];
+    tb.B0 = pb.tabB[0];
+    tb.B1 = pb.tabB[1];
+    for (long long slot = blockIdx.x; slot < a.B; slot += gridDim.x) {
+        const long long b = a.order ? a.order[slot] : slot;
+        S2d s;
+        if (!s2d_setup(a, sm, b, s)) {
+            if (threadIdx.x == 0) {
+                a.logE[b] = NAN;
+                if (a.alive) a.alive[b] = -2;
+            }
+            continue;
+        }
+        double *A = s.A, *Bf = s.Bf;
+        {
+            const double *init = (a.flags & BLG_F_INIT_STATE) ? a.init_state + b * (long long)G : a.prior;
+            for (int g = threadIdx.x; g < G; g += blockDim.x) A[g] = init[g];
+        }
+        __syncthreads();
+        const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
+        double *seq = store ? a.alpha_seq + b * T * (long long)G : nullptr;
+        LogProduct lp;
+        lp.init();
+        bool dead = false;
+        double kappa = 1.0;
+
+        for (long long t = 0; t < T; ++t) {
+            const bool trans = t > 0 || (a.flags & BLG_F_TRANSITION_FIRST);
+            const long long idx = t - 1;
+            const bool act0 = trans && s.ops.k0 >= 0 && s.R0 > 0 && in_window(s.w0, idx, false);
+            const bool act1 = trans && s.ops.k1 >= 0 && s.R1 > 0 && in_window(s.w1, idx, false);
+            const bool pre = trans && s.ops.pre >= 0 && in_window(s.wPre, idx, false);
+            const bool post = trans && s.ops.post >= 0 && in_window(s.wPost, idx, false);
+            double *row = (store && t > 0) ? seq + (t - 1) * (long long)G : nullptr;
+            const double kap = kappa, pPre = s.parPre, pPost = s.parPost;
+            const double *rb = a.reset_base;
+            // input of the first stage: previous state with its lazy normaliser (and the row flush of alpha[t-1])
+            auto fill = [&](int g) {
+                const double x = A[g] * kap;
+                if (row) __stcs(row + g, x);  // core.py:389, :408: normalised filtering distribution of step t-1
+                return (pre || post) ? (post ? 0.0 : __ldg(rb + g) * pPre) : x;
+            };
+            double part = 0.0;
+            auto epi = [&](int g, double v) {  // core.py:375-382: prior * likelihood
+                if (post) v = __ldg(rb + g) * pPost;
+                const double y = v * lik_at(a, tb, t, g);
+                part += y;
+                return y;
+            };
+            auto pass = [&](int, double v) { return v; };
+            // order of the two convolutions = program order
+            const bool first0 = s.ops.k0 >= 0 && (s.ops.k1 < 0 || s.ops.k0 < s.ops.k1);
+            const int nact = (act0 ? 1 : 0) + (act1 ? 1 : 0);
+            if (post || nact == 0) {  // no convolution (or its result is discarded by a trailing reset): one sweep
+                for (int g = threadIdx.x; g < G; g += blockDim.x) Bf[g] = epi(g, fill(g));
+            } else if (nact == 1) {
+                if (act0)
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, fill, epi);
+                else
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, fill, epi);
+            } else {
+                auto rd = [&](int g) { return Bf[g]; };
+                if (first0) {
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, fill, pass);
+                    __syncthreads();
+                    conv_stage(a, s, 1, s.R1, s.W1, A, rd, epi);
+                } else {
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, fill, pass);
+                    __syncthreads();
+                    conv_stage(a, s, 0, s.R0, s.W0, A, rd, epi);
+                }
+            }
+            if (post || nact < 2) {  // new state sits in Bf
+                double *tmp = A;
+                A = Bf;
+                Bf = tmp;
+            }
+            const double norm = block_sum(part, s.rs);  // core.py:385 (also makes the new state visible)
+            if (!(norm > 0.0)) {                         // core.py:388-400
+                dead = true;
+                break;
+            }
+            kappa = fast_rcp(norm);
+            if (threadIdx.x == 0) {
+                lp.mul(norm);                                         // core.py:403
+                if (a.local) a.local[b * T + t] = norm * pb.lc_prod;  // core.py:404
+            }
+        }
+        if (!dead) {
+            if (store) {
+                double *row = seq + (T - 1) * (long long)G;
+                for (int g = threadIdx.x; g < G; g += blockDim.x) __stcs(row + g, A[g] * kappa);
+            }
+            if ((a.flags & BLG_F_SAVE_STATE) && a.final_state) {
+                double *fs = a.final_state + b * (long long)G;
+                for (int g = threadIdx.x; g < G; g += blockDim.x) fs[g] = A[g] * kappa;
+            }
+        }
+        if (threadIdx.x == 0) {
+            double logE = lp.log_value();
+            if (dead)
+                logE = -INFINITY;
+            else if (!(a.flags & BLG_F_INIT_STATE))
+                logE += log(pb.lc_prod);  // core.py:417
+            a.logE[b] = logE;
+            if (a.alive) a.alive[b] = dead ? 0 : 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4f backward
+__global__ void __launch_bounds__(1024, 1) bwd_stream2d_kernel(const PassArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const DevProblem &pb = a.pb;
+    const int G = pb.G;
+    const long long T = a.T;
+    LikTables tb;
+    tb.A0 = pb.tabA[0];
+    tb.A1 = pb.tabA[1];
+    tb.A2 = pb.tabA[2];
+    tb.B0 = pb.tabB[0];
+    tb.B1 = pb.tabB[1];
+    const bool acc = (a.flags & BLG_F_ACCUMULATE) != 0;
+    for (long long slot = blockIdx.x; slot < a.B; slot += gridDim.x) {
+        const long long b = a.order ? a.order[slot] : slot;
+        if (a.alive && a.alive[b] != 1) continue;  // the forward pass aborted (core.py:400)
+        S2d s;
+        if (!s2d_setup(a, sm, b, s)) continue;
+        double *A = s.A, *Bf = s.Bf;
+        double *seq = a.alpha_seq + b * T * (long long)G;
+        const double wgt = acc ? exp(a.log_weight[b]) : 0.0;
+        // beta = 1/G (core.py:424-425); sums for the first posterior
+        double sab = 0.0, sbb = 0.0;
+        {
+            const double beta0 = 1.0 / (double)G;
+            const double *al = seq + (T - 1) * (long long)G;
+            for (int g = threadIdx.x; g < G; g += blockDim.x) {
+                A[g] = beta0;
+                sab += al[g] * beta0;
+                sbb += beta0;
+            }
+        }
+        block_sum2(sab, sbb, s.rs);
+        bool dead = false;
+
+        for (long long i = T - 1; i >= 0; --i) {
+            if (!(sab > 0.0) || !(sbb > 0.0)) {  // core.py:440-452
+                dead = true;
+                break;
+            }
+            const double inv = fast_rcp(sab);  // posterior = alpha*beta / sum(alpha*beta)  core.py:436-441
+            const double kb = fast_rcp(sbb);   // core.py:470 (beta only enters scale-free expressions)
+            const bool act0 = s.ops.k0 >= 0 && s.R0 > 0 && in_window(s.w0, i, true);
+            const bool act1 = s.ops.k1 >= 0 && s.R1 > 0 && in_window(s.w1, i, true);
+            const bool pre = s.ops.pre >= 0 && in_window(s.wPre, i, true);
+            const bool post = s.ops.post >= 0 && in_window(s.wPost, i, true);
+            double *row = seq + i * (long long)G;
+            const double *nextRow = i > 0 ? seq + (i - 1) * (long long)G : nullptr;
+            double *av = acc ? a.avg + i * (long long)G : nullptr;
+            const double pPre = s.parPre, pPost = s.parPost;
+            const double *rb = a.reset_base;
+            double q = 0.0;
+            // input of the first stage: beta*likelihood (core.py:467); on the way the smoothed posterior of step i is
+            // written (core.py:441) and sum(post/lik) accumulated (core.py:463)
+            auto fill = [&](int g) {
+                const double beta = A[g];
+                const double lk = lik_at(a, tb, i, g);
+                const double p = row[g] * beta * inv;
+                q += fast_div(p, lk);
+                if (acc) {
+                    if (wgt > 0.0) atomicAdd(av + g, wgt * (p < kTiny ? kTiny : p));
+                } else {
+                    __stcs(row + g, p);
+                }
+                return (pre || post) ? (post ? 0.0 : __ldg(rb + g) * pPre) : beta * kb * lk;
+            };
+            sab = 0.0;
+            sbb = 0.0;
+            auto epi = [&](int g, double v) {  // new beta (unnormalised) and the sums the next step needs
+                if (post) v = __ldg(rb + g) * pPost;
+                if (nextRow) sab = fma(nextRow[g], v, sab);
+                sbb += v;
+                return v;
+            };
+            auto pass = [&](int, double v) { return v; };
+            const bool first0 = s.ops.k0 >= 0 && (s.ops.k1 < 0 || s.ops.k0 < s.ops.k1);
+            const int nact = (act0 ? 1 : 0) + (act1 ? 1 : 0);
+            if (post || nact == 0) {
+                for (int g = threadIdx.x; g < G; g += blockDim.x) Bf[g] = epi(g, fill(g));
+            } else if (nact == 1) {
+                if (act0)
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, fill, epi);
+                else
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, fill, epi);
+            } else {
+                auto rd = [&](int g) { return Bf[g]; };
+                if (first0) {
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, fill, pass);
+                    __syncthreads();
+                    conv_stage(a, s, 1, s.R1, s.W1, A, rd, epi);
+                } else {
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, fill, pass);
+                    __syncthreads();
+                    conv_stage(a, s, 0, s.R0, s.W0, A, rd, epi);
+                }
+            }
+            if (post || nact < 2) {
+                double *tmp = A;
+                A = Bf;
+                Bf = tmp;
+            }
+            q = block_sum(q, s.rs);
+            block_sum2(sab, sbb, s.rs);
+            if (threadIdx.x == 0 && a.local) a.local[b * T + i] = fast_div(1.0, q * pb.lc_prod);  // core.py:463
+            if (i == 0) break;
+        }
+        if (dead && threadIdx.x == 0) {
+            a.logE[b] = -INFINITY;
+            if (a.alive) a.alive[b] = -1;
+        }
+    }
+}
+
+}  // namespace blg

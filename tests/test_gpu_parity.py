@@ -125,7 +125,9 @@ def test_properties_at_scale(cuda_engine):
 
 @pytest.mark.parametrize('name', ['ref_tm_nested', 'ref_cps_1cp_1bp_2hp', 'syn_hyper_gauss_2d', 'syn_study_scaledar1_2d',
                                   'syn_study_2d_axis0_wide', 'syn_hyper_poisson_sweep', 'syn_online_mixed',
-                                  'syn_study_multicolumn', 'ref_om_gaussianmean'])
+                                  'syn_study_multicolumn', 'ref_om_gaussianmean', 'syn_cps_gauss_2d',
+                                  'ref_study_2d_grw', 'ref_study_2d_static', 'ref_hyper_1hp', 'ref_online_static',
+                                  'ref_om_scaledar1', 'ref_om_laplace'])
 def test_stream_kernels_on_golden_cases(name, use_cuda, monkeypatch):
     """The large-grid (global-memory streamed) kernels forced onto small cases: same goldens."""
     import bayesloop_b200 as bl
