@@ -381,7 +381,9 @@ bool stream_layout(const blg_plan *pl, const blg_program &pg, PassArgs &a, Layou
 }
 
 template <typename K>
-int launch_stream(K kernel, blg_plan *pl, PassArgs &a, const Layout &lay, long long B, cudaStream_t st, const char *name) {
+int launch_stream(K kernel, blg_plan *pl, PassArgs &a, Layout lay, long long B, cudaStream_t st, const char *name,
+                  int threads = 1024) {
+    lay.nt = threads;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     long long grid = B < pl->num_sms ? B : pl->num_sms;  // one persistent CTA per SM, looping over combos
@@ -532,7 +534,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     if (!resident_layout(pl, in->prog, false, false, a, lay) || getenv("BLG_FORCE_STREAM")) {
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream forward kernel");
         if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D"))
-            return launch_stream(fwd_stream2d_kernel, pl, a, lay, in->B, st, "fwd_stream2d");
+            return launch_stream(fwd_stream2d_kernel, pl, a, lay, in->B, st, "fwd_stream2d", 512);
         return launch_stream(fwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "fwd_stream");
     }
     a.use_bulk = bulkOk ? 1 : 0;
@@ -578,7 +580,7 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     if (getenv("BLG_FORCE_STREAM") || (!fits && !resident_layout(pl, in->prog, true, false, a, lay))) {
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream backward kernel");
         if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D"))
-            return launch_stream(bwd_stream2d_kernel, pl, a, lay, in->B, st, "bwd_stream2d");
+            return launch_stream(bwd_stream2d_kernel, pl, a, lay, in->B, st, "bwd_stream2d", 512);
         return launch_stream(bwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "bwd_stream");
     }
     a.use_bulk = (fits && a.off_stage >= 0) ? 1 : 0;

@@ -121,11 +121,36 @@ __device__ __forceinline__ bool in_window(const int *w, long long idx, bool back
     return idx >= (long long)w[backward ? 2 : 0] && idx < (long long)w[backward ? 3 : 1];
 }
 
-// One convolution stage over the whole grid.  `fill(g)` produces the input value of cell g (and may have side
+struct Raw3 {
+    double x, y, z;
+};
+
+// Grid sweep with memory-level parallelism: `load(g)` only reads (up to three values per cell), `apply(g, raw)`
+// transforms / stores.  Four cells per thread are in flight before the first dependent instruction, which is what
+// hides the L2 latency of the streamed state (one CTA per SM, 32 warps).
+template <typename Cell, typename Load, typename Apply, typename Sink>
+__device__ __forceinline__ void sweep4(int count, Cell cell, Load load, Apply apply, Sink sink) {
+    const int nt = blockDim.x;
+    for (int e0 = threadIdx.x; e0 < count; e0 += 4 * nt) {
+        Raw3 raw[4];
+        int g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * nt;
+            g[u] = e < count ? cell(e) : -1;
+            if (g[u] >= 0) raw[u] = load(g[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (g[u] >= 0) sink(e0 + u * nt, g[u], apply(g[u], raw[u]));
+    }
+}
+
+// One convolution stage over the whole grid.  `load`/`apply` produce the input value of a cell (apply may have side
 // effects such as flushing a row to HBM); `epi(g, value)` is applied to every output, result stored to dst[g].
-template <typename Fill, typename Epi>
+template <typename Load, typename Apply, typename Epi>
 __device__ __forceinline__ void conv_stage(const PassArgs &a, const S2d &s, int axis, int R, const double *W, double *dst,
-                                           Fill fill, Epi epi) {
+                                           Load load, Apply apply, Epi epi) {
     const int n0 = a.pb.n0, n1 = a.pb.n1;
     double *tile = s.tile;
     if (axis == 1) {
@@ -133,7 +158,8 @@ __device__ __forceinline__ void conv_stage(const PassArgs &a, const S2d &s, int 
         for (int r0 = 0; r0 < n0; r0 += rowsPer) {
             const int rows = min(rowsPer, n0 - r0);
             const int base = r0 * n1;
-            for (int e = threadIdx.x; e < rows * n1; e += blockDim.x) tile[e] = fill(base + e);
+            sweep4(rows * n1, [&](int e) { return base + e; }, load, apply,
+                   [&](int e, int, double v) { tile[e] = v; });
             __syncthreads();
             auto ep = [&](int l, int i, double v) { return epi(base + l * n1 + i, v); };
             if (R + 2 * kConvM <= n1)
@@ -148,10 +174,12 @@ __device__ __forceinline__ void conv_stage(const PassArgs &a, const S2d &s, int 
         cols = max(1, min(cols, n1));
         for (int c0 = 0; c0 < n1; c0 += cols) {
             const int w = min(cols, n1 - c0);
-            for (int e = threadIdx.x; e < n0 * w; e += blockDim.x) {
-                const int rr = e / w, cc = e - rr * w;
-                tile[e] = fill(rr * n1 + c0 + cc);
-            }
+            sweep4(n0 * w,
+                   [&](int e) {
+                       const int rr = e / w;
+                       return rr * n1 + c0 + (e - rr * w);
+                   },
+                   load, apply, [&](int e, int, double v) { tile[e] = v; });
             __syncthreads();
             auto ep = [&](int l, int i, double v) { return epi(i * n1 + c0 + l, v); };
             if (R + 2 * kConvM <= n0)
@@ -170,7 +198,7 @@ __device__ __forceinline__ double lik_at(const PassArgs &a, const LikTables &tb,
 }
 
 // ------------------------------------------------------------------------------------------------ K3f forward
-__global__ void __launch_bounds__(1024, 1) fwd_stream2d_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(512, 1) fwd_stream2d_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
     const int G = pb.G;
@@ -215,10 +243,18 @@ __global__ void __launch_bounds__(1024, 1) fwd_stream2d_kernel(const PassArgs a)
             const double kap = kappa, pPre = s.parPre, pPost = s.parPost;
             const double *rb = a.reset_base;
             // input of the first stage: previous state with its lazy normaliser (and the row flush of alpha[t-1])
-            auto fill = [&](int g) {
-                const double x = A[g] * kap;
+            const double *Ard = A;
+            auto load = [&](int g) {
+                Raw3 r;
+                r.x = Ard[g];
+                r.y = pre ? __ldg(rb + g) : 0.0;
+                r.z = 0.0;
+                return r;
+            };
+            auto fill = [&](int g, const Raw3 &r) {
+                const double x = r.x * kap;
                 if (row) __stcs(row + g, x);  // core.py:389, :408: normalised filtering distribution of step t-1
-                return (pre || post) ? (post ? 0.0 : __ldg(rb + g) * pPre) : x;
+                return pre ? r.y * pPre : x;
             };
             double part = 0.0;
             auto epi = [&](int g, double v) {  // core.py:375-382: prior * likelihood
@@ -231,23 +267,31 @@ __global__ void __launch_bounds__(1024, 1) fwd_stream2d_kernel(const PassArgs a)
             // order of the two convolutions = program order
             const bool first0 = s.ops.k0 >= 0 && (s.ops.k1 < 0 || s.ops.k0 < s.ops.k1);
             const int nact = (act0 ? 1 : 0) + (act1 ? 1 : 0);
+            double *Bw = Bf;
+            const double *Brd = Bf;
+            auto rdl = [&](int g) {
+                Raw3 r;
+                r.x = Brd[g];
+                r.y = r.z = 0.0;
+                return r;
+            };
+            auto rda = [&](int, const Raw3 &r) { return r.x; };
             if (post || nact == 0) {  // no convolution (or its result is discarded by a trailing reset): one sweep
-                for (int g = threadIdx.x; g < G; g += blockDim.x) Bf[g] = epi(g, fill(g));
+                sweep4(G, [&](int e) { return e; }, load, fill, [&](int, int g, double v) { Bw[g] = epi(g, v); });
             } else if (nact == 1) {
                 if (act0)
-                    conv_stage(a, s, 0, s.R0, s.W0, Bf, fill, epi);
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, epi);
                 else
-                    conv_stage(a, s, 1, s.R1, s.W1, Bf, fill, epi);
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, epi);
             } else {
-                auto rd = [&](int g) { return Bf[g]; };
                 if (first0) {
-                    conv_stage(a, s, 0, s.R0, s.W0, Bf, fill, pass);
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, pass);
                     __syncthreads();
-                    conv_stage(a, s, 1, s.R1, s.W1, A, rd, epi);
+                    conv_stage(a, s, 1, s.R1, s.W1, A, rdl, rda, epi);
                 } else {
-                    conv_stage(a, s, 1, s.R1, s.W1, Bf, fill, pass);
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, pass);
                     __syncthreads();
-                    conv_stage(a, s, 0, s.R0, s.W0, A, rd, epi);
+                    conv_stage(a, s, 0, s.R0, s.W0, A, rdl, rda, epi);
                 }
             }
             if (post || nact < 2) {  // new state sits in Bf
@@ -289,7 +333,7 @@ __global__ void __launch_bounds__(1024, 1) fwd_stream2d_kernel(const PassArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------ K4f backward
-__global__ void __launch_bounds__(1024, 1) bwd_stream2d_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(512, 1) bwd_stream2d_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
     const int G = pb.G;
@@ -342,10 +386,18 @@ __global__ void __launch_bounds__(1024, 1) bwd_stream2d_kernel(const PassArgs a)
             double q = 0.0;
             // input of the first stage: beta*likelihood (core.py:467); on the way the smoothed posterior of step i is
             // written (core.py:441) and sum(post/lik) accumulated (core.py:463)
-            auto fill = [&](int g) {
-                const double beta = A[g];
-                const double lk = lik_at(a, tb, i, g);
-                const double p = row[g] * beta * inv;
+            const double *Ard = A;
+            auto load = [&](int g) {
+                Raw3 r;
+                r.x = Ard[g];
+                r.y = row[g];
+                r.z = lik_at(a, tb, i, g);
+                return r;
+            };
+            auto fill = [&](int g, const Raw3 &r) {
+                const double beta = r.x;
+                const double lk = r.z;
+                const double p = r.y * beta * inv;
                 q += fast_div(p, lk);
                 if (acc) {
                     if (wgt > 0.0) atomicAdd(av + g, wgt * (p < kTiny ? kTiny : p));
@@ -365,23 +417,31 @@ __global__ void __launch_bounds__(1024, 1) bwd_stream2d_kernel(const PassArgs a)
             auto pass = [&](int, double v) { return v; };
             const bool first0 = s.ops.k0 >= 0 && (s.ops.k1 < 0 || s.ops.k0 < s.ops.k1);
             const int nact = (act0 ? 1 : 0) + (act1 ? 1 : 0);
+            double *Bw = Bf;
+            const double *Brd = Bf;
+            auto rdl = [&](int g) {
+                Raw3 r;
+                r.x = Brd[g];
+                r.y = r.z = 0.0;
+                return r;
+            };
+            auto rda = [&](int, const Raw3 &r) { return r.x; };
             if (post || nact == 0) {
-                for (int g = threadIdx.x; g < G; g += blockDim.x) Bf[g] = epi(g, fill(g));
+                sweep4(G, [&](int e) { return e; }, load, fill, [&](int, int g, double v) { Bw[g] = epi(g, v); });
             } else if (nact == 1) {
                 if (act0)
-                    conv_stage(a, s, 0, s.R0, s.W0, Bf, fill, epi);
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, epi);
                 else
-                    conv_stage(a, s, 1, s.R1, s.W1, Bf, fill, epi);
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, epi);
             } else {
-                auto rd = [&](int g) { return Bf[g]; };
                 if (first0) {
-                    conv_stage(a, s, 0, s.R0, s.W0, Bf, fill, pass);
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, pass);
                     __syncthreads();
-                    conv_stage(a, s, 1, s.R1, s.W1, A, rd, epi);
+                    conv_stage(a, s, 1, s.R1, s.W1, A, rdl, rda, epi);
                 } else {
-                    conv_stage(a, s, 1, s.R1, s.W1, Bf, fill, pass);
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, pass);
                     __syncthreads();
-                    conv_stage(a, s, 0, s.R0, s.W0, A, rd, epi);
+                    conv_stage(a, s, 0, s.R0, s.W0, A, rdl, rda, epi);
                 }
             }
             if (post || nact < 2) {
