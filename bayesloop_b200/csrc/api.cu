@@ -345,7 +345,7 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int
 }
 
 // Stream kernels (grids that do not fit in shared memory): state in global scratch, convolution tiles in smem.
-bool stream_layout(const blg_plan *pl, const blg_program &pg, PassArgs &a, Layout &lay) {
+bool stream_layout(const blg_plan *pl, const blg_program &pg, PassArgs &a, Layout &lay, int chunkM = 0) {
     const DevProblem &d = pl->dev;
     a.halo = 0;
     a.Gp = even_up(d.G);
@@ -362,7 +362,8 @@ bool stream_layout(const blg_plan *pl, const blg_program &pg, PassArgs &a, Layou
         a.pg.w_len[k] = 0;
         if (pg.kind[k] == BLG_OP_GRW) {
             const int taps = 2 * pg.max_radius[k] + 1;
-            a.pg.w_len[k] = even_up(((taps + kConvM - 1) / kConvM) * kConvM + kConvM);
+            a.pg.w_len[k] = chunkM ? ((taps + chunkM - 1) / chunkM + 1) * (chunkM + 1)
+                                   : even_up(((taps + kConvM - 1) / kConvM) * kConvM + kConvM);
             woff += a.pg.w_len[k];
         }
     }
@@ -371,9 +372,13 @@ bool stream_layout(const blg_plan *pl, const blg_program &pg, PassArgs &a, Layou
     off = a.off_misc + kMiscDoubles;
     a.off_tile = off;
     const long long room = (long long)(kSmemLimit / sizeof(double)) - off;
-    long long tile = room < 20480 ? room : 20480;  // 160 KB is plenty; leaves L1 for the streamed state
+    long long tile = room < 24576 ? room : 24576;  // <= 192 KB; the rest of the SM's memory stays L1 for the streamed state
     const int longest = d.n0 > d.n1 ? d.n0 : d.n1;
-    if (tile < longest) return false;  // one complete line of the convolution axis must fit
+    int rmax = 0;
+    for (int k = 0; k < pg.n_ops; ++k)
+        if (pg.kind[k] == BLG_OP_GRW && pg.max_radius[k] > rmax) rmax = pg.max_radius[k];
+    // generic stream kernel: one complete line; 2-D kernels: one line with halo + its output line
+    if (tile < (chunkM ? 2LL * longest + 2 * (rmax + 2 * chunkM) : (long long)longest)) return false;
     a.tile_doubles = (int)tile;
     lay.bytes = (size_t)(off + tile) * sizeof(double);
     lay.nt = 1024;
@@ -532,9 +537,10 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     }
     a.halo = 0;
     if (!resident_layout(pl, in->prog, false, false, a, lay) || getenv("BLG_FORCE_STREAM")) {
-        if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream forward kernel");
-        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D"))
+        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D") &&
+            stream_layout(pl, in->prog, a, lay, kM2d))
             return launch_stream(fwd_stream2d_kernel, pl, a, lay, in->B, st, "fwd_stream2d", 512);
+        if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream forward kernel");
         return launch_stream(fwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "fwd_stream");
     }
     a.use_bulk = bulkOk ? 1 : 0;
@@ -578,9 +584,10 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
     if (!fits) fits = false;
     if (getenv("BLG_FORCE_STREAM") || (!fits && !resident_layout(pl, in->prog, true, false, a, lay))) {
-        if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream backward kernel");
-        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D"))
+        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D") &&
+            stream_layout(pl, in->prog, a, lay, kM2d))
             return launch_stream(bwd_stream2d_kernel, pl, a, lay, in->B, st, "bwd_stream2d", 512);
+        if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream backward kernel");
         return launch_stream(bwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "bwd_stream");
     }
     a.use_bulk = (fits && a.off_stage >= 0) ? 1 : 0;

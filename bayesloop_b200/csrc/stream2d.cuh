@@ -19,6 +19,8 @@
 
 namespace blg {
 
+constexpr int kM2d = 9;  // outputs per work item of the 2-D tile convolution
+
 struct Stream2dOps {
     int k0, k1;        // program index of the GRW acting on axis 0 / axis 1 (-1: none)
     int pre, post;     // program index of a RESET before all / after all GRWs (-1: none)
@@ -103,16 +105,16 @@ __device__ __forceinline__ bool s2d_setup(const PassArgs &a, double *sm, long lo
     s.W1 = sm + a.off_w + (s.ops.k1 >= 0 ? a.pg.w_off[s.ops.k1] : 0);
     __syncthreads();  // previous combo is done with the weight tables
     if (s.ops.k0 >= 0) {
-        if (2 * s.R0 + 1 + kConvM > a.pg.w_len[s.ops.k0])
+        if ((2 * s.R0 + kM2d) / kM2d * (kM2d + 1) > a.pg.w_len[s.ops.k0])
             ok = false;
         else if (s.R0 > 0)
-            build_weights(s.W0, a.pg.w_len[s.ops.k0], s.sig0, s.R0, s.rs);
+            build_weights_chunked<kM2d>(s.W0, a.pg.w_len[s.ops.k0], s.sig0, s.R0, s.rs);
     }
     if (s.ops.k1 >= 0) {
-        if (2 * s.R1 + 1 + kConvM > a.pg.w_len[s.ops.k1])
+        if ((2 * s.R1 + kM2d) / kM2d * (kM2d + 1) > a.pg.w_len[s.ops.k1])
             ok = false;
         else if (s.R1 > 0)
-            build_weights(s.W1, a.pg.w_len[s.ops.k1], s.sig1, s.R1, s.rs);
+            build_weights_chunked<kM2d>(s.W1, a.pg.w_len[s.ops.k1], s.sig1, s.R1, s.rs);
     }
     return ok;
 }
@@ -120,6 +122,13 @@ __device__ __forceinline__ bool s2d_setup(const PassArgs &a, double *sm, long lo
 __device__ __forceinline__ bool in_window(const int *w, long long idx, bool backward) {
     return idx >= (long long)w[backward ? 2 : 0] && idx < (long long)w[backward ? 3 : 1];
 }
+
+// exact e / d for 0 <= e < 2^32 / d with one multiply-high (d fixed per stage)
+struct FastDiv {
+    unsigned m, d;
+    __device__ __forceinline__ explicit FastDiv(int dd) : m((unsigned)((0x100000000ull + (unsigned)dd - 1) / (unsigned)dd)), d((unsigned)dd) {}
+    __device__ __forceinline__ int div(int e) const { return d == 1 ? e : (int)__umulhi((unsigned)e, m); }
+};
 
 struct Raw3 {
     double x, y, z;
@@ -142,52 +151,142 @@ __device__ __forceinline__ void sweep4(int count, Cell cell, Load load, Apply ap
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (g[u] >= 0) sink(e0 + u * nt, g[u], apply(g[u], raw[u]));
+            if (g[u] >= 0) sink(e0 + u * nt, g[u], apply(g[u], raw[u]));  // apply may return a value or the raw triple
     }
 }
 
-// One convolution stage over the whole grid.  `load`/`apply` produce the input value of a cell (apply may have side
-// effects such as flushing a row to HBM); `epi(g, value)` is applied to every output, result stored to dst[g].
-template <typename Load, typename Apply, typename Epi>
+// conv_item of fast1d.cuh with an element stride: M outputs of one line, inputs es doubles apart (es = 1 along rows,
+// es = tile width along columns), halo already in the tile, weights in the chunk-padded layout.
+template <int M>
+__device__ __forceinline__ void conv_item_strided(const double *__restrict__ line, int es, int i0, int R,
+                                                  const double *__restrict__ W, double (&acc)[M]) {
+    constexpr int MP = M + 1;
+    const double *p = line + (long long)(i0 - R) * es;
+    double win[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        win[m] = p[m * es];
+        acc[m] = 0.0;
+    }
+    p += M * es;
+    const int chunks = (2 * R + M) / M;
+    const double *wc = W;
+    for (int c = 0; c < chunks; ++c) {
+        double w[M];
+#pragma unroll
+        for (int k = 0; k < M / 2; ++k) {
+            const double2 t = reinterpret_cast<const double2 *>(wc)[k];
+            w[2 * k] = t.x;
+            w[2 * k + 1] = t.y;
+        }
+        w[M - 1] = wc[M - 1];
+#pragma unroll
+        for (int u = 0; u < M; ++u) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc[m] = fma(w[u], win[(u + m) % M], acc[m]);
+            win[u] = p[u * es];
+        }
+        p += M * es;
+        wc += MP;
+    }
+}
+
+// One convolution stage over the whole grid, tile by tile.  A tile holds L complete lines of the convolution axis
+// WITH a reflected halo of H = R + 2M cells on both ends (so the inner loop has no boundary logic), plus an output
+// tile of the same L lines:
+//   1. sweep4: coalesced, 4-deep batched loads of the tile cells (`load`/`apply`; apply may flush a row to HBM)
+//   2. halo fill from the tile interior (general reflect, valid for R >= n)
+//   3. register-blocked convolution (conv_item_strided) into the output tile
+//   4. sweep4 over the output tile: `eload(g)` (likelihood row, next alpha row ...) batched, `eapply` -> dst[g]
+template <typename Load, typename Apply, typename ELoad, typename EApply>
 __device__ __forceinline__ void conv_stage(const PassArgs &a, const S2d &s, int axis, int R, const double *W, double *dst,
-                                           Load load, Apply apply, Epi epi) {
+                                           Load load, Apply apply, ELoad eload, EApply eapply) {
+    constexpr int M = kM2d;
     const int n0 = a.pb.n0, n1 = a.pb.n1;
-    double *tile = s.tile;
-    if (axis == 1) {
-        const int rowsPer = max(1, a.tile_doubles / n1);
-        for (int r0 = 0; r0 < n0; r0 += rowsPer) {
-            const int rows = min(rowsPer, n0 - r0);
-            const int base = r0 * n1;
-            sweep4(rows * n1, [&](int e) { return base + e; }, load, apply,
-                   [&](int e, int, double v) { tile[e] = v; });
-            __syncthreads();
-            auto ep = [&](int l, int i, double v) { return epi(base + l * n1 + i, v); };
-            if (R + 2 * kConvM <= n1)
-                conv_lines<kConvM, true>(tile, dst + base, W, R, n1, 1, rows, n1, 1, n1, ep);
-            else
-                conv_lines<kConvM, false>(tile, dst + base, W, R, n1, 1, rows, n1, 1, n1, ep);
-            __syncthreads();
-        }
-    } else {
-        int cols = a.tile_doubles / n0;
-        if (cols > 32) cols = cols / 32 * 32;
-        cols = max(1, min(cols, n1));
-        for (int c0 = 0; c0 < n1; c0 += cols) {
-            const int w = min(cols, n1 - c0);
-            sweep4(n0 * w,
+    const int n = axis == 1 ? n1 : n0, other = axis == 1 ? n0 : n1;
+    const int H = R + 2 * M;
+    const int ext = n + 2 * H;
+    int L = a.tile_doubles / (ext + n);  // lines per tile (input with halo + output)
+    if (axis == 0 && L > 32) L = L / 32 * 32;
+    L = max(1, min(L, other));
+    double *tin = s.tile;
+    const int S = (n + M - 1) / M;
+    const FastDiv dn(n), dS(S), d2H(2 * H);
+    for (int l0 = 0; l0 < other; l0 += L) {
+        const int nl = min(L, other - l0);
+        const FastDiv dnl(nl);
+        double *tout = tin + (size_t)nl * ext;
+        // 1. interior cells.  axis 1: tin[l][H + j] (pitch ext);  axis 0: tin[(H + i)][c] (pitch nl)
+        if (axis == 1) {
+            sweep4(nl * n, [&](int e) { return l0 * n1 + e; }, load, apply,  // n == n1: rows are contiguous
+                   [&](int e, int, double v) { tin[e + dn.div(e) * 2 * H + H] = v; });
+        } else {
+            sweep4(n * nl,
                    [&](int e) {
-                       const int rr = e / w;
-                       return rr * n1 + c0 + (e - rr * w);
+                       const int i = dnl.div(e);
+                       return i * n1 + l0 + (e - i * nl);
                    },
-                   load, apply, [&](int e, int, double v) { tile[e] = v; });
-            __syncthreads();
-            auto ep = [&](int l, int i, double v) { return epi(i * n1 + c0 + l, v); };
-            if (R + 2 * kConvM <= n0)
-                conv_lines<kConvM, true>(tile, dst + c0, W, R, n0, w, w, 1, n1, 1, ep);
-            else
-                conv_lines<kConvM, false>(tile, dst + c0, W, R, n0, w, w, 1, n1, 1, ep);
-            __syncthreads();
+                   load, apply, [&](int e, int, double v) { tin[H * nl + e] = v; });
         }
+        __syncthreads();
+        // 2. reflected halo (NI_EXTEND_REFLECT, any R)
+        for (int e = threadIdx.x; e < 2 * H * nl; e += blockDim.x) {
+            int l, k;
+            if (axis == 1) {
+                l = d2H.div(e);
+                k = e - l * 2 * H;
+            } else {
+                k = dnl.div(e);
+                l = e - k * nl;
+            }
+            const int pos = k < H ? k - H : n + (k - H);  // extended index in [-H, 0) or [n, n+H)
+            const int src = reflect_any(pos, n);
+            if (axis == 1)
+                tin[l * ext + H + pos] = tin[l * ext + H + src];
+            else
+                tin[(H + pos) * nl + l] = tin[(H + src) * nl + l];
+        }
+        __syncthreads();
+        // 3. convolution: item = (line, segment of M outputs)
+        const int items = nl * S;
+        for (int w = threadIdx.x; w < items; w += blockDim.x) {
+            int l, sg;
+            if (axis == 1) {
+                l = dS.div(w);
+                sg = w - l * S;
+            } else {
+                sg = dnl.div(w);
+                l = w - sg * nl;
+            }
+            const int i0 = sg * M;
+            double acc[M];
+            if (axis == 1) {
+                conv_item_strided<M>(tin + (size_t)l * ext + H, 1, i0, R, W, acc);
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+                    if (i0 + m < n) tout[l * n + i0 + m] = acc[m];
+            } else {
+                conv_item_strided<M>(tin + (size_t)H * nl + l, nl, i0, R, W, acc);
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+                    if (i0 + m < n) tout[(i0 + m) * nl + l] = acc[m];
+            }
+        }
+        __syncthreads();
+        // 4. coalesced epilogue + store
+        if (axis == 1) {
+            sweep4(nl * n, [&](int e) { return l0 * n1 + e; }, eload, [&](int, const Raw3 &r) { return r; },
+                   [&](int e, int g, const Raw3 &r) { dst[g] = eapply(g, r, tout[e]); });
+        } else {
+            sweep4(n * nl,
+                   [&](int e) {
+                       const int i = dnl.div(e);
+                       return i * n1 + l0 + (e - i * nl);
+                   },
+                   eload, [&](int, const Raw3 &r) { return r; },
+                   [&](int e, int g, const Raw3 &r) { dst[g] = eapply(g, r, tout[e]); });
+        }
+        __syncthreads();
     }
 }
 
@@ -257,13 +356,21 @@ __global__ void __launch_bounds__(512, 1) fwd_stream2d_kernel(const PassArgs a) 
                 return pre ? r.y * pPre : x;
             };
             double part = 0.0;
-            auto epi = [&](int g, double v) {  // core.py:375-382: prior * likelihood
-                if (post) v = __ldg(rb + g) * pPost;
-                const double y = v * lik_at(a, tb, t, g);
+            auto eload = [&](int g) {
+                Raw3 r;
+                r.x = lik_at(a, tb, t, g);
+                r.y = post ? __ldg(rb + g) : 0.0;
+                r.z = 0.0;
+                return r;
+            };
+            auto eapply = [&](int, const Raw3 &r, double v) {  // core.py:375-382: prior * likelihood
+                if (post) v = r.y * pPost;
+                const double y = v * r.x;
                 part += y;
                 return y;
             };
-            auto pass = [&](int, double v) { return v; };
+            auto nol = [&](int) { return Raw3(); };
+            auto pass = [&](int, const Raw3 &, double v) { return v; };
             // order of the two convolutions = program order
             const bool first0 = s.ops.k0 >= 0 && (s.ops.k1 < 0 || s.ops.k0 < s.ops.k1);
             const int nact = (act0 ? 1 : 0) + (act1 ? 1 : 0);
@@ -277,21 +384,37 @@ __global__ void __launch_bounds__(512, 1) fwd_stream2d_kernel(const PassArgs a) 
             };
             auto rda = [&](int, const Raw3 &r) { return r.x; };
             if (post || nact == 0) {  // no convolution (or its result is discarded by a trailing reset): one sweep
-                sweep4(G, [&](int e) { return e; }, load, fill, [&](int, int g, double v) { Bw[g] = epi(g, v); });
+                sweep4(G, [&](int e) { return e; },
+                       [&](int g) {
+                           Raw3 r = load(g);
+                           const Raw3 e = eload(g);
+                           r.z = e.x;
+                           if (post) r.y = e.y;
+                           return r;
+                       },
+                       [&](int g, const Raw3 &r) {
+                           const double v = fill(g, r);
+                           Raw3 e;
+                           e.x = r.z;
+                           e.y = r.y;
+                           e.z = 0.0;
+                           return eapply(g, e, v);
+                       },
+                       [&](int, int g, double v) { Bw[g] = v; });
             } else if (nact == 1) {
                 if (act0)
-                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, epi);
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, eload, eapply);
                 else
-                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, epi);
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, eload, eapply);
             } else {
                 if (first0) {
-                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, pass);
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, nol, pass);
                     __syncthreads();
-                    conv_stage(a, s, 1, s.R1, s.W1, A, rdl, rda, epi);
+                    conv_stage(a, s, 1, s.R1, s.W1, A, rdl, rda, eload, eapply);
                 } else {
-                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, pass);
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, nol, pass);
                     __syncthreads();
-                    conv_stage(a, s, 0, s.R0, s.W0, A, rdl, rda, epi);
+                    conv_stage(a, s, 0, s.R0, s.W0, A, rdl, rda, eload, eapply);
                 }
             }
             if (post || nact < 2) {  // new state sits in Bf
@@ -408,13 +531,21 @@ __global__ void __launch_bounds__(512, 1) bwd_stream2d_kernel(const PassArgs a) 
             };
             sab = 0.0;
             sbb = 0.0;
-            auto epi = [&](int g, double v) {  // new beta (unnormalised) and the sums the next step needs
-                if (post) v = __ldg(rb + g) * pPost;
-                if (nextRow) sab = fma(nextRow[g], v, sab);
+            auto eload = [&](int g) {
+                Raw3 r;
+                r.x = nextRow ? nextRow[g] : 0.0;
+                r.y = post ? __ldg(rb + g) : 0.0;
+                r.z = 0.0;
+                return r;
+            };
+            auto eapply = [&](int, const Raw3 &r, double v) {  // new beta (unnormalised) + the sums the next step needs
+                if (post) v = r.y * pPost;
+                sab = fma(r.x, v, sab);
                 sbb += v;
                 return v;
             };
-            auto pass = [&](int, double v) { return v; };
+            auto nol = [&](int) { return Raw3(); };
+            auto pass = [&](int, const Raw3 &, double v) { return v; };
             const bool first0 = s.ops.k0 >= 0 && (s.ops.k1 < 0 || s.ops.k0 < s.ops.k1);
             const int nact = (act0 ? 1 : 0) + (act1 ? 1 : 0);
             double *Bw = Bf;
@@ -427,21 +558,22 @@ __global__ void __launch_bounds__(512, 1) bwd_stream2d_kernel(const PassArgs a) 
             };
             auto rda = [&](int, const Raw3 &r) { return r.x; };
             if (post || nact == 0) {
-                sweep4(G, [&](int e) { return e; }, load, fill, [&](int, int g, double v) { Bw[g] = epi(g, v); });
+                sweep4(G, [&](int e) { return e; }, load, fill,
+                       [&](int, int g, double v) { Bw[g] = eapply(g, eload(g), v); });
             } else if (nact == 1) {
                 if (act0)
-                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, epi);
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, eload, eapply);
                 else
-                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, epi);
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, eload, eapply);
             } else {
                 if (first0) {
-                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, pass);
+                    conv_stage(a, s, 0, s.R0, s.W0, Bf, load, fill, nol, pass);
                     __syncthreads();
-                    conv_stage(a, s, 1, s.R1, s.W1, A, rdl, rda, epi);
+                    conv_stage(a, s, 1, s.R1, s.W1, A, rdl, rda, eload, eapply);
                 } else {
-                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, pass);
+                    conv_stage(a, s, 1, s.R1, s.W1, Bf, load, fill, nol, pass);
                     __syncthreads();
-                    conv_stage(a, s, 0, s.R0, s.W0, A, rdl, rda, epi);
+                    conv_stage(a, s, 0, s.R0, s.W0, A, rdl, rda, eload, eapply);
                 }
             }
             if (post || nact < 2) {
