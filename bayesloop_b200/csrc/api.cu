@@ -452,9 +452,31 @@ int launch_resident(K kernel, const PassArgs &a, const Layout &lay, long long B,
         fprintf(stderr, "[blgrid] %s: grid %lld x %d threads, %zu B smem/CTA, %d CTA/SM, halo %d, bulk %d\n", name, B,
                 lay.nt, lay.bytes, occ, a.halo, a.use_bulk);
     }
-    kernel<<<(unsigned)B, lay.nt, lay.bytes, st>>>(a);
+    long long *trace = nullptr;
+    PassArgs a2 = a;
+    if (getenv("BLG_TRACE")) {  // debugging aid: per-CTA {smid, combo, start, end} (globaltimer ns), dumped as CSV
+        CUDA_TRY(cudaMalloc(&trace, (size_t)B * 4 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(trace, 0, (size_t)B * 4 * sizeof(long long)));
+        a2.trace = trace;
+    }
+    kernel<<<(unsigned)B, lay.nt, lay.bytes, st>>>(a2);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
+    if (trace) {
+        std::vector<long long> h((size_t)B * 4);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(trace);
+        static int seq = 0;
+        char path[512];
+        snprintf(path, sizeof path, "%s.%s.%d.csv", getenv("BLG_TRACE"), name, seq++);
+        if (FILE *f = fopen(path, "w")) {
+            fprintf(f, "block,smid,combo,start_ns,end_ns\n");
+            for (long long i = 0; i < B; ++i)
+                fprintf(f, "%lld,%lld,%lld,%lld,%lld\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+            fclose(f);
+        }
+    }
     return 0;
 }
 
@@ -537,7 +559,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     }
     a.halo = 0;
     if (!resident_layout(pl, in->prog, false, false, a, lay) || getenv("BLG_FORCE_STREAM")) {
-        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D") &&
+        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && getenv("BLG_STREAM2D") &&
             stream_layout(pl, in->prog, a, lay, kM2d))
             return launch_stream(fwd_stream2d_kernel, pl, a, lay, in->B, st, "fwd_stream2d", 512);
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream forward kernel");
@@ -584,7 +606,7 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
     if (!fits) fits = false;
     if (getenv("BLG_FORCE_STREAM") || (!fits && !resident_layout(pl, in->prog, true, false, a, lay))) {
-        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && !getenv("BLG_NO_STREAM2D") &&
+        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && getenv("BLG_STREAM2D") &&
             stream_layout(pl, in->prog, a, lay, kM2d))
             return launch_stream(bwd_stream2d_kernel, pl, a, lay, in->B, st, "bwd_stream2d", 512);
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream backward kernel");

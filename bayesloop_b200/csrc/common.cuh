@@ -80,6 +80,7 @@ struct PassArgs {
     double *scratch;     // stream kernels: [gridDim.x][2][Gp] state buffers in global memory (L2 resident)
     int off_tile;        // stream kernels: offset (doubles) and size of the shared-memory convolution tile
     int tile_doubles;
+    long long *trace;    // debugging: per-CTA {smid, combo, start, end} or NULL
     int halo;            // fast 1-D kernels: reflected halo cells on each side of the state (0 = generic kernels)
 };
 
@@ -195,6 +196,26 @@ __device__ __forceinline__ double block_max(double v, RedScratch &rs) {
     double s = slot[0];
     for (int w = 1; w < nw; ++w) s = fmax(s, slot[w]);
     return s;
+}
+
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void trace_begin(const PassArgs &a, long long b) {
+    if (a.trace && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.trace[4 * (long long)blockIdx.x + 0] = smid;
+        a.trace[4 * (long long)blockIdx.x + 1] = b;
+        a.trace[4 * (long long)blockIdx.x + 2] = global_ns();
+    }
+}
+
+__device__ __forceinline__ void trace_end(const PassArgs &a) {
+    if (a.trace && threadIdx.x == 0) a.trace[4 * (long long)blockIdx.x + 3] = global_ns();
 }
 
 // ------------------------------------------------------------------------------------------------ reciprocal

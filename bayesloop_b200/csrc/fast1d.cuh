@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
     const long long b = a.sm_assign ? combo_of_sm(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6))
                                     : (a.order ? a.order[combo_of_block(a)] : combo_of_block(a));
     if (b < 0) return;
+    trace_begin(a, b);
     const int n = pb.G, halo = a.halo;
     const long long T = a.T;
     Fast1dSetup s;
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
         a.logE[b] = logE;
         if (a.alive) a.alive[b] = dead ? 0 : 1;
     }
+    trace_end(a);
 }
 
 // ------------------------------------------------------------------------------------------------ K2f backward
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
     const long long b = a.sm_assign ? combo_of_sm(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6))
                                     : (a.order ? a.order[combo_of_block(a)] : combo_of_block(a));
     if (b < 0) return;
+    trace_begin(a, b);
     if (a.alive && a.alive[b] != 1) return;  // the forward pass aborted (core.py:400)
     const int n = pb.G, halo = a.halo;
     const long long T = a.T;
@@ -458,6 +461,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
         a.logE[b] = -INFINITY;
         if (a.alive) a.alive[b] = -1;
     }
+    trace_end(a);
 }
 
 }  // namespace blg
