@@ -106,14 +106,16 @@ class Program:
 
     def _assignment(self, lo, hi, sms, slots=4):
         """Combos of one call pre-assigned to SMs: longest-processing-time-first into `sms` bins of `slots`
-        entries.  Cost per time step of a chain ~ fixed bookkeeping + taps of its convolutions (measured on B200:
-        1.6 us + 0.0105 us per tap for a 1000-cell grid); heavy chains end up with fewer / lighter neighbours."""
+        entries.  Cost model fitted to a per-CTA trace on B200 (tools/trace_c2.py, BLG_TRACE): all CTAs of an SM
+        finish together, and the SM's time per step is ~1.37 us per resident CTA + 2.2 ns per convolution tap
+        (1000-cell grid) -- the fixed per-step work of a chain dominates, so SMs that must take 4 chains get the
+        lightest ones."""
         if hi - lo > sms * slots:
             return None
         key = (lo, hi, sms, slots)
         if key not in self._orders:
             taps = (2 * self.host['radius'][lo:hi] + 1).sum(axis=1).astype(float)
-            cost = 1.6 + 0.0105 * taps
+            cost = 1.37 + 0.0022 * taps
             table = np.full((sms, slots), -1, dtype=np.int32)
             load = np.zeros(sms)
             fill = np.zeros(sms, dtype=np.int64)
