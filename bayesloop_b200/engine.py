@@ -57,6 +57,9 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_ASSIGNMENTS = {}  # host-side memo of per-SM assignment tables, keyed by the radius table of a sweep
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -114,6 +117,10 @@ class Program:
             return None
         key = (lo, hi, sms, slots)
         if key not in self._orders:
+            memo = (self.host['radius'][lo:hi].tobytes(), sms, slots)
+            if memo in _ASSIGNMENTS:  # same sweep fitted again (new data, same hyper-grid): reuse the host table
+                self._orders[key] = self._engine.to_device(_ASSIGNMENTS[memo])
+                return self._orders[key]
             taps = (2 * self.host['radius'][lo:hi] + 1).sum(axis=1).astype(float)
             cost = 1.37 + 0.0022 * taps
             table = np.full((sms, slots), -1, dtype=np.int32)
@@ -125,6 +132,9 @@ class Program:
                 table[sm, fill[sm]] = b
                 fill[sm] += 1
                 load[sm] += cost[b]
+            if len(_ASSIGNMENTS) > 32:
+                _ASSIGNMENTS.clear()
+            _ASSIGNMENTS[memo] = table
             self._orders[key] = self._engine.to_device(table)
         return self._orders[key]
 
@@ -197,7 +207,15 @@ class Engine:
         return torch.zeros(shape, dtype=dtype, device=self.device)
 
     def to_host(self, tensor):
-        return tensor.detach().cpu().numpy()
+        """Device -> host.  Large results land in page-locked memory from torch's caching host allocator (an 80 MB
+        posterior sequence: ~3 ms at PCIe/C2C speed instead of ~30 ms through a pageable bounce copy); the returned
+        NumPy array keeps that buffer alive and hands it back to the cache when it is garbage collected."""
+        t = tensor.detach()
+        if self.device.type == 'cuda' and t.numel() * t.element_size() >= (1 << 20):
+            host = torch.empty(t.shape, dtype=t.dtype, device='cpu', pin_memory=True)
+            host.copy_(t)
+            return host.numpy()
+        return t.cpu().numpy()
 
     def sm_count(self):
         if self.device.type == 'cuda':
