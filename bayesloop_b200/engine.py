@@ -190,6 +190,7 @@ class Engine:
         if L.blg_version() != 1:
             raise EngineError('ABI version mismatch in {}'.format(lib_path))
         self.backend = L.blg_backend().decode()
+        self._staging = {}
 
     # ---------------------------------------------------------------------------------------------- memory
     def to_device(self, array, pinned=False):
@@ -207,14 +208,21 @@ class Engine:
         return torch.zeros(shape, dtype=dtype, device=self.device)
 
     def to_host(self, tensor):
-        """Device -> host.  Large results land in page-locked memory from torch's caching host allocator (an 80 MB
-        posterior sequence: ~3 ms at PCIe/C2C speed instead of ~30 ms through a pageable bounce copy); the returned
-        NumPy array keeps that buffer alive and hands it back to the cache when it is garbage collected."""
+        """Device -> host.  Large results go through ONE page-locked staging buffer kept by the engine (allocated
+        once per size; cudaHostAlloc of 80 MB costs far more than the copy) and are then copied into an ordinary
+        NumPy array owned by the caller."""
         t = tensor.detach()
-        if self.device.type == 'cuda' and t.numel() * t.element_size() >= (1 << 20):
-            host = torch.empty(t.shape, dtype=t.dtype, device='cpu', pin_memory=True)
-            host.copy_(t)
-            return host.numpy()
+        nbytes = t.numel() * t.element_size()
+        if self.device.type == 'cuda' and nbytes >= (1 << 20):
+            stage = self._staging.get(nbytes)
+            if stage is None:
+                if len(self._staging) >= 4:
+                    self._staging.clear()
+                stage = torch.empty(nbytes, dtype=torch.uint8, device='cpu', pin_memory=True)
+                self._staging[nbytes] = stage
+            view = stage.view(t.dtype).view(t.shape)
+            view.copy_(t.contiguous())
+            return view.numpy().copy()
         return t.cpu().numpy()
 
     def sm_count(self):
