@@ -12,6 +12,7 @@ symbols and takes host pointers) and pass it explicitly to the studies.  Nothing
 import ctypes
 import os
 import threading
+import weakref
 
 import numpy as np
 import torch
@@ -58,6 +59,11 @@ def _ptr(t):
 
 
 _ASSIGNMENTS = {}  # host-side memo of per-SM assignment tables, keyed by the radius table of a sweep
+
+
+def _give_back(pool, stage):
+    if len(pool) < 3:
+        pool.append(stage)
 
 
 class EngineError(RuntimeError):
@@ -190,7 +196,7 @@ class Engine:
         if L.blg_version() != 1:
             raise EngineError('ABI version mismatch in {}'.format(lib_path))
         self.backend = L.blg_backend().decode()
-        self._staging = {}
+        self._pinned = {}
 
     # ---------------------------------------------------------------------------------------------- memory
     def to_device(self, array, pinned=False):
@@ -208,21 +214,19 @@ class Engine:
         return torch.zeros(shape, dtype=dtype, device=self.device)
 
     def to_host(self, tensor):
-        """Device -> host.  Large results go through ONE page-locked staging buffer kept by the engine (allocated
-        once per size; cudaHostAlloc of 80 MB costs far more than the copy) and are then copied into an ordinary
-        NumPy array owned by the caller."""
+        """Device -> host.  Large results are downloaded straight into page-locked buffers that the returned NumPy
+        array owns; when the array (and every view of it) is garbage collected the buffer goes back to a small pool,
+        so steady-state fits neither call cudaHostAlloc (tens of ms for 80 MB) nor fault in fresh pageable memory."""
         t = tensor.detach()
         nbytes = t.numel() * t.element_size()
         if self.device.type == 'cuda' and nbytes >= (1 << 20):
-            stage = self._staging.get(nbytes)
-            if stage is None:
-                if len(self._staging) >= 4:
-                    self._staging.clear()
-                stage = torch.empty(nbytes, dtype=torch.uint8, device='cpu', pin_memory=True)
-                self._staging[nbytes] = stage
+            pool = self._pinned.setdefault(nbytes, [])
+            stage = pool.pop() if pool else torch.empty(nbytes, dtype=torch.uint8, device='cpu', pin_memory=True)
             view = stage.view(t.dtype).view(t.shape)
             view.copy_(t.contiguous())
-            return view.numpy().copy()
+            out = view.numpy()
+            weakref.finalize(out, _give_back, pool, stage)
+            return out
         return t.cpu().numpy()
 
     def sm_count(self):
