@@ -10,6 +10,8 @@ post-processes O(B) / O(T x G) results; nothing here touches a grid cell per tim
 import math
 from collections.abc import Iterable
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -197,7 +199,7 @@ class Study(object):
             raise ConfigurationError('The "BreakPoint" transition model can only be used with the '
                                      '"SerialTransitionModel" class.')
         self.transitionModel = T
-        T.study = self
+        T.study = weakref.proxy(self)  # back-pointer of core.py:281 without a reference cycle: results are freed on release
         T.latticeConstant = self.latticeConstant
         if not silent:
             print('+ Transition model: {}. Hyper-Parameter(s): {}'

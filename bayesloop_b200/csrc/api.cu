@@ -11,9 +11,7 @@
 #include <vector>
 
 #include "aux.cuh"
-#include "fast1d.cuh"
-#include "resident.cuh"
-#include "stream2d.cuh"
+#include "kernels.h"
 
 using namespace blg;
 
@@ -86,9 +84,15 @@ int blg_plan_create(const blg_problem *p, blg_plan **out) {
     pl->pb = *p;
     pl->pb.n[1] = n1;
     CUDA_TRY(cudaGetDevice(&pl->device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, pl->device));
-    pl->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, pl->device));
+    {   // scratch of the stream kernels comes from the stream-ordered pool: keep it cached between calls
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, pl->device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     const char *env = getenv("BLG_SERPENTINE");
     pl->serpentine = env ? atoi(env) : 1;
 
@@ -385,8 +389,7 @@ bool stream_layout(const blg_plan *pl, const blg_program &pg, PassArgs &a, Layou
     return true;
 }
 
-template <typename K>
-int launch_stream(K kernel, blg_plan *pl, PassArgs &a, Layout lay, long long B, cudaStream_t st, const char *name,
+int launch_stream(PassKernel kernel, blg_plan *pl, PassArgs &a, Layout lay, long long B, cudaStream_t st, const char *name,
                   int threads = 1024) {
     lay.nt = threads;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
@@ -441,8 +444,7 @@ int fast_m(bool backward) {
     return (m == 5 || m == 7 || m == 9) ? m : 7;
 }
 
-template <typename K>
-int launch_resident(K kernel, const PassArgs &a, const Layout &lay, long long B, cudaStream_t st, const char *name) {
+int launch_resident(PassKernel kernel, const PassArgs &a, const Layout &lay, long long B, cudaStream_t st, const char *name) {
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
     // several CTAs (combos) must share an SM: ask for the full shared-memory carveout
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -545,30 +547,18 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
         a.use_bulk = bulkOk ? 1 : 0;
         long long grid = in->B;
         if (prep_sm_assign(pl, in, a, grid, st)) return -1;
-#define BLG_FWD_FAST(MM)                                                                                           \
-    if (M == MM) {                                                                                                 \
-        if (lay.nt <= 128) return launch_resident(fwd_fast1d_kernel<MM, 128, 4>, a, lay, grid, st, "fwd_fast1d"); \
-        if (lay.nt <= 160) return launch_resident(fwd_fast1d_kernel<MM, 160, 4>, a, lay, grid, st, "fwd_fast1d"); \
-        if (lay.nt <= 256) return launch_resident(fwd_fast1d_kernel<MM, 256, 4>, a, lay, grid, st, "fwd_fast1d"); \
-        return launch_resident(fwd_fast1d_kernel<MM, 1024, 1>, a, lay, grid, st, "fwd_fast1d");                   \
-    }
-        BLG_FWD_FAST(5)
-        BLG_FWD_FAST(7)
-        BLG_FWD_FAST(9)
-#undef BLG_FWD_FAST
+        if (PassKernel k = fwd_fast1d_entry(M, lay.nt)) return launch_resident(k, a, lay, grid, st, "fwd_fast1d");
     }
     a.halo = 0;
     if (!resident_layout(pl, in->prog, false, false, a, lay) || getenv("BLG_FORCE_STREAM")) {
-        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && getenv("BLG_STREAM2D") &&
-            stream_layout(pl, in->prog, a, lay, kM2d))
-            return launch_stream(fwd_stream2d_kernel, pl, a, lay, in->B, st, "fwd_stream2d", 512);
+        if (pl->dev.ndim == 2 && stream2d_supports(in->prog.n_ops, in->prog.kind, in->prog.axis) && getenv("BLG_STREAM2D") &&
+            stream_layout(pl, in->prog, a, lay, stream2d_chunk()))
+            return launch_stream(fwd_stream2d_entry(), pl, a, lay, in->B, st, "fwd_stream2d", 512);
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream forward kernel");
-        return launch_stream(fwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "fwd_stream");
+        return launch_stream(fwd_resident_entry(1024, true), pl, a, lay, in->B, st, "fwd_stream");
     }
     a.use_bulk = bulkOk ? 1 : 0;
-    if (lay.nt <= 256) return launch_resident(fwd_resident_kernel<256, 4, false>, a, lay, in->B, st, "fwd_resident");
-    if (lay.nt <= 512) return launch_resident(fwd_resident_kernel<512, 2, false>, a, lay, in->B, st, "fwd_resident");
-    return launch_resident(fwd_resident_kernel<1024, 1, false>, a, lay, in->B, st, "fwd_resident");
+    return launch_resident(fwd_resident_entry(lay.nt, false), a, lay, in->B, st, "fwd_resident");
 }
 
 int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {
@@ -590,32 +580,20 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
         a.use_bulk = alignedRows ? 1 : 0;
         long long grid = in->B;
         if (prep_sm_assign(pl, in, a, grid, st)) return -1;
-#define BLG_BWD_FAST(MM)                                                                                           \
-    if (M == MM) {                                                                                                 \
-        if (lay.nt <= 128) return launch_resident(bwd_fast1d_kernel<MM, 128, 4>, a, lay, grid, st, "bwd_fast1d"); \
-        if (lay.nt <= 160) return launch_resident(bwd_fast1d_kernel<MM, 160, 4>, a, lay, grid, st, "bwd_fast1d"); \
-        if (lay.nt <= 256) return launch_resident(bwd_fast1d_kernel<MM, 256, 4>, a, lay, grid, st, "bwd_fast1d"); \
-        return launch_resident(bwd_fast1d_kernel<MM, 1024, 1>, a, lay, grid, st, "bwd_fast1d");                   \
-    }
-        BLG_BWD_FAST(5)
-        BLG_BWD_FAST(7)
-        BLG_BWD_FAST(9)
-#undef BLG_BWD_FAST
+        if (PassKernel k = bwd_fast1d_entry(M, lay.nt)) return launch_resident(k, a, lay, grid, st, "bwd_fast1d");
     }
     a.halo = 0;
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
     if (!fits) fits = false;
     if (getenv("BLG_FORCE_STREAM") || (!fits && !resident_layout(pl, in->prog, true, false, a, lay))) {
-        if (pl->dev.ndim == 2 && classify2d(in->prog.n_ops, in->prog.kind, in->prog.axis).ok && getenv("BLG_STREAM2D") &&
-            stream_layout(pl, in->prog, a, lay, kM2d))
-            return launch_stream(bwd_stream2d_kernel, pl, a, lay, in->B, st, "bwd_stream2d", 512);
+        if (pl->dev.ndim == 2 && stream2d_supports(in->prog.n_ops, in->prog.kind, in->prog.axis) && getenv("BLG_STREAM2D") &&
+            stream_layout(pl, in->prog, a, lay, stream2d_chunk()))
+            return launch_stream(bwd_stream2d_entry(), pl, a, lay, in->B, st, "bwd_stream2d", 512);
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream backward kernel");
-        return launch_stream(bwd_resident_kernel<1024, 1, true>, pl, a, lay, in->B, st, "bwd_stream");
+        return launch_stream(bwd_resident_entry(1024, true), pl, a, lay, in->B, st, "bwd_stream");
     }
     a.use_bulk = (fits && a.off_stage >= 0) ? 1 : 0;
-    if (lay.nt <= 256) return launch_resident(bwd_resident_kernel<256, 4, false>, a, lay, in->B, st, "bwd_resident");
-    if (lay.nt <= 512) return launch_resident(bwd_resident_kernel<512, 2, false>, a, lay, in->B, st, "bwd_resident");
-    return launch_resident(bwd_resident_kernel<1024, 1, false>, a, lay, in->B, st, "bwd_resident");
+    return launch_resident(bwd_resident_entry(lay.nt, false), a, lay, in->B, st, "bwd_resident");
 }
 
 int blg_accumulate(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {

@@ -1,0 +1,27 @@
+// kernels.h -- host-visible entry points of the pass kernels.  Every kernel family is compiled in its own
+// translation unit (fast1d_inst.cu, resident_inst.cu, stream2d_inst.cu) so that the library builds in parallel;
+// api.cu only sees these function pointers (all pass kernels share the signature void(const PassArgs)).
+#pragma once
+
+#include "common.cuh"
+
+namespace blg {
+
+using PassKernel = void (*)(const PassArgs);
+
+// fast 1-D kernels (fast1d.cuh): M in {5, 7, 9} outputs per thread; nt = threads of the launch (<= 128, <= 160,
+// <= 256, else 1024).  Return nullptr for a combination that is not compiled.
+PassKernel fwd_fast1d_entry(int M, int nt);
+PassKernel bwd_fast1d_entry(int M, int nt);
+
+// generic resident kernels (resident.cuh): nt in {256, 512, 1024}; stream = state in global scratch (1024 threads)
+PassKernel fwd_resident_entry(int nt, bool stream);
+PassKernel bwd_resident_entry(int nt, bool stream);
+
+// fused 2-D stream kernels (stream2d.cuh), 512 threads; kStream2dM = outputs per work item (layout parameter)
+PassKernel fwd_stream2d_entry();
+PassKernel bwd_stream2d_entry();
+int stream2d_chunk();
+bool stream2d_supports(int n_ops, const int *kind, const int *axis);
+
+}  // namespace blg

@@ -16,6 +16,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "fast1d.cuh"
 
 namespace blg {
 
@@ -297,7 +298,8 @@ __device__ __forceinline__ double lik_at(const PassArgs &a, const LikTables &tb,
 }
 
 // ------------------------------------------------------------------------------------------------ K3f forward
-__global__ void __launch_bounds__(512, 1) fwd_stream2d_kernel(const PassArgs a) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) fwd_stream2d_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
     const int G = pb.G;
@@ -456,7 +458,8 @@ __global__ void __launch_bounds__(512, 1) fwd_stream2d_kernel(const PassArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------ K4f backward
-__global__ void __launch_bounds__(512, 1) bwd_stream2d_kernel(const PassArgs a) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) bwd_stream2d_kernel(const PassArgs a) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
     const int G = pb.G;

@@ -9,6 +9,7 @@ comes from libblgrid.so.
 machine without a GPU: tests/ build an Engine around the CPU oracle (oracle/libblgrid_oracle.so exports the same
 symbols and takes host pointers) and pass it explicitly to the studies.  Nothing in this package refers to oracle/.
 """
+import collections
 import ctypes
 import os
 import threading
@@ -197,6 +198,7 @@ class Engine:
             raise EngineError('ABI version mismatch in {}'.format(lib_path))
         self.backend = L.blg_backend().decode()
         self._pinned = {}
+        self._plans = collections.OrderedDict()  # problem signature -> Plan (scratch and tables stay allocated)
 
     # ---------------------------------------------------------------------------------------------- memory
     def to_device(self, array, pinned=False):
@@ -257,8 +259,17 @@ class Engine:
 
     # ---------------------------------------------------------------------------------------------- calls
     def plan(self, coords, lattice, om_kind, seg_len, n_cols):
+        """Plan for one (grid, observation model) description.  Plans are cached per engine (LRU of 8): repeated fits
+        of the same problem reuse the device tables and the scratch the library grew inside the plan, so a
+        steady-state fit performs no cudaMalloc/cudaFree (each of them synchronises the device)."""
         ndim = len(coords)
         hostCoords = [np.ascontiguousarray(c, dtype=np.float64) for c in coords]
+        key = (ndim, tuple(c.tobytes() for c in hostCoords), tuple(float(x) for x in lattice[:ndim]), int(om_kind),
+               int(seg_len), int(n_cols), self.stream().value)
+        cached = self._plans.get(key)
+        if cached is not None:
+            self._plans.move_to_end(key)
+            return cached
         pb = _Problem()
         pb.ndim = ndim
         for a in range(2):
@@ -273,7 +284,11 @@ class Engine:
         else:
             self._check(self.lib.blg_plan_create(ctypes.byref(pb), ctypes.byref(handle)))
         n = [pb.n[0], pb.n[1]]
-        return Plan(self, handle, ndim, n, n[0] * n[1])
+        plan = Plan(self, handle, ndim, n, n[0] * n[1])
+        self._plans[key] = plan
+        while len(self._plans) > 8:
+            self._plans.popitem(last=False)
+        return plan
 
     def _io(self, T, B, data, prior, reset_base, lik_table, program, lo, log_weight, init_state, log_evidence,
             local_evidence, alive, alpha_seq, avg, final_state):
