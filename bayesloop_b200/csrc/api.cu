@@ -230,27 +230,37 @@ int ensure_w(blg_plan *pl, long long count) {
 }
 
 // Shared likelihood table: worth it as soon as a few combos share it; bounded so it never competes with alpha_seq.
-int prep_lik_table(blg_plan *pl, const blg_inputs *in, PassArgs &a, cudaStream_t st) {
+// permM > 0: "owner order" of the warp-specialised 1-D kernels (rows of permM planes x permNC entries, see
+// lik_table_perm_kernel); a caller-supplied table (BLG_OM_TABLE) is permuted into the same scratch.
+int prep_lik_table(blg_plan *pl, const blg_inputs *in, PassArgs &a, cudaStream_t st, int permM = 0, int permNC = 0) {
     const DevProblem &d = pl->dev;
-    if (d.om_kind == BLG_OM_TABLE || getenv("BLG_NO_LIK_TABLE")) return 0;
-    const long long count = in->T * (long long)d.G;
-    if (in->B < 4 || count * 8 > (6LL << 30)) return 0;
+    a.lik_pitch = d.G;
+    if (!permM && (d.om_kind == BLG_OM_TABLE || getenv("BLG_NO_LIK_TABLE"))) return 0;
+    const long long pitch = permM ? (long long)permM * permNC : (long long)d.G;
+    const long long count = in->T * pitch;
+    if (!permM && in->B < 4) return 0;
+    if (count * 8 > (6LL << 30)) return permM ? 1 : 0;
     if (count > pl->lik_cap) {
         if (pl->d_lik) CUDA_TRY(cudaFree(pl->d_lik));
         pl->d_lik = nullptr;
         pl->lik_cap = 0;
         if (cudaMalloc(&pl->d_lik, (size_t)count * sizeof(double)) != cudaSuccess) {
             cudaGetLastError();
-            return 0;  // no room: keep evaluating the likelihood in the passes
+            return permM ? 1 : 0;  // no room: keep evaluating the likelihood in the passes
         }
         pl->lik_cap = count;
     }
     const int nt = 256;
-    lik_table_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(d, pl->d_steps, in->T, pl->d_lik);
+    if (permM)
+        lik_table_perm_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(
+            d, pl->d_steps, d.om_kind == BLG_OM_TABLE ? in->lik_table : nullptr, in->T, permM, permNC, pl->d_lik);
+    else
+        lik_table_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(d, pl->d_steps, in->T, pl->d_lik);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     a.pb.om_kind = BLG_OM_TABLE;
     a.lik_table = pl->d_lik;
+    a.lik_pitch = pitch;
     return 0;
 }
 
@@ -344,6 +354,48 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int
     a.off_misc = even_up(off);
     lay.bytes = (size_t)(a.off_misc + kMiscDoubles) * sizeof(double);
     int nt = (items + 31) / 32 * 32;
+    lay.nt = nt;
+    return lay.bytes <= kSmemLimit;
+}
+
+// Warp-specialised fast path (fast1d_ws.cuh): same shapes as fast1d_layout; chooses (M, threads) so that the compute
+// warps (threads/32 - 1) cover the grid with M cells per thread.
+bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, PassArgs &a, Layout &lay, int &M) {
+    const DevProblem &d = pl->dev;
+    if (getenv("BLG_NO_FAST1D") || getenv("BLG_NO_WS")) return false;
+    if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
+    int nt = 128;
+    if (d.G <= 96 * 3) M = 3;
+    else if (d.G <= 96 * 7) M = 7;
+    else if (d.G <= 96 * 11) M = 11;
+    else if (d.G <= 224 * 11) { M = 11; nt = 256; }
+    else return false;
+    const int halo = even_up(pg.max_radius[0] + 2 * M);
+    if (halo > d.G) return false;
+    a.halo = halo;
+    a.Gp = even_up(d.G);
+    a.n0p = even_up(d.n0);
+    a.n1p = 2;
+    const int pitch = a.Gp + 2 * halo;
+    int off = 2 * pitch;
+    a.off_stage = -1;
+    if (backward) {
+        a.off_stage = off;
+        off += 2 * a.Gp;
+    }
+    a.off_tab = -1;
+    a.off_w = off;
+    const int taps = 2 * pg.max_radius[0] + 1;
+    a.pg.w_off[0] = 0;
+    a.pg.w_len[0] = ((taps + M - 1) / M + 1) * (M + 1);  // chunk-padded layout of conv_item (fast1d.cuh)
+    off += a.pg.w_len[0];
+    a.off_misc = even_up(off);
+    off = a.off_misc + kMiscDoubles;
+    a.ws_part = off;
+    off += 3 * (nt - 32);
+    a.ws_ctl = off;
+    off += 4;
+    lay.bytes = (size_t)off * sizeof(double);
     lay.nt = nt;
     return lay.bytes <= kSmemLimit;
 }
@@ -539,9 +591,23 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     memset(&a, 0, sizeof a);
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
-    if (prep_lik_table(pl, in, a, st)) return -1;
     Layout lay;
     const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
+    {
+        int wsM = 0;
+        if (fast1d_ws_layout(pl, in->prog, false, a, lay, wsM)) {
+            const int rc = prep_lik_table(pl, in, a, st, wsM, lay.nt - 32);
+            if (rc < 0) return -1;
+            if (rc == 0) {
+                a.use_bulk = bulkOk ? 1 : 0;
+                long long grid = in->B;
+                if (prep_sm_assign(pl, in, a, grid, st)) return -1;
+                if (PassKernel k = fwd_fast1d_ws_entry(wsM, lay.nt)) return launch_resident(k, a, lay, grid, st, "fwd_fast1d_ws");
+                return fail("warp-specialised forward kernel missing");
+            }
+        }
+    }
+    if (prep_lik_table(pl, in, a, st)) return -1;
     const int M = fast_m(false);
     if (fast1d_layout(pl, in->prog, false, M, a, lay)) {
         a.use_bulk = bulkOk ? 1 : 0;
@@ -572,9 +638,23 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     memset(&a, 0, sizeof a);
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
-    if (prep_lik_table(pl, in, a, st)) return -1;
     Layout lay;
     const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
+    {
+        int wsM = 0;
+        if (alignedRows && !acc && fast1d_ws_layout(pl, in->prog, true, a, lay, wsM)) {
+            const int rc = prep_lik_table(pl, in, a, st, wsM, lay.nt - 32);
+            if (rc < 0) return -1;
+            if (rc == 0) {
+                a.use_bulk = 1;
+                long long grid = in->B;
+                if (prep_sm_assign(pl, in, a, grid, st)) return -1;
+                if (PassKernel k = bwd_fast1d_ws_entry(wsM, lay.nt)) return launch_resident(k, a, lay, grid, st, "bwd_fast1d_ws");
+                return fail("warp-specialised backward kernel missing");
+            }
+        }
+    }
+    if (prep_lik_table(pl, in, a, st)) return -1;
     const int M = fast_m(true);
     if (fast1d_layout(pl, in->prog, true, M, a, lay)) {
         a.use_bulk = alignedRows ? 1 : 0;

@@ -58,6 +58,35 @@ __global__ void lik_table_kernel(DevProblem pb, const StepC *__restrict__ steps,
     table[e] = lik_cell(pb, tb, steps + t * pb.ncols_eff, i0, i1);
 }
 
+// The same table in "owner order" for the warp-specialised 1-D kernels (fast1d_ws.cuh): row t holds M planes of NC
+// entries, plane m entry c = likelihood of cell c*M + m (0 beyond the grid), so the M loads of compute thread c are
+// coalesced across the warp.  `src` != NULL: permute a caller-supplied table (BLG_OM_TABLE) instead of evaluating.
+__global__ void lik_table_perm_kernel(DevProblem pb, const StepC *__restrict__ steps, const double *__restrict__ src,
+                                      long long T, int M, int NC, double *__restrict__ table) {
+    const long long pitch = (long long)M * NC;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= T * pitch) return;
+    const long long t = e / pitch;
+    const int q = (int)(e - t * pitch);
+    const int m = q / NC, c = q - m * NC;
+    const int g = c * M + m;
+    double v = 0.0;
+    if (g < pb.G) {
+        if (src) {
+            v = src[t * pb.G + g];
+        } else {
+            LikTables tb;
+            tb.A0 = pb.tabA[0];
+            tb.A1 = pb.tabA[1];
+            tb.A2 = pb.tabA[2];
+            tb.B0 = pb.tabB[0];
+            tb.B1 = pb.tabB[1];
+            v = lik_cell(pb, tb, steps + t * pb.ncols_eff, g, 0);
+        }
+    }
+    table[e] = v;
+}
+
 // out[j] = sum_k weight[k] * state[k][j]   (core.py:1410, :2195-2197, :2212); fixed summation order
 __global__ void mix_kernel(const double *__restrict__ state, const double *__restrict__ weight, long long K, long long n,
                            double *__restrict__ out) {

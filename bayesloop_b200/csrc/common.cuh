@@ -82,6 +82,8 @@ struct PassArgs {
     int tile_doubles;
     long long *trace;    // debugging: per-CTA {smid, combo, start, end} or NULL
     int halo;            // fast 1-D kernels: reflected halo cells on each side of the state (0 = generic kernels)
+    int ws_part, ws_ctl; // warp-specialised 1-D kernels: offsets (doubles) of the partial sums / control block
+    long long lik_pitch; // row pitch (doubles) of lik_table: G, or M*threads for the owner-order table
 };
 
 __device__ __forceinline__ long long combo_of_block(const PassArgs &a) {

@@ -30,4 +30,30 @@ PassKernel bwd_fast1d_entry(int M, int nt) {
     }
 }
 
+// warp-specialised kernels (fast1d_ws_inst.cu)
+#define BLG_WS(M, NT)                          \
+    PassKernel fwd_fast1d_ws_m##M##_nt##NT(); \
+    PassKernel bwd_fast1d_ws_m##M##_nt##NT();
+BLG_WS(3, 128)
+BLG_WS(7, 128)
+BLG_WS(11, 128)
+BLG_WS(11, 256)
+#undef BLG_WS
+
+PassKernel fwd_fast1d_ws_entry(int M, int nt) {
+    if (nt == 128 && M == 3) return fwd_fast1d_ws_m3_nt128();
+    if (nt == 128 && M == 7) return fwd_fast1d_ws_m7_nt128();
+    if (nt == 128 && M == 11) return fwd_fast1d_ws_m11_nt128();
+    if (nt == 256 && M == 11) return fwd_fast1d_ws_m11_nt256();
+    return nullptr;
+}
+
+PassKernel bwd_fast1d_ws_entry(int M, int nt) {
+    if (nt == 128 && M == 3) return bwd_fast1d_ws_m3_nt128();
+    if (nt == 128 && M == 7) return bwd_fast1d_ws_m7_nt128();
+    if (nt == 128 && M == 11) return bwd_fast1d_ws_m11_nt128();
+    if (nt == 256 && M == 11) return bwd_fast1d_ws_m11_nt256();
+    return nullptr;
+}
+
 }  // namespace blg

@@ -1,0 +1,433 @@
+// fast1d_ws.cuh -- K1w/K2w: warp-specialised version of the fast 1-D kernels (1-D grid, program = ONE
+// GaussianRandomWalk: BASELINE.json configs[0], configs[1]).
+//
+// Why (measured on B200 with ncu, profiles/r1b_*): in the single-role kernels of fast1d.cuh the convolution is 57 % of
+// the executed instructions but only 37 % of the stall samples -- the time goes into the short serial section around
+// it (strided 8-byte global loads/stores at ~28 sectors per request, the 5-level shuffle reduction, the reciprocal,
+// the row store), which a sweep with only ~3.5 resident chains per SM cannot hide.  Here a CTA is
+//     NCW = NT/32 - 1 COMPUTE warps: per step  lik loads -> convolution (registers) -> x kappa x lik -> state + one
+//                                    partial sum per thread to shared memory -> CTA barrier;
+//     1 SERVICE warp:                after the barrier reduces the partial sums, computes the normaliser (Newton
+//                                    reciprocal), hands it back through shared memory + a named barrier, stores the
+//                                    normalised row with coalesced 16-byte accesses (forward) / scales and stores the
+//                                    smoothed row and refills the alpha ring with bulk-async copies (backward), keeps
+//                                    the log-evidence product -- all of it overlapped with the next convolution.
+// The service warp's index rotates with the CTA's slot on its SM so that the four sub-partitions get the same mix.
+// The likelihood table of the call is generated in "owner order" ([t][m][thread], lik_table_perm_kernel) so that
+// every compute thread fetches its M cells with fully coalesced loads and cells beyond the grid read 0.
+//
+// Semantics: identical to fast1d.cuh (core.py:372-417, :424-470; transitionModels.py:96-118).
+#pragma once
+
+#include "fast1d.cuh"
+
+namespace blg {
+
+__device__ __forceinline__ void named_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// combo of this CTA (see combo_of_sm in common.cuh) plus the CTA's arrival index on its SM
+__device__ __forceinline__ long long combo_and_slot(const PassArgs &a, int *sh, int &slot) {
+    if (threadIdx.x == 0) {
+        int b = -1, k = 0;
+        if (a.sm_assign) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            int *counters = a.sm_state, *claimed = a.sm_state + a.sm_count;
+            b = -2;
+            if ((int)smid < a.sm_count) {
+                k = atomicAdd(&counters[smid], 1);
+                if (k < a.sm_slots) {
+                    b = a.sm_assign[smid * a.sm_slots + k];
+                    if (b >= 0 && atomicCAS(&claimed[b], 0, 1) != 0) b = -1;
+                }
+            }
+            if (b == -2) {  // late arrival: adopt a combo nobody has claimed yet
+                b = -1;
+                for (long long j = 0; j < a.B; ++j) {
+                    const int cand = a.order ? a.order[j] : (int)j;
+                    if (atomicCAS(&claimed[cand], 0, 1) == 0) {
+                        b = cand;
+                        break;
+                    }
+                }
+            }
+        } else {
+            const long long j = combo_of_block(a);
+            b = (int)(a.order ? a.order[j] : j);
+            k = (int)(blockIdx.x / (a.num_sms > 0 ? a.num_sms : 1));
+        }
+        sh[0] = b;
+        sh[1] = k;
+    }
+    __syncthreads();
+    slot = sh[1];
+    return sh[0];
+}
+
+// v[0..M) -> cells i0.. of a haloed line, plus their mirror images inside the halo (halo <= n)
+template <int M>
+__device__ __forceinline__ void store_cells_mirrored(double *line, int i0, int n, int halo, const double (&v)[M]) {
+    if (i0 + M <= n) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) line[i0 + m] = v[m];
+    } else {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            if (i0 + m < n) line[i0 + m] = v[m];
+    }
+    if (i0 < halo) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            if (i0 + m < halo && i0 + m < n) line[-1 - (i0 + m)] = v[m];
+    }
+    if (i0 + M > n - halo) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            if (i0 + m >= n - halo && i0 + m < n) line[2 * n - 1 - (i0 + m)] = v[m];
+    }
+}
+
+__device__ __forceinline__ void trace_end_lane0(const PassArgs &a, int lane) {
+    if (a.trace && lane == 0) a.trace[4 * (long long)blockIdx.x + 3] = global_ns();
+}
+
+struct WsRoles {
+    int lane, warp, rot, ct, i0;
+    bool service, owner;
+};
+
+template <int M, int NT>
+__device__ __forceinline__ WsRoles ws_roles(int slot, int n) {
+    constexpr int NW = NT / 32;
+    WsRoles r;
+    r.lane = threadIdx.x & 31;
+    r.warp = threadIdx.x >> 5;
+    r.rot = slot % NW;
+    r.service = r.warp == r.rot;
+    const int cw = r.warp - (r.warp > r.rot ? 1 : 0);
+    r.ct = cw * 32 + r.lane;
+    r.i0 = r.ct * M;
+    r.owner = !r.service && r.i0 < n;
+    return r;
+}
+
+// Control block of the ws kernels (doubles at a.ws_ctl): [0],[1] normaliser by step parity, [2] (as int) dead flag.
+
+// ------------------------------------------------------------------------------------------------ K1w forward
+template <int M, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) fwd_fast1d_ws_kernel(const PassArgs a) {
+    constexpr int NW = NT / 32, NCOMP = (NW - 1) * 32;
+    extern __shared__ __align__(16) double sm[];
+    const DevProblem &pb = a.pb;
+    int slot;
+    const long long b = combo_and_slot(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6), slot);
+    if (b < 0) return;
+    trace_begin(a, b);
+    const int n = pb.G, halo = a.halo;
+    const long long T = a.T;
+    Fast1dSetup s;
+    // weights, windows (fast1d_setup without the per-cell likelihood tables: the table is always shared here)
+    s.buf0 = sm + halo;
+    s.buf1 = sm + (a.Gp + 2 * halo) + halo;
+    s.rs.buf = sm + a.off_misc;
+    s.rs.phase = 0;
+    s.W = sm + a.off_w;
+    s.sigma = a.pg.param[b];
+    s.R = a.pg.radius[b];
+    {
+        const int *win = a.pg.window + b * 4;
+        s.f_lo = win[0];
+        s.f_hi = win[1];
+    }
+    if (!(s.sigma > 0.0) || s.R <= 0) s.R = 0;
+    if ((2 * s.R + M) / M * (M + 1) > a.pg.w_len[0]) {  // radius beyond blg_program.max_radius
+        if (threadIdx.x == 0) {
+            a.logE[b] = NAN;
+            if (a.alive) a.alive[b] = -2;
+        }
+        return;
+    }
+    build_weights_chunked<M>(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
+    const WsRoles r = ws_roles<M, NT>(slot, n);
+    double *PP = sm + a.ws_part;
+    volatile double *ctl = sm + a.ws_ctl;
+    volatile int *deadFlag = reinterpret_cast<volatile int *>(sm + a.ws_ctl + 2);
+    {
+        const double *init = (a.flags & BLG_F_INIT_STATE) ? a.init_state + b * (long long)n : a.prior;
+        for (int g = threadIdx.x; g < n; g += NT) store_mirrored(s.buf0, g, n, halo, init[g]);
+        for (int j = threadIdx.x; j < NCOMP; j += NT) PP[j] = 0.0;  // threads without cells never write their slot
+        if (threadIdx.x == 0) *deadFlag = 0;
+    }
+    __syncthreads();
+    const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
+    const bool first = (a.flags & BLG_F_TRANSITION_FIRST) != 0;
+
+    if (!r.service) {
+        // ------------------------------------------------------------------ compute warps
+        double *cur = s.buf0, *nxt = s.buf1;
+        const double *likp = a.lik_table + r.ct;
+        const long long pitch = a.lik_pitch;
+        double kappa = 1.0;
+        for (long long t = 0; t < T; ++t) {
+            double v[M], lk[M];
+            if (r.owner) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + t * pitch + m * NCOMP);
+            }
+            const bool trans = (t > 0 || first) && (t - 1 >= s.f_lo) && (t - 1 < s.f_hi);
+            if (r.owner) {
+                if (trans && s.R > 0) {
+                    conv_item<M>(cur, r.i0, s.R, s.W, v);  // transitionModels.py:111
+                } else {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) v[m] = cur[r.i0 + m];
+                }
+            }
+            if (t > 0) {  // normaliser of the previous step, produced by the service warp during the convolution
+                named_sync(1, NT);
+                if (*deadFlag) break;
+                kappa = ctl[(t - 1) & 1];
+            }
+            if (r.owner) {
+                // alpha <- prior * likelihood (core.py:375-382); cells beyond the grid carry lik = 0
+#pragma unroll
+                for (int m = 0; m < M; ++m) v[m] *= kappa * lk[m];
+                store_cells_mirrored<M>(nxt, r.i0, n, halo, v);
+                PP[r.ct] = tree_sum<M>(v);
+            }
+            __syncthreads();  // new state and its partial sums are visible to everybody
+            double *tmp = cur;
+            cur = nxt;
+            nxt = tmp;
+        }
+    } else {
+        // ------------------------------------------------------------------ service warp
+        double *seq = store ? a.alpha_seq + b * T * (long long)n : nullptr;
+        const bool vec = a.use_bulk != 0;  // rows are 16-byte aligned
+        LogProduct lp;
+        lp.init();
+        bool dead = false;
+        for (long long t = 0; t < T; ++t) {
+            __syncthreads();
+            double part = 0.0;
+#pragma unroll
+            for (int j = 0; j < NCOMP / 32; ++j) part += PP[j * 32 + r.lane];
+            const double norm = warp_sum(part);  // core.py:385
+            if (!(norm > 0.0)) {                 // core.py:388-400
+                dead = true;
+                if (r.lane == 0) *deadFlag = 1;
+                if (t + 1 < T) named_arrive(1, NT);
+                break;
+            }
+            const double kappa = fast_rcp(norm);
+            if (r.lane == 0) ctl[t & 1] = kappa;
+            if (t + 1 < T) named_arrive(1, NT);
+            const double *st = (t & 1) ? s.buf0 : s.buf1;  // the buffer the compute warps just filled
+            if (store) {  // core.py:389, :408 -- normalised filtering distribution
+                double *row = seq + t * (long long)n;
+                if (vec) {
+                    for (int j = 2 * r.lane; j < n; j += 64) {
+                        double2 x = *reinterpret_cast<const double2 *>(st + j);
+                        x.x *= kappa;
+                        x.y *= kappa;
+                        __stcs(reinterpret_cast<double2 *>(row + j), x);
+                    }
+                } else {
+                    for (int j = r.lane; j < n; j += 32) __stcs(row + j, st[j] * kappa);
+                }
+            }
+            if ((a.flags & BLG_F_SAVE_STATE) && a.final_state && t == T - 1) {
+                double *fs = a.final_state + b * (long long)n;
+                for (int j = r.lane; j < n; j += 32) fs[j] = st[j] * kappa;
+            }
+            if (r.lane == 0) {
+                lp.mul(norm);                                         // core.py:403
+                if (a.local) a.local[b * T + t] = norm * pb.lc_prod;  // core.py:404
+            }
+        }
+        if (r.lane == 0) {
+            double logE = lp.log_value();
+            if (dead)
+                logE = -INFINITY;
+            else if (!(a.flags & BLG_F_INIT_STATE))
+                logE += log(pb.lc_prod);  // core.py:417
+            a.logE[b] = logE;
+            if (a.alive) a.alive[b] = dead ? 0 : 1;
+        }
+        trace_end_lane0(a, r.lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K2w backward
+template <int M, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassArgs a) {
+    constexpr int NW = NT / 32, NCOMP = (NW - 1) * 32;
+    extern __shared__ __align__(16) double sm[];
+    const DevProblem &pb = a.pb;
+    int slot;
+    const long long b = combo_and_slot(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6), slot);
+    if (b < 0) return;
+    trace_begin(a, b);
+    if (a.alive && a.alive[b] != 1) return;  // the forward pass aborted (core.py:400)
+    const int n = pb.G, halo = a.halo;
+    const long long T = a.T;
+    Fast1dSetup s;
+    s.buf0 = sm + halo;
+    s.buf1 = sm + (a.Gp + 2 * halo) + halo;
+    s.rs.buf = sm + a.off_misc;
+    s.rs.phase = 0;
+    s.W = sm + a.off_w;
+    s.sigma = a.pg.param[b];
+    s.R = a.pg.radius[b];
+    {
+        const int *win = a.pg.window + b * 4;
+        s.b_lo = win[2];
+        s.b_hi = win[3];
+    }
+    if (!(s.sigma > 0.0) || s.R <= 0) s.R = 0;
+    if ((2 * s.R + M) / M * (M + 1) > a.pg.w_len[0]) return;
+    build_weights_chunked<M>(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
+    const WsRoles r = ws_roles<M, NT>(slot, n);
+    double *PP = sm + a.ws_part;  // [3][NCOMP]
+    volatile double *ctl = sm + a.ws_ctl;
+    volatile int *deadFlag = reinterpret_cast<volatile int *>(sm + a.ws_ctl + 2);
+    double *seq = a.alpha_seq + b * T * (long long)n;
+    double *const S0 = sm + a.off_stage;  // alpha[t] ring: 2 slots of Gp doubles; overwritten in place by alpha*beta
+    const int Gp = a.Gp;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
+    const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
+    for (int j = threadIdx.x; j < 3 * NCOMP; j += NT) PP[j] = 0.0;  // threads without cells never write their slots
+    if (threadIdx.x == 0) {
+        *deadFlag = 0;
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (!r.service) {
+        // ------------------------------------------------------------------ compute warps
+        double *cur = s.buf0, *nxt = s.buf1;
+        const double *likp = a.lik_table + r.ct;
+        const long long pitch = a.lik_pitch;
+        uint32_t phases = 0u;  // bit s = parity of the next completion of ring slot s
+        double beta[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) beta[m] = (r.owner && r.i0 + m < n) ? 1.0 / (double)n : 0.0;  // core.py:424-425
+        double kb = 1.0;  // keeps the (scale-free) beta recursion in range: 1 / sum(beta) of the previous step
+        for (long long i = T - 1; i >= 0; --i) {
+            const int sb = (int)(i & 1);
+            double lk[M];
+            if (r.owner) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + i * pitch + m * NCOMP);
+            }
+            if (i < T - 1) {
+                const bool trans = (i + 1 >= s.b_lo) && (i + 1 < s.b_hi);
+                if (r.owner) {
+                    if (trans && s.R > 0) {
+                        conv_item<M>(cur, r.i0, s.R, s.W, beta);  // transitionModels.py:117-118
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < M; ++m) beta[m] = cur[r.i0 + m];
+                    }
+#pragma unroll
+                    for (int m = 0; m < M; ++m)
+                        if (r.i0 + m >= n) beta[m] = 0.0;
+                }
+                named_sync(1, NT);
+                if (*deadFlag) break;
+                kb = ctl[(i + 1) & 1];
+            }
+            mbar_wait(&bars[sb], (phases >> sb) & 1u);
+            phases ^= 1u << sb;
+            double *A = S0 + sb * Gp;
+            if (r.owner) {
+                double pu[M], ql[M], st[M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const int li = r.i0 + m;
+                    const double al = li < n ? A[li] : 0.0;
+                    pu[m] = al * beta[m];                           // posterior ~ alpha*beta   core.py:436
+                    ql[m] = li < n ? fast_div(pu[m], lk[m]) : 0.0;  // core.py:463
+                    st[m] = beta[m] * kb * lk[m];                   // beta*likelihood          core.py:467
+                    if (li < n) A[li] = pu[m];
+                }
+                store_cells_mirrored<M>(nxt, r.i0, n, halo, st);
+                PP[r.ct] = tree_sum<M>(pu);
+                PP[NCOMP + r.ct] = tree_sum<M>(beta);
+                PP[2 * NCOMP + r.ct] = tree_sum<M>(ql);
+            }
+            __syncthreads();
+            double *tmp = cur;
+            cur = nxt;
+            nxt = tmp;
+        }
+    } else {
+        // ------------------------------------------------------------------ service warp
+        if (r.lane == 0) {
+            bulk_load(S0 + ((T - 1) & 1) * Gp, seq + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) & 1]);
+            if (T >= 2) bulk_load(S0 + ((T - 2) & 1) * Gp, seq + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) & 1]);
+        }
+        bool dead = false;
+        long long i = T - 1;
+        for (; i >= 0; --i) {
+            const int sb = (int)(i & 1);
+            __syncthreads();
+            double spu = 0.0, sbeta = 0.0, sql = 0.0;
+#pragma unroll
+            for (int j = 0; j < NCOMP / 32; ++j) {
+                spu += PP[j * 32 + r.lane];
+                sbeta += PP[NCOMP + j * 32 + r.lane];
+                sql += PP[2 * NCOMP + j * 32 + r.lane];
+            }
+            spu = warp_sum(spu);
+            sbeta = warp_sum(sbeta);
+            sql = warp_sum(sql);
+            if (!(spu > 0.0) || !(sbeta > 0.0)) {  // core.py:440-452
+                dead = true;
+                if (r.lane == 0) *deadFlag = 1;
+                if (i > 0) named_arrive(1, NT);
+                break;
+            }
+            const double inv = fast_rcp(spu);  // posterior = alpha*beta / sum(alpha*beta)   core.py:439-441
+            if (r.lane == 0) ctl[i & 1] = fast_rcp(sbeta);  // core.py:470, applied lazily by the compute warps
+            if (i > 0) named_arrive(1, NT);
+            double *row = seq + i * (long long)n;
+            const double *P = S0 + sb * Gp;
+            for (int j = 2 * r.lane; j < n; j += 64) {
+                double2 x = *reinterpret_cast<const double2 *>(P + j);
+                x.x *= inv;
+                x.y *= inv;
+                __stcs(reinterpret_cast<double2 *>(row + j), x);
+            }
+            __syncwarp();
+            if (r.lane == 0) {
+                if (i >= 2) {  // the slot is free again: prefetch alpha[i-2] into it
+                    fence_proxy_async();
+                    bulk_load(S0 + sb * Gp, seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
+                }
+                if (a.local) a.local[b * T + i] = fast_div(spu, sql * pb.lc_prod);  // 1/(sum(post/lik)*lc)  core.py:463
+            }
+        }
+        if (dead) {
+            // drain the prefetch that is still in flight before the CTA's shared memory is released
+            if (i >= 1) {
+                const long long rr = i - 1;
+                mbar_wait(&bars[rr & 1], (uint32_t)(((T - 1 - rr) >> 1) & 1));
+            }
+            if (r.lane == 0) {
+                a.logE[b] = -INFINITY;
+                if (a.alive) a.alive[b] = -1;
+            }
+        }
+        trace_end_lane0(a, r.lane);
+    }
+}
+
+}  // namespace blg

@@ -14,6 +14,11 @@ using PassKernel = void (*)(const PassArgs);
 PassKernel fwd_fast1d_entry(int M, int nt);
 PassKernel bwd_fast1d_entry(int M, int nt);
 
+// warp-specialised fast 1-D kernels (fast1d_ws.cuh): (M, nt) in {(3,128), (7,128), (11,128), (11,256)}; nt/32 - 1
+// compute warps own M cells per thread, one service warp normalises / stores / prefetches
+PassKernel fwd_fast1d_ws_entry(int M, int nt);
+PassKernel bwd_fast1d_ws_entry(int M, int nt);
+
 // generic resident kernels (resident.cuh): nt in {256, 512, 1024}; stream = state in global scratch (1024 threads)
 PassKernel fwd_resident_entry(int nt, bool stream);
 PassKernel bwd_resident_entry(int nt, bool stream);
