@@ -173,12 +173,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) fwd_fast1d_ws_kernel(const PassA
         const double *likp = a.lik_table + r.ct;
         const long long pitch = a.lik_pitch;
         double kappa = 1.0;
-        for (long long t = 0; t < T; ++t) {
-            double v[M], lk[M];
-            if (r.owner) {
+        double lk[M];  // likelihood of this thread's cells, fetched one step ahead (right after the previous use)
+        if (r.owner) {
 #pragma unroll
-                for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + t * pitch + m * NCOMP);
-            }
+            for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + m * NCOMP);
+        }
+        for (long long t = 0; t < T; ++t) {
+            double v[M];
             const bool trans = (t > 0 || first) && (t - 1 >= s.f_lo) && (t - 1 < s.f_hi);
             if (r.owner) {
                 if (trans && s.R > 0) {
@@ -197,6 +198,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) fwd_fast1d_ws_kernel(const PassA
                 // alpha <- prior * likelihood (core.py:375-382); cells beyond the grid carry lik = 0
 #pragma unroll
                 for (int m = 0; m < M; ++m) v[m] *= kappa * lk[m];
+                if (t + 1 < T) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + (t + 1) * pitch + m * NCOMP);
+                }
                 store_cells_mirrored<M>(nxt, r.i0, n, halo, v);
                 PP[r.ct] = tree_sum<M>(v);
             }
@@ -320,13 +325,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassA
 #pragma unroll
         for (int m = 0; m < M; ++m) beta[m] = (r.owner && r.i0 + m < n) ? 1.0 / (double)n : 0.0;  // core.py:424-425
         double kb = 1.0;  // keeps the (scale-free) beta recursion in range: 1 / sum(beta) of the previous step
+        double lk[M];  // likelihood of this thread's cells, fetched one step ahead (right after the previous use)
+        if (r.owner) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + (T - 1) * pitch + m * NCOMP);
+        }
         for (long long i = T - 1; i >= 0; --i) {
             const int sb = (int)(i & 1);
-            double lk[M];
-            if (r.owner) {
-#pragma unroll
-                for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + i * pitch + m * NCOMP);
-            }
             if (i < T - 1) {
                 const bool trans = (i + 1 >= s.b_lo) && (i + 1 < s.b_hi);
                 if (r.owner) {
@@ -348,20 +353,32 @@ __global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassA
             phases ^= 1u << sb;
             double *A = S0 + sb * Gp;
             if (r.owner) {
-                double pu[M], ql[M], st[M];
+                double st[M];
+                double spu0 = 0.0, spu1 = 0.0, sql0 = 0.0, sql1 = 0.0;  // two chains each: short dependency paths
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
                     const int li = r.i0 + m;
                     const double al = li < n ? A[li] : 0.0;
-                    pu[m] = al * beta[m];                           // posterior ~ alpha*beta   core.py:436
-                    ql[m] = li < n ? fast_div(pu[m], lk[m]) : 0.0;  // core.py:463
-                    st[m] = beta[m] * kb * lk[m];                   // beta*likelihood          core.py:467
-                    if (li < n) A[li] = pu[m];
+                    const double pu = al * beta[m];                            // posterior ~ alpha*beta   core.py:436
+                    const double ql = li < n ? fast_div(pu, lk[m]) : 0.0;      // core.py:463
+                    st[m] = beta[m] * kb * lk[m];                              // beta*likelihood          core.py:467
+                    if (li < n) A[li] = pu;
+                    if (m & 1) {
+                        spu1 += pu;
+                        sql1 += ql;
+                    } else {
+                        spu0 += pu;
+                        sql0 += ql;
+                    }
+                }
+                if (i > 0) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + (i - 1) * pitch + m * NCOMP);
                 }
                 store_cells_mirrored<M>(nxt, r.i0, n, halo, st);
-                PP[r.ct] = tree_sum<M>(pu);
+                PP[r.ct] = spu0 + spu1;
                 PP[NCOMP + r.ct] = tree_sum<M>(beta);
-                PP[2 * NCOMP + r.ct] = tree_sum<M>(ql);
+                PP[2 * NCOMP + r.ct] = sql0 + sql1;
             }
             __syncthreads();
             double *tmp = cur;

@@ -116,10 +116,10 @@ class Program:
 
     def _assignment(self, lo, hi, sms, slots=4):
         """Combos of one call pre-assigned to SMs: longest-processing-time-first into `sms` bins of `slots`
-        entries.  Cost model fitted to a per-CTA trace on B200 (tools/trace_c2.py, BLG_TRACE): all CTAs of an SM
-        finish together, and the SM's time per step is ~1.37 us per resident CTA + 2.2 ns per convolution tap
-        (1000-cell grid) -- the fixed per-step work of a chain dominates, so SMs that must take 4 chains get the
-        lightest ones."""
+        entries.  Cost model fitted to a per-CTA trace of the warp-specialised kernels on B200 (tools/trace_c2.py,
+        BLG_TRACE; 1000-cell grid): all CTAs of an SM finish together and the SM's time per step is
+        ~0.08 us per resident CTA + 0.02 us per convolution tap -- the convolution dominates, the fixed per-step
+        work of a chain is hidden by the service warp."""
         if hi - lo > sms * slots:
             return None
         key = (lo, hi, sms, slots)
@@ -129,7 +129,7 @@ class Program:
                 self._orders[key] = self._engine.to_device(_ASSIGNMENTS[memo])
                 return self._orders[key]
             taps = (2 * self.host['radius'][lo:hi] + 1).sum(axis=1).astype(float)
-            cost = 1.37 + 0.0022 * taps
+            cost = 0.08 + 0.02 * taps
             table = np.full((sms, slots), -1, dtype=np.int32)
             load = np.zeros(sms)
             fill = np.zeros(sms, dtype=np.int64)
