@@ -19,6 +19,7 @@ namespace {
 
 thread_local char g_err[512];
 std::atomic<long long> g_launches{0};
+const char *g_last_kernel = "none";
 
 int fail(const char *fmt, const char *detail = "") {
     snprintf(g_err, sizeof g_err, fmt, detail);
@@ -65,6 +66,7 @@ int blg_version(void) { return BLG_ABI_VERSION; }
 const char *blg_last_error(void) { return g_err; }
 const char *blg_backend(void) { return "cuda:sm_100a"; }
 int64_t blg_launch_count(void) { return g_launches.load(); }
+const char *blg_last_kernel(void) { return g_last_kernel; }
 
 int blg_plan_create(const blg_problem *p, blg_plan **out) {
     if (!p || !out) return fail("null argument");
@@ -444,6 +446,7 @@ bool stream_layout(const blg_plan *pl, const blg_program &pg, PassArgs &a, Layou
 int launch_stream(PassKernel kernel, blg_plan *pl, PassArgs &a, Layout lay, long long B, cudaStream_t st, const char *name,
                   int threads = 1024) {
     lay.nt = threads;
+    g_last_kernel = name;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     long long grid = B < pl->num_sms ? B : pl->num_sms;  // one persistent CTA per SM, looping over combos
@@ -458,6 +461,118 @@ int launch_stream(PassKernel kernel, blg_plan *pl, PassArgs &a, Layout lay, long
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFreeAsync(scratch, st));
+    return 0;
+}
+
+// Cluster-resident 2-D kernels (cluster2d.cuh): picks the cluster size C (bands of rows per CTA) such that one band
+// is one work item per thread in both convolutions, the axis-0 radius fits in the smallest band, and the state
+// buffer (+ the alpha staging band of the backward pass) fits in shared memory.
+bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags, bool backward, PassArgs &a, Layout &lay,
+                      int &C) {
+    const DevProblem &d = pl->dev;
+    if (d.ndim != 2 || getenv("BLG_NO_CLUSTER2D")) return false;
+    if (flags & (BLG_F_INIT_STATE | BLG_F_SAVE_STATE | BLG_F_TRANSITION_FIRST | BLG_F_ACCUMULATE)) return false;
+    if (!stream2d_supports(pg.n_ops, pg.kind, pg.axis)) return false;
+    if (d.n1 % 2) return false;  // 16-byte aligned bands for the bulk-async copies
+    int NT, M0, M1, cells;
+    cluster2d_params(&NT, &M0, &M1, &cells);
+    int r0max = 0, r1max = 0;
+    for (int k = 0; k < pg.n_ops; ++k)
+        if (pg.kind[k] == BLG_OP_GRW) {
+            int &r = pg.axis[k] == 0 ? r0max : r1max;
+            if (pg.max_radius[k] > r) r = pg.max_radius[k];
+        }
+    if (r1max + M1 > d.n1) return false;
+    const char *force = getenv("BLG_CLUSTER2D_C");
+    for (int c = 8; c >= 2; c /= 2) {
+        if (force && atoi(force) != c) continue;
+        const int nb = (d.n0 + c - 1) / c;
+        const int last = d.n0 - (c - 1) * nb;
+        if (last < 1 || r0max > last) continue;
+        if (nb * ((d.n1 + M1 - 1) / M1) > NT || d.n1 * ((nb + M0 - 1) / M0) > NT || nb * d.n1 > cells * NT) continue;
+        const int nbp = (nb + M0 - 1) / M0 * M0;
+        int off = 0;
+        a.c2_nb = nb;
+        a.c2_h0 = r0max;
+        a.c2_off_x = off;
+        a.c2_x_doubles = (2 * r0max + nbp) * d.n1;
+        off += a.c2_x_doubles;
+        a.c2_off_s = off;
+        if (backward) off += nb * d.n1;
+        a.off_w = off;
+        int woff = 0;
+        for (int k = 0; k < pg.n_ops; ++k) {
+            a.pg.w_off[k] = woff;
+            a.pg.w_len[k] = 0;
+            if (pg.kind[k] == BLG_OP_GRW) {
+                a.pg.w_len[k] = even_up(2 * pg.max_radius[k] + 1);
+                woff += a.pg.w_len[k];
+            }
+        }
+        off += woff;
+        a.off_misc = even_up(off);
+        lay.bytes = (size_t)(a.off_misc + kMiscDoubles) * sizeof(double);
+        lay.nt = NT;
+        if (lay.bytes > kSmemLimit) continue;
+        a.halo = 0;
+        a.Gp = even_up(d.G);
+        C = c;
+        return true;
+    }
+    return false;
+}
+
+int launch_cluster(PassKernel kernel, const PassArgs &a, const Layout &lay, long long B, int C, cudaStream_t st,
+                   const char *name) {
+    g_last_kernel = name;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(B * C), 1, 1);
+    cfg.blockDim = dim3((unsigned)lay.nt, 1, 1);
+    cfg.dynamicSmemBytes = lay.bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (getenv("BLG_VERBOSE")) {
+        int clusters = 0;
+        cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg);
+        fprintf(stderr, "[blgrid] %s: %lld clusters x %d CTAs x %d threads, %zu B smem/CTA, band %d rows, halo %d rows, "
+                        "%d clusters resident\n", name, B, C, lay.nt, lay.bytes, a.c2_nb, a.c2_h0, clusters);
+    }
+    long long *trace = nullptr;
+    PassArgs a2 = a;
+    const long long nblk = B * C;
+    if (getenv("BLG_TRACE")) {  // per-CTA phase cycle counters (forward kernel built with PROF)
+        CUDA_TRY(cudaMalloc(&trace, (size_t)nblk * 8 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(trace, 0, (size_t)nblk * 8 * sizeof(long long)));
+        a2.trace = trace;
+    }
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a2));
+    ++g_launches;
+    if (trace) {
+        std::vector<long long> h((size_t)nblk * 8);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(trace);
+        static int seq = 0;
+        char path[512];
+        snprintf(path, sizeof path, "%s.%s.%d.csv", getenv("BLG_TRACE"), name, seq++);
+        if (FILE *f = fopen(path, "w")) {
+            fprintf(f, "block,flush,axis0,axis1,wait_split,sweep,reduce,total,steps\n");
+            for (long long i = 0; i < nblk; ++i) {
+                fprintf(f, "%lld", i);
+                for (int k = 0; k < 8; ++k) fprintf(f, ",%lld", h[8 * i + k]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     return 0;
 }
 
@@ -497,6 +612,7 @@ int fast_m(bool backward) {
 }
 
 int launch_resident(PassKernel kernel, const PassArgs &a, const Layout &lay, long long B, cudaStream_t st, const char *name) {
+    g_last_kernel = name;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
     // several CTAs (combos) must share an SM: ask for the full shared-memory carveout
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -616,6 +732,13 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
         if (PassKernel k = fwd_fast1d_entry(M, lay.nt)) return launch_resident(k, a, lay, grid, st, "fwd_fast1d");
     }
     a.halo = 0;
+    {
+        int C = 0;
+        const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, false, false, a, lay);
+        if (want && !getenv("BLG_FORCE_STREAM") && (!store || (uintptr_t)out->alpha_seq % 16 == 0) &&
+            cluster2d_layout(pl, in->prog, flags, false, a, lay, C))
+            return launch_cluster(fwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr), a, lay, in->B, C, st, "fwd_cluster2d");
+    }
     if (!resident_layout(pl, in->prog, false, false, a, lay) || getenv("BLG_FORCE_STREAM")) {
         if (pl->dev.ndim == 2 && stream2d_supports(in->prog.n_ops, in->prog.kind, in->prog.axis) && getenv("BLG_STREAM2D") &&
             stream_layout(pl, in->prog, a, lay, stream2d_chunk()))
@@ -663,6 +786,13 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
         if (PassKernel k = bwd_fast1d_entry(M, lay.nt)) return launch_resident(k, a, lay, grid, st, "bwd_fast1d");
     }
     a.halo = 0;
+    {
+        int C = 0;
+        const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, true, false, a, lay);
+        if (want && !getenv("BLG_FORCE_STREAM") && (uintptr_t)out->alpha_seq % 16 == 0 &&
+            cluster2d_layout(pl, in->prog, flags, true, a, lay, C))
+            return launch_cluster(bwd_cluster2d_entry(), a, lay, in->B, C, st, "bwd_cluster2d");
+    }
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
     if (!fits) fits = false;
     if (getenv("BLG_FORCE_STREAM") || (!fits && !resident_layout(pl, in->prog, true, false, a, lay))) {

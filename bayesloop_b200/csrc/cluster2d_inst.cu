@@ -1,0 +1,19 @@
+// cluster2d_inst.cu -- cluster-resident 2-D kernels: nvcc -c -DBLG_INST_BWD={0,1} cluster2d_inst.cu
+#include "kernels.h"
+#include "cluster2d.cuh"
+
+namespace blg {
+
+#if BLG_INST_BWD
+PassKernel bwd_cluster2d_entry() { return bwd_cluster2d_kernel<kC2Threads>; }
+#else
+PassKernel fwd_cluster2d_entry(bool prof) { return prof ? fwd_cluster2d_kernel<kC2Threads, true> : fwd_cluster2d_kernel<kC2Threads, false>; }
+void cluster2d_params(int *threads, int *m0, int *m1, int *cells) {
+    *threads = kC2Threads;
+    *m0 = kC2M0;
+    *m1 = kC2M1;
+    *cells = kC2Cells;
+}
+#endif
+
+}  // namespace blg

@@ -84,6 +84,9 @@ struct PassArgs {
     int halo;            // fast 1-D kernels: reflected halo cells on each side of the state (0 = generic kernels)
     int ws_part, ws_ctl; // warp-specialised 1-D kernels: offsets (doubles) of the partial sums / control block
     long long lik_pitch; // row pitch (doubles) of lik_table: G, or M*threads for the owner-order table
+    // cluster-resident 2-D kernels (cluster2d.cuh): rows per band, halo rows per side, offsets (doubles) of the state
+    // buffer and the staging band, size of the state buffer
+    int c2_nb, c2_h0, c2_off_x, c2_off_s, c2_x_doubles;
 };
 
 __device__ __forceinline__ long long combo_of_block(const PassArgs &a) {

@@ -183,6 +183,7 @@ class Engine:
         L.blg_last_error.restype = ctypes.c_char_p
         L.blg_backend.restype = ctypes.c_char_p
         L.blg_launch_count.restype = ctypes.c_int64
+        L.blg_last_kernel.restype = ctypes.c_char_p
         L.blg_plan_create.argtypes = [ctypes.POINTER(_Problem), ctypes.POINTER(ctypes.c_void_p)]
         L.blg_plan_destroy.argtypes = [ctypes.c_void_p]
         L.blg_plan_destroy.restype = None
@@ -252,6 +253,10 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.blg_launch_count())
+
+    def last_kernel(self):
+        """Kernel family of the last forward / backward pass (tests assert the device path with it)."""
+        return self.lib.blg_last_kernel().decode()
 
     def _check(self, rc):
         if rc != 0:

@@ -165,6 +165,10 @@ int blg_mix(blg_plan *plan, const double *state, const double *weight, int64_t K
 /* Number of kernels launched by this library since load (bench.py's gpu_launches claim). */
 int64_t blg_launch_count(void);
 
+/* Name of the kernel family the last blg_forward / blg_backward call launched ("fwd_fast1d_ws", "bwd_cluster2d",
+ * "fwd_stream", ...; "oracle" for the CPU checker): lets the tests assert which device path produced a result. */
+const char *blg_last_kernel(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,3 +134,90 @@ def test_stream_kernels_on_golden_cases(name, use_cuda, monkeypatch):
     monkeypatch.setenv('BLG_FORCE_STREAM', '1')
     S, got = parity.run_case(name, bl)
     parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cluster-resident 2-D kernels (bayesloop_b200/csrc/cluster2d.cuh): forced onto small grids, checked against the
+# reference goldens and the CPU oracle; the engine reports which kernel family ran, so a silent fall-back fails.
+
+def _gauss2d_cp(bl, engine, n0, n1, T, seed=7):
+    rng = np.random.default_rng(seed)
+    x = np.concatenate([rng.normal(-1, 0.8, T // 2), rng.normal(1.2, 0.8, T - T // 2)])
+    S = bl.HyperStudy(silent=True, engine=engine)
+    S.loadData(x, silent=True)
+    S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, n0), 'std', bl.oint(0, 3, n1)),
+          bl.tm.CombinedTransitionModel(bl.tm.ChangePoint('tChange', [7, T // 2, T - 5]),
+                                        bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.3, 2), target='mean'),
+                                        bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.2, 2), target='std')),
+          silent=True)
+    return S
+
+
+CLUSTER_CONFIGS = {
+    'gauss_2d_64x48': CONFIGS['gauss_2d_64x48'],
+    'gauss_2d_100x100': CONFIGS['gauss_2d_100x100'],
+    'gauss_2d_256x96': CONFIGS['gauss_2d_256x96_stream'],
+    'gauss_2d_cp_96x64': lambda bl, e: _gauss2d_cp(bl, e, 96, 64, T=40),
+    'gauss_2d_ragged_90x50': lambda bl, e: _gauss2d(bl, e, 90, 50, T=25, hb=3, seed=9),  # 90 rows: last band shorter
+}
+
+
+@pytest.mark.parametrize('name', sorted(CLUSTER_CONFIGS))
+@pytest.mark.parametrize('mode', ['full', 'forwardOnly', 'evidenceOnly'])
+def test_cluster2d_matches_cpu_oracle(name, mode, cuda_engine, oracle_engine, monkeypatch):
+    import bayesloop_b200 as bl
+    monkeypatch.setenv('BLG_CLUSTER2D', '1')
+    kw = dict(forwardOnly=(mode == 'forwardOnly'), evidenceOnly=(mode == 'evidenceOnly'))
+    got = helpers.abi_sweep(cuda_engine, CLUSTER_CONFIGS[name](bl, cuda_engine), **kw)
+    assert cuda_engine.last_kernel() == ('bwd_cluster2d' if mode == 'full' else 'fwd_cluster2d')
+    want = helpers.abi_sweep(oracle_engine, CLUSTER_CONFIGS[name](bl, oracle_engine), **kw)
+    np.testing.assert_array_equal(got['alive'], want['alive'])
+    np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-10)
+    np.testing.assert_allclose(got['local'], want['local'], rtol=1e-7)
+    np.testing.assert_allclose(got['localEvidence'], want['localEvidence'], rtol=1e-7)
+    if mode != 'evidenceOnly':
+        rowmax = want['avg'].max(axis=1, keepdims=True)
+        assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-6 * np.abs(want['avg']) + 1e-12 * rowmax)
+        np.testing.assert_allclose(got['means'], want['means'], rtol=1e-8)
+
+
+@pytest.mark.parametrize('csize', ['2', '4'])
+@pytest.mark.parametrize('name', ['syn_hyper_gauss_2d', 'syn_cps_gauss_2d', 'ref_study_2d_grw', 'ref_study_2d_static'])
+def test_cluster2d_on_golden_cases(name, csize, use_cuda, monkeypatch):
+    """Cluster sizes 2 and 4 on the reference's own 2-D known answers (20x20 ... 40x36 grids)."""
+    import bayesloop_b200 as bl
+    monkeypatch.setenv('BLG_CLUSTER2D', '1')
+    monkeypatch.setenv('BLG_CLUSTER2D_C', csize)
+    S, got = parity.run_case(name, bl)
+    assert use_cuda.last_kernel() == 'bwd_cluster2d'
+    parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)
+
+
+def test_cluster2d_agrees_with_stream_kernels_at_c3_size(cuda_engine, monkeypatch):
+    """256 x 256 (BASELINE.json configs[2] grid), too big for the CPU oracle in seconds: the cluster-resident kernels
+    (8 CTAs per combo, default dispatch) against the independent global-memory stream kernels, plus row sums."""
+    import bayesloop_b200 as bl
+
+    def study():
+        rng = np.random.default_rng(2)
+        T = 48
+        mu = np.cumsum(rng.normal(0, 0.05, T))
+        S = bl.HyperStudy(silent=True, engine=cuda_engine)
+        S.loadData(rng.normal(mu, 1.0), silent=True)
+        S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, 256), 'std', bl.oint(0, 3, 256)),
+              bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, 3), target='mean'),
+                                            bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, 3), target='std')),
+              silent=True)
+        return S
+
+    got = helpers.abi_sweep(cuda_engine, study())
+    assert cuda_engine.last_kernel() == 'bwd_cluster2d'
+    monkeypatch.setenv('BLG_NO_CLUSTER2D', '1')
+    want = helpers.abi_sweep(cuda_engine, study())
+    assert cuda_engine.last_kernel() == 'bwd_stream'
+    np.testing.assert_array_equal(got['alive'], want['alive'])
+    np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-11)
+    np.testing.assert_allclose(got['local'], want['local'], rtol=1e-8)
+    rowmax = want['avg'].max(axis=1, keepdims=True)
+    assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-7 * np.abs(want['avg']) + 1e-13 * rowmax)
+    np.testing.assert_allclose(got['avg'].sum(axis=1), 1.0, rtol=1e-12)
