@@ -387,7 +387,9 @@ class Study(object):
         common = dict(T=T, B=1, data=ses.data, prior=ses.prior, lik_table=ses.likTable, program=program,
                       reset_base=ses.reset_base() if ctx.usesReset else None, log_evidence=logE,
                       local_evidence=local, alive=alive, alpha_seq=seq)
-        eng.run('forward', ses.plan, _engine.F_EVIDENCE_ONLY if evidenceOnly else 0, **common)
+        # a backward pass follows: the filtering rows may stay unnormalised (the smoother is scale-free per row)
+        fwdFlags = _engine.F_EVIDENCE_ONLY if evidenceOnly else (0 if forwardOnly else _engine.F_RAW_ALPHA)
+        eng.run('forward', ses.plan, fwdFlags, **common)
         state = int(eng.to_host(alive)[0])
         if state == 1 and not (forwardOnly or evidenceOnly):
             eng.run('backward', ses.plan, 0, **common)
@@ -662,7 +664,8 @@ class HyperStudy(Study):
             common = dict(T=T, B=nb, data=ses.data, prior=ses.prior, lik_table=ses.likTable, program=sw['program'],
                           lo=w0, reset_base=sw['resetBase'], log_evidence=logE[w0:w1], local_evidence=local[w0:w1],
                           alive=alive[w0:w1], alpha_seq=buf)
-            eng.run('forward', ses.plan, _engine.F_EVIDENCE_ONLY if evidenceOnly else 0, **common)
+            eng.run('forward', ses.plan,
+                    _engine.F_EVIDENCE_ONLY if evidenceOnly else (0 if forwardOnly else _engine.F_RAW_ALPHA), **common)
             waves += 1
             le = eng.to_host(logE[w0:w1])  # the evidences fix the averaging weights of this wave
             logEHost[w0:w1] = le

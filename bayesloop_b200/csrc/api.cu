@@ -474,8 +474,8 @@ bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags,
     if (flags & (BLG_F_INIT_STATE | BLG_F_SAVE_STATE | BLG_F_TRANSITION_FIRST | BLG_F_ACCUMULATE)) return false;
     if (!stream2d_supports(pg.n_ops, pg.kind, pg.axis)) return false;
     if (d.n1 % 2) return false;  // 16-byte aligned bands for the bulk-async copies
-    int NT, M0, M1, cells;
-    cluster2d_params(&NT, &M0, &M1, &cells);
+    int NT, M0, M1, cells, wpad;
+    cluster2d_params(&NT, &M0, &M1, &cells, &wpad);
     int r0max = 0, r1max = 0;
     for (int k = 0; k < pg.n_ops; ++k)
         if (pg.kind[k] == BLG_OP_GRW) {
@@ -495,17 +495,18 @@ bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags,
         a.c2_nb = nb;
         a.c2_h0 = r0max;
         a.c2_off_x = off;
-        a.c2_x_doubles = (2 * r0max + nbp) * d.n1;
+        a.c2_rows = 2 * r0max + nbp;
+        a.c2_x_doubles = a.c2_rows * d.n1;
         off += a.c2_x_doubles;
         a.c2_off_s = off;
-        if (backward) off += nb * d.n1;
+        if (backward || a.pb.om_kind == BLG_OM_TABLE) off += nb * d.n1;  // alpha band / staged likelihood band
         a.off_w = off;
         int woff = 0;
         for (int k = 0; k < pg.n_ops; ++k) {
             a.pg.w_off[k] = woff;
             a.pg.w_len[k] = 0;
             if (pg.kind[k] == BLG_OP_GRW) {
-                a.pg.w_len[k] = even_up(2 * pg.max_radius[k] + 1);
+                a.pg.w_len[k] = even_up(2 * pg.max_radius[k] + 1 + wpad);  // zero taps: unguarded tap loops
                 woff += a.pg.w_len[k];
             }
         }

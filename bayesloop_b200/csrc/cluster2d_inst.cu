@@ -8,11 +8,12 @@ namespace blg {
 PassKernel bwd_cluster2d_entry() { return bwd_cluster2d_kernel<kC2Threads>; }
 #else
 PassKernel fwd_cluster2d_entry(bool prof) { return prof ? fwd_cluster2d_kernel<kC2Threads, true> : fwd_cluster2d_kernel<kC2Threads, false>; }
-void cluster2d_params(int *threads, int *m0, int *m1, int *cells) {
+void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad) {
     *threads = kC2Threads;
     *m0 = kC2M0;
     *m1 = kC2M1;
     *cells = kC2Cells;
+    *wpad = kC2WPad;
 }
 #endif
 

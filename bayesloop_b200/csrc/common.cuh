@@ -86,7 +86,7 @@ struct PassArgs {
     long long lik_pitch; // row pitch (doubles) of lik_table: G, or M*threads for the owner-order table
     // cluster-resident 2-D kernels (cluster2d.cuh): rows per band, halo rows per side, offsets (doubles) of the state
     // buffer and the staging band, size of the state buffer
-    int c2_nb, c2_h0, c2_off_x, c2_off_s, c2_x_doubles;
+    int c2_nb, c2_h0, c2_off_x, c2_off_s, c2_x_doubles, c2_rows;
 };
 
 __device__ __forceinline__ long long combo_of_block(const PassArgs &a) {

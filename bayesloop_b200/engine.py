@@ -25,6 +25,7 @@ F_INIT_STATE = 1 << 1
 F_TRANSITION_FIRST = 1 << 2
 F_SAVE_STATE = 1 << 3
 F_ACCUMULATE = 1 << 4
+F_RAW_ALPHA = 1 << 6  # forward rows may stay unnormalised (a backward pass follows)
 F_NORMALIZE_ROWS = 1 << 5
 
 _dp = ctypes.POINTER(ctypes.c_double)

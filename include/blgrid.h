@@ -63,7 +63,10 @@ enum blg_flags {
     BLG_F_SAVE_STATE = 1u << 3,       /* write the last normalised alpha to final_state[b][G]                     */
     BLG_F_ACCUMULATE = 1u << 4,       /* backward: avg[t][g] += exp(log_weight[b]) * max(post, 1e-300)            */
                                       /* (core.py:1358-1366) instead of overwriting alpha_seq with the posterior  */
-    BLG_F_NORMALIZE_ROWS = 1u << 5    /* finalize: divide each [G] row by its sum first (core.py:1379-1382)       */
+    BLG_F_NORMALIZE_ROWS = 1u << 5,   /* finalize: divide each [G] row by its sum first (core.py:1379-1382)       */
+    BLG_F_RAW_ALPHA = 1u << 6         /* forward: the rows of alpha_seq may be left UNNORMALISED (each row scaled */
+                                      /* by a positive factor): valid only as the input of blg_backward, which is */
+                                      /* scale-free per row (core.py:436-441 renormalises alpha*beta)             */
 };
 
 /* Static description of the grid and the observation model (host pointers; copied by blg_plan_create). */
