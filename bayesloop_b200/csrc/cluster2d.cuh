@@ -137,14 +137,10 @@ __device__ __forceinline__ void c2_conv_col(uint32_t col, uint32_t pitchB, uint3
     }
 }
 
-// Address of cell i of a row under NI_EXTEND_REFLECT (valid for -n <= i; indices past 2n-1, only reached under zero
-// taps, are clamped).
-__device__ __forceinline__ uint32_t c2_reflect_addr(uint32_t row, int i, int n) {
-    i = min(i, 2 * n - 1);
-    const int lo = -1 - i, hi = 2 * n - 1 - i;
-    int r = i < 0 ? lo : i;
-    r = i >= n ? hi : r;
-    return row + 8u * (uint32_t)r;
+// Address of cell i of a row under NI_EXTEND_REFLECT, valid for -n <= i < 2n (guaranteed by R + M <= n):
+// i < 0 -> -1-i = ~i,  i >= n -> 2n-1-i,  i.e. min(max(i, ~i), 2n-1-i).
+__device__ __forceinline__ uint32_t c2_reflect_addr(uint32_t row, int i, int n2m1) {
+    return row + 8u * (uint32_t)min(max(i, ~i), n2m1 - i);
 }
 
 // M outputs of one ROW starting at cell i0 (`row`: address of cell 0), R + M <= n.
@@ -152,6 +148,7 @@ template <int M>
 __device__ __forceinline__ void c2_conv_row(uint32_t row, int i0, int n, int R, int taps, uint32_t W, double (&acc)[M]) {
     double win[M];
     int e = i0 - R;
+    n = 2 * n - 1;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
         win[m] = c2_lds(c2_reflect_addr(row, e + m, n));

@@ -181,6 +181,65 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def c3_sample(bl, eng, torch, steps=3, warmup=2, n=256, T=200, hyper=6):
+    """Secondary measurement (not the headline): a bounded sample of BASELINE.json configs[2] ("C3": Gaussian
+    256 x 256 grid, GaussianRandomWalk on both parameters) -- hyper x hyper combos spread evenly over the 64 x 64
+    hyper-grid of SURVEY.md 8d, first T time steps, full fit on the cluster-resident 2-D kernels."""
+    rng = np.random.default_rng(2)
+    mu = np.clip(np.cumsum(rng.normal(0, 0.02, T)), -2, 2)
+    sd = np.clip(1.0 + np.cumsum(rng.normal(0, 0.01, T)), 0.5, 2.0)
+    x = rng.normal(mu, sd)
+    S = bl.HyperStudy(silent=True)
+    S.loadData(x, silent=True)
+    S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, n), 'std', bl.oint(0, 3, n)),
+          bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, hyper), target='mean'),
+                                        bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, hyper), target='std')),
+          silent=True)
+    S._formatData()
+    S._createHyperGrid(silent=True)
+    sw = S._prepareSweep(False, False)
+    ms = {'forward': [], 'backward': [], 'accumulate': []}
+    names = {}
+    events = []
+    plain = eng.run
+
+    def timed(which, plan, flags, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plain(which, plan, flags, **kw)
+        e1.record()
+        names[which] = eng.last_kernel() if which != 'accumulate' else 'accumulate_kernel'
+        events.append((which, e0, e1))
+
+    eng.run = timed
+    try:
+        for _ in range(warmup):
+            S._executeSweep(sw)
+        torch.cuda.synchronize()
+        del events[:]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            res = S._executeSweep(sw)
+        b.record()
+        torch.cuda.synchronize()
+    finally:
+        eng.run = plain
+    for which, e0, e1 in events:
+        if which in ms:
+            ms[which].append(e0.elapsed_time(e1))
+    B = hyper * hyper
+    cells = float(B) * T * n * n
+    step_ms = a.elapsed_time(b) / steps
+    per = {'forward': 8.0, 'backward': 16.0, 'accumulate': 8.0}
+    kern = {names.get(k, k): {'ms': float(np.mean(v)), 'GBps': per[k] * cells / (float(np.mean(v)) * 1e-3) / 1e9}
+            for k, v in ms.items() if v}
+    return {'workload': 'C3 sample: Gaussian 2-D grid %dx%d, GRW on both parameters, %dx%d of the 64x64 hyper-grid, '
+                        'first %d time steps, full fit' % (n, n, hyper, hyper, T),
+            'value': 2.0 * cells / (step_ms * 1e-3), 'unit': 'cell-updates/s', 'ms_per_step': step_ms, 'kernels': kern,
+            'combos': B, 'log_evidence_best_combo': float(np.max(res[1]))}
+
+
 def workload_config(args, n_total):
     return {'workload': 'C2 HyperStudy: Poisson 1-D grid=%d, GaussianRandomWalk sigma sweep cint(0,%g,%d) '
                         '(%d per GPU), synthetic counts T=%d, full fit (forward+backward+averaging)'
@@ -204,6 +263,7 @@ def main():
     ap.add_argument('--combos-per-gpu', dest='combos', type=int, default=COMBOS_PER_GPU)
     ap.add_argument('--cpu-T', dest='cpu_T', type=int, default=1000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-c3', dest='no_c3', action='store_true', help='skip the secondary C3 (2-D) sample')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -242,12 +302,16 @@ def main():
     recording = {'on': False, 'events': []}
     plain_run = eng.run
 
+    kernel_names = {'accumulate': 'accumulate_kernel'}
+
     def timed_run(which, plan, flags, **kw):
         if recording['on'] and which in kernel_ms:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             plain_run(which, plan, flags, **kw)
             e1.record()
+            if which != 'accumulate':
+                kernel_names[which] = eng.last_kernel() + '_kernel'
             recording['events'].append((which, e0, e1))
         else:
             plain_run(which, plan, flags, **kw)
@@ -310,7 +374,7 @@ def main():
         # stores the posterior (16 B); the averaging pass reads every posterior once (8 B)  ->  32 B per cell for the
         # two passes = 16 B per grid-cell update (forward 8 B + backward 24 B in HyperStudy mode)
         bytes_per_cell = {'forward': 8.0, 'backward': 16.0, 'accumulate': 8.0}
-        names = {'forward': 'fwd_fast1d_kernel', 'backward': 'bwd_fast1d_kernel', 'accumulate': 'accumulate_kernel'}
+        names = {k: kernel_names.get(k, k) for k in kernel_ms}
         per_launch_cells = n_loc * T * G / max(1, waves)
         kern = {}
         for which, samples in kernel_ms.items():
@@ -339,6 +403,11 @@ def main():
             'roofline': roofline,
             'log_evidence': float(S2.logEvidence),
         }
+        if world == 1 and not args.no_c3:
+            try:
+                line['extra'] = {'c3_sample': c3_sample(bl, eng, torch)}
+            except Exception as exc:  # secondary measurement: never lose the headline line over it
+                line['extra'] = {'c3_sample': {'error': repr(exc)}}
         if world == 1 and not args.no_cpu_baseline:
             rows = list(np.unique(np.linspace(0, n_total - 1, 8).round().astype(int)))
             T_cpu = min(args.cpu_T, T)
