@@ -565,7 +565,7 @@ int launch_cluster(PassKernel kernel, const PassArgs &a, const Layout &lay, long
         char path[512];
         snprintf(path, sizeof path, "%s.%s.%d.csv", getenv("BLG_TRACE"), name, seq++);
         if (FILE *f = fopen(path, "w")) {
-            fprintf(f, "block,flush,axis0,axis1,wait_split,sweep,reduce,total,steps\n");
+            fprintf(f, "block,c0,c1,c2,c3,c4,c5,c6,c7\n");  // phase counters: see PROF in cluster2d.cuh
             for (long long i = 0; i < nblk; ++i) {
                 fprintf(f, "%lld", i);
                 for (int k = 0; k < 8; ++k) fprintf(f, ",%lld", h[8 * i + k]);
@@ -792,7 +792,7 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
         const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, true, false, a, lay);
         if (want && !getenv("BLG_FORCE_STREAM") && (uintptr_t)out->alpha_seq % 16 == 0 &&
             cluster2d_layout(pl, in->prog, flags, true, a, lay, C))
-            return launch_cluster(bwd_cluster2d_entry(), a, lay, in->B, C, st, "bwd_cluster2d");
+            return launch_cluster(bwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr), a, lay, in->B, C, st, "bwd_cluster2d");
     }
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
     if (!fits) fits = false;

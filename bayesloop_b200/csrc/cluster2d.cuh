@@ -426,16 +426,17 @@ __device__ __forceinline__ bool c2_transition(const PassArgs &a, const C2 &s, bo
     return act0 || act1;
 }
 
-// likelihood-table values of the thread's elementwise cells for time step t (issued early: consumed after two CTA
-// barriers, which hide most of the L2 latency).  Without a table the likelihood is evaluated inside the elementwise loop.
+// likelihood-table values of the first 8 of the thread's 16 elementwise cells for time step t, issued early (after
+// the arithmetic of the last convolution; consumed after two CTA barriers, which hide most of the L2 latency).  The
+// other 8 are requested at the start of the sweep and arrive while the first batch is processed (register budget).
+__device__ __forceinline__ const double *c2_lik_row(const PassArgs &a, const C2 &s, long long t) {
+    return a.lik_table + t * (long long)a.pb.G + (size_t)s.r0 * a.pb.n1;
+}
 __device__ __forceinline__ void c2_lik(const PassArgs &a, const C2 &s, long long t, double (&lk)[kC2Cells]) {
     if (a.pb.om_kind != BLG_OM_TABLE) return;
-    const double *lt = a.lik_table + t * (long long)a.pb.G + (size_t)s.r0 * a.pb.n1;
+    const double *lt = c2_lik_row(a, s, t);
 #pragma unroll
-    for (int k = 0; k < kC2Cells; ++k) {
-        const int g = threadIdx.x + k * kC2Threads;
-        lk[k] = g < s.cnt ? __ldg(lt + g) : 0.0;
-    }
+    for (int k = 0; k < 8; ++k) lk[k] = __ldg(lt + min((int)threadIdx.x + k * kC2Threads, s.cnt - 1));
 }
 
 // Elementwise sweep over the thread's cells g = tid + k * threads of the band.  Fast path (likelihood table, no
@@ -473,6 +474,40 @@ __device__ __forceinline__ void c2_sweep(const PassArgs &a, const C2 &s, const L
                 c -= n1;
                 ++r;
             }
+        }
+    }
+}
+
+// row[g] = factor * band[g] for the thread's cells, streaming stores; batches of 8 shared-memory loads in flight
+__device__ __forceinline__ void c2_flush(const C2 &s, uint32_t srcAddr, double *row, double factor) {
+    const int lastCell = s.cnt - 1;
+#pragma unroll
+    for (int k0 = 0; k0 < kC2Cells; k0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            v[k] = c2_lds(srcAddr + 8u * (uint32_t)min((int)threadIdx.x + (k0 + k) * kC2Threads, lastCell));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int g = threadIdx.x + (k0 + k) * kC2Threads;
+            if (g <= lastCell) __stcs(row + g, v[k] * factor);
+        }
+    }
+}
+
+// band[g] *= factor for the thread's cells (same cell ownership as the sweeps: no barrier needed before)
+__device__ __forceinline__ void c2_scale_inplace(const C2 &s, uint32_t addr, double factor) {
+    const int lastCell = s.cnt - 1;
+#pragma unroll
+    for (int k0 = 0; k0 < kC2Cells; k0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            v[k] = c2_lds(addr + 8u * (uint32_t)min((int)threadIdx.x + (k0 + k) * kC2Threads, lastCell));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int g = threadIdx.x + (k0 + k) * kC2Threads;
+            if (g <= lastCell) c2_sts(addr + 8u * (uint32_t)g, v[k] * factor);
         }
     }
 }
@@ -573,8 +608,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) 
                     break;
                 }
                 // alpha[t-1] = kappa * X (core.py:389, :408)
-                double *row = seq + (t - 1) * (long long)G;
-                for (int g = threadIdx.x; g < s.cnt; g += kC2Threads) __stcs(row + g, c2_Xb(a)[g] * kappa);
+                c2_flush(s, s.xbAddr, seq + (t - 1) * (long long)G, kappa);
             }
         }
         const bool trans = t > 0;
@@ -659,8 +693,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) 
         if (!takeNorm(T - 1)) {
             dead = true;
         } else if (store && !raw) {
-            double *row = seq + (T - 1) * (long long)G;
-            for (int g = threadIdx.x; g < s.cnt; g += kC2Threads) __stcs(row + g, c2_Xb(a)[g] * kappa);
+            c2_flush(s, s.xbAddr, seq + (T - 1) * (long long)G, kappa);
         }
     }
     if (likInFlight) mbar_wait(barLik, likPhase);  // a combo that died leaves with its last staging copy landed
@@ -686,7 +719,9 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) 
 // State X = beta_i * lik_i (unnormalised by one step); S = u_i = alpha_i * beta_i, the unnormalised smoothed
 // posterior of step i, which leaves for HBM (divided by its cluster-wide sum) at the beginning of the next
 // iteration and is then refilled with alpha[i-1] by one bulk-async (TMA) copy that lands during the convolutions.
-template <int NT>
+// PROF counters (a.trace[blockIdx.x * 8 + k]): 0 collect (halo rows + sums), 1 posterior flush + alpha TMA issue,
+// 2 axis-0 stage, 3 axis-1 stage + likelihood loads, 4 wait alpha + split barrier, 5 sweep, 6 publish, 7 steps
+template <int NT, bool PROF>
 __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) {
     static_assert(NT == kC2Threads, "layout constants assume kC2Threads");
     const DevProblem &pb = a.pb;
@@ -723,20 +758,25 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
     bool dead = false;
     double kb = 1.0;
     double sums[3];
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     // elementwise phase for row j: betaNew = beta0 | reset | X * scale;  u = alpha_j * betaNew -> S;  X = betaNew * lik_j
     auto elementwise = [&](int mode /*0: beta0, 1: X*scale, 2: post reset*/, double scale, long long j,
-                           const double (&lk)[kC2Cells]) {
+                           double (&lk)[kC2Cells]) {
+        const long long e0 = PROF ? clock64() : 0;
         mbar_wait(bar, phase);  // alpha[j] band has landed in S
         phase ^= 1u;
         c2_wait();  // halo rows consumed everywhere
+        const long long e1 = PROF ? clock64() : 0;
         sums[0] = sums[1] = sums[2] = 0.0;
         double x[kC2Cells], al[kC2Cells];
+        const double *ltRow = pb.om_kind == BLG_OM_TABLE ? c2_lik_row(a, s, j) : nullptr;
         c2_sweep(
             a, s, tb, j, mode == 1,
             [&](int k, int gi) {
                 x[k] = c2_lds(s.xbAddr + 8u * (uint32_t)gi);
                 al[k] = c2_lds(s.sAddr + 8u * (uint32_t)gi);
+                if (k < 8) lk[k + 8] = __ldg(ltRow + min(gi + 8 * kC2Threads, s.cnt - 1));
             },
             [&](int k, int g, bool valid) {
                 const double bn = x[k] * scale;
@@ -748,7 +788,12 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
                 }
                 sums[0] += valid ? u : 0.0;
                 sums[1] += valid ? bn : 0.0;
-                sums[2] += valid ? fast_div(u, lik) : 0.0;  // core.py:463
+                // core.py:463 post/lik without the IEEE division subroutine: the fast reciprocal flushes subnormal
+                // operands, so tiny likelihoods are rescaled by 2^600 first (exact); lik == 0 gives NaN like 0/0 does
+                // (u = 0 there: alpha carries the same likelihood factor)
+                const bool small = lik < 1e-290;
+                const double qv = u * fast_rcp(small ? lik * 0x1p600 : lik);
+                sums[2] += valid ? (small ? qv * 0x1p600 : qv) : 0.0;
             },
             [&](int g, double lik) {
                 double bn;
@@ -765,7 +810,14 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
                 sums[2] += fast_div(u, lik);
                 c2_Xb(a)[g] = bn * lik;
             });
+        const long long e2 = PROF ? clock64() : 0;
         c2_publish<3>(a, s, sums, []() {});
+        if (PROF) {
+            const long long e3 = clock64();
+            tk[4] += e1 - e0;
+            tk[5] += e2 - e1;
+            tk[6] += e3 - e2;
+        }
     };
 
     {
@@ -775,8 +827,10 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         elementwise(0, 1.0, T - 1, lk);
     }
     for (long long i = T - 1; i >= 0; --i) {
+        const long long c0 = PROF ? clock64() : 0;
         c2_collect_halo(a, s);
         c2_collect<3>(a, s, sums);
+        const long long c1 = PROF ? clock64() : 0;
         const double sab = sums[0], sbb = sums[1], q = sums[2];
         if (!(sab > 0.0) || !(sbb > 0.0)) {  // core.py:440-452
             dead = true;
@@ -785,19 +839,24 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         const double inv = fast_rcp(sab);
         kb = fast_rcp(sbb);  // core.py:470 (beta only enters scale-free expressions)
         if (lead && a.local) a.local[b * T + i] = fast_div(1.0, q * inv * pb.lc_prod);  // core.py:463
-        // F: smoothed posterior of step i (core.py:441)
-        {
-            double *row = seq + i * (long long)G;
-            for (int g = threadIdx.x; g < s.cnt; g += kC2Threads) __stcs(row + g, c2_S(a)[g] * inv);
-        }
+        // F: smoothed posterior of step i (core.py:441): normalised in place, then one bulk-async store of the band
+        c2_scale_inplace(s, s.sAddr, inv);
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) bulk_store(seq + i * (long long)G, c2_S(a), bandBytes);
         if (i == 0) break;
-        __syncthreads();  // S is free
-        if (threadIdx.x == 0) {
-            fence_proxy_async();
-            bulk_load(c2_S(a), seq + (i - 1) * (long long)G, bandBytes, bar);
-            if (pb.om_kind == BLG_OM_TABLE && i >= 2)
-                c2_prefetch_l2(a.lik_table + (i - 2) * (long long)G + (size_t)s.r0 * n1, bandBytes);
-        }
+        // alpha[i-1] is fetched into the same buffer as soon as the store has read it: issued by thread 0 after its
+        // share of the axis-0 convolution (no waiting), or right away when that stage is idle
+        bool alphaPending = true;
+        auto issueAlpha = [&]() {
+            if (alphaPending && threadIdx.x == 0) {
+                bulk_wait_read<0>();
+                bulk_load(c2_S(a), seq + (i - 1) * (long long)G, bandBytes, bar);
+                if (pb.om_kind == BLG_OM_TABLE && i >= 2)
+                    c2_prefetch_l2(a.lik_table + (i - 2) * (long long)G + (size_t)s.r0 * n1, bandBytes);
+            }
+            alphaPending = false;
+        };
         const bool post = c2_in(s.loPost, s.hiPost, i);
         const bool pre = !post && c2_in(s.loPre, s.hiPre, i);
         const bool act0 = !post && s.R0 > 0 && c2_in(s.lo0, s.hi0, i);
@@ -807,11 +866,24 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
             c2_reset_band(a, s, s.parPre);
             scale = 1.0;
         }
+        if (!act0) issueAlpha();
         double lk[kC2Cells];
-        long long cm;
-        c2_transition<false>(a, s, act0, act1, cm, []() {}, [&]() { c2_lik(a, s, i - 1, lk); });
+        const long long c2 = PROF ? clock64() : 0;
+        long long cm = c2;
+        c2_transition<PROF>(a, s, act0, act1, cm, issueAlpha, [&]() { c2_lik(a, s, i - 1, lk); });
+        if (PROF) {
+            const long long c3 = clock64();
+            tk[0] += c1 - c0;
+            tk[1] += c2 - c1;
+            tk[2] += cm - c2;
+            tk[3] += c3 - cm;
+            tk[7] += 1;
+        }
         elementwise(post ? 2 : 1, scale, i - 1, lk);
     }
+    if (threadIdx.x == 0) bulk_wait_all();
+    if (PROF && a.trace && threadIdx.x == 0)
+        for (int k = 0; k < 8; ++k) a.trace[(long long)blockIdx.x * 8 + k] = tk[k];
     if (dead && lead) {
         a.logE[b] = -INFINITY;
         if (a.alive) a.alive[b] = -1;

@@ -5,7 +5,7 @@
 namespace blg {
 
 #if BLG_INST_BWD
-PassKernel bwd_cluster2d_entry() { return bwd_cluster2d_kernel<kC2Threads>; }
+PassKernel bwd_cluster2d_entry(bool prof) { return prof ? bwd_cluster2d_kernel<kC2Threads, true> : bwd_cluster2d_kernel<kC2Threads, false>; }
 #else
 PassKernel fwd_cluster2d_entry(bool prof) { return prof ? fwd_cluster2d_kernel<kC2Threads, true> : fwd_cluster2d_kernel<kC2Threads, false>; }
 void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad) {

@@ -31,7 +31,7 @@ bool stream2d_supports(int n_ops, const int *kind, const int *axis);
 
 // cluster-resident 2-D kernels (cluster2d.cuh): 512 threads, one cluster of 2/4/8 CTAs per combo
 PassKernel fwd_cluster2d_entry(bool prof = false);  // prof: per-phase cycle counters into PassArgs::trace
-PassKernel bwd_cluster2d_entry();
+PassKernel bwd_cluster2d_entry(bool prof = false);
 // layout parameters of cluster2d.cuh: threads, rows per axis-0 item, cells per axis-1 item, cells per thread
 void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad);
 
