@@ -106,6 +106,17 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at this workload, from the committed
+    `ncu --set full` capture (profiles/r1_ncu_summary.json); None if the capture does not cover it."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_ncu_summary.json')) as f:
+            entry = json.load(f)['bench_c2'][kernel]
+        return float(entry['dram_bytes_read']) + float(entry['dram_bytes_write'])
+    except Exception:
+        return None
+
+
 def hbm_peak():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -149,7 +160,7 @@ def run_reference(args, rank, world):
     workers = min(cores, 64)
     n_total = COMBOS_PER_GPU * args.gpus
     T_cpu = min(args.cpu_T, args.T)
-    per_worker = 2
+    per_worker = 4
     rows_all = np.unique(np.linspace(0, n_total - 1, workers * per_worker).round().astype(int))
     chunks = [list(c) for c in np.array_split(rows_all, workers) if len(c)]
     counts = synthetic_counts(args.T)
@@ -261,7 +272,7 @@ def main():
     ap.add_argument('--grid', type=int, default=GRID)
     ap.add_argument('--sigma-max', dest='sigma_max', type=float, default=SIGMA_MAX)
     ap.add_argument('--combos-per-gpu', dest='combos', type=int, default=COMBOS_PER_GPU)
-    ap.add_argument('--cpu-T', dest='cpu_T', type=int, default=1000)
+    ap.add_argument('--cpu-T', dest='cpu_T', type=int, default=4000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-c3', dest='no_c3', action='store_true', help='skip the secondary C3 (2-D) sample')
     args = ap.parse_args()
@@ -386,7 +397,7 @@ def main():
         total_kernel_ms = sum(v['ms'] for v in kern.values()) * waves
         sweep_gbs = 32.0 * n_loc * T * G / (total_kernel_ms * 1e-3) / 1e9
         roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': kern[dominant]['GBps'], 'peak': peak, 'unit': 'GB/s',
-                    'frac': kern[dominant]['frac'], 'traffic': None, 'peak_source': peak_src,
+                    'frac': kern[dominant]['frac'], 'traffic': ncu_traffic(dominant), 'peak_source': peak_src,
                     'kernels': kern, 'all_kernels_GBps': sweep_gbs, 'all_kernels_frac': sweep_gbs / peak,
                     'kernel_share_of_step': total_kernel_ms / dev_ms,
                     'note': 'reference-like sigma sweep (kernel radius <= 67): the convolution makes the passes FP64-FMA '
@@ -409,7 +420,7 @@ def main():
             except Exception as exc:  # secondary measurement: never lose the headline line over it
                 line['extra'] = {'c3_sample': {'error': repr(exc)}}
         if world == 1 and not args.no_cpu_baseline:
-            rows = list(np.unique(np.linspace(0, n_total - 1, 8).round().astype(int)))
+            rows = list(np.unique(np.linspace(0, n_total - 1, 24).round().astype(int)))
             T_cpu = min(args.cpu_T, T)
             upd, sec = cpu_port_sample(counts, G, args.sigma_max, n_total, rows, T_cpu)
             line['cpu_baseline'] = {'value': upd / sec, 'unit': 'cell-updates/s', 'cores': 1, 'kind': 'port',
