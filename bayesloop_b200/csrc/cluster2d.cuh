@@ -375,9 +375,9 @@ __device__ __forceinline__ void c2_reset_band(const PassArgs &a, const C2 &s, do
 // the last convolution (early issue of loads consumed by the elementwise phase).  Returns with all threads
 // synchronised on the new band; the split cluster barrier "halo rows consumed" has been ARRIVED at (the caller
 // waits before it pushes).  Returns true if the band was overwritten (beforeWrite has run).
-template <bool TIMED, typename BeforeWrite, typename AfterConv>
+template <bool TIMED, typename BeforeWrite, typename AfterConv, typename AfterWrite>
 __device__ __forceinline__ bool c2_transition(const PassArgs &a, const C2 &s, bool act0, bool act1, long long &tmid,
-                                              BeforeWrite beforeWrite, AfterConv afterConv) {
+                                              BeforeWrite beforeWrite, AfterConv afterConv, AfterWrite afterWrite) {
     const int n1 = a.pb.n1;
     const uint32_t rowB = (uint32_t)n1 * 8u;
     if (act0) {
@@ -419,24 +419,27 @@ __device__ __forceinline__ bool c2_transition(const PassArgs &a, const C2 &s, bo
             for (int m = 0; m < kC2M1; ++m)
                 if (i0 + m < n1) c2_sts(out + 8u * (uint32_t)m, acc[m]);
         }
+        afterWrite();  // the accumulators are dead: room for the second batch of early loads
         __syncthreads();
     } else {
         afterConv();
+        afterWrite();
     }
     return act0 || act1;
 }
 
-// likelihood-table values of the first 8 of the thread's 16 elementwise cells for time step t, issued early (after
-// the arithmetic of the last convolution; consumed after two CTA barriers, which hide most of the L2 latency).  The
-// other 8 are requested at the start of the sweep and arrive while the first batch is processed (register budget).
+// likelihood-table values of the thread's 16 elementwise cells for time step t, issued early in two halves of 8
+// (register budget): cells 0-7 after the arithmetic of the last convolution, cells 8-15 after its write-back, when
+// the accumulators are dead; both are consumed after the following CTA barrier(s), which hide the L2 latency.
 __device__ __forceinline__ const double *c2_lik_row(const PassArgs &a, const C2 &s, long long t) {
     return a.lik_table + t * (long long)a.pb.G + (size_t)s.r0 * a.pb.n1;
 }
+template <int K0>
 __device__ __forceinline__ void c2_lik(const PassArgs &a, const C2 &s, long long t, double (&lk)[kC2Cells]) {
     if (a.pb.om_kind != BLG_OM_TABLE) return;
     const double *lt = c2_lik_row(a, s, t);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) lk[k] = __ldg(lt + min((int)threadIdx.x + k * kC2Threads, s.cnt - 1));
+    for (int k = K0; k < K0 + 8; ++k) lk[k] = __ldg(lt + min((int)threadIdx.x + k * kC2Threads, s.cnt - 1));
 }
 
 // Elementwise sweep over the thread's cells g = tid + k * threads of the band.  Fast path (likelihood table, no
@@ -628,7 +631,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) 
         }
         const long long c1 = PROF ? clock64() : 0;
         long long cm = c1;
-        const bool wrote = c2_transition<PROF>(a, s, act0, act1, cm, drainStore, []() {});
+        const bool wrote = c2_transition<PROF>(a, s, act0, act1, cm, drainStore, []() {}, []() {});
         if (!wrote && pendingStore) {
             drainStore();
             __syncthreads();
@@ -770,13 +773,11 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         const long long e1 = PROF ? clock64() : 0;
         sums[0] = sums[1] = sums[2] = 0.0;
         double x[kC2Cells], al[kC2Cells];
-        const double *ltRow = pb.om_kind == BLG_OM_TABLE ? c2_lik_row(a, s, j) : nullptr;
         c2_sweep(
             a, s, tb, j, mode == 1,
             [&](int k, int gi) {
                 x[k] = c2_lds(s.xbAddr + 8u * (uint32_t)gi);
                 al[k] = c2_lds(s.sAddr + 8u * (uint32_t)gi);
-                if (k < 8) lk[k + 8] = __ldg(ltRow + min(gi + 8 * kC2Threads, s.cnt - 1));
             },
             [&](int k, int g, bool valid) {
                 const double bn = x[k] * scale;
@@ -822,7 +823,8 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
 
     {
         double lk[kC2Cells];
-        c2_lik(a, s, T - 1, lk);
+        c2_lik<0>(a, s, T - 1, lk);
+        c2_lik<8>(a, s, T - 1, lk);
         c2_arrive_relaxed();  // pairs with the wait inside elementwise()
         elementwise(0, 1.0, T - 1, lk);
     }
@@ -870,7 +872,8 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         double lk[kC2Cells];
         const long long c2 = PROF ? clock64() : 0;
         long long cm = c2;
-        c2_transition<PROF>(a, s, act0, act1, cm, issueAlpha, [&]() { c2_lik(a, s, i - 1, lk); });
+        c2_transition<PROF>(a, s, act0, act1, cm, issueAlpha, [&]() { c2_lik<0>(a, s, i - 1, lk); },
+                            [&]() { c2_lik<8>(a, s, i - 1, lk); });
         if (PROF) {
             const long long c3 = clock64();
             tk[0] += c1 - c0;

@@ -396,10 +396,24 @@ def main():
         dominant = max(kern, key=lambda k: kern[k]['ms'])
         total_kernel_ms = sum(v['ms'] for v in kern.values()) * waves
         sweep_gbs = 32.0 * n_loc * T * G / (total_kernel_ms * 1e-3) / 1e9
+        # the binding unit of this workload is the FP64 pipe (convolution taps), reported next to the HBM roofline:
+        # DFMA per pass = T * G * sum over combos of (2 R_b + 1), R_b = int(4 sigma_b / lattice + 0.5)
+        sig = np.asarray(bl.cint(0, args.sigma_max, n_total), dtype=float)[:n_loc]
+        lattice = 12.0 / (G + 1)
+        radius = np.where(sig > 0, np.floor(4.0 * sig / lattice + 0.5), 0.0)
+        taps = np.where(radius > 0, 2.0 * radius + 1.0, 0.0)
+        flop_pass = 2.0 * T * G * float(taps.sum())
+        fp64_peak = 58.5 * 148 * 1.965e9 * 2 / 1e12  # tools/micro/dfma_bench.cu on B200: 58.5 FMA lanes/clk/SM
+        fp64 = {'peak_tflops': fp64_peak, 'peak_source': 'measured: tools/micro/dfma_bench.cu (58.5 DFMA lanes/clk/SM x 148 '
+                                                         'SMs x 1.965 GHz)',
+                'convolution_flop_per_pass': flop_pass, 'mean_taps': float(taps.mean()),
+                'kernels': {name: {'tflops': flop_pass / (v['ms'] * 1e-3) / 1e12,
+                                   'frac': flop_pass / (v['ms'] * 1e-3) / 1e12 / fp64_peak}
+                            for name, v in kern.items() if 'accumulate' not in name}}
         roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': kern[dominant]['GBps'], 'peak': peak, 'unit': 'GB/s',
                     'frac': kern[dominant]['frac'], 'traffic': ncu_traffic(dominant), 'peak_source': peak_src,
                     'kernels': kern, 'all_kernels_GBps': sweep_gbs, 'all_kernels_frac': sweep_gbs / peak,
-                    'kernel_share_of_step': total_kernel_ms / dev_ms,
+                    'kernel_share_of_step': total_kernel_ms / dev_ms, 'fp64': fp64,
                     'note': 'reference-like sigma sweep (kernel radius <= 67): the convolution makes the passes FP64-FMA '
                             'bound, not HBM bound (SURVEY.md 8d); see profiles/ for the FP64 pipe utilisation'}
         line = {

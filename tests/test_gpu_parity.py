@@ -221,3 +221,33 @@ def test_cluster2d_agrees_with_stream_kernels_at_c3_size(cuda_engine, monkeypatc
     rowmax = want['avg'].max(axis=1, keepdims=True)
     assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-7 * np.abs(want['avg']) + 1e-13 * rowmax)
     np.testing.assert_allclose(got['avg'].sum(axis=1), 1.0, rtol=1e-12)
+
+
+def test_cluster2d_agrees_with_stream_kernels_at_c4_size(cuda_engine, monkeypatch):
+    """200 x 200 with a change-point sweep in front of the two random walks (BASELINE.json configs[3] in miniature):
+    cluster-resident kernels (8 CTAs x 25 rows, reset inside the kernel) against the stream kernels."""
+    import bayesloop_b200 as bl
+
+    def study():
+        rng = np.random.default_rng(3)
+        T = 40
+        x = np.concatenate([rng.normal(-0.5, 1.0, T // 2), rng.normal(1.0, 1.0, T - T // 2)])
+        S = bl.HyperStudy(silent=True, engine=cuda_engine)
+        S.loadData(x, silent=True)
+        S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, 200), 'std', bl.oint(0, 3, 200)),
+              bl.tm.CombinedTransitionModel(bl.tm.ChangePoint('tChange', [5, 20, 33]),
+                                            bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, 2), target='mean'),
+                                            bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, 2), target='std')),
+              silent=True)
+        return S
+
+    got = helpers.abi_sweep(cuda_engine, study())
+    assert cuda_engine.last_kernel() == 'bwd_cluster2d'
+    monkeypatch.setenv('BLG_NO_CLUSTER2D', '1')
+    want = helpers.abi_sweep(cuda_engine, study())
+    assert cuda_engine.last_kernel() == 'bwd_stream'
+    np.testing.assert_array_equal(got['alive'], want['alive'])
+    np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-11)
+    rowmax = want['avg'].max(axis=1, keepdims=True)
+    assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-7 * np.abs(want['avg']) + 1e-13 * rowmax)
+    np.testing.assert_allclose(got['means'], want['means'], rtol=1e-9)
