@@ -251,3 +251,30 @@ def test_cluster2d_agrees_with_stream_kernels_at_c4_size(cuda_engine, monkeypatc
     rowmax = want['avg'].max(axis=1, keepdims=True)
     assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-7 * np.abs(want['avg']) + 1e-13 * rowmax)
     np.testing.assert_allclose(got['means'], want['means'], rtol=1e-9)
+
+
+def test_cluster2d_dead_combos_match_oracle(cuda_engine, oracle_engine, monkeypatch):
+    """A data point that underflows the likelihood of every cell kills the forward pass of every combo at that step
+    (core.py:388-400): the cluster kernels must agree on `alive` and -inf evidences, and all CTAs of a cluster must
+    leave together (no hang)."""
+    import bayesloop_b200 as bl
+    monkeypatch.setenv('BLG_CLUSTER2D', '1')
+
+    def study(engine):
+        rng = np.random.default_rng(11)
+        x = rng.normal(0.0, 1.0, 30)
+        x[17] = 1e6
+        S = bl.HyperStudy(silent=True, engine=engine)
+        S.loadData(x, silent=True)
+        S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, 64), 'std', bl.oint(0, 3, 48)),
+              bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.3, 3), target='mean'),
+                                            bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.2, 2), target='std')),
+              silent=True)
+        return S
+
+    got = helpers.abi_sweep(cuda_engine, study(cuda_engine))
+    assert cuda_engine.last_kernel().endswith('cluster2d')
+    want = helpers.abi_sweep(oracle_engine, study(oracle_engine))
+    np.testing.assert_array_equal(got['alive'], want['alive'])
+    assert np.all(got['alive'] != 1)
+    np.testing.assert_array_equal(np.isneginf(got['logE']), np.isneginf(want['logE']))
