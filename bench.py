@@ -275,6 +275,7 @@ def main():
     ap.add_argument('--cpu-T', dest='cpu_T', type=int, default=4000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-c3', dest='no_c3', action='store_true', help='skip the secondary C3 (2-D) sample')
+    ap.add_argument('--no-narrow', dest='no_narrow', action='store_true', help='skip the secondary narrow C2 sweep')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -428,11 +429,56 @@ def main():
             'roofline': roofline,
             'log_evidence': float(S2.logEvidence),
         }
+        if world == 1 and not args.no_c3 and not args.no_narrow:
+            # secondary: the narrow sweep of SURVEY.md 8d (sigma <= 0.05, radius <= 17): the regime where the passes
+            # move towards the HBM roofline (fewer taps per stored byte); device-resident, same shape otherwise
+            try:
+                Sn = build_study(bl, counts, n_total, G, 0.05)
+                Sn._formatData()
+                Sn._createHyperGrid(silent=True)
+                swn = Sn._prepareSweep(False, False)
+                kernel_ms_n = {'forward': [], 'backward': [], 'accumulate': []}
+                evs = []
+
+                def timed_n(which, plan, flags, **kw):
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    plain_run(which, plan, flags, **kw)
+                    a1.record()
+                    evs.append((which, a0, a1))
+
+                eng.run = timed_n
+                for _ in range(2):
+                    Sn._executeSweep(swn)
+                del evs[:]
+                n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n0.record()
+                for _ in range(3):
+                    Sn._executeSweep(swn)
+                n1.record()
+                torch.cuda.synchronize()
+                eng.run = timed_run
+                for which, a0, a1 in evs:
+                    if which in kernel_ms_n:
+                        kernel_ms_n[which].append(a0.elapsed_time(a1))
+                ms_n = n0.elapsed_time(n1) / 3
+                cells = float(n_loc) * T * G
+                line.setdefault('extra', {})['c2_narrow'] = {
+                    'workload': 'C2 with the narrow sweep cint(0,0.05,%d): kernel radius <= 17' % n_total,
+                    'value': 2.0 * cells / (ms_n * 1e-3), 'unit': 'cell-updates/s', 'ms_per_step': ms_n,
+                    'kernels': {k: {'ms': float(np.mean(v)),
+                                    'hbm_frac': bytes_per_cell[k] * cells / (float(np.mean(v)) * 1e-3) / 1e9 / peak}
+                                for k, v in kernel_ms_n.items() if v}}
+                del swn, Sn
+                torch.cuda.empty_cache()
+            except Exception as exc:
+                eng.run = timed_run
+                line.setdefault('extra', {})['c2_narrow'] = {'error': repr(exc)}
         if world == 1 and not args.no_c3:
             try:
-                line['extra'] = {'c3_sample': c3_sample(bl, eng, torch)}
+                line.setdefault('extra', {})['c3_sample'] = c3_sample(bl, eng, torch)
             except Exception as exc:  # secondary measurement: never lose the headline line over it
-                line['extra'] = {'c3_sample': {'error': repr(exc)}}
+                line.setdefault('extra', {})['c3_sample'] = {'error': repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             rows = list(np.unique(np.linspace(0, n_total - 1, 24).round().astype(int)))
             T_cpu = min(args.cpu_T, T)
