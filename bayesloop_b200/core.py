@@ -391,8 +391,11 @@ class Study(object):
         fwdFlags = _engine.F_EVIDENCE_ONLY if evidenceOnly else (0 if forwardOnly else _engine.F_RAW_ALPHA)
         eng.run('forward', ses.plan, fwdFlags, **common)
         state = int(eng.to_host(alive)[0])
+        rawRows = False
         if state == 1 and not (forwardOnly or evidenceOnly):
-            eng.run('backward', ses.plan, 0, **common)
+            # smoothed rows may come back unnormalised (+ their scale): finalize normalises them below
+            eng.run('backward', ses.plan, _engine.F_RAW_POSTERIOR, row_scale=eng.empty((1, T)), **common)
+            rawRows = True
             state = int(eng.to_host(alive)[0])
         self.localEvidence = eng.to_host(local)[0]
         self.logEvidence = float(eng.to_host(logE)[0])
@@ -409,7 +412,7 @@ class Study(object):
             self.posteriorMeanValues = []
             return
         means = eng.empty((len(self.gridSize), T))
-        eng.finalize(ses.plan, seq, T, means, 0)
+        eng.finalize(ses.plan, seq, T, means, _engine.F_NORMALIZE_ROWS if rawRows else 0)
         self.posteriorSequence = eng.to_host(seq).reshape([T] + self.gridSize)
         self.posteriorMeanValues = eng.to_host(means)
         if not silent:
@@ -635,13 +638,14 @@ class HyperStudy(Study):
         sw['hpDev'] = eng.to_device(hp) if B > 0 else None
         sw['part'] = eng.zeros(T)
         if evidenceOnly:
-            sw['wave'], sw['buf'], sw['avg'], sw['means'] = max(B, 1), None, None, None
+            sw['wave'], sw['buf'], sw['avg'], sw['means'], sw['rowScale'] = max(B, 1), None, None, None, None
         else:
             sw['avg'] = eng.zeros((T, G))
             sw['means'] = eng.empty((len(self.gridSize), T))
             budget = int(eng.free_bytes() * 0.85) - T * G * 8
             sw['wave'] = int(max(1, min(B, budget // max(1, T * G * 8))))
             sw['buf'] = eng.empty((sw['wave'], T, G)) if B > 0 else None
+            sw['rowScale'] = eng.empty((sw['wave'], T)) if (B > 0 and not forwardOnly) else None
         with np.errstate(divide='ignore'):
             sw['logHp'] = np.log(hp)
         return sw
@@ -682,10 +686,12 @@ class HyperStudy(Study):
             if not forwardOnly:
                 # smoothed posteriors overwrite the stored sequences in place; combos whose backward pass hits a
                 # zero norm flag themselves (alive = -1) and are dropped from the average as a whole (core.py:1358)
-                eng.run('backward', ses.plan, 0, **common)
+                # (rows may come back unnormalised with their scale in rowScale, applied by the accumulation)
+                eng.run('backward', ses.plan, _engine.F_RAW_POSTERIOR, row_scale=sw['rowScale'], **common)
             weights = eng.to_device(np.where(finite, lw - (shift if np.isfinite(shift) else 0.), -np.inf))
             # evidence-weighted sum over the combos of this wave, fixed summation order (deterministic)
-            eng.run('accumulate', ses.plan, 0, log_weight=weights, avg=avg, **common)
+            eng.run('accumulate', ses.plan, 0, log_weight=weights, avg=avg,
+                    row_scale=None if forwardOnly else sw['rowScale'], **common)
         aliveHost = eng.to_host(alive)[:B]
         logEHost = np.where(aliveHost == 1, logEHost, -np.inf)
         # averaged local evidence: sum_b localEvidence_b * hyperprior_b (core.py:1410)

@@ -58,6 +58,7 @@ struct blg_plan {
     int *d_sm_state;  // per-SM arrival counters + per-combo claim flags (fast 1-D kernels with sm_assign)
     long long sm_state_cap;
     int serpentine;
+    bool rows_raw;  // the last backward pass left its rows unnormalised (row_scale holds the factors)
 };
 
 extern "C" {
@@ -193,6 +194,7 @@ int blg_plan_create(const blg_problem *p, blg_plan **out) {
     pl->lik_cap = 0;
     pl->d_sm_state = nullptr;
     pl->sm_state_cap = 0;
+    pl->rows_raw = false;
     *out = pl;
     return 0;
 }
@@ -683,6 +685,7 @@ int fill_args(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32
     a.alpha_seq = out->alpha_seq;
     a.avg = out->avg;
     a.final_state = out->final_state;
+    a.row_scale = (flags & BLG_F_RAW_POSTERIOR) ? out->row_scale : nullptr;
     a.steps = pl->d_steps;
     a.flags = flags;
     a.num_sms = pl->num_sms;
@@ -706,6 +709,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     if ((flags & BLG_F_SAVE_STATE) && !out->final_state) return fail("final_state missing");
     PassArgs a;
     memset(&a, 0, sizeof a);
+    pl->rows_raw = false;
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
     Layout lay;
@@ -762,6 +766,15 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     memset(&a, 0, sizeof a);
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
+    pl->rows_raw = false;
+    if (flags & BLG_F_RAW_POSTERIOR) {  // kernels that normalise their rows leave the factor at 1
+        if (!out->row_scale) return fail("row_scale required with RAW_POSTERIOR");
+        if (acc) return fail("RAW_POSTERIOR and ACCUMULATE exclude each other");
+        const long long n = in->B * in->T;
+        fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out->row_scale, n, 1.0);
+        ++g_launches;
+        CUDA_TRY(cudaGetLastError());
+    }
     Layout lay;
     const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
     {
@@ -791,8 +804,10 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
         int C = 0;
         const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, true, false, a, lay);
         if (want && !getenv("BLG_FORCE_STREAM") && (uintptr_t)out->alpha_seq % 16 == 0 &&
-            cluster2d_layout(pl, in->prog, flags, true, a, lay, C))
+            cluster2d_layout(pl, in->prog, flags, true, a, lay, C)) {
+            pl->rows_raw = a.row_scale != nullptr;
             return launch_cluster(bwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr), a, lay, in->B, C, st, "bwd_cluster2d");
+        }
     }
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
     if (!fits) fits = false;
@@ -816,7 +831,13 @@ int blg_accumulate(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, u
     const int nt = 256;
     weights_kernel<<<(unsigned)((in->B + nt - 1) / nt), nt, 0, st>>>(in->log_weight, out->alive, in->B, pl->d_w);
     const long long count = in->T * (long long)pl->dev.G;
-    accumulate_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(out->alpha_seq, pl->d_w, in->B, count, out->avg);
+    const unsigned blocks = (unsigned)((count + nt - 1) / nt);
+    if (pl->rows_raw && out->row_scale)
+        accumulate_kernel<true><<<blocks, nt, 0, st>>>(out->alpha_seq, pl->d_w, in->B, count, out->avg, out->row_scale, in->T,
+                                                       pl->dev.G);
+    else
+        accumulate_kernel<false><<<blocks, nt, 0, st>>>(out->alpha_seq, pl->d_w, in->B, count, out->avg, nullptr, in->T,
+                                                        pl->dev.G);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());
     return 0;

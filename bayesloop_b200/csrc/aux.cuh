@@ -108,11 +108,15 @@ __global__ void weights_kernel(const double *__restrict__ logw, const int *__res
     if (b < B) w[b] = (!alive || alive[b] == 1) ? exp(logw[b]) : 0.0;
 }
 
-// avg[e] += sum_b w[b] * max(seq[b][e], 1e-300)   (core.py:1362-1366 applied to stored sequences)
+// avg[e] += sum_b w[b] * max(scale[b][t] * seq[b][e], 1e-300)   (core.py:1362-1366 applied to stored sequences;
+// scale = NULL: rows are normalised already; otherwise the per-row factor left by a BLG_F_RAW_POSTERIOR backward pass)
+template <bool SCALED>
 __global__ void accumulate_kernel(const double *__restrict__ seq, const double *__restrict__ w, long long B,
-                                  long long count, double *__restrict__ avg) {
+                                  long long count, double *__restrict__ avg, const double *__restrict__ scale, long long T,
+                                  int G) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count) return;
+    const long long t = SCALED ? e / G : 0;
     double s = 0.0;
     long long b = 0;
     for (; b + 8 <= B; b += 8) {  // 8 independent streaming loads in flight per thread
@@ -122,15 +126,22 @@ __global__ void accumulate_kernel(const double *__restrict__ seq, const double *
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const double wb = __ldg(w + b + u);
-            if (wb > 0.0) s = fma(wb, v[u] < kTiny ? kTiny : v[u], s);  // wb == 0: combo not alive (rows may hold NaN)
+            const double p = SCALED ? v[u] * __ldg(scale + (b + u) * T + t) : v[u];
+            if (wb > 0.0) s = fma(wb, p < kTiny ? kTiny : p, s);  // wb == 0: combo not alive (rows may hold NaN)
         }
     }
     for (; b < B; ++b) {
         const double wb = __ldg(w + b);
         const double v = __ldcs(seq + b * count + e);
-        if (wb > 0.0) s = fma(wb, v < kTiny ? kTiny : v, s);
+        const double p = SCALED ? v * __ldg(scale + b * T + t) : v;
+        if (wb > 0.0) s = fma(wb, p < kTiny ? kTiny : p, s);
     }
     avg[e] += s;
+}
+
+__global__ void fill_kernel(double *__restrict__ x, long long count, double value) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < count) x[e] = value;
 }
 
 // One CTA per row t: optional normalisation by the row sum (core.py:1379-1382) and posterior means

@@ -286,11 +286,26 @@ __device__ __forceinline__ void c2_publish(const PassArgs &a, C2 &s, double (&v)
         if (lane == 0) wpart[k * 16 + warp] = t;
     }
     __syncthreads();
-    afterSync();
     const uint32_t barLocal = smem_u32(c2_halo_bar(a, par)), sumLocal = smem_u32(c2_sum_bar(a, par));
     if (threadIdx.x == 0) {
         c2_expect_tx(c2_sum_bar(a, par), (uint32_t)(s.C * K * sizeof(double)));
         if (s.R0 > 0) c2_expect_tx(c2_halo_bar(a, par), (uint32_t)(2 * s.R0 * a.pb.n1 * sizeof(double)));
+    }
+    afterSync();
+    // the partial sums first (their all-to-all is the longer chain), from the last warp: warp 0 issues the TMA copies
+    if (warp == kC2Threads / 32 - 1 && lane < s.C) {
+        double *slots = c2_misc(a) + kC2Slots + par * 3 * kC2MaxCluster;
+        const uint32_t rbar = c2_map(sumLocal, (unsigned)lane);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int w = 0; w < kC2Threads / 32; w += 2) {
+                t0 += wpart[k * 16 + w];
+                t1 += wpart[k * 16 + w + 1];
+            }
+            c2_st_async(c2_map(smem_u32(&slots[k * kC2MaxCluster + s.rank]), (unsigned)lane), t0 + t1, rbar);
+        }
     }
     if (s.R0 > 0) {
         const int n1 = a.pb.n1, pairs = s.R0 * n1 / 2;
@@ -315,16 +330,6 @@ __device__ __forceinline__ void c2_publish(const PassArgs &a, C2 &s, double (&v)
             const uint32_t dDn = bottom ? (uint32_t)(a.c2_h0 + s.nb + s.R0 - 1 - k) * rowB + cB
                                         : (uint32_t)(a.c2_h0 - s.R0) * rowB + 16u * (uint32_t)e;
             c2_st_async2(dnX + dDn, a1, dnBar);
-        }
-    }
-    if ((int)threadIdx.x < s.C) {
-        double *slots = c2_misc(a) + kC2Slots + par * 3 * kC2MaxCluster;
-        const uint32_t rbar = c2_map(sumLocal, (unsigned)threadIdx.x);
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double tot = 0.0;
-            for (int w = 0; w < kC2Threads / 32; ++w) tot += wpart[k * 16 + w];
-            c2_st_async(c2_map(smem_u32(&slots[k * kC2MaxCluster + s.rank]), (unsigned)threadIdx.x), tot, rbar);
         }
     }
     s.bits ^= 1u;
@@ -759,17 +764,37 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
     const double *rb = a.reset_base;
     const double beta0 = 1.0 / (double)G;  // core.py:424-425
     bool dead = false;
-    double kb = 1.0;
+    double kb = 1.0, inv = 1.0;
     double sums[3];
     long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     // elementwise phase for row j: betaNew = beta0 | reset | X * scale;  u = alpha_j * betaNew -> S;  X = betaNew * lik_j
-    auto elementwise = [&](int mode /*0: beta0, 1: X*scale, 2: post reset*/, double scale, long long j,
-                           double (&lk)[kC2Cells]) {
+    // raw mode (BLG_F_RAW_POSTERIOR): the unnormalised row u_i leaves by a bulk store right after the sweep that made
+    // it and its factor 1/sum(u_i) goes to row_scale; the sums are then only needed by the NEXT sweep, so their
+    // all-to-all hides behind the convolutions (like the evidence increment of the forward pass)
+    const bool raw = a.row_scale != nullptr;
+    // sums of row `row`: normalisers, local evidence, row scale; false = zero norm (core.py:440-452)
+    auto takeSums = [&](long long row) -> bool {
+        c2_collect<3>(a, s, sums);
+        const double sab = sums[0], sbb = sums[1], q = sums[2];
+        if (!(sab > 0.0) || !(sbb > 0.0)) return false;
+        inv = fast_rcp(sab);  // posterior = alpha*beta / sum(alpha*beta)  core.py:436-441
+        kb = fast_rcp(sbb);   // core.py:470 (beta only enters scale-free expressions)
+        if (lead) {
+            if (a.local) a.local[b * T + row] = fast_div(1.0, q * inv * pb.lc_prod);  // core.py:463
+            if (raw) a.row_scale[b * T + row] = inv;
+        }
+        return true;
+    };
+    // elementwise phase for row j; lateRow >= 0: first collect the sums of that (previous) row
+    auto elementwise = [&](int mode /*0: beta0, 1: X*scale, 2: post reset*/, bool unitScale, long long j,
+                           double (&lk)[kC2Cells], long long lateRow) -> bool {
         const long long e0 = PROF ? clock64() : 0;
         mbar_wait(bar, phase);  // alpha[j] band has landed in S
         phase ^= 1u;
         c2_wait();  // halo rows consumed everywhere
+        if (lateRow >= 0 && !takeSums(lateRow)) return false;
+        const double scale = unitScale ? 1.0 : kb;
         const long long e1 = PROF ? clock64() : 0;
         sums[0] = sums[1] = sums[2] = 0.0;
         double x[kC2Cells], al[kC2Cells];
@@ -811,14 +836,18 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
                 sums[2] += fast_div(u, lik);
                 c2_Xb(a)[g] = bn * lik;
             });
+        if (raw) fence_proxy_async();  // S is read by the bulk-async store below
         const long long e2 = PROF ? clock64() : 0;
-        c2_publish<3>(a, s, sums, []() {});
+        c2_publish<3>(a, s, sums, [&]() {
+            if (raw && threadIdx.x == 0) bulk_store(seq + j * (long long)G, c2_S(a), bandBytes);
+        });
         if (PROF) {
             const long long e3 = clock64();
             tk[4] += e1 - e0;
             tk[5] += e2 - e1;
             tk[6] += e3 - e2;
         }
+        return true;
     };
 
     {
@@ -826,27 +855,27 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         c2_lik<0>(a, s, T - 1, lk);
         c2_lik<8>(a, s, T - 1, lk);
         c2_arrive_relaxed();  // pairs with the wait inside elementwise()
-        elementwise(0, 1.0, T - 1, lk);
+        elementwise(0, true, T - 1, lk, -1);
     }
     for (long long i = T - 1; i >= 0; --i) {
         const long long c0 = PROF ? clock64() : 0;
         c2_collect_halo(a, s);
-        c2_collect<3>(a, s, sums);
+        if (!raw) {
+            if (!takeSums(i)) {
+                dead = true;
+                break;
+            }
+            // smoothed posterior of step i (core.py:441): normalised in place, then one bulk-async store of the band
+            c2_scale_inplace(s, s.sAddr, inv);
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0) bulk_store(seq + i * (long long)G, c2_S(a), bandBytes);
+        }
         const long long c1 = PROF ? clock64() : 0;
-        const double sab = sums[0], sbb = sums[1], q = sums[2];
-        if (!(sab > 0.0) || !(sbb > 0.0)) {  // core.py:440-452
-            dead = true;
+        if (i == 0) {
+            if (raw && !takeSums(0)) dead = true;
             break;
         }
-        const double inv = fast_rcp(sab);
-        kb = fast_rcp(sbb);  // core.py:470 (beta only enters scale-free expressions)
-        if (lead && a.local) a.local[b * T + i] = fast_div(1.0, q * inv * pb.lc_prod);  // core.py:463
-        // F: smoothed posterior of step i (core.py:441): normalised in place, then one bulk-async store of the band
-        c2_scale_inplace(s, s.sAddr, inv);
-        fence_proxy_async();
-        __syncthreads();
-        if (threadIdx.x == 0) bulk_store(seq + i * (long long)G, c2_S(a), bandBytes);
-        if (i == 0) break;
         // alpha[i-1] is fetched into the same buffer as soon as the store has read it: issued by thread 0 after its
         // share of the axis-0 convolution (no waiting), or right away when that stage is idle
         bool alphaPending = true;
@@ -863,11 +892,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         const bool pre = !post && c2_in(s.loPre, s.hiPre, i);
         const bool act0 = !post && s.R0 > 0 && c2_in(s.lo0, s.hi0, i);
         const bool act1 = !post && s.R1 > 0 && c2_in(s.lo1, s.hi1, i);
-        double scale = kb;
-        if (pre) {
-            c2_reset_band(a, s, s.parPre);
-            scale = 1.0;
-        }
+        if (pre) c2_reset_band(a, s, s.parPre);
         if (!act0) issueAlpha();
         double lk[kC2Cells];
         const long long c2 = PROF ? clock64() : 0;
@@ -882,7 +907,10 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
             tk[3] += c3 - cm;
             tk[7] += 1;
         }
-        elementwise(post ? 2 : 1, scale, i - 1, lk);
+        if (!elementwise(post ? 2 : 1, pre, i - 1, lk, raw ? i : -1)) {
+            dead = true;
+            break;
+        }
     }
     if (threadIdx.x == 0) bulk_wait_all();
     if (PROF && a.trace && threadIdx.x == 0)

@@ -61,6 +61,7 @@ struct PassArgs {
     long long T, B;
     const double *prior, *reset_base, *lik_table, *log_weight, *init_state;
     double *logE, *local, *alpha_seq, *avg, *final_state;
+    double *row_scale;   // [B][T] normalising factor of each smoothed row (BLG_F_RAW_POSTERIOR) or NULL
     int *alive;
     const StepC *steps;  // [T][ncols_eff]
     unsigned flags;

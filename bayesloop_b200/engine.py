@@ -26,6 +26,7 @@ F_TRANSITION_FIRST = 1 << 2
 F_SAVE_STATE = 1 << 3
 F_ACCUMULATE = 1 << 4
 F_RAW_ALPHA = 1 << 6  # forward rows may stay unnormalised (a backward pass follows)
+F_RAW_POSTERIOR = 1 << 7  # backward rows may stay unnormalised; row_scale[b][t] receives the normalising factor
 F_NORMALIZE_ROWS = 1 << 5
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -53,7 +54,8 @@ class _Inputs(ctypes.Structure):
 
 class _Outputs(ctypes.Structure):
     _fields_ = [('log_evidence', ctypes.c_void_p), ('local_evidence', ctypes.c_void_p), ('alive', ctypes.c_void_p),
-                ('alpha_seq', ctypes.c_void_p), ('avg', ctypes.c_void_p), ('final_state', ctypes.c_void_p)]
+                ('alpha_seq', ctypes.c_void_p), ('avg', ctypes.c_void_p), ('final_state', ctypes.c_void_p),
+                ('row_scale', ctypes.c_void_p)]
 
 
 def _ptr(t):
@@ -297,7 +299,7 @@ class Engine:
         return plan
 
     def _io(self, T, B, data, prior, reset_base, lik_table, program, lo, log_weight, init_state, log_evidence,
-            local_evidence, alive, alpha_seq, avg, final_state):
+            local_evidence, alive, alpha_seq, avg, final_state, row_scale=None):
         i = _Inputs()
         i.T, i.B = int(T), int(B)
         i.data, i.prior, i.reset_base, i.lik_table = _ptr(data), _ptr(prior), _ptr(reset_base), _ptr(lik_table)
@@ -306,13 +308,14 @@ class Engine:
         o = _Outputs()
         o.log_evidence, o.local_evidence, o.alive = _ptr(log_evidence), _ptr(local_evidence), _ptr(alive)
         o.alpha_seq, o.avg, o.final_state = _ptr(alpha_seq), _ptr(avg), _ptr(final_state)
+        o.row_scale = _ptr(row_scale)
         return i, o
 
     def run(self, which, plan, flags, **kw):
         """which in {'forward', 'backward', 'accumulate'}; keyword arguments are the fields of blg_inputs/outputs
         (tensors on self.device) plus `program` and `lo` (first combo row of the program used by this call)."""
         names = ('T', 'B', 'data', 'prior', 'reset_base', 'lik_table', 'program', 'lo', 'log_weight', 'init_state',
-                 'log_evidence', 'local_evidence', 'alive', 'alpha_seq', 'avg', 'final_state')
+                 'log_evidence', 'local_evidence', 'alive', 'alpha_seq', 'avg', 'final_state', 'row_scale')
         args = [kw.get(k) for k in names]
         args[7] = args[7] or 0
         i, o = self._io(*args)

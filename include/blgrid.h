@@ -64,9 +64,13 @@ enum blg_flags {
     BLG_F_ACCUMULATE = 1u << 4,       /* backward: avg[t][g] += exp(log_weight[b]) * max(post, 1e-300)            */
                                       /* (core.py:1358-1366) instead of overwriting alpha_seq with the posterior  */
     BLG_F_NORMALIZE_ROWS = 1u << 5,   /* finalize: divide each [G] row by its sum first (core.py:1379-1382)       */
-    BLG_F_RAW_ALPHA = 1u << 6         /* forward: the rows of alpha_seq may be left UNNORMALISED (each row scaled */
+    BLG_F_RAW_ALPHA = 1u << 6,        /* forward: the rows of alpha_seq may be left UNNORMALISED (each row scaled */
                                       /* by a positive factor): valid only as the input of blg_backward, which is */
                                       /* scale-free per row (core.py:436-441 renormalises alpha*beta)             */
+    BLG_F_RAW_POSTERIOR = 1u << 7     /* backward: the smoothed rows may be left unnormalised; row_scale[b][t]    */
+                                      /* (required) receives the factor that normalises row t of combo b (1.0 if  */
+                                      /* the implementation normalised the row itself).  blg_accumulate applies   */
+                                      /* row_scale when it is given; blg_finalize(NORMALIZE_ROWS) normalises B = 1 */
 };
 
 /* Static description of the grid and the observation model (host pointers; copied by blg_plan_create). */
@@ -126,6 +130,7 @@ typedef struct blg_outputs {
                             /*                ACCUMULATE: overwritten by the smoothed posteriors (core.py:436-441)  */
     double *avg;            /* device [T][G]  backward with ACCUMULATE: running weighted sum (caller zero-fills)     */
     double *final_state;    /* device [B][G]  only with BLG_F_SAVE_STATE                                            */
+    double *row_scale;      /* device [B][T]  backward with BLG_F_RAW_POSTERIOR: written; accumulate: read if non-NULL */
 } blg_outputs;
 
 typedef struct blg_plan blg_plan;
