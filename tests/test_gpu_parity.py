@@ -278,3 +278,19 @@ def test_cluster2d_dead_combos_match_oracle(cuda_engine, oracle_engine, monkeypa
     np.testing.assert_array_equal(got['alive'], want['alive'])
     assert np.all(got['alive'] != 1)
     np.testing.assert_array_equal(np.isneginf(got['logE']), np.isneginf(want['logE']))
+
+
+@pytest.mark.parametrize('name', ['gauss_2d_200x200_stream', 'gauss_2d_256x96_stream'])
+def test_stream2d_opt_in_kernels_match_cpu_oracle(name, cuda_engine, oracle_engine, monkeypatch):
+    """The fused two-phase stream kernels (stream2d.cuh, opt-in through BLG_STREAM2D) stay correct: they are the
+    fallback for GaussianRandomWalk programs on grids the cluster kernels cannot take."""
+    import bayesloop_b200 as bl
+    monkeypatch.setenv('BLG_STREAM2D', '1')
+    monkeypatch.setenv('BLG_NO_CLUSTER2D', '1')
+    got = helpers.abi_sweep(cuda_engine, CONFIGS[name](bl, cuda_engine))
+    assert cuda_engine.last_kernel() == 'bwd_stream2d'
+    want = helpers.abi_sweep(oracle_engine, CONFIGS[name](bl, oracle_engine))
+    np.testing.assert_array_equal(got['alive'], want['alive'])
+    np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-10)
+    rowmax = want['avg'].max(axis=1, keepdims=True)
+    assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-6 * np.abs(want['avg']) + 1e-12 * rowmax)

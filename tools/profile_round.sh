@@ -11,4 +11,4 @@ ncu --set full --clock-control none --import-source on -k regex:'fast1d_ws|accum
 # C3 sample: cluster-resident 2-D kernels
 ncu --set full --clock-control none --import-source on -k regex:cluster2d --launch-skip 2 -c 2 \
     -o gpurun_out/${TAG}_c3_cluster python tools/exp_2d.py 256 200 6 0.1 > gpurun_out/${TAG}_ncu_c3.log 2>&1
-tail -2 gpurun_out/${TAG}_ncu_c2.log gpurun_out/${TAG}_ncu_c3.log
+tail -n 2 gpurun_out/${TAG}_ncu_c2.log; tail -n 2 gpurun_out/${TAG}_ncu_c3.log
