@@ -19,7 +19,12 @@
 //
 // HBM rows: the forward pass stages the likelihood band of the NEXT step with one bulk-async (TMA) copy and, when
 // the caller allows unnormalised rows (BLG_F_RAW_ALPHA: a backward pass follows, which is scale-free per row), stores
-// alpha[t] with one bulk-async copy straight out of the state buffer; the backward pass receives alpha[t-1] by TMA.
+// alpha[t] with one bulk-async copy straight out of the state buffer; the backward pass receives alpha[t-1] by TMA into
+// the band whose smoothed row u = alpha * beta has just left by TMA (BLG_F_RAW_POSTERIOR: unnormalised, its factor
+// 1/sum(u) goes to row_scale[b][t]; otherwise normalised in place first).  With raw rows no phase of a step needs the
+// cluster-wide sums of the previous one before its elementwise sweep, so their all-to-all hides behind the
+// convolutions.  The likelihood row of the backward pass comes through registers (coalesced loads issued after the
+// last convolution, L2-prefetched two steps ahead by a bulk prefetch): a second staging band does not fit at 256^2.
 //
 // Both convolutions commute (separable, linear), so axis 0 always runs first whatever the program order; the results
 // agree with the reference order to rounding (1e-16 relative).  Semantics: core.py:372-417, :434-470,
@@ -27,7 +32,7 @@
 #pragma once
 
 #include "common.cuh"
-#include "stream2d.cuh"  // classify2d, in_window
+#include "stream2d.cuh"  // classify2d (which programs the 2-D kernels understand)
 
 namespace blg {
 

@@ -55,6 +55,10 @@ def test_cuda_library_contains_sm100a_sass_with_bulk_copies():
     assert 'sm_100a' in out
     assert 'UBLKCP' in out, 'bulk-async copy instructions missing from the SASS'
     assert 'fwd_resident_kernel' in out and 'bwd_resident_kernel' in out
+    # thread-block-cluster kernels: cluster barrier, st.async into distributed shared memory, mbarrier transactions
+    assert 'fwd_cluster2d_kernel' in out and 'bwd_cluster2d_kernel' in out
+    for mnemonic in ('UCGABAR_ARV', 'UCGABAR_WAIT', 'STAS.128', 'SYNCS.ARRIVE.TRANS64'):
+        assert mnemonic in out, mnemonic + ' missing from the SASS'
 
 
 def test_product_fails_loudly_without_cuda(monkeypatch):

@@ -1,4 +1,5 @@
-"""Experiment: C3-shaped HyperStudy (Gaussian 2-D grid, GaussianRandomWalk on both axes) on the stream kernels.
+"""Experiment: C3-shaped HyperStudy (Gaussian 2-D grid, GaussianRandomWalk on both axes); default dispatch = the
+cluster-resident kernels (BLG_NO_CLUSTER2D=1: stream kernels; BLG_TRACE=<prefix>: per-phase cycle counters).
 python tools/exp_2d.py [n=256] [T=100] [hyper=12 -> B = hyper^2] [smax=0.1]"""
 import os
 import sys
