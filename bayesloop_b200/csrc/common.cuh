@@ -241,6 +241,16 @@ __device__ __forceinline__ double fast_div(double a, double b) {
     return fabs(b) > 1e-290 ? a * fast_rcp(b) : a / b;
 }
 
+// a / b for b >= 0 with neither the division subroutine nor a branch (the unrolled per-cell epilogues keep their
+// instruction-level parallelism): operands below the range of the fast reciprocal are rescaled by 2^600 (exact).
+// b == 0 gives NaN; that is what 0 / 0 gives, and the callers' numerators vanish with b (post = alpha*beta carries the
+// same likelihood factor, core.py:463).
+__device__ __forceinline__ double fast_div_pos(double a, double b) {
+    const bool small = b < 1e-290;
+    const double q = a * fast_rcp(small ? b * 0x1p600 : b);
+    return small ? q * 0x1p600 : q;
+}
+
 // ------------------------------------------------------------------------------------------------ log-evidence
 // logE = sum_t log(norm_t) (core.py:403) without a log() on the per-step critical path: the product of the norms is
 // carried as mantissa * 2^exponent (two frexp per step, ~10 instructions) and one log() is taken at the end.

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassA
                     const int li = r.i0 + m;
                     const double al = li < n ? A[li] : 0.0;
                     const double pu = al * beta[m];                            // posterior ~ alpha*beta   core.py:436
-                    const double ql = li < n ? fast_div(pu, lk[m]) : 0.0;      // core.py:463
+                    const double ql = li < n ? fast_div_pos(pu, lk[m]) : 0.0;  // core.py:463
                     st[m] = beta[m] * kb * lk[m];                              // beta*likelihood          core.py:467
                     if (li < n) A[li] = pu;
                     if (m & 1) {
