@@ -527,7 +527,6 @@ bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags,
 
 int launch_cluster(PassKernel kernel, const PassArgs &a, const Layout &lay, long long B, int C, cudaStream_t st,
                    const char *name) {
-    g_last_kernel = name;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -542,12 +541,17 @@ int launch_cluster(PassKernel kernel, const PassArgs &a, const Layout &lay, long
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (getenv("BLG_VERBOSE")) {
+    {   // a device (or partition) that cannot co-schedule one such cluster: tell the caller to use the stream kernels
         int clusters = 0;
-        cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg);
-        fprintf(stderr, "[blgrid] %s: %lld clusters x %d CTAs x %d threads, %zu B smem/CTA, band %d rows, halo %d rows, "
-                        "%d clusters resident\n", name, B, C, lay.nt, lay.bytes, a.c2_nb, a.c2_h0, clusters);
+        if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) != cudaSuccess || clusters < 1) {
+            cudaGetLastError();
+            return 1;
+        }
+        if (getenv("BLG_VERBOSE"))
+            fprintf(stderr, "[blgrid] %s: %lld clusters x %d CTAs x %d threads, %zu B smem/CTA, band %d rows, halo %d rows, "
+                            "%d clusters resident\n", name, B, C, lay.nt, lay.bytes, a.c2_nb, a.c2_h0, clusters);
     }
+    g_last_kernel = name;
     long long *trace = nullptr;
     PassArgs a2 = a;
     const long long nblk = B * C;
@@ -741,8 +745,10 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
         int C = 0;
         const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, false, false, a, lay);
         if (want && !getenv("BLG_FORCE_STREAM") && (!store || (uintptr_t)out->alpha_seq % 16 == 0) &&
-            cluster2d_layout(pl, in->prog, flags, false, a, lay, C))
-            return launch_cluster(fwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr), a, lay, in->B, C, st, "fwd_cluster2d");
+            cluster2d_layout(pl, in->prog, flags, false, a, lay, C)) {
+            const int rc = launch_cluster(fwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr), a, lay, in->B, C, st, "fwd_cluster2d");
+            if (rc <= 0) return rc;  // 1: clusters cannot be scheduled here -> stream kernels below
+        }
     }
     if (!resident_layout(pl, in->prog, false, false, a, lay) || getenv("BLG_FORCE_STREAM")) {
         if (pl->dev.ndim == 2 && stream2d_supports(in->prog.n_ops, in->prog.kind, in->prog.axis) && getenv("BLG_STREAM2D") &&
@@ -805,8 +811,9 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
         const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, true, false, a, lay);
         if (want && !getenv("BLG_FORCE_STREAM") && (uintptr_t)out->alpha_seq % 16 == 0 &&
             cluster2d_layout(pl, in->prog, flags, true, a, lay, C)) {
-            pl->rows_raw = a.row_scale != nullptr;
-            return launch_cluster(bwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr), a, lay, in->B, C, st, "bwd_cluster2d");
+            const int rc = launch_cluster(bwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr), a, lay, in->B, C, st, "bwd_cluster2d");
+            if (rc == 0) pl->rows_raw = a.row_scale != nullptr;
+            if (rc <= 0) return rc;
         }
     }
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
