@@ -385,9 +385,16 @@ __device__ __forceinline__ void c2_reset_band(const PassArgs &a, const C2 &s, do
 // the last convolution (early issue of loads consumed by the elementwise phase).  Returns with all threads
 // synchronised on the new band; the split cluster barrier "halo rows consumed" has been ARRIVED at (the caller
 // waits before it pushes).  Returns true if the band was overwritten (beforeWrite has run).
-template <bool TIMED, typename BeforeWrite, typename AfterConv, typename AfterWrite>
+struct C2Identity {
+    __device__ __forceinline__ double operator()(uint32_t, double v) const { return v; }
+};
+
+// `epi(offset, value)` maps every output of the axis-1 convolution on its way back into the band (offset = byte offset
+// of the cell inside the band): the forward pass fuses prior x likelihood and the partial sums of the step there.
+template <bool TIMED, typename BeforeWrite, typename AfterConv, typename AfterWrite, typename Epi = C2Identity>
 __device__ __forceinline__ bool c2_transition(const PassArgs &a, const C2 &s, bool act0, bool act1, long long &tmid,
-                                              BeforeWrite beforeWrite, AfterConv afterConv, AfterWrite afterWrite) {
+                                              BeforeWrite beforeWrite, AfterConv afterConv, AfterWrite afterWrite,
+                                              Epi epi = Epi()) {
     const int n1 = a.pb.n1;
     const uint32_t rowB = (uint32_t)n1 * 8u;
     if (act0) {
@@ -424,10 +431,10 @@ __device__ __forceinline__ bool c2_transition(const PassArgs &a, const C2 &s, bo
         if (!act0) beforeWrite();
         __syncthreads();
         if (has) {
-            const uint32_t out = s.xbAddr + (uint32_t)l * rowB + 8u * (uint32_t)i0;
+            const uint32_t off = (uint32_t)l * rowB + 8u * (uint32_t)i0;
 #pragma unroll
             for (int m = 0; m < kC2M1; ++m)
-                if (i0 + m < n1) c2_sts(out + 8u * (uint32_t)m, acc[m]);
+                if (i0 + m < n1) c2_sts(s.xbAddr + off + 8u * (uint32_t)m, epi(off + 8u * (uint32_t)m, acc[m]));
         }
         afterWrite();  // the accumulators are dead: room for the second batch of early loads
         __syncthreads();
@@ -641,44 +648,70 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) 
         }
         const long long c1 = PROF ? clock64() : 0;
         long long cm = c1;
-        const bool wrote = c2_transition<PROF>(a, s, act0, act1, cm, drainStore, []() {}, []() {});
+        // With a staged likelihood band and an active axis-1 stage the elementwise phase is FUSED into the write-back
+        // of that convolution (alpha <- prior * likelihood, core.py:375-382): two passes over the band less.  The
+        // normaliser of the previous step is collected right after the convolution arithmetic (hidden behind it).
+        const bool fused = table && act1;
+        bool normOk = true, normTaken = false;
+        double kmul = (pre || post) ? 1.0 : kappa;
+        double part[1] = {0.0};
+        auto beforeEpilogue = [&]() {
+            if (!fused) return;
+            mbar_wait(barLik, likPhase);
+            likPhase ^= 1u;
+            likInFlight = false;
+            if (t > 0 && lateNorm) {
+                normOk = takeNorm(t - 1);
+                normTaken = true;
+                if (!pre) kmul = kappa;
+            }
+        };
+        const bool wrote = c2_transition<PROF>(a, s, act0, act1, cm, drainStore, beforeEpilogue, []() {},
+                                               [&](uint32_t off, double v) {
+                                                   if (!fused) return v;
+                                                   const double y = v * kmul * c2_lds(s.sAddr + off);
+                                                   part[0] += y;
+                                                   return y;
+                                               });
         if (!wrote && pendingStore) {
             drainStore();
             __syncthreads();
         }
         const long long c2 = PROF ? clock64() : 0;
-        // E: alpha <- prior * likelihood (core.py:375-382), unnormalised
-        if (table) {
+        if (table && !fused) {
             mbar_wait(barLik, likPhase);
             likPhase ^= 1u;
             likInFlight = false;
         }
         c2_wait();  // every CTA has consumed its halo rows
-        if (t > 0 && lateNorm && !takeNorm(t - 1)) {
+        if (!normTaken && t > 0 && lateNorm) normOk = takeNorm(t - 1);
+        if (!normOk) {  // core.py:388-400 (uniform over the cluster)
             dead = true;
             break;
         }
         const long long c3 = PROF ? clock64() : 0;
-        const double kmul = (pre || post) ? 1.0 : kappa;
-        double part[1] = {0.0};
-        double x[kC2Cells], l[kC2Cells];
-        c2_sweep(
-            a, s, tb, t, !post,
-            [&](int k, int gi) {
-                x[k] = c2_lds(s.xbAddr + 8u * (uint32_t)gi);
-                l[k] = c2_lds(s.sAddr + 8u * (uint32_t)gi);
-            },
-            [&](int k, int g, bool valid) {
-                const double y = x[k] * kmul * l[k];
-                if (valid) c2_sts(s.xbAddr + 8u * (uint32_t)g, y);
-                part[0] += valid ? y : 0.0;
-            },
-            [&](int g, double lik) {
-                const double v = post ? __ldg(rb + (size_t)s.r0 * n1 + g) * s.parPost : c2_Xb(a)[g] * kmul;
-                const double y = v * lik;
-                c2_Xb(a)[g] = y;
-                part[0] += y;
-            });
+        if (!fused) {
+            // E: alpha <- prior * likelihood (core.py:375-382), unnormalised
+            if (!(pre || post)) kmul = kappa;
+            double x[kC2Cells], l[kC2Cells];
+            c2_sweep(
+                a, s, tb, t, !post,
+                [&](int k, int gi) {
+                    x[k] = c2_lds(s.xbAddr + 8u * (uint32_t)gi);
+                    l[k] = c2_lds(s.sAddr + 8u * (uint32_t)gi);
+                },
+                [&](int k, int g, bool valid) {
+                    const double y = x[k] * kmul * l[k];
+                    if (valid) c2_sts(s.xbAddr + 8u * (uint32_t)g, y);
+                    part[0] += valid ? y : 0.0;
+                },
+                [&](int g, double lik) {
+                    const double v = post ? __ldg(rb + (size_t)s.r0 * n1 + g) * s.parPost : c2_Xb(a)[g] * kmul;
+                    const double y = v * lik;
+                    c2_Xb(a)[g] = y;
+                    part[0] += y;
+                });
+        }
         if (raw) fence_proxy_async();  // the band is read by the bulk-async store below
         const long long c4 = PROF ? clock64() : 0;
         const bool more = table && t + 1 < T;
