@@ -127,7 +127,7 @@ class Program:
             return None
         key = (lo, hi, sms, slots)
         if key not in self._orders:
-            memo = (self.host['radius'][lo:hi].tobytes(), sms, slots)
+            memo = (self.host['radius'][lo:hi].tobytes(), sms, slots, os.environ.get('BLG_SLOT_ORDER', ''))
             if memo in _ASSIGNMENTS:  # same sweep fitted again (new data, same hyper-grid): reuse the host table
                 self._orders[key] = self._engine.to_device(_ASSIGNMENTS[memo])
                 return self._orders[key]
@@ -142,6 +142,15 @@ class Program:
                 table[sm, fill[sm]] = b
                 fill[sm] += 1
                 load[sm] += cost[b]
+            order_mode = os.environ.get('BLG_SLOT_ORDER', 'heavy_first')
+            if order_mode != 'heavy_first':
+                # CTAs claim the slots of their SM in arrival order and the warp schedulers favour older warps
+                for sm in range(sms):
+                    k = int(fill[sm])
+                    if order_mode == 'light_first':
+                        table[sm, :k] = table[sm, :k][::-1].copy()
+                    elif order_mode == 'heavy_second' and k >= 2:
+                        table[sm, [0, 1]] = table[sm, [1, 0]]
             if len(_ASSIGNMENTS) > 32:
                 _ASSIGNMENTS.clear()
             _ASSIGNMENTS[memo] = table
