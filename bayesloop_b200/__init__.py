@@ -8,7 +8,7 @@
     S.fit()
 
 Same names as the reference package (bayesloop/__init__.py:4-18) for everything on the hot path; the probability
-parser, plotting, Jeffreys-prior derivation and file I/O of the reference are outside this engine's scope
+parser, plotting and Jeffreys-prior derivation of the reference are outside this engine's scope
 (DESIGN.md "Out of scope").
 """
 from . import observationModels
@@ -17,8 +17,9 @@ from . import transitionModels
 from . import transitionModels as tm
 from .core import ChangepointStudy, HyperStudy, OnlineStudy, Study
 from .exceptions import ConfigurationError, PostProcessingError
+from .fileIO import load, save
 from .helper import cint, oint
 
 __all__ = ['Study', 'HyperStudy', 'ChangepointStudy', 'OnlineStudy', 'observationModels', 'om', 'transitionModels',
-           'tm', 'cint', 'oint', 'ConfigurationError', 'PostProcessingError']
+           'tm', 'cint', 'oint', 'ConfigurationError', 'PostProcessingError', 'save', 'load']
 __version__ = '0.1.0'

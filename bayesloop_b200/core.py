@@ -1042,6 +1042,7 @@ class OnlineStudy(HyperStudy):
         self.formattedTimestamps.append(self.rawTimestamps[-1])
 
         nTM = len(self.transitionModels)
+        self._resume()
         if self.firstStep:
             self._setupDevice()
             if self.transitionModelPrior is None:
@@ -1112,9 +1113,42 @@ class OnlineStudy(HyperStudy):
             self.localTransitionModelSequence.append(self.localTransitionModelDistribution.copy())
         self.firstStep = False
 
+    # ------------------------------------------------------------------------------------ checkpoint / resume
+    # SURVEY.md 8f row f3 (reference: bl.save / bl.load pickle the whole study, fileIO.py:10-37).  The hypotheses'
+    # posteriors live in HBM between steps; pickling brings them to the host, unpickling re-creates the device side
+    # lazily (plan, concatenated program, state upload) on whatever engine is current -- a study checkpointed on one
+    # GPU resumes on another, or on a different rank.
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        dev = d.pop('_dev', None)
+        d['_dev'] = None
+        d['_engineOverride'] = None  # engines hold library handles and a device: not part of the state
+        if dev is not None:
+            eng = dev['eng']
+            d['_checkpoint'] = dict(state=eng.to_host(dev['state']).copy(), weights=np.array(dev.get('weights')),
+                                    H=dev['H'], G=dev['G'])
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+
+    def _resume(self):
+        """Re-create the device side of an unpickled study (no-op otherwise)."""
+        ck = self.__dict__.get('_checkpoint')
+        if self._dev is None and ck is not None and not self.firstStep:
+            self._setupDevice()
+            dev = self._dev
+            if (dev['H'], dev['G']) != (ck['H'], ck['G']):
+                raise ConfigurationError('Checkpoint does not match the models of this study.')
+            dev['state'].copy_(dev['eng'].to_device(ck['state']))
+            dev['weights'] = ck['weights']
+            dev['mixedValid'] = False
+            self._checkpoint = None
+
     # device-resident results, copied to the host when somebody looks at them
     @property
     def marginalizedPosterior(self):
+        self._resume()
         dev = self._dev
         if dev is None:
             return None
@@ -1131,6 +1165,7 @@ class OnlineStudy(HyperStudy):
 
     @property
     def parameterPosterior(self):
+        self._resume()
         dev = self._dev
         if dev is None:
             return None

@@ -294,3 +294,28 @@ def test_stream2d_opt_in_kernels_match_cpu_oracle(name, cuda_engine, oracle_engi
     np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-10)
     rowmax = want['avg'].max(axis=1, keepdims=True)
     assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-6 * np.abs(want['avg']) + 1e-12 * rowmax)
+
+
+def test_online_study_checkpoint_resume_on_device(use_cuda, tmp_path):
+    """bl.save / bl.load of an OnlineStudy whose hypothesis posteriors live in HBM: the resumed stream continues
+    bit-identically (same kernels, same state)."""
+    import contextlib
+    import io
+    import bayesloop_b200 as bl
+    from test_host_logic import _online_study
+    rng = np.random.default_rng(21)
+    x = np.zeros(30)
+    for i in range(1, len(x)):
+        x[i] = 0.5 * x[i - 1] + rng.normal()
+    with contextlib.redirect_stdout(io.StringIO()):
+        A, B = _online_study(bl), _online_study(bl)
+        for d in x:
+            A.step(d)
+        for d in x[:11]:
+            B.step(d)
+        bl.save(str(tmp_path / 'online.bl'), B)
+        C = bl.load(str(tmp_path / 'online.bl'))
+        for d in x[11:]:
+            C.step(d)
+    assert C.logEvidence == A.logEvidence
+    np.testing.assert_array_equal(C.marginalizedPosterior, A.marginalizedPosterior)

@@ -29,3 +29,43 @@ def test_golden_matches_reference_docs():
     for name, want in cases.REFERENCE_PINNED_LOG10E.items():
         got = float(load_golden(name)['logEvidence']) / np.log(10)
         assert abs(got - want) < 1e-5
+
+
+def _online_study(bl):
+    S = bl.OnlineStudy(storeHistory=False, silent=True)
+    S.setOM(bl.om.ScaledAR1('rho', bl.oint(-1, 1, 24), 'sigma', bl.oint(0, 3, 28)), silent=True)
+    S.add('normal', bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s1', bl.cint(0, 0.1, 3), target='rho'),
+                                                  bl.tm.GaussianRandomWalk('s2', bl.cint(0, 0.2, 2), target='sigma')))
+    S.add('chaotic', bl.tm.RegimeSwitch('p', bl.cint(-8, -3, 3)))
+    S.add('indep', bl.tm.Independent())
+    return S
+
+
+def test_online_study_checkpoint_resume(use_oracle):
+    """an OnlineStudy pickled between two steps (device state -> host) and resumed continues
+    exactly like the uninterrupted one (reference: bl.save / bl.load, fileIO.py:10-37)."""
+    import contextlib
+    import io
+    import pickle
+    import bayesloop_b200 as bl
+    rng = np.random.default_rng(21)
+    x = np.zeros(40)
+    for i in range(1, len(x)):
+        x[i] = 0.5 * x[i - 1] + rng.normal()
+    with contextlib.redirect_stdout(io.StringIO()):
+        A, B = _online_study(bl), _online_study(bl)
+        for d in x:
+            A.step(d)
+        for d in x[:17]:
+            B.step(d)
+        blob = pickle.dumps(B)
+        del B
+        C = pickle.loads(blob)
+        np.testing.assert_allclose(C.marginalizedPosterior, pickle.loads(blob).marginalizedPosterior)  # usable at once
+        for d in x[17:]:
+            C.step(d)
+    assert C.logEvidence == A.logEvidence
+    np.testing.assert_array_equal(C.marginalizedPosterior, A.marginalizedPosterior)
+    np.testing.assert_array_equal(C.transitionModelDistribution, A.transitionModelDistribution)
+    for a, c in zip(A.parameterPosterior, C.parameterPosterior):
+        np.testing.assert_array_equal(a, c)
