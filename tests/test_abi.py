@@ -69,3 +69,17 @@ def test_product_fails_loudly_without_cuda(monkeypatch):
     engine.set_default_engine(None)
     with pytest.raises(engine.EngineError):
         engine.default_engine()
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The Python binding lays its structures out exactly like include/blgrid.h (sizes from a C compiler)."""
+    from bayesloop_b200 import engine
+    src = tmp_path / 'sizes.c'
+    src.write_text('#include <stdio.h>\n#include "blgrid.h"\nint main(void) { printf("%zu %zu %zu %zu\\n", '
+                   'sizeof(blg_problem), sizeof(blg_program), sizeof(blg_inputs), sizeof(blg_outputs)); return 0; }\n')
+    exe = tmp_path / 'sizes'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    want = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    got = [ctypes.sizeof(engine._Problem), ctypes.sizeof(engine._Program), ctypes.sizeof(engine._Inputs),
+           ctypes.sizeof(engine._Outputs)]
+    assert got == want
