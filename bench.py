@@ -17,7 +17,10 @@ grid-cell updates.
              host->device copies of data/program and device->host copies of the averaged posterior sequence,
              means and evidences inside the timed region
   roofline   dominant kernel: algorithmic HBM bytes per launch / live CUDA-event duration, vs MEASURED_PEAKS.json
+  roofline.fp64 the binding unit of this workload: convolution flop per pass / kernel time vs the measured DFMA peak
   cpu_baseline  oracle/np_oracle.py (NumPy+SciPy port of the reference loop) on a bounded sample, 1 core
+  extra.c2_narrow   the same sweep with sigma <= 0.05 (radius <= 17): the HBM-leaning regime (N = 1 only)
+  extra.c3_sample   bounded sample of BASELINE.json configs[2] (256 x 256 grid) on the cluster-resident kernels (N = 1)
 """
 import argparse
 import json
