@@ -470,7 +470,7 @@ int launch_stream(PassKernel kernel, blg_plan *pl, PassArgs &a, Layout lay, long
 // is one work item per thread in both convolutions, the axis-0 radius fits in the smallest band, and the state
 // buffer (+ the alpha staging band of the backward pass) fits in shared memory.
 bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags, bool backward, PassArgs &a, Layout &lay,
-                      int &C) {
+                      int &C, int &M0out) {
     const DevProblem &d = pl->dev;
     if (d.ndim != 2 || getenv("BLG_NO_CLUSTER2D")) return false;
     if (flags & (BLG_F_INIT_STATE | BLG_F_SAVE_STATE | BLG_F_TRANSITION_FIRST | BLG_F_ACCUMULATE)) return false;
@@ -491,8 +491,11 @@ bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags,
         const int nb = (d.n0 + c - 1) / c;
         const int last = d.n0 - (c - 1) * nb;
         if (last < 1 || r0max > last) continue;
-        if (nb * ((d.n1 + M1 - 1) / M1) > NT || d.n1 * ((nb + M0 - 1) / M0) > NT || nb * d.n1 > cells * NT) continue;
-        const int nbp = (nb + M0 - 1) / M0 * M0;
+        // rows per axis-0 work item: 16, or 13 where that wastes fewer rows of the band (25-row bands of a 200^2 grid)
+        int m0 = M0;
+        if ((nb + 12) / 13 * 13 < (nb + M0 - 1) / M0 * M0 && d.n1 * ((nb + 12) / 13) <= NT) m0 = 13;
+        if (nb * ((d.n1 + M1 - 1) / M1) > NT || d.n1 * ((nb + m0 - 1) / m0) > NT || nb * d.n1 > cells * NT) continue;
+        const int nbp = (nb + m0 - 1) / m0 * m0;
         int off = 0;
         a.c2_nb = nb;
         a.c2_h0 = r0max;
@@ -520,6 +523,7 @@ bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags,
         a.halo = 0;
         a.Gp = even_up(d.G);
         C = c;
+        M0out = m0;
         return true;
     }
     return false;
@@ -742,11 +746,11 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     }
     a.halo = 0;
     {
-        int C = 0;
+        int C = 0, m0 = 16;
         const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, false, false, a, lay);
         if (want && !getenv("BLG_FORCE_STREAM") && (!store || (uintptr_t)out->alpha_seq % 16 == 0) &&
-            cluster2d_layout(pl, in->prog, flags, false, a, lay, C)) {
-            const int rc = launch_cluster(fwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr), a, lay, in->B, C, st, "fwd_cluster2d");
+            cluster2d_layout(pl, in->prog, flags, false, a, lay, C, m0)) {
+            const int rc = launch_cluster(fwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr, m0), a, lay, in->B, C, st, "fwd_cluster2d");
             if (rc <= 0) return rc;  // 1: clusters cannot be scheduled here -> stream kernels below
         }
     }
@@ -807,11 +811,11 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     }
     a.halo = 0;
     {
-        int C = 0;
+        int C = 0, m0 = 16;
         const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, true, false, a, lay);
         if (want && !getenv("BLG_FORCE_STREAM") && (uintptr_t)out->alpha_seq % 16 == 0 &&
-            cluster2d_layout(pl, in->prog, flags, true, a, lay, C)) {
-            const int rc = launch_cluster(bwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr), a, lay, in->B, C, st, "bwd_cluster2d");
+            cluster2d_layout(pl, in->prog, flags, true, a, lay, C, m0)) {
+            const int rc = launch_cluster(bwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr, m0), a, lay, in->B, C, st, "bwd_cluster2d");
             if (rc == 0) pl->rows_raw = a.row_scale != nullptr;
             if (rc <= 0) return rc;
         }

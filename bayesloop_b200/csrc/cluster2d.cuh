@@ -37,7 +37,8 @@
 namespace blg {
 
 constexpr int kC2Threads = 512;
-constexpr int kC2M0 = 16;      // rows per work item of the axis-0 convolution
+constexpr int kC2M0 = 16;      // rows per work item of the axis-0 convolution (template parameter M0: 16 or 13, whichever
+                               // wastes fewer rows of the band: 32-row bands -> 16, 25-row bands -> 13)
 constexpr int kC2M1 = 17;      // cells per work item of the axis-1 convolution (odd: conflict-free 64-bit LDS)
 constexpr int kC2Cells = 16;   // cells per thread of the elementwise phases (band <= 16 * 512 cells)
 constexpr int kC2MaxCluster = 8;
@@ -391,20 +392,20 @@ struct C2Identity {
 
 // `epi(offset, value)` maps every output of the axis-1 convolution on its way back into the band (offset = byte offset
 // of the cell inside the band): the forward pass fuses prior x likelihood and the partial sums of the step there.
-template <bool TIMED, typename BeforeWrite, typename AfterConv, typename AfterWrite, typename Epi = C2Identity>
+template <bool TIMED, int M0, typename BeforeWrite, typename AfterConv, typename AfterWrite, typename Epi = C2Identity>
 __device__ __forceinline__ bool c2_transition(const PassArgs &a, const C2 &s, bool act0, bool act1, long long &tmid,
                                               BeforeWrite beforeWrite, AfterConv afterConv, AfterWrite afterWrite,
                                               Epi epi = Epi()) {
     const int n1 = a.pb.n1;
     const uint32_t rowB = (uint32_t)n1 * 8u;
     if (act0) {
-        const int S0 = (a.c2_nb + kC2M0 - 1) / kC2M0;
+        const int S0 = (a.c2_nb + M0 - 1) / M0;
         const int w = threadIdx.x;
         const bool has = w < n1 * S0;
-        const int seg = w / n1, c = w - seg * n1, i0 = seg * kC2M0;
-        double acc[kC2M0];
+        const int seg = w / n1, c = w - seg * n1, i0 = seg * M0;
+        double acc[M0];
         if (has)
-            c2_conv_col<kC2M0>(s.xAddr + (uint32_t)(a.c2_h0 + i0 - s.R0) * rowB + 8u * (uint32_t)c, rowB,
+            c2_conv_col<M0>(s.xAddr + (uint32_t)(a.c2_h0 + i0 - s.R0) * rowB + 8u * (uint32_t)c, rowB,
                                s.xAddr + (uint32_t)(a.c2_rows - 1) * rowB + 8u * (uint32_t)c, 2 * s.R0 + 1, s.w0Addr, acc);
         beforeWrite();
         __syncthreads();
@@ -412,7 +413,7 @@ __device__ __forceinline__ bool c2_transition(const PassArgs &a, const C2 &s, bo
         if (has) {
             const uint32_t out = s.xbAddr + (uint32_t)i0 * rowB + 8u * (uint32_t)c;
 #pragma unroll
-            for (int m = 0; m < kC2M0; ++m)
+            for (int m = 0; m < M0; ++m)
                 if (i0 + m < s.nb) c2_sts(out + (uint32_t)m * rowB, acc[m]);
         }
         __syncthreads();
@@ -548,7 +549,7 @@ __device__ __forceinline__ void c2_init_barriers(const PassArgs &a, uint64_t *tm
 // PROF: per-CTA cycle counters of the step phases (thread 0), written to a.trace[blockIdx.x * 8 + k]:
 // 0 wait for the halo rows (+ normaliser and flush when rows are stored normalised), 1 axis-0 stage, 2 axis-1 stage,
 // 3 staged likelihood + split barrier + normaliser, 4 elementwise sweep, 5 publish, 6 whole loop, 7 steps
-template <int NT, bool PROF>
+template <int NT, bool PROF, int M0>
 __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) {
     static_assert(NT == kC2Threads, "layout constants assume kC2Threads");
     const DevProblem &pb = a.pb;
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) 
                 if (!pre) kmul = kappa;
             }
         };
-        const bool wrote = c2_transition<PROF>(a, s, act0, act1, cm, drainStore, beforeEpilogue, []() {},
+        const bool wrote = c2_transition<PROF, M0>(a, s, act0, act1, cm, drainStore, beforeEpilogue, []() {},
                                                [&](uint32_t off, double v) {
                                                    if (!fused) return v;
                                                    const double y = v * kmul * c2_lds(s.sAddr + off);
@@ -767,7 +768,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) 
 // iteration and is then refilled with alpha[i-1] by one bulk-async (TMA) copy that lands during the convolutions.
 // PROF counters (a.trace[blockIdx.x * 8 + k]): 0 collect (halo rows + sums), 1 posterior flush + alpha TMA issue,
 // 2 axis-0 stage, 3 axis-1 stage + likelihood loads, 4 wait alpha + split barrier, 5 sweep, 6 publish, 7 steps
-template <int NT, bool PROF>
+template <int NT, bool PROF, int M0>
 __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) {
     static_assert(NT == kC2Threads, "layout constants assume kC2Threads");
     const DevProblem &pb = a.pb;
@@ -935,7 +936,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         double lk[kC2Cells];
         const long long c2 = PROF ? clock64() : 0;
         long long cm = c2;
-        c2_transition<PROF>(a, s, act0, act1, cm, issueAlpha, [&]() { c2_lik<0>(a, s, i - 1, lk); },
+        c2_transition<PROF, M0>(a, s, act0, act1, cm, issueAlpha, [&]() { c2_lik<0>(a, s, i - 1, lk); },
                             [&]() { c2_lik<8>(a, s, i - 1, lk); });
         if (PROF) {
             const long long c3 = clock64();

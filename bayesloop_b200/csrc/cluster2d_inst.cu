@@ -5,9 +5,15 @@
 namespace blg {
 
 #if BLG_INST_BWD
-PassKernel bwd_cluster2d_entry(bool prof) { return prof ? bwd_cluster2d_kernel<kC2Threads, true> : bwd_cluster2d_kernel<kC2Threads, false>; }
+PassKernel bwd_cluster2d_entry(bool prof, int m0) {
+    if (m0 == 13) return prof ? bwd_cluster2d_kernel<kC2Threads, true, 13> : bwd_cluster2d_kernel<kC2Threads, false, 13>;
+    return prof ? bwd_cluster2d_kernel<kC2Threads, true, 16> : bwd_cluster2d_kernel<kC2Threads, false, 16>;
+}
 #else
-PassKernel fwd_cluster2d_entry(bool prof) { return prof ? fwd_cluster2d_kernel<kC2Threads, true> : fwd_cluster2d_kernel<kC2Threads, false>; }
+PassKernel fwd_cluster2d_entry(bool prof, int m0) {
+    if (m0 == 13) return prof ? fwd_cluster2d_kernel<kC2Threads, true, 13> : fwd_cluster2d_kernel<kC2Threads, false, 13>;
+    return prof ? fwd_cluster2d_kernel<kC2Threads, true, 16> : fwd_cluster2d_kernel<kC2Threads, false, 16>;
+}
 void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad) {
     *threads = kC2Threads;
     *m0 = kC2M0;

@@ -30,8 +30,9 @@ int stream2d_chunk();
 bool stream2d_supports(int n_ops, const int *kind, const int *axis);
 
 // cluster-resident 2-D kernels (cluster2d.cuh): 512 threads, one cluster of 2/4/8 CTAs per combo
-PassKernel fwd_cluster2d_entry(bool prof = false);  // prof: per-phase cycle counters into PassArgs::trace
-PassKernel bwd_cluster2d_entry(bool prof = false);
+// prof: per-phase cycle counters into PassArgs::trace; m0 in {16, 13}: rows per axis-0 work item
+PassKernel fwd_cluster2d_entry(bool prof, int m0);
+PassKernel bwd_cluster2d_entry(bool prof, int m0);
 // layout parameters of cluster2d.cuh: threads, rows per axis-0 item, cells per axis-1 item, cells per thread
 void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad);
 
