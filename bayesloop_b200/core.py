@@ -1199,7 +1199,55 @@ class OnlineStudy(HyperStudy):
         raise NotImplementedError('OnlineStudy object has no "fit" method. Use "step" instead.')
 
     # ------------------------------------------------------------------------------------------- accessors
+    # Host-side views of the streaming results (reference: core.py:2231-2897).  The "current" ones read the device
+    # state of the last step; the time-indexed ones need storeHistory=True (the history lives on the host).
+    def _needHistory(self, what, instead):
+        if not self.storeHistory:
+            raise PostProcessingError('To get past {}, Online Study must be called with flag "storeHistory=True". '
+                                      'Use "{}" instead.'.format(what, instead))
+
+    def _timeIndex(self, t):
+        stamps = list(self.formattedTimestamps)
+        if t not in stamps:
+            raise PostProcessingError('Supplied time ({}) does not exist in data or is out of range.'.format(t))
+        return stamps.index(t)
+
+    def _locateHyperParameter(self, name):
+        """(transition-model index, hyper-parameter index) of a hyper-parameter of any added model; the last
+        model that knows the name wins, like the loop of core.py:2593-2599."""
+        found = None
+        for i, tm in enumerate(self.transitionModels):
+            try:
+                found = (i, self._getHyperParameterIndex(tm, name))
+            except PostProcessingError:
+                pass
+        if found is None:
+            raise PostProcessingError('No hyper-parameter "{}" found. Check hyper-parameter names.'.format(name))
+        return found
+
+    def _hyperMarginal(self, flat, tmIndex, hpIndex):
+        steps = [len(x) for x in self.allFlatHyperParameterValues[tmIndex]]
+        cube = np.asarray(flat, dtype=float).reshape(steps, order='C')
+        others = tuple(a for a in range(cube.ndim) if a != hpIndex)
+        return np.sum(cube, axis=others) if others else cube.copy()
+
+    def getParameterDistribution(self, t, name, plot=False, density=True, **kwargs):
+        """Marginal distribution of one parameter at time stamp `t` or 'avg' (core.py:2231-2260)."""
+        self._needHistory('parameter distributions', 'getCurrentParameterDistribution')
+        seq = np.asarray(self.posteriorSequence)
+        dist = np.sum(seq, axis=0) / len(seq) if isinstance(t, str) and t == 'avg' else seq[self._timeIndex(t)]
+        axis = self._parameterIndex(name)
+        others = tuple(a for a in range(dist.ndim) if a != axis)
+        marginal = np.sum(dist, axis=others) if others else dist.copy()
+        if density:
+            marginal = marginal / self.latticeConstant[axis]
+        return self.marginalGrid[axis], marginal
+
+    def getPD(self, t, name, plot=False, density=True, **kwargs):
+        return self.getParameterDistribution(t, name, plot=plot, density=density, **kwargs)
+
     def getCurrentParameterDistribution(self, name, plot=False, density=True, **kwargs):
+        """Marginal distribution of one parameter after the last step (core.py:2268-2315)."""
         axis = self._parameterIndex(name)
         post = self.marginalizedPosterior
         others = tuple(a for a in range(post.ndim) if a != axis)
@@ -1208,20 +1256,127 @@ class OnlineStudy(HyperStudy):
             marginal = marginal / self.latticeConstant[axis]
         return self.marginalGrid[axis], marginal
 
+    def getCPD(self, name, plot=False, density=True, **kwargs):
+        return self.getCurrentParameterDistribution(name, plot=plot, density=density, **kwargs)
+
+    def getParameterDistributions(self, name, plot=False, density=True, **kwargs):
+        """Marginal distributions of one parameter for all steps so far: [T, n_axis] (core.py:2323-2351)."""
+        self._needHistory('parameter distributions', 'getCurrentParameterDistribution')
+        axis = self._parameterIndex(name)
+        seq = np.asarray(self.posteriorSequence)
+        others = tuple(a + 1 for a in range(seq.ndim - 1) if a != axis)
+        marginal = np.sum(seq, axis=others) if others else seq.copy()
+        if density:
+            marginal = marginal / self.latticeConstant[axis]
+        return self.marginalGrid[axis], marginal
+
+    def getPDs(self, name, plot=False, density=True, **kwargs):
+        return self.getParameterDistributions(name, plot=plot, density=density, **kwargs)
+
     def getCurrentTransitionModelDistribution(self, local=False, plot=False, **kwargs):
         dist = self.localTransitionModelDistribution if local else self.transitionModelDistribution
-        return self.transitionModelNames, dist
+        return np.array(self.transitionModelNames), dist
+
+    def getCTMD(self, local=False):
+        return self.getCurrentTransitionModelDistribution(local=local)
+
+    def getCurrentTransitionModelProbability(self, transitionModel, local=False):
+        i = self.transitionModelNames.index(transitionModel)
+        return (self.localTransitionModelDistribution if local else self.transitionModelDistribution)[i]
+
+    def getCTMP(self, transitionModel, local=False):
+        return self.getCurrentTransitionModelProbability(transitionModel, local=local)
+
+    def getTransitionModelDistributions(self, local=False):
+        """Names and [T, #models] probabilities of the transition models for all steps (core.py:2430-2450)."""
+        self._needHistory('transition model distributions', 'getCurrentTransitionModelDistribution')
+        seq = self.localTransitionModelSequence if local else self.transitionModelSequence
+        return np.array(self.transitionModelNames), np.array(seq)
+
+    def getTransitionModelProbabilities(self, transitionModel, local=False):
+        self._needHistory('transition model distributions', 'getCurrentTransitionModelDistribution')
+        i = self.transitionModelNames.index(transitionModel)
+        seq = self.localTransitionModelSequence if local else self.transitionModelSequence
+        return np.array(seq)[:, i]
+
+    def getTMPs(self, transitionModel, local=False):
+        return self.getTransitionModelProbabilities(transitionModel, local=local)
+
+    def getCurrentParameterMeanValue(self, name):
+        return np.sum(self.marginalizedPosterior * self.grid[self._parameterIndex(name)])
+
+    def getParameterMeanValue(self, t, name):
+        """Posterior mean of one parameter at time stamp `t`.  (The reference indexes the stored posterior a second
+        time with `t`, core.py:2541 -- a quirk that only works on 1-D grids by accident; this is the mean of the
+        whole posterior of that step, i.e. getParameterMeanValues(name)[index of t].)"""
+        self._needHistory('parameter mean values', 'getCurrentParameterMeanValue')
+        axis = self._parameterIndex(name)
+        return np.sum(np.asarray(self.posteriorSequence[self._timeIndex(t)]) * self.grid[axis])
+
+    def getParameterMeanValues(self, name):
+        self._needHistory('parameter mean values', 'getCurrentParameterMeanValue')
+        return np.array(self.posteriorMeanValues).T[self._parameterIndex(name)]
+
+    def _hyperMean(self, flat, tmIndex, hpIndex):
+        values = np.asarray(self.hyperParameterValues[tmIndex], dtype=float)[:, hpIndex]
+        return np.sum(values * np.asarray(flat, dtype=float)) * np.prod(self.hyperGridConstants[tmIndex])
+
+    def getHyperParameterMeanValue(self, t, name):
+        """Mean of one hyper-parameter under its model's hyper-posterior at time stamp `t` (core.py:2574-2614)."""
+        self._needHistory('hyper-parameter mean values', 'getCurrentHyperParameterMeanValue')
+        tmIndex, hpIndex = self._locateHyperParameter(name)
+        return self._hyperMean(self.hyperParameterSequence[self._timeIndex(t)][tmIndex], tmIndex, hpIndex)
+
+    def getCurrentHyperParameterMeanValue(self, name):
+        tmIndex, hpIndex = self._locateHyperParameter(name)
+        return self._hyperMean(self.hyperParameterDistribution[tmIndex], tmIndex, hpIndex)
+
+    def getHyperParameterMeanValues(self, name):
+        self._needHistory('hyper-parameter mean values', 'getCurrentHyperParameterMeanValue')
+        tmIndex, hpIndex = self._locateHyperParameter(name)
+        return np.array([self._hyperMean(h[tmIndex], tmIndex, hpIndex) for h in self.hyperParameterSequence])
+
+    def getHyperParameterDistribution(self, t, name, plot=False, **kwargs):
+        """Marginal distribution of one hyper-parameter at time stamp `t` or 'avg' (core.py:2651-2718; like the
+        reference, the stored densities are returned as they are, without the hyper-grid constant)."""
+        self._needHistory('hyper-parameter distributions', 'getCurrentHyperParameterDistribution')
+        tmIndex, hpIndex = self._locateHyperParameter(name)
+        if isinstance(t, str) and t == 'avg':
+            flat = np.mean([np.asarray(h[tmIndex], dtype=float) for h in self.hyperParameterSequence], axis=0)
+        else:
+            flat = self.hyperParameterSequence[self._timeIndex(t)][tmIndex]
+        return self.allFlatHyperParameterValues[tmIndex][hpIndex], self._hyperMarginal(flat, tmIndex, hpIndex)
+
+    def getHPD(self, t, name, plot=False, **kwargs):
+        return self.getHyperParameterDistribution(t, name, plot=plot, **kwargs)
 
     def getCurrentHyperParameterDistribution(self, name, plot=False, **kwargs):
-        for i, names in enumerate(self.hyperParameterNames):
-            if name in names:
-                axis = list(names).index(name)
-                shape = [len(x) if isinstance(x, Iterable) else 1 for x in self.allFlatHyperParameterValues[i]]
-                cube = np.asarray(self.hyperParameterDistribution[i]).reshape(shape, order='C')
-                others = tuple(a for a in range(cube.ndim) if a != axis)
-                marginal = (np.sum(cube, axis=others) if others else cube) * np.prod(self.hyperGridConstants[i])
-                return self.allFlatHyperParameterValues[i][axis], marginal
-        raise PostProcessingError('Could not find any hyper-parameter named {}.'.format(name))
+        """Marginal probabilities of one hyper-parameter after the last step (core.py:2726-2777)."""
+        tmIndex, hpIndex = self._locateHyperParameter(name)
+        marginal = self._hyperMarginal(self.hyperParameterDistribution[tmIndex], tmIndex, hpIndex)
+        return self.allFlatHyperParameterValues[tmIndex][hpIndex], marginal * np.prod(self.hyperGridConstants[tmIndex])
+
+    def getCHPD(self, name, plot=False, **kwargs):
+        return self.getCurrentHyperParameterDistribution(name, plot=plot, **kwargs)
+
+    def getHyperParameterDistributions(self, name):
+        """Marginal probabilities of one hyper-parameter for all steps: sorted unique values and [T, #values],
+        each row normalised to one (core.py:2785-2831)."""
+        self._needHistory('hyper-parameter distributions', 'getCurrentHyperParameterDistribution')
+        tmIndex, hpIndex = self._locateHyperParameter(name)
+        column = np.asarray(self.hyperParameterValues[tmIndex], dtype=float)[:, hpIndex]
+        values, inverse = np.unique(column, return_inverse=True)
+        seq = np.array([np.asarray(h[tmIndex], dtype=float) for h in self.hyperParameterSequence])
+        marginal = np.zeros((len(seq), len(values)))
+        for k in range(len(values)):
+            marginal[:, k] = np.sum(seq[:, inverse == k], axis=1)
+        return values, marginal / np.sum(marginal, axis=1)[:, None]
+
+    def getHPDs(self, name):
+        return self.getHyperParameterDistributions(name)
+
+    def getJointHyperParameterDistribution(self, names, plot=False, figure=None, subplot=111, **kwargs):
+        raise NotImplementedError('This method is not available in "OnlineStudy".')  # core.py:2897-2898
 
 
 class _ResetShim:
