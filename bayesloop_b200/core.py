@@ -463,6 +463,66 @@ class Study(object):
         print('    + Log10-evidence: {:.5f}'.format(self.logEvidence / np.log(10)), '- Parameter values:', x)
         return -self.logEvidence
 
+    # -------------------------------------------------------------------------------------------- simulate
+    def simulate(self, x, t=None, density=False):
+        """Probability (density) of observation values `x` under the posterior of time stamp `t` (or the time-averaged
+        posterior for t=None), reference: core.py:567-602 -- prob[i] = sum_g pdf(x[i] | g) * post[g].
+
+        On the device this is ONE evidence-only forward pass over the pseudo series `x` whose transition program
+        restores `post` before every step (the RESET operator of the Independent model, transitionModels.py:339-360):
+        the evidence increment of step i is exactly sum_g pdf(x[i] | g) * post[g], so no extra kernel is needed."""
+        om = self.observationModel
+        if om.segmentLength > 1:
+            raise NotImplementedError('Method "simulate" is only available for observation models with '
+                                      'segment length 1.')
+        seq = np.asarray(self.posteriorSequence, dtype=float)
+        if seq.ndim < 2 or seq.size == 0:
+            raise PostProcessingError('Cannot simulate observations as the posterior sequence has not yet been '
+                                      'computed. Run complete fit.')
+        if t is None:
+            post = np.sum(seq, axis=0) / len(seq)
+        else:
+            stamps = list(self.formattedTimestamps)
+            if t not in stamps:
+                raise PostProcessingError('Supplied time ({}) does not exist in data or is out of range.'.format(t))
+            post = seq[stamps.index(t)]
+        eng = self._engine()
+        x = np.asarray(x, dtype=float)
+        n = len(x)
+        G = int(np.prod(self.gridSize))
+        nCols = 1 if x.ndim == 1 else int(x.shape[1])
+        kind = getattr(om, 'deviceKind', KIND_TABLE)
+        if type(om).pdf is not ObservationModel.pdf:
+            kind = KIND_TABLE
+        plan = eng.plan(self.marginalGrid, self.latticeConstant, kind, 1, nCols)
+        table = None
+        if kind == KIND_TABLE:
+            table = np.array([np.asarray(om.pdf(self.grid, [xi]), dtype=float).ravel() for xi in x])
+        base = eng.to_device(post.reshape(-1))
+        always = np.array([[_tm.ALWAYS[0], _tm.ALWAYS[1], _tm.ALWAYS[0], _tm.ALWAYS[1]]], dtype=np.int32)
+        program = _engine.Program(eng, [dict(kind=_tm.OP_RESET, axis=0, param=np.ones(1),
+                                             radius=np.zeros(1, dtype=np.int32), window=always)], 1)
+        prob = np.zeros(n)
+        lo = 0
+        while lo < n:  # one pass; a value with zero probability ends a pass (core.py:388-400) and starts the next one
+            m = n - lo
+            local, logE = eng.zeros((1, m)), eng.zeros(1)
+            alive = eng.zeros(1, dtype=torch.int32)
+            eng.run('forward', plan, _engine.F_EVIDENCE_ONLY, T=m, B=1,
+                    data=eng.to_device(x[lo:].reshape(m, nCols)), prior=base, reset_base=base,
+                    lik_table=None if table is None else eng.to_device(table[lo:]), program=program,
+                    log_evidence=logE, local_evidence=local, alive=alive)
+            got = eng.to_host(local)[0] / np.prod(self.latticeConstant)
+            if int(eng.to_host(alive)[0]) == 1:
+                prob[lo:] = got
+                break
+            dead = int(np.flatnonzero(~(got > 0))[0])
+            prob[lo:lo + dead] = got[:dead]
+            lo += dead + 1
+        if not density:
+            prob /= np.sum(prob)
+        return prob
+
     # ------------------------------------------------------------------------------------------- accessors
     def _parameterIndex(self, name):
         names = list(self.observationModel.parameterNames)

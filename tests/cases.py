@@ -448,7 +448,39 @@ def syn_online_mixed(bl):  # C5 in miniature: GRW pair sweep + RegimeSwitch swee
     return S
 
 
+# ----------------------------------------------------------------------------- simulate (core.py:567-602)
+def _with_queries(S, queries):
+    """`extract` evaluates S.simulate(x, t, density) for every (x, t, density) listed here."""
+    S.simulateQueries = queries
+    return S
+
+
+def sim_coal_poisson(bl):  # predictive distribution of yearly accident counts from the coal-mining fit
+    S = bl.Study(silent=True)
+    S.loadExampleData(silent=True)
+    S.set(bl.om.Poisson('accident_rate', bl.oint(0, 6, 200)),
+          bl.tm.GaussianRandomWalk('sigma', 0.2, target='accident_rate'), silent=True)
+    S.fit(silent=True)
+    counts = np.arange(12)
+    return _with_queries(S, [(counts, 1855, False), (counts, 1940, True), (counts, None, False),
+                             (np.array([3, 3, 0, 40, 1]), None, True)])
+
+
+def sim_hyper_gauss_2d(bl):  # model-averaged posterior of a HyperStudy on a 2-D grid
+    S = syn_hyper_gauss_2d(bl)
+    xs = np.linspace(-4, 4, 33)
+    return _with_queries(S, [(xs, None, True), (xs, 17, False),
+                             (np.array([0.5, 1e3, -0.25, -1e3, 2.]), 30, True)])  # +-1e3: the pdf is exactly zero
+
+
+def sim_online_static(bl):  # stored history of an OnlineStudy
+    S = ref_online_static(bl)
+    xs = np.linspace(-1, 7, 17)
+    return _with_queries(S, [(xs, 3, True), (xs, None, False)])
+
+
 CASES = {f.__name__: f for f in [
+    sim_coal_poisson, sim_hyper_gauss_2d, sim_online_static,
     ref_tm_static, ref_tm_grw, ref_tm_changepoint, ref_tm_regimeswitch, ref_tm_independent, ref_tm_notequal,
     ref_tm_nested,
     ref_om_bernoulli, ref_om_poisson, ref_om_gaussian, ref_om_laplace, ref_om_gaussianmean, ref_om_whitenoise,
@@ -499,6 +531,8 @@ def extract(S):
     """Raw result arrays of a fitted study (works for the reference and for the product)."""
     out = {'logEvidence': _arr(S.logEvidence)}
     name = type(S).__name__
+    for k, (x, t, density) in enumerate(getattr(S, 'simulateQueries', [])):
+        out['simulate_%d' % k] = _arr(S.simulate(x, t=t, density=density))
     if name == 'OnlineStudy':
         out['posteriorSequence'] = _arr(S.posteriorSequence)
         out['posteriorMeanValues'] = _arr(S.posteriorMeanValues)
