@@ -970,6 +970,11 @@ class OnlineStudy(HyperStudy):
     All hypotheses -- every hyper-parameter combination of every added transition model -- live in ONE device
     batch: their programs are concatenated and masked per hypothesis, the per-hypothesis posteriors stay resident
     in HBM between `step` calls, and each `step` is one batched kernel launch plus O(#hypotheses) host arithmetic.
+
+    Under torch.distributed (one process per GPU) the hypotheses are dealt round-robin over the ranks
+    (distributed.py): every rank calls `step` with the same data point and ends up with identical evidences and
+    distributions; `marginalizedPosterior`, `parameterPosterior` and `transitionModelPosterior` are then COLLECTIVE
+    reads (all-reduce / all-gather), to be made by all ranks together.
     """
 
     def __init__(self, storeHistory=False, silent=False, engine=None):
@@ -1066,9 +1071,15 @@ class OnlineStudy(HyperStudy):
                 ops.append(full)
             row += count
         G = int(np.prod(self.gridSize))
-        dev = dict(eng=eng, plan=plan, kind=kind, nCols=nCols, G=G, H=H,
-                   program=_engine.Program(eng, ops, H), state=eng.empty((H, G)), step=eng.zeros(H),
-                   alive=eng.zeros(H, dtype=torch.int32), mixed=eng.empty(G), tmPost=None,
+        # one process per GPU: hypothesis h lives on rank h % world (distributed.py); a single process owns them all
+        from . import distributed as dist
+        rows = dist.shard_rows(H)
+        Hr = len(rows)
+        for op in ops:
+            op['param'], op['radius'], op['window'] = op['param'][rows], op['radius'][rows], op['window'][rows]
+        dev = dict(eng=eng, plan=plan, kind=kind, nCols=nCols, G=G, H=H, rows=rows, Hr=Hr,
+                   program=_engine.Program(eng, ops, Hr), state=eng.empty((Hr, G)), step=eng.zeros(Hr),
+                   alive=eng.zeros(Hr, dtype=torch.int32), mixed=eng.empty(G), tmPost=None,
                    prior=eng.to_device(np.asarray(self._computePrior(silent=False), dtype=float).reshape(-1)),
                    resetBase=None)
         if usesReset:
@@ -1126,10 +1137,14 @@ class OnlineStudy(HyperStudy):
         flags = _engine.F_EVIDENCE_ONLY | _engine.F_SAVE_STATE
         if not self.firstStep:
             flags |= _engine.F_INIT_STATE | _engine.F_TRANSITION_FIRST
-        eng.run('forward', plan, flags, T=1, B=H, data=eng.to_device(segment), prior=dev['prior'],
-                reset_base=dev['resetBase'], lik_table=likTable, program=dev['program'], init_state=dev['state'],
-                log_evidence=dev['step'], alive=dev['alive'], final_state=dev['state'])
-        inc = eng.to_host(dev['step'])  # log n_i per hypothesis (+ log prod(latticeConstant) on the first step)
+        if dev['Hr'] > 0:
+            eng.run('forward', plan, flags, T=1, B=dev['Hr'], data=eng.to_device(segment), prior=dev['prior'],
+                    reset_base=dev['resetBase'], lik_table=likTable, program=dev['program'],
+                    init_state=dev['state'], log_evidence=dev['step'], alive=dev['alive'], final_state=dev['state'])
+        # log n_i per hypothesis (+ log prod(latticeConstant) on the first step); with several ranks this all-gather
+        # of H doubles is the only per-step exchange
+        from . import distributed as dist
+        inc = dist.gather_dealt(eng, dev['step'], H)
 
         # O(H) bookkeeping of core.py:2171-2215
         weights = np.zeros(H)
@@ -1186,7 +1201,7 @@ class OnlineStudy(HyperStudy):
         if dev is not None:
             eng = dev['eng']
             d['_checkpoint'] = dict(state=eng.to_host(dev['state']).copy(), weights=np.array(dev.get('weights')),
-                                    H=dev['H'], G=dev['G'])
+                                    H=dev['H'], G=dev['G'], rows=np.array(dev['rows']))
         return d
 
     def __setstate__(self, d):
@@ -1200,6 +1215,9 @@ class OnlineStudy(HyperStudy):
             dev = self._dev
             if (dev['H'], dev['G']) != (ck['H'], ck['G']):
                 raise ConfigurationError('Checkpoint does not match the models of this study.')
+            if not np.array_equal(ck.get('rows', np.arange(ck['H'])), dev['rows']):
+                raise ConfigurationError('Checkpoint was written by a different rank / world size: each rank resumes '
+                                         'the hypotheses it owned.')
             dev['state'].copy_(dev['eng'].to_device(ck['state']))
             dev['weights'] = ck['weights']
             dev['mixedValid'] = False
@@ -1214,7 +1232,13 @@ class OnlineStudy(HyperStudy):
             return None
         if not dev.get('mixedValid'):
             eng = dev['eng']
-            eng.mix(dev['plan'], dev['state'], eng.to_device(dev['weights']), dev['H'], dev['G'], dev['mixed'])
+            from . import distributed as dist
+            if dev['Hr'] > 0:
+                eng.mix(dev['plan'], dev['state'], eng.to_device(dev['weights'][dev['rows']]), dev['Hr'], dev['G'],
+                        dev['mixed'])
+            else:
+                dev['mixed'].zero_()
+            dist.reduce_sum(eng, dev['mixed'])  # per-rank weighted row sums -> the mixture over all hypotheses
             dev['mixedHost'] = eng.to_host(dev['mixed']).reshape(self.gridSize)
             dev['mixedValid'] = True
         return dev['mixedHost']
@@ -1229,7 +1253,8 @@ class OnlineStudy(HyperStudy):
         dev = self._dev
         if dev is None:
             return None
-        flat = dev['eng'].to_host(dev['state'])
+        from . import distributed as dist
+        flat = dist.gather_dealt(dev['eng'], dev['state'], dev['H'])
         out, row = [], 0
         for count in self.tmCounts:
             out.append(flat[row:row + count].reshape([count] + self.gridSize))

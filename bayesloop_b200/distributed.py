@@ -11,6 +11,11 @@ scaling efficiency at 2 GPUs).  Every rank runs its own waves with NO per-step c
   * all-reduce(max) of the per-rank reference log-weight, local re-base by exp(m_r - M), then
     all-reduce(sum) of the running average [T x G] over NCCL / NVLink                          -- core.py:1339-1340
 
+OnlineStudy shards its hypotheses the same way (row h of the concatenated hypothesis list -> rank h % world): every
+rank filters its own rows of the [H x G] state; per step one all-gather of the H evidence increments (H doubles)
+keeps the O(H) bookkeeping of core.py:2171-2215 identical on all ranks, and the marginalised posterior is an
+all-reduce(sum) of the per-rank weighted row sums [G] when somebody reads it.
+
 Backend is NCCL for CUDA engines (fp64 sums over NVSwitch) and gloo for the CPU test harness.
 """
 import math
@@ -52,6 +57,24 @@ def gather_rows(eng, logE, alive, Ball):
         outE[rows] = host[0, :len(rows)]
         outA[rows] = host[1, :len(rows)]
     return outE, outA.astype(np.int64)
+
+
+def gather_dealt(eng, mine, total):
+    """All-gather arrays whose FIRST axis is dealt round-robin over the ranks (`shard_rows`) and return the whole
+    array in global row order.  `mine`: this rank's rows as a tensor on the engine's device, shape [n_r, ...]."""
+    rank, size = world()
+    if size == 1:
+        return eng.to_host(mine)
+    width = -(-int(total) // size)
+    send = torch.zeros((width,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+    send[:mine.shape[0]] = mine
+    recv = [torch.empty_like(send) for _ in range(size)]
+    td.all_gather(recv, send)
+    out = np.empty((int(total),) + tuple(mine.shape[1:]), dtype=eng.to_host(send[:0]).dtype)
+    for r, block in enumerate(recv):
+        rows = shard_rows(total, r, size)
+        out[rows] = eng.to_host(block[:len(rows)])
+    return out
 
 
 def reduce_sum(eng, tensor):

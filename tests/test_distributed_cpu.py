@@ -1,5 +1,7 @@
-"""N > 1 path on CPU: two gloo ranks shard a HyperStudy's combinations, run them through the CPU oracle engine and
-merge (all-gather of evidences, max + sum all-reduce of the running average).  Result must equal the golden."""
+"""N > 1 path on CPU: two gloo ranks shard a HyperStudy's combinations (or an OnlineStudy's hypotheses), run them
+through the CPU oracle engine and merge (all-gather of evidences, max + sum all-reduce of the running average; for the
+online study an all-gather of the evidence increments per step and a sum all-reduce of the mixture).  Result must
+equal the golden of the unsharded reference run."""
 import os
 import socket
 import sys
@@ -23,7 +25,8 @@ def _worker(rank, world, port, name, out_dir):
     from conftest import ORACLE_SO
     engine.set_default_engine(engine.Engine(ORACLE_SO, 'cpu'))
     S, got = parity.run_case(name, bl)
-    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), shard=np.array(S.sweepStats['rows']), **got)
+    shard = S._dev['rows'] if type(S).__name__ == 'OnlineStudy' else S.sweepStats['rows']
+    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), shard=np.array(shard), **got)
     td.destroy_process_group()
 
 
@@ -59,6 +62,34 @@ def test_two_ranks_changepoint_study_with_uneven_shards(tmp_path):
     ranks = _run(name, tmp_path)
     want = load_golden(name)
     assert [len(r['shard']) for r in ranks] == [55, 54] and ranks[1]['shard'][0] == 1
+    for r in ranks:
+        r.pop('shard')
+        parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)
+
+
+def test_two_ranks_online_study_shards_hypotheses(tmp_path):
+    """C5 in miniature over two ranks: 6 random-walk pairs + 3 regime-switch values + Independent = 10 hypotheses,
+    dealt round-robin; every rank ends up with the complete, identical results."""
+    import parity
+    from conftest import load_golden
+    name = 'syn_online_mixed'
+    ranks = _run(name, tmp_path)
+    want = load_golden(name)
+    assert [list(r['shard']) for r in ranks] == [[0, 2, 4, 6, 8], [1, 3, 5, 7, 9]]
+    for r in ranks:
+        r.pop('shard')
+        parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)
+
+
+def test_three_ranks_online_study_with_uneven_shards(tmp_path):
+    """The reference's own two-model online test (tests/test_onlinestudy.py:34-84): 4 + 1 hypotheses over three
+    ranks (2 + 2 + 1)."""
+    import parity
+    from conftest import load_golden
+    name = 'ref_online_2tm'
+    ranks = _run(name, tmp_path, world=3)
+    want = load_golden(name)
+    assert [list(r['shard']) for r in ranks] == [[0, 3], [1, 4], [2]]
     for r in ranks:
         r.pop('shard')
         parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)
