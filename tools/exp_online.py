@@ -1,5 +1,7 @@
 """Experiment: C5-shaped OnlineStudy (ScaledAR1 2-D grid n x n, 240 GRW-pair hypotheses + 15 RegimeSwitch + 1
-Independent = 256) -- seconds per step() through the public API.   python tools/exp_online.py [n=512] [steps=40]"""
+Independent = 256) -- seconds per step() through the public API.   python tools/exp_online.py [n=512] [steps=40]
+Several GPUs (hypotheses dealt over the ranks, one all-gather of 256 doubles per step):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/exp_online.py"""
 import os
 import sys
 import time
@@ -17,6 +19,10 @@ rng = np.random.default_rng(4)
 x = np.zeros(steps + 12)
 for i in range(1, len(x)):
     x[i] = 0.6 * x[i - 1] + rng.normal(0, 1.0)
+world = int(os.environ.get('WORLD_SIZE', '1'))
+if world > 1:
+    import torch.distributed as td
+    td.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0'))))
 eng = E.default_engine()
 S = bl.OnlineStudy(storeHistory=False, silent=True)
 S.setOM(bl.om.ScaledAR1('rho', bl.oint(-1, 1, n), 'sigma', bl.oint(0, 3, n)), silent=True)
@@ -32,5 +38,12 @@ for d in x[12:]:
     S.step(d)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / steps
-print('grid %dx%d, 256 hypotheses: %.2f ms per step -> %.3g cell-updates/s (kernel: %s)'
-      % (n, n, 1e3 * dt, 256.0 * n * n / dt, eng.last_kernel()), flush=True)
+if world > 1:
+    worst = torch.tensor([dt], device=eng.device, dtype=torch.float64)
+    td.all_reduce(worst, op=td.ReduceOp.MAX)
+    dt = float(worst.item())
+if int(os.environ.get('RANK', '0')) == 0:
+    print('grid %dx%d, 256 hypotheses on %d GPU(s): %.2f ms per step -> %.3g cell-updates/s (kernel: %s)'
+          % (n, n, world, 1e3 * dt, 256.0 * n * n / dt, eng.last_kernel()), flush=True)
+if world > 1:
+    td.destroy_process_group()
