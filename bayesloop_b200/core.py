@@ -1078,6 +1078,7 @@ class OnlineStudy(HyperStudy):
         for op in ops:
             op['param'], op['radius'], op['window'] = op['param'][rows], op['radius'][rows], op['window'][rows]
         dev = dict(eng=eng, plan=plan, kind=kind, nCols=nCols, G=G, H=H, rows=rows, Hr=Hr,
+                   separable=_rows_separable(ops, Hr),
                    program=_engine.Program(eng, ops, Hr), state=eng.empty((Hr, G)), step=eng.zeros(Hr),
                    alive=eng.zeros(Hr, dtype=torch.int32), mixed=eng.empty(G), tmPost=None,
                    prior=eng.to_device(np.asarray(self._computePrior(silent=False), dtype=float).reshape(-1)),
@@ -1137,6 +1138,8 @@ class OnlineStudy(HyperStudy):
         flags = _engine.F_EVIDENCE_ONLY | _engine.F_SAVE_STATE
         if not self.firstStep:
             flags |= _engine.F_INIT_STATE | _engine.F_TRANSITION_FIRST
+        if dev['separable']:
+            flags |= _engine.F_SEPARABLE_ROWS
         if dev['Hr'] > 0:
             eng.run('forward', plan, flags, T=1, B=dev['Hr'], data=eng.to_device(segment), prior=dev['prior'],
                     reset_base=dev['resetBase'], lik_table=likTable, program=dev['program'],
@@ -1462,6 +1465,31 @@ class OnlineStudy(HyperStudy):
 
     def getJointHyperParameterDistribution(self, names, plot=False, figure=None, subplot=111, **kwargs):
         raise NotImplementedError('This method is not available in "OnlineStudy".')  # core.py:2897-2898
+
+
+def _rows_separable(ops, rows):
+    """The promise behind BLG_F_SEPARABLE_ROWS (include/blgrid.h) for the step index -1 that OnlineStudy hands to
+    its models: in every row the active operators are GaussianRandomWalks on distinct axes, optionally followed by
+    one RegimeSwitch, or a single reset (Independent).  Such a row needs one pass over its cells and two sums, which
+    is what lets the engine tile a step over the whole GPU."""
+    for r in range(rows):
+        active = []
+        for op in ops:
+            lo, hi = int(op['window'][r][0]), int(op['window'][r][1])
+            if not (lo <= -1 < hi):
+                continue
+            if op['kind'] == _tm.OP_GRW and not (op['param'][r] > 0 and op['radius'][r] > 0):
+                continue  # a random walk of zero width is the identity (transitionModels.py:110-113)
+            active.append((op['kind'], op['axis']))
+        kinds = [k for k, _ in active]
+        if kinds == [_tm.OP_RESET]:
+            continue
+        if kinds and kinds[-1] == _tm.OP_REGIME:
+            active = active[:-1]
+        axes = [ax for k, ax in active if k == _tm.OP_GRW]
+        if len(axes) != len(active) or len(set(axes)) != len(axes):
+            return False
+    return True
 
 
 class _ResetShim:

@@ -37,6 +37,12 @@ int fail(const char *fmt, const char *detail = "") {
 
 inline int even_up(int x) { return (x + 1) & ~1; }
 
+// The tiled OnlineStudy step (online2d.cuh) is opt-in (BLG_ONLINE2D=1) until it has been through the B200 parity run.
+inline bool online2d_enabled() {
+    const char *e = getenv("BLG_ONLINE2D");
+    return e && atoi(e) != 0;
+}
+
 constexpr int kMiscDoubles = 384;  // reduction scratch (128) + params (16) + radius/window ints (40) + 2 mbarriers
                                    // + per-warp partial sums of the fast 1-D kernels (192)
 constexpr size_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
@@ -745,6 +751,37 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
         if (PassKernel k = fwd_fast1d_entry(M, lay.nt)) return launch_resident(k, a, lay, grid, st, "fwd_fast1d");
     }
     a.halo = 0;
+    {   // one OnlineStudy step on a large 2-D grid: tiles x hypotheses over the whole GPU (online2d.cuh)
+        const uint32_t need = BLG_F_SEPARABLE_ROWS | BLG_F_EVIDENCE_ONLY | BLG_F_INIT_STATE | BLG_F_TRANSITION_FIRST |
+                              BLG_F_SAVE_STATE;
+        if (in->T == 1 && pl->dev.ndim == 2 && (flags & need) == need && online2d_enabled() && in->B <= 65535 &&
+            (getenv("BLG_ONLINE2D_SMALL") || !resident_layout(pl, in->prog, false, false, a, lay))) {
+            int r0 = 0, r1 = 0;
+            bool ok = true;
+            for (int k = 0; k < in->prog.n_ops; ++k) {
+                if (in->prog.kind[k] == BLG_OP_NOTEQUAL) ok = false;
+                if (in->prog.kind[k] == BLG_OP_GRW) {
+                    int &r = in->prog.axis[k] == 0 ? r0 : r1;
+                    if (in->prog.max_radius[k] > r) r = in->prog.max_radius[k];
+                }
+            }
+            O2Launch L;
+            if (ok && online2d_plan(pl->dev.n0, pl->dev.n1, r0, r1, &L)) {
+                const size_t doubles = (size_t)in->B * pl->dev.G + (size_t)in->B * L.tilesY * L.tilesX * 2;
+                double *scratch = nullptr;
+                CUDA_TRY(cudaMallocAsync(&scratch, doubles * sizeof(double), st));
+                if (getenv("BLG_VERBOSE"))
+                    fprintf(stderr, "[blgrid] online2d: %lld hypotheses x %d x %d tiles, %zu B smem/CTA, radii <= %d / %d\n",
+                            (long long)in->B, L.tilesY, L.tilesX, L.smemBytes, r0, r1);
+                const int rc = online2d_run(a, L, scratch, st);
+                g_launches += 2;
+                g_last_kernel = "online2d";
+                if (rc != 0) return fail("online2d launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+                CUDA_TRY(cudaFreeAsync(scratch, st));
+                return 0;
+            }
+        }
+    }
     {
         int C = 0, m0 = 16;
         const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, false, false, a, lay);

@@ -36,4 +36,14 @@ PassKernel bwd_cluster2d_entry(bool prof, int m0);
 // layout parameters of cluster2d.cuh: threads, rows per axis-0 item, cells per axis-1 item, cells per thread
 void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad);
 
+// tiled OnlineStudy step (online2d.cuh): 64 x 64 tiles x hypotheses, T = 1, rows promised separable by the caller
+// (BLG_F_SEPARABLE_ROWS).  online2d_plan: false when tile + halo do not fit in shared memory; scratch holds
+// B * G + B * tiles * 2 doubles; online2d_run returns a cudaError_t (0 = launched K7 and K8).
+struct O2Launch {
+    int tilesY, tilesX, P, inRowsMax, w0len, w1len;
+    size_t smemBytes;
+};
+bool online2d_plan(int n0, int n1, int r0max, int r1max, O2Launch *L);
+int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStream_t st);
+
 }  // namespace blg

@@ -28,6 +28,7 @@ F_ACCUMULATE = 1 << 4
 F_RAW_ALPHA = 1 << 6  # forward rows may stay unnormalised (a backward pass follows)
 F_RAW_POSTERIOR = 1 << 7  # backward rows may stay unnormalised; row_scale[b][t] receives the normalising factor
 F_NORMALIZE_ROWS = 1 << 5
+F_SEPARABLE_ROWS = 1 << 8  # caller's promise about the active operators of every row (include/blgrid.h)
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int32)

@@ -67,10 +67,15 @@ enum blg_flags {
     BLG_F_RAW_ALPHA = 1u << 6,        /* forward: the rows of alpha_seq may be left UNNORMALISED (each row scaled */
                                       /* by a positive factor): valid only as the input of blg_backward, which is */
                                       /* scale-free per row (core.py:436-441 renormalises alpha*beta)             */
-    BLG_F_RAW_POSTERIOR = 1u << 7     /* backward: the smoothed rows may be left unnormalised; row_scale[b][t]    */
+    BLG_F_RAW_POSTERIOR = 1u << 7,    /* backward: the smoothed rows may be left unnormalised; row_scale[b][t]    */
                                       /* (required) receives the factor that normalises row t of combo b (1.0 if  */
                                       /* the implementation normalised the row itself).  blg_accumulate applies   */
                                       /* row_scale when it is given; blg_finalize(NORMALIZE_ROWS) normalises B = 1 */
+    BLG_F_SEPARABLE_ROWS = 1u << 8    /* forward, caller's promise about the program: in every row the operators    */
+                                      /* that are active at the steps of this call are GRWs on distinct axes,      */
+                                      /* optionally followed by ONE REGIME, or a single RESET.  Lets an              */
+                                      /* OnlineStudy step (T = 1, core.py:2157-2175) run tiled over the whole GPU;  */
+                                      /* a hint only -- results do not depend on it                                 */
 };
 
 /* Static description of the grid and the observation model (host pointers; copied by blg_plan_create). */

@@ -5,6 +5,8 @@ C ABI, against (1) the golden vectors of the unmodified reference, (2) the CPU o
 Tolerances (BASELINE.json north_star: 1e-6 relative in fp64): log-evidences 1e-9 relative; posterior grids 1e-6
 relative with an absolute floor of 1e-12 x the per-time-step maximum (cells far in the tails carry rounding noise of
 different summation orders)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -319,3 +321,69 @@ def test_online_study_checkpoint_resume_on_device(use_cuda, tmp_path):
             C.step(d)
     assert C.logEvidence == A.logEvidence
     np.testing.assert_array_equal(C.marginalizedPosterior, A.marginalizedPosterior)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tiled OnlineStudy step (bayesloop_b200/csrc/online2d.cuh): opt-in (BLG_ONLINE2D=1) until it has been through a B200
+# parity run; these tests switch it on themselves and are collected when BLG_TEST_ONLINE2D=1.
+online2d = pytest.mark.skipif(os.environ.get('BLG_TEST_ONLINE2D') != '1',
+                              reason='tiled online step is opt-in: set BLG_TEST_ONLINE2D=1')
+
+
+def _online_big(bl, engine, n0=150, n1=130, steps=6):
+    rng = np.random.default_rng(31)
+    x = np.zeros(steps + 1)
+    for i in range(1, len(x)):
+        x[i] = 0.55 * x[i - 1] + rng.normal()
+    S = bl.OnlineStudy(storeHistory=False, silent=True, engine=engine)
+    S.setOM(bl.om.ScaledAR1('rho', bl.oint(-1, 1, n0), 'sigma', bl.oint(0, 3, n1)), silent=True)
+    S.add('normal', bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s1', bl.cint(0, 0.12, 3), target='rho'),
+                                                  bl.tm.GaussianRandomWalk('s2', bl.cint(0, 0.2, 2), target='sigma')))
+    S.add('bounded', bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s3', [0.05, 0.1], target='sigma'),
+                                                   bl.tm.RegimeSwitch('q', -6)))
+    S.add('chaotic', bl.tm.RegimeSwitch('p', bl.cint(-8, -3, 3)))
+    S.add('indep', bl.tm.Independent())
+    S.add('static', bl.tm.Static())
+    for d in x:
+        S.step(d)
+    return S
+
+
+@online2d
+@pytest.mark.gpu
+def test_online2d_tiled_step_matches_cpu_oracle(cuda_engine, oracle_engine, monkeypatch):
+    """150 x 130 grid (3 x 3 tiles, ragged right and bottom), random walks on either / both axes, random walk +
+    RegimeSwitch, RegimeSwitch alone, Independent (reset) and Static in one batch, against the CPU oracle."""
+    import contextlib
+    import io
+    import bayesloop_b200 as bl
+    monkeypatch.setenv('BLG_ONLINE2D', '1')
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = _online_big(bl, cuda_engine)
+        assert got._dev['separable']
+        assert cuda_engine.last_kernel() == 'online2d'
+        want = _online_big(bl, oracle_engine)
+    np.testing.assert_allclose(got.logEvidence, want.logEvidence, rtol=1e-10)
+    for a, b in zip(got.logEvidenceList, want.logEvidenceList):
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(got.transitionModelDistribution, want.transitionModelDistribution, rtol=1e-8)
+    np.testing.assert_allclose(got.localTransitionModelDistribution, want.localTransitionModelDistribution, rtol=1e-8)
+    gm, wm = got.marginalizedPosterior, want.marginalizedPosterior
+    assert np.all(np.abs(gm - wm) <= 1e-7 * np.abs(wm) + 1e-13 * wm.max())
+    for a, b in zip(got.parameterPosterior, want.parameterPosterior):
+        top = b.reshape(len(b), -1).max(axis=1).reshape(-1, 1, 1)
+        assert np.all(np.abs(a - b) <= 1e-7 * np.abs(b) + 1e-13 * top)
+
+
+@online2d
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['ref_online_static', 'ref_online_2tm', 'syn_online_mixed'])
+def test_online2d_on_golden_cases(name, use_cuda, monkeypatch):
+    """The reference's own online tests (tests/test_onlinestudy.py) forced through the tiled kernels on their small
+    grids (one mostly masked tile per hypothesis)."""
+    import bayesloop_b200 as bl
+    monkeypatch.setenv('BLG_ONLINE2D', '1')
+    monkeypatch.setenv('BLG_ONLINE2D_SMALL', '1')
+    S, got = parity.run_case(name, bl)
+    assert use_cuda.last_kernel() == 'online2d'
+    parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)

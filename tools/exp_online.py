@@ -45,5 +45,11 @@ if world > 1:
 if int(os.environ.get('RANK', '0')) == 0:
     print('grid %dx%d, 256 hypotheses on %d GPU(s): %.2f ms per step -> %.3g cell-updates/s (kernel: %s)'
           % (n, n, world, 1e3 * dt, 256.0 * n * n / dt, eng.last_kernel()), flush=True)
+post = S.marginalizedPosterior  # collective read with several ranks
+if int(os.environ.get('RANK', '0')) == 0:
+    # fingerprints for comparing kernel families (BLG_ONLINE2D=1 vs the stream kernels) on the same stream
+    print('logE %.12f  mean rho %.12f  mean sigma %.12f  P(normal) %.12f'
+          % (S.logEvidence, S.getCurrentParameterMeanValue('rho'), S.getCurrentParameterMeanValue('sigma'),
+             S.getCurrentTransitionModelProbability('normal')), flush=True)
 if world > 1:
     td.destroy_process_group()
