@@ -37,10 +37,10 @@ int fail(const char *fmt, const char *detail = "") {
 
 inline int even_up(int x) { return (x + 1) & ~1; }
 
-// The tiled OnlineStudy step (online2d.cuh) is opt-in (BLG_ONLINE2D=1) until it has been through the B200 parity run.
+// The tiled OnlineStudy step (online2d.cuh) is the default for large 2-D grids; BLG_ONLINE2D=0 returns to the stream kernels.
 inline bool online2d_enabled() {
     const char *e = getenv("BLG_ONLINE2D");
-    return e && atoi(e) != 0;
+    return !e || atoi(e) != 0;
 }
 
 constexpr int kMiscDoubles = 384;  // reduction scratch (128) + params (16) + radius/window ints (40) + 2 mbarriers

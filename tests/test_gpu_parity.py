@@ -5,8 +5,6 @@ C ABI, against (1) the golden vectors of the unmodified reference, (2) the CPU o
 Tolerances (BASELINE.json north_star: 1e-6 relative in fp64): log-evidences 1e-9 relative; posterior grids 1e-6
 relative with an absolute floor of 1e-12 x the per-time-step maximum (cells far in the tails carry rounding noise of
 different summation orders)."""
-import os
-
 import numpy as np
 import pytest
 
@@ -324,10 +322,8 @@ def test_online_study_checkpoint_resume_on_device(use_cuda, tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# tiled OnlineStudy step (bayesloop_b200/csrc/online2d.cuh): opt-in (BLG_ONLINE2D=1) until it has been through a B200
-# parity run; these tests switch it on themselves and are collected when BLG_TEST_ONLINE2D=1.
-online2d = pytest.mark.skipif(os.environ.get('BLG_TEST_ONLINE2D') != '1',
-                              reason='tiled online step is opt-in: set BLG_TEST_ONLINE2D=1')
+# tiled OnlineStudy step (bayesloop_b200/csrc/online2d.cuh): the default for 2-D grids beyond shared memory
+# (BLG_ONLINE2D=0 returns to the stream kernels; BLG_ONLINE2D_SMALL=1 forces it onto grids that would fit).
 
 
 def _online_big(bl, engine, n0=150, n1=130, steps=6):
@@ -349,8 +345,6 @@ def _online_big(bl, engine, n0=150, n1=130, steps=6):
     return S
 
 
-@online2d
-@pytest.mark.gpu
 def test_online2d_tiled_step_matches_cpu_oracle(cuda_engine, oracle_engine, monkeypatch):
     """150 x 130 grid (3 x 3 tiles, ragged right and bottom), random walks on either / both axes, random walk +
     RegimeSwitch, RegimeSwitch alone, Independent (reset) and Static in one batch, against the CPU oracle."""
@@ -375,8 +369,6 @@ def test_online2d_tiled_step_matches_cpu_oracle(cuda_engine, oracle_engine, monk
         assert np.all(np.abs(a - b) <= 1e-7 * np.abs(b) + 1e-13 * top)
 
 
-@online2d
-@pytest.mark.gpu
 @pytest.mark.parametrize('name', ['ref_online_static', 'ref_online_2tm', 'syn_online_mixed'])
 def test_online2d_on_golden_cases(name, use_cuda, monkeypatch):
     """The reference's own online tests (tests/test_onlinestudy.py) forced through the tiled kernels on their small
