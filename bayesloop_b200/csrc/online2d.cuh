@@ -44,7 +44,17 @@ struct O2Lik {
     }
 };
 
+// 8-byte asynchronous global->shared copy (LDGSTS): the loads of a thread are all in flight at once instead of one
+// load -> store round trip per row (the r1k capture: half of K7's stall samples sit on the STS behind the tile loads)
+struct AsyncCopy {
+    __device__ __forceinline__ void operator()(double *dst, const double *src) const {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    }
+};
+
 // shared memory (doubles): in[inRowsMax][P] | mid[kTH][P] | W0[w0len] | W1[w1len] | reduction scratch [4 * kMaxWarps]
+// ASYNC: tile loads through cp.async (opt-in, BLG_ONLINE2D_ASYNC=1: written after the last GPU run of round 1)
+template <bool ASYNC>
 __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const PassArgs a, const O2Geom geo) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
@@ -113,7 +123,12 @@ __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const Pa
         if (!fits) {
             s2 = NAN;
         } else {
-            o2::load_phase(t, src, in, tid, nt);
+            if (ASYNC) {
+                o2::load_phase(t, src, in, tid, nt, AsyncCopy());
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            } else {
+                o2::load_phase(t, src, in, tid, nt);
+            }
             if (R0 > 0) {
                 build_weights(W0, o2::padded_taps(R0, o2::kM0), sig0, R0, rs);
             } else {
@@ -124,6 +139,7 @@ __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const Pa
             } else {
                 for (int j = tid; j < o2::kM1; j += nt) W1[j] = j == 0 ? 1.0 : 0.0;
             }
+            if (ASYNC) asm volatile("cp.async.wait_group 0;" ::: "memory");  // the weights were built behind the loads
             __syncthreads();
             o2::conv0_phase(t, in, mid, W0, tid, nt);
             __syncthreads();

@@ -1,4 +1,6 @@
 // online2d_inst.cu -- tiled OnlineStudy step (online2d.cuh): layout + launch of K7 / K8
+#include <cstdlib>
+
 #include "kernels.h"
 #include "online2d.cuh"
 
@@ -26,10 +28,12 @@ int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStre
     geo.w1len = L.w1len;
     geo.scratch = scratch;
     geo.partial = scratch + (size_t)a.B * a.pb.G;
-    cudaError_t e = cudaFuncSetAttribute(online2d_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes);
+    const char *env = getenv("BLG_ONLINE2D_ASYNC");
+    void (*tile)(const PassArgs, const O2Geom) = (env && atoi(env) != 0) ? online2d_tile_kernel<true> : online2d_tile_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes);
     if (e != cudaSuccess) return (int)e;
     const unsigned tiles = (unsigned)(L.tilesY * L.tilesX);
-    online2d_tile_kernel<<<(unsigned)a.B * tiles, o2::kThreads, L.smemBytes, st>>>(a, geo);
+    tile<<<(unsigned)a.B * tiles, o2::kThreads, L.smemBytes, st>>>(a, geo);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     long long chunks = (a.pb.G + 256LL * 8 - 1) / (256LL * 8);  // 8 cells per thread

@@ -44,13 +44,19 @@ struct Tile {
 
 // Phase L: the tile with its halo (R0 rows above / below, R1 columns left / right, reflected at the grid edges; tiles
 // that stick out of the grid read reflected cells too -- finite values that the epilogue masks) -> in[inRows][P].
-BLG_HD void load_phase(const Tile &t, const double *src, double *in, int tid, int nt) {
+// `copy(dst, src)` moves one cell: a plain load + store, or an asynchronous global->shared copy in the kernel.
+struct PlainCopy {
+    BLG_HD void operator()(double *dst, const double *src) const { *dst = *src; }
+};
+
+template <class Copy = PlainCopy>
+BLG_HD void load_phase(const Tile &t, const double *src, double *in, int tid, int nt, Copy copy = Copy()) {
     const int rows = t.inRows(), cols = t.inCols();
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;  // one row per warp: coalesced, no integer division
     for (int i = warp; i < rows; i += nw) {
         const double *line = src + (long long)reflect(t.r0 - t.R0 + i, t.n0) * t.n1;
         double *row = in + i * t.P;
-        for (int j = lane; j < cols; j += 32) row[j] = line[reflect(t.c0 - t.R1 + j, t.n1)];
+        for (int j = lane; j < cols; j += 32) copy(row + j, line + reflect(t.c0 - t.R1 + j, t.n1));
     }
 }
 
