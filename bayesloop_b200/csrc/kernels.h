@@ -40,6 +40,7 @@ void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad);
 // (BLG_F_SEPARABLE_ROWS).  online2d_plan: false when tile + halo do not fit in shared memory; scratch holds
 // B * G + B * tiles * 2 doubles; online2d_run returns a cudaError_t (0 = launched K7 and K8).
 struct O2Launch {
+    int TH;  // rows of a tile: 64 (512 threads, one CTA per SM) or 32 (256 threads, two CTAs per SM; BLG_ONLINE2D_TH=32)
     int tilesY, tilesX, P, inRowsMax, w0len, w1len;
     size_t smemBytes;
 };

@@ -53,9 +53,12 @@ struct AsyncCopy {
 };
 
 // shared memory (doubles): in[inRowsMax][P] | mid[kTH][P] | W0[w0len] | W1[w1len] | reduction scratch [4 * kMaxWarps]
-// ASYNC: tile loads through cp.async (opt-in, BLG_ONLINE2D_ASYNC=1: written after the last GPU run of round 1)
-template <bool ASYNC>
-__global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const PassArgs a, const O2Geom geo) {
+// ASYNC: tile loads through cp.async (opt-in, BLG_ONLINE2D_ASYNC=1).  TH / NT: rows of a tile and threads per CTA --
+// 64 / 512 (one CTA per SM) is the configuration that went through the B200 parity run; 32 / 256 (opt-in,
+// BLG_ONLINE2D_TH=32) halves shared memory and registers per CTA so that two CTAs share an SM and one tile loads while
+// the other convolves.  Both opt-in variants were written after the last GPU run of round 1.
+template <bool ASYNC, int TH, int NT>
+__global__ void __launch_bounds__(NT, TH == 64 ? 1 : 2) online2d_tile_kernel(const PassArgs a, const O2Geom geo) {
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
     const int tiles = geo.tilesY * geo.tilesX;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const Pa
     const int ty = tile / geo.tilesX, tx = tile - ty * geo.tilesX;
     double *in = sm;
     double *mid = in + (size_t)geo.inRowsMax * geo.P;
-    double *W0 = mid + (size_t)o2::kTH * geo.P;
+    double *W0 = mid + (size_t)TH * geo.P;
     double *W1 = W0 + geo.w0len;
     RedScratch rs;
     rs.buf = W1 + geo.w1len;
@@ -99,10 +102,10 @@ __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const Pa
         }
     }
 
-    o2::Tile t;
+    o2::Tile<TH> t;
     t.n0 = pb.n0;
     t.n1 = pb.n1;
-    t.r0 = ty * o2::kTH;
+    t.r0 = ty * TH;
     t.c0 = tx * o2::kTW;
     t.R0 = R0;
     t.R1 = R1;

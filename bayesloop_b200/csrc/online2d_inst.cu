@@ -7,13 +7,15 @@
 namespace blg {
 
 bool online2d_plan(int n0, int n1, int r0max, int r1max, O2Launch *L) {
-    L->tilesY = (n0 + o2::kTH - 1) / o2::kTH;
+    const char *env = getenv("BLG_ONLINE2D_TH");
+    L->TH = (env && atoi(env) == 32) ? 32 : o2::kTH;
+    L->tilesY = (n0 + L->TH - 1) / L->TH;
     L->tilesX = (n1 + o2::kTW - 1) / o2::kTW;
     L->P = (o2::kTW + 2 * r1max) | 1;
-    L->inRowsMax = o2::kTH + 2 * r0max;
+    L->inRowsMax = L->TH + 2 * r0max;
     L->w0len = o2::padded_taps(r0max, o2::kM0);
     L->w1len = o2::padded_taps(r1max, o2::kM1);
-    const size_t doubles = (size_t)L->inRowsMax * L->P + (size_t)o2::kTH * L->P + L->w0len + L->w1len + 4 * kMaxWarps;
+    const size_t doubles = (size_t)L->inRowsMax * L->P + (size_t)L->TH * L->P + L->w0len + L->w1len + 4 * kMaxWarps;
     L->smemBytes = doubles * sizeof(double);
     return L->smemBytes <= 232448;  // 227 KB opt-in maximum per CTA on sm_100
 }
@@ -29,11 +31,23 @@ int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStre
     geo.scratch = scratch;
     geo.partial = scratch + (size_t)a.B * a.pb.G;
     const char *env = getenv("BLG_ONLINE2D_ASYNC");
-    void (*tile)(const PassArgs, const O2Geom) = (env && atoi(env) != 0) ? online2d_tile_kernel<true> : online2d_tile_kernel<false>;
+    const bool async = env && atoi(env) != 0;
+    void (*tile)(const PassArgs, const O2Geom);
+    int threads = o2::kThreads;
+    if (L.TH == 32) {
+        tile = async ? online2d_tile_kernel<true, 32, 256> : online2d_tile_kernel<false, 32, 256>;
+        threads = 256;
+    } else {
+        tile = async ? online2d_tile_kernel<true, o2::kTH, o2::kThreads> : online2d_tile_kernel<false, o2::kTH, o2::kThreads>;
+    }
     cudaError_t e = cudaFuncSetAttribute(tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes);
     if (e != cudaSuccess) return (int)e;
+    if (L.TH == 32) {  // two CTAs per SM need the full shared-memory carveout
+        e = cudaFuncSetAttribute(tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+    }
     const unsigned tiles = (unsigned)(L.tilesY * L.tilesX);
-    tile<<<(unsigned)a.B * tiles, o2::kThreads, L.smemBytes, st>>>(a, geo);
+    tile<<<(unsigned)a.B * tiles, threads, L.smemBytes, st>>>(a, geo);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     long long chunks = (a.pb.G + 256LL * 8 - 1) / (256LL * 8);  // 8 cells per thread

@@ -3,7 +3,7 @@
 // (tid = threadIdx.x, a __syncthreads() between phases) and in the CPU emulation tools/emu/online2d_emu.cpp
 // (a loop over tid per phase), which checks it against a direct reflect convolution without a GPU.
 //
-// One tile = kTH x kTW cells of one hypothesis.  Reference semantics: the transition of OnlineStudy.step
+// One tile = TH x kTW cells of one hypothesis (TH = 64, or 32 for the two-CTAs-per-SM variant).  Reference semantics: the transition of OnlineStudy.step
 // (bayesloop/core.py:2166 -> transitionModels.py:96-115, gaussian_filter1d along each axis, mode='reflect') followed by
 // posterior = prior * likelihood (core.py:2170).
 #pragma once
@@ -17,7 +17,7 @@
 namespace blg {
 namespace o2 {
 
-constexpr int kTH = 64;        // rows of a tile
+constexpr int kTH = 64;        // rows of a tile (default; the functions below take the rows as template parameter TH)
 constexpr int kTW = 64;        // columns of a tile
 constexpr int kM0 = 16;        // rows per work item of the axis-0 convolution
 constexpr int kM1 = 8;         // cells per work item of the axis-1 convolution
@@ -33,12 +33,13 @@ BLG_HD int reflect(int i, int n) {  // NI_EXTEND_REFLECT for any index (d c b a 
 
 BLG_HD int padded_taps(int R, int M) { return (2 * R + 1 + M - 1) / M * M; }  // weight table length (zero padded)
 
+template <int TH = kTH>
 struct Tile {
     int n0, n1;  // grid
     int r0, c0;  // first row / column of the tile
     int R0, R1;  // radii of this hypothesis; 0 = no convolution along that axis (single tap of weight 1)
     int P;       // pitch (doubles) of the shared-memory buffers: odd, >= kTW + 2 * max R1 of the launch
-    BLG_HD int inRows() const { return kTH + 2 * R0; }
+    BLG_HD int inRows() const { return TH + 2 * R0; }
     BLG_HD int inCols() const { return kTW + 2 * R1; }
 };
 
@@ -49,8 +50,8 @@ struct PlainCopy {
     BLG_HD void operator()(double *dst, const double *src) const { *dst = *src; }
 };
 
-template <class Copy = PlainCopy>
-BLG_HD void load_phase(const Tile &t, const double *src, double *in, int tid, int nt, Copy copy = Copy()) {
+template <int TH, class Copy = PlainCopy>
+BLG_HD void load_phase(const Tile<TH> &t, const double *src, double *in, int tid, int nt, Copy copy = Copy()) {
     const int rows = t.inRows(), cols = t.inCols();
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;  // one row per warp: coalesced, no integer division
     for (int i = warp; i < rows; i += nw) {
@@ -101,23 +102,25 @@ BLG_HD void conv_valid(const double *src, double *dst, const double *W, int taps
     }
 }
 
-// Phase A: axis-0 convolution of every column of the haloed tile: in[inRows][P] -> mid[kTH][P] (inCols columns).
-BLG_HD void conv0_phase(const Tile &t, const double *in, double *mid, const double *W0, int tid, int nt) {
-    conv_valid<kM0>(in, mid, W0, 2 * t.R0 + 1, kTH, t.inRows(), t.P, t.inCols(), 1, t.P, 1, tid, nt);
+// Phase A: axis-0 convolution of every column of the haloed tile: in[inRows][P] -> mid[TH][P] (inCols columns).
+template <int TH>
+BLG_HD void conv0_phase(const Tile<TH> &t, const double *in, double *mid, const double *W0, int tid, int nt) {
+    conv_valid<kM0>(in, mid, W0, 2 * t.R0 + 1, TH, t.inRows(), t.P, t.inCols(), 1, t.P, 1, tid, nt);
 }
 
-// Phase B: axis-1 convolution of every row: mid[kTH][P] -> out[kTH][P] (kTW columns).
-BLG_HD void conv1_phase(const Tile &t, const double *mid, double *out, const double *W1, int tid, int nt) {
-    conv_valid<kM1>(mid, out, W1, 2 * t.R1 + 1, kTW, t.inCols(), 1, kTH, t.P, 1, t.P, tid, nt);
+// Phase B: axis-1 convolution of every row: mid[TH][P] -> out[TH][P] (kTW columns).
+template <int TH>
+BLG_HD void conv1_phase(const Tile<TH> &t, const double *mid, double *out, const double *W1, int tid, int nt) {
+    conv_valid<kM1>(mid, out, W1, 2 * t.R1 + 1, kTW, t.inCols(), 1, TH, t.P, 1, t.P, tid, nt);
 }
 
 // Phase E: v = transitioned prior of the cell (optionally clamped from below: RegimeSwitch, transitionModels.py:405),
 // u = v * likelihood -> dst (global, unnormalised); per-thread partial sums s1 += v, s2 += u.
 // `lik(gi, gj, g)` returns the likelihood of grid cell (gi, gj), g = gi * n1 + gj.
-template <class Lik>
-BLG_HD void epilogue_phase(const Tile &t, const double *out, double *dst, bool clamp, double limit, Lik lik, int tid, int nt,
+template <int TH, class Lik>
+BLG_HD void epilogue_phase(const Tile<TH> &t, const double *out, double *dst, bool clamp, double limit, Lik lik, int tid, int nt,
                            double &s1, double &s2) {
-    for (int e = tid; e < kTH * kTW; e += nt) {
+    for (int e = tid; e < TH * kTW; e += nt) {
         const int i = e / kTW, j = e - i * kTW;
         const int gi = t.r0 + i, gj = t.c0 + j;
         if (gi < t.n0 && gj < t.n1) {
@@ -134,10 +137,10 @@ BLG_HD void epilogue_phase(const Tile &t, const double *out, double *dst, bool c
 
 // Hypotheses without a convolution (Static, RegimeSwitch alone, Independent / reset): the same epilogue straight from
 // global memory.  reset != nullptr: v = reset[g] * scale (transitionModels.py:350-359), else v = src[g].
-template <class Lik>
-BLG_HD void pointwise_phase(const Tile &t, const double *src, const double *reset, double scale, double *dst, bool clamp,
+template <int TH, class Lik>
+BLG_HD void pointwise_phase(const Tile<TH> &t, const double *src, const double *reset, double scale, double *dst, bool clamp,
                             double limit, Lik lik, int tid, int nt, double &s1, double &s2) {
-    for (int e = tid; e < kTH * kTW; e += nt) {
+    for (int e = tid; e < TH * kTW; e += nt) {
         const int i = e / kTW, j = e - i * kTW;
         const int gi = t.r0 + i, gj = t.c0 + j;
         if (gi < t.n0 && gj < t.n1) {

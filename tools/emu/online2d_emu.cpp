@@ -1,5 +1,5 @@
 // CPU emulation of the tiled OnlineStudy step (bayesloop_b200/csrc/online2d.cuh): the per-thread phases of
-// online2d_phases.h are run for tid = 0 .. kThreads-1 with a barrier between the phases (exactly what the kernel does
+// online2d_phases.h are run for tid = 0 .. NT-1 with a barrier between the phases (exactly what the kernel does
 // with __syncthreads()), tile by tile, and compared with a direct whole-grid computation: reflect correlation along
 // axis 0, then axis 1 (scipy.ndimage.gaussian_filter1d semantics), clamp, x likelihood, sums.
 // TEST INFRASTRUCTURE: g++ -O2 -std=c++17 tools/emu/online2d_emu.cpp -o /tmp/online2d_emu && /tmp/online2d_emu
@@ -42,6 +42,7 @@ struct Case {
     int mode;  // 0 convolution, 1 pointwise (state), 2 pointwise reset
 };
 
+template <int TH, int NT>
 static int run(const Case &c, unsigned seed) {
     std::mt19937_64 rng(seed);
     std::uniform_real_distribution<double> U(0.0, 1.0);
@@ -83,9 +84,9 @@ static int run(const Case &c, unsigned seed) {
 
     // ---- emulation of the kernel, tile by tile
     const int r0max = R0 + 3, r1max = R1 + 2;  // the launch-wide maxima are larger than this hypothesis' radii
-    const int P = (kTW + 2 * r1max) | 1, inRowsMax = kTH + 2 * r0max;
-    std::vector<double> in((size_t)inRowsMax * P), mid((size_t)kTH * P), got(G, -1.0);
-    const int tilesY = (n0 + kTH - 1) / kTH, tilesX = (n1 + kTW - 1) / kTW;
+    const int P = (kTW + 2 * r1max) | 1, inRowsMax = TH + 2 * r0max;
+    std::vector<double> in((size_t)inRowsMax * P), mid((size_t)TH * P), got(G, -1.0);
+    const int tilesY = (n0 + TH - 1) / TH, tilesX = (n1 + kTW - 1) / kTW;
     auto likf = [&](int gi, int gj, long long g) {
         if (g != (long long)gi * n1 + gj) std::abort();
         return lik[g];
@@ -93,22 +94,22 @@ static int run(const Case &c, unsigned seed) {
     double s1 = 0.0, s2 = 0.0;
     for (int ty = 0; ty < tilesY; ++ty)
         for (int tx = 0; tx < tilesX; ++tx) {
-            Tile t{n0, n1, ty * kTH, tx * kTW, R0, R1, P};
+            Tile<TH> t{n0, n1, ty * TH, tx * kTW, R0, R1, P};
             const double poison = std::nan("");
             for (auto &x : in) x = poison;  // anything the phases read without having written it shows up as NaN
             for (auto &x : mid) x = poison;
             const bool clamp = c.clamp && c.mode != 2;
             if (c.mode != 0) {
-                for (int tid = 0; tid < kThreads; ++tid)
+                for (int tid = 0; tid < NT; ++tid)
                     pointwise_phase(t, state.data(), c.mode == 2 ? base.data() : nullptr, 0.37, got.data(), clamp, c.limit,
-                                    likf, tid, kThreads, s1, s2);
+                                    likf, tid, NT, s1, s2);
                 continue;
             }
-            for (int tid = 0; tid < kThreads; ++tid) load_phase(t, state.data(), in.data(), tid, kThreads);
-            for (int tid = 0; tid < kThreads; ++tid) conv0_phase(t, in.data(), mid.data(), W0.data(), tid, kThreads);
-            for (int tid = 0; tid < kThreads; ++tid) conv1_phase(t, mid.data(), in.data(), W1.data(), tid, kThreads);
-            for (int tid = 0; tid < kThreads; ++tid)
-                epilogue_phase(t, in.data(), got.data(), clamp, c.limit, likf, tid, kThreads, s1, s2);
+            for (int tid = 0; tid < NT; ++tid) load_phase(t, state.data(), in.data(), tid, NT);
+            for (int tid = 0; tid < NT; ++tid) conv0_phase(t, in.data(), mid.data(), W0.data(), tid, NT);
+            for (int tid = 0; tid < NT; ++tid) conv1_phase(t, mid.data(), in.data(), W1.data(), tid, NT);
+            for (int tid = 0; tid < NT; ++tid)
+                epilogue_phase(t, in.data(), got.data(), clamp, c.limit, likf, tid, NT, s1, s2);
         }
     double worst = 0.0;
     for (int g = 0; g < G; ++g) {
@@ -117,8 +118,8 @@ static int run(const Case &c, unsigned seed) {
     }
     const double e1 = std::fabs(s1 - S1) / S1, e2 = std::fabs(s2 - S2) / S2;
     const bool ok = worst < 1e-12 && e1 < 1e-12 && e2 < 1e-12;
-    std::printf("%s grid %3dx%-3d R %2d/%-2d mode %d clamp %d: max rel err %.2e, sums %.1e %.1e\n", ok ? "ok  " : "FAIL", n0, n1,
-                R0, R1, c.mode, (int)c.clamp, worst, e1, e2);
+    std::printf("%s tile %dx%d/%d threads grid %3dx%-3d R %2d/%-2d mode %d clamp %d: max rel err %.2e, sums %.1e %.1e\n",
+                ok ? "ok  " : "FAIL", TH, kTW, NT, n0, n1, R0, R1, c.mode, (int)c.clamp, worst, e1, e2);
     return ok ? 0 : 1;
 }
 
@@ -133,7 +134,8 @@ int main() {
     };
     int bad = 0;
     unsigned seed = 1;
-    for (const Case &c : cases) bad += run(c, seed++);
+    for (const Case &c : cases) bad += run<64, 512>(c, seed++);
+    for (const Case &c : cases) bad += run<32, 256>(c, seed++);  // the two-CTAs-per-SM configuration
     std::printf(bad ? "%d case(s) FAILED\n" : "all cases passed\n", bad);
     return bad ? 1 : 0;
 }
