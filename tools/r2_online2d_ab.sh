@@ -1,0 +1,14 @@
+#!/bin/bash
+# First GPU call of round 2 for the tiled online step (K7): parity tests and the C5-shaped timing under each of the
+# variants that were written after the last GPU run of round 1 (cp.async tile loads, 32-row tiles with two CTAs per SM).
+#   gpurun --timeout 300 -- 'bash tools/r2_online2d_ab.sh'
+mkdir -p gpurun_out
+for v in "BLG_ONLINE2D=0" "BLG_ONLINE2D=1" "BLG_ONLINE2D_ASYNC=1" "BLG_ONLINE2D_TH=32" "BLG_ONLINE2D_ASYNC=1 BLG_ONLINE2D_TH=32"; do
+    tag=$(echo "$v" | tr ' =' '__')
+    echo "== $v"
+    if [ "$v" != "BLG_ONLINE2D=0" ]; then
+        env $v timeout 90 python -m pytest tests/test_gpu_parity.py -m gpu -q -k online2d 2>&1 | tail -1
+    fi
+    env $v timeout 60 python tools/exp_online.py 512 60 2>&1 | tail -2 | tee gpurun_out/r2_online_$tag.log
+done
+# note: tests/test_gpu_parity.py sets BLG_ONLINE2D=1 itself; the other variables pass through to the library
