@@ -18,7 +18,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize('name', sorted(cases.CASES))
 def test_case_matches_reference_golden(name, use_cuda):
+    import os
     import bayesloop_b200 as bl
+    if name in cases.GPU_DEFERRED and os.environ.get('BLG_TEST_DEFERRED') != '1':
+        pytest.skip('added after the last GPU run of round 1 (cases.GPU_DEFERRED); set BLG_TEST_DEFERRED=1')
     before = use_cuda.launch_count()
     S, got = parity.run_case(name, bl)
     assert use_cuda.launch_count() > before, 'no CUDA kernel was launched'
