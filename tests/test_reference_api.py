@@ -253,3 +253,20 @@ def test_onlinestudy_without_history_refuses_past_queries(bl):
                  lambda: S.getHyperParameterMeanValues('s1'), lambda: S.getHyperParameterMeanValue(4, 's1')):
         with pytest.raises(bl.exceptions.PostProcessingError):
             call()
+
+
+# -------------------------------------------------------------------------------------- tests/test_fileio.py
+def test_save_load(bl, tmp_path):  # test_fileio.py:8-17 (the prior is a lambda: the study must still be storable)
+    S = bl.HyperStudy()
+    S.loadData(D5)
+    S.setOM(gauss20(bl))
+    S.setTM(bl.tm.Static())
+    S.fit()
+    bl.save(str(tmp_path / 'study.bl'), S)
+    R = bl.load(str(tmp_path / 'study.bl'))
+    assert type(R) is type(S)
+    assert R.logEvidence == S.logEvidence
+    np.testing.assert_array_equal(R.posteriorSequence, S.posteriorSequence)
+    np.testing.assert_array_equal(R.getParameterMeanValues('mean'), S.getParameterMeanValues('mean'))
+    R.fit()  # a loaded study is a working study
+    assert R.logEvidence == S.logEvidence
