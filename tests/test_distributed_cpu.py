@@ -93,3 +93,16 @@ def test_three_ranks_online_study_with_uneven_shards(tmp_path):
     for r in ranks:
         r.pop('shard')
         parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)
+
+
+def test_more_ranks_than_hypotheses(tmp_path):
+    """One hypothesis (Static) on two ranks: the second rank owns nothing and still reports the complete results."""
+    import parity
+    from conftest import load_golden
+    name = 'ref_online_static'
+    ranks = _run(name, tmp_path)
+    want = load_golden(name)
+    assert [list(r['shard']) for r in ranks] == [[0], []]
+    for r in ranks:
+        r.pop('shard')
+        parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)
