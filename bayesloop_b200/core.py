@@ -19,7 +19,7 @@ from . import engine as _engine
 from . import transitionModels as _tm
 from .exceptions import ConfigurationError, PostProcessingError
 from .helper import assignNestedItem, flatten, is_regular, recursiveIndex
-from .observationModels import KIND_GAUSSIAN_MEAN, KIND_TABLE, ObservationModel
+from .observationModels import KIND_GAUSSIAN_MEAN, KIND_POISSON, KIND_TABLE, ObservationModel
 from .preprocessing import movingWindow
 from .transitionModels import TransitionModel
 
@@ -72,6 +72,9 @@ class _Session:
             raise NotImplementedError('The engine supports observation models with one or two parameters.')
         if kind == KIND_GAUSSIAN_MEAN and self.nCols != 2:
             raise ConfigurationError('GaussianMean expects data rows of the form [value, std].')
+        if kind == KIND_POISSON and np.any(raw[np.isfinite(raw)] < 0):
+            # observationModels.py:502 takes the factorial of the count: math.factorial raises for negative values
+            raise ValueError('factorial() not defined for negative values')
         self.kind = kind
         self.plan = eng.plan(study.marginalGrid, study.latticeConstant, kind, om.segmentLength, self.nCols)
         self.data = eng.to_device(raw.reshape(len(raw), self.nCols), pinned=True)
@@ -373,6 +376,14 @@ class Study(object):
     def _fitSingle(self, forwardOnly, evidenceOnly, silent):
         """One combination of hyper-parameter values: forward filter, backward smoother, means (core.py:330-486)."""
         eng = self._engine()
+        if len(self.formattedData) == 0:
+            # fewer data points than one segment: the loops of core.py:372-470 do not run, the evidence is the
+            # constant of core.py:417 and every sequence is empty
+            self.logEvidence = float(np.log(np.prod(self.latticeConstant)))
+            self.localEvidence = np.empty(0)
+            self.posteriorSequence = np.empty([0] + list(self.gridSize))
+            self.posteriorMeanValues = np.empty([len(self.gridSize), 0])
+            return
         ses = _Session(self, eng)
         T, G = ses.T, ses.G
         values = self._unpackAllHyperParameters()

@@ -1,0 +1,179 @@
+"""TEST INFRASTRUCTURE ONLY (build container; needs /root/reference).  Differential probe: odd configurations and error
+paths are run through the unmodified reference and through the product (host logic -> C ABI -> CPU oracle) and the
+outcomes are compared -- same exception type, or same log-evidence / means / grids / distributions to 1e-8.
+
+    python oracle/differential_probe.py      # prints one line per probe: same | DIFF (reference vs product)
+
+Known, deliberate differences (documented in tests/test_host_logic.py and DESIGN.md): Poisson counts > 170 overflow the
+reference's factorial (OverflowError) where the product evaluates lgamma; an unknown `target` raises
+ConfigurationError instead of a bare ValueError; timestamps of the wrong length fall back to the integer range (the
+reference leaves them unset and crashes later).
+"""
+import contextlib
+import io
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+warnings.filterwarnings('ignore')
+
+import ref_shim  # noqa: E402
+
+
+def main():
+    import sympy.stats as stats
+    ref = ref_shim.import_reference()
+    from bayesloop_b200 import engine
+    engine.set_default_engine(engine.Engine(os.path.join(HERE, 'libblgrid_oracle.so'), 'cpu'))
+    import bayesloop_b200 as ours
+
+    def run(bl, build, attrs):
+        sink = io.StringIO()
+        with contextlib.redirect_stdout(sink), contextlib.redirect_stderr(sink), np.errstate(all='ignore'):
+            try:
+                S = build(bl)
+                return ('ok',) + tuple(np.asarray(a(S), dtype=float) for a in attrs)
+            except Exception as e:  # noqa: BLE001 -- the exception type is the thing compared
+                return ('exc', type(e).__name__, str(e)[:90])
+
+    def generic(cls, data, om, tm, ts=None, **kw):
+        def build(bl):
+            S = getattr(bl, cls)()
+            if ts is None:
+                S.loadData(np.array(data))
+            else:
+                S.loadData(np.array(data), timestamps=ts)
+            S.set(om(bl), tm(bl))
+            S.fit(**kw)
+            return S
+        return build
+
+    def online(data, models, prior=None, store=True):
+        def build(bl):
+            S = bl.OnlineStudy(storeHistory=store)
+            S.setOM(G2(bl))
+            for n, m in models(bl):
+                S.add(n, m)
+            if prior is not None:
+                S.setTransitionModelPrior(prior)
+            for d in data:
+                S.step(d)
+            return S
+        return build
+
+    def P(bl):
+        return bl.om.Poisson('r', bl.oint(0, 6, 40))
+
+    def G2(bl):
+        return bl.om.Gaussian('m', bl.cint(-2, 2, 16), 's', bl.oint(0, 2, 14))
+
+    def static(bl):
+        return bl.tm.Static()
+
+    def grw(bl, v=0.2):
+        return bl.tm.GaussianRandomWalk('s', v, target='r')
+
+    std = [lambda S: S.logEvidence, lambda S: S.posteriorMeanValues,
+           lambda S: np.concatenate([np.ravel(g) for g in S.marginalGrid])]
+    hyp = std + [lambda S: S.hyperParameterDistribution]
+    rng = np.random.default_rng(5)
+    xs = rng.normal(0.3, 0.8, 15)
+    xn = xs.copy()
+    xn[4] = np.nan
+    xc = rng.poisson(3, 15)
+    xb = rng.integers(0, 2, 15)
+    xg = np.stack([xs, 0.5 + rng.random(15)], axis=1)
+    ar = lambda bl: bl.om.ScaledAR1('rho', bl.oint(-1, 1, 20), 'sig', bl.oint(0, 2, 20))  # noqa: E731
+    serial2 = lambda bl: bl.tm.SerialTransitionModel(  # noqa: E731
+        bl.tm.Static(), bl.tm.ChangePoint('t1', 'all'), bl.tm.Static(), bl.tm.ChangePoint('t2', 'all'), bl.tm.Static())
+    nested = lambda bl: bl.tm.SerialTransitionModel(  # noqa: E731
+        bl.tm.GaussianRandomWalk('a', 0.2, target='r'), bl.tm.ChangePoint('t', 6),
+        bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('b', 0.4, target='r'), bl.tm.RegimeSwitch('p', -5)),
+        bl.tm.BreakPoint('u', 11), bl.tm.Independent())
+    probes = {
+        'single data point': (generic('Study', [3.], P, grw), std),
+        'two points, segment of two (T = 1)': (generic('Study', [0.3, -0.2], ar, static), std),
+        'one point, segment of two (T = 0)': (generic('Study', [0.3], ar, static), std),
+        'all data missing': (generic('Study', [np.nan] * 3, P, grw), std),
+        'grid of one cell': (generic('Study', [1., 2., 3.], lambda bl: bl.om.Poisson('r', bl.oint(0, 6, 1)), static), std),
+        'grid of two cells, wide walk': (generic('Study', [1., 2., 3.], lambda bl: bl.om.Poisson('r', bl.oint(0, 6, 2)),
+                                                 lambda bl: grw(bl, 5.0)), std),
+        'walk far wider than the grid': (generic('Study', [1., 2., 3.], P, lambda bl: grw(bl, 100.0)), std),
+        'negative Poisson count': (generic('Study', [1., -2., 3.], P, static), std),
+        'change-point at the last step': (generic('Study', [1., 2., 3., 4.], P, lambda bl: bl.tm.ChangePoint('t', 3)), std),
+        'change-point outside the data': (generic('Study', [1., 2., 3., 4.], P, lambda bl: bl.tm.ChangePoint('t', 17)), std),
+        'hyper: one-element list': (generic('HyperStudy', [1., 2., 3., 4.], P, lambda bl: grw(bl, [0.3])), std),
+        'hyper: evidenceOnly': (generic('HyperStudy', [1., 2., 3., 4.], P, lambda bl: grw(bl, [0.1, 0.3]), evidenceOnly=True),
+                                [lambda S: S.logEvidence, lambda S: S.hyperParameterDistribution]),
+        'hyper: forwardOnly, two hyper-parameters': (generic(
+            'HyperStudy', [1, 2, 3, 2, 5, 1], P,
+            lambda bl: bl.tm.CombinedTransitionModel(grw(bl, [0.1, 0.2, 0.3]), bl.tm.RegimeSwitch('p', [-7, -4])),
+            forwardOnly=True), hyp + [lambda S: S.localEvidence]),
+        'hyper: identical change-/break-points': (generic(
+            'HyperStudy', [1, 2, 1, 6, 7, 6], P,
+            lambda bl: bl.tm.SerialTransitionModel(bl.tm.Static(), bl.tm.ChangePoint('t1', [2, 3]), bl.tm.Static(),
+                                                   bl.tm.ChangePoint('t2', [3, 4]), bl.tm.Static())), []),
+        'changepoint study: all, 4 points': (generic('ChangepointStudy', [1., 2., 5., 6.],
+                                                     lambda bl: bl.om.Poisson('r', bl.oint(0, 8, 50)),
+                                                     lambda bl: bl.tm.ChangePoint('t', 'all')), hyp),
+        'changepoint study: two change-points, all': (generic('ChangepointStudy', [1, 2, 1, 6, 7, 6, 2, 1], P, serial2), hyp),
+        'serial: break-points on time stamps': (generic(
+            'HyperStudy', [1, 2, 1, 6, 7, 6, 2, 1], P,
+            lambda bl: bl.tm.SerialTransitionModel(grw(bl, [0.1, 0.4]), bl.tm.BreakPoint('b', [1903, 1905]), bl.tm.Static()),
+            ts=[1900 + i for i in range(8)]), hyp),
+        'serial: nested change-point, break-point, independent': (generic(
+            'Study', xc, lambda bl: bl.om.Poisson('r', bl.oint(0, 8, 60)), nested), std),
+        'random walk without target': (generic('Study', [1, 2, 3], P, lambda bl: bl.tm.GaussianRandomWalk('s', 0.1)), []),
+        'prior array of the wrong shape': (generic('Study', [1, 2, 3],
+                                                   lambda bl: bl.om.Poisson('r', bl.oint(0, 6, 40), prior=np.ones(7)), static), []),
+        'two data columns multiplied': (generic('Study', [[1, 2], [2, 3], [3, 1]], P, static), std),
+        'NotEqual on a 2-D grid': (generic('Study', xs, G2, lambda bl: bl.tm.NotEqual('q', -4)), std),
+        'online: missing data point': (online(xn, lambda bl: [('a', bl.tm.GaussianRandomWalk('s', [0.1, 0.2], target='m')),
+                                                               ('b', bl.tm.Static())]),
+                                       [lambda S: S.logEvidence, lambda S: S.marginalizedPosterior,
+                                        lambda S: S.transitionModelDistribution]),
+        'online: unnormalised model prior': (online(xs, lambda bl: [('a', bl.tm.RegimeSwitch('p', [-5, -3])),
+                                                                     ('b', bl.tm.Independent())], prior=[2., 1.]),
+                                             [lambda S: S.logEvidence, lambda S: S.transitionModelDistribution,
+                                              lambda S: S.localTransitionModelDistribution]),
+        'online: model prior of the wrong length': (online(xs, lambda bl: [('a', bl.tm.Static())], prior=[0.5, 0.5]), []),
+        'online: duplicate hyper-parameter names': (online(
+            xs, lambda bl: [('a', bl.tm.GaussianRandomWalk('s', 0.1, target='m')),
+                            ('b', bl.tm.GaussianRandomWalk('s', 0.2, target='s'))]), []),
+        'default grid + Jeffreys prior: Poisson': (generic('Study', xc, lambda bl: bl.om.Poisson('r'), static), std),
+        'default grids: Gaussian': (generic('Study', xs, lambda bl: bl.om.Gaussian('m', None, 's', None), static), std),
+        'default grids: Laplace': (generic('Study', xs, lambda bl: bl.om.Laplace('m', None, 'b', None), static), std),
+        'default grid: Bernoulli': (generic('Study', xb, lambda bl: bl.om.Bernoulli('p'), static), std),
+        'default grid: WhiteNoise': (generic('Study', xs, lambda bl: bl.om.WhiteNoise('s'), static), std),
+        'default grid: GaussianMean': (generic('Study', xg, lambda bl: bl.om.GaussianMean('m'), static), std),
+        'default grids: AR1': (generic('Study', xs, lambda bl: bl.om.AR1('rho', None, 'sig', None), static), std),
+        'default grids: ScaledAR1': (generic('Study', xs, lambda bl: bl.om.ScaledAR1('rho', None, 'sig', None), static), std),
+        'grid given as a number of points': (generic('Study', xc, lambda bl: bl.om.Poisson('r', 50), static), std),
+        'list of SymPy priors': (generic('Study', xs, lambda bl: bl.om.Gaussian(
+            'm', bl.cint(-2, 2, 20), 's', bl.oint(0, 2, 20),
+            prior=[stats.Normal('a', 0, 1), stats.Exponential('b', 1)]), static), std),
+    }
+    diffs = 0
+    for name, (build, attrs) in probes.items():
+        r, o = run(ref, build, attrs), run(ours, build, attrs)
+        if r[0] != o[0]:
+            same = False
+        elif r[0] == 'exc':
+            same = r[1] == o[1]
+        else:
+            same = all(x.shape == y.shape and np.allclose(x, y, rtol=1e-8, atol=1e-300 if x.ndim else 1e-12, equal_nan=True)
+                       for x, y in zip(r[1:], o[1:]))
+        diffs += not same
+        detail = '' if same else '   reference: %s | product: %s' % (r[:3] if r[0] == 'exc' else 'ok', o[:3] if o[0] == 'exc' else 'ok')
+        print('%-52s %s%s' % (name, 'same' if same else 'DIFF', detail))
+    print('%d probes, %d differ' % (len(probes), diffs))
+
+
+if __name__ == '__main__':
+    main()

@@ -69,3 +69,26 @@ def test_online_study_checkpoint_resume(use_oracle):
     np.testing.assert_array_equal(C.transitionModelDistribution, A.transitionModelDistribution)
     for a, c in zip(A.parameterPosterior, C.parameterPosterior):
         np.testing.assert_array_equal(a, c)
+
+
+def test_edge_cases_behave_like_the_reference(use_oracle):
+    """Probed against the unmodified reference in the build container (it cannot travel): a series shorter than one
+    segment gives empty sequences and logE = log(prod(latticeConstant)) (the loops of core.py:372-470 never run,
+    :417 still does); a negative Poisson count raises ValueError (math.factorial, observationModels.py:502)."""
+    import contextlib
+    import io
+    import bayesloop_b200 as bl
+    with contextlib.redirect_stdout(io.StringIO()):
+        S = bl.Study(silent=True)
+        S.loadData(np.array([0.3]), silent=True)
+        S.set(bl.om.ScaledAR1('rho', bl.oint(-1, 1, 20), 'sig', bl.oint(0, 2, 20)), bl.tm.Static(), silent=True)
+        S.fit(silent=True)
+        assert abs(S.logEvidence - (-4.702750514326955)) < 1e-12
+        assert S.posteriorSequence.shape == (0, 20, 20) and S.posteriorMeanValues.shape == (2, 0)
+        assert len(S.localEvidence) == 0
+
+        P = bl.Study(silent=True)
+        P.loadData(np.array([1., -2., 3.]), silent=True)
+        P.set(bl.om.Poisson('r', bl.oint(0, 6, 50)), bl.tm.Static(), silent=True)
+        with pytest.raises(ValueError):
+            P.fit(silent=True)
