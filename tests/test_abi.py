@@ -83,3 +83,30 @@ def test_ctypes_structs_match_the_header(tmp_path):
     got = [ctypes.sizeof(engine._Problem), ctypes.sizeof(engine._Program), ctypes.sizeof(engine._Inputs),
            ctypes.sizeof(engine._Outputs)]
     assert got == want
+
+
+def test_python_constants_match_the_header_enums():
+    """Flags, operator codes and observation-model codes are duplicated in the binding (engine.py,
+    transitionModels.py, observationModels.py): they must be the values of include/blgrid.h."""
+    from bayesloop_b200 import engine, observationModels as om, transitionModels as tm
+    text = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    enum = {}
+    for name, value in re.findall(r'\b(BLG_[A-Z0-9_]+)\s*=\s*([^,}\n]+)', text):
+        value = value.strip()
+        m = re.fullmatch(r'1u\s*<<\s*(\d+)', value)
+        enum[name] = 1 << int(m.group(1)) if m else int(value)
+    for py, c in (('F_EVIDENCE_ONLY', 'BLG_F_EVIDENCE_ONLY'), ('F_INIT_STATE', 'BLG_F_INIT_STATE'),
+                  ('F_TRANSITION_FIRST', 'BLG_F_TRANSITION_FIRST'), ('F_SAVE_STATE', 'BLG_F_SAVE_STATE'),
+                  ('F_ACCUMULATE', 'BLG_F_ACCUMULATE'), ('F_NORMALIZE_ROWS', 'BLG_F_NORMALIZE_ROWS'),
+                  ('F_RAW_ALPHA', 'BLG_F_RAW_ALPHA'), ('F_RAW_POSTERIOR', 'BLG_F_RAW_POSTERIOR'),
+                  ('F_SEPARABLE_ROWS', 'BLG_F_SEPARABLE_ROWS')):
+        assert getattr(engine, py) == enum[c], (py, c)
+    for py, c in (('OP_GRW', 'BLG_OP_GRW'), ('OP_REGIME', 'BLG_OP_REGIME'), ('OP_RESET', 'BLG_OP_RESET'),
+                  ('OP_NOTEQUAL', 'BLG_OP_NOTEQUAL')):
+        assert getattr(tm, py) == enum[c], (py, c)
+    for py, c in (('KIND_POISSON', 'BLG_OM_POISSON'), ('KIND_GAUSSIAN', 'BLG_OM_GAUSSIAN'),
+                  ('KIND_SCALED_AR1', 'BLG_OM_SCALED_AR1'), ('KIND_AR1', 'BLG_OM_AR1'),
+                  ('KIND_WHITE_NOISE', 'BLG_OM_WHITE_NOISE'), ('KIND_GAUSSIAN_MEAN', 'BLG_OM_GAUSSIAN_MEAN'),
+                  ('KIND_LAPLACE', 'BLG_OM_LAPLACE'), ('KIND_BERNOULLI', 'BLG_OM_BERNOULLI'), ('KIND_TABLE', 'BLG_OM_TABLE')):
+        assert getattr(om, py) == enum[c], (py, c)
+    assert engine.MAX_OPS == int(re.search(r'#define BLG_MAX_OPS (\d+)', text).group(1))
