@@ -821,6 +821,9 @@ class HyperStudy(Study):
                 Study.fit(self, forwardOnly=forwardOnly, evidenceOnly=evidenceOnly, silent=silent)
             return
 
+        if len(self.formattedData) == 0:
+            # the reference fails in its averaging step with this exception type (core.py:1372, np.amax of an empty array)
+            raise ValueError('zero-size series: fewer data points than one segment of the observation model')
         if not silent:
             print('+ Started new fit.')
             print('    + {} analyses to run.'.format(len(self.hyperGridValues)))
