@@ -1,5 +1,7 @@
 """Experiment: C4-shaped sweep (BASELINE.json configs[3] in miniature): Gaussian 2-D grid n x n, one change-point x
-GaussianRandomWalk on both parameters; B = cps * hyper^2 combos.   python tools/exp_c4.py [n=200] [T=300] [cps=10] [hyper=3]"""
+GaussianRandomWalk on both parameters; B = cps * hyper^2 combos.   python tools/exp_c4.py [n=200] [T=300] [cps=10] [hyper=3]
+Several GPUs (combos dealt over the ranks, merged over NCCL; strong scaling of the same B):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/exp_c4.py 200 300 40 4"""
 import os
 import sys
 import time
@@ -17,6 +19,10 @@ cps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 H = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 rng = np.random.default_rng(3)
 x = np.concatenate([rng.normal(-0.5, 1.0, T // 2), rng.normal(1.0, 1.0, T - T // 2)])
+world = int(os.environ.get('WORLD_SIZE', '1'))
+if world > 1:
+    import torch.distributed as td
+    td.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0'))))
 eng = E.default_engine()
 S = bl.HyperStudy(silent=True)
 S.loadData(x, silent=True)
@@ -36,7 +42,14 @@ for _ in range(3):
     res = S._executeSweep(sw)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / 3
+if world > 1:
+    worst = torch.tensor([dt], device=eng.device, dtype=torch.float64)
+    td.all_reduce(worst, op=td.ReduceOp.MAX)
+    dt = float(worst.item())
 B = cps * H * H
-print('grid %dx%d T=%d B=%d (%d change-points x %dx%d sigmas): %.1f ms per full fit -> %.3g cell-updates/s (kernel: %s), '
-      'best combo logE %.4f' % (n, n, T, B, cps, H, H, 1e3 * dt, 2.0 * B * T * n * n / dt, eng.last_kernel(),
-                                float(np.max(res[1]))), flush=True)
+if int(os.environ.get('RANK', '0')) == 0:
+    print('grid %dx%d T=%d B=%d (%d change-points x %dx%d sigmas) on %d GPU(s): %.1f ms per full fit -> %.3g cell-updates/s '
+          '(kernel: %s), best combo logE %.4f' % (n, n, T, B, cps, H, H, world, 1e3 * dt, 2.0 * B * T * n * n / dt,
+                                                  eng.last_kernel(), float(np.max(res[1]))), flush=True)
+if world > 1:
+    td.destroy_process_group()
