@@ -3,6 +3,8 @@
 # variants that were written after the last GPU run of round 1 (cp.async tile loads, 32-row tiles with two CTAs per SM).
 #   gpurun --timeout 300 -- 'bash tools/r2_online2d_ab.sh'
 mkdir -p gpurun_out
+# random operator programs, CUDA against the CPU oracle (tests/test_gpu_fuzz.py)
+BLG_TEST_FUZZ=150 timeout 240 python -m pytest tests/test_gpu_fuzz.py -m gpu -q 2>&1 | tail -3
 # cases added after the last GPU minute of round 1 (tests/cases.py: GPU_DEFERRED)
 BLG_TEST_DEFERRED=1 timeout 120 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "sympy or scipy or numpy" 2>&1 | tail -3
 for v in "BLG_ONLINE2D=0" "BLG_ONLINE2D=1" "BLG_ONLINE2D_ASYNC=1" "BLG_ONLINE2D_TH=32" "BLG_ONLINE2D_ASYNC=1 BLG_ONLINE2D_TH=32"; do
