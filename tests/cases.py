@@ -540,7 +540,14 @@ def sim_online_static(bl):  # stored history of an OnlineStudy
     return _with_queries(S, [(xs, 3, True), (xs, None, False)])
 
 
+def sim_scipy_gamma(bl):  # simulate with a plugin likelihood: the table of the queried values is built on the host
+    S = syn_hyper_scipy_gamma(bl)
+    xs = np.linspace(0.2, 6, 25)
+    return _with_queries(S, [(xs, None, True), (xs, 11, False)])
+
+
 CASES = {f.__name__: f for f in [
+    sim_scipy_gamma,
     sim_coal_poisson, sim_hyper_gauss_2d, sim_online_static,
     ref_om_sympy_1p, ref_om_sympy_2p, ref_om_scipy_1p, ref_om_scipy_2p, ref_om_numpy_1p, ref_om_numpy_2p,
     syn_hyper_scipy_gamma,
@@ -565,7 +572,7 @@ CASES = {f.__name__: f for f in [
 # their first run on the B200 is the first call of round 2 (tests/test_gpu_parity.py collects them when
 # BLG_TEST_DEFERRED=1, tools/r2_online2d_ab.sh sets it).  The kernels they reach (likelihood table + resident / cluster
 # kernels) are the ones every B >= 4 sweep already runs; only the combination "caller-supplied table" is new.
-GPU_DEFERRED = ('ref_om_sympy_1p', 'ref_om_sympy_2p', 'ref_om_scipy_1p', 'ref_om_scipy_2p', 'ref_om_numpy_1p',
+GPU_DEFERRED = ('sim_scipy_gamma', 'ref_om_sympy_1p', 'ref_om_sympy_2p', 'ref_om_scipy_1p', 'ref_om_scipy_2p', 'ref_om_numpy_1p',
                 'ref_om_numpy_2p', 'syn_hyper_scipy_gamma')
 
 # Values hard-coded in the reference's own test-suite / docs: name -> logEvidence
