@@ -59,6 +59,14 @@ def test_cuda_library_contains_sm100a_sass_with_bulk_copies():
     assert 'fwd_cluster2d_kernel' in out and 'bwd_cluster2d_kernel' in out
     for mnemonic in ('UCGABAR_ARV', 'UCGABAR_WAIT', 'STAS.128', 'SYNCS.ARRIVE.TRANS64'):
         assert mnemonic in out, mnemonic + ' missing from the SASS'
+    # tiled online step: both tile heights, the cp.async (LDGSTS) load variant, and no local memory in any of them
+    assert 'online2d_tile_kernel' in out and 'online2d_finish_kernel' in out
+    blocks = out.split('Function : ')
+    tiles = [b for b in blocks if b.startswith('_ZN3blg20online2d_tile_kernel')]
+    assert len(tiles) == 4
+    assert any('LDGSTS' in b for b in tiles)
+    for b in tiles:
+        assert 'DFMA' in b and ' LDL' not in b and ' STL' not in b, 'register spill in the tile kernel'
 
 
 def test_product_fails_loudly_without_cuda(monkeypatch):
