@@ -120,7 +120,8 @@ def draw_case(seed):
     stamps = None if (t0 == 0 or online) else np.arange(t0, t0 + len(data))
     if online:
         t0 = 0
-        models = [draw_leaf(rng, names, params, True, T, 0) for _ in range(int(rng.integers(1, 4)))]
+        models = [draw_tree(rng, names, params, True, T, 0, depth=1) if rng.random() < 0.4 else
+                  draw_leaf(rng, names, params, True, T, 0) for _ in range(int(rng.integers(1, 4)))]
     elif study == 'ChangepointStudy':
         tree = draw_changepoint_tree(rng, names, params, T, t0 + (1 if which == 'ar1' else 0))
     else:
