@@ -16,3 +16,7 @@ for v in "BLG_ONLINE2D=0" "BLG_ONLINE2D=1" "BLG_ONLINE2D_ASYNC=1" "BLG_ONLINE2D_
     env $v timeout 60 python tools/exp_online.py 512 60 2>&1 | tail -2 | tee gpurun_out/r2_online_$tag.log
 done
 # note: tests/test_gpu_parity.py sets BLG_ONLINE2D=1 itself; the other variables pass through to the library
+# one ncu capture of the tile kernel under the most aggressive variant (compare with profiles/r1k_ncu_online2d.json)
+BLG_ONLINE2D_ASYNC=1 BLG_ONLINE2D_TH=32 timeout 120 ncu --set full --clock-control none --import-source on -k regex:online2d_tile \
+    -s 20 -c 1 -f -o gpurun_out/r2_online2d_tile_async_th32 python tools/exp_online.py 512 30 > gpurun_out/r2_ncu_online2d.log 2>&1
+tail -2 gpurun_out/r2_ncu_online2d.log
