@@ -20,6 +20,20 @@ from .exceptions import ConfigurationError, PostProcessingError
 from .fileIO import load, save
 from .helper import cint, oint
 
+
+def _out_of_scope(name, where):
+    def stub(*args, **kwargs):
+        raise NotImplementedError('bayesloop_b200.{} is not part of this engine ({} of the reference is host-side '
+                                  'post-processing / symbolic set-up outside the accelerated path; DESIGN.md "Out of '
+                                  'scope").'.format(name, where))
+    stub.__name__ = name
+    return stub
+
+
+Parser = _out_of_scope('Parser', 'bayesloop/parser.py')
+getJeffreysPrior = _out_of_scope('getJeffreysPrior', 'bayesloop/jeffreys.py:17-68')
+computeJeffreysPriorAR1 = _out_of_scope('computeJeffreysPriorAR1', 'bayesloop/jeffreys.py:71-108')
+
 __all__ = ['Study', 'HyperStudy', 'ChangepointStudy', 'OnlineStudy', 'observationModels', 'om', 'transitionModels',
            'tm', 'cint', 'oint', 'ConfigurationError', 'PostProcessingError', 'save', 'load']
 __version__ = '0.1.0'

@@ -211,6 +211,27 @@ class Study(object):
     def setTM(self, T, silent=False):
         self.setTransitionModel(T, silent=silent)
 
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d['_engineOverride'] = None  # engines hold library handles and a device: not part of a saved study
+        return d
+
+    def _attachBackPointers(self):
+        """(Re-)attach the weak `study` back-pointer of every transition model of this study (dropped by pickling)."""
+        def walk(model):
+            if model is None:
+                return
+            model.study = weakref.proxy(self)
+            for sub in getattr(model, 'models', []):
+                walk(sub)
+        walk(self.transitionModel)
+        for model in getattr(self, 'transitionModels', []):
+            walk(model)
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._attachBackPointers()
+
     def set(self, *args, **kwargs):
         for key in kwargs:
             if key != 'silent':
@@ -417,6 +438,10 @@ class Study(object):
             self._warnZeroNorm(backward=(state == -1))
             self.logEvidence = -np.inf
             if not evidenceOnly:
+                # the reference leaves np.empty memory behind the step that died (core.py:399-400); what was computed up
+                # to there is exposed as distributions: rows stored raw (F_RAW_ALPHA / F_RAW_POSTERIOR) are normalised
+                if not forwardOnly:
+                    eng.finalize(ses.plan, seq, T, eng.empty((len(self.gridSize), T)), _engine.F_NORMALIZE_ROWS)
                 self.posteriorSequence = eng.to_host(seq).reshape([T] + self.gridSize)
             return
         if evidenceOnly:
@@ -1223,6 +1248,7 @@ class OnlineStudy(HyperStudy):
 
     def __setstate__(self, d):
         self.__dict__.update(d)
+        self._attachBackPointers()
 
     def _resume(self):
         """Re-create the device side of an unpickled study (no-op otherwise)."""
@@ -1519,3 +1545,30 @@ def _logsumexp(x):
     if not np.isfinite(top):
         return top
     return top + np.log(np.sum(np.exp(x - top)))
+
+
+def _guard_plot_arguments():
+    """The accessors keep the reference's signatures, including `plot=`; plotting (matplotlib) is outside this engine,
+    so `plot=True` raises instead of being silently ignored."""
+    import functools
+    import inspect
+
+    def guard(fn, position):
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            wanted = kwargs.get('plot', args[position] if len(args) > position else False)
+            if wanted:
+                raise NotImplementedError('{}(plot=True): plotting is not part of bayesloop_b200; the method returns '
+                                          'the arrays the reference would plot.'.format(fn.__name__))
+            return fn(*args, **kwargs)
+        return wrapper
+
+    for cls in (Study, HyperStudy, ChangepointStudy, OnlineStudy):
+        for name, fn in list(vars(cls).items()):
+            if inspect.isfunction(fn):
+                params = list(inspect.signature(fn).parameters)
+                if 'plot' in params:
+                    setattr(cls, name, guard(fn, params.index('plot')))
+
+
+_guard_plot_arguments()

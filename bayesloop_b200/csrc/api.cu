@@ -5,6 +5,7 @@
 // the per-hypothesis loop of OnlineStudy.step (core.py:2157-2175, :2195-2212).  No torch types cross this file; the
 // caller hands raw device pointers and a cudaStream_t.
 #include <atomic>
+#include <cfloat>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -37,10 +38,61 @@ int fail(const char *fmt, const char *detail = "") {
 
 inline int even_up(int x) { return (x + 1) & ~1; }
 
-// The tiled OnlineStudy step (online2d.cuh) is the default for large 2-D grids; BLG_ONLINE2D=0 returns to the stream kernels.
-inline bool online2d_enabled() {
-    const char *e = getenv("BLG_ONLINE2D");
-    return !e || atoi(e) != 0;
+// Dispatch / tuning options of a plan.  Resolved ONCE: blg_plan_create reads the BLG_* environment variables
+// (debugging aids of tools/), blg_plan_set_option overrides them by name; no call on the per-step path looks at the
+// process environment, so which kernel family runs is a property of the plan, not of process state.
+struct Opts {
+    int no_fast1d = 0;       // never take the fused 1-D kernels (fast1d.cuh / fast1d_ws.cuh)
+    int no_ws = 0;           // fused 1-D kernels: single-role variant instead of the warp-specialised one
+    int no_bulk = 0;         // no bulk-async (TMA) row copies
+    int no_lik_table = 0;    // evaluate the likelihood in the passes instead of one shared [T][G] table per call
+    int no_order = 0;        // ignore blg_program.order
+    int no_sm_assign = 0;    // ignore blg_program.sm_assign
+    int force_stream = 0;    // global-memory stream kernels even where the state fits on chip
+    int cluster2d = 0;       // cluster-resident 2-D kernels even where one SM's shared memory would do
+    int no_cluster2d = 0;    // never take the cluster-resident 2-D kernels
+    int cluster2d_c = 0;     // force the cluster size (2, 4, 8); 0 = largest that fits
+    int online2d = 1;        // tiled OnlineStudy step for 2-D grids beyond shared memory (0: stream kernels)
+    int online2d_small = 0;  // tiled OnlineStudy step also on grids that would fit in shared memory
+    int online2d_async = 1;  // tile loads through cp.async (0: LDG -> STS round trips)
+    int serpentine = 1;      // alternate the block -> combo mapping per wave of SMs
+    int verbose = 0;         // print the launch geometry to stderr
+    int ws_m = 0, ws_nt = 0; // warp-specialised 1-D kernels: force (cells per thread, threads); 0 = by grid size
+    char trace[256] = {0};   // per-CTA trace files <trace>.<kernel>.<n>.csv (debugging aid)
+};
+
+struct OptName {
+    const char *name, *env;
+    int Opts::*field;
+};
+const OptName kOptNames[] = {
+    {"no_fast1d", "BLG_NO_FAST1D", &Opts::no_fast1d},
+    {"no_ws", "BLG_NO_WS", &Opts::no_ws},
+    {"no_bulk", "BLG_NO_BULK", &Opts::no_bulk},
+    {"no_lik_table", "BLG_NO_LIK_TABLE", &Opts::no_lik_table},
+    {"no_order", "BLG_NO_ORDER", &Opts::no_order},
+    {"no_sm_assign", "BLG_NO_SM_ASSIGN", &Opts::no_sm_assign},
+    {"force_stream", "BLG_FORCE_STREAM", &Opts::force_stream},
+    {"cluster2d", "BLG_CLUSTER2D", &Opts::cluster2d},
+    {"no_cluster2d", "BLG_NO_CLUSTER2D", &Opts::no_cluster2d},
+    {"cluster2d_c", "BLG_CLUSTER2D_C", &Opts::cluster2d_c},
+    {"online2d", "BLG_ONLINE2D", &Opts::online2d},
+    {"online2d_small", "BLG_ONLINE2D_SMALL", &Opts::online2d_small},
+    {"online2d_async", "BLG_ONLINE2D_ASYNC", &Opts::online2d_async},
+    {"serpentine", "BLG_SERPENTINE", &Opts::serpentine},
+    {"verbose", "BLG_VERBOSE", &Opts::verbose},
+    {"ws_m", "BLG_WS_M", &Opts::ws_m},
+    {"ws_nt", "BLG_WS_NT", &Opts::ws_nt},
+};
+
+void opts_from_env(Opts &o) {
+    for (const OptName &n : kOptNames)
+        if (const char *e = getenv(n.env)) {
+            char *end = nullptr;
+            const long v = strtol(e, &end, 10);
+            o.*(n.field) = (end == e) ? 1 : (int)v;  // "BLG_X=" or "BLG_X=yes" switch a flag on
+        }
+    if (const char *e = getenv("BLG_TRACE")) snprintf(o.trace, sizeof o.trace, "%s", e);
 }
 
 constexpr int kMiscDoubles = 384;  // reduction scratch (128) + params (16) + radius/window ints (40) + 2 mbarriers
@@ -63,8 +115,9 @@ struct blg_plan {
     long long lik_cap;
     int *d_sm_state;  // per-SM arrival counters + per-combo claim flags (fast 1-D kernels with sm_assign)
     long long sm_state_cap;
-    int serpentine;
-    bool rows_raw;  // the last backward pass left its rows unnormalised (row_scale holds the factors)
+    double *d_o2;  // tiled OnlineStudy step: unnormalised cells [B][G] + per-tile partial sums, kept between steps
+    long long o2_cap;
+    Opts opt;
 };
 
 extern "C" {
@@ -102,8 +155,7 @@ int blg_plan_create(const blg_problem *p, blg_plan **out) {
         }
         cudaGetLastError();
     }
-    const char *env = getenv("BLG_SERPENTINE");
-    pl->serpentine = env ? atoi(env) : 1;
+    opts_from_env(pl->opt);
 
     // host tables (see lik_column in common.cuh)
     std::vector<double> h((size_t)(4 * n0 + 3 * n1), 0.0);
@@ -116,7 +168,9 @@ int blg_plan_create(const blg_problem *p, blg_plan **out) {
         switch (om) {
             case BLG_OM_POISSON:
                 A0[i] = x;
-                A1[i] = log(x);
+                // lambda == 0: the reference evaluates 0**k * exp(-0) / k! = (k == 0) (observationModels.py:502); with
+                // log(0) = -inf the device form k * log(lambda) would be 0 * -inf = NaN for a zero count
+                A1[i] = x == 0.0 ? -DBL_MAX : log(x);
                 useA[0] = useA[1] = true;
                 break;
             case BLG_OM_GAUSSIAN:
@@ -200,9 +254,20 @@ int blg_plan_create(const blg_problem *p, blg_plan **out) {
     pl->lik_cap = 0;
     pl->d_sm_state = nullptr;
     pl->sm_state_cap = 0;
-    pl->rows_raw = false;
+    pl->d_o2 = nullptr;
+    pl->o2_cap = 0;
     *out = pl;
     return 0;
+}
+
+int blg_plan_set_option(blg_plan *pl, const char *name, int64_t value) {
+    if (!pl || !name) return fail("null argument");
+    for (const OptName &n : kOptNames)
+        if (strcmp(n.name, name) == 0) {
+            pl->opt.*(n.field) = (int)value;
+            return 0;
+        }
+    return fail("unknown plan option: %s", name);
 }
 
 void blg_plan_destroy(blg_plan *pl) {
@@ -212,6 +277,7 @@ void blg_plan_destroy(blg_plan *pl) {
     if (pl->d_w) cudaFree(pl->d_w);
     if (pl->d_lik) cudaFree(pl->d_lik);
     if (pl->d_sm_state) cudaFree(pl->d_sm_state);
+    if (pl->d_o2) cudaFree(pl->d_o2);
     delete pl;
 }
 
@@ -245,7 +311,7 @@ int ensure_w(blg_plan *pl, long long count) {
 int prep_lik_table(blg_plan *pl, const blg_inputs *in, PassArgs &a, cudaStream_t st, int permM = 0, int permNC = 0) {
     const DevProblem &d = pl->dev;
     a.lik_pitch = d.G;
-    if (!permM && (d.om_kind == BLG_OM_TABLE || getenv("BLG_NO_LIK_TABLE"))) return 0;
+    if (!permM && (d.om_kind == BLG_OM_TABLE || pl->opt.no_lik_table)) return 0;
     const long long pitch = permM ? (long long)permM * permNC : (long long)d.G;
     const long long count = in->T * pitch;
     if (!permM && in->B < 4) return 0;
@@ -335,7 +401,7 @@ bool resident_layout(const blg_plan *pl, const blg_program &pg, bool backward, b
 // Fast path (fast1d.cuh): 1-D grid, program = one GaussianRandomWalk, halo <= n, one work item per thread.
 bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int M, PassArgs &a, Layout &lay) {
     const DevProblem &d = a.pb;  // om_kind is TABLE when the shared likelihood table is in use
-    if (getenv("BLG_NO_FAST1D")) return false;
+    if (pl->opt.no_fast1d) return false;
     if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
     const int halo = even_up(pg.max_radius[0] + 2 * M);
     const int items = (d.G + M - 1) / M;
@@ -372,7 +438,7 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int
 // warps (threads/32 - 1) cover the grid with M cells per thread.
 bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, PassArgs &a, Layout &lay, int &M) {
     const DevProblem &d = pl->dev;
-    if (getenv("BLG_NO_FAST1D") || getenv("BLG_NO_WS")) return false;
+    if (pl->opt.no_fast1d || pl->opt.no_ws) return false;
     if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
     int nt = 128;
     if (d.G <= 96 * 3) M = 3;
@@ -462,7 +528,7 @@ int launch_stream(PassKernel kernel, blg_plan *pl, PassArgs &a, Layout lay, long
     CUDA_TRY(cudaMallocAsync(&scratch, (size_t)grid * 2 * a.Gp * sizeof(double), st));
     a.scratch = scratch;
     a.use_bulk = 0;
-    if (getenv("BLG_VERBOSE"))
+    if (pl->opt.verbose)
         fprintf(stderr, "[blgrid] %s: grid %lld x %d threads, %zu B smem/CTA, tile %d doubles, scratch %.1f MB\n", name,
                 grid, lay.nt, lay.bytes, a.tile_doubles, grid * 2.0 * a.Gp * 8 / 1e6);
     kernel<<<(unsigned)grid, lay.nt, lay.bytes, st>>>(a);
@@ -478,9 +544,9 @@ int launch_stream(PassKernel kernel, blg_plan *pl, PassArgs &a, Layout lay, long
 bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags, bool backward, PassArgs &a, Layout &lay,
                       int &C, int &M0out) {
     const DevProblem &d = pl->dev;
-    if (d.ndim != 2 || getenv("BLG_NO_CLUSTER2D")) return false;
+    if (d.ndim != 2 || pl->opt.no_cluster2d) return false;
     if (flags & (BLG_F_INIT_STATE | BLG_F_SAVE_STATE | BLG_F_TRANSITION_FIRST | BLG_F_ACCUMULATE)) return false;
-    if (!stream2d_supports(pg.n_ops, pg.kind, pg.axis)) return false;
+    if (!cluster2d_supports(pg.n_ops, pg.kind, pg.axis)) return false;
     if (d.n1 % 2) return false;  // 16-byte aligned bands for the bulk-async copies
     int NT, M0, M1, cells, wpad;
     cluster2d_params(&NT, &M0, &M1, &cells, &wpad);
@@ -491,9 +557,9 @@ bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags,
             if (pg.max_radius[k] > r) r = pg.max_radius[k];
         }
     if (r1max + M1 > d.n1) return false;
-    const char *force = getenv("BLG_CLUSTER2D_C");
+    const int force = pl->opt.cluster2d_c;
     for (int c = 8; c >= 2; c /= 2) {
-        if (force && atoi(force) != c) continue;
+        if (force && force != c) continue;
         const int nb = (d.n0 + c - 1) / c;
         const int last = d.n0 - (c - 1) * nb;
         if (last < 1 || r0max > last) continue;
@@ -535,8 +601,8 @@ bool cluster2d_layout(const blg_plan *pl, const blg_program &pg, uint32_t flags,
     return false;
 }
 
-int launch_cluster(PassKernel kernel, const PassArgs &a, const Layout &lay, long long B, int C, cudaStream_t st,
-                   const char *name) {
+int launch_cluster(const blg_plan *pl, PassKernel kernel, const PassArgs &a, const Layout &lay, long long B, int C,
+                   cudaStream_t st, const char *name) {
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -557,7 +623,7 @@ int launch_cluster(PassKernel kernel, const PassArgs &a, const Layout &lay, long
             cudaGetLastError();
             return 1;
         }
-        if (getenv("BLG_VERBOSE"))
+        if (pl->opt.verbose)
             fprintf(stderr, "[blgrid] %s: %lld clusters x %d CTAs x %d threads, %zu B smem/CTA, band %d rows, halo %d rows, "
                             "%d clusters resident\n", name, B, C, lay.nt, lay.bytes, a.c2_nb, a.c2_h0, clusters);
     }
@@ -565,7 +631,7 @@ int launch_cluster(PassKernel kernel, const PassArgs &a, const Layout &lay, long
     long long *trace = nullptr;
     PassArgs a2 = a;
     const long long nblk = B * C;
-    if (getenv("BLG_TRACE")) {  // per-CTA phase cycle counters (forward kernel built with PROF)
+    if (pl->opt.trace[0]) {  // per-CTA phase cycle counters (forward kernel built with PROF)
         CUDA_TRY(cudaMalloc(&trace, (size_t)nblk * 8 * sizeof(long long)));
         CUDA_TRY(cudaMemset(trace, 0, (size_t)nblk * 8 * sizeof(long long)));
         a2.trace = trace;
@@ -579,7 +645,7 @@ int launch_cluster(PassKernel kernel, const PassArgs &a, const Layout &lay, long
         cudaFree(trace);
         static int seq = 0;
         char path[512];
-        snprintf(path, sizeof path, "%s.%s.%d.csv", getenv("BLG_TRACE"), name, seq++);
+        snprintf(path, sizeof path, "%s.%s.%d.csv", pl->opt.trace, name, seq++);
         if (FILE *f = fopen(path, "w")) {
             fprintf(f, "block,c0,c1,c2,c3,c4,c5,c6,c7\n");  // phase counters: see PROF in cluster2d.cuh
             for (long long i = 0; i < nblk; ++i) {
@@ -603,7 +669,7 @@ int prep_sm_assign(blg_plan *pl, const blg_inputs *in, PassArgs &a, long long &g
     a.sm_count = 0;
     a.sm_slots = 0;
     grid = in->B;
-    if (!pg.sm_assign || pg.sm_count != pl->num_sms || pg.sm_slots < 1 || getenv("BLG_NO_SM_ASSIGN")) return 0;
+    if (!pg.sm_assign || pg.sm_count != pl->num_sms || pg.sm_slots < 1 || pl->opt.no_sm_assign) return 0;
     if ((long long)pg.sm_count * pg.sm_slots < in->B) return 0;
     const long long need = pg.sm_count + in->B;
     if (need > pl->sm_state_cap) {
@@ -622,18 +688,15 @@ int prep_sm_assign(blg_plan *pl, const blg_inputs *in, PassArgs &a, long long &g
     return 0;
 }
 
-int fast_m(bool backward) {
-    const char *e = getenv(backward ? "BLG_FAST_M_BWD" : "BLG_FAST_M");
-    const int m = e ? atoi(e) : 9;
-    return (m == 5 || m == 7 || m == 9) ? m : 7;
-}
+constexpr int kFastM = 9;  // cells per thread of the single-role fused 1-D kernels (the one compiled fallback)
 
-int launch_resident(PassKernel kernel, const PassArgs &a, const Layout &lay, long long B, cudaStream_t st, const char *name) {
+int launch_resident(const blg_plan *pl, PassKernel kernel, const PassArgs &a, const Layout &lay, long long B, cudaStream_t st,
+                    const char *name) {
     g_last_kernel = name;
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
     // several CTAs (combos) must share an SM: ask for the full shared-memory carveout
     CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (getenv("BLG_VERBOSE")) {
+    if (pl->opt.verbose) {
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, lay.nt, lay.bytes);
         fprintf(stderr, "[blgrid] %s: grid %lld x %d threads, %zu B smem/CTA, %d CTA/SM, halo %d, bulk %d\n", name, B,
@@ -641,7 +704,7 @@ int launch_resident(PassKernel kernel, const PassArgs &a, const Layout &lay, lon
     }
     long long *trace = nullptr;
     PassArgs a2 = a;
-    if (getenv("BLG_TRACE")) {  // debugging aid: per-CTA {smid, combo, start, end} (globaltimer ns), dumped as CSV
+    if (pl->opt.trace[0]) {  // debugging aid: per-CTA {smid, combo, start, end} (globaltimer ns), dumped as CSV
         CUDA_TRY(cudaMalloc(&trace, (size_t)B * 4 * sizeof(long long)));
         CUDA_TRY(cudaMemset(trace, 0, (size_t)B * 4 * sizeof(long long)));
         a2.trace = trace;
@@ -656,7 +719,7 @@ int launch_resident(PassKernel kernel, const PassArgs &a, const Layout &lay, lon
         cudaFree(trace);
         static int seq = 0;
         char path[512];
-        snprintf(path, sizeof path, "%s.%s.%d.csv", getenv("BLG_TRACE"), name, seq++);
+        snprintf(path, sizeof path, "%s.%s.%d.csv", pl->opt.trace, name, seq++);
         if (FILE *f = fopen(path, "w")) {
             fprintf(f, "block,smid,combo,start_ns,end_ns\n");
             for (long long i = 0; i < B; ++i)
@@ -685,7 +748,7 @@ int fill_args(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32
     a.pg.param = pg.param;
     a.pg.radius = pg.radius;
     a.pg.window = pg.window;
-    a.order = getenv("BLG_NO_ORDER") ? nullptr : pg.order;
+    a.order = pl->opt.no_order ? nullptr : pg.order;
     a.T = in->T;
     a.B = in->B;
     a.prior = in->prior;
@@ -703,7 +766,7 @@ int fill_args(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32
     a.steps = pl->d_steps;
     a.flags = flags;
     a.num_sms = pl->num_sms;
-    a.serpentine = (pl->serpentine && in->B > pl->num_sms) ? 1 : 0;
+    a.serpentine = (pl->opt.serpentine && in->B > pl->num_sms) ? 1 : 0;
     if (pl->dev.om_kind == BLG_OM_TABLE && !in->lik_table) return fail("lik_table required for BLG_OM_TABLE");
     return 0;
 }
@@ -723,11 +786,10 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     if ((flags & BLG_F_SAVE_STATE) && !out->final_state) return fail("final_state missing");
     PassArgs a;
     memset(&a, 0, sizeof a);
-    pl->rows_raw = false;
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
     Layout lay;
-    const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
+    const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !pl->opt.no_bulk;
     {
         int wsM = 0;
         if (fast1d_ws_layout(pl, in->prog, false, a, lay, wsM)) {
@@ -737,25 +799,25 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
                 a.use_bulk = bulkOk ? 1 : 0;
                 long long grid = in->B;
                 if (prep_sm_assign(pl, in, a, grid, st)) return -1;
-                if (PassKernel k = fwd_fast1d_ws_entry(wsM, lay.nt)) return launch_resident(k, a, lay, grid, st, "fwd_fast1d_ws");
+                if (PassKernel k = fwd_fast1d_ws_entry(wsM, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "fwd_fast1d_ws");
                 return fail("warp-specialised forward kernel missing");
             }
         }
     }
     if (prep_lik_table(pl, in, a, st)) return -1;
-    const int M = fast_m(false);
+    const int M = kFastM;
     if (fast1d_layout(pl, in->prog, false, M, a, lay)) {
         a.use_bulk = bulkOk ? 1 : 0;
         long long grid = in->B;
         if (prep_sm_assign(pl, in, a, grid, st)) return -1;
-        if (PassKernel k = fwd_fast1d_entry(M, lay.nt)) return launch_resident(k, a, lay, grid, st, "fwd_fast1d");
+        if (PassKernel k = fwd_fast1d_entry(M, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "fwd_fast1d");
     }
     a.halo = 0;
     {   // one OnlineStudy step on a large 2-D grid: tiles x hypotheses over the whole GPU (online2d.cuh)
         const uint32_t need = BLG_F_SEPARABLE_ROWS | BLG_F_EVIDENCE_ONLY | BLG_F_INIT_STATE | BLG_F_TRANSITION_FIRST |
                               BLG_F_SAVE_STATE;
-        if (in->T == 1 && pl->dev.ndim == 2 && (flags & need) == need && online2d_enabled() && in->B <= 65535 &&
-            (getenv("BLG_ONLINE2D_SMALL") || !resident_layout(pl, in->prog, false, false, a, lay))) {
+        if (in->T == 1 && pl->dev.ndim == 2 && (flags & need) == need && pl->opt.online2d && in->B <= 65535 &&
+            (pl->opt.online2d_small || !resident_layout(pl, in->prog, false, false, a, lay))) {
             int r0 = 0, r1 = 0;
             bool ok = true;
             for (int k = 0; k < in->prog.n_ops; ++k) {
@@ -766,40 +828,41 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
                 }
             }
             O2Launch L;
-            if (ok && online2d_plan(pl->dev.n0, pl->dev.n1, r0, r1, &L)) {
+            if (ok && online2d_plan(pl->dev.n0, pl->dev.n1, r0, r1, pl->opt.online2d_async != 0, &L)) {
                 const size_t doubles = (size_t)in->B * pl->dev.G + (size_t)in->B * L.tilesY * L.tilesX * 2;
-                double *scratch = nullptr;
-                CUDA_TRY(cudaMallocAsync(&scratch, doubles * sizeof(double), st));
-                if (getenv("BLG_VERBOSE"))
+                if ((long long)doubles > pl->o2_cap) {  // grows once per study: no allocation on the per-step path
+                    if (pl->d_o2) CUDA_TRY(cudaFree(pl->d_o2));
+                    pl->d_o2 = nullptr;
+                    pl->o2_cap = 0;
+                    CUDA_TRY(cudaMalloc(&pl->d_o2, doubles * sizeof(double)));
+                    pl->o2_cap = (long long)doubles;
+                }
+                if (pl->opt.verbose)
                     fprintf(stderr, "[blgrid] online2d: %lld hypotheses x %d x %d tiles, %zu B smem/CTA, radii <= %d / %d\n",
                             (long long)in->B, L.tilesY, L.tilesX, L.smemBytes, r0, r1);
-                const int rc = online2d_run(a, L, scratch, st);
+                const int rc = online2d_run(a, L, pl->d_o2, st);
                 g_launches += 2;
                 g_last_kernel = "online2d";
                 if (rc != 0) return fail("online2d launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-                CUDA_TRY(cudaFreeAsync(scratch, st));
                 return 0;
             }
         }
     }
     {
         int C = 0, m0 = 16;
-        const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, false, false, a, lay);
-        if (want && !getenv("BLG_FORCE_STREAM") && (!store || (uintptr_t)out->alpha_seq % 16 == 0) &&
+        const bool want = pl->opt.cluster2d || !resident_layout(pl, in->prog, false, false, a, lay);
+        if (want && !pl->opt.force_stream && (!store || (uintptr_t)out->alpha_seq % 16 == 0) &&
             cluster2d_layout(pl, in->prog, flags, false, a, lay, C, m0)) {
-            const int rc = launch_cluster(fwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr, m0), a, lay, in->B, C, st, "fwd_cluster2d");
+            const int rc = launch_cluster(pl, fwd_cluster2d_entry(pl->opt.trace[0] != 0, m0), a, lay, in->B, C, st, "fwd_cluster2d");
             if (rc <= 0) return rc;  // 1: clusters cannot be scheduled here -> stream kernels below
         }
     }
-    if (!resident_layout(pl, in->prog, false, false, a, lay) || getenv("BLG_FORCE_STREAM")) {
-        if (pl->dev.ndim == 2 && stream2d_supports(in->prog.n_ops, in->prog.kind, in->prog.axis) && getenv("BLG_STREAM2D") &&
-            stream_layout(pl, in->prog, a, lay, stream2d_chunk()))
-            return launch_stream(fwd_stream2d_entry(), pl, a, lay, in->B, st, "fwd_stream2d", 512);
+    if (!resident_layout(pl, in->prog, false, false, a, lay) || pl->opt.force_stream) {
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream forward kernel");
         return launch_stream(fwd_resident_entry(1024, true), pl, a, lay, in->B, st, "fwd_stream");
     }
     a.use_bulk = bulkOk ? 1 : 0;
-    return launch_resident(fwd_resident_entry(lay.nt, false), a, lay, in->B, st, "fwd_resident");
+    return launch_resident(pl, fwd_resident_entry(lay.nt, false), a, lay, in->B, st, "fwd_resident");
 }
 
 int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {
@@ -813,7 +876,6 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     memset(&a, 0, sizeof a);
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
-    pl->rows_raw = false;
     if (flags & BLG_F_RAW_POSTERIOR) {  // kernels that normalise their rows leave the factor at 1
         if (!out->row_scale) return fail("row_scale required with RAW_POSTERIOR");
         if (acc) return fail("RAW_POSTERIOR and ACCUMULATE exclude each other");
@@ -823,7 +885,7 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
         CUDA_TRY(cudaGetLastError());
     }
     Layout lay;
-    const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !getenv("BLG_NO_BULK");
+    const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !pl->opt.no_bulk;
     {
         int wsM = 0;
         if (alignedRows && !acc && fast1d_ws_layout(pl, in->prog, true, a, lay, wsM)) {
@@ -833,41 +895,37 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
                 a.use_bulk = 1;
                 long long grid = in->B;
                 if (prep_sm_assign(pl, in, a, grid, st)) return -1;
-                if (PassKernel k = bwd_fast1d_ws_entry(wsM, lay.nt)) return launch_resident(k, a, lay, grid, st, "bwd_fast1d_ws");
+                if (PassKernel k = bwd_fast1d_ws_entry(wsM, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "bwd_fast1d_ws");
                 return fail("warp-specialised backward kernel missing");
             }
         }
     }
     if (prep_lik_table(pl, in, a, st)) return -1;
-    const int M = fast_m(true);
+    const int M = kFastM;
     if (fast1d_layout(pl, in->prog, true, M, a, lay)) {
         a.use_bulk = alignedRows ? 1 : 0;
         long long grid = in->B;
         if (prep_sm_assign(pl, in, a, grid, st)) return -1;
-        if (PassKernel k = bwd_fast1d_entry(M, lay.nt)) return launch_resident(k, a, lay, grid, st, "bwd_fast1d");
+        if (PassKernel k = bwd_fast1d_entry(M, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "bwd_fast1d");
     }
     a.halo = 0;
     {
         int C = 0, m0 = 16;
-        const bool want = getenv("BLG_CLUSTER2D") || !resident_layout(pl, in->prog, true, false, a, lay);
-        if (want && !getenv("BLG_FORCE_STREAM") && (uintptr_t)out->alpha_seq % 16 == 0 &&
+        const bool want = pl->opt.cluster2d || !resident_layout(pl, in->prog, true, false, a, lay);
+        if (want && !pl->opt.force_stream && (uintptr_t)out->alpha_seq % 16 == 0 &&
             cluster2d_layout(pl, in->prog, flags, true, a, lay, C, m0)) {
-            const int rc = launch_cluster(bwd_cluster2d_entry(getenv("BLG_TRACE") != nullptr, m0), a, lay, in->B, C, st, "bwd_cluster2d");
-            if (rc == 0) pl->rows_raw = a.row_scale != nullptr;
+            const int rc = launch_cluster(pl, bwd_cluster2d_entry(pl->opt.trace[0] != 0, m0), a, lay, in->B, C, st, "bwd_cluster2d");
             if (rc <= 0) return rc;
         }
     }
     bool fits = alignedRows && resident_layout(pl, in->prog, true, true, a, lay);
     if (!fits) fits = false;
-    if (getenv("BLG_FORCE_STREAM") || (!fits && !resident_layout(pl, in->prog, true, false, a, lay))) {
-        if (pl->dev.ndim == 2 && stream2d_supports(in->prog.n_ops, in->prog.kind, in->prog.axis) && getenv("BLG_STREAM2D") &&
-            stream_layout(pl, in->prog, a, lay, stream2d_chunk()))
-            return launch_stream(bwd_stream2d_entry(), pl, a, lay, in->B, st, "bwd_stream2d", 512);
+    if (pl->opt.force_stream || (!fits && !resident_layout(pl, in->prog, true, false, a, lay))) {
         if (!stream_layout(pl, in->prog, a, lay)) return fail("grid / kernel radius too large for the stream backward kernel");
         return launch_stream(bwd_resident_entry(1024, true), pl, a, lay, in->B, st, "bwd_stream");
     }
     a.use_bulk = (fits && a.off_stage >= 0) ? 1 : 0;
-    return launch_resident(bwd_resident_entry(lay.nt, false), a, lay, in->B, st, "bwd_resident");
+    return launch_resident(pl, bwd_resident_entry(lay.nt, false), a, lay, in->B, st, "bwd_resident");
 }
 
 int blg_accumulate(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream) {
@@ -880,7 +938,7 @@ int blg_accumulate(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, u
     weights_kernel<<<(unsigned)((in->B + nt - 1) / nt), nt, 0, st>>>(in->log_weight, out->alive, in->B, pl->d_w);
     const long long count = in->T * (long long)pl->dev.G;
     const unsigned blocks = (unsigned)((count + nt - 1) / nt);
-    if (pl->rows_raw && out->row_scale)
+    if (out->row_scale)  // stateless: the factors are applied whenever the caller hands them (kernels pre-fill 1.0)
         accumulate_kernel<true><<<blocks, nt, 0, st>>>(out->alpha_seq, pl->d_w, in->B, count, out->avg, out->row_scale, in->T,
                                                        pl->dev.G);
     else

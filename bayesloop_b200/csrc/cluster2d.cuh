@@ -32,9 +32,54 @@
 #pragma once
 
 #include "common.cuh"
-#include "stream2d.cuh"  // classify2d (which programs the 2-D kernels understand)
 
 namespace blg {
+
+struct C2Ops {
+    int k0, k1;        // program index of the GRW acting on axis 0 / axis 1 (-1: none)
+    int pre, post;     // program index of a RESET before all / after all GRWs (-1: none)
+    bool ok;
+};
+
+// Host and device share this classification: which programs the cluster-resident 2-D kernels understand.
+__host__ __device__ inline C2Ops classify2d(int n_ops, const int *kind, const int *axis) {
+    C2Ops o;
+    o.k0 = o.k1 = o.pre = o.post = -1;
+    o.ok = true;
+    int firstGrw = -1, lastGrw = -1;
+    for (int k = 0; k < n_ops; ++k)
+        if (kind[k] == BLG_OP_GRW) {
+            if (firstGrw < 0) firstGrw = k;
+            lastGrw = k;
+            if (axis[k] == 0 && o.k0 < 0)
+                o.k0 = k;
+            else if (axis[k] == 1 && o.k1 < 0)
+                o.k1 = k;
+            else
+                o.ok = false;
+        }
+    for (int k = 0; k < n_ops; ++k) {
+        if (kind[k] == BLG_OP_GRW) continue;
+        if (kind[k] != BLG_OP_RESET) {
+            o.ok = false;
+            continue;
+        }
+        if (firstGrw < 0 || k > lastGrw) {
+            if (o.post < 0)
+                o.post = k;
+            else
+                o.ok = false;
+        } else if (k < firstGrw) {
+            if (o.pre < 0)
+                o.pre = k;
+            else
+                o.ok = false;
+        } else {
+            o.ok = false;
+        }
+    }
+    return o;
+}
 
 constexpr int kC2Threads = 512;
 constexpr int kC2M0 = 16;      // rows per work item of the axis-0 convolution (template parameter M0: 16 or 13, whichever
@@ -223,7 +268,7 @@ __device__ __forceinline__ bool c2_setup(const PassArgs &a, long long b, C2 &s) 
     s.xbAddr = smem_u32(c2_Xb(a));
     s.sAddr = smem_u32(c2_S(a));
     s.bits = 0u;
-    const Stream2dOps ops = classify2d(a.pg.n_ops, a.pg.kind, a.pg.axis);
+    const C2Ops ops = classify2d(a.pg.n_ops, a.pg.kind, a.pg.axis);
     const int NK = a.pg.n_ops;
     auto load = [&](int k, double &par, int &rad, int &lo, int &hi) {
         par = 0.0;

@@ -14,6 +14,7 @@ PassKernel fwd_cluster2d_entry(bool prof, int m0) {
     if (m0 == 13) return prof ? fwd_cluster2d_kernel<kC2Threads, true, 13> : fwd_cluster2d_kernel<kC2Threads, false, 13>;
     return prof ? fwd_cluster2d_kernel<kC2Threads, true, 16> : fwd_cluster2d_kernel<kC2Threads, false, 16>;
 }
+bool cluster2d_supports(int n_ops, const int *kind, const int *axis) { return classify2d(n_ops, kind, axis).ok; }
 void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad) {
     *threads = kC2Threads;
     *m0 = kC2M0;

@@ -7,15 +7,11 @@ namespace blg {
 #define BLG_DECL(M)                      \
     PassKernel fwd_fast1d_entry_m##M(int); \
     PassKernel bwd_fast1d_entry_m##M(int);
-BLG_DECL(5)
-BLG_DECL(7)
 BLG_DECL(9)
 #undef BLG_DECL
 
 PassKernel fwd_fast1d_entry(int M, int nt) {
     switch (M) {
-        case 5: return fwd_fast1d_entry_m5(nt);
-        case 7: return fwd_fast1d_entry_m7(nt);
         case 9: return fwd_fast1d_entry_m9(nt);
         default: return nullptr;
     }
@@ -23,8 +19,6 @@ PassKernel fwd_fast1d_entry(int M, int nt) {
 
 PassKernel bwd_fast1d_entry(int M, int nt) {
     switch (M) {
-        case 5: return bwd_fast1d_entry_m5(nt);
-        case 7: return bwd_fast1d_entry_m7(nt);
         case 9: return bwd_fast1d_entry_m9(nt);
         default: return nullptr;
     }

@@ -1,5 +1,5 @@
 // kernels.h -- host-visible entry points of the pass kernels.  Every kernel family is compiled in its own
-// translation unit (fast1d_inst.cu, resident_inst.cu, stream2d_inst.cu) so that the library builds in parallel;
+// translation unit (fast1d_inst.cu, resident_inst.cu, cluster2d_inst.cu ...) so that the library builds in parallel;
 // api.cu only sees these function pointers (all pass kernels share the signature void(const PassArgs)).
 #pragma once
 
@@ -9,8 +9,8 @@ namespace blg {
 
 using PassKernel = void (*)(const PassArgs);
 
-// fast 1-D kernels (fast1d.cuh): M in {5, 7, 9} outputs per thread; nt = threads of the launch (<= 128, <= 160,
-// <= 256, else 1024).  Return nullptr for a combination that is not compiled.
+// single-role fused 1-D kernels (fast1d.cuh): M = 9 outputs per thread (the fallback for grids the warp-specialised
+// kernels do not cover); nt = threads of the launch (<= 128, <= 160, <= 256, else 1024).  nullptr: not compiled.
 PassKernel fwd_fast1d_entry(int M, int nt);
 PassKernel bwd_fast1d_entry(int M, int nt);
 
@@ -23,11 +23,8 @@ PassKernel bwd_fast1d_ws_entry(int M, int nt);
 PassKernel fwd_resident_entry(int nt, bool stream);
 PassKernel bwd_resident_entry(int nt, bool stream);
 
-// fused 2-D stream kernels (stream2d.cuh), 512 threads; kStream2dM = outputs per work item (layout parameter)
-PassKernel fwd_stream2d_entry();
-PassKernel bwd_stream2d_entry();
-int stream2d_chunk();
-bool stream2d_supports(int n_ops, const int *kind, const int *axis);
+// which transition programs the cluster-resident 2-D kernels understand (classify2d in cluster2d.cuh)
+bool cluster2d_supports(int n_ops, const int *kind, const int *axis);
 
 // cluster-resident 2-D kernels (cluster2d.cuh): 512 threads, one cluster of 2/4/8 CTAs per combo
 // prof: per-phase cycle counters into PassArgs::trace; m0 in {16, 13}: rows per axis-0 work item
@@ -40,11 +37,11 @@ void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad);
 // (BLG_F_SEPARABLE_ROWS).  online2d_plan: false when tile + halo do not fit in shared memory; scratch holds
 // B * G + B * tiles * 2 doubles; online2d_run returns a cudaError_t (0 = launched K7 and K8).
 struct O2Launch {
-    int TH;  // rows of a tile: 64 (512 threads, one CTA per SM) or 32 (256 threads, two CTAs per SM; BLG_ONLINE2D_TH=32)
+    int async;  // tile loads through cp.async (the default; measured 1.92 vs 2.58 ms per C5 step, profiles/r2a_online_ab.txt)
     int tilesY, tilesX, P, inRowsMax, w0len, w1len;
     size_t smemBytes;
 };
-bool online2d_plan(int n0, int n1, int r0max, int r1max, O2Launch *L);
+bool online2d_plan(int n0, int n1, int r0max, int r1max, bool async, O2Launch *L);
 int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStream_t st);
 
 }  // namespace blg

@@ -10,6 +10,7 @@ machine without a GPU: tests/ build an Engine around the CPU oracle (oracle/libb
 symbols and takes host pointers) and pass it explicitly to the studies.  Nothing in this package refers to oracle/.
 """
 import collections
+import contextlib
 import ctypes
 import os
 import threading
@@ -200,6 +201,7 @@ class Engine:
         L.blg_plan_create.argtypes = [ctypes.POINTER(_Problem), ctypes.POINTER(ctypes.c_void_p)]
         L.blg_plan_destroy.argtypes = [ctypes.c_void_p]
         L.blg_plan_destroy.restype = None
+        L.blg_plan_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]
         for name in ('blg_forward', 'blg_backward', 'blg_accumulate'):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.POINTER(_Inputs), ctypes.POINTER(_Outputs),
                                          ctypes.c_uint32, ctypes.c_void_p]
@@ -213,6 +215,7 @@ class Engine:
         self.backend = L.blg_backend().decode()
         self._pinned = {}
         self._plans = collections.OrderedDict()  # problem signature -> Plan (scratch and tables stay allocated)
+        self._options = {}  # dispatch options applied to every plan this engine creates (blg_plan_set_option)
 
     # ---------------------------------------------------------------------------------------------- memory
     def to_device(self, array, pinned=False):
@@ -275,6 +278,19 @@ class Engine:
         if rc != 0:
             raise EngineError('{}: {}'.format(self.backend, self.lib.blg_last_error().decode()))
 
+    # ---------------------------------------------------------------------------------------------- options
+    @contextlib.contextmanager
+    def options(self, **kw):
+        """Dispatch options (include/blgrid.h: blg_plan_set_option) for the plans created inside the `with` block,
+        e.g. `with engine.options(force_stream=1): study.fit()`.  They are part of the plan-cache key, so a plan made
+        under other options is never reused.  Options choose the kernel family, not the result."""
+        saved = dict(self._options)
+        self._options.update({k: int(v) for k, v in kw.items()})
+        try:
+            yield self
+        finally:
+            self._options = saved
+
     # ---------------------------------------------------------------------------------------------- calls
     def plan(self, coords, lattice, om_kind, seg_len, n_cols):
         """Plan for one (grid, observation model) description.  Plans are cached per engine (LRU of 8): repeated fits
@@ -283,7 +299,7 @@ class Engine:
         ndim = len(coords)
         hostCoords = [np.ascontiguousarray(c, dtype=np.float64) for c in coords]
         key = (ndim, tuple(c.tobytes() for c in hostCoords), tuple(float(x) for x in lattice[:ndim]), int(om_kind),
-               int(seg_len), int(n_cols), self.stream().value)
+               int(seg_len), int(n_cols), self.stream().value, tuple(sorted(self._options.items())))
         cached = self._plans.get(key)
         if cached is not None:
             self._plans.move_to_end(key)
@@ -301,6 +317,8 @@ class Engine:
                 self._check(self.lib.blg_plan_create(ctypes.byref(pb), ctypes.byref(handle)))
         else:
             self._check(self.lib.blg_plan_create(ctypes.byref(pb), ctypes.byref(handle)))
+        for name, value in self._options.items():
+            self._check(self.lib.blg_plan_set_option(handle, name.encode(), int(value)))
         n = [pb.n[0], pb.n[1]]
         plan = Plan(self, handle, ndim, n, n[0] * n[1])
         self._plans[key] = plan

@@ -148,6 +148,14 @@ class TransitionModel:
         self.latticeConstant = None
         self.tOffset = 0
 
+    # The back-pointer `study` (core.py:281 of the reference) is a weak proxy here; a proxy forwards __reduce_ex__
+    # to the study it points to, so pickle / cloudpickle would serialise a SECOND, half-initialised study in its
+    # place.  It is dropped on the way out and re-attached by Study.__setstate__.
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d['study'] = None
+        return d
+
 
 def _as_array(value):
     return np.array(value) if isinstance(value, (list, tuple)) else value
@@ -351,3 +359,30 @@ class SerialTransitionModel(TransitionModel):
             sub.lower(ctx, window.clip(*ctx.steps_between(edges[:, k], edges[:, k + 1])))
         for j in np.flatnonzero(self.changePointMask):  # embedded change-points (transitionModels.py:788-818)
             ctx.emit(OP_RESET, 0, ctx.lcProd, 0, window.clip(*ctx.steps_equal(points[:, j])))
+
+
+class _Unsupported(TransitionModel):
+    """Transition models of the reference that have no device operator in this engine (each needs its own kernel
+    family: 3x-padded FFT convolution, cubic-spline shift, dense 2-D convolution; SURVEY.md section 2 row 8 marks them
+    out of scope).  Constructing one fails immediately and says so, instead of an AttributeError on `bl.tm.<name>`
+    or a late failure inside fit()."""
+    label = ''
+    reference = ''
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError('bayesloop_b200 has no device kernel for the transition model "{}" ({}); there is '
+                                  'no CPU fallback.  Supported: Static, GaussianRandomWalk, ChangePoint, RegimeSwitch, '
+                                  'Independent, NotEqual, CombinedTransitionModel, SerialTransitionModel, BreakPoint.'
+                                  .format(self.label, self.reference))
+
+
+class AlphaStableRandomWalk(_Unsupported):
+    label, reference = 'AlphaStableRandomWalk', 'bayesloop/transitionModels.py:121-260'
+
+
+class Deterministic(_Unsupported):
+    label, reference = 'Deterministic', 'bayesloop/transitionModels.py:477-606'
+
+
+class BivariateRandomWalk(_Unsupported):
+    label, reference = 'BivariateRandomWalk', 'bayesloop/transitionModels.py:843-911'

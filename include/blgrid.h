@@ -18,6 +18,8 @@
  *     the same symbols and exists ONLY as the parity checker for the tests.
  *   - the caller owns every buffer; the library allocates only small per-plan tables.
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
+ *   - the calls are stateless apart from scratch the plan grows: nothing a call leaves in the plan changes the
+ *     result of a later call (blg_accumulate applies row_scale whenever the caller passes it).
  *   - grids are C-contiguous, last parameter fastest (np.meshgrid(..., indexing='ij'), core.py:169):
  *     cell g = i0 * n[1] + i1.  All floating point data is IEEE binary64 (the reference computes in
  *     float64 throughout).
@@ -69,8 +71,8 @@ enum blg_flags {
                                       /* scale-free per row (core.py:436-441 renormalises alpha*beta)             */
     BLG_F_RAW_POSTERIOR = 1u << 7,    /* backward: the smoothed rows may be left unnormalised; row_scale[b][t]    */
                                       /* (required) receives the factor that normalises row t of combo b (1.0 if  */
-                                      /* the implementation normalised the row itself).  blg_accumulate applies   */
-                                      /* row_scale when it is given; blg_finalize(NORMALIZE_ROWS) normalises B = 1 */
+                                      /* the implementation normalised the row itself).  blg_accumulate multiplies */
+                                      /* by row_scale whenever it is non-NULL; blg_finalize(NORMALIZE_ROWS) normalises B = 1 */
     BLG_F_SEPARABLE_ROWS = 1u << 8    /* forward, caller's promise about the program: in every row the operators    */
                                       /* that are active at the steps of this call are GRWs on distinct axes,      */
                                       /* optionally followed by ONE REGIME, or a single RESET.  Lets an              */
@@ -148,6 +150,13 @@ const char *blg_backend(void);
 
 int blg_plan_create(const blg_problem *problem, blg_plan **plan);
 void blg_plan_destroy(blg_plan *plan);
+
+/* Dispatch / tuning option of a plan, by name (e.g. "force_stream", "cluster2d", "cluster2d_c", "no_ws", "online2d",
+ * "online2d_async", "verbose"; the full list is the table kOptNames in bayesloop_b200/csrc/api.cu).  Options are
+ * resolved here and at plan creation (which reads the BLG_* debugging variables of the environment ONCE): no
+ * per-call path looks at process state.  They select WHICH kernel family runs, never what it computes: results
+ * agree to rounding whatever the options.  Unknown names return -1.  The CPU oracle accepts and ignores them. */
+int blg_plan_set_option(blg_plan *plan, const char *name, int64_t value);
 
 /* Forward filter for B combos: replaces the loop core.py:372-411 (+ :417). */
 int blg_forward(blg_plan *plan, const blg_inputs *in, const blg_outputs *out, uint32_t flags, void *stream);

@@ -421,6 +421,15 @@ def syn_study_odd_grid(bl):  # odd G (no 16-byte aligned rows), tiny sigma (R = 
     return _study(bl, bl.Study, x, L, bl.tm.GaussianRandomWalk('sigma', 0.01, target='rate'))
 
 
+def syn_poisson_rate_zero(bl):  # grid point lambda == 0 with zero counts: 0**0 * exp(-0) / 0! = 1 (observationModels.py:502)
+    S = bl.HyperStudy(silent=True)
+    S.loadExampleData(silent=True)
+    S.set(bl.om.Poisson('rate', bl.cint(0, 6, 200), prior=None),
+          bl.tm.GaussianRandomWalk('sigma', bl.cint(0, 0.4, 5), target='rate'), silent=True)
+    S.fit(silent=True)
+    return S
+
+
 def syn_hyper_dead_combo(bl):  # zero-norm abort (core.py:388-400): combos whose grid cannot explain a jump
     x = np.array([0., 0., 0., 0., 0., 0., 900., 0., 0., 0.])
     L = bl.om.Gaussian('mean', bl.cint(-1, 1, 16), 'std', bl.oint(0, 0.5, 12))
@@ -565,15 +574,8 @@ CASES = {f.__name__: f for f in [
     syn_hyper_poisson_sweep, syn_hyper_poisson_forward_only, syn_hyper_poisson_evidence_only, syn_hyper_gauss_2d,
     syn_cps_gauss_2d, syn_cps_two_breakpoints, syn_study_scaledar1_2d, syn_study_missing_data,
     syn_study_ar1_missing, syn_study_multicolumn, syn_study_timestamps, syn_study_wide_kernel, syn_study_odd_grid,
-    syn_hyper_dead_combo, syn_study_2d_axis0_wide, syn_online_mixed,
+    syn_hyper_dead_combo, syn_study_2d_axis0_wide, syn_online_mixed, syn_poisson_rate_zero,
 ]}
-
-# Cases added after the last GPU minute of round 1: pinned against the reference and green through the C oracle on CPU;
-# their first run on the B200 is the first call of round 2 (tests/test_gpu_parity.py collects them when
-# BLG_TEST_DEFERRED=1, tools/r2_online2d_ab.sh sets it).  The kernels they reach (likelihood table + resident / cluster
-# kernels) are the ones every B >= 4 sweep already runs; only the combination "caller-supplied table" is new.
-GPU_DEFERRED = ('sim_scipy_gamma', 'ref_om_sympy_1p', 'ref_om_sympy_2p', 'ref_om_scipy_1p', 'ref_om_scipy_2p', 'ref_om_numpy_1p',
-                'ref_om_numpy_2p', 'syn_hyper_scipy_gamma')
 
 # Values hard-coded in the reference's own test-suite / docs: name -> logEvidence
 REFERENCE_PINNED_LOGE = {

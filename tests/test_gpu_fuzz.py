@@ -2,8 +2,7 @@
 trees of Combined / Serial models with change- and break-points, hyper-parameter lists, missing data, all four study
 types) run through the CUDA library and through the oracle, same host logic on both sides.
 
-Opt-in for now (BLG_TEST_FUZZ=<number of cases>): written after the last GPU minute of round 1; tools/r2_online2d_ab.sh
-runs it first thing in round 2."""
+300 cases by default under `-m gpu` (BLG_TEST_FUZZ=<n> changes the count): a few seconds on the B200 box."""
 import contextlib
 import io
 import os
@@ -55,7 +54,13 @@ def test_harness_agrees_with_itself(oracle_engine):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get('BLG_TEST_FUZZ'), reason='opt-in: BLG_TEST_FUZZ=<number of random cases>')
 def test_random_programs_cuda_vs_oracle(cuda_engine, oracle_engine):
-    n = int(os.environ['BLG_TEST_FUZZ'])
+    n = int(os.environ.get('BLG_TEST_FUZZ', '300'))
     assert run_cases(cuda_engine, oracle_engine, n) == []
+
+
+@pytest.mark.gpu
+def test_random_programs_on_the_stream_kernels(cuda_engine, oracle_engine):
+    """The same generator with the global-memory stream kernels forced (plan option force_stream)."""
+    with cuda_engine.options(force_stream=1):
+        assert run_cases(cuda_engine, oracle_engine, 60, seed0=1000) == []

@@ -16,15 +16,38 @@ from conftest import load_golden
 pytestmark = pytest.mark.gpu
 
 
+def _families():
+    """Kernel family (blg_last_kernel) every golden case ran on when it last passed on a B200: a dispatch regression
+    -- e.g. the headline sweep silently falling back from fwd/bwd_fast1d_ws to the generic resident kernels -- fails
+    the case even though its numbers still agree.  tests/golden/kernel_families.json is written from a GPU run
+    (BLG_RECORD_FAMILIES=<path> collects the observed names); a case missing from it is recorded, not asserted."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'kernel_families.json')
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        return json.load(f)
+
+
 @pytest.mark.parametrize('name', sorted(cases.CASES))
 def test_case_matches_reference_golden(name, use_cuda):
+    import json
     import os
     import bayesloop_b200 as bl
-    if name in cases.GPU_DEFERRED and os.environ.get('BLG_TEST_DEFERRED') != '1':
-        pytest.skip('added after the last GPU run of round 1 (cases.GPU_DEFERRED); set BLG_TEST_DEFERRED=1')
     before = use_cuda.launch_count()
     S, got = parity.run_case(name, bl)
     assert use_cuda.launch_count() > before, 'no CUDA kernel was launched'
+    family = use_cuda.last_kernel()
+    record = os.environ.get('BLG_RECORD_FAMILIES')
+    if record:
+        seen = json.load(open(record)) if os.path.exists(record) else {}
+        seen[name] = family
+        with open(record, 'w') as f:
+            json.dump(seen, f, indent=0, sort_keys=True)
+    want_family = _families().get(name)
+    if want_family is not None:
+        assert family == want_family, 'dispatch changed: {} ran on {}, expected {}'.format(name, family, want_family)
     parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)
     want = float(load_golden(name)['logEvidence'])
     if np.isfinite(want):
@@ -68,13 +91,25 @@ CONFIGS = {
 }
 
 
+# default dispatch of the shapes behind BASELINE.json configs[1] (1-D grid, one GaussianRandomWalk: warp-specialised
+# fused kernels) and configs[2]/[3] (2-D grids beyond one SM's shared memory: cluster-resident kernels)
+EXPECTED_FAMILY = {'poisson_c2_small': 'fast1d_ws', 'poisson_wide_kernels': 'fast1d_ws', 'poisson_odd_grid': 'fast1d_ws',
+                   'poisson_regime': 'resident', 'gauss_2d_200x200_stream': 'cluster2d', 'gauss_2d_256x96_stream': 'cluster2d'}
+
+
 @pytest.mark.parametrize('name', sorted(CONFIGS))
 @pytest.mark.parametrize('mode', ['full', 'forwardOnly', 'evidenceOnly'])
 def test_cuda_matches_cpu_oracle(name, mode, cuda_engine, oracle_engine):
     import bayesloop_b200 as bl
     kw = dict(forwardOnly=(mode == 'forwardOnly'), evidenceOnly=(mode == 'evidenceOnly'))
     got = helpers.abi_sweep(cuda_engine, CONFIGS[name](bl, cuda_engine), **kw)
+    if name in EXPECTED_FAMILY:  # the kernels that carry the performance claims must be the ones that ran
+        assert cuda_engine.last_kernel() == ('bwd_' if mode == 'full' else 'fwd_') + EXPECTED_FAMILY[name]
     want = helpers.abi_sweep(oracle_engine, CONFIGS[name](bl, oracle_engine), **kw)
+    _assert_sweeps_agree(got, want, mode)
+
+
+def _assert_sweeps_agree(got, want, mode='full'):
     np.testing.assert_array_equal(got['alive'], want['alive'])
     np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-10)
     np.testing.assert_allclose(got['local'], want['local'], rtol=1e-7)
@@ -131,11 +166,12 @@ def test_properties_at_scale(cuda_engine):
                                   'syn_study_multicolumn', 'ref_om_gaussianmean', 'syn_cps_gauss_2d',
                                   'ref_study_2d_grw', 'ref_study_2d_static', 'ref_hyper_1hp', 'ref_online_static',
                                   'ref_om_scaledar1', 'ref_om_laplace'])
-def test_stream_kernels_on_golden_cases(name, use_cuda, monkeypatch):
+def test_stream_kernels_on_golden_cases(name, use_cuda):
     """The large-grid (global-memory streamed) kernels forced onto small cases: same goldens."""
     import bayesloop_b200 as bl
-    monkeypatch.setenv('BLG_FORCE_STREAM', '1')
-    S, got = parity.run_case(name, bl)
+    with use_cuda.options(force_stream=1, online2d=0):
+        S, got = parity.run_case(name, bl)
+    assert use_cuda.last_kernel().endswith('_stream')
     parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)
 
 
@@ -167,101 +203,84 @@ CLUSTER_CONFIGS = {
 
 @pytest.mark.parametrize('name', sorted(CLUSTER_CONFIGS))
 @pytest.mark.parametrize('mode', ['full', 'forwardOnly', 'evidenceOnly'])
-def test_cluster2d_matches_cpu_oracle(name, mode, cuda_engine, oracle_engine, monkeypatch):
+def test_cluster2d_matches_cpu_oracle(name, mode, cuda_engine, oracle_engine):
     import bayesloop_b200 as bl
-    monkeypatch.setenv('BLG_CLUSTER2D', '1')
     kw = dict(forwardOnly=(mode == 'forwardOnly'), evidenceOnly=(mode == 'evidenceOnly'))
-    got = helpers.abi_sweep(cuda_engine, CLUSTER_CONFIGS[name](bl, cuda_engine), **kw)
+    with cuda_engine.options(cluster2d=1):
+        got = helpers.abi_sweep(cuda_engine, CLUSTER_CONFIGS[name](bl, cuda_engine), **kw)
     assert cuda_engine.last_kernel() == ('bwd_cluster2d' if mode == 'full' else 'fwd_cluster2d')
     want = helpers.abi_sweep(oracle_engine, CLUSTER_CONFIGS[name](bl, oracle_engine), **kw)
-    np.testing.assert_array_equal(got['alive'], want['alive'])
-    np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-10)
-    np.testing.assert_allclose(got['local'], want['local'], rtol=1e-7)
-    np.testing.assert_allclose(got['localEvidence'], want['localEvidence'], rtol=1e-7)
-    if mode != 'evidenceOnly':
-        rowmax = want['avg'].max(axis=1, keepdims=True)
-        assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-6 * np.abs(want['avg']) + 1e-12 * rowmax)
-        np.testing.assert_allclose(got['means'], want['means'], rtol=1e-8)
+    _assert_sweeps_agree(got, want, mode)
 
 
 @pytest.mark.parametrize('csize', ['2', '4'])
 @pytest.mark.parametrize('name', ['syn_hyper_gauss_2d', 'syn_cps_gauss_2d', 'ref_study_2d_grw', 'ref_study_2d_static'])
-def test_cluster2d_on_golden_cases(name, csize, use_cuda, monkeypatch):
+def test_cluster2d_on_golden_cases(name, csize, use_cuda):
     """Cluster sizes 2 and 4 on the reference's own 2-D known answers (20x20 ... 40x36 grids)."""
     import bayesloop_b200 as bl
-    monkeypatch.setenv('BLG_CLUSTER2D', '1')
-    monkeypatch.setenv('BLG_CLUSTER2D_C', csize)
-    S, got = parity.run_case(name, bl)
+    with use_cuda.options(cluster2d=1, cluster2d_c=int(csize)):
+        S, got = parity.run_case(name, bl)
     assert use_cuda.last_kernel() == 'bwd_cluster2d'
     parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)
 
 
-def test_cluster2d_agrees_with_stream_kernels_at_c3_size(cuda_engine, monkeypatch):
-    """256 x 256 (BASELINE.json configs[2] grid), too big for the CPU oracle in seconds: the cluster-resident kernels
-    (8 CTAs per combo, default dispatch) against the independent global-memory stream kernels, plus row sums."""
+def _c3_study(bl, engine, T=48, hyper=3):
+    """BASELINE.json configs[2] grid and hyper-ranges: Gaussian 256 x 256, GRW on both parameters."""
+    rng = np.random.default_rng(2)
+    mu = np.cumsum(rng.normal(0, 0.05, T))
+    S = bl.HyperStudy(silent=True, engine=engine)
+    S.loadData(rng.normal(mu, 1.0), silent=True)
+    S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, 256), 'std', bl.oint(0, 3, 256)),
+          bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, hyper), target='mean'),
+                                        bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, hyper), target='std')),
+          silent=True)
+    return S
+
+
+def _c4_study(bl, engine, T=40):
+    """BASELINE.json configs[3] in miniature: 200 x 200, change-point sweep in front of the two random walks."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.normal(-0.5, 1.0, T // 2), rng.normal(1.0, 1.0, T - T // 2)])
+    S = bl.HyperStudy(silent=True, engine=engine)
+    S.loadData(x, silent=True)
+    S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, 200), 'std', bl.oint(0, 3, 200)),
+          bl.tm.CombinedTransitionModel(bl.tm.ChangePoint('tChange', [5, 20, 33]),
+                                        bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, 2), target='mean'),
+                                        bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, 2), target='std')),
+          silent=True)
+    return S
+
+
+def test_cluster2d_matches_cpu_oracle_at_c3_size(cuda_engine, oracle_engine):
+    """256 x 256 (BASELINE.json configs[2] grid), 9 combos x 48 steps, default dispatch (8 CTAs per combo) against the
+    C oracle (a few seconds of CPU), plus the stream kernels as a third, independent implementation."""
     import bayesloop_b200 as bl
-
-    def study():
-        rng = np.random.default_rng(2)
-        T = 48
-        mu = np.cumsum(rng.normal(0, 0.05, T))
-        S = bl.HyperStudy(silent=True, engine=cuda_engine)
-        S.loadData(rng.normal(mu, 1.0), silent=True)
-        S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, 256), 'std', bl.oint(0, 3, 256)),
-              bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, 3), target='mean'),
-                                            bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, 3), target='std')),
-              silent=True)
-        return S
-
-    got = helpers.abi_sweep(cuda_engine, study())
+    got = helpers.abi_sweep(cuda_engine, _c3_study(bl, cuda_engine))
     assert cuda_engine.last_kernel() == 'bwd_cluster2d'
-    monkeypatch.setenv('BLG_NO_CLUSTER2D', '1')
-    want = helpers.abi_sweep(cuda_engine, study())
-    assert cuda_engine.last_kernel() == 'bwd_stream'
-    np.testing.assert_array_equal(got['alive'], want['alive'])
-    np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-11)
-    np.testing.assert_allclose(got['local'], want['local'], rtol=1e-8)
-    rowmax = want['avg'].max(axis=1, keepdims=True)
-    assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-7 * np.abs(want['avg']) + 1e-13 * rowmax)
+    want = helpers.abi_sweep(oracle_engine, _c3_study(bl, oracle_engine))
+    _assert_sweeps_agree(got, want)
     np.testing.assert_allclose(got['avg'].sum(axis=1), 1.0, rtol=1e-12)
-
-
-def test_cluster2d_agrees_with_stream_kernels_at_c4_size(cuda_engine, monkeypatch):
-    """200 x 200 with a change-point sweep in front of the two random walks (BASELINE.json configs[3] in miniature):
-    cluster-resident kernels (8 CTAs x 25 rows, reset inside the kernel) against the stream kernels."""
-    import bayesloop_b200 as bl
-
-    def study():
-        rng = np.random.default_rng(3)
-        T = 40
-        x = np.concatenate([rng.normal(-0.5, 1.0, T // 2), rng.normal(1.0, 1.0, T - T // 2)])
-        S = bl.HyperStudy(silent=True, engine=cuda_engine)
-        S.loadData(x, silent=True)
-        S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, 200), 'std', bl.oint(0, 3, 200)),
-              bl.tm.CombinedTransitionModel(bl.tm.ChangePoint('tChange', [5, 20, 33]),
-                                            bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, 2), target='mean'),
-                                            bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, 2), target='std')),
-              silent=True)
-        return S
-
-    got = helpers.abi_sweep(cuda_engine, study())
-    assert cuda_engine.last_kernel() == 'bwd_cluster2d'
-    monkeypatch.setenv('BLG_NO_CLUSTER2D', '1')
-    want = helpers.abi_sweep(cuda_engine, study())
+    with cuda_engine.options(no_cluster2d=1):
+        third = helpers.abi_sweep(cuda_engine, _c3_study(bl, cuda_engine))
     assert cuda_engine.last_kernel() == 'bwd_stream'
-    np.testing.assert_array_equal(got['alive'], want['alive'])
-    np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-11)
-    rowmax = want['avg'].max(axis=1, keepdims=True)
-    assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-7 * np.abs(want['avg']) + 1e-13 * rowmax)
-    np.testing.assert_allclose(got['means'], want['means'], rtol=1e-9)
+    _assert_sweeps_agree(third, want)
 
 
-def test_cluster2d_dead_combos_match_oracle(cuda_engine, oracle_engine, monkeypatch):
+def test_cluster2d_matches_cpu_oracle_at_c4_size(cuda_engine, oracle_engine):
+    """200 x 200 with change-points (BASELINE.json configs[3] grid): cluster kernels, reset inside the kernel, against
+    the C oracle."""
+    import bayesloop_b200 as bl
+    got = helpers.abi_sweep(cuda_engine, _c4_study(bl, cuda_engine))
+    assert cuda_engine.last_kernel() == 'bwd_cluster2d'
+    want = helpers.abi_sweep(oracle_engine, _c4_study(bl, oracle_engine))
+    _assert_sweeps_agree(got, want)
+
+
+def test_cluster2d_dead_combos_match_oracle(cuda_engine, oracle_engine):
     """A data point that underflows the likelihood of every cell kills the forward pass of every combo at that step
     (core.py:388-400): the cluster kernels must agree on `alive` and -inf evidences, and all CTAs of a cluster must
     leave together (no hang)."""
     import bayesloop_b200 as bl
-    monkeypatch.setenv('BLG_CLUSTER2D', '1')
 
     def study(engine):
         rng = np.random.default_rng(11)
@@ -275,28 +294,13 @@ def test_cluster2d_dead_combos_match_oracle(cuda_engine, oracle_engine, monkeypa
               silent=True)
         return S
 
-    got = helpers.abi_sweep(cuda_engine, study(cuda_engine))
+    with cuda_engine.options(cluster2d=1):
+        got = helpers.abi_sweep(cuda_engine, study(cuda_engine))
     assert cuda_engine.last_kernel().endswith('cluster2d')
     want = helpers.abi_sweep(oracle_engine, study(oracle_engine))
     np.testing.assert_array_equal(got['alive'], want['alive'])
     assert np.all(got['alive'] != 1)
     np.testing.assert_array_equal(np.isneginf(got['logE']), np.isneginf(want['logE']))
-
-
-@pytest.mark.parametrize('name', ['gauss_2d_200x200_stream', 'gauss_2d_256x96_stream'])
-def test_stream2d_opt_in_kernels_match_cpu_oracle(name, cuda_engine, oracle_engine, monkeypatch):
-    """The fused two-phase stream kernels (stream2d.cuh, opt-in through BLG_STREAM2D) stay correct: they are the
-    fallback for GaussianRandomWalk programs on grids the cluster kernels cannot take."""
-    import bayesloop_b200 as bl
-    monkeypatch.setenv('BLG_STREAM2D', '1')
-    monkeypatch.setenv('BLG_NO_CLUSTER2D', '1')
-    got = helpers.abi_sweep(cuda_engine, CONFIGS[name](bl, cuda_engine))
-    assert cuda_engine.last_kernel() == 'bwd_stream2d'
-    want = helpers.abi_sweep(oracle_engine, CONFIGS[name](bl, oracle_engine))
-    np.testing.assert_array_equal(got['alive'], want['alive'])
-    np.testing.assert_allclose(got['logE'], want['logE'], rtol=1e-10)
-    rowmax = want['avg'].max(axis=1, keepdims=True)
-    assert np.all(np.abs(got['avg'] - want['avg']) <= 1e-6 * np.abs(want['avg']) + 1e-12 * rowmax)
 
 
 def test_online_study_checkpoint_resume_on_device(use_cuda, tmp_path):
@@ -326,7 +330,7 @@ def test_online_study_checkpoint_resume_on_device(use_cuda, tmp_path):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # tiled OnlineStudy step (bayesloop_b200/csrc/online2d.cuh): the default for 2-D grids beyond shared memory
-# (BLG_ONLINE2D=0 returns to the stream kernels; BLG_ONLINE2D_SMALL=1 forces it onto grids that would fit).
+# (plan option online2d=0 returns to the stream kernels; online2d_small=1 forces it onto grids that would fit).
 
 
 def _online_big(bl, engine, n0=150, n1=130, steps=6):
@@ -348,18 +352,7 @@ def _online_big(bl, engine, n0=150, n1=130, steps=6):
     return S
 
 
-def test_online2d_tiled_step_matches_cpu_oracle(cuda_engine, oracle_engine, monkeypatch):
-    """150 x 130 grid (3 x 3 tiles, ragged right and bottom), random walks on either / both axes, random walk +
-    RegimeSwitch, RegimeSwitch alone, Independent (reset) and Static in one batch, against the CPU oracle."""
-    import contextlib
-    import io
-    import bayesloop_b200 as bl
-    monkeypatch.setenv('BLG_ONLINE2D', '1')
-    with contextlib.redirect_stdout(io.StringIO()):
-        got = _online_big(bl, cuda_engine)
-        assert got._dev['separable']
-        assert cuda_engine.last_kernel() == 'online2d'
-        want = _online_big(bl, oracle_engine)
+def _assert_online_agree(got, want):
     np.testing.assert_allclose(got.logEvidence, want.logEvidence, rtol=1e-10)
     for a, b in zip(got.logEvidenceList, want.logEvidenceList):
         np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9)
@@ -372,13 +365,41 @@ def test_online2d_tiled_step_matches_cpu_oracle(cuda_engine, oracle_engine, monk
         assert np.all(np.abs(a - b) <= 1e-7 * np.abs(b) + 1e-13 * top)
 
 
+@pytest.mark.parametrize('loads', ['cp_async', 'ldg'])
+def test_online2d_tiled_step_matches_cpu_oracle(loads, cuda_engine, oracle_engine):
+    """150 x 130 grid (3 x 3 tiles, ragged right and bottom), random walks on either / both axes, random walk +
+    RegimeSwitch, RegimeSwitch alone, Independent (reset) and Static in one batch, against the CPU oracle; both
+    tile-load variants (cp.async is the default)."""
+    import contextlib
+    import io
+    import bayesloop_b200 as bl
+    with contextlib.redirect_stdout(io.StringIO()):
+        with cuda_engine.options(online2d_small=1, online2d_async=int(loads == 'cp_async')):
+            got = _online_big(bl, cuda_engine)
+        assert got._dev['separable']
+        assert cuda_engine.last_kernel() == 'online2d'
+        want = _online_big(bl, oracle_engine)
+    _assert_online_agree(got, want)
+
+
+def test_online2d_matches_cpu_oracle_at_c5_size(cuda_engine, oracle_engine):
+    """512 x 512 (BASELINE.json configs[4] grid), 3 steps, default dispatch: the tiled kernels against the C oracle."""
+    import contextlib
+    import io
+    import bayesloop_b200 as bl
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = _online_big(bl, cuda_engine, n0=512, n1=512, steps=3)
+        assert cuda_engine.last_kernel() == 'online2d'
+        want = _online_big(bl, oracle_engine, n0=512, n1=512, steps=3)
+    _assert_online_agree(got, want)
+
+
 @pytest.mark.parametrize('name', ['ref_online_static', 'ref_online_2tm', 'syn_online_mixed'])
-def test_online2d_on_golden_cases(name, use_cuda, monkeypatch):
+def test_online2d_on_golden_cases(name, use_cuda):
     """The reference's own online tests (tests/test_onlinestudy.py) forced through the tiled kernels on their small
     grids (one mostly masked tile per hypothesis)."""
     import bayesloop_b200 as bl
-    monkeypatch.setenv('BLG_ONLINE2D', '1')
-    monkeypatch.setenv('BLG_ONLINE2D_SMALL', '1')
-    S, got = parity.run_case(name, bl)
+    with use_cuda.options(online2d=1, online2d_small=1):
+        S, got = parity.run_case(name, bl)
     assert use_cuda.last_kernel() == 'online2d'
     parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)
