@@ -630,6 +630,7 @@ class HyperStudy(Study):
         self.logEvidenceList = []
         self.localEvidenceList = []
         self.sweepStats = {}
+        self.maxWave = None
         if not silent:
             print('  --> Hyper-study')
 
@@ -740,23 +741,30 @@ class HyperStudy(Study):
             sw['means'] = eng.empty((len(self.gridSize), T))
             budget = int(eng.free_bytes() * 0.85) - T * G * 8
             sw['wave'] = int(max(1, min(B, budget // max(1, T * G * 8))))
+            if self.maxWave:  # user cap on the combinations fitted concurrently (memory, or to exercise the wave logic)
+                sw['wave'] = int(max(1, min(sw['wave'], self.maxWave)))
             sw['buf'] = eng.empty((sw['wave'], T, G)) if B > 0 else None
             sw['rowScale'] = eng.empty((sw['wave'], T)) if (B > 0 and not forwardOnly) else None
         with np.errstate(divide='ignore'):
             sw['logHp'] = np.log(hp)
+        sw['logHpDev'] = eng.to_device(sw['logHp']) if B > 0 else None
+        sw['shift'] = eng.full(1, -math.inf)          # running reference log-weight of the average (device scalar)
+        sw['weights'] = eng.zeros(max(B, 1))          # log-weights of the combos relative to it
         return sw
 
     def _executeSweep(self, sw):
-        """Kernels of one sweep (inputs already resident): per wave one forward pass, the evidences fix the
-        averaging weights, one backward(+accumulate) pass; then local-evidence mix, cross-rank merge, finalize."""
+        """Kernels of one sweep (inputs already resident).  Per wave: forward pass; the wave's averaging weights and
+        the re-base of the running sum are computed ON THE DEVICE from the evidences (blg_wave_weights: the streaming
+        form of np.logaddexp, core.py:1358-1366); backward pass; weighted accumulation.  Everything is enqueued on
+        one stream without a host round trip: the host reads the evidences once, after the cross-rank merge."""
         from . import distributed as dist
         eng, ses, T, G, B = sw['eng'], sw['ses'], sw['T'], sw['G'], sw['B']
         evidenceOnly, forwardOnly = sw['evidenceOnly'], sw['forwardOnly']
         logE, local, alive, avg, buf, wave = sw['logE'], sw['local'], sw['alive'], sw['avg'], sw['buf'], sw['wave']
+        shift, weights = sw['shift'], sw['weights']
         if avg is not None:
             avg.zero_()
-        shift = -np.inf
-        logEHost = np.zeros(B)
+        shift.fill_(-math.inf)
         waves = 0
         for w0 in range(0, B, wave):
             w1 = min(B, w0 + wave)
@@ -767,39 +775,30 @@ class HyperStudy(Study):
             eng.run('forward', ses.plan,
                     _engine.F_EVIDENCE_ONLY if evidenceOnly else (0 if forwardOnly else _engine.F_RAW_ALPHA), **common)
             waves += 1
-            le = eng.to_host(logE[w0:w1])  # the evidences fix the averaging weights of this wave
-            logEHost[w0:w1] = le
             if evidenceOnly:
                 continue
-            lw = le + sw['logHp'][w0:w1]
-            finite = np.isfinite(lw)
-            if finite.any():
-                top = float(np.max(lw[finite]))
-                if top > shift:
-                    if np.isfinite(shift):
-                        eng.scale(ses.plan, avg, T * G, math.exp(shift - top))
-                    shift = top
+            # the evidences of the wave fix its averaging weights; a larger reference log-weight re-bases the sum
+            eng.wave_weights(ses.plan, logE[w0:w1], sw['logHpDev'][w0:w1], nb, shift, avg, T * G, weights[w0:w1])
             if not forwardOnly:
                 # smoothed posteriors overwrite the stored sequences in place; combos whose backward pass hits a
                 # zero norm flag themselves (alive = -1) and are dropped from the average as a whole (core.py:1358)
                 # (rows may come back unnormalised with their scale in rowScale, applied by the accumulation)
                 eng.run('backward', ses.plan, _engine.F_RAW_POSTERIOR, row_scale=sw['rowScale'], **common)
-            weights = eng.to_device(np.where(finite, lw - (shift if np.isfinite(shift) else 0.), -np.inf))
             # evidence-weighted sum over the combos of this wave, fixed summation order (deterministic)
-            eng.run('accumulate', ses.plan, 0, log_weight=weights, avg=avg,
+            eng.run('accumulate', ses.plan, 0, log_weight=weights[w0:w1], avg=avg,
                     row_scale=None if forwardOnly else sw['rowScale'], **common)
-        aliveHost = eng.to_host(alive)[:B]
-        logEHost = np.where(aliveHost == 1, logEHost, -np.inf)
         # averaged local evidence: sum_b localEvidence_b * hyperprior_b (core.py:1410)
         part = sw['part']
         part.zero_()
         if B > 0:
             eng.mix(ses.plan, local, sw['hpDev'], B, T, part)
-        logEAll, aliveAll = dist.gather_rows(eng, logEHost, aliveHost, sw['Ball'])
+        # cross-rank merge, all collectives enqueued back to back; ONE device -> host read of the evidences at the end
         localEv = dist.reduce_sum(eng, part)
         if not evidenceOnly:
             dist.rebase_and_reduce(eng, ses.plan, avg, shift, T * G)
             eng.finalize(ses.plan, avg, T, sw['means'], _engine.F_NORMALIZE_ROWS)
+        logEAll, aliveAll = dist.gather_rows(eng, logE[:B], alive[:B], sw['Ball'])
+        logEAll = np.where(aliveAll == 1, logEAll, -np.inf)
         self.sweepStats = dict(waves=waves, wave=wave, rows=sw['rows'], launches=eng.launch_count())
         return eng, logEAll, aliveAll, localEv, avg, sw['means']
 

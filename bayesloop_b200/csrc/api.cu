@@ -115,6 +115,7 @@ struct blg_plan {
     long long lik_cap;
     int *d_sm_state;  // per-SM arrival counters + per-combo claim flags (fast 1-D kernels with sm_assign)
     long long sm_state_cap;
+    double *d_factor;  // device scalar: re-base factor of blg_wave_weights / blg_rebase
     double *d_o2;  // tiled OnlineStudy step: unnormalised cells [B][G] + per-tile partial sums, kept between steps
     long long o2_cap;
     Opts opt;
@@ -256,6 +257,12 @@ int blg_plan_create(const blg_problem *p, blg_plan **out) {
     pl->sm_state_cap = 0;
     pl->d_o2 = nullptr;
     pl->o2_cap = 0;
+    pl->d_factor = nullptr;
+    if (cudaMalloc(&pl->d_factor, sizeof(double)) != cudaSuccess) {
+        cudaFree(pl->d_tables);
+        delete pl;
+        return fail("cudaMalloc of plan scalars failed");
+    }
     *out = pl;
     return 0;
 }
@@ -278,6 +285,7 @@ void blg_plan_destroy(blg_plan *pl) {
     if (pl->d_lik) cudaFree(pl->d_lik);
     if (pl->d_sm_state) cudaFree(pl->d_sm_state);
     if (pl->d_o2) cudaFree(pl->d_o2);
+    if (pl->d_factor) cudaFree(pl->d_factor);
     delete pl;
 }
 
@@ -955,6 +963,34 @@ int blg_scale(blg_plan *pl, double *x, int64_t count, double factor, void *strea
     const int nt = 256;
     scale_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(x, count, factor);
     ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int blg_wave_weights(blg_plan *pl, const double *log_evidence, const double *log_prior, int64_t B, double *shift,
+                     double *avg, int64_t count, double *log_weight, void *stream) {
+    if (!pl || !log_evidence || !log_prior || !shift || !log_weight) return fail("null argument");
+    if (B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    wave_weights_kernel<<<1, 1024, 0, st>>>(log_evidence, log_prior, B, shift, pl->d_factor, log_weight);
+    ++g_launches;
+    if (avg && count > 0) {
+        const int nt = 256;
+        scale_dev_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(avg, count, pl->d_factor);
+        ++g_launches;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int blg_rebase(blg_plan *pl, double *x, int64_t count, const double *from, const double *to, void *stream) {
+    if (!pl || !x || !from || !to) return fail("null argument");
+    if (count <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    rebase_factor_kernel<<<1, 1, 0, st>>>(from, to, pl->d_factor);
+    const int nt = 256;
+    scale_dev_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(x, count, pl->d_factor);
+    g_launches += 2;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -139,6 +139,47 @@ __global__ void accumulate_kernel(const double *__restrict__ seq, const double *
     avg[e] += s;
 }
 
+// One block: averaging weights of a wave relative to the running reference log-weight (blg_wave_weights).
+// factor[0] receives exp(old shift - new shift), the re-base of the running sum (1 when nothing moves).
+__global__ void __launch_bounds__(1024) wave_weights_kernel(const double *__restrict__ logE, const double *__restrict__ logPrior,
+                                                            long long B, double *__restrict__ shift,
+                                                            double *__restrict__ factor, double *__restrict__ logw) {
+    __shared__ double scratch[2 * kMaxWarps];
+    RedScratch rs;
+    rs.buf = scratch;
+    rs.phase = 0;
+    double top = -INFINITY;
+    for (long long b = threadIdx.x; b < B; b += blockDim.x) {
+        const double lw = logE[b] + logPrior[b];
+        if (isfinite(lw)) top = fmax(top, lw);
+    }
+    top = block_max(top, rs);
+    const double old = shift[0];
+    const double now = fmax(old, top);  // fmax ignores nothing here: both are -inf or finite
+    for (long long b = threadIdx.x; b < B; b += blockDim.x) {
+        const double lw = logE[b] + logPrior[b];
+        logw[b] = isfinite(lw) ? lw - now : -INFINITY;
+    }
+    __syncthreads();  // everybody has read shift[0]
+    if (threadIdx.x == 0) {
+        factor[0] = (isfinite(old) && now > old) ? exp(old - now) : 1.0;
+        shift[0] = now;
+    }
+}
+
+// x[i] *= f[0] with a device scalar; a factor of exactly 1 leaves the array untouched (no traffic)
+__global__ void scale_dev_kernel(double *__restrict__ x, long long count, const double *__restrict__ f) {
+    const double v = __ldg(f);
+    if (v == 1.0) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) x[i] *= v;
+}
+
+__global__ void rebase_factor_kernel(const double *__restrict__ from, const double *__restrict__ to, double *__restrict__ f) {
+    const double a = from[0], b = to[0];
+    f[0] = (isfinite(a) && isfinite(b) && b != a) ? exp(a - b) : 1.0;
+}
+
 __global__ void fill_kernel(double *__restrict__ x, long long count, double value) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < count) x[e] = value;

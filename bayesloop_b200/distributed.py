@@ -39,23 +39,23 @@ def shard_rows(B, rank=None, size=None):
 
 
 def gather_rows(eng, logE, alive, Ball):
-    """All-gather the per-rank log-evidence / alive arrays and put them back into hyper-grid row order."""
+    """All-gather the per-rank log-evidence / alive flags (device tensors) and return them on the host in hyper-grid
+    row order.  One collective of a packed [2 x width] block per rank and one device -> host copy."""
     rank, size = world()
     if size == 1:
-        return np.asarray(logE, dtype=float), np.asarray(alive)
+        return np.asarray(eng.to_host(logE), dtype=float), np.asarray(eng.to_host(alive)).astype(np.int64)
     width = -(-int(Ball) // size)
-    mine = np.full((2, width), np.nan)
-    mine[0, :len(logE)] = logE
-    mine[1, :len(alive)] = alive
-    send = eng.to_device(mine)
+    send = torch.full((2, width), float('nan'), dtype=torch.float64, device=logE.device)
+    send[0, :logE.shape[0]] = logE
+    send[1, :alive.shape[0]] = alive.to(torch.float64)
     recv = [torch.empty_like(send) for _ in range(size)]
     td.all_gather(recv, send)
+    host = eng.to_host(torch.stack(recv))
     outE, outA = np.empty(int(Ball)), np.empty(int(Ball))
-    for r, block in enumerate(recv):
+    for r in range(size):
         rows = shard_rows(Ball, r, size)
-        host = eng.to_host(block)
-        outE[rows] = host[0, :len(rows)]
-        outA[rows] = host[1, :len(rows)]
+        outE[rows] = host[r, 0, :len(rows)]
+        outA[rows] = host[r, 1, :len(rows)]
     return outE, outA.astype(np.int64)
 
 
@@ -84,13 +84,13 @@ def reduce_sum(eng, tensor):
 
 
 def rebase_and_reduce(eng, plan, avg, shift, count):
-    """Bring every rank's running average onto the common reference log-weight M = max_r shift_r and sum them."""
+    """Bring every rank's running average onto the common reference log-weight M = max_r shift_r and sum them
+    (the merge of core.py:1339-1340).  `shift` is a device scalar: max all-reduce, device-side re-base
+    (blg_rebase), sum all-reduce -- enqueued back to back, no host synchronisation in between."""
     if world()[1] == 1:
         return shift
-    top = eng.to_device(np.array([shift if np.isfinite(shift) else -1e308]))
+    top = shift.clone()
     td.all_reduce(top, op=td.ReduceOp.MAX)
-    M = float(eng.to_host(top)[0])
-    if np.isfinite(shift) and M > shift:
-        eng.scale(plan, avg, count, math.exp(shift - M))
+    eng.rebase(plan, avg, count, shift, top)
     td.all_reduce(avg, op=td.ReduceOp.SUM)
-    return M
+    return top

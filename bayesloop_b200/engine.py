@@ -209,6 +209,10 @@ class Engine:
                                    ctypes.c_uint32, ctypes.c_void_p]
         L.blg_mix.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                               ctypes.c_void_p, ctypes.c_void_p]
+        L.blg_wave_weights.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+        L.blg_rebase.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_void_p]
         L.blg_scale.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p]
         if L.blg_version() != 1:
             raise EngineError('ABI version mismatch in {}'.format(lib_path))
@@ -228,6 +232,9 @@ class Engine:
 
     def empty(self, shape, dtype=torch.float64):
         return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def full(self, shape, value, dtype=torch.float64):
+        return torch.full(shape if isinstance(shape, (tuple, list)) else (shape,), value, dtype=dtype, device=self.device)
 
     def zeros(self, shape, dtype=torch.float64):
         return torch.zeros(shape, dtype=dtype, device=self.device)
@@ -357,6 +364,16 @@ class Engine:
     def mix(self, plan, state, weight, K, n, out):
         self._check(self.lib.blg_mix(plan.handle, _ptr(state), _ptr(weight), int(K), int(n), _ptr(out),
                                      self.stream()))
+
+    def wave_weights(self, plan, log_evidence, log_prior, B, shift, avg, count, log_weight):
+        """Device-side averaging weights of one wave + re-base of the running sum (include/blgrid.h)."""
+        self._check(self.lib.blg_wave_weights(plan.handle, _ptr(log_evidence), _ptr(log_prior), int(B), _ptr(shift),
+                                              _ptr(avg), int(count) if avg is not None else 0, _ptr(log_weight),
+                                              self.stream()))
+
+    def rebase(self, plan, x, count, shift_from, shift_to):
+        self._check(self.lib.blg_rebase(plan.handle, _ptr(x), int(count), _ptr(shift_from), _ptr(shift_to),
+                                        self.stream()))
 
     def scale(self, plan, x, count, factor):
         self._check(self.lib.blg_scale(plan.handle, _ptr(x), int(count), float(factor), self.stream()))

@@ -174,6 +174,19 @@ int blg_accumulate(blg_plan *plan, const blg_inputs *in, const blg_outputs *out,
  * (the streaming form of np.logaddexp in core.py:1363; also exp(m_r - M) between ranks). */
 int blg_scale(blg_plan *plan, double *x, int64_t count, double factor, void *stream);
 
+/* Averaging weights of one wave of a sweep without a host round trip -- the streaming form of np.logaddexp in
+ * core.py:1358-1366.  With lw[b] = log_evidence[b] + log_prior[b], top = max of the finite lw and
+ * new = max(shift[0], top):  if shift[0] is finite and new > shift[0] the running sum is re-based,
+ * avg[i] *= exp(shift[0] - new) for i < count;  log_weight[b] = lw[b] - new (-inf where lw is not finite);
+ * shift[0] = new.  shift: device [1], -inf before the first wave; avg may be NULL with count = 0. */
+int blg_wave_weights(blg_plan *plan, const double *log_evidence, const double *log_prior, int64_t B, double *shift,
+                     double *avg, int64_t count, double *log_weight, void *stream);
+
+/* x[i] *= exp(from[0] - to[0]), i < count, with DEVICE scalars; nothing happens while from[0] is -inf (nothing was
+ * accumulated).  Brings a rank's running average onto the common reference log-weight after an all-reduce(max) of
+ * the ranks' shifts (merge of core.py:1339-1340) without reading the scalars back. */
+int blg_rebase(blg_plan *plan, double *x, int64_t count, const double *from, const double *to, void *stream);
+
 /* Row normalisation (optional) and posterior means of a [T][G] sequence: core.py:1379-1382, :480-483,
  * :1416-1419.  means is device [ndim][T]. */
 int blg_finalize(blg_plan *plan, double *seq, int64_t T, double *means, uint32_t flags, void *stream);

@@ -31,6 +31,26 @@ def test_golden_matches_reference_docs():
         assert abs(got - want) < 1e-5
 
 
+@pytest.mark.parametrize('name,wave', [('syn_hyper_poisson_sweep', 5), ('syn_hyper_poisson_sweep', 1),
+                                       ('syn_hyper_dead_combo', 1), ('syn_cps_gauss_2d', 7), ('ref_cps_coal_all', 10)])
+def test_sweep_in_several_waves_matches_the_golden(name, wave, use_oracle, monkeypatch):
+    """The device-side averaging across waves (blg_wave_weights: weights relative to a running reference log-weight,
+    re-base of the running sum when a later wave brings a larger evidence) reproduces the reference's
+    np.logaddexp accumulation (core.py:1358-1366) whatever the wave size."""
+    import bayesloop_b200 as bl
+    from bayesloop_b200 import core
+    plain = core.HyperStudy.__init__
+
+    def capped(self, *a, **kw):
+        plain(self, *a, **kw)
+        self.maxWave = wave
+
+    monkeypatch.setattr(core.HyperStudy, '__init__', capped)
+    S, got = parity.run_case(name, bl)
+    assert S.sweepStats['waves'] >= 2
+    parity.compare(name, got, load_golden(name), rtol=2e-9, atol_post=1e-13)
+
+
 def _online_study(bl):
     S = bl.OnlineStudy(storeHistory=False, silent=True)
     S.setOM(bl.om.ScaledAR1('rho', bl.oint(-1, 1, 24), 'sigma', bl.oint(0, 3, 28)), silent=True)
