@@ -942,7 +942,9 @@ class ChangepointStudy(HyperStudy):
             out.append(transitionModel)
         return out
 
-    def fit(self, forwardOnly=False, evidenceOnly=False, silent=False, nJobs=1):
+    def _prepareChangepoints(self, silent=False):
+        """Hyper-grid of a change-point study: Cartesian grid, then only the strictly ordered tuples of change-/
+        break-point times are kept and the prior mass of the full grid is restored (core.py:1777-1834)."""
         self._formatData()
         if len(list(flatten(self._unpackSerialTransitionModels(self.transitionModel)))) > 1:
             raise NotImplementedError('Multiple instances of SerialTransition models are currently not supported by '
@@ -975,6 +977,9 @@ class ChangepointStudy(HyperStudy):
         self.flatHyperPriorValues = self.allHyperPriorValues[self.mask]
         self.flatHyperPriorValues = self.flatHyperPriorValues * (np.sum(self.allHyperPriorValues) /
                                                                  np.sum(self.allHyperPriorValues[self.mask]))
+
+    def fit(self, forwardOnly=False, evidenceOnly=False, silent=False, nJobs=1):
+        self._prepareChangepoints(silent=silent)
         HyperStudy.fit(self, forwardOnly=forwardOnly, evidenceOnly=evidenceOnly, silent=silent, nJobs=nJobs,
                        customHyperGrid=True)
         full = np.zeros(len(self.allHyperGridValues))

@@ -454,6 +454,11 @@ bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, 
     else if (d.G <= 96 * 11) M = 11;
     else if (d.G <= 224 * 11) { M = 11; nt = 256; }
     else return false;
+    if (pl->opt.ws_m > 0 && pl->opt.ws_nt > 0 && (pl->opt.ws_nt / 32 - 1) * 32 * pl->opt.ws_m >= d.G &&
+        fwd_fast1d_ws_entry(pl->opt.ws_m, pl->opt.ws_nt)) {  // tuning override: (cells per thread, threads)
+        M = pl->opt.ws_m;
+        nt = pl->opt.ws_nt;
+    }
     const int halo = even_up(pg.max_radius[0] + 2 * M);
     if (halo > d.G) return false;
     a.halo = halo;

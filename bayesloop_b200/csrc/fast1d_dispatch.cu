@@ -32,6 +32,8 @@ BLG_WS(3, 128)
 BLG_WS(7, 128)
 BLG_WS(11, 128)
 BLG_WS(11, 256)
+BLG_WS(9, 160)
+BLG_WS(7, 192)
 #undef BLG_WS
 
 PassKernel fwd_fast1d_ws_entry(int M, int nt) {
@@ -39,6 +41,8 @@ PassKernel fwd_fast1d_ws_entry(int M, int nt) {
     if (nt == 128 && M == 7) return fwd_fast1d_ws_m7_nt128();
     if (nt == 128 && M == 11) return fwd_fast1d_ws_m11_nt128();
     if (nt == 256 && M == 11) return fwd_fast1d_ws_m11_nt256();
+    if (nt == 160 && M == 9) return fwd_fast1d_ws_m9_nt160();
+    if (nt == 192 && M == 7) return fwd_fast1d_ws_m7_nt192();
     return nullptr;
 }
 
@@ -47,6 +51,8 @@ PassKernel bwd_fast1d_ws_entry(int M, int nt) {
     if (nt == 128 && M == 7) return bwd_fast1d_ws_m7_nt128();
     if (nt == 128 && M == 11) return bwd_fast1d_ws_m11_nt128();
     if (nt == 256 && M == 11) return bwd_fast1d_ws_m11_nt256();
+    if (nt == 160 && M == 9) return bwd_fast1d_ws_m9_nt160();
+    if (nt == 192 && M == 7) return bwd_fast1d_ws_m7_nt192();
     return nullptr;
 }
 

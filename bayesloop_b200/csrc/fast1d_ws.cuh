@@ -116,11 +116,27 @@ __device__ __forceinline__ WsRoles ws_roles(int slot, int n) {
     return r;
 }
 
-// Control block of the ws kernels (doubles at a.ws_ctl): [0],[1] normaliser by step parity, [2] (as int) dead flag.
+// Control block of the ws kernels (doubles at a.ws_ctl): [0],[1] scale factor by step parity, [2] (as int) dead flag.
+//
+// LAGGED SCALE (round 2).  The state is kept unnormalised; the only reason to scale it at all is to keep its magnitude
+// in range.  Round 1 applied the exact normaliser of the PREVIOUS step, which the service warp produces ~400 cycles
+// after the step barrier: the compute warps of short steps waited for it at a second (named) barrier -- 13 % of
+// their stall samples in profiles/r1j_regions_c2_c3.txt.  Now step t multiplies by
+//         k_t = s_{t-2}^(-3/4),     s_j = sum of the unnormalised state after step j,
+// a value that has been in shared memory since the service warp passed the barrier of step t-1, so ONE CTA barrier
+// per step remains and nobody waits for the service warp.  With u_t = conv(u_{t-1}) * k_t * lik_t the log-magnitude
+// obeys x_t = x_{t-1} - 3/4 x_{t-2} + log(norm_t): a damped recursion (|roots| = 0.87, fixed point 4/3 log(norm));
+// the exponent 1 would be marginally stable (|roots| = 1) and random-walk out of range over 10^4 steps.  The true
+// evidence increment is recovered exactly by the service warp, norm_t = s_t / (k_t * s_{t-1}) (core.py:385), rows are
+// normalised with the exact 1/s_t, or leave unnormalised (BLG_F_RAW_ALPHA / BLG_F_RAW_POSTERIOR) by one bulk store.
+__device__ __forceinline__ double lagged_scale(double s) {  // s^(-3/4) to a few ulp (any positive factor would do)
+    const double r = rsqrt(s);
+    return r * sqrt(r);
+}
 
 // ------------------------------------------------------------------------------------------------ K1w forward
 template <int M, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT) fwd_fast1d_ws_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(const PassArgs a) {
     constexpr int NW = NT / 32, NCOMP = (NW - 1) * 32;
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
@@ -166,13 +182,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) fwd_fast1d_ws_kernel(const PassA
     __syncthreads();
     const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
     const bool first = (a.flags & BLG_F_TRANSITION_FIRST) != 0;
+    // a backward pass follows (it is scale-free per row): rows leave unnormalised by one bulk-async copy per step
+    const bool rawRows = store && a.use_bulk != 0 && (a.flags & BLG_F_RAW_ALPHA);
 
     if (!r.service) {
         // ------------------------------------------------------------------ compute warps
         double *cur = s.buf0, *nxt = s.buf1;
         const double *likp = a.lik_table + r.ct;
         const long long pitch = a.lik_pitch;
-        double kappa = 1.0;
         double lk[M];  // likelihood of this thread's cells, fetched one step ahead (right after the previous use)
         if (r.owner) {
 #pragma unroll
@@ -189,11 +206,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) fwd_fast1d_ws_kernel(const PassA
                     for (int m = 0; m < M; ++m) v[m] = cur[r.i0 + m];
                 }
             }
-            if (t > 0) {  // normaliser of the previous step, produced by the service warp during the convolution
-                named_sync(1, NT);
-                if (*deadFlag) break;
-                kappa = ctl[(t - 1) & 1];
-            }
+            // lagged scale k_t: written by the service warp before it arrived at the barrier of step t-1
+            const double kappa = t >= 2 ? ctl[t & 1] : 1.0;
             if (r.owner) {
                 // alpha <- prior * likelihood (core.py:375-382); cells beyond the grid carry lik = 0
 #pragma unroll
@@ -205,7 +219,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) fwd_fast1d_ws_kernel(const PassA
                 store_cells_mirrored<M>(nxt, r.i0, n, halo, v);
                 PP[r.ct] = tree_sum<M>(v);
             }
+            if (rawRows) fence_proxy_async();  // the new state is read by the service warp's bulk-async row store
             __syncthreads();  // new state and its partial sums are visible to everybody
+            if (*deadFlag) break;  // set by the service warp after the barrier of an EARLIER step
             double *tmp = cur;
             cur = nxt;
             nxt = tmp;
@@ -214,48 +230,66 @@ __global__ void __launch_bounds__(NT, 512 / NT) fwd_fast1d_ws_kernel(const PassA
         // ------------------------------------------------------------------ service warp
         double *seq = store ? a.alpha_seq + b * T * (long long)n : nullptr;
         const bool vec = a.use_bulk != 0;  // rows are 16-byte aligned
+        const bool raw = rawRows;
+        const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
         LogProduct lp;
         lp.init();
         bool dead = false;
+        double sPrev = 1.0;            // s_{t-1}; the initial state enters as it is (core.py:363, :382)
+        double kNow = 1.0, kNext = 1.0;  // k_t, k_{t+1}
         for (long long t = 0; t < T; ++t) {
             __syncthreads();
+            if (dead) break;  // the compute warps have seen the flag behind this barrier
             double part = 0.0;
 #pragma unroll
             for (int j = 0; j < NCOMP / 32; ++j) part += PP[j * 32 + r.lane];
-            const double norm = warp_sum(part);  // core.py:385
-            if (!(norm > 0.0)) {                 // core.py:388-400
+            const double st_sum = warp_sum(part);
+            const double kAfter = lagged_scale(st_sum);  // k_{t+2}
+            if (r.lane == 0) ctl[t & 1] = kAfter;
+            const double norm = fast_div(st_sum, kNow * sPrev);  // core.py:385: evidence increment of step t
+            if (!(st_sum > 0.0) || !(norm > 0.0) || isinf(st_sum)) {  // core.py:388-400
                 dead = true;
                 if (r.lane == 0) *deadFlag = 1;
-                if (t + 1 < T) named_arrive(1, NT);
-                break;
+                continue;  // one more barrier: the compute warps read the flag behind it
             }
-            const double kappa = fast_rcp(norm);
-            if (r.lane == 0) ctl[t & 1] = kappa;
-            if (t + 1 < T) named_arrive(1, NT);
             const double *st = (t & 1) ? s.buf0 : s.buf1;  // the buffer the compute warps just filled
-            if (store) {  // core.py:389, :408 -- normalised filtering distribution
+            if (raw) {
+                // the row leaves unnormalised, straight out of the state buffer; the buffer is rewritten by the compute
+                // warps after the NEXT barrier, so the copy must have read it before this warp arrives there
+                if (r.lane == 0) {
+                    fence_proxy_async();
+                    bulk_store(seq + t * (long long)n, st, rowBytes);
+                }
+            } else if (store) {  // core.py:389, :408 -- normalised filtering distribution
+                const double inv = fast_rcp(st_sum);
                 double *row = seq + t * (long long)n;
                 if (vec) {
                     for (int j = 2 * r.lane; j < n; j += 64) {
                         double2 x = *reinterpret_cast<const double2 *>(st + j);
-                        x.x *= kappa;
-                        x.y *= kappa;
+                        x.x *= inv;
+                        x.y *= inv;
                         __stcs(reinterpret_cast<double2 *>(row + j), x);
                     }
                 } else {
-                    for (int j = r.lane; j < n; j += 32) __stcs(row + j, st[j] * kappa);
+                    for (int j = r.lane; j < n; j += 32) __stcs(row + j, st[j] * inv);
                 }
             }
             if ((a.flags & BLG_F_SAVE_STATE) && a.final_state && t == T - 1) {
+                const double inv = fast_rcp(st_sum);
                 double *fs = a.final_state + b * (long long)n;
-                for (int j = r.lane; j < n; j += 32) fs[j] = st[j] * kappa;
+                for (int j = r.lane; j < n; j += 32) fs[j] = st[j] * inv;
             }
             if (r.lane == 0) {
                 lp.mul(norm);                                         // core.py:403
                 if (a.local) a.local[b * T + t] = norm * pb.lc_prod;  // core.py:404
+                if (raw) bulk_wait_read<0>();
             }
+            sPrev = st_sum;
+            kNow = kNext;
+            kNext = kAfter;
         }
         if (r.lane == 0) {
+            if (raw) bulk_wait_all();
             double logE = lp.log_value();
             if (dead)
                 logE = -INFINITY;
@@ -270,7 +304,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fwd_fast1d_ws_kernel(const PassA
 
 // ------------------------------------------------------------------------------------------------ K2w backward
 template <int M, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(const PassArgs a) {
     constexpr int NW = NT / 32, NCOMP = (NW - 1) * 32;
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
@@ -314,6 +348,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassA
         fence_proxy_async();
     }
     __syncthreads();
+    const bool rawRows = a.row_scale != nullptr;  // BLG_F_RAW_POSTERIOR: rows leave unnormalised + their factor
 
     if (!r.service) {
         // ------------------------------------------------------------------ compute warps
@@ -324,7 +359,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassA
         double beta[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) beta[m] = (r.owner && r.i0 + m < n) ? 1.0 / (double)n : 0.0;  // core.py:424-425
-        double kb = 1.0;  // keeps the (scale-free) beta recursion in range: 1 / sum(beta) of the previous step
         double lk[M];  // likelihood of this thread's cells, fetched one step ahead (right after the previous use)
         if (r.owner) {
 #pragma unroll
@@ -345,10 +379,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassA
                     for (int m = 0; m < M; ++m)
                         if (r.i0 + m >= n) beta[m] = 0.0;
                 }
-                named_sync(1, NT);
-                if (*deadFlag) break;
-                kb = ctl[(i + 1) & 1];
             }
+            // keeps the (scale-free) beta recursion in range: lagged power of sum(beta) two steps back (see lagged_scale)
+            const double kb = i <= T - 3 ? ctl[i & 1] : 1.0;
             mbar_wait(&bars[sb], (phases >> sb) & 1u);
             phases ^= 1u << sb;
             double *A = S0 + sb * Gp;
@@ -377,16 +410,19 @@ __global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassA
                 }
                 store_cells_mirrored<M>(nxt, r.i0, n, halo, st);
                 PP[r.ct] = spu0 + spu1;
-                PP[NCOMP + r.ct] = tree_sum<M>(beta);
+                PP[NCOMP + r.ct] = tree_sum<M>(st);  // sum of the new state (magnitude control only)
                 PP[2 * NCOMP + r.ct] = sql0 + sql1;
             }
+            if (rawRows) fence_proxy_async();  // alpha * beta in the ring slot is read by the bulk-async row store
             __syncthreads();
+            if (*deadFlag) break;
             double *tmp = cur;
             cur = nxt;
             nxt = tmp;
         }
     } else {
         // ------------------------------------------------------------------ service warp
+        const bool raw = rawRows;
         if (r.lane == 0) {
             bulk_load(S0 + ((T - 1) & 1) * Gp, seq + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) & 1]);
             if (T >= 2) bulk_load(S0 + ((T - 2) & 1) * Gp, seq + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) & 1]);
@@ -396,46 +432,57 @@ __global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassA
         for (; i >= 0; --i) {
             const int sb = (int)(i & 1);
             __syncthreads();
-            double spu = 0.0, sbeta = 0.0, sql = 0.0;
+            if (dead) break;
+            double spu = 0.0, sstate = 0.0, sql = 0.0;
 #pragma unroll
             for (int j = 0; j < NCOMP / 32; ++j) {
                 spu += PP[j * 32 + r.lane];
-                sbeta += PP[NCOMP + j * 32 + r.lane];
+                sstate += PP[NCOMP + j * 32 + r.lane];
                 sql += PP[2 * NCOMP + j * 32 + r.lane];
             }
             spu = warp_sum(spu);
-            sbeta = warp_sum(sbeta);
+            sstate = warp_sum(sstate);
             sql = warp_sum(sql);
-            if (!(spu > 0.0) || !(sbeta > 0.0)) {  // core.py:440-452
+            if (r.lane == 0) ctl[i & 1] = lagged_scale(sstate);  // used by step i-2
+            if (!(spu > 0.0) || !(sstate > 0.0) || isinf(sstate)) {  // core.py:440-452
                 dead = true;
                 if (r.lane == 0) *deadFlag = 1;
-                if (i > 0) named_arrive(1, NT);
-                break;
+                continue;
             }
             const double inv = fast_rcp(spu);  // posterior = alpha*beta / sum(alpha*beta)   core.py:439-441
-            if (r.lane == 0) ctl[i & 1] = fast_rcp(sbeta);  // core.py:470, applied lazily by the compute warps
-            if (i > 0) named_arrive(1, NT);
             double *row = seq + i * (long long)n;
-            const double *P = S0 + sb * Gp;
-            for (int j = 2 * r.lane; j < n; j += 64) {
-                double2 x = *reinterpret_cast<const double2 *>(P + j);
-                x.x *= inv;
-                x.y *= inv;
-                __stcs(reinterpret_cast<double2 *>(row + j), x);
+            double *P = S0 + sb * Gp;
+            if (raw) {
+                if (r.lane == 0) {
+                    fence_proxy_async();
+                    bulk_store(row, P, rowBytes);
+                    a.row_scale[b * T + i] = inv;
+                }
+            } else {
+                for (int j = 2 * r.lane; j < n; j += 64) {
+                    double2 x = *reinterpret_cast<const double2 *>(P + j);
+                    x.x *= inv;
+                    x.y *= inv;
+                    __stcs(reinterpret_cast<double2 *>(row + j), x);
+                }
             }
             __syncwarp();
             if (r.lane == 0) {
+                if (a.local) a.local[b * T + i] = fast_div(spu, sql * pb.lc_prod);  // 1/(sum(post/lik)*lc)  core.py:463
+                if (raw) bulk_wait_read<0>();
                 if (i >= 2) {  // the slot is free again: prefetch alpha[i-2] into it
                     fence_proxy_async();
-                    bulk_load(S0 + sb * Gp, seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
+                    bulk_load(P, seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
                 }
-                if (a.local) a.local[b * T + i] = fast_div(spu, sql * pb.lc_prod);  // 1/(sum(post/lik)*lc)  core.py:463
             }
         }
         if (dead) {
-            // drain the prefetch that is still in flight before the CTA's shared memory is released
-            if (i >= 1) {
-                const long long rr = i - 1;
+            // drain the prefetch that is still in flight before the CTA's shared memory is released: the step that died
+            // (index i + 1 after the loop's decrement and the extra barrier) consumed its slot; the other slot holds the
+            // load issued one step earlier
+            const long long died = i + 1;
+            if (died >= 1) {
+                const long long rr = died - 1;
                 mbar_wait(&bars[rr & 1], (uint32_t)(((T - 1 - rr) >> 1) & 1));
             }
             if (r.lane == 0) {
@@ -443,6 +490,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bwd_fast1d_ws_kernel(const PassA
                 if (a.alive) a.alive[b] = -1;
             }
         }
+        if (raw && r.lane == 0) bulk_wait_all();
         trace_end_lane0(a, r.lane);
     }
 }

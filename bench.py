@@ -1,28 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- grid-cell updates / second of a HyperStudy sweep (BASELINE.json metric), one JSON line on rank 0.
+"""bench.py -- grid-cell updates / second of the bayesloop sweeps (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py --gpus 1 --steps 5 --warmup 3                       # this repo's CUDA engine
+    python bench.py --gpus 1 --steps 5 --warmup 3                       # this repo's CUDA engine, headline config C2
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus 8 --steps 5 --warmup 3                       # one rank per GPU, NCCL
+    python bench.py --config c3 --gpus 1                                # make another BASELINE config the headline
     python bench.py --impl reference --gpus 1 --steps 2 --warmup 1      # reference CPU path (NumPy port), host cores
 
-Workload (config.workload): BASELINE.json configs[1] = "C2": HyperStudy, Poisson observation model on a 1-D grid
-of 1000 rates, GaussianRandomWalk sigma sweep of 512 values PER GPU (weak scaling: 512*N values of the same
-interval), synthetic Poisson counts T = 10000 (seed 1).  A "step" is one complete
-HyperStudy.fit: forward filter + backward smoother + evidence-weighted averaging of all combinations = 2*B*T*G
-grid-cell updates.
+Workloads (BASELINE.json configs, inputs of SURVEY.md section 8d; one "step" = one complete fit of the study):
 
-  value      sweep with inputs already resident in HBM (CUDA events, max over ranks)
-  e2e        the same through the public API bl.HyperStudy(...).fit() with HOST (NumPy) inputs and results:
-             host->device copies of data/program and device->host copies of the averaged posterior sequence,
-             means and evidences inside the timed region
-  roofline   dominant kernel: algorithmic HBM bytes per launch / live CUDA-event duration, vs MEASURED_PEAKS.json
-  roofline.fp64 the binding unit of this workload: convolution flop per pass / kernel time vs the measured DFMA peak
-  cpu_baseline  oracle/np_oracle.py (NumPy+SciPy port of the reference loop) on a bounded sample, 1 core
-  extra.c2_narrow   the same sweep with sigma <= 0.05 (radius <= 17): the HBM-leaning regime (N = 1 only)
-  extra.c3_sample   bounded sample of BASELINE.json configs[2] (256 x 256 grid) on the cluster-resident kernels (N = 1)
+  c2  (default headline, configs[1])  HyperStudy, Poisson 1-D grid 1000, GaussianRandomWalk sigma sweep, T = 10000.
+      512 sigma values PER GPU (weak scaling: cint(0, 0.2, 512 N)); full fit = 2 B T G cell updates.
+  c3  (configs[2])  HyperStudy, Gaussian 256 x 256 grid, GRW on both parameters, the FULL 64 x 64 hyper-grid (4096
+      combinations), steady-state window of the first 200 time steps, STRONG scaling: 4096 / N
+      combinations per rank, evidence all-gather + all-reduce of the [T x G] average inside the timed region.
+  c4  (configs[3])  change-point study, Gaussian 200 x 200 grid, 100 change-points x 10 x 10 random-walk widths =
+      10000 combinations, window of 400 time steps with the change-points spread over it, STRONG scaling.
+  c5  (configs[4])  OnlineStudy, ScaledAR1 512 x 512 grid, 256 hypotheses (240 GRW pairs + 15 RegimeSwitch + 1
+      Independent), window of 200 steps, hypotheses dealt over the ranks (STRONG), one all-gather per step.
+
+The headline line carries `value` (inputs resident in HBM, CUDA events, max over ranks), `e2e` (public API with HOST
+inputs/results), `roofline` (dominant kernel, algorithmic bytes / live event time vs MEASURED_PEAKS.json),
+`cpu_baseline` (NumPy port of the reference loop on a bounded sample, 1 core).  With the default headline (c2) the
+other three configs are measured too and reported under `extra` at EVERY N, so the driver's 1/2/4/8-GPU runs also
+record the strong scaling of c3 / c4 / c5 (each with its collective share).
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -35,27 +40,163 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GRID = 1000
-T_FULL = 10000
-COMBOS_PER_GPU = 512
-SIGMA_MAX = 0.2  # "reference-like" sweep of SURVEY.md 8d: sigma_n <= 16.7 grid cells, kernel radius <= 67
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+FP64_LANES = 58.5          # tools/micro/dfma_bench.cu on B200: DFMA lanes / clk / SM
+BYTES_PER_CELL = {'forward': 8.0, 'backward': 16.0, 'accumulate': 8.0}  # algorithmic HBM bytes
 
 
+# ------------------------------------------------------------------------------------------------ workloads
 def synthetic_counts(T, seed=1):
     rng = np.random.default_rng(seed)
     lam = 3.0 + 2.0 * np.sin(2.0 * np.pi * np.arange(T) / 2000.0)
     return rng.poisson(lam).astype(np.float64)
 
 
-def build_study(bl, counts, n_sigma, grid, sigma_max, engine=None):
-    S = bl.HyperStudy(silent=True, engine=engine)
-    S.loadData(counts, silent=True)
-    S.set(bl.om.Poisson('rate', bl.oint(0, 12, grid)),
-          bl.tm.GaussianRandomWalk('sigma', bl.cint(0, sigma_max, n_sigma), target='rate'), silent=True)
-    return S
+def gauss_series(T, seed, jump_at=None):
+    rng = np.random.default_rng(seed)
+    mu = np.clip(np.cumsum(rng.normal(0, 0.02, T)), -2, 2)
+    if jump_at is not None:
+        mu[jump_at:] += 1.5
+    sd = np.clip(1.0 + np.cumsum(rng.normal(0, 0.01, T)), 0.5, 2.0)
+    return rng.normal(mu, sd)
 
 
+def ar1_series(T, seed=4):
+    rng = np.random.default_rng(seed)
+    x = np.zeros(T)
+    for i in range(1, T):
+        x[i] = 0.6 * x[i - 1] + rng.normal(0, 1.0)
+    return x
+
+
+class C2:
+    key, scaling, kind = 'c2', 'weak', 'sweep'
+
+    def __init__(self, args, world):
+        self.T, self.G, self.sigma_max = args.T or 10000, args.grid, args.sigma_max
+        self.B = args.combos * world
+        self.world = world
+        self.data = synthetic_counts(self.T)
+        self.shape = (self.G,)
+
+    def study(self, bl, engine=None, T=None, sigma_max=None):
+        S = bl.HyperStudy(silent=True, engine=engine)
+        S.loadData(self.data[:T or self.T], silent=True)
+        S.set(bl.om.Poisson('rate', bl.oint(0, 12, self.G)),
+              bl.tm.GaussianRandomWalk('sigma', bl.cint(0, sigma_max or self.sigma_max, self.B), target='rate'),
+              silent=True)
+        return S
+
+    def describe(self):
+        per = self.B // self.world
+        return {'workload': 'C2 HyperStudy: Poisson 1-D grid=%d, GaussianRandomWalk sigma sweep cint(0,%g,%d) '
+                            '(%d per GPU), synthetic counts T=%d, full fit (forward+backward+averaging)'
+                            % (self.G, self.sigma_max, self.B, per, self.T),
+                'grid': self.G, 'T': self.T, 'combos': self.B, 'combos_per_gpu': per, 'sigma_max': self.sigma_max,
+                'parallelism': 'combos sharded over %d rank(s)' % self.world,
+                'l2': 'working set per step (alpha sequences, %.1f GB/GPU) exceeds the 126 MB L2; no explicit flush'
+                      % (per * self.T * self.G * 8 / 1e9)}
+
+
+class C3:
+    key, scaling, kind = 'c3', 'strong', 'sweep'
+
+    def __init__(self, args, world):
+        self.T, self.n, self.h = args.T or 200, 256, args.hyper
+        self.G, self.B, self.world = self.n * self.n, self.h * self.h, world
+        self.data = gauss_series(self.T, 2)
+        self.shape = (self.n, self.n)
+
+    def study(self, bl, engine=None, T=None):
+        S = bl.HyperStudy(silent=True, engine=engine)
+        S.loadData(self.data[:T or self.T], silent=True)
+        S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, self.n), 'std', bl.oint(0, 3, self.n)),
+              bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, self.h), target='mean'),
+                                            bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, self.h), target='std')),
+              silent=True)
+        return S
+
+    def describe(self):
+        return {'workload': 'C3 HyperStudy: Gaussian 2-D grid %dx%d, GaussianRandomWalk on both parameters, full %dx%d '
+                            'hyper-grid (%d combos), steady-state window of %d time steps, full fit'
+                            % (self.n, self.n, self.h, self.h, self.B, self.T),
+                'grid': [self.n, self.n], 'T': self.T, 'combos': self.B, 'combos_per_gpu': self.B // self.world,
+                'parallelism': 'combos dealt over %d rank(s); all-gather of evidences + all-reduce of the [T x G] average'
+                               % self.world,
+                'l2': 'alpha sequences of a wave (%.1f GB per rank) exceed the 126 MB L2; no explicit flush'
+                      % (min(self.B // self.world, 1400) * self.T * self.G * 8 / 1e9)}
+
+
+class C4(C3):
+    key = 'c4'
+
+    def __init__(self, args, world):
+        self.T, self.n = args.T or 400, 200
+        self.ncp, self.hs = args.changepoints, 10
+        self.G, self.B, self.world = self.n * self.n, self.ncp * self.hs * self.hs, world
+        self.data = gauss_series(self.T, 3, jump_at=self.T // 2)
+        self.shape = (self.n, self.n)
+
+    def study(self, bl, engine=None, T=None):
+        T = T or self.T
+        S = bl.ChangepointStudy(silent=True, engine=engine)
+        S.loadData(self.data[:T], silent=True)
+        ncp = min(self.ncp, T - 2)
+        step = max(1, T // ncp)
+        points = np.arange(step // 2, T - 1, step)[:ncp]
+        S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, self.n), 'std', bl.oint(0, 3, self.n)),
+              bl.tm.CombinedTransitionModel(bl.tm.ChangePoint('tChange', points),
+                                            bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, self.hs), target='mean'),
+                                            bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, self.hs), target='std')),
+              silent=True)
+        return S
+
+    def describe(self):
+        return {'workload': 'C4 ChangepointStudy: Gaussian 2-D grid %dx%d, %d change-points x %dx%d random-walk widths '
+                            '(%d combos), window of %d time steps with the change-points spread over it, full fit'
+                            % (self.n, self.n, self.ncp, self.hs, self.hs, self.B, self.T),
+                'grid': [self.n, self.n], 'T': self.T, 'combos': self.B, 'combos_per_gpu': self.B // self.world,
+                'parallelism': 'combos dealt over %d rank(s); all-gather of evidences + all-reduce of the [T x G] average'
+                               % self.world,
+                'l2': 'alpha sequences of a wave exceed the 126 MB L2; no explicit flush'}
+
+
+class C5:
+    key, scaling, kind = 'c5', 'strong', 'online'
+
+    def __init__(self, args, world):
+        self.T, self.n = args.T or 200, 512
+        self.G, self.B, self.world = self.n * self.n, 256, world
+        self.lead = 12
+        self.data = ar1_series(self.T + self.lead + 1)
+        self.shape = (self.n, self.n)
+
+    def study(self, bl, engine=None, T=None):
+        S = bl.OnlineStudy(storeHistory=False, silent=True, engine=engine)
+        S.setOM(bl.om.ScaledAR1('rho', bl.oint(-1, 1, self.n), 'sigma', bl.oint(0, 3, self.n)), silent=True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            S.add('normal', bl.tm.CombinedTransitionModel(
+                bl.tm.GaussianRandomWalk('s1', bl.cint(0, 0.03, 16), target='rho'),
+                bl.tm.GaussianRandomWalk('s2', bl.cint(0, 0.03, 15), target='sigma')))
+            S.add('chaotic', bl.tm.RegimeSwitch('p', bl.cint(-10, -3, 15)))
+            S.add('indep', bl.tm.Independent())
+        return S
+
+    def describe(self):
+        return {'workload': 'C5 OnlineStudy: ScaledAR1 2-D grid %dx%d, 256 hypotheses (240 GRW pairs + 15 RegimeSwitch + '
+                            '1 Independent), window of %d step() calls after %d lead-in steps'
+                            % (self.n, self.n, self.T, self.lead),
+                'grid': [self.n, self.n], 'T': self.T, 'combos': self.B, 'combos_per_gpu': self.B // self.world,
+                'parallelism': 'hypotheses dealt over %d rank(s); one all-gather of 256 evidence increments per step'
+                               % self.world,
+                'l2': 'hypothesis states (%.0f MB per rank) exceed the 126 MB L2; no explicit flush'
+                      % (self.B // self.world * self.G * 8 / 1e6)}
+
+
+WORKLOADS = {'c2': C2, 'c3': C3, 'c4': C4, 'c5': C5}
+
+
+# ------------------------------------------------------------------------------------------------ helpers
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -109,68 +250,339 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at this workload, from the committed
-    `ncu --set full` capture (profiles/r1_ncu_summary.json); None if the capture does not cover it."""
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r1_ncu_summary.json')) as f:
-            entry = json.load(f)['bench_c2'][kernel]
-        return float(entry['dram_bytes_read']) + float(entry['dram_bytes_write'])
-    except Exception:
-        return None
+def ncu_traffic(config, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at this workload from the committed
+    `ncu --set full` captures (profiles/*_ncu_summary.json, written by tools/ncu_summary.py); the newest capture that
+    covers the kernel wins and its tag is reported, so a stale number is visible as such."""
+    best = (None, None)
+    pdir = os.path.join(ROOT, 'profiles')
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if not name.endswith('_ncu_summary.json'):
+            continue
+        try:
+            with open(os.path.join(pdir, name)) as f:
+                entry = json.load(f).get('bench_' + config, {}).get(kernel)
+            if entry:
+                best = (float(entry['dram_bytes_read']) + float(entry['dram_bytes_write']), name)
+        except Exception:
+            continue
+    return best
 
 
 def hbm_peak():
-    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
             return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
     except Exception:
         return FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md)'
 
 
-def cpu_port_sample(counts, grid, sigma_max, n_sigma_total, rows, T_cpu):
-    """Reference-style NumPy loop (oracle/np_oracle.py) on `rows` of the sweep and the first T_cpu data points.
-    Returns (cell updates, seconds).  The lowering comes from the product's host code; the arithmetic timed here
-    is NumPy/SciPy only."""
+def taps_of(sw):
+    """Convolution taps per cell and step of every combo of a prepared sweep (sum over its GRW operators)."""
+    radius = np.asarray(sw['program'].host['radius'], dtype=float)
+    param = np.asarray(sw['program'].host['param'], dtype=float)
+    grw = np.array([k == 1 for k in sw['program'].kinds], dtype=bool)
+    if radius.size == 0 or not grw.any():
+        return np.zeros(len(radius))
+    active = (radius[:, grw] > 0) & (param[:, grw] > 0)
+    return np.where(active, 2.0 * radius[:, grw] + 1.0, 0.0).sum(axis=1)
+
+
+class Timers:
+    """CUDA-event brackets around engine calls and collectives, on the launching (current) stream."""
+
+    def __init__(self, torch):
+        self.torch, self.on, self.events = torch, False, []
+
+    def wrap(self, label, fn, name_of=None):
+        def timed(*a, **kw):
+            if not self.on:
+                return fn(*a, **kw)
+            e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            self.events.append((label(*a, **kw) if callable(label) else label, e0, e1, name_of() if name_of else None))
+            return out
+        return timed
+
+    def collect(self):
+        ms, names = {}, {}
+        for label, e0, e1, name in self.events:
+            ms.setdefault(label, []).append(e0.elapsed_time(e1))
+            if name:
+                names[label] = name
+        self.events = []
+        return ms, names
+
+
+def measure_sweep(wl, bl, eng, torch, td, world, steps, warmup, local_rank, e2e=True, clocks=False):
+    """Device-resident sweep (`value`), per-kernel and per-collective event times, optional end-to-end fit."""
+    from bayesloop_b200 import distributed as dist
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    timers = Timers(torch)
+    plain_run = eng.run
+    eng.run = timers.wrap(lambda which, *a, **kw: which, plain_run, name_of=eng.last_kernel)
+    plain = {k: getattr(dist, k) for k in ('rebase_and_reduce', 'gather_rows', 'reduce_sum')}
+    for k, fn in plain.items():
+        setattr(dist, k, timers.wrap('collective:' + k, fn))
+    try:
+        S = wl.study(bl)
+        S._formatData()
+        if hasattr(S, '_prepareChangepoints'):
+            S._prepareChangepoints(silent=True)
+        else:
+            S._createHyperGrid(silent=True)
+        sw = S._prepareSweep(False, False)
+        taps = taps_of(sw)
+        for _ in range(warmup):
+            S._executeSweep(sw)
+        launches0 = eng.launch_count()
+        sampler = ClockSampler(local_rank) if clocks else contextlib.nullcontext()
+        with sampler as clk:
+            barrier()
+            timers.on = True
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                res = S._executeSweep(sw)
+            e1.record()
+            barrier()
+            timers.on = False
+        dev_ms = e0.elapsed_time(e1) / steps
+        launches = (eng.launch_count() - launches0) // max(1, steps)
+        ms, names = timers.collect()
+        stats = dict(S.sweepStats)
+        logE_best = float(np.max(res[1])) if len(res[1]) else float('nan')
+        n_local = sw['B']
+        del sw, res
+        torch.cuda.empty_cache()
+        e2e_ms, logE = None, None
+        if e2e:
+            for _ in range(min(warmup, 2)):
+                S2 = wl.study(bl)
+                S2.fit(silent=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                S2 = wl.study(bl)
+                S2.fit(silent=True)
+            barrier()
+            e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+            logE = float(S2.logEvidence)
+            del S2
+            torch.cuda.empty_cache()
+    finally:
+        eng.run = plain_run
+        for k, fn in plain.items():
+            setattr(dist, k, fn)
+    times = torch.tensor([dev_ms, e2e_ms or 0.0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        td.all_reduce(times, op=td.ReduceOp.MAX)
+    dev_ms, e2e_max = [float(x) for x in times.cpu()]
+    return dict(dev_ms=dev_ms, e2e_ms=e2e_max if e2e else None, ms=ms, names=names, launches=int(launches), stats=stats,
+                steps=steps,
+                n_local=n_local, taps=taps, logE=logE, logE_best=logE_best,
+                clocks=clk.summary() if clocks else None)
+
+
+def sweep_report(wl, m, peak, peak_src, world):
+    """Turn the raw timings of measure_sweep into the bench line's value / roofline / e2e objects."""
+    T, G = wl.T, wl.G
+    updates = 2.0 * wl.B * T * G
+    waves = max(1, m['stats'].get('waves', 1))
+    n_loc = m['n_local']
+    kern = {}
+    for which in ('forward', 'backward', 'accumulate'):
+        if which in m['ms']:
+            total = float(np.sum(m['ms'][which])) / m['steps']  # ms per sweep (all waves)
+            name = (m['names'].get(which, which) + '_kernel') if which != 'accumulate' else 'accumulate_kernel'
+            gbs = BYTES_PER_CELL[which] * n_loc * T * G / (total * 1e-3) / 1e9
+            kern[name] = {'ms': total, 'launches_per_step': waves, 'GBps': gbs, 'frac': gbs / peak,
+                          'bytes_per_cell': BYTES_PER_CELL[which]}
+    coll = {k.split(':', 1)[1]: float(np.sum(v)) / m['steps'] for k, v in m['ms'].items() if k.startswith('collective:')}
+    dominant = max(kern, key=lambda k: kern[k]['ms'])
+    kernel_ms = sum(v['ms'] for v in kern.values())
+    coll_ms = sum(coll.values())
+    fp64_peak = FP64_LANES * 148 * 1.965e9 * 2 / 1e12
+    flop_pass = 2.0 * T * G * float(m['taps'].sum())
+    fp64 = {'peak_tflops': fp64_peak,
+            'peak_source': 'measured: tools/micro/dfma_bench.cu (58.5 DFMA lanes/clk/SM x 148 SMs x 1.965 GHz)',
+            'convolution_flop_per_pass': flop_pass, 'mean_taps': float(m['taps'].mean()) if len(m['taps']) else 0.0,
+            'kernels': {name: {'tflops': flop_pass / (v['ms'] * 1e-3) / 1e12,
+                               'frac': flop_pass / (v['ms'] * 1e-3) / 1e12 / fp64_peak}
+                        for name, v in kern.items() if 'accumulate' not in name}}
+    traffic, tag = ncu_traffic(wl.key, dominant)
+    roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': kern[dominant]['GBps'], 'peak': peak, 'unit': 'GB/s',
+                'frac': kern[dominant]['frac'], 'traffic': traffic,
+                'traffic_source': ('committed ncu capture profiles/%s' % tag) if tag else None,
+                'peak_source': peak_src, 'kernels': kern,
+                'all_kernels_GBps': 32.0 * n_loc * T * G / (kernel_ms * 1e-3) / 1e9,
+                'all_kernels_frac': 32.0 * n_loc * T * G / (kernel_ms * 1e-3) / 1e9 / peak,
+                'kernel_share_of_step': kernel_ms / m['dev_ms'], 'collectives_ms': coll,
+                'collective_share_of_step': coll_ms / m['dev_ms'], 'waves': waves, 'fp64': fp64}
+    out = {'value': updates / (m['dev_ms'] * 1e-3), 'unit': 'cell-updates/s', 'ms_per_step': m['dev_ms'],
+           'gpu_launches_per_step': m['launches'], 'roofline': roofline}
+    if m['e2e_ms']:
+        n_local = wl.B // world
+        out['e2e'] = {'value': updates / (m['e2e_ms'] * 1e-3), 'unit': 'cell-updates/s', 'ms_per_step': m['e2e_ms'],
+                      'h2d_bytes_per_step': int(wl.data.nbytes + n_local * 2 * (8 + 4 + 16) + 2 * G * 8 + n_local * 16),
+                      'd2h_bytes_per_step': int(T * G * 8 + T * 8 * (1 + len(wl.shape)) + wl.B * 16)}
+        out['log_evidence'] = m['logE']
+    return out
+
+
+def measure_online(wl, bl, eng, torch, td, world, local_rank, clocks=False):
+    """C5: T step() calls of an OnlineStudy through the public API (each step: H2D of the new segment, one batched
+    launch over this rank's hypotheses, all-gather + D2H of the evidence increments), after a lead-in.  Device time =
+    CUDA events around the whole window on the launching stream; per-kernel time from event brackets per call."""
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    S = wl.study(bl)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        for d in wl.data[:wl.lead + 1]:
+            S.step(d)
+    timers = Timers(torch)
+    plain_run = eng.run
+    eng.run = timers.wrap(lambda which, *a, **kw: which, plain_run, name_of=eng.last_kernel)
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank) if clocks else contextlib.nullcontext()
+    try:
+        with sampler as clk, contextlib.redirect_stdout(sink):
+            barrier()
+            timers.on = True
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for d in wl.data[wl.lead + 1:wl.lead + 1 + wl.T]:
+                S.step(d)
+            e1.record()
+            barrier()
+            wall_ms = 1e3 * (time.perf_counter() - t0)
+            timers.on = False
+    finally:
+        eng.run = plain_run
+    dev_ms = e0.elapsed_time(e1)
+    ms, names = timers.collect()
+    launches = eng.launch_count() - launches0
+    times = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        td.all_reduce(times, op=td.ReduceOp.MAX)
+    dev_ms, wall_ms = [float(x) for x in times.cpu()]
+    post = S.marginalizedPosterior  # collective read
+    return dict(dev_ms=dev_ms, wall_ms=wall_ms, ms=ms, names=names, launches=int(launches), logE=float(S.logEvidence),
+                n_local=int(S._dev['Hr']), mean_rho=float(np.sum(post * S.grid[0])),
+                clocks=clk.summary() if clocks else None)
+
+
+def online_report(wl, m, peak, peak_src):
+    T, G = wl.T, wl.G
+    updates = float(wl.B) * T * G
+    fwd = m['ms'].get('forward', [])
+    step_kernel_ms = float(np.mean(fwd)) if fwd else float('nan')
+    # algorithmic bytes per cell and step: K7 reads the state and writes the unnormalised cells, K8 reads them and writes
+    # the normalised state: 32 B (DESIGN.md section 4)
+    gbs = 32.0 * m['n_local'] * G / (step_kernel_ms * 1e-3) / 1e9
+    name = m['names'].get('forward', 'online2d') + '_kernels'
+    traffic, tag = ncu_traffic(wl.key, 'online2d_tile_kernel')
+    roofline = {'bound': 'hbm', 'kernel': name, 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak,
+                'traffic': traffic, 'traffic_source': ('committed ncu capture profiles/%s (tile kernel only)' % tag) if tag else None,
+                'peak_source': peak_src, 'kernels': {name: {'ms': step_kernel_ms, 'GBps': gbs, 'frac': gbs / peak,
+                                                            'bytes_per_cell': 32.0}},
+                'kernel_share_of_step': step_kernel_ms * len(fwd) / m['dev_ms'] if fwd else None}
+    return {'value': updates / (m['dev_ms'] * 1e-3), 'unit': 'cell-updates/s', 'ms_per_step': m['dev_ms'],
+            'ms_per_online_step': m['dev_ms'] / T, 'gpu_launches_per_step': m['launches'], 'roofline': roofline,
+            'e2e': {'value': updates / (m['wall_ms'] * 1e-3), 'unit': 'cell-updates/s', 'ms_per_step': m['wall_ms'],
+                    'ms_per_online_step': m['wall_ms'] / T,
+                    'h2d_bytes_per_step': int(T * 2 * 8), 'd2h_bytes_per_step': int(T * wl.B * 8)},
+            'log_evidence': m['logE'], 'posterior_mean_rho': m['mean_rho']}
+
+
+# ------------------------------------------------------------------------------------------------ CPU port
+def cpu_port_sample(key, args_dict, world, share, T_cpu):
+    """Reference-style NumPy loop (oracle/np_oracle.py) on a share of the workload's sweep -- share = (i, n, per):
+    chunk i of n of `n * per` combos spread evenly over the sweep -- and its first T_cpu data points.  Returns
+    (cell updates, seconds, combos fitted, combos of the sweep).  The lowering comes from the product's host code;
+    the arithmetic timed here is NumPy/SciPy only."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import bayesloop_b200 as bl
     import helpers
     import np_oracle
-    S = build_study(bl, counts[:T_cpu], n_sigma_total, grid, sigma_max)
-    ops, hp, _ = helpers.lowered(S)
+    wl = WORKLOADS[key](argparse.Namespace(**args_dict), world)
+
+    def pick(B):
+        i, n, per = share
+        rows_all = np.unique(np.linspace(0, B - 1, n * per).round().astype(int))
+        return [int(r) for r in np.array_split(rows_all, n)[i]]
+
+    if wl.kind == 'online':
+        S = wl.study(bl)
+        S.rawData = np.asarray(wl.data[:2])
+        pb = helpers.np_problem_online(S, wl.data[:T_cpu + 1])
+        ops = helpers.online_ops(S)
+        rows = pick(S.tmCount)
+        t0 = time.perf_counter()
+        np_oracle.online_steps(pb, ops, rows)
+        return float(len(rows)) * pb.T * int(np.prod(pb.shape)), time.perf_counter() - t0, len(rows), S.tmCount
+    S = wl.study(bl, T=T_cpu)
+    if hasattr(S, '_prepareChangepoints'):
+        S._prepareChangepoints(silent=True)
+        ctx = S._lower(np.asarray(S.hyperGridValues, dtype=float), S.formattedTimestamps)
+        ops, hp = ctx.ops, np.asarray(S.flatHyperPriorValues, dtype=float)
+    else:
+        ops, hp, _ = helpers.lowered(S)
     pb = helpers.np_problem(S)
+    rows = pick(len(hp))
     t0 = time.perf_counter()
     np_oracle.hyper_fit(pb, ops, hp, rows=rows)
-    return np_oracle.cell_updates(pb, len(rows)), time.perf_counter() - t0
+    return np_oracle.cell_updates(pb, len(rows)), time.perf_counter() - t0, len(rows), len(hp)
 
 
-def _cpu_worker(args):
-    counts, grid, sigma_max, n_total, rows, T_cpu = args
+def _cpu_worker(job):
     os.environ.setdefault('OMP_NUM_THREADS', '1')
-    return cpu_port_sample(counts, grid, sigma_max, n_total, rows, T_cpu)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return cpu_port_sample(*job)
+
+
+CPU_SAMPLE = {'c2': (24, 4000), 'c3': (6, 40), 'c4': (6, 40), 'c5': (8, 12)}  # (combos, time steps) of the 1-core sample
+
+
+def cpu_baseline(wl, args, world):
+    n, T_cpu = CPU_SAMPLE[wl.key]
+    T_cpu = min(T_cpu, wl.T)
+    with contextlib.redirect_stdout(io.StringIO()):
+        upd, sec, fitted, total = cpu_port_sample(wl.key, vars(args), world, (0, 1, n), T_cpu)
+    return {'value': upd / sec, 'unit': 'cell-updates/s', 'cores': 1, 'kind': 'port',
+            'sample': '%d of %d combos (evenly spaced), first %d of %d time steps, oracle/np_oracle.py '
+                      '(NumPy + scipy.ndimage.gaussian_filter1d), %.1f s' % (fitted, total, T_cpu, wl.T, sec)}
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (NumPy port; the reference itself is Python and is not installed on
     the GPU box) on all host cores, rows of the sweep split across worker processes like HyperStudy._parallelFit
-    (core.py:1463-1465).  Each step is a bounded sample of the C2 workload."""
+    (core.py:1463-1465).  Each step is a bounded sample of the workload."""
     if rank != 0:
         return
     import multiprocessing as mp
+    wl = WORKLOADS[args.config](args, args.gpus)
     cores = max(1, (os.cpu_count() or 1))
     workers = min(cores, 64)
-    n_total = COMBOS_PER_GPU * args.gpus
-    T_cpu = min(args.cpu_T, args.T)
-    per_worker = 4
-    rows_all = np.unique(np.linspace(0, n_total - 1, workers * per_worker).round().astype(int))
-    chunks = [list(c) for c in np.array_split(rows_all, workers) if len(c)]
-    counts = synthetic_counts(args.T)
-    jobs = [(counts, args.grid, args.sigma_max, n_total, rows, T_cpu) for rows in chunks]
+    per_worker = {'c2': 4, 'c3': 2, 'c4': 2, 'c5': 2}[wl.key]
+    T_cpu = min({'c2': args.cpu_T, 'c3': 24, 'c4': 24, 'c5': 8}[wl.key], wl.T)
+    jobs = [(wl.key, vars(args), args.gpus, (i, workers, per_worker), T_cpu) for i in range(workers)]
     ctx = mp.get_context('spawn')
     times = []
-    with ctx.Pool(len(chunks)) as pool:
+    with ctx.Pool(workers) as pool:
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             res = pool.map(_cpu_worker, jobs)
@@ -180,14 +592,14 @@ def run_reference(args, rank, world):
     updates = float(sum(r[0] for r in res))
     ms = 1e3 * float(np.mean(times))
     value = updates / (ms / 1e3)
-    sample = '%d of %d sigma values (evenly spaced), first %d of %d time steps, %d worker processes' % (
-        len(rows_all), n_total, T_cpu, args.T, len(chunks))
+    sample = '%d of %d combos (evenly spaced), first %d of %d time steps, %d worker processes' % (
+        sum(r[2] for r in res), res[0][3], T_cpu, wl.T, workers)
     line = {
         'impl': 'reference', 'metric': 'grid_cell_updates_per_s', 'value': value, 'unit': 'cell-updates/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args, n_total),
-        'cpu_baseline': {'value': value, 'unit': 'cell-updates/s', 'cores': len(chunks), 'kind': 'port',
+        'higher_is_better': True, 'scaling': wl.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': wl.describe(),
+        'cpu_baseline': {'value': value, 'unit': 'cell-updates/s', 'cores': workers, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': value, 'unit': 'cell-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -195,94 +607,26 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def c3_sample(bl, eng, torch, steps=3, warmup=2, n=256, T=200, hyper=6):
-    """Secondary measurement (not the headline): a bounded sample of BASELINE.json configs[2] ("C3": Gaussian
-    256 x 256 grid, GaussianRandomWalk on both parameters) -- hyper x hyper combos spread evenly over the 64 x 64
-    hyper-grid of SURVEY.md 8d, first T time steps, full fit on the cluster-resident 2-D kernels."""
-    rng = np.random.default_rng(2)
-    mu = np.clip(np.cumsum(rng.normal(0, 0.02, T)), -2, 2)
-    sd = np.clip(1.0 + np.cumsum(rng.normal(0, 0.01, T)), 0.5, 2.0)
-    x = rng.normal(mu, sd)
-    S = bl.HyperStudy(silent=True)
-    S.loadData(x, silent=True)
-    S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, n), 'std', bl.oint(0, 3, n)),
-          bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.1, hyper), target='mean'),
-                                        bl.tm.GaussianRandomWalk('s_std', bl.cint(0, 0.05, hyper), target='std')),
-          silent=True)
-    S._formatData()
-    S._createHyperGrid(silent=True)
-    sw = S._prepareSweep(False, False)
-    ms = {'forward': [], 'backward': [], 'accumulate': []}
-    names = {}
-    events = []
-    plain = eng.run
-
-    def timed(which, plan, flags, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        plain(which, plan, flags, **kw)
-        e1.record()
-        names[which] = eng.last_kernel() if which != 'accumulate' else 'accumulate_kernel'
-        events.append((which, e0, e1))
-
-    eng.run = timed
-    try:
-        for _ in range(warmup):
-            S._executeSweep(sw)
-        torch.cuda.synchronize()
-        del events[:]
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(steps):
-            res = S._executeSweep(sw)
-        b.record()
-        torch.cuda.synchronize()
-    finally:
-        eng.run = plain
-    for which, e0, e1 in events:
-        if which in ms:
-            ms[which].append(e0.elapsed_time(e1))
-    B = hyper * hyper
-    cells = float(B) * T * n * n
-    step_ms = a.elapsed_time(b) / steps
-    per = {'forward': 8.0, 'backward': 16.0, 'accumulate': 8.0}
-    kern = {names.get(k, k): {'ms': float(np.mean(v)), 'GBps': per[k] * cells / (float(np.mean(v)) * 1e-3) / 1e9}
-            for k, v in ms.items() if v}
-    return {'workload': 'C3 sample: Gaussian 2-D grid %dx%d, GRW on both parameters, %dx%d of the 64x64 hyper-grid, '
-                        'first %d time steps, full fit' % (n, n, hyper, hyper, T),
-            'value': 2.0 * cells / (step_ms * 1e-3), 'unit': 'cell-updates/s', 'ms_per_step': step_ms, 'kernels': kern,
-            'combos': B, 'log_evidence_best_combo': float(np.max(res[1]))}
-
-
-def workload_config(args, n_total):
-    return {'workload': 'C2 HyperStudy: Poisson 1-D grid=%d, GaussianRandomWalk sigma sweep cint(0,%g,%d) '
-                        '(%d per GPU), synthetic counts T=%d, full fit (forward+backward+averaging)'
-                        % (args.grid, args.sigma_max, n_total, n_total // max(1, args.gpus), args.T),
-            'grid': args.grid, 'T': args.T, 'combos': n_total, 'combos_per_gpu': n_total // max(1, args.gpus),
-            'sigma_max': args.sigma_max, 'parallelism': 'combos sharded over %d rank(s)' % args.gpus,
-            'l2': 'working set per step (alpha sequences, %.1f GB/GPU) exceeds the 126 MB L2; no explicit flush'
-                  % (n_total // max(1, args.gpus) * args.T * args.grid * 8 / 1e9)}
-
-
+# ------------------------------------------------------------------------------------------------ main
 def main():
-    global COMBOS_PER_GPU
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--T', type=int, default=T_FULL)
-    ap.add_argument('--grid', type=int, default=GRID)
-    ap.add_argument('--sigma-max', dest='sigma_max', type=float, default=SIGMA_MAX)
-    ap.add_argument('--combos-per-gpu', dest='combos', type=int, default=COMBOS_PER_GPU)
+    ap.add_argument('--config', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--T', type=int, default=0, help='time steps (default: 10000 for c2, window of 200 / 400 / 200 for c3 / c4 / c5)')
+    ap.add_argument('--grid', type=int, default=1000, help='c2: cells of the 1-D grid')
+    ap.add_argument('--sigma-max', dest='sigma_max', type=float, default=0.2)
+    ap.add_argument('--combos-per-gpu', dest='combos', type=int, default=512, help='c2: sigma values per GPU')
+    ap.add_argument('--hyper', type=int, default=64, help='c3: values per hyper-parameter axis')
+    ap.add_argument('--changepoints', type=int, default=100, help='c4: change-point values')
     ap.add_argument('--cpu-T', dest='cpu_T', type=int, default=4000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-c3', dest='no_c3', action='store_true', help='skip the secondary C3 (2-D) sample')
-    ap.add_argument('--no-narrow', dest='no_narrow', action='store_true', help='skip the secondary narrow C2 sweep')
+    ap.add_argument('--no-extra', dest='no_extra', action='store_true', help='headline only: skip the other configs')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3  # timing rule: at least 3 warm-up steps
-    COMBOS_PER_GPU = args.combos
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -301,197 +645,64 @@ def main():
     import bayesloop_b200 as bl
     from bayesloop_b200 import engine as eng_mod
     eng = eng_mod.default_engine()
+    peak, peak_src = hbm_peak()
 
-    def barrier():
-        if world > 1:
-            td.barrier()
-        torch.cuda.synchronize()
-
-    n_total = args.combos * world
-    counts = synthetic_counts(args.T)
-    G, T = args.grid, args.T
-    updates = 2.0 * n_total * T * G
-
-    # ---- per-kernel event timing (live, on the launching stream) ---------------------------------------------
-    kernel_ms = {'forward': [], 'backward': [], 'accumulate': []}
-    recording = {'on': False, 'events': []}
-    plain_run = eng.run
-
-    kernel_names = {'accumulate': 'accumulate_kernel'}
-
-    def timed_run(which, plan, flags, **kw):
-        if recording['on'] and which in kernel_ms:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            plain_run(which, plan, flags, **kw)
-            e1.record()
-            if which != 'accumulate':
-                kernel_names[which] = eng.last_kernel() + '_kernel'
-            recording['events'].append((which, e0, e1))
+    def run_config(key, steps, warmup, headline):
+        wl = WORKLOADS[key](args if (headline or not args.T) else argparse.Namespace(**dict(vars(args), T=0)), world)
+        if wl.kind == 'online':
+            m = measure_online(wl, bl, eng, torch, td, world, local, clocks=headline)
+            rep = online_report(wl, m, peak, peak_src)
         else:
-            plain_run(which, plan, flags, **kw)
+            m = measure_sweep(wl, bl, eng, torch, td, world, steps, warmup, local, e2e=True, clocks=headline)
+            rep = sweep_report(wl, m, peak, peak_src, world)
+        rep['config'] = wl.describe()
+        rep['scaling'] = wl.scaling
+        rep['n_gpus'] = world
+        return wl, m, rep
 
-    eng.run = timed_run
-
-    # ---- device-resident sweep ("value") -----------------------------------------------------------------------
-    S = build_study(bl, counts, n_total, G, args.sigma_max)
-    S._formatData()
-    S._createHyperGrid(silent=True)
-    sw = S._prepareSweep(False, False)
-    for _ in range(args.warmup):
-        S._executeSweep(sw)
-    launches0 = eng.launch_count()
-    with ClockSampler(local) as clocks:
-        barrier()
-        recording['on'] = True
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            S._executeSweep(sw)
-        e1.record()
-        barrier()
-        recording['on'] = False
-    dev_ms = e0.elapsed_time(e1) / args.steps
-    launches = (eng.launch_count() - launches0) // max(1, args.steps)
-    for which, a, b in recording['events']:
-        kernel_ms[which].append(a.elapsed_time(b))
-    waves = S.sweepStats['waves']
-    del sw
-    torch.cuda.empty_cache()
-
-    # ---- end to end through the public API ("e2e") --------------------------------------------------------------
-    def e2e_step():
-        S2 = build_study(bl, counts, n_total, G, args.sigma_max)
-        S2.fit(silent=True)
-        return S2
-
-    for _ in range(min(args.warmup, 3)):
-        S2 = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        S2 = e2e_step()
-    barrier()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    n_local = n_total // world
-    h2d = counts.nbytes + n_local * (8 + 4 + 16) + G * 8 + n_local * 8
-    d2h = T * G * 8 + T * 8 + n_local * 8 + n_local * 4 + T * 8
-
-    times = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device='cuda')
-    if world > 1:
-        td.all_reduce(times, op=td.ReduceOp.MAX)
-    dev_ms, e2e_ms = [float(x) for x in times.cpu()]
-
+    wl, m, rep = run_config(args.config, args.steps, args.warmup, True)
+    line = None
     if rank == 0:
-        peak, peak_src = hbm_peak()
-        n_loc = n_total // world
-        # algorithmic HBM bytes per (combo, time step, cell): forward stores alpha[t] (8 B); backward reads alpha[t] and
-        # stores the posterior (16 B); the averaging pass reads every posterior once (8 B)  ->  32 B per cell for the
-        # two passes = 16 B per grid-cell update (forward 8 B + backward 24 B in HyperStudy mode)
-        bytes_per_cell = {'forward': 8.0, 'backward': 16.0, 'accumulate': 8.0}
-        names = {k: kernel_names.get(k, k) for k in kernel_ms}
-        per_launch_cells = n_loc * T * G / max(1, waves)
-        kern = {}
-        for which, samples in kernel_ms.items():
-            if samples:
-                ms = float(np.mean(samples))
-                gbs = bytes_per_cell[which] * per_launch_cells / (ms * 1e-3) / 1e9
-                kern[names[which]] = {'ms': ms, 'GBps': gbs, 'frac': gbs / peak, 'bytes_per_cell': bytes_per_cell[which]}
-        dominant = max(kern, key=lambda k: kern[k]['ms'])
-        total_kernel_ms = sum(v['ms'] for v in kern.values()) * waves
-        sweep_gbs = 32.0 * n_loc * T * G / (total_kernel_ms * 1e-3) / 1e9
-        # the binding unit of this workload is the FP64 pipe (convolution taps), reported next to the HBM roofline:
-        # DFMA per pass = T * G * sum over combos of (2 R_b + 1), R_b = int(4 sigma_b / lattice + 0.5)
-        sig = np.asarray(bl.cint(0, args.sigma_max, n_total), dtype=float)[:n_loc]
-        lattice = 12.0 / (G + 1)
-        radius = np.where(sig > 0, np.floor(4.0 * sig / lattice + 0.5), 0.0)
-        taps = np.where(radius > 0, 2.0 * radius + 1.0, 0.0)
-        flop_pass = 2.0 * T * G * float(taps.sum())
-        fp64_peak = 58.5 * 148 * 1.965e9 * 2 / 1e12  # tools/micro/dfma_bench.cu on B200: 58.5 FMA lanes/clk/SM
-        fp64 = {'peak_tflops': fp64_peak, 'peak_source': 'measured: tools/micro/dfma_bench.cu (58.5 DFMA lanes/clk/SM x 148 '
-                                                         'SMs x 1.965 GHz)',
-                'convolution_flop_per_pass': flop_pass, 'mean_taps': float(taps.mean()),
-                'kernels': {name: {'tflops': flop_pass / (v['ms'] * 1e-3) / 1e12,
-                                   'frac': flop_pass / (v['ms'] * 1e-3) / 1e12 / fp64_peak}
-                            for name, v in kern.items() if 'accumulate' not in name}}
-        roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': kern[dominant]['GBps'], 'peak': peak, 'unit': 'GB/s',
-                    'frac': kern[dominant]['frac'], 'traffic': ncu_traffic(dominant), 'peak_source': peak_src,
-                    'kernels': kern, 'all_kernels_GBps': sweep_gbs, 'all_kernels_frac': sweep_gbs / peak,
-                    'kernel_share_of_step': total_kernel_ms / dev_ms, 'fp64': fp64,
-                    'note': 'reference-like sigma sweep (kernel radius <= 67): the convolution makes the passes FP64-FMA '
-                            'bound, not HBM bound (SURVEY.md 8d); see profiles/ for the FP64 pipe utilisation'}
-        line = {
-            'metric': 'grid_cell_updates_per_s', 'value': updates / (dev_ms * 1e-3), 'unit': 'cell-updates/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': workload_config(args, n_total),
-            'clocks': clocks.summary(),
-            'e2e': {'value': updates / (e2e_ms * 1e-3), 'unit': 'cell-updates/s', 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
-            'gpu_launches': int(launches) * args.steps,
-            'roofline': roofline,
-            'log_evidence': float(S2.logEvidence),
-        }
-        if world == 1 and not args.no_c3 and not args.no_narrow:
-            # secondary: the narrow sweep of SURVEY.md 8d (sigma <= 0.05, radius <= 17): the regime where the passes
-            # move towards the HBM roofline (fewer taps per stored byte); device-resident, same shape otherwise
-            try:
-                Sn = build_study(bl, counts, n_total, G, 0.05)
-                Sn._formatData()
-                Sn._createHyperGrid(silent=True)
-                swn = Sn._prepareSweep(False, False)
-                kernel_ms_n = {'forward': [], 'backward': [], 'accumulate': []}
-                evs = []
-
-                def timed_n(which, plan, flags, **kw):
-                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a0.record()
-                    plain_run(which, plan, flags, **kw)
-                    a1.record()
-                    evs.append((which, a0, a1))
-
-                eng.run = timed_n
-                for _ in range(2):
-                    Sn._executeSweep(swn)
-                del evs[:]
-                n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                n0.record()
-                for _ in range(3):
-                    Sn._executeSweep(swn)
-                n1.record()
-                torch.cuda.synchronize()
-                eng.run = timed_run
-                for which, a0, a1 in evs:
-                    if which in kernel_ms_n:
-                        kernel_ms_n[which].append(a0.elapsed_time(a1))
-                ms_n = n0.elapsed_time(n1) / 3
-                cells = float(n_loc) * T * G
-                line.setdefault('extra', {})['c2_narrow'] = {
-                    'workload': 'C2 with the narrow sweep cint(0,0.05,%d): kernel radius <= 17' % n_total,
-                    'value': 2.0 * cells / (ms_n * 1e-3), 'unit': 'cell-updates/s', 'ms_per_step': ms_n,
-                    'kernels': {k: {'ms': float(np.mean(v)),
-                                    'hbm_frac': bytes_per_cell[k] * cells / (float(np.mean(v)) * 1e-3) / 1e9 / peak}
-                                for k, v in kernel_ms_n.items() if v}}
-                del swn, Sn
-                torch.cuda.empty_cache()
+        line = {'metric': 'grid_cell_updates_per_s', 'value': rep['value'], 'unit': 'cell-updates/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': rep['ms_per_step'], 'higher_is_better': True,
+                'scaling': wl.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': rep['config'],
+                'clocks': m['clocks'], 'e2e': rep['e2e'],
+                'gpu_launches': rep['gpu_launches_per_step'] * (args.steps if wl.kind == 'sweep' else 1),
+                'roofline': rep['roofline'], 'log_evidence': rep.get('log_evidence')}
+        if wl.kind == 'online':
+            line['ms_per_online_step'] = rep['ms_per_online_step']
+    extra = {}
+    if args.config == 'c2' and not args.no_extra:
+        # the other BASELINE configs, measured at EVERY N (strong scaling); never lose the headline over them
+        if world == 1:
+            try:  # narrow sweep of SURVEY.md 8d (sigma <= 0.05, radius <= 17): the HBM-leaning regime of C2
+                narrow = C2(argparse.Namespace(**dict(vars(args), sigma_max=0.05)), world)
+                mn = measure_sweep(narrow, bl, eng, torch, td, world, 3, 2, local, e2e=False)
+                rn = sweep_report(narrow, mn, peak, peak_src, world)
+                extra['c2_narrow'] = {'workload': 'C2 with the narrow sweep cint(0,0.05,%d): kernel radius <= 17' % narrow.B,
+                                      'value': rn['value'], 'unit': 'cell-updates/s', 'ms_per_step': rn['ms_per_step'],
+                                      'kernels': {k: {'ms': v['ms'], 'hbm_frac': v['frac']}
+                                                  for k, v in rn['roofline']['kernels'].items()}}
             except Exception as exc:
-                eng.run = timed_run
-                line.setdefault('extra', {})['c2_narrow'] = {'error': repr(exc)}
-        if world == 1 and not args.no_c3:
+                extra['c2_narrow'] = {'error': repr(exc)}
+        for key in ('c3', 'c4', 'c5'):
             try:
-                line.setdefault('extra', {})['c3_sample'] = c3_sample(bl, eng, torch)
-            except Exception as exc:  # secondary measurement: never lose the headline line over it
-                line.setdefault('extra', {})['c3_sample'] = {'error': repr(exc)}
+                wl2, m2, rep2 = run_config(key, 2, 1, False)
+                if rank == 0 and world == 1 and not args.no_cpu_baseline and key != 'c4':
+                    rep2['cpu_baseline'] = cpu_baseline(wl2, args, world)
+                    rep2['vs_cpu_1core'] = rep2['value'] / rep2['cpu_baseline']['value']
+                extra[key] = rep2
+            except Exception as exc:  # identical control flow on all ranks: the failure is deterministic
+                extra[key] = {'error': repr(exc)}
+                torch.cuda.empty_cache()
+    if rank == 0:
+        if extra:
+            line['extra'] = extra
         if world == 1 and not args.no_cpu_baseline:
-            rows = list(np.unique(np.linspace(0, n_total - 1, 24).round().astype(int)))
-            T_cpu = min(args.cpu_T, T)
-            upd, sec = cpu_port_sample(counts, G, args.sigma_max, n_total, rows, T_cpu)
-            line['cpu_baseline'] = {'value': upd / sec, 'unit': 'cell-updates/s', 'cores': 1, 'kind': 'port',
-                                    'sample': '%d of %d sigma values (evenly spaced), first %d of %d time steps, '
-                                              'oracle/np_oracle.py (NumPy + scipy.ndimage.gaussian_filter1d), %.1f s'
-                                              % (len(rows), n_total, T_cpu, T, sec)}
+            line['cpu_baseline'] = cpu_baseline(wl, args, world)
         print(json.dumps(line), flush=True)
     if world > 1:
+        td.barrier()
         td.destroy_process_group()
 
 

@@ -195,6 +195,22 @@ def finish_average(pb, log_avg):
     return avg, means
 
 
+def online_steps(pb, ops, rows, use_scipy=True):
+    """OnlineStudy.step for the hypotheses `rows` over the whole series (core.py:2143-2175): ONE likelihood per step
+    shared by all hypotheses, then per hypothesis transition (t = -1, core.py:2167) x likelihood, sum, divide.
+    Returns the log-evidences of the hypotheses."""
+    post = {b: None for b in rows}
+    logE = {b: np.log(pb.lc) for b in rows}
+    for i in range(pb.T):
+        lik = pb.likelihood(i)
+        for b in rows:
+            alpha = (pb.prior if post[b] is None else apply_ops(pb, ops, b, -1, False, post[b], use_scipy)) * lik
+            ni = np.sum(alpha)
+            logE[b] += np.log(ni)
+            post[b] = alpha / ni
+    return np.array([logE[b] for b in rows])
+
+
 def cell_updates(pb, n_combos, forward_only=False, evidence_only=False):
     per_pass = n_combos * pb.T * int(np.prod(pb.shape))
     return per_pass if (forward_only or evidence_only) else 2 * per_pass

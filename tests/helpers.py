@@ -40,6 +40,42 @@ def np_problem(study):
                              study.rawData, prior, reset_base=base)
 
 
+def online_ops(study):
+    """Concatenated per-hypothesis program of an OnlineStudy (what OnlineStudy._setupDevice hands to the engine), as
+    host arrays: ops with window/param/radius rows for ALL hypotheses."""
+    ops, row, H = [], 0, study.tmCount
+    for tm, rows, count in zip(study.transitionModels, study.hyperParameterValues, study.tmCounts):
+        hyper = np.asarray(rows, dtype=float).reshape(count, -1) if len(rows) > 0 else np.zeros((1, 0))
+        study.setTransitionModel(tm, silent=True)
+        ctx = study._lower(hyper, np.array([-1.]), online=True, model=tm)
+        for op in ctx.ops:
+            full = dict(kind=op['kind'], axis=op['axis'], param=np.zeros(H), radius=np.zeros(H, dtype=np.int32),
+                        window=np.zeros((H, 4), dtype=np.int32))
+            full['param'][row:row + count] = op['param']
+            full['radius'][row:row + count] = op['radius']
+            full['window'][row:row + count] = op['window']
+            ops.append(full)
+        row += count
+    return ops
+
+
+def np_problem_online(study, series):
+    """np_oracle.Problem of an OnlineStudy fed with `series` (grid and prior from the study's observation model)."""
+    import np_oracle
+    om = study.observationModel
+    prior = np.array(study._computePrior(silent=True), dtype=float)
+    p = om.prior
+    if callable(p):
+        base = np.asarray(p(*study.grid), dtype=float) * np.ones(study.gridSize)
+    elif isinstance(p, np.ndarray):
+        base = np.array(p, dtype=float)
+    else:
+        base = np.ones(study.gridSize)
+    base = base / base.sum()
+    return np_oracle.Problem(study.marginalGrid, study.latticeConstant, om.deviceKind, om.segmentLength,
+                             np.asarray(series, dtype=float), prior, reset_base=base)
+
+
 def abi_sweep(engine, study, forwardOnly=False, evidenceOnly=False):
     """Run the product's sweep on `engine` and bring everything back to the host."""
     study._engineOverride = engine
