@@ -718,15 +718,16 @@ int launch_resident(const blg_plan *pl, PassKernel kernel, const PassArgs &a, co
     long long *trace = nullptr;
     PassArgs a2 = a;
     if (pl->opt.trace[0]) {  // debugging aid: per-CTA {smid, combo, start, end} (globaltimer ns), dumped as CSV
-        CUDA_TRY(cudaMalloc(&trace, (size_t)B * 4 * sizeof(long long)));
-        CUDA_TRY(cudaMemset(trace, 0, (size_t)B * 4 * sizeof(long long)));
+        // + per warp {convolution, epilogue, barrier cycles, hardware warp id} (warp-specialised forward kernel)
+        CUDA_TRY(cudaMalloc(&trace, (size_t)B * 36 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(trace, 0, (size_t)B * 36 * sizeof(long long)));
         a2.trace = trace;
     }
     kernel<<<(unsigned)B, lay.nt, lay.bytes, st>>>(a2);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     if (trace) {
-        std::vector<long long> h((size_t)B * 4);
+        std::vector<long long> h((size_t)B * 36);
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(trace);
@@ -734,9 +735,14 @@ int launch_resident(const blg_plan *pl, PassKernel kernel, const PassArgs &a, co
         char path[512];
         snprintf(path, sizeof path, "%s.%s.%d.csv", pl->opt.trace, name, seq++);
         if (FILE *f = fopen(path, "w")) {
-            fprintf(f, "block,smid,combo,start_ns,end_ns\n");
-            for (long long i = 0; i < B; ++i)
-                fprintf(f, "%lld,%lld,%lld,%lld,%lld\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+            fprintf(f, "block,smid,combo,start_ns,end_ns");
+            for (int w = 0; w < 8; ++w) fprintf(f, ",w%d_conv,w%d_epi,w%d_bar,w%d_hwid", w, w, w, w);
+            fprintf(f, "\n");
+            for (long long i = 0; i < B; ++i) {
+                fprintf(f, "%lld,%lld,%lld,%lld,%lld", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                for (int k = 0; k < 32; ++k) fprintf(f, ",%lld", h[4 * B + 32 * i + k]);
+                fprintf(f, "\n");
+            }
             fclose(f);
         }
     }
@@ -842,7 +848,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
             }
             O2Launch L;
             if (ok && online2d_plan(pl->dev.n0, pl->dev.n1, r0, r1, pl->opt.online2d_async != 0, &L)) {
-                const size_t doubles = (size_t)in->B * pl->dev.G + (size_t)in->B * L.tilesY * L.tilesX * 2;
+                const size_t doubles = online2d_scratch_doubles(in->B, pl->dev.G, L);
                 if ((long long)doubles > pl->o2_cap) {  // grows once per study: no allocation on the per-step path
                     if (pl->d_o2) CUDA_TRY(cudaFree(pl->d_o2));
                     pl->d_o2 = nullptr;
@@ -854,7 +860,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
                     fprintf(stderr, "[blgrid] online2d: %lld hypotheses x %d x %d tiles, %zu B smem/CTA, radii <= %d / %d\n",
                             (long long)in->B, L.tilesY, L.tilesX, L.smemBytes, r0, r1);
                 const int rc = online2d_run(a, L, pl->d_o2, st);
-                g_launches += 2;
+                g_launches += 3;
                 g_last_kernel = "online2d";
                 if (rc != 0) return fail("online2d launch failed: %s", cudaGetErrorString((cudaError_t)rc));
                 return 0;

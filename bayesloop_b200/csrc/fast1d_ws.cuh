@@ -107,7 +107,10 @@ __device__ __forceinline__ WsRoles ws_roles(int slot, int n) {
     WsRoles r;
     r.lane = threadIdx.x & 31;
     r.warp = threadIdx.x >> 5;
-    r.rot = slot % NW;
+    // the service role rotates with the CTA's slot so that the four sub-partitions (warp index mod 4) see the same mix;
+    // with a number of warps that is not a multiple of four the hardware's slot allocation already rotates the CTAs,
+    // and the LAST warp serves: the compute warps of a 5-warp CTA then sit on four different sub-partitions
+    r.rot = (NW % 4 == 0) ? slot % NW : NW - 1;
     r.service = r.warp == r.rot;
     const int cw = r.warp - (r.warp > r.rot ? 1 : 0);
     r.ct = cw * 32 + r.lane;
@@ -195,9 +198,13 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
 #pragma unroll
             for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + m * NCOMP);
         }
+        // debugging aid (BLG_TRACE): cycles this warp spends in the convolution / the epilogue / waiting at the barrier
+        const bool prof = a.trace != nullptr;
+        long long cConv = 0, cEpi = 0, cBar = 0;
         for (long long t = 0; t < T; ++t) {
             double v[M];
             const bool trans = (t > 0 || first) && (t - 1 >= s.f_lo) && (t - 1 < s.f_hi);
+            const long long p0 = prof ? clock64() : 0;
             if (r.owner) {
                 if (trans && s.R > 0) {
                     conv_item<M>(cur, r.i0, s.R, s.W, v);  // transitionModels.py:111
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
                     for (int m = 0; m < M; ++m) v[m] = cur[r.i0 + m];
                 }
             }
+            const long long p1 = prof ? clock64() : 0;
             // lagged scale k_t: written by the service warp before it arrived at the barrier of step t-1
             const double kappa = t >= 2 ? ctl[t & 1] : 1.0;
             if (r.owner) {
@@ -220,11 +228,26 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
                 PP[r.ct] = tree_sum<M>(v);
             }
             if (rawRows) fence_proxy_async();  // the new state is read by the service warp's bulk-async row store
+            const long long p2 = prof ? clock64() : 0;
             __syncthreads();  // new state and its partial sums are visible to everybody
+            if (prof) {
+                cConv += p1 - p0;
+                cEpi += p2 - p1;
+                cBar += clock64() - p2;
+            }
             if (*deadFlag) break;  // set by the service warp after the barrier of an EARLIER step
             double *tmp = cur;
             cur = nxt;
             nxt = tmp;
+        }
+        if (prof && r.lane == 0) {
+            unsigned wid;
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+            long long *w = a.trace + 4 * (long long)gridDim.x + ((long long)blockIdx.x * 8 + r.warp) * 4;
+            w[0] = cConv;
+            w[1] = cEpi;
+            w[2] = cBar;
+            w[3] = wid;
         }
     } else {
         // ------------------------------------------------------------------ service warp

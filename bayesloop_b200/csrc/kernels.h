@@ -35,13 +35,14 @@ void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad);
 
 // tiled OnlineStudy step (online2d.cuh): 64 x 64 tiles x hypotheses, T = 1, rows promised separable by the caller
 // (BLG_F_SEPARABLE_ROWS).  online2d_plan: false when tile + halo do not fit in shared memory; scratch holds
-// B * G + B * tiles * 2 doubles; online2d_run returns a cudaError_t (0 = launched K7 and K8).
+// online2d_scratch_doubles(B, G, L) doubles; online2d_run returns a cudaError_t (0 = launched the three kernels).
 struct O2Launch {
     int async;  // tile loads through cp.async (the default; measured 1.92 vs 2.58 ms per C5 step, profiles/r2a_online_ab.txt)
     int tilesY, tilesX, P, inRowsMax, w0len, w1len;
     size_t smemBytes;
 };
 bool online2d_plan(int n0, int n1, int r0max, int r1max, bool async, O2Launch *L);
+size_t online2d_scratch_doubles(long long B, long long G, const O2Launch &L);
 int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStream_t st);
 
 }  // namespace blg

@@ -25,6 +25,15 @@
 
 namespace blg {
 
+// per-hypothesis descriptor of one step, resolved once per launch by online2d_desc_kernel (the tile CTAs used to
+// walk the operator program in global memory themselves: a chain of dependent loads at the start of every tile)
+struct O2Hyp {
+    int R0, R1;   // radii of the active random walks (0: none along that axis)
+    int mode;     // 0 convolution, 1 pointwise (state as it is), 2 reset
+    int clamp;    // RegimeSwitch lower bound active
+    double sig0, sig1, limit, scale;
+};
+
 struct O2Geom {
     int tilesY, tilesX;  // tiles per hypothesis
     int P;               // pitch of the shared-memory buffers (doubles, odd)
@@ -32,7 +41,11 @@ struct O2Geom {
     int w0len, w1len;    // padded weight table lengths (doubles)
     double *scratch;     // [H][G] unnormalised posterior cells
     double *partial;     // [H][tiles][2]: sum(v * lik), sum(v)
+    O2Hyp *hyp;          // [H]
+    int *counter;        // work queue: next unit (zeroed before the launch)
 };
+
+constexpr int kO2Chunk = 8;  // tiles of one hypothesis handed out per queue access (weights are built once per unit)
 
 struct O2Lik {
     const PassArgs &a;
@@ -45,39 +58,24 @@ struct O2Lik {
 };
 
 // 8-byte asynchronous global->shared copy (LDGSTS): the loads of a thread are all in flight at once instead of one
-// load -> store round trip per row (the r1k capture: half of K7's stall samples sit on the STS behind the tile loads)
+// load -> store round trip per row (the r1k capture: half of K7's stall samples sat on the STS behind the tile loads)
 struct AsyncCopy {
     __device__ __forceinline__ void operator()(double *dst, const double *src) const {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
     }
 };
 
-// shared memory (doubles): in[inRowsMax][P] | mid[kTH][P] | W0[w0len] | W1[w1len] | reduction scratch [4 * kMaxWarps]
-// ASYNC: tile loads through cp.async (opt-in, BLG_ONLINE2D_ASYNC=1).  TH / NT: rows of a tile and threads per CTA --
-// 64 / 512 (one CTA per SM) is the configuration that went through the B200 parity run; 32 / 256 (opt-in,
-// BLG_ONLINE2D_TH=32) halves shared memory and registers per CTA so that two CTAs share an SM and one tile loads while
-// the other convolves.  Both opt-in variants were written after the last GPU run of round 1.
-template <bool ASYNC, int TH, int NT>
-__global__ void __launch_bounds__(NT, TH == 64 ? 1 : 2) online2d_tile_kernel(const PassArgs a, const O2Geom geo) {
-    extern __shared__ __align__(16) double sm[];
-    const DevProblem &pb = a.pb;
-    const int tiles = geo.tilesY * geo.tilesX;
-    const long long h = blockIdx.x / tiles;
-    const int tile = blockIdx.x - (int)h * tiles;
-    const int ty = tile / geo.tilesX, tx = tile - ty * geo.tilesX;
-    double *in = sm;
-    double *mid = in + (size_t)geo.inRowsMax * geo.P;
-    double *W0 = mid + (size_t)TH * geo.P;
-    double *W1 = W0 + geo.w0len;
-    RedScratch rs;
-    rs.buf = W1 + geo.w1len;
-    rs.phase = 0;
-
-    // active operators of this hypothesis at the step handed to the models (index -1: TRANSITION_FIRST, T = 1)
+// active operators of every hypothesis at the step handed to the models (index -1: TRANSITION_FIRST, T = 1)
+__global__ void online2d_desc_kernel(const PassArgs a, O2Hyp *out) {
+    const long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= a.B) return;
     const int K = a.pg.n_ops;
-    int R0 = 0, R1 = 0;
-    double sig0 = 0.0, sig1 = 0.0, limit = 0.0, scale = 1.0;
-    bool clamp = false, reset = false;
+    O2Hyp d;
+    d.R0 = d.R1 = 0;
+    d.sig0 = d.sig1 = d.limit = 0.0;
+    d.scale = 1.0;
+    d.clamp = 0;
+    bool reset = false;
     for (int k = 0; k < K; ++k) {
         const int lo = a.pg.window[(h * K + k) * 4 + 0], hi = a.pg.window[(h * K + k) * 4 + 1];
         if (-1 < lo || -1 >= hi) continue;
@@ -87,75 +85,145 @@ __global__ void __launch_bounds__(NT, TH == 64 ? 1 : 2) online2d_tile_kernel(con
             const int R = a.pg.radius[h * K + k];
             if (!(par > 0.0) || R <= 0) continue;  // transitionModels.py:110-113
             if (a.pg.axis[k] == 0) {
-                R0 = R;
-                sig0 = par;
+                d.R0 = R;
+                d.sig0 = par;
             } else {
-                R1 = R;
-                sig1 = par;
+                d.R1 = R;
+                d.sig1 = par;
             }
         } else if (kind == BLG_OP_REGIME) {
-            clamp = true;
-            limit = par;
+            d.clamp = 1;
+            d.limit = par;
         } else if (kind == BLG_OP_RESET) {
             reset = true;
-            scale = par;
+            d.scale = par;
         }
     }
+    if (reset) d.clamp = 0;
+    d.mode = reset ? 2 : ((d.R0 == 0 && d.R1 == 0) ? 1 : 0);
+    out[h] = d;
+}
 
-    o2::Tile<TH> t;
-    t.n0 = pb.n0;
-    t.n1 = pb.n1;
-    t.r0 = ty * TH;
-    t.c0 = tx * o2::kTW;
-    t.R0 = R0;
-    t.R1 = R1;
-    t.P = geo.P;
+// shared memory (doubles): in[inRowsMax][P] | mid[kTH][P] | W0[w0len] | W1[w1len] | reduction scratch [4 * kMaxWarps]
+//
+// PERSISTENT, PIPELINED (round 2): one CTA per SM takes units of kO2Chunk consecutive tiles of one hypothesis from an
+// atomic queue (cost per tile varies with the radii).  Per unit the weights are built once; per tile
+//     wait for the haloed input tile (cp.async) -> axis-0 convolution in -> mid -> barrier
+//     -> issue the NEXT tile's loads into `in` -> axis-1 convolution out of `mid` into registers, fused with the
+//        clamp, the likelihood multiply, the global store and the partial sums (conv1_epilogue_phase)
+// so the tile loads overlap the second convolution and the output tile never returns to shared memory.
+// ASYNC = false keeps the plain LDG -> STS loads (no overlap; the reference point of profiles/r2a_online_ab.txt).
+template <bool ASYNC>
+__global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const PassArgs a, const O2Geom geo) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int TH = o2::kTH;
+    __shared__ int unitSh;
+    const DevProblem &pb = a.pb;
+    const int tiles = geo.tilesY * geo.tilesX;
+    const int chunksPerHyp = (tiles + kO2Chunk - 1) / kO2Chunk;
+    const long long units = a.B * (long long)chunksPerHyp;
+    double *in = sm;
+    double *mid = in + (size_t)geo.inRowsMax * geo.P;
+    double *W0 = mid + (size_t)TH * geo.P;
+    double *W1 = W0 + geo.w0len;
+    RedScratch rs;
+    rs.buf = W1 + geo.w1len;
+    rs.phase = 0;
     O2Lik lik{a, {pb.tabA[0], pb.tabA[1], pb.tabA[2], pb.tabB[0], pb.tabB[1]}, a.steps};
-    const double *src = a.init_state + h * (long long)pb.G;
-    double *dst = geo.scratch + h * (long long)pb.G;
-    double s1 = 0.0, s2 = 0.0;
     const int tid = threadIdx.x, nt = blockDim.x;
 
-    if (reset || (R0 == 0 && R1 == 0)) {
-        if (reset) clamp = false;
-        o2::pointwise_phase(t, src, reset ? a.reset_base : nullptr, scale, dst, clamp, limit, lik, tid, nt, s1, s2);
-    } else {
+    for (;;) {
+        __syncthreads();  // the previous unit is done with shared memory (and with unitSh)
+        if (tid == 0) unitSh = atomicAdd(geo.counter, 1);
+        __syncthreads();
+        const long long u = unitSh;
+        if (u >= units) break;
+        const long long h = u / chunksPerHyp;
+        const int first = (int)(u - h * chunksPerHyp) * kO2Chunk;
+        const int count = min(kO2Chunk, tiles - first);
+        const O2Hyp hp = geo.hyp[h];
+        const bool clamp = hp.clamp != 0;
+        const double *src = a.init_state + h * (long long)pb.G;
+        double *dst = geo.scratch + h * (long long)pb.G;
+        double *part = geo.partial + ((size_t)h * tiles + first) * 2;
+
+        o2::Tile<TH> t;
+        t.n0 = pb.n0;
+        t.n1 = pb.n1;
+        t.R0 = hp.R0;
+        t.R1 = hp.R1;
+        t.P = geo.P;
+        auto place = [&](int k) {
+            const int tile = first + k, ty = tile / geo.tilesX;
+            t.r0 = ty * TH;
+            t.c0 = (tile - ty * geo.tilesX) * o2::kTW;
+        };
+        auto publish = [&](int k, double s1, double s2) {  // per-tile partial sums; every thread calls (block reduction)
+            block_sum2(s2, s1, rs);
+            if (tid == 0) {
+                part[2 * k] = s2;
+                // no clamp: the transitioned prior is used as it is (S1 = 1, carried by the hypothesis' first tile)
+                part[2 * k + 1] = clamp ? s1 : (first + k == 0 ? 1.0 : 0.0);
+            }
+        };
+
+        if (hp.mode != 0) {
+            for (int k = 0; k < count; ++k) {
+                place(k);
+                double s1 = 0.0, s2 = 0.0;
+                o2::pointwise_phase(t, src, hp.mode == 2 ? a.reset_base : nullptr, hp.scale, dst, clamp, hp.limit, lik, tid,
+                                    nt, s1, s2);
+                publish(k, s1, s2);
+            }
+            continue;
+        }
         // a radius beyond the tables the host sized (blg_program.max_radius is a promise): poison this hypothesis
-        const bool fits = o2::padded_taps(R0, o2::kM0) <= geo.w0len && o2::padded_taps(R1, o2::kM1) <= geo.w1len &&
+        const bool fits = o2::padded_taps(hp.R0, o2::kM0) <= geo.w0len && o2::padded_taps(hp.R1, o2::kM1) <= geo.w1len &&
                           t.inRows() <= geo.inRowsMax && t.inCols() <= geo.P;
         if (!fits) {
-            s2 = NAN;
-        } else {
-            if (ASYNC) {
-                o2::load_phase(t, src, in, tid, nt, AsyncCopy());
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            } else {
-                o2::load_phase(t, src, in, tid, nt);
-            }
-            if (R0 > 0) {
-                build_weights(W0, o2::padded_taps(R0, o2::kM0), sig0, R0, rs);
-            } else {
-                for (int j = tid; j < o2::kM0; j += nt) W0[j] = j == 0 ? 1.0 : 0.0;
-            }
-            if (R1 > 0) {
-                build_weights(W1, o2::padded_taps(R1, o2::kM1), sig1, R1, rs);
-            } else {
-                for (int j = tid; j < o2::kM1; j += nt) W1[j] = j == 0 ? 1.0 : 0.0;
-            }
-            if (ASYNC) asm volatile("cp.async.wait_group 0;" ::: "memory");  // the weights were built behind the loads
-            __syncthreads();
-            o2::conv0_phase(t, in, mid, W0, tid, nt);
-            __syncthreads();
-            o2::conv1_phase(t, mid, in, W1, tid, nt);  // the haloed input is dead: its buffer takes the output tile
-            __syncthreads();
-            o2::epilogue_phase(t, in, dst, clamp, limit, lik, tid, nt, s1, s2);
+            if (tid == 0)
+                for (int k = 0; k < count; ++k) {
+                    part[2 * k] = NAN;
+                    part[2 * k + 1] = 1.0;
+                }
+            continue;
         }
-    }
-    block_sum2(s2, s1, rs);
-    if (threadIdx.x == 0) {
-        double *p = geo.partial + ((size_t)h * tiles + tile) * 2;
-        p[0] = s2;
-        p[1] = clamp ? s1 : (tile == 0 ? 1.0 : 0.0);  // no clamp: the transitioned prior is used as it is (S1 = 1)
+        place(0);
+        if (ASYNC) {
+            o2::load_phase(t, src, in, tid, nt, AsyncCopy());
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+            o2::load_phase(t, src, in, tid, nt);
+        }
+        if (hp.R0 > 0) {
+            build_weights(W0, o2::padded_taps(hp.R0, o2::kM0), hp.sig0, hp.R0, rs);
+        } else {
+            for (int j = tid; j < o2::kM0; j += nt) W0[j] = j == 0 ? 1.0 : 0.0;
+        }
+        if (hp.R1 > 0) {
+            build_weights(W1, o2::padded_taps(hp.R1, o2::kM1), hp.sig1, hp.R1, rs);
+        } else {
+            for (int j = tid; j < o2::kM1; j += nt) W1[j] = j == 0 ? 1.0 : 0.0;
+        }
+        for (int k = 0; k < count; ++k) {
+            if (ASYNC) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();  // input tile (and, for k = 0, the weights) visible to everybody
+            o2::conv0_phase(t, in, mid, W0, tid, nt);
+            __syncthreads();  // `in` is dead: the next tile may land in it while this one is finished out of `mid`
+            o2::Tile<TH> cur = t;
+            if (k + 1 < count) {
+                place(k + 1);
+                if (ASYNC) {
+                    o2::load_phase(t, src, in, tid, nt, AsyncCopy());
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                } else {
+                    o2::load_phase(t, src, in, tid, nt);
+                }
+            }
+            double s1 = 0.0, s2 = 0.0;
+            o2::conv1_epilogue_phase(cur, mid, W1, dst, clamp, hp.limit, lik, tid, nt, s1, s2);
+            publish(k, s1, s2);  // its barrier also orders this tile's reads of `mid` before the next axis-0 pass
+        }
     }
 }
 

@@ -17,6 +17,11 @@ bool online2d_plan(int n0, int n1, int r0max, int r1max, bool async, O2Launch *L
     return L->smemBytes <= 232448;  // 227 KB opt-in maximum per CTA on sm_100
 }
 
+size_t online2d_scratch_doubles(long long B, long long G, const O2Launch &L) {
+    // unnormalised cells [B][G] | per-tile partial sums [B][tiles][2] | descriptors [B] | queue counter
+    return (size_t)B * G + (size_t)B * L.tilesY * L.tilesX * 2 + (size_t)B * (sizeof(O2Hyp) / sizeof(double)) + 2;
+}
+
 int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStream_t st) {
     O2Geom geo;
     geo.tilesY = L.tilesY;
@@ -27,15 +32,20 @@ int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStre
     geo.w1len = L.w1len;
     geo.scratch = scratch;
     geo.partial = scratch + (size_t)a.B * a.pb.G;
-    // 64-row tiles, 512 threads, one CTA per SM.  (A 32-row / 256-thread variant with two CTAs per SM was measured in
-    // round 2 and dropped: 2.75 ms vs 2.58 ms per C5 step without cp.async, 2.09 vs 1.92 ms with it.)
-    void (*tile)(const PassArgs, const O2Geom) = L.async ? online2d_tile_kernel<true, o2::kTH, o2::kThreads>
-                                                         : online2d_tile_kernel<false, o2::kTH, o2::kThreads>;
-    const int threads = o2::kThreads;
-    cudaError_t e = cudaFuncSetAttribute(tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes);
+    geo.hyp = reinterpret_cast<O2Hyp *>(geo.partial + (size_t)a.B * L.tilesY * L.tilesX * 2);
+    geo.counter = reinterpret_cast<int *>(geo.hyp + a.B);
+    cudaError_t e = cudaMemsetAsync(geo.counter, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
-    const unsigned tiles = (unsigned)(L.tilesY * L.tilesX);
-    tile<<<(unsigned)a.B * tiles, threads, L.smemBytes, st>>>(a, geo);
+    online2d_desc_kernel<<<(unsigned)((a.B + 127) / 128), 128, 0, st>>>(a, geo.hyp);
+    // persistent CTAs, one per SM (64-row tiles, 512 threads), units of tiles from an atomic queue.  (A 32-row /
+    // 256-thread variant with two CTAs per SM was measured in round 2 and dropped: 2.09 vs 1.92 ms per C5 step.)
+    void (*tile)(const PassArgs, const O2Geom) = L.async ? online2d_tile_kernel<true> : online2d_tile_kernel<false>;
+    e = cudaFuncSetAttribute(tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes);
+    if (e != cudaSuccess) return (int)e;
+    const long long tiles = (long long)L.tilesY * L.tilesX;
+    const long long units = a.B * ((tiles + kO2Chunk - 1) / kO2Chunk);
+    const long long grid = units < a.num_sms ? units : a.num_sms;
+    tile<<<(unsigned)grid, o2::kThreads, L.smemBytes, st>>>(a, geo);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     long long chunks = (a.pb.G + 256LL * 8 - 1) / (256LL * 8);  // 8 cells per thread

@@ -94,9 +94,7 @@ CONFIGS = {
 # default dispatch of the shapes behind BASELINE.json configs[1] (1-D grid, one GaussianRandomWalk: warp-specialised
 # fused kernels) and configs[2]/[3] (2-D grids beyond one SM's shared memory: cluster-resident kernels)
 EXPECTED_FAMILY = {'poisson_c2_small': 'fast1d_ws', 'poisson_wide_kernels': 'fast1d_ws', 'poisson_odd_grid': 'fast1d_ws',
-                   'poisson_regime': 'resident', 'gauss_2d_200x200_stream': 'stream', 'gauss_2d_256x96_stream': 'stream'}
-# (the two *_stream shapes carry axis-0 kernels wider than a band of rows: the cluster kernels decline, the global-memory
-# stream kernels take over; the cluster kernels at these sizes are covered by the C3 / C4 tests below)
+                   'poisson_regime': 'resident'}
 
 
 @pytest.mark.parametrize('name', sorted(CONFIGS))
