@@ -130,6 +130,45 @@ class Study(object):
         if not silent:
             print('+ Created new study.')
 
+    # ------------------------------------------------------------------------- device-resident results (row f4)
+    # After a fit the [T x G] posterior sequence stays in HBM; reading `posteriorSequence` downloads it (once) and
+    # releases the device copy.  Marginal distributions and the time-averaged posterior (core.py:886, :915, :979-980)
+    # are computed on the device while it is there: only [T x n_axis] numbers cross PCIe instead of T x G.
+    @property
+    def posteriorSequence(self):
+        dev = self.__dict__.get('_postDev')
+        if dev is not None:
+            eng, plan, tensor, shape = dev
+            self.__dict__['_postHost'] = eng.to_host(tensor).reshape(shape)
+            self.__dict__['_postDev'] = None
+        return self.__dict__.get('_postHost', [])
+
+    @posteriorSequence.setter
+    def posteriorSequence(self, value):
+        self.__dict__['_postHost'] = value
+        self.__dict__['_postDev'] = None
+
+    def _setDeviceSequence(self, eng, plan, tensor, shape):
+        self.__dict__['_postHost'] = None
+        self.__dict__['_postDev'] = (eng, plan, tensor, list(shape))
+
+    def _deviceMarginal(self, axis, row=None, average=False):
+        """Marginal over the other grid axis, computed in HBM: all rows ([T, n_axis]), one row, or the time average."""
+        eng, plan, tensor, shape = self.__dict__['_postDev']
+        T, G = shape[0], int(np.prod(shape[1:]))
+        seq = tensor.reshape(T, G)
+        n = shape[1 + axis]
+        if average:
+            mean = eng.empty(G)
+            eng.time_average(plan, seq, T, mean)
+            seq, T = mean.reshape(1, G), 1
+        elif row is not None:
+            seq, T = seq[row:row + 1], 1
+        out = eng.empty((T, n))
+        eng.marginal(plan, seq, T, axis, out)
+        host = eng.to_host(out)
+        return host if (row is None and not average) else host[0]
+
     # ------------------------------------------------------------------------------------------ plumbing
     def _engine(self):
         return self._engineOverride if self._engineOverride is not None else _engine.default_engine()
@@ -212,8 +251,10 @@ class Study(object):
         self.setTransitionModel(T, silent=silent)
 
     def __getstate__(self):
+        self.posteriorSequence  # noqa: B018 -- brings a device-resident sequence to the host
         d = self.__dict__.copy()
         d['_engineOverride'] = None  # engines hold library handles and a device: not part of a saved study
+        d['_postDev'] = None
         return d
 
     def _attachBackPointers(self):
@@ -449,7 +490,7 @@ class Study(object):
             return
         means = eng.empty((len(self.gridSize), T))
         eng.finalize(ses.plan, seq, T, means, _engine.F_NORMALIZE_ROWS if rawRows else 0)
-        self.posteriorSequence = eng.to_host(seq).reshape([T] + self.gridSize)
+        self._setDeviceSequence(eng, ses.plan, seq[0], [T] + list(self.gridSize))
         self.posteriorMeanValues = eng.to_host(means)
         if not silent:
             if not forwardOnly:
@@ -567,6 +608,8 @@ class Study(object):
         return names.index(name)
 
     def _hasPosterior(self):
+        if self.__dict__.get('_postDev') is not None:
+            return True
         return isinstance(self.posteriorSequence, np.ndarray) and self.posteriorSequence.size > 0
 
     def getParameterMeanValues(self, name):
@@ -577,16 +620,21 @@ class Study(object):
         if not self._hasPosterior():
             raise PostProcessingError('Cannot plot posterior sequence as it has not yet been computed. '
                                       'Run complete fit.')
-        if isinstance(t, str) and t == 'avg':
-            dist = np.sum(self.posteriorSequence, axis=0) / len(self.posteriorSequence)
-        else:
+        axis = self._parameterIndex(name)
+        average = isinstance(t, str) and t == 'avg'
+        if not average:
             stamps = list(self.formattedTimestamps)
             if t not in stamps:
                 raise PostProcessingError('Supplied time ({}) does not exist in data or is out of range.'.format(t))
-            dist = self.posteriorSequence[stamps.index(t)]
-        axis = self._parameterIndex(name)
-        others = tuple(a for a in range(dist.ndim) if a != axis)
-        marginal = np.sum(dist, axis=others) if others else dist.copy()
+        if self.__dict__.get('_postDev') is not None:  # sequence still in HBM: reduce it there
+            marginal = self._deviceMarginal(axis, row=None if average else stamps.index(t), average=average)
+        else:
+            if average:
+                dist = np.sum(self.posteriorSequence, axis=0) / len(self.posteriorSequence)
+            else:
+                dist = self.posteriorSequence[stamps.index(t)]
+            others = tuple(a for a in range(dist.ndim) if a != axis)
+            marginal = np.sum(dist, axis=others) if others else dist.copy()
         if density:
             marginal = marginal / self.latticeConstant[axis]
         return self.marginalGrid[axis], marginal
@@ -600,9 +648,12 @@ class Study(object):
             raise PostProcessingError('Cannot plot posterior sequence as it has not yet been computed. '
                                       'Run complete fit.')
         axis = self._parameterIndex(name)
-        seq = np.asarray(self.posteriorSequence)
-        others = tuple(a + 1 for a in range(seq.ndim - 1) if a != axis)
-        marginal = np.sum(seq, axis=others) if others else seq.copy()
+        if self.__dict__.get('_postDev') is not None:  # sequence still in HBM: only [T x n_axis] numbers come back
+            marginal = self._deviceMarginal(axis)
+        else:
+            seq = np.asarray(self.posteriorSequence)
+            others = tuple(a + 1 for a in range(seq.ndim - 1) if a != axis)
+            marginal = np.sum(seq, axis=others) if others else seq.copy()
         if density:
             marginal = marginal / self.latticeConstant[axis]
         return self.marginalGrid[axis], marginal
@@ -803,8 +854,22 @@ class HyperStudy(Study):
         return eng, logEAll, aliveAll, localEv, avg, sw['means']
 
     def _sweep(self, forwardOnly, evidenceOnly):
-        eng, logE, alive, localEv, avg, means = self._executeSweep(self._prepareSweep(forwardOnly, evidenceOnly))
+        sw = self._prepareSweep(forwardOnly, evidenceOnly)
+        self._sweepPlan = sw['ses'].plan
+        eng, logE, alive, localEv, avg, means = self._executeSweep(sw)
         return eng, logE, alive, eng.to_host(localEv), avg, means
+
+    @property
+    def averagePosteriorSequence(self):
+        """Evidence-weighted average of the posterior sequences (core.py:1372-1385): the fitted sequence itself."""
+        if self.__dict__.get('_avgIsPosterior'):
+            return self.posteriorSequence
+        return self.__dict__.get('_avgHost')
+
+    @averagePosteriorSequence.setter
+    def averagePosteriorSequence(self, value):
+        self.__dict__['_avgIsPosterior'] = False
+        self.__dict__['_avgHost'] = value
 
     def fit(self, forwardOnly=False, evidenceOnly=False, silent=False, nJobs=1, customHyperGrid=False):
         """Fit every combination of hyper-parameter values and average the models by their evidence (contract of
@@ -857,8 +922,9 @@ class HyperStudy(Study):
         self.logEvidenceList = list(logE)
         T = len(self.formattedData)
         if not evidenceOnly:
-            self.averagePosteriorSequence = eng.to_host(avg).reshape([T] + self.gridSize)
-            self.posteriorSequence = self.averagePosteriorSequence
+            # the averaged sequence stays in HBM until somebody reads it (posteriorSequence / averagePosteriorSequence)
+            self._setDeviceSequence(eng, self._sweepPlan, avg, [T] + list(self.gridSize))
+            self.__dict__['_avgIsPosterior'] = True
             if not silent:
                 print('    + Computed average posterior sequence')
 
@@ -1395,9 +1461,12 @@ class OnlineStudy(HyperStudy):
         """Marginal distributions of one parameter for all steps so far: [T, n_axis] (core.py:2323-2351)."""
         self._needHistory('parameter distributions', 'getCurrentParameterDistribution')
         axis = self._parameterIndex(name)
-        seq = np.asarray(self.posteriorSequence)
-        others = tuple(a + 1 for a in range(seq.ndim - 1) if a != axis)
-        marginal = np.sum(seq, axis=others) if others else seq.copy()
+        if self.__dict__.get('_postDev') is not None:  # sequence still in HBM: only [T x n_axis] numbers come back
+            marginal = self._deviceMarginal(axis)
+        else:
+            seq = np.asarray(self.posteriorSequence)
+            others = tuple(a + 1 for a in range(seq.ndim - 1) if a != axis)
+            marginal = np.sum(seq, axis=others) if others else seq.copy()
         if density:
             marginal = marginal / self.latticeConstant[axis]
         return self.marginalGrid[axis], marginal

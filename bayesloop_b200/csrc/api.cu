@@ -448,12 +448,20 @@ bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, 
     const DevProblem &d = pl->dev;
     if (pl->opt.no_fast1d || pl->opt.no_ws) return false;
     if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
-    int nt = 128;
-    if (d.G <= 96 * 3) M = 3;
-    else if (d.G <= 96 * 7) M = 7;
-    else if (d.G <= 96 * 11) M = 11;
-    else if (d.G <= 224 * 11) { M = 11; nt = 256; }
-    else return false;
+    // 4 compute warps (one per SM sub-partition) + the service warp = 160 threads, M = smallest odd cell count per
+    // thread that covers the grid; beyond 128 * 11 cells 8 compute warps (two per sub-partition) = 288 threads.
+    // Round 2, per-warp trace profiles/r2d_ws_trace.txt: with 3 compute warps per chain the busiest sub-partition
+    // carried 1.6x the mean convolution load (the chain's pace is set by it); with 4 the load is level (0.93).
+    int nt = 160;
+    M = 0;
+    for (int m = 3; m <= 11 && !M; m += 2)
+        if (128 * m >= d.G) M = m;
+    if (!M) {
+        nt = 288;
+        for (int m = 7; m <= 11 && !M; m += 2)
+            if (256 * m >= d.G) M = m;
+    }
+    if (!M) return false;
     if (pl->opt.ws_m > 0 && pl->opt.ws_nt > 0 && (pl->opt.ws_nt / 32 - 1) * 32 * pl->opt.ws_m >= d.G &&
         fwd_fast1d_ws_entry(pl->opt.ws_m, pl->opt.ws_nt)) {  // tuning override: (cells per thread, threads)
         M = pl->opt.ws_m;
@@ -1013,6 +1021,34 @@ int blg_finalize(blg_plan *pl, double *seq, int64_t T, double *means, uint32_t f
     long long blocks = T < (long long)pl->num_sms * 8 ? T : (long long)pl->num_sms * 8;
     finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(seq, T, d.G, d.n1, d.ndim, d.c0, d.c1, means,
                                                                          (flags & BLG_F_NORMALIZE_ROWS) ? 1 : 0);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int blg_marginal(blg_plan *pl, const double *seq, int64_t T, int32_t axis, double *out, void *stream) {
+    if (!pl || !seq || !out) return fail("null argument");
+    const DevProblem &d = pl->dev;
+    if (axis < 0 || axis >= d.ndim) return fail("axis out of range");
+    if (T <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.ndim == 1) {
+        CUDA_TRY(cudaMemcpyAsync(out, seq, (size_t)T * d.G * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    const int nt = 256;
+    const long long threads = axis == 0 ? T * d.n0 * 32 : T * d.n1;
+    marginal_kernel<<<(unsigned)((threads + nt - 1) / nt), nt, 0, st>>>(seq, T, d.n0, d.n1, axis, out);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int blg_time_average(blg_plan *pl, const double *seq, int64_t T, double *out, void *stream) {
+    if (!pl || !seq || !out) return fail("null argument");
+    if (T <= 0) return fail("empty sequence");
+    const int nt = 256;
+    time_average_kernel<<<(unsigned)((pl->dev.G + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(seq, T, pl->dev.G, out);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return 0;

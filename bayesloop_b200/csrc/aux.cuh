@@ -180,6 +180,41 @@ __global__ void rebase_factor_kernel(const double *__restrict__ from, const doub
     f[0] = (isfinite(a) && isfinite(b) && b != a) ? exp(a - b) : 1.0;
 }
 
+// Marginal over the other axis of every row of a [T][n0][n1] sequence (core.py:915, :979-980).  One warp per output
+// element group: axis 0 -> out[t][i0] = sum_j seq[t][i0][j] (contiguous line, lanes stride the line, shuffle sum);
+// axis 1 -> out[t][j] = sum_i seq[t][i][j] (one thread per column, coalesced across the warp).  Fixed order.
+__global__ void marginal_kernel(const double *__restrict__ seq, long long T, int n0, int n1, int axis,
+                                double *__restrict__ out) {
+    if (axis == 0) {
+        const long long line = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // (t, i0)
+        const int lane = threadIdx.x & 31;
+        if (line >= T * n0) return;
+        const double *p = seq + line * n1;
+        double s = 0.0;
+        for (int j = lane; j < n1; j += 32) s += p[j];
+        s = warp_sum(s);
+        if (lane == 0) out[line] = s;
+    } else {
+        const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (t, j)
+        if (e >= T * n1) return;
+        const long long t = e / n1;
+        const int j = (int)(e - t * n1);
+        const double *p = seq + t * (long long)n0 * n1 + j;
+        double s = 0.0;
+        for (int i = 0; i < n0; ++i) s += p[(long long)i * n1];
+        out[e] = s;
+    }
+}
+
+// out[g] = (1/T) sum_t seq[t][g]   (core.py:886)
+__global__ void time_average_kernel(const double *__restrict__ seq, long long T, long long G, double *__restrict__ out) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double s = 0.0;
+    for (long long t = 0; t < T; ++t) s += __ldcs(seq + t * G + g);
+    out[g] = s / (double)T;
+}
+
 __global__ void fill_kernel(double *__restrict__ x, long long count, double value) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < count) x[e] = value;

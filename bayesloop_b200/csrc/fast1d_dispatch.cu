@@ -24,35 +24,28 @@ PassKernel bwd_fast1d_entry(int M, int nt) {
     }
 }
 
-// warp-specialised kernels (fast1d_ws_inst.cu)
+// warp-specialised kernels (fast1d_ws_inst.cu): 4 compute warps + 1 service warp (160 threads) or 8 + 1 (288), so
+// that every SM sub-partition carries the same number of compute warps of every chain
+#define BLG_WS_ALL(X) X(3, 160) X(5, 160) X(7, 160) X(9, 160) X(11, 160) X(7, 288) X(9, 288) X(11, 288)
 #define BLG_WS(M, NT)                          \
     PassKernel fwd_fast1d_ws_m##M##_nt##NT(); \
     PassKernel bwd_fast1d_ws_m##M##_nt##NT();
-BLG_WS(3, 128)
-BLG_WS(7, 128)
-BLG_WS(11, 128)
-BLG_WS(11, 256)
-BLG_WS(9, 160)
-BLG_WS(7, 192)
+BLG_WS_ALL(BLG_WS)
 #undef BLG_WS
 
 PassKernel fwd_fast1d_ws_entry(int M, int nt) {
-    if (nt == 128 && M == 3) return fwd_fast1d_ws_m3_nt128();
-    if (nt == 128 && M == 7) return fwd_fast1d_ws_m7_nt128();
-    if (nt == 128 && M == 11) return fwd_fast1d_ws_m11_nt128();
-    if (nt == 256 && M == 11) return fwd_fast1d_ws_m11_nt256();
-    if (nt == 160 && M == 9) return fwd_fast1d_ws_m9_nt160();
-    if (nt == 192 && M == 7) return fwd_fast1d_ws_m7_nt192();
+#define BLG_WS(MM, NT) \
+    if (nt == NT && M == MM) return fwd_fast1d_ws_m##MM##_nt##NT();
+    BLG_WS_ALL(BLG_WS)
+#undef BLG_WS
     return nullptr;
 }
 
 PassKernel bwd_fast1d_ws_entry(int M, int nt) {
-    if (nt == 128 && M == 3) return bwd_fast1d_ws_m3_nt128();
-    if (nt == 128 && M == 7) return bwd_fast1d_ws_m7_nt128();
-    if (nt == 128 && M == 11) return bwd_fast1d_ws_m11_nt128();
-    if (nt == 256 && M == 11) return bwd_fast1d_ws_m11_nt256();
-    if (nt == 160 && M == 9) return bwd_fast1d_ws_m9_nt160();
-    if (nt == 192 && M == 7) return bwd_fast1d_ws_m7_nt192();
+#define BLG_WS(MM, NT) \
+    if (nt == NT && M == MM) return bwd_fast1d_ws_m##MM##_nt##NT();
+    BLG_WS_ALL(BLG_WS)
+#undef BLG_WS
     return nullptr;
 }
 

@@ -14,8 +14,8 @@ using PassKernel = void (*)(const PassArgs);
 PassKernel fwd_fast1d_entry(int M, int nt);
 PassKernel bwd_fast1d_entry(int M, int nt);
 
-// warp-specialised fast 1-D kernels (fast1d_ws.cuh): (M, nt) in {(3,128), (7,128), (11,128), (11,256)}; nt/32 - 1
-// compute warps own M cells per thread, one service warp normalises / stores / prefetches
+// warp-specialised fast 1-D kernels (fast1d_ws.cuh): nt = 160 (4 compute warps, M in {3,5,7,9,11}) or 288 (8 compute
+// warps, M in {7,9,11}); the compute warps own M cells per thread, one service warp normalises / stores / prefetches
 PassKernel fwd_fast1d_ws_entry(int M, int nt);
 PassKernel bwd_fast1d_ws_entry(int M, int nt);
 

@@ -213,6 +213,9 @@ class Engine:
                                        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
         L.blg_rebase.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p]
+        L.blg_marginal.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
+                                   ctypes.c_void_p]
+        L.blg_time_average.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
         L.blg_scale.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p]
         if L.blg_version() != 1:
             raise EngineError('ABI version mismatch in {}'.format(lib_path))
@@ -374,6 +377,12 @@ class Engine:
     def rebase(self, plan, x, count, shift_from, shift_to):
         self._check(self.lib.blg_rebase(plan.handle, _ptr(x), int(count), _ptr(shift_from), _ptr(shift_to),
                                         self.stream()))
+
+    def marginal(self, plan, seq, T, axis, out):
+        self._check(self.lib.blg_marginal(plan.handle, _ptr(seq), int(T), int(axis), _ptr(out), self.stream()))
+
+    def time_average(self, plan, seq, T, out):
+        self._check(self.lib.blg_time_average(plan.handle, _ptr(seq), int(T), _ptr(out), self.stream()))
 
     def scale(self, plan, x, count, factor):
         self._check(self.lib.blg_scale(plan.handle, _ptr(x), int(count), float(factor), self.stream()))

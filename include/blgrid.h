@@ -191,6 +191,14 @@ int blg_rebase(blg_plan *plan, double *x, int64_t count, const double *from, con
  * :1416-1419.  means is device [ndim][T]. */
 int blg_finalize(blg_plan *plan, double *seq, int64_t T, double *means, uint32_t flags, void *stream);
 
+/* Post-processing queries on a device-resident [T][G] sequence without downloading it:
+ *   blg_marginal      out[t][i] = sum over the OTHER grid axis of seq[t][.]   (core.py:915, :979-980); out device
+ *                     [T][n[axis]]; a 1-D grid is copied
+ *   blg_time_average  out[g] = (1/T) sum_t seq[t][g]                          (core.py:886); out device [G]
+ * Fixed summation order (deterministic). */
+int blg_marginal(blg_plan *plan, const double *seq, int64_t T, int32_t axis, double *out, void *stream);
+int blg_time_average(blg_plan *plan, const double *seq, int64_t T, double *out, void *stream);
+
 /* Weighted sum of K rows: out[j] = sum_k weight[k] * state[k][j], j < n.  Used for the OnlineStudy
  * marginalisations (core.py:2195-2197, :2212; n = G) and for the averaged local evidence of a HyperStudy
  * (core.py:1410; K = B, n = T).  state device [K][n], weight device [K], out device [n]. */

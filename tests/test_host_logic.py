@@ -112,3 +112,28 @@ def test_edge_cases_behave_like_the_reference(use_oracle):
         P.set(bl.om.Poisson('r', bl.oint(0, 6, 50)), bl.tm.Static(), silent=True)
         with pytest.raises(ValueError):
             P.fit(silent=True)
+
+
+def test_marginals_from_the_resident_sequence_equal_host_reductions(use_oracle):
+    """while the fitted [T x G] sequence is still in engine memory, marginal distributions and the
+    time average (core.py:886, :915, :979-980) are reduced there (blg_marginal / blg_time_average); once the attribute
+    has been read they are NumPy reductions of the downloaded array.  Both paths must agree."""
+    import bayesloop_b200 as bl
+    S, _ = None, None
+    rng = np.random.default_rng(3)
+    S = bl.HyperStudy(silent=True)
+    S.loadData(rng.normal(0.3, 1.0, 25), silent=True)
+    S.set(bl.om.Gaussian('mean', bl.cint(-2, 2, 18), 'std', bl.oint(0, 3, 14)),
+          bl.tm.GaussianRandomWalk('s', bl.cint(0, 0.3, 3), target='mean'), silent=True)
+    S.fit(silent=True)
+    assert S.__dict__['_postDev'] is not None  # nothing has been downloaded yet
+    dev = {k: (S.getParameterDistributions(k)[1], S.getParameterDistribution(7, k)[1], S.getParameterDistribution('avg', k)[1])
+           for k in ('mean', 'std')}
+    assert S.__dict__['_postDev'] is not None
+    seq = S.averagePosteriorSequence  # download
+    assert S.__dict__['_postDev'] is None and seq.shape == (25, 18, 14)
+    for k in ('mean', 'std'):
+        host = (S.getParameterDistributions(k)[1], S.getParameterDistribution(7, k)[1], S.getParameterDistribution('avg', k)[1])
+        for a, b in zip(dev[k], host):
+            np.testing.assert_allclose(a, b, rtol=1e-13)
+    assert dev['mean'][0].shape == (25, 18) and dev['std'][0].shape == (25, 14)
