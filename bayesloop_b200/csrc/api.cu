@@ -409,7 +409,7 @@ bool resident_layout(const blg_plan *pl, const blg_program &pg, bool backward, b
 // Fast path (fast1d.cuh): 1-D grid, program = one GaussianRandomWalk, halo <= n, one work item per thread.
 bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int M, PassArgs &a, Layout &lay) {
     const DevProblem &d = a.pb;  // om_kind is TABLE when the shared likelihood table is in use
-    if (pl->opt.no_fast1d) return false;
+    if (pl->opt.no_fast1d || pl->opt.force_stream) return false;
     if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
     const int halo = even_up(pg.max_radius[0] + 2 * M);
     const int items = (d.G + M - 1) / M;
@@ -446,7 +446,7 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int
 // warps (threads/32 - 1) cover the grid with M cells per thread.
 bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, PassArgs &a, Layout &lay, int &M) {
     const DevProblem &d = pl->dev;
-    if (pl->opt.no_fast1d || pl->opt.no_ws) return false;
+    if (pl->opt.no_fast1d || pl->opt.no_ws || pl->opt.force_stream) return false;
     if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
     // 4 compute warps (one per SM sub-partition) + the service warp = 160 threads, M = smallest odd cell count per
     // thread that covers the grid; beyond 128 * 11 cells 8 compute warps (two per sub-partition) = 288 threads.

@@ -38,6 +38,7 @@ void cluster2d_params(int *threads, int *m0, int *m1, int *cells, int *wpad);
 // online2d_scratch_doubles(B, G, L) doubles; online2d_run returns a cudaError_t (0 = launched the three kernels).
 struct O2Launch {
     int async;  // tile loads through cp.async (the default; measured 1.92 vs 2.58 ms per C5 step, profiles/r2a_online_ab.txt)
+    int pipelined;  // the output tile has its own shared-memory buffer (set by online2d_plan when it fits)
     int tilesY, tilesX, P, inRowsMax, w0len, w1len;
     size_t smemBytes;
 };

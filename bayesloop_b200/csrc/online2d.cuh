@@ -43,6 +43,8 @@ struct O2Geom {
     double *partial;     // [H][tiles][2]: sum(v * lik), sum(v)
     O2Hyp *hyp;          // [H]
     int *counter;        // work queue: next unit (zeroed before the launch)
+    int pipelined;       // 1: the output tile has a shared-memory buffer of its own, so the next tile's loads overlap
+                         //    the axis-1 pass and the epilogue; 0 (radii too wide for that): it reuses `in`
 };
 
 constexpr int kO2Chunk = 8;  // tiles of one hypothesis handed out per queue access (weights are built once per unit)
@@ -104,14 +106,17 @@ __global__ void online2d_desc_kernel(const PassArgs a, O2Hyp *out) {
     out[h] = d;
 }
 
-// shared memory (doubles): in[inRowsMax][P] | mid[kTH][P] | W0[w0len] | W1[w1len] | reduction scratch [4 * kMaxWarps]
+// shared memory (doubles): in[inRowsMax][P] | mid[kTH][P] | out[kTH][kOutP] | W0[w0len] | W1[w1len] | reduction
+// scratch [4 * kMaxWarps]
 //
 // PERSISTENT, PIPELINED (round 2): one CTA per SM takes units of kO2Chunk consecutive tiles of one hypothesis from an
 // atomic queue (cost per tile varies with the radii).  Per unit the weights are built once; per tile
 //     wait for the haloed input tile (cp.async) -> axis-0 convolution in -> mid -> barrier
-//     -> issue the NEXT tile's loads into `in` -> axis-1 convolution out of `mid` into registers, fused with the
-//        clamp, the likelihood multiply, the global store and the partial sums (conv1_epilogue_phase)
-// so the tile loads overlap the second convolution and the output tile never returns to shared memory.
+//     -> issue the NEXT tile's loads into `in` -> axis-1 convolution mid -> out -> barrier -> epilogue (clamp,
+//        likelihood multiply, coalesced global store, partial sums)
+// so the tile loads overlap the second convolution and the epilogue.  (A variant that fused the epilogue into the
+// axis-1 write-back from registers was measured and dropped: its per-row scattered 8-byte global accesses cost what
+// the saved shared-memory pass gained, 1.33 ms per C5 step either way.)
 // ASYNC = false keeps the plain LDG -> STS loads (no overlap; the reference point of profiles/r2a_online_ab.txt).
 template <bool ASYNC>
 __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const PassArgs a, const O2Geom geo) {
@@ -124,7 +129,9 @@ __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const Pa
     const long long units = a.B * (long long)chunksPerHyp;
     double *in = sm;
     double *mid = in + (size_t)geo.inRowsMax * geo.P;
-    double *W0 = mid + (size_t)TH * geo.P;
+    double *own = mid + (size_t)TH * geo.P;
+    double *out = geo.pipelined ? own : in;
+    double *W0 = own + (geo.pipelined ? (size_t)TH * o2::kOutP : 0);
     double *W1 = W0 + geo.w0len;
     RedScratch rs;
     rs.buf = W1 + geo.w1len;
@@ -210,19 +217,25 @@ __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const Pa
             __syncthreads();  // input tile (and, for k = 0, the weights) visible to everybody
             o2::conv0_phase(t, in, mid, W0, tid, nt);
             __syncthreads();  // `in` is dead: the next tile may land in it while this one is finished out of `mid`
-            o2::Tile<TH> cur = t;
-            if (k + 1 < count) {
-                place(k + 1);
-                if (ASYNC) {
-                    o2::load_phase(t, src, in, tid, nt, AsyncCopy());
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                } else {
-                    o2::load_phase(t, src, in, tid, nt);
+            const o2::Tile<TH> cur = t;
+            auto loadNext = [&]() {
+                if (k + 1 < count) {
+                    place(k + 1);
+                    if (ASYNC) {
+                        o2::load_phase(t, src, in, tid, nt, AsyncCopy());
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    } else {
+                        o2::load_phase(t, src, in, tid, nt);
+                    }
                 }
-            }
+            };
+            if (geo.pipelined) loadNext();
+            o2::conv1_phase(cur, mid, out, W1, tid, nt);
+            __syncthreads();
             double s1 = 0.0, s2 = 0.0;
-            o2::conv1_epilogue_phase(cur, mid, W1, dst, clamp, hp.limit, lik, tid, nt, s1, s2);
-            publish(k, s1, s2);  // its barrier also orders this tile's reads of `mid` before the next axis-0 pass
+            o2::epilogue_phase(cur, out, dst, clamp, hp.limit, lik, tid, nt, s1, s2);
+            publish(k, s1, s2);  // its barrier also orders this tile's reads of `out` before the next axis-1 pass
+            if (!geo.pipelined) loadNext();  // `out` aliases `in`: the next tile can only land now
         }
     }
 }

@@ -12,9 +12,12 @@ bool online2d_plan(int n0, int n1, int r0max, int r1max, bool async, O2Launch *L
     L->inRowsMax = o2::kTH + 2 * r0max;
     L->w0len = o2::padded_taps(r0max, o2::kM0);
     L->w1len = o2::padded_taps(r1max, o2::kM1);
-    const size_t doubles = (size_t)L->inRowsMax * L->P + (size_t)o2::kTH * L->P + L->w0len + L->w1len + 4 * kMaxWarps;
-    L->smemBytes = doubles * sizeof(double);
-    return L->smemBytes <= 232448;  // 227 KB opt-in maximum per CTA on sm_100
+    const size_t base = (size_t)L->inRowsMax * L->P + (size_t)o2::kTH * L->P + L->w0len + L->w1len + 4 * kMaxWarps;
+    const size_t limit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+    // pipelined: the output tile gets a buffer of its own (the next tile loads while this one is finished)
+    L->pipelined = (base + (size_t)o2::kTH * o2::kOutP) * sizeof(double) <= limit ? 1 : 0;
+    L->smemBytes = (base + (L->pipelined ? (size_t)o2::kTH * o2::kOutP : 0)) * sizeof(double);
+    return L->smemBytes <= limit;
 }
 
 size_t online2d_scratch_doubles(long long B, long long G, const O2Launch &L) {
@@ -30,6 +33,7 @@ int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStre
     geo.inRowsMax = L.inRowsMax;
     geo.w0len = L.w0len;
     geo.w1len = L.w1len;
+    geo.pipelined = L.pipelined;
     geo.scratch = scratch;
     geo.partial = scratch + (size_t)a.B * a.pb.G;
     geo.hyp = reinterpret_cast<O2Hyp *>(geo.partial + (size_t)a.B * L.tilesY * L.tilesX * 2);

@@ -108,56 +108,47 @@ BLG_HD void conv0_phase(const Tile<TH> &t, const double *in, double *mid, const 
     conv_valid<kM0>(in, mid, W0, 2 * t.R0 + 1, TH, t.inRows(), t.P, t.inCols(), 1, t.P, 1, tid, nt);
 }
 
-// Phase B+E, fused: axis-1 convolution of every row of mid[TH][P] straight into registers, then
-// v = transitioned prior of the cell (optionally clamped from below: RegimeSwitch, transitionModels.py:405),
-// u = v * likelihood -> dst (global, unnormalised); per-thread partial sums s1 += v, s2 += u.
-// Work item = kM1 consecutive cells of one row; consecutive threads take consecutive ROWS (odd pitch => conflict-free
-// 64-bit shared loads).  The likelihoods of the item's cells are requested BEFORE the convolution, so their latency
-// hides behind its arithmetic; the output tile never goes back to shared memory, which leaves the input buffer free
-// for the NEXT tile's loads while this phase runs.  `lik(gi, gj, g)`: likelihood of grid cell (gi, gj), g = gi * n1 + gj.
+// Phase B: axis-1 convolution of every row: mid[TH][P] -> out[TH][kOutP] (kTW columns).  `out` is a buffer of its own:
+// the haloed input buffer is already receiving the NEXT tile while this phase and the epilogue run.
+constexpr int kOutP = kTW + 1;  // odd pitch: consecutive threads take consecutive rows => conflict-free 64-bit stores
+
+template <int TH>
+BLG_HD void conv1_phase(const Tile<TH> &t, const double *mid, double *out, const double *W1, int tid, int nt) {
+    conv_valid<kM1>(mid, out, W1, 2 * t.R1 + 1, kTW, t.inCols(), 1, TH, t.P, 1, kOutP, tid, nt);
+}
+
+// Phase E: v = transitioned prior of the cell (optionally clamped from below: RegimeSwitch, transitionModels.py:405),
+// u = v * likelihood -> dst (global, unnormalised); per-thread partial sums s1 += v, s2 += u.  Consecutive threads
+// take consecutive cells of a row: coalesced likelihood loads and stores.
+// `lik(gi, gj, g)` returns the likelihood of grid cell (gi, gj), g = gi * n1 + gj.
 template <int TH, class Lik>
-BLG_HD void conv1_epilogue_phase(const Tile<TH> &t, const double *mid, const double *W1, double *dst, bool clamp,
-                                 double limit, Lik lik, int tid, int nt, double &s1, double &s2) {
-    constexpr int M = kM1;
-    constexpr int S = kTW / M;
-    const int taps = 2 * t.R1 + 1, last = t.inCols() - 1;
-    for (int w = tid; w < S * TH; w += nt) {
-        const int s = w / TH, l = w - s * TH;
-        const int gi = t.r0 + l, gj0 = t.c0 + s * M;
-        if (gi >= t.n0 || gj0 >= t.n1) continue;  // item outside the grid (ragged tile)
-        const long long g0 = (long long)gi * t.n1 + gj0;
-        double lk[M];
+BLG_HD void epilogue_phase(const Tile<TH> &t, const double *out, double *dst, bool clamp, double limit, Lik lik, int tid, int nt,
+                           double &s1, double &s2) {
+    // batches of 4 cells per thread: the likelihood requests of a batch are all in flight before the first product
+    // (one request -> multiply -> store at a time left 12 % of the kernel's stall samples on that multiply)
+    constexpr int B = 4;
+    for (int e0 = tid; e0 < TH * kTW; e0 += B * nt) {
+        double lk[B], v[B];
+        long long g[B];
+        bool ok[B];
 #pragma unroll
-        for (int m = 0; m < M; ++m) lk[m] = gj0 + m < t.n1 ? lik(gi, gj0 + m, g0 + m) : 0.0;
-        const double *line = mid + l * t.P;
-        int idx = s * M;
-        double win[M], acc[M];
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const int q = idx + m < last ? idx + m : last;
-            win[m] = line[q];
-            acc[m] = 0.0;
-        }
-        idx += M;
-        for (int j0 = 0; j0 < taps; j0 += M) {
-#pragma unroll
-            for (int u = 0; u < M; ++u) {
-                const double wt = W1[j0 + u];
-#pragma unroll
-                for (int m = 0; m < M; ++m) acc[m] = fma(wt, win[(u + m) % M], acc[m]);
-                const int q = idx < last ? idx : last;
-                win[u] = line[q];
-                ++idx;
-            }
+        for (int b = 0; b < B; ++b) {
+            const int e = e0 + b * nt;
+            const int i = e / kTW, j = e - i * kTW;
+            const int gi = t.r0 + i, gj = t.c0 + j;
+            ok[b] = e < TH * kTW && gi < t.n0 && gj < t.n1;
+            g[b] = (long long)gi * t.n1 + gj;
+            lk[b] = ok[b] ? lik(gi, gj, g[b]) : 0.0;
+            v[b] = ok[b] ? out[i * kOutP + j] : 0.0;
         }
 #pragma unroll
-        for (int m = 0; m < M; ++m)
-            if (gj0 + m < t.n1) {
-                double v = acc[m];
-                if (clamp) v = v < limit ? limit : v;
-                const double u = v * lk[m];
-                dst[g0 + m] = u;
-                s1 += v;
+        for (int b = 0; b < B; ++b)
+            if (ok[b]) {
+                double x = v[b];
+                if (clamp) x = x < limit ? limit : x;
+                const double u = x * lk[b];
+                dst[g[b]] = u;
+                s1 += x;
                 s2 += u;
             }
     }
@@ -168,18 +159,31 @@ BLG_HD void conv1_epilogue_phase(const Tile<TH> &t, const double *mid, const dou
 template <int TH, class Lik>
 BLG_HD void pointwise_phase(const Tile<TH> &t, const double *src, const double *reset, double scale, double *dst, bool clamp,
                             double limit, Lik lik, int tid, int nt, double &s1, double &s2) {
-    for (int e = tid; e < TH * kTW; e += nt) {
-        const int i = e / kTW, j = e - i * kTW;
-        const int gi = t.r0 + i, gj = t.c0 + j;
-        if (gi < t.n0 && gj < t.n1) {
-            const long long g = (long long)gi * t.n1 + gj;
-            double v = reset ? reset[g] * scale : src[g];
-            if (clamp) v = v < limit ? limit : v;
-            const double u = v * lik(gi, gj, g);
-            dst[g] = u;
-            s1 += v;
-            s2 += u;
+    constexpr int B = 4;  // batches as in epilogue_phase: all global requests of a batch in flight together
+    for (int e0 = tid; e0 < TH * kTW; e0 += B * nt) {
+        double lk[B], v[B];
+        long long g[B];
+        bool ok[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int e = e0 + b * nt;
+            const int i = e / kTW, j = e - i * kTW;
+            const int gi = t.r0 + i, gj = t.c0 + j;
+            ok[b] = e < TH * kTW && gi < t.n0 && gj < t.n1;
+            g[b] = (long long)gi * t.n1 + gj;
+            lk[b] = ok[b] ? lik(gi, gj, g[b]) : 0.0;
+            v[b] = ok[b] ? (reset ? reset[g[b]] * scale : src[g[b]]) : 0.0;
         }
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+            if (ok[b]) {
+                double x = v[b];
+                if (clamp) x = x < limit ? limit : x;
+                const double u = x * lk[b];
+                dst[g[b]] = u;
+                s1 += x;
+                s2 += u;
+            }
     }
 }
 

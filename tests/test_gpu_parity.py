@@ -333,16 +333,16 @@ def test_online_study_checkpoint_resume_on_device(use_cuda, tmp_path):
 # (plan option online2d=0 returns to the stream kernels; online2d_small=1 forces it onto grids that would fit).
 
 
-def _online_big(bl, engine, n0=150, n1=130, steps=6):
+def _online_big(bl, engine, n0=150, n1=130, steps=6, w=1.0):
     rng = np.random.default_rng(31)
     x = np.zeros(steps + 1)
     for i in range(1, len(x)):
         x[i] = 0.55 * x[i - 1] + rng.normal()
     S = bl.OnlineStudy(storeHistory=False, silent=True, engine=engine)
     S.setOM(bl.om.ScaledAR1('rho', bl.oint(-1, 1, n0), 'sigma', bl.oint(0, 3, n1)), silent=True)
-    S.add('normal', bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s1', bl.cint(0, 0.12, 3), target='rho'),
-                                                  bl.tm.GaussianRandomWalk('s2', bl.cint(0, 0.2, 2), target='sigma')))
-    S.add('bounded', bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s3', [0.05, 0.1], target='sigma'),
+    S.add('normal', bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s1', bl.cint(0, 0.12 * w, 3), target='rho'),
+                                                  bl.tm.GaussianRandomWalk('s2', bl.cint(0, 0.2 * w, 2), target='sigma')))
+    S.add('bounded', bl.tm.CombinedTransitionModel(bl.tm.GaussianRandomWalk('s3', [0.05 * w, 0.1 * w], target='sigma'),
                                                    bl.tm.RegimeSwitch('q', -6)))
     S.add('chaotic', bl.tm.RegimeSwitch('p', bl.cint(-8, -3, 3)))
     S.add('indep', bl.tm.Independent())
@@ -388,9 +388,9 @@ def test_online2d_matches_cpu_oracle_at_c5_size(cuda_engine, oracle_engine):
     import io
     import bayesloop_b200 as bl
     with contextlib.redirect_stdout(io.StringIO()):
-        got = _online_big(bl, cuda_engine, n0=512, n1=512, steps=3)
+        got = _online_big(bl, cuda_engine, n0=512, n1=512, steps=3, w=0.25)  # widths of the C5 sweep (sigma <= 0.03)
         assert cuda_engine.last_kernel() == 'online2d'
-        want = _online_big(bl, oracle_engine, n0=512, n1=512, steps=3)
+        want = _online_big(bl, oracle_engine, n0=512, n1=512, steps=3, w=0.25)
     _assert_online_agree(got, want)
 
 
