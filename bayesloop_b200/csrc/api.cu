@@ -489,7 +489,7 @@ bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, 
     a.off_misc = even_up(off);
     off = a.off_misc + kMiscDoubles;
     a.ws_part = off;
-    off += 3 * (nt - 32);
+    off += 6 * (nt - 32);  // partial sums: [2 parities][3 sums][compute threads]
     a.ws_ctl = off;
     off += 4;
     lay.bytes = (size_t)off * sizeof(double);
@@ -790,6 +790,9 @@ int fill_args(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32
     a.avg = out->avg;
     a.final_state = out->final_state;
     a.row_scale = (flags & BLG_F_RAW_POSTERIOR) ? out->row_scale : nullptr;
+    a.seq_stride = out->seq_stride > 0 ? out->seq_stride : in->T * (long long)pl->dev.G;
+    a.row_stride = out->row_stride > 0 ? out->row_stride : in->T;
+    if (a.seq_stride < in->T * (long long)pl->dev.G || a.row_stride < in->T) return fail("seq_stride / row_stride smaller than one sequence");
     a.steps = pl->d_steps;
     a.flags = flags;
     a.num_sms = pl->num_sms;
@@ -816,7 +819,8 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     if (prep_steps(pl, in, st)) return -1;
     if (fill_args(pl, in, out, flags, a)) return -1;
     Layout lay;
-    const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !pl->opt.no_bulk;
+    const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && a.seq_stride % 2 == 0 &&
+                        !pl->opt.no_bulk;
     {
         int wsM = 0;
         if (fast1d_ws_layout(pl, in->prog, false, a, lay, wsM)) {
@@ -907,12 +911,13 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
         if (!out->row_scale) return fail("row_scale required with RAW_POSTERIOR");
         if (acc) return fail("RAW_POSTERIOR and ACCUMULATE exclude each other");
         const long long n = in->B * in->T;
-        fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out->row_scale, n, 1.0);
+        fill_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out->row_scale, in->B, in->T, a.row_stride, 1.0);
         ++g_launches;
         CUDA_TRY(cudaGetLastError());
     }
     Layout lay;
-    const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && !pl->opt.no_bulk;
+    const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && a.seq_stride % 2 == 0 &&
+                             !pl->opt.no_bulk;
     {
         int wsM = 0;
         if (alignedRows && !acc && fast1d_ws_layout(pl, in->prog, true, a, lay, wsM)) {
@@ -964,13 +969,15 @@ int blg_accumulate(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, u
     const int nt = 256;
     weights_kernel<<<(unsigned)((in->B + nt - 1) / nt), nt, 0, st>>>(in->log_weight, out->alive, in->B, pl->d_w);
     const long long count = in->T * (long long)pl->dev.G;
+    const long long seqStride = out->seq_stride > 0 ? out->seq_stride : count;
+    const long long rowStride = out->row_stride > 0 ? out->row_stride : in->T;
     const unsigned blocks = (unsigned)((count + nt - 1) / nt);
     if (out->row_scale)  // stateless: the factors are applied whenever the caller hands them (kernels pre-fill 1.0)
         accumulate_kernel<true><<<blocks, nt, 0, st>>>(out->alpha_seq, pl->d_w, in->B, count, out->avg, out->row_scale, in->T,
-                                                       pl->dev.G);
+                                                       pl->dev.G, seqStride, rowStride);
     else
         accumulate_kernel<false><<<blocks, nt, 0, st>>>(out->alpha_seq, pl->d_w, in->B, count, out->avg, nullptr, in->T,
-                                                        pl->dev.G);
+                                                        pl->dev.G, seqStride, rowStride);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -113,7 +113,7 @@ __global__ void weights_kernel(const double *__restrict__ logw, const int *__res
 template <bool SCALED>
 __global__ void accumulate_kernel(const double *__restrict__ seq, const double *__restrict__ w, long long B,
                                   long long count, double *__restrict__ avg, const double *__restrict__ scale, long long T,
-                                  int G) {
+                                  int G, long long seqStride, long long rowStride) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count) return;
     const long long t = SCALED ? e / G : 0;
@@ -122,18 +122,18 @@ __global__ void accumulate_kernel(const double *__restrict__ seq, const double *
     for (; b + 8 <= B; b += 8) {  // 8 independent streaming loads in flight per thread
         double v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcs(seq + (b + u) * count + e);
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(seq + (b + u) * seqStride + e);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const double wb = __ldg(w + b + u);
-            const double p = SCALED ? v[u] * __ldg(scale + (b + u) * T + t) : v[u];
+            const double p = SCALED ? v[u] * __ldg(scale + (b + u) * rowStride + t) : v[u];
             if (wb > 0.0) s = fma(wb, p < kTiny ? kTiny : p, s);  // wb == 0: combo not alive (rows may hold NaN)
         }
     }
     for (; b < B; ++b) {
         const double wb = __ldg(w + b);
-        const double v = __ldcs(seq + b * count + e);
-        const double p = SCALED ? v * __ldg(scale + b * T + t) : v;
+        const double v = __ldcs(seq + b * seqStride + e);
+        const double p = SCALED ? v * __ldg(scale + b * rowStride + t) : v;
         if (wb > 0.0) s = fma(wb, p < kTiny ? kTiny : p, s);
     }
     avg[e] += s;
@@ -218,6 +218,12 @@ __global__ void time_average_kernel(const double *__restrict__ seq, long long T,
 __global__ void fill_kernel(double *__restrict__ x, long long count, double value) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < count) x[e] = value;
+}
+
+// x[b * stride + t] = value for b < B, t < T (rows of a strided [B][T] array)
+__global__ void fill_rows_kernel(double *__restrict__ x, long long B, long long T, long long stride, double value) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < B * T) x[(e / T) * stride + (e % T)] = value;
 }
 
 // One CTA per row t: optional normalisation by the row sum (core.py:1379-1382) and posterior means

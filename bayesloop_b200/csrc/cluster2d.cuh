@@ -515,10 +515,14 @@ __device__ __forceinline__ void c2_sweep(const PassArgs &a, const C2 &s, const L
     const bool table = a.pb.om_kind == BLG_OM_TABLE;
     if (table && fast) {
         const int lastCell = s.cnt - 1;
+        const int own = min((int)threadIdx.x, lastCell);  // cells beyond the band re-read the thread's OWN first cell
 #pragma unroll
         for (int k0 = 0; k0 < kC2Cells; k0 += 8) {
 #pragma unroll
-            for (int k = k0; k < k0 + 8; ++k) load(k, min((int)threadIdx.x + k * kC2Threads, lastCell));
+            for (int k = k0; k < k0 + 8; ++k) {
+                const int g = (int)threadIdx.x + k * kC2Threads;
+                load(k, g <= lastCell ? g : own);
+            }
 #pragma unroll
             for (int k = k0; k < k0 + 8; ++k) {
                 const int g = threadIdx.x + k * kC2Threads;
@@ -641,7 +645,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) 
     }
     c2_arrive();  // all CTAs of the cluster are resident and initialised before anybody pushes
     c2_wait();
-    double *seq = store ? a.alpha_seq + b * T * (long long)G + (size_t)s.r0 * n1 : nullptr;
+    double *seq = store ? a.alpha_seq + b * a.seq_stride + (size_t)s.r0 * n1 : nullptr;
     const double *rb = a.reset_base;
     LogProduct lp;
     lp.init();
@@ -659,7 +663,7 @@ __global__ void __launch_bounds__(NT, 1) fwd_cluster2d_kernel(const PassArgs a) 
         kappa = fast_rcp(norm);
         if (lead) {
             lp.mul(norm);                                              // core.py:403
-            if (a.local) a.local[b * T + tPrev] = norm * pb.lc_prod;   // core.py:404
+            if (a.local) a.local[b * a.row_stride + tPrev] = norm * pb.lc_prod;   // core.py:404
         }
         return true;
     };
@@ -834,7 +838,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
     const int n1 = a.pb.n1;
     uint64_t *bar = reinterpret_cast<uint64_t *>(c2_misc(a) + kC2Mbar);
     uint32_t phase = 0;
-    double *seq = a.alpha_seq + b * T * (long long)G + (size_t)s.r0 * n1;
+    double *seq = a.alpha_seq + b * a.seq_stride + (size_t)s.r0 * n1;
     const uint32_t bandBytes = (uint32_t)(s.cnt * sizeof(double));
     {
         const int total = a.c2_x_doubles;
@@ -865,8 +869,8 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         inv = fast_rcp(sab);  // posterior = alpha*beta / sum(alpha*beta)  core.py:436-441
         kb = fast_rcp(sbb);   // core.py:470 (beta only enters scale-free expressions)
         if (lead) {
-            if (a.local) a.local[b * T + row] = fast_div(1.0, q * inv * pb.lc_prod);  // core.py:463
-            if (raw) a.row_scale[b * T + row] = inv;
+            if (a.local) a.local[b * a.row_stride + row] = fast_div(1.0, q * inv * pb.lc_prod);  // core.py:463
+            if (raw) a.row_scale[b * a.row_stride + row] = inv;
         }
         return true;
     };
@@ -976,7 +980,10 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         const bool pre = !post && c2_in(s.loPre, s.hiPre, i);
         const bool act0 = !post && s.R0 > 0 && c2_in(s.lo0, s.hi0, i);
         const bool act1 = !post && s.R1 > 0 && c2_in(s.lo1, s.hi1, i);
-        if (pre) c2_reset_band(a, s, s.parPre);
+        if (pre) {
+            __syncthreads();  // the publish phase of the previous sweep may still be reading the band rows it pushes
+            c2_reset_band(a, s, s.parPre);
+        }
         if (!act0) issueAlpha();
         double lk[kC2Cells];
         const long long c2 = PROF ? clock64() : 0;

@@ -62,6 +62,8 @@ struct PassArgs {
     const double *prior, *reset_base, *lik_table, *log_weight, *init_state;
     double *logE, *local, *alpha_seq, *avg, *final_state;
     double *row_scale;   // [B][T] normalising factor of each smoothed row (BLG_F_RAW_POSTERIOR) or NULL
+    long long seq_stride;  // doubles between consecutive combos in alpha_seq (T * G when packed)
+    long long row_stride;  // doubles between consecutive combos in local / row_scale (T when packed)
     int *alive;
     const StepC *steps;  // [T][ncols_eff]
     unsigned flags;

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
     __syncthreads();
 
     const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
-    double *seq = store ? a.alpha_seq + b * T * (long long)n : nullptr;
+    double *seq = store ? a.alpha_seq + b * a.seq_stride : nullptr;
     const int nce = pb.ncols_eff;
     const bool table = pb.om_kind == BLG_OM_TABLE;
     LogProduct lp;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_fast1d_kernel(const PassArgs a) 
         }
         if (service) {
             lp.mul(norm);                                         // core.py:403
-            if (a.local) a.local[b * T + t] = norm * pb.lc_prod;  // core.py:404
+            if (a.local) a.local[b * a.row_stride + t] = norm * pb.lc_prod;  // core.py:404
         }
         double *tmp = cur;
         cur = nxt;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
     const bool acc = (a.flags & BLG_F_ACCUMULATE) != 0;
     const double wgt = acc ? exp(a.log_weight[b]) : 0.0;
     double *cur = s.buf0, *nxt = s.buf1;
-    double *seq = a.alpha_seq + b * T * (long long)n;
+    double *seq = a.alpha_seq + b * a.seq_stride;
     const bool staged = a.use_bulk != 0;
     double *S[2] = {sm + a.off_stage, sm + a.off_stage + a.Gp};  // alpha[t] staging ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
                 }
             }
         }
-        if (service && a.local) a.local[b * T + i] = fast_div(spu, sql * pb.lc_prod);  // 1/(sum(post/lik)*lc)  core.py:463
+        if (service && a.local) a.local[b * a.row_stride + i] = fast_div(spu, sql * pb.lc_prod);  // 1/(sum(post/lik)*lc)  core.py:463
         double *tmp = cur;
         cur = nxt;
         nxt = tmp;

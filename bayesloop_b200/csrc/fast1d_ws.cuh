@@ -119,7 +119,11 @@ __device__ __forceinline__ WsRoles ws_roles(int slot, int n) {
     return r;
 }
 
-// Control block of the ws kernels (doubles at a.ws_ctl): [0],[1] scale factor by step parity, [2] (as int) dead flag.
+// Control block of the ws kernels (doubles at a.ws_ctl): [0],[1] scale factor by step parity, [2] (as int) the step at
+// which the service warp found a zero norm (-1: alive).  The partial sums PP are double buffered by step parity: the
+// compute warps of step t+1 write while the service warp may still be reading those of step t.  All CTA-wide barriers
+// inside the role branches are NAMED barriers with an explicit thread count (bar.sync 1, NT): the two roles reach them
+// from different code paths, which __syncthreads() does not allow; both roles execute the same number of them.
 //
 // LAGGED SCALE (round 2).  The state is kept unnormalised; the only reason to scale it at all is to keep its magnitude
 // in range.  Round 1 applied the exact normaliser of the PREVIOUS step, which the service warp produces ~400 cycles
@@ -179,8 +183,8 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
     {
         const double *init = (a.flags & BLG_F_INIT_STATE) ? a.init_state + b * (long long)n : a.prior;
         for (int g = threadIdx.x; g < n; g += NT) store_mirrored(s.buf0, g, n, halo, init[g]);
-        for (int j = threadIdx.x; j < NCOMP; j += NT) PP[j] = 0.0;  // threads without cells never write their slot
-        if (threadIdx.x == 0) *deadFlag = 0;
+        for (int j = threadIdx.x; j < 2 * NCOMP; j += NT) PP[j] = 0.0;  // threads without cells never write their slots
+        if (threadIdx.x == 0) *deadFlag = -1;
     }
     __syncthreads();
     const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
@@ -225,17 +229,21 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
                     for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + (t + 1) * pitch + m * NCOMP);
                 }
                 store_cells_mirrored<M>(nxt, r.i0, n, halo, v);
-                PP[r.ct] = tree_sum<M>(v);
+                PP[(t & 1) * NCOMP + r.ct] = tree_sum<M>(v);
             }
             if (rawRows) fence_proxy_async();  // the new state is read by the service warp's bulk-async row store
             const long long p2 = prof ? clock64() : 0;
-            __syncthreads();  // new state and its partial sums are visible to everybody
+            named_sync(1, NT);  // new state and its partial sums are visible to everybody
             if (prof) {
                 cConv += p1 - p0;
                 cEpi += p2 - p1;
                 cBar += clock64() - p2;
             }
-            if (*deadFlag) break;  // set by the service warp after the barrier of an EARLIER step
+            {   // a zero norm found by the service warp behind the barrier of an EARLIER step ends the chain here; the
+                // flag carries the step so that both roles leave after the same number of barriers
+                const int ds = *deadFlag;
+                if (ds >= 0 && ds < t) break;
+            }
             double *tmp = cur;
             cur = nxt;
             nxt = tmp;
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
         }
     } else {
         // ------------------------------------------------------------------ service warp
-        double *seq = store ? a.alpha_seq + b * T * (long long)n : nullptr;
+        double *seq = store ? a.alpha_seq + b * a.seq_stride : nullptr;
         const bool vec = a.use_bulk != 0;  // rows are 16-byte aligned
         const bool raw = rawRows;
         const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
@@ -261,18 +269,18 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
         double sPrev = 1.0;            // s_{t-1}; the initial state enters as it is (core.py:363, :382)
         double kNow = 1.0, kNext = 1.0;  // k_t, k_{t+1}
         for (long long t = 0; t < T; ++t) {
-            __syncthreads();
-            if (dead) break;  // the compute warps have seen the flag behind this barrier
+            named_sync(1, NT);
+            if (dead) break;  // the compute warps see the flag behind this barrier
             double part = 0.0;
 #pragma unroll
-            for (int j = 0; j < NCOMP / 32; ++j) part += PP[j * 32 + r.lane];
+            for (int j = 0; j < NCOMP / 32; ++j) part += PP[(t & 1) * NCOMP + j * 32 + r.lane];
             const double st_sum = warp_sum(part);
             const double kAfter = lagged_scale(st_sum);  // k_{t+2}
             if (r.lane == 0) ctl[t & 1] = kAfter;
             const double norm = fast_div(st_sum, kNow * sPrev);  // core.py:385: evidence increment of step t
             if (!(st_sum > 0.0) || !(norm > 0.0) || isinf(st_sum)) {  // core.py:388-400
                 dead = true;
-                if (r.lane == 0) *deadFlag = 1;
+                if (r.lane == 0) *deadFlag = (int)t;
                 continue;  // one more barrier: the compute warps read the flag behind it
             }
             const double *st = (t & 1) ? s.buf0 : s.buf1;  // the buffer the compute warps just filled
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
             }
             if (r.lane == 0) {
                 lp.mul(norm);                                         // core.py:403
-                if (a.local) a.local[b * T + t] = norm * pb.lc_prod;  // core.py:404
+                if (a.local) a.local[b * a.row_stride + t] = norm * pb.lc_prod;  // core.py:404
                 if (raw) bulk_wait_read<0>();
             }
             sPrev = st_sum;
@@ -358,14 +366,14 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
     double *PP = sm + a.ws_part;  // [3][NCOMP]
     volatile double *ctl = sm + a.ws_ctl;
     volatile int *deadFlag = reinterpret_cast<volatile int *>(sm + a.ws_ctl + 2);
-    double *seq = a.alpha_seq + b * T * (long long)n;
+    double *seq = a.alpha_seq + b * a.seq_stride;
     double *const S0 = sm + a.off_stage;  // alpha[t] ring: 2 slots of Gp doubles; overwritten in place by alpha*beta
     const int Gp = a.Gp;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
     const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
-    for (int j = threadIdx.x; j < 3 * NCOMP; j += NT) PP[j] = 0.0;  // threads without cells never write their slots
+    for (int j = threadIdx.x; j < 6 * NCOMP; j += NT) PP[j] = 0.0;  // threads without cells never write their slots
     if (threadIdx.x == 0) {
-        *deadFlag = 0;
+        *deadFlag = -1;
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         fence_proxy_async();
@@ -432,13 +440,17 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
                     for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + (i - 1) * pitch + m * NCOMP);
                 }
                 store_cells_mirrored<M>(nxt, r.i0, n, halo, st);
-                PP[r.ct] = spu0 + spu1;
-                PP[NCOMP + r.ct] = tree_sum<M>(st);  // sum of the new state (magnitude control only)
-                PP[2 * NCOMP + r.ct] = sql0 + sql1;
+                double *pp = PP + sb * 3 * NCOMP;
+                pp[r.ct] = spu0 + spu1;
+                pp[NCOMP + r.ct] = tree_sum<M>(st);  // sum of the new state (magnitude control only)
+                pp[2 * NCOMP + r.ct] = sql0 + sql1;
             }
             if (rawRows) fence_proxy_async();  // alpha * beta in the ring slot is read by the bulk-async row store
-            __syncthreads();
-            if (*deadFlag) break;
+            named_sync(1, NT);
+            {
+                const int ds = *deadFlag;  // step at which the service warp found a zero norm (rows run downwards)
+                if (ds >= 0 && ds > i) break;
+            }
             double *tmp = cur;
             cur = nxt;
             nxt = tmp;
@@ -454,14 +466,15 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
         long long i = T - 1;
         for (; i >= 0; --i) {
             const int sb = (int)(i & 1);
-            __syncthreads();
+            named_sync(1, NT);
             if (dead) break;
             double spu = 0.0, sstate = 0.0, sql = 0.0;
+            const double *pp = PP + sb * 3 * NCOMP;
 #pragma unroll
             for (int j = 0; j < NCOMP / 32; ++j) {
-                spu += PP[j * 32 + r.lane];
-                sstate += PP[NCOMP + j * 32 + r.lane];
-                sql += PP[2 * NCOMP + j * 32 + r.lane];
+                spu += pp[j * 32 + r.lane];
+                sstate += pp[NCOMP + j * 32 + r.lane];
+                sql += pp[2 * NCOMP + j * 32 + r.lane];
             }
             spu = warp_sum(spu);
             sstate = warp_sum(sstate);
@@ -469,7 +482,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
             if (r.lane == 0) ctl[i & 1] = lagged_scale(sstate);  // used by step i-2
             if (!(spu > 0.0) || !(sstate > 0.0) || isinf(sstate)) {  // core.py:440-452
                 dead = true;
-                if (r.lane == 0) *deadFlag = 1;
+                if (r.lane == 0) *deadFlag = (int)i;
                 continue;
             }
             const double inv = fast_rcp(spu);  // posterior = alpha*beta / sum(alpha*beta)   core.py:439-441
@@ -479,7 +492,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
                 if (r.lane == 0) {
                     fence_proxy_async();
                     bulk_store(row, P, rowBytes);
-                    a.row_scale[b * T + i] = inv;
+                    a.row_scale[b * a.row_stride + i] = inv;
                 }
             } else {
                 for (int j = 2 * r.lane; j < n; j += 64) {
@@ -491,7 +504,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
             }
             __syncwarp();
             if (r.lane == 0) {
-                if (a.local) a.local[b * T + i] = fast_div(spu, sql * pb.lc_prod);  // 1/(sum(post/lik)*lc)  core.py:463
+                if (a.local) a.local[b * a.row_stride + i] = fast_div(spu, sql * pb.lc_prod);  // 1/(sum(post/lik)*lc)  core.py:463
                 if (raw) bulk_wait_read<0>();
                 if (i >= 2) {  // the slot is free again: prefetch alpha[i-2] into it
                     fence_proxy_async();

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) online2d_finish_kernel(const PassArgs a, 
         double logE = dead ? -INFINITY : log(norm);
         if (!dead && !(a.flags & BLG_F_INIT_STATE)) logE += log(a.pb.lc_prod);
         a.logE[h] = logE;
-        if (a.local && !dead) a.local[h * a.T] = norm * a.pb.lc_prod;
+        if (a.local && !dead) a.local[h * a.row_stride] = norm * a.pb.lc_prod;
         if (a.alive) a.alive[h] = dead ? 0 : 1;
     }
     if (dead) return;  // like the persistent kernels: the state of a dead hypothesis is left untouched

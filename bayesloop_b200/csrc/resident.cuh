@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_resident_kernel(const PassArgs a
 
     const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
     const bool bulk = store && a.use_bulk;
-    double *seq = store ? a.alpha_seq + b * T * (long long)G : nullptr;
+    double *seq = store ? a.alpha_seq + b * a.seq_stride : nullptr;
     const int nce = pb.ncols_eff;
     double logE = 0.0;
     bool dead = false;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(NT, MINB) fwd_resident_kernel(const PassArgs a
         }
         if (threadIdx.x == 0) {
             logE += log(norm);                                          // core.py:403
-            if (a.local) a.local[b * T + t] = norm * pb.lc_prod;        // core.py:404
+            if (a.local) a.local[b * a.row_stride + t] = norm * pb.lc_prod;        // core.py:404
         }
         if (bulk) fence_proxy_async();
         __syncthreads();
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
     const double beta0 = 1.0 / (double)G;  // core.py:424-425
     for (int g = threadIdx.x; g < G; g += blockDim.x) r.cur[g] = beta0;
 
-    double *seq = a.alpha_seq + b * T * (long long)G;
+    double *seq = a.alpha_seq + b * a.seq_stride;
     const bool staged = !STREAM && a.off_stage >= 0 && a.use_bulk;
     double *S[2] = {sm + (staged ? a.off_stage : 0), sm + (staged ? a.off_stage + a.Gp : 0)};
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
         q = block_sum(q, r.rs);
         if (staged && threadIdx.x == 0 && i >= 2)  // everybody is past the barrier: S[sb] is free again
             bulk_load(S[sb], seq + (i - 2) * (long long)G, rowBytes, &bars[sb]);
-        if (threadIdx.x == 0 && a.local) a.local[b * T + i] = 1.0 / (q * pb.lc_prod);
+        if (threadIdx.x == 0 && a.local) a.local[b * a.row_stride + i] = 1.0 / (q * pb.lc_prod);
         apply_ops<STREAM>(a, r, i, true, b, sm);
         part = 0.0;
         for (int g = threadIdx.x; g < G; g += blockDim.x) part += r.cur[g];

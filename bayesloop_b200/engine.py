@@ -57,7 +57,7 @@ class _Inputs(ctypes.Structure):
 class _Outputs(ctypes.Structure):
     _fields_ = [('log_evidence', ctypes.c_void_p), ('local_evidence', ctypes.c_void_p), ('alive', ctypes.c_void_p),
                 ('alpha_seq', ctypes.c_void_p), ('avg', ctypes.c_void_p), ('final_state', ctypes.c_void_p),
-                ('row_scale', ctypes.c_void_p)]
+                ('row_scale', ctypes.c_void_p), ('seq_stride', ctypes.c_int64), ('row_stride', ctypes.c_int64)]
 
 
 def _ptr(t):
@@ -337,7 +337,7 @@ class Engine:
         return plan
 
     def _io(self, T, B, data, prior, reset_base, lik_table, program, lo, log_weight, init_state, log_evidence,
-            local_evidence, alive, alpha_seq, avg, final_state, row_scale=None):
+            local_evidence, alive, alpha_seq, avg, final_state, row_scale=None, seq_stride=0, row_stride=0):
         i = _Inputs()
         i.T, i.B = int(T), int(B)
         i.data, i.prior, i.reset_base, i.lik_table = _ptr(data), _ptr(prior), _ptr(reset_base), _ptr(lik_table)
@@ -347,13 +347,15 @@ class Engine:
         o.log_evidence, o.local_evidence, o.alive = _ptr(log_evidence), _ptr(local_evidence), _ptr(alive)
         o.alpha_seq, o.avg, o.final_state = _ptr(alpha_seq), _ptr(avg), _ptr(final_state)
         o.row_scale = _ptr(row_scale)
+        o.seq_stride, o.row_stride = int(seq_stride or 0), int(row_stride or 0)
         return i, o
 
     def run(self, which, plan, flags, **kw):
         """which in {'forward', 'backward', 'accumulate'}; keyword arguments are the fields of blg_inputs/outputs
         (tensors on self.device) plus `program` and `lo` (first combo row of the program used by this call)."""
         names = ('T', 'B', 'data', 'prior', 'reset_base', 'lik_table', 'program', 'lo', 'log_weight', 'init_state',
-                 'log_evidence', 'local_evidence', 'alive', 'alpha_seq', 'avg', 'final_state', 'row_scale')
+                 'log_evidence', 'local_evidence', 'alive', 'alpha_seq', 'avg', 'final_state', 'row_scale', 'seq_stride',
+                 'row_stride')
         args = [kw.get(k) for k in names]
         args[7] = args[7] or 0
         i, o = self._io(*args)

@@ -138,6 +138,11 @@ typedef struct blg_outputs {
     double *avg;            /* device [T][G]  backward with ACCUMULATE: running weighted sum (caller zero-fills)     */
     double *final_state;    /* device [B][G]  only with BLG_F_SAVE_STATE                                            */
     double *row_scale;      /* device [B][T]  backward with BLG_F_RAW_POSTERIOR: written; accumulate: read if non-NULL */
+    int64_t seq_stride;     /* doubles between the sequences of consecutive combos in alpha_seq; 0 = T * G (packed).       */
+    int64_t row_stride;     /* doubles between the rows of consecutive combos in local_evidence and row_scale; 0 = T.     */
+                            /* Strides let a call work on a WINDOW of time steps of sequences that live in a larger       */
+                            /* [B][T_full][G] buffer (pointer offset + T of the window): the sub-calls of the change-point */
+                            /* prefix sharing run in place this way.                                */
 } blg_outputs;
 
 typedef struct blg_plan blg_plan;
