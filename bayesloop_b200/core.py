@@ -52,6 +52,42 @@ def _free_symbols(rv):
     return []
 
 
+def _share_structure(ops, T):
+    """Change-point prefix sharing: can the combinations of a lowered sweep be arranged as
+    (groups) x (change-points), where the members of a group differ ONLY in the step at which ONE reset operator fires?
+    A ChangePoint erases the history (transitionModels.py:300-312): before it every member of the group filters
+    exactly like the change-point-free model, after it the backward message is that model's as well.
+    Returns None or dict(k, group[B], cidx[B], cvals[nC], nG, nC)."""
+    resets = [k for k, op in enumerate(ops) if op['kind'] == _tm.OP_RESET]
+    if len(resets) != 1 or T < 3:
+        return None
+    k = resets[0]
+    win = np.asarray(ops[k]['window'], dtype=np.int64)
+    B = len(win)
+    if B < 4:
+        return None
+    c = win[:, 0]
+    if not (np.all(win[:, 1] == c + 1) and np.all(win[:, 2] == c + 1) and np.all(win[:, 3] == c + 2)):
+        return None  # not a single-step reset (e.g. Independent: every step)
+    if c.min() < 0 or c.max() > T - 2:
+        return None
+    keys = []
+    for j, op in enumerate(ops):
+        w = np.asarray(op['window'])
+        if j != k and not np.all(w == w[0]):
+            return None  # another operator's activity depends on the combination (Serial models): not shareable
+        keys.append(np.asarray(op['param'], dtype=float).reshape(B, 1))
+        keys.append(np.asarray(op['radius'], dtype=float).reshape(B, 1))
+    _, group = np.unique(np.hstack(keys), axis=0, return_inverse=True)
+    group = np.asarray(group).reshape(-1)
+    cvals, cidx = np.unique(c, return_inverse=True)
+    cidx = np.asarray(cidx).reshape(-1)
+    nG, nC = int(group.max()) + 1, len(cvals)
+    if nC < 2 or nG * nC != B or len(np.unique(group * nC + cidx)) != B:
+        return None  # not a full (groups x change-points) rectangle
+    return dict(k=k, group=group, cidx=cidx, cvals=cvals.astype(np.int64), nG=nG, nC=nC)
+
+
 class _Session:
     """Device-side constants of one fit: plan, data series, prior, likelihood table."""
 
@@ -682,6 +718,7 @@ class HyperStudy(Study):
         self.localEvidenceList = []
         self.sweepStats = {}
         self.maxWave = None
+        self.shareChangepoints = True  # change-point prefix sharing where the sweep allows it (_share_structure)
         if not silent:
             print('  --> Hyper-study')
 
@@ -772,13 +809,32 @@ class HyperStudy(Study):
         ses = _Session(self, eng)
         T, G = ses.T, ses.G
         Ball = len(self.hyperGridValues)
-        rows = dist.shard_rows(Ball)
+        hyperAll = np.asarray(self.hyperGridValues, dtype=float).reshape(Ball, -1)
+        ctx = self._lower(hyperAll, self.formattedTimestamps)
+        share = None
+        if self.shareChangepoints and not (forwardOnly or evidenceOnly):
+            share = _share_structure(ctx.ops, T)
+        if share is None:
+            rows = dist.shard_rows(Ball)
+        else:
+            # groups (or, with fewer groups than ranks, change-points) dealt round-robin over the ranks; this rank's
+            # combinations are laid out change-point-major: slot = (change-point index) * nG + (group index)
+            rank, size = dist.world()
+            gsel = np.arange(rank, share['nG'], size) if share['nG'] >= size else np.arange(share['nG'])
+            csel = np.arange(share['nC']) if share['nG'] >= size else np.arange(rank, share['nC'], size)
+            where = np.full((share['nC'], share['nG']), -1, dtype=np.int64)
+            where[share['cidx'], share['group']] = np.arange(Ball)
+            rows = where[np.ix_(csel, gsel)].reshape(-1)
+            share = dict(share, nG=len(gsel), nC=len(csel), cvals=share['cvals'][csel])
+            if share['nG'] == 0 or share['nC'] < 2:
+                share, rows = None, dist.shard_rows(Ball)
         B = len(rows)
-        hyper = np.asarray(self.hyperGridValues, dtype=float).reshape(Ball, -1)[rows]
         hp = np.asarray(self.flatHyperPriorValues, dtype=float)[rows]
-        ctx = self._lower(hyper, self.formattedTimestamps)
+        ops = [dict(op, param=np.asarray(op['param'])[rows], radius=np.asarray(op['radius'])[rows],
+                    window=np.asarray(op['window'])[rows]) for op in ctx.ops]
+        ctx.ops = ops
         sw = dict(eng=eng, ses=ses, T=T, G=G, Ball=Ball, rows=rows, B=B, hp=hp, ops=ctx.ops,
-                  forwardOnly=forwardOnly, evidenceOnly=evidenceOnly)
+                  forwardOnly=forwardOnly, evidenceOnly=evidenceOnly, share=share)
         sw['program'] = _engine.Program(eng, ctx.ops, B)
         sw['resetBase'] = ses.reset_base() if ctx.usesReset else None
         sw['logE'], sw['local'] = eng.zeros(max(B, 1)), eng.zeros((max(B, 1), T))
@@ -791,9 +847,16 @@ class HyperStudy(Study):
             sw['avg'] = eng.zeros((T, G))
             sw['means'] = eng.empty((len(self.gridSize), T))
             budget = int(eng.free_bytes() * 0.85) - T * G * 8
+            if share is not None:
+                self._prepareShared(sw, budget)
+                budget -= 2 * share['nG'] * T * G * 8
             sw['wave'] = int(max(1, min(B, budget // max(1, T * G * 8))))
+            if share is not None:  # whole change-points per wave
+                sw['wave'] = max(1, sw['wave'] // share['nG']) * share['nG']
             if self.maxWave:  # user cap on the combinations fitted concurrently (memory, or to exercise the wave logic)
                 sw['wave'] = int(max(1, min(sw['wave'], self.maxWave)))
+                if share is not None:
+                    sw['wave'] = max(1, sw['wave'] // share['nG']) * share['nG']
             sw['buf'] = eng.empty((sw['wave'], T, G)) if B > 0 else None
             sw['rowScale'] = eng.empty((sw['wave'], T)) if (B > 0 and not forwardOnly) else None
         with np.errstate(divide='ignore'):
@@ -803,12 +866,138 @@ class HyperStudy(Study):
         sw['weights'] = eng.zeros(max(B, 1))          # log-weights of the combos relative to it
         return sw
 
+    def _prepareShared(self, sw, budget):
+        """Programs and buffers of the change-point prefix sharing (see _share_structure / _executeSharedSweep)."""
+        eng, T, G, share = sw['eng'], sw['T'], sw['G'], sw['share']
+        nG, k = share['nG'], share['k']
+        if 2 * nG * T * G * 8 > budget // 2:  # the two shared sequences must leave room for the combinations
+            sw['share'] = None
+            return
+        first = np.arange(nG)  # slots of the first change-point: one representative per group
+
+        def variant(window):
+            out = []
+            for j, op in enumerate(sw['ops']):
+                w = np.asarray(op['window'])[first].copy()
+                if j == k:
+                    w[:] = window
+                out.append(dict(op, param=np.asarray(op['param'])[first], radius=np.asarray(op['radius'])[first], window=w))
+            return _engine.Program(eng, out, nG)
+
+        sw['progShared'] = variant([0, 0, 0, 0])  # the reset never fires: the change-point-free model of each group
+        sw['progSuffix'] = variant([0, 1, 1, 2])  # reset after the FIRST step of a window that starts at the change-point
+        sw['alphaS'], sw['ratio'] = eng.empty((nG, T, G)), eng.empty((nG, T, G))
+        sw['localS'], sw['scratchLocal'] = eng.zeros((nG, T)), eng.zeros((nG, T))
+        sw['rowScaleS'], sw['logES'] = eng.empty((nG, T)), eng.zeros(nG)
+        sw['aliveS'] = eng.zeros(nG, dtype=torch.int32)
+        sw['saveRow'], sw['scratchLogE'] = eng.empty((nG, G)), eng.zeros(nG)
+        sw['cOfSlot'] = eng.to_device(np.repeat(share['cvals'], nG))
+        sw['gOfSlot'] = eng.to_device(np.tile(np.arange(nG), share['nC']))
+
+    def _executeSharedSweep(self, sw):
+        """Sweep with change-point prefix sharing.  Combination (g, c) = group g with its
+        reset after step c.  Because the reset erases the history (transitionModels.py:300-312):
+          * filtering rows t <= c and the evidence increments up to c are those of the group's change-point-free run;
+          * filtering rows t > c come from a forward pass over the steps c .. T-1 only (its first row is discarded);
+          * the backward message of rows t > c is the change-point-free run's, so smoothed row = alpha(g, c)[t] * beta(g)[t]
+            (blg_share_apply; `ratio` below holds beta up to a factor per row);
+          * smoothed rows t <= c come from a backward pass over the rows 0 .. c+1 only (shared alpha rows copied in;
+            the reset fires when row c+1 is processed, so what that row held is irrelevant; it is restored after).
+        Executed cell updates per combination: (T - c) + (c + 2) instead of 2 T.  All passes are the ordinary kernels
+        on WINDOWS of the sequences (seq_stride / row_stride of include/blgrid.h)."""
+        from . import distributed as dist
+        eng, ses, T, G, B = sw['eng'], sw['ses'], sw['T'], sw['G'], sw['B']
+        share = sw['share']
+        nG, nC, cvals = share['nG'], share['nC'], [int(c) for c in share['cvals']]
+        plan, buf, avg, local, alive, logE = ses.plan, sw['buf'], sw['avg'], sw['local'], sw['alive'], sw['logE']
+        rowScale, shift, weights = sw['rowScale'], sw['shift'], sw['weights']
+        alphaS, ratio, localS = sw['alphaS'], sw['ratio'], sw['localS']
+        lc = float(np.prod(self.latticeConstant))
+        avg.zero_()
+        shift.fill_(-math.inf)
+        base = dict(prior=ses.prior, reset_base=sw['resetBase'])
+        executed = 0
+
+        def window(t0):  # inputs of a call whose first row is time step t0
+            return dict(data=ses.data[t0:], lik_table=None if ses.likTable is None else ses.likTable[t0:])
+
+        # 1. the change-point-free run of every group: filtering rows, and the backward message itself -- the smoother
+        #    run on a sequence of ONES returns alpha * beta = beta row by row (the beta recursion, core.py:467-470, does
+        #    not depend on alpha), exact where a quotient posterior / alpha would lose the cells whose alpha underflows
+        shared = dict(T=T, B=nG, program=sw['progShared'], log_evidence=sw['logES'], alive=sw['aliveS'], **base, **window(0))
+        eng.run('forward', plan, _engine.F_RAW_ALPHA, alpha_seq=alphaS, local_evidence=localS, **shared)
+        ratio.fill_(1.0)
+        eng.run('backward', plan, _engine.F_RAW_POSTERIOR, alpha_seq=ratio, local_evidence=sw['scratchLocal'],
+                row_scale=sw['rowScaleS'], **shared)
+        executed += 2 * nG * T
+        if not bool((sw['aliveS'] == 1).all()):
+            return None  # a group whose change-point-free run dies: let the plain sweep sort out who survives
+        prefix = torch.cumsum(torch.log(localS / lc), dim=1)  # [nG][T]: log-evidence of the steps 0 .. t
+
+        perWave = sw['wave'] // nG  # change-points per wave
+        steps = torch.arange(T, device=local.device)
+        waves = 0
+        for ci0 in range(0, nC, perWave):
+            ci1 = min(nC, ci0 + perWave)
+            s0, nb = ci0 * nG, (ci1 - ci0) * nG
+            waves += 1
+            # 2a. filtering rows after the change-point: forward pass over the steps c .. T-1
+            for ci in range(ci0, ci1):
+                c, j = cvals[ci], (ci - ci0) * nG
+                eng.run('forward', plan, _engine.F_RAW_ALPHA, T=T - c, B=nG, program=sw['progSuffix'],
+                        alpha_seq=buf[j:j + nG, c:], seq_stride=T * G, local_evidence=local[s0 + j:s0 + j + nG, c:],
+                        row_stride=T, log_evidence=sw['scratchLogE'], alive=alive[s0 + j:s0 + j + nG], **base, **window(c))
+                executed += nG * (T - c)
+            # evidence of every combination: shared steps 0 .. c, own steps c+1 .. T-1 (core.py:403, :417)
+            cs, gs = sw['cOfSlot'][s0:s0 + nb], sw['gOfSlot'][s0:s0 + nb]
+            own = torch.where(steps[None, :] > cs[:, None], torch.log(local[s0:s0 + nb] / lc), torch.zeros((), device=local.device,
+                                                                                                       dtype=local.dtype))
+            le = prefix[gs, cs] + own.sum(dim=1) + math.log(lc)
+            logE[s0:s0 + nb] = torch.where(alive[s0:s0 + nb] == 1, le, torch.full_like(le, -math.inf))
+            eng.wave_weights(plan, logE[s0:s0 + nb], sw['logHpDev'][s0:s0 + nb], nb, shift, avg, T * G, weights[s0:s0 + nb])
+            # 2b. smoothed rows
+            for ci in range(ci0, ci1):
+                c, j = cvals[ci], (ci - ci0) * nG
+                sl = slice(s0 + j, s0 + j + nG)
+                eng.share_apply(plan, ratio[:, c + 1:], T * G, T=T - c - 1, B=nG, alpha_seq=buf[j:j + nG, c + 1:],
+                                seq_stride=T * G, row_scale=rowScale[j:j + nG, c + 1:], local_evidence=local[sl, c + 1:],
+                                row_stride=T, alive=alive[sl], log_evidence=logE[sl], program=sw['progSuffix'], **base,
+                                **window(c + 1))
+                sw['saveRow'].copy_(buf[j:j + nG, c + 1])
+                keepScale, keepLocal = rowScale[j:j + nG, c + 1].clone(), local[sl, c + 1].clone()
+                buf[j:j + nG, :c + 2] = alphaS[:, :c + 2]
+                eng.run('backward', plan, _engine.F_RAW_POSTERIOR, T=c + 2, B=nG, program=sw['program'], lo=s0 + j,
+                        alpha_seq=buf[j:j + nG], seq_stride=T * G, row_scale=rowScale[j:j + nG], row_stride=T,
+                        local_evidence=local[sl], log_evidence=logE[sl], alive=alive[sl], **base, **window(0))
+                buf[j:j + nG, c + 1] = sw['saveRow']
+                rowScale[j:j + nG, c + 1] = keepScale
+                local[sl, c + 1] = keepLocal
+                executed += nG * (c + 2)
+            eng.run('accumulate', plan, 0, T=T, B=nb, program=sw['program'], lo=s0, log_weight=weights[s0:s0 + nb], avg=avg,
+                    alpha_seq=buf, row_scale=rowScale, alive=alive[s0:s0 + nb], log_evidence=logE[s0:s0 + nb], **base,
+                    **window(0))
+        part = sw['part']
+        part.zero_()
+        eng.mix(plan, local, sw['hpDev'], B, T, part)
+        localEv = dist.reduce_sum(eng, part)
+        dist.rebase_and_reduce(eng, plan, avg, shift, T * G)
+        eng.finalize(plan, avg, T, sw['means'], _engine.F_NORMALIZE_ROWS)
+        logEAll, aliveAll = dist.gather_rows(eng, logE[:B], alive[:B], sw['Ball'], rows=sw['rows'])
+        logEAll = np.where(aliveAll == 1, logEAll, -np.inf)
+        self.sweepStats = dict(waves=waves, wave=sw['wave'], rows=sw['rows'], launches=eng.launch_count(), shared=True,
+                               executed_updates=int(executed) * G, nominal_updates=2 * int(B) * T * G)
+        return eng, logEAll, aliveAll, localEv, avg, sw['means']
+
     def _executeSweep(self, sw):
         """Kernels of one sweep (inputs already resident).  Per wave: forward pass; the wave's averaging weights and
         the re-base of the running sum are computed ON THE DEVICE from the evidences (blg_wave_weights: the streaming
         form of np.logaddexp, core.py:1358-1366); backward pass; weighted accumulation.  Everything is enqueued on
         one stream without a host round trip: the host reads the evidences once, after the cross-rank merge."""
         from . import distributed as dist
+        if sw.get('share') is not None:
+            out = self._executeSharedSweep(sw)
+            if out is not None:
+                return out
         eng, ses, T, G, B = sw['eng'], sw['ses'], sw['T'], sw['G'], sw['B']
         evidenceOnly, forwardOnly = sw['evidenceOnly'], sw['forwardOnly']
         logE, local, alive, avg, buf, wave = sw['logE'], sw['local'], sw['alive'], sw['avg'], sw['buf'], sw['wave']
@@ -848,9 +1037,11 @@ class HyperStudy(Study):
         if not evidenceOnly:
             dist.rebase_and_reduce(eng, ses.plan, avg, shift, T * G)
             eng.finalize(ses.plan, avg, T, sw['means'], _engine.F_NORMALIZE_ROWS)
-        logEAll, aliveAll = dist.gather_rows(eng, logE[:B], alive[:B], sw['Ball'])
+        logEAll, aliveAll = dist.gather_rows(eng, logE[:B], alive[:B], sw['Ball'], rows=sw['rows'])
         logEAll = np.where(aliveAll == 1, logEAll, -np.inf)
-        self.sweepStats = dict(waves=waves, wave=wave, rows=sw['rows'], launches=eng.launch_count())
+        self.sweepStats = dict(waves=waves, wave=wave, rows=sw['rows'], launches=eng.launch_count(), shared=False,
+                               executed_updates=(1 if (evidenceOnly or forwardOnly) else 2) * int(B) * T * G,
+                               nominal_updates=(1 if (evidenceOnly or forwardOnly) else 2) * int(B) * T * G)
         return eng, logEAll, aliveAll, localEv, avg, sw['means']
 
     def _sweep(self, forwardOnly, evidenceOnly):

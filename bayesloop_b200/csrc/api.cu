@@ -1061,6 +1061,42 @@ int blg_time_average(blg_plan *pl, const double *seq, int64_t T, double *out, vo
     return 0;
 }
 
+int blg_share_apply(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, const double *ratio, int64_t ratio_stride,
+                    void *stream) {
+    if (!pl || !in || !out || !ratio || !out->alpha_seq || !out->row_scale) return fail("null argument");
+    if (in->B <= 0 || in->T <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevProblem &d = pl->dev;
+    const long long rowBytes = (long long)d.G;
+    const long long seqStride = out->seq_stride > 0 ? out->seq_stride : in->T * rowBytes;
+    const long long rowStride = out->row_stride > 0 ? out->row_stride : in->T;
+    const long long ratioStride = ratio_stride > 0 ? ratio_stride : in->T * rowBytes;
+    const double *lik = in->lik_table;
+    if (d.om_kind != BLG_OM_TABLE) {  // likelihood rows of the window: the plan's shared table
+        if (prep_steps(pl, in, st)) return -1;
+        const long long count = in->T * rowBytes;
+        if (count > pl->lik_cap) {
+            if (pl->d_lik) CUDA_TRY(cudaFree(pl->d_lik));
+            pl->d_lik = nullptr;
+            pl->lik_cap = 0;
+            CUDA_TRY(cudaMalloc(&pl->d_lik, (size_t)count * sizeof(double)));
+            pl->lik_cap = count;
+        }
+        lik_table_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d, pl->d_steps, in->T, pl->d_lik);
+        ++g_launches;
+        lik = pl->d_lik;
+    } else if (!lik) {
+        return fail("lik_table required for BLG_OM_TABLE");
+    }
+    if (in->B * in->T > 2147483647LL) return fail("too many rows for one blg_share_apply call");
+    share_apply_kernel<<<(unsigned)(in->B * in->T), 256, 0, st>>>(out->alpha_seq, seqStride, ratio, ratioStride, lik, in->T,
+                                                                  d.G, d.lc_prod, out->row_scale, out->local_evidence,
+                                                                  rowStride, out->alive);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int blg_mix(blg_plan *pl, const double *state, const double *weight, int64_t K, int64_t n, double *out, void *stream) {
     if (!pl || !state || !weight || !out) return fail("null argument");
     if (n <= 0) return 0;

@@ -215,6 +215,39 @@ __global__ void time_average_kernel(const double *__restrict__ seq, long long T,
     out[g] = s / (double)T;
 }
 
+// One CTA per (combo, row): u = alpha * ratio in place, row_scale = 1 / sum(u), local evidence from sum(u / lik).
+// `lik`: likelihood table of the window ([T][G]); grid = B * T blocks.
+__global__ void __launch_bounds__(256) share_apply_kernel(double *__restrict__ seq, long long seqStride,
+                                                          const double *__restrict__ ratio, long long ratioStride,
+                                                          const double *__restrict__ lik, long long T, int G, double lcProd,
+                                                          double *__restrict__ rowScale, double *__restrict__ local,
+                                                          long long rowStride, int *__restrict__ alive) {
+    __shared__ double scratch[6 * kMaxWarps];
+    RedScratch rs;
+    rs.buf = scratch;
+    rs.phase = 0;
+    const long long b = blockIdx.x / T, t = blockIdx.x - b * T;
+    if (alive && alive[b] != 1) return;
+    double *row = seq + b * seqStride + t * G;
+    const double *rr = ratio + b * ratioStride + t * G, *lk = lik + t * (long long)G;
+    double s = 0.0, q = 0.0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const double u = row[g] * __ldcs(rr + g);
+        row[g] = u;
+        s += u;
+        q += fast_div(u, __ldg(lk + g));  // core.py:463 (0 / 0 = NaN like the reference: alpha carries the likelihood)
+    }
+    block_sum2(s, q, rs);
+    if (threadIdx.x == 0) {
+        if (!(s > 0.0)) {  // core.py:440-452
+            if (alive) alive[b] = -1;
+            return;
+        }
+        rowScale[b * rowStride + t] = 1.0 / s;
+        if (local) local[b * rowStride + t] = s / (q * lcProd);
+    }
+}
+
 __global__ void fill_kernel(double *__restrict__ x, long long count, double value) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < count) x[e] = value;

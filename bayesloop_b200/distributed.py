@@ -38,25 +38,38 @@ def shard_rows(B, rank=None, size=None):
     return np.arange(rank, int(B), size)
 
 
-def gather_rows(eng, logE, alive, Ball):
+def gather_rows(eng, logE, alive, Ball, rows=None):
     """All-gather the per-rank log-evidence / alive flags (device tensors) and return them on the host in hyper-grid
-    row order.  One collective of a packed [2 x width] block per rank and one device -> host copy."""
+    row order.  `rows`: global row index of each of this rank's entries (default: the round-robin deal).  One
+    collective of a packed [3 x width] block per rank and one device -> host copy."""
     rank, size = world()
+    if rows is None:
+        rows = shard_rows(Ball, rank, size)
+    rows = np.asarray(rows, dtype=np.int64)
     if size == 1:
-        return np.asarray(eng.to_host(logE), dtype=float), np.asarray(eng.to_host(alive)).astype(np.int64)
+        outE, outA = np.empty(int(Ball)), np.zeros(int(Ball), dtype=np.int64)
+        outE[rows] = np.asarray(eng.to_host(logE), dtype=float)
+        outA[rows] = np.asarray(eng.to_host(alive)).astype(np.int64)
+        return outE, outA
     width = -(-int(Ball) // size)
-    send = torch.full((2, width), float('nan'), dtype=torch.float64, device=logE.device)
+    counts = torch.tensor([len(rows)], dtype=torch.int64, device=logE.device)
+    most = counts.clone()
+    td.all_reduce(most, op=td.ReduceOp.MAX)
+    width = max(width, int(most.item()))
+    send = torch.full((3, width), -1.0, dtype=torch.float64, device=logE.device)
     send[0, :logE.shape[0]] = logE
     send[1, :alive.shape[0]] = alive.to(torch.float64)
+    send[2, :len(rows)] = torch.from_numpy(rows.astype(np.float64)).to(logE.device)
     recv = [torch.empty_like(send) for _ in range(size)]
     td.all_gather(recv, send)
     host = eng.to_host(torch.stack(recv))
-    outE, outA = np.empty(int(Ball)), np.empty(int(Ball))
+    outE, outA = np.empty(int(Ball)), np.zeros(int(Ball), dtype=np.int64)
     for r in range(size):
-        rows = shard_rows(Ball, r, size)
-        outE[rows] = host[r, 0, :len(rows)]
-        outA[rows] = host[r, 1, :len(rows)]
-    return outE, outA.astype(np.int64)
+        idx = host[r, 2]
+        keep = idx >= 0
+        outE[idx[keep].astype(np.int64)] = host[r, 0][keep]
+        outA[idx[keep].astype(np.int64)] = host[r, 1][keep].astype(np.int64)
+    return outE, outA
 
 
 def gather_dealt(eng, mine, total):

@@ -213,6 +213,8 @@ class Engine:
                                        ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
         L.blg_rebase.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p]
+        L.blg_share_apply.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Inputs), ctypes.POINTER(_Outputs), ctypes.c_void_p,
+                                      ctypes.c_int64, ctypes.c_void_p]
         L.blg_marginal.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
                                    ctypes.c_void_p]
         L.blg_time_average.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
@@ -379,6 +381,17 @@ class Engine:
     def rebase(self, plan, x, count, shift_from, shift_to):
         self._check(self.lib.blg_rebase(plan.handle, _ptr(x), int(count), _ptr(shift_from), _ptr(shift_to),
                                         self.stream()))
+
+    def share_apply(self, plan, ratio, ratio_stride, **kw):
+        """blg_share_apply: keyword arguments as in run() (T, B, data / lik_table, program, alpha_seq window, strides ...)."""
+        names = ('T', 'B', 'data', 'prior', 'reset_base', 'lik_table', 'program', 'lo', 'log_weight', 'init_state',
+                 'log_evidence', 'local_evidence', 'alive', 'alpha_seq', 'avg', 'final_state', 'row_scale', 'seq_stride',
+                 'row_stride')
+        args = [kw.get(k) for k in names]
+        args[7] = args[7] or 0
+        i, o = self._io(*args)
+        self._check(self.lib.blg_share_apply(plan.handle, ctypes.byref(i), ctypes.byref(o), _ptr(ratio), int(ratio_stride),
+                                             self.stream()))
 
     def marginal(self, plan, seq, T, axis, out):
         self._check(self.lib.blg_marginal(plan.handle, _ptr(seq), int(T), int(axis), _ptr(out), self.stream()))

@@ -204,6 +204,21 @@ int blg_finalize(blg_plan *plan, double *seq, int64_t T, double *means, uint32_t
 int blg_marginal(blg_plan *plan, const double *seq, int64_t T, int32_t axis, double *out, void *stream);
 int blg_time_average(blg_plan *plan, const double *seq, int64_t T, double *out, void *stream);
 
+/* Change-point prefix sharing.  A ChangePoint erases the history at tChange
+ * (transitionModels.py:300-312), so all combinations that differ only in tChange share the filtering recursion BEFORE
+ * it and the backward message AFTER it: both come from ONE change-point-free run per group of combinations.
+ * The message itself needs no new pass: blg_backward on a sequence of ONES returns alpha * beta = beta row by row.
+ *   blg_share_apply   rows t < in->T of the B combos of the call (a WINDOW of their sequences: pointer offsets +
+ *                     seq_stride / row_stride): u = alpha_seq[b][t][g] * ratio[b][t][g] in place -- the smoothed
+ *                     row up to its scale, which goes to row_scale[b][t] = 1 / sum(u) -- and
+ *                     local_evidence[b][t] = 1 / (sum(post / lik) * prod(lattice))  (core.py:436-441, :463).
+ *                     ratio: device, the backward message (any positive factor per row) of B sequences
+ *                     `ratio_stride` doubles apart, same window.  in->data (or
+ *                     in->lik_table) point at the first time step of the window.  Combos with alive[b] != 1 are
+ *                     skipped; a zero row sum sets alive[b] = -1 (core.py:440-452). */
+int blg_share_apply(blg_plan *plan, const blg_inputs *in, const blg_outputs *out, const double *ratio,
+                    int64_t ratio_stride, void *stream);
+
 /* Weighted sum of K rows: out[j] = sum_k weight[k] * state[k][j], j < n.  Used for the OnlineStudy
  * marginalisations (core.py:2195-2197, :2212; n = G) and for the averaged local evidence of a HyperStudy
  * (core.py:1410; K = B, n = T).  state device [K][n], weight device [K], out device [n]. */

