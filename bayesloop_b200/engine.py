@@ -266,8 +266,12 @@ class Engine:
         return 0
 
     def free_bytes(self):
+        """HBM available to a sweep: what the driver reports free PLUS what torch's caching allocator holds without
+        using it (the buffers of the previous fit live there: without them a second fit in the same process would size
+        its waves for a nearly full device)."""
         if self.device.type == 'cuda':
-            return torch.cuda.mem_get_info(self.device)[0]
+            cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+            return torch.cuda.mem_get_info(self.device)[0] + max(0, cached)
         return 8 << 30
 
     def stream(self):

@@ -15,7 +15,8 @@ import bayesloop_b200 as bl  # noqa: E402
 from bayesloop_b200 import engine as E  # noqa: E402
 
 fits = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-counts = bench.synthetic_counts(10000)
+import argparse  # noqa: E402
+wl = bench.C2(argparse.Namespace(T=10000, grid=1000, sigma_max=0.2, combos=512), 1)
 acc = collections.OrderedDict()
 
 
@@ -33,7 +34,8 @@ def wrap(cls, name):
     setattr(cls, name, timed)
 
 
-for n in ('to_host', 'to_device', 'empty', 'zeros', 'plan', 'run', 'finalize', 'mix', 'scale', 'free_bytes'):
+for n in ('to_host', 'to_device', 'empty', 'zeros', 'full', 'plan', 'run', 'finalize', 'mix', 'scale', 'free_bytes', 'wave_weights',
+          'rebase'):
     wrap(E.Engine, n)
 wrap(E.Plan, '__del__')
 wrap(bl.HyperStudy, '_prepareSweep')
@@ -46,7 +48,7 @@ for it in range(fits):
     acc.clear()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    S2 = bench.build_study(bl, counts, 512, 1000, 0.2)
+    S2 = wl.study(bl)
     t1 = time.perf_counter()
     S2.fit(silent=True)
     t2 = time.perf_counter()
