@@ -872,7 +872,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
                     fprintf(stderr, "[blgrid] online2d: %lld hypotheses x %d x %d tiles, %zu B smem/CTA, radii <= %d / %d\n",
                             (long long)in->B, L.tilesY, L.tilesX, L.smemBytes, r0, r1);
                 const int rc = online2d_run(a, L, pl->d_o2, st);
-                g_launches += 3;
+                g_launches += 4;
                 g_last_kernel = "online2d";
                 if (rc != 0) return fail("online2d launch failed: %s", cudaGetErrorString((cudaError_t)rc));
                 return 0;

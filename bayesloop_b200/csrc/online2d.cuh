@@ -240,32 +240,45 @@ __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const Pa
     }
 }
 
-// grid (chunks, H): every block re-derives the sums of its hypothesis from the per-tile partials in the same order.
-__global__ void __launch_bounds__(256) online2d_finish_kernel(const PassArgs a, const O2Geom geo) {
-    const long long h = blockIdx.y;
+// K8a: one warp per hypothesis adds the per-tile partial sums in a fixed order (lane-strided, then a shuffle tree:
+// deterministic), writes the evidence increment / alive flag and leaves 1 / sum(u) for K8b (0: dead, state untouched).
+// (Round 1 let every block of the streaming kernel re-derive the sums with a serial loop over the tiles: ~10 us of
+// dependent L2 loads in front of every block made K8 latency bound, 335 us for 1.07 GB.)
+__global__ void __launch_bounds__(128) online2d_sums_kernel(const PassArgs a, const O2Geom geo, double *__restrict__ inv) {
+    const long long h = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (h >= a.B) return;
     const int tiles = geo.tilesY * geo.tilesX;
     const double *p = geo.partial + (size_t)h * tiles * 2;
     double s2 = 0.0, s1 = 0.0;
-    for (int k = 0; k < tiles; ++k) {
+    for (int k = lane; k < tiles; k += 32) {
         s2 += p[2 * k];
         s1 += p[2 * k + 1];
     }
+    s2 = warp_sum(s2);
+    s1 = warp_sum(s1);
+    if (lane != 0) return;
     const double norm = s2 / s1;
     const bool dead = !(norm > 0.0) || !(s2 > 0.0) || isinf(norm);  // core.py:2171 has no guard; the engine reports it
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double logE = dead ? -INFINITY : log(norm);
-        if (!dead && !(a.flags & BLG_F_INIT_STATE)) logE += log(a.pb.lc_prod);
-        a.logE[h] = logE;
-        if (a.local && !dead) a.local[h * a.row_stride] = norm * a.pb.lc_prod;
-        if (a.alive) a.alive[h] = dead ? 0 : 1;
-    }
-    if (dead) return;  // like the persistent kernels: the state of a dead hypothesis is left untouched
-    const double inv = 1.0 / s2;
+    double logE = dead ? -INFINITY : log(norm);
+    if (!dead && !(a.flags & BLG_F_INIT_STATE)) logE += log(a.pb.lc_prod);
+    a.logE[h] = logE;
+    if (a.local && !dead) a.local[h * a.row_stride] = norm * a.pb.lc_prod;
+    if (a.alive) a.alive[h] = dead ? 0 : 1;
+    inv[h] = dead ? 0.0 : 1.0 / s2;
+}
+
+// K8b, grid (chunks, H): final_state = scratch / sum(u), streaming; like the persistent kernels the state of a dead
+// hypothesis is left untouched.
+__global__ void __launch_bounds__(256) online2d_finish_kernel(const PassArgs a, const O2Geom geo, const double *__restrict__ inv) {
+    const long long h = blockIdx.y;
+    const double f = __ldg(inv + h);
+    if (!(f > 0.0)) return;
     const long long G = a.pb.G;
     const double *src = geo.scratch + h * G;
     double *dst = a.final_state + h * G;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < G; g += (long long)gridDim.x * blockDim.x)
-        dst[g] = src[g] * inv;
+        dst[g] = __ldcs(src + g) * f;
 }
 
 }  // namespace blg

@@ -21,8 +21,8 @@ bool online2d_plan(int n0, int n1, int r0max, int r1max, bool async, O2Launch *L
 }
 
 size_t online2d_scratch_doubles(long long B, long long G, const O2Launch &L) {
-    // unnormalised cells [B][G] | per-tile partial sums [B][tiles][2] | descriptors [B] | queue counter
-    return (size_t)B * G + (size_t)B * L.tilesY * L.tilesX * 2 + (size_t)B * (sizeof(O2Hyp) / sizeof(double)) + 2;
+    // unnormalised cells [B][G] | per-tile partial sums [B][tiles][2] | descriptors [B] | queue counter | 1 / sum [B]
+    return (size_t)B * G + (size_t)B * L.tilesY * L.tilesX * 2 + (size_t)B * (sizeof(O2Hyp) / sizeof(double)) + 2 + (size_t)B;
 }
 
 int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStream_t st) {
@@ -55,7 +55,9 @@ int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStre
     long long chunks = (a.pb.G + 256LL * 8 - 1) / (256LL * 8);  // 8 cells per thread
     if (chunks < 1) chunks = 1;
     if (chunks > 1024) chunks = 1024;
-    online2d_finish_kernel<<<dim3((unsigned)chunks, (unsigned)a.B), 256, 0, st>>>(a, geo);
+    double *inv = reinterpret_cast<double *>(geo.counter) + 1;  // [B] behind the queue counter
+    online2d_sums_kernel<<<(unsigned)((a.B * 32 + 127) / 128), 128, 0, st>>>(a, geo, inv);
+    online2d_finish_kernel<<<dim3((unsigned)chunks, (unsigned)a.B), 256, 0, st>>>(a, geo, inv);
     return (int)cudaGetLastError();
 }
 
