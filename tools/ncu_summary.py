@@ -1,9 +1,9 @@
 """Turn the ncu artefacts of tools/profile_round.sh (gpurun_out/<tag>_*) into the tracked summaries under profiles/:
 
-    python tools/ncu_summary.py r1h
+    python tools/ncu_summary.py r2m
 
   profiles/<tag>_launches_bench.csv   per-kernel launch list of the bench command (count, total / mean duration, share)
-  profiles/r1_ncu_summary.json        key `ncu --set full` metrics per kernel (read by bench.py for roofline.traffic)
+  profiles/<tag>_ncu_summary.json     key `ncu --set full` metrics per kernel (read by bench.py for roofline.traffic)
 """
 import csv
 import json
@@ -77,7 +77,7 @@ def launches(tag):
     dst = os.path.join(PROF, tag + '_launches_bench.csv')
     with open(dst, 'w') as f:
         f.write('# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 2 --warmup 3 '
-                '--no-cpu-baseline (cold-cache, serialised launches: shares matter, not absolutes)\n')
+                '--no-cpu-baseline --no-extra (cold-cache, serialised launches: shares matter, not absolutes)\n')
         f.write('kernel,launches,total_ms,mean_ms,share\n')
         for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('%s,%d,%.3f,%.3f,%.4f\n' % (name, n, ms, ms / n, ms / total))
@@ -85,16 +85,19 @@ def launches(tag):
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else 'r1h'
+    tag = sys.argv[1] if len(sys.argv) > 1 else 'r2'
     os.makedirs(PROF, exist_ok=True)
     print(launches(tag))
     summary = {'tag': tag, 'command': 'tools/profile_round.sh ' + tag,
                'note': 'ncu --set full --clock-control none; bytes and durations are per launch'}
-    c2 = raw_page(os.path.join(OUT, tag + '_c2_ws.ncu-rep'))
-    summary['bench_c2'] = {e['kernel'].split('<')[0].replace('blg::', ''): e for e in c2}
-    c3 = raw_page(os.path.join(OUT, tag + '_c3_cluster.ncu-rep'))
-    summary['c3_sample_256x256_T200_B36'] = {e['kernel'].split('<')[0].replace('blg::', ''): e for e in c3}
-    dst = os.path.join(PROF, 'r1_ncu_summary.json')
+    for key, rep, what in (('bench_c2', '_c2_ws', 'C2 at the bench shape (512 combos, T = 10000)'),
+                           ('bench_c3', '_c3_cluster', 'C3 grid and hyper-ranges, 8 x 8 of the hyper-grid, 200 steps'),
+                           ('bench_c5', '_c5_online', 'C5 at the full shape (512 x 512, 256 hypotheses), one step')):
+        path = os.path.join(OUT, tag + rep + '.ncu-rep')
+        if os.path.exists(path):
+            summary[key] = {e['kernel'].split('<')[0].replace('blg::', ''): e for e in raw_page(path)}
+            summary[key + '_workload'] = what
+    dst = os.path.join(PROF, tag + '_ncu_summary.json')
     with open(dst, 'w') as f:
         json.dump(summary, f, indent=1, sort_keys=True)
     print(dst)
