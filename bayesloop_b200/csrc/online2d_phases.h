@@ -84,9 +84,24 @@ BLG_HD void conv_valid(const double *src, double *dst, const double *W, int taps
             acc[m] = 0.0;
         }
         idx += M;
-        for (int j0 = 0; j0 < taps; j0 += M) {
+        // whole chunks of M taps, then the remaining taps behind uniform guards (a zero-padded last chunk would spend
+        // up to M - 1 useless FMAs per output: 25 % of the work at the radii of BASELINE.json configs[4])
+        const int full = taps / M, rem = taps - full * M;
+        int j0 = 0;
+        for (int c = 0; c < full; ++c, j0 += M) {
 #pragma unroll
             for (int u = 0; u < M; ++u) {
+                const double wt = W[j0 + u];
+#pragma unroll
+                for (int m = 0; m < M; ++m) acc[m] = fma(wt, win[(u + m) % M], acc[m]);
+                const int q = idx < last ? idx : last;
+                win[u] = line[q * elemStride];
+                ++idx;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < M - 1; ++u) {
+            if (u < rem) {
                 const double wt = W[j0 + u];
 #pragma unroll
                 for (int m = 0; m < M; ++m) acc[m] = fma(wt, win[(u + m) % M], acc[m]);
