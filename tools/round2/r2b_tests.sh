@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU call: full parity suite (kernel families recorded), smoke, headline bench.
-#   gpurun --timeout 900 -- 'bash tools/r2b_tests.sh'
+#   gpurun --timeout 900 -- 'bash tools/round2/r2b_tests.sh'
 mkdir -p gpurun_out
 rm -f gpurun_out/kernel_families.json
 BLG_RECORD_FAMILIES=gpurun_out/kernel_families.json timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/r2b_pytest_gpu.log 2>&1

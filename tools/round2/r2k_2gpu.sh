@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU call: NCCL parity test + the bench under torchrun (all configs through the extras)
-#   gpurun --gpus 2 --timeout 1500 -- 'bash tools/r2k_2gpu.sh'
+#   gpurun --gpus 2 --timeout 1500 -- 'bash tools/round2/r2k_2gpu.sh'
 mkdir -p gpurun_out
 nvidia-smi -L
 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/r2k_multi.log 2>&1
