@@ -892,6 +892,7 @@ class HyperStudy(Study):
         sw['aliveS'] = eng.zeros(nG, dtype=torch.int32)
         sw['saveRow'], sw['scratchLogE'] = eng.empty((nG, G)), eng.zeros(nG)
         sw['cOfSlot'] = eng.to_device(np.repeat(share['cvals'], nG))
+        sw['cpDev'] = eng.to_device(np.asarray(share['cvals'], dtype=np.int32))
         sw['gOfSlot'] = eng.to_device(np.tile(np.arange(nG), share['nC']))
 
     def _executeSharedSweep(self, sw):
@@ -901,8 +902,9 @@ class HyperStudy(Study):
           * filtering rows t > c come from a forward pass over the steps c .. T-1 only (its first row is discarded);
           * the backward message of rows t > c is the change-point-free run's, so smoothed row = alpha(g, c)[t] * beta(g)[t]
             (blg_share_apply; `ratio` below holds beta up to a factor per row);
-          * smoothed rows t <= c come from a backward pass over the rows 0 .. c+1 only (shared alpha rows copied in;
-            the reset fires when row c+1 is processed, so what that row held is irrelevant; it is restored after).
+          * smoothed rows t <= c come from a backward pass over the rows 0 .. c+1 only, reading the group's shared
+            filtering rows out of place (alpha_src); the reset fires when row c+1 is processed, so what that row holds is
+            irrelevant; the combination's own row c+1 is restored after.
         Executed cell updates per combination: (T - c) + (c + 2) instead of 2 T.  All passes are the ordinary kernels
         on WINDOWS of the sequences (seq_stride / row_stride of include/blgrid.h)."""
         from . import distributed as dist
@@ -955,18 +957,19 @@ class HyperStudy(Study):
             le = prefix[gs, cs] + own.sum(dim=1) + math.log(lc)
             logE[s0:s0 + nb] = torch.where(alive[s0:s0 + nb] == 1, le, torch.full_like(le, -math.inf))
             eng.wave_weights(plan, logE[s0:s0 + nb], sw['logHpDev'][s0:s0 + nb], nb, shift, avg, T * G, weights[s0:s0 + nb])
-            # 2b. smoothed rows
+            # 2b. smoothed rows after the change-point, all change-points of the wave in one call: own filtering rows x
+            #     the group's backward message (read once per group and row)
+            eng.share_apply(plan, ratio, T * G, nG, sw['cpDev'][ci0:ci1], T=T, B=nb, alpha_seq=buf, seq_stride=T * G,
+                            row_scale=rowScale, local_evidence=local[s0:s0 + nb], row_stride=T, alive=alive[s0:s0 + nb],
+                            log_evidence=logE[s0:s0 + nb], program=sw['progSuffix'], **base, **window(0))
+            #     ... and before it: backward pass over the rows 0 .. c+1
             for ci in range(ci0, ci1):
                 c, j = cvals[ci], (ci - ci0) * nG
                 sl = slice(s0 + j, s0 + j + nG)
-                eng.share_apply(plan, ratio[:, c + 1:], T * G, T=T - c - 1, B=nG, alpha_seq=buf[j:j + nG, c + 1:],
-                                seq_stride=T * G, row_scale=rowScale[j:j + nG, c + 1:], local_evidence=local[sl, c + 1:],
-                                row_stride=T, alive=alive[sl], log_evidence=logE[sl], program=sw['progSuffix'], **base,
-                                **window(c + 1))
                 sw['saveRow'].copy_(buf[j:j + nG, c + 1])
                 keepScale, keepLocal = rowScale[j:j + nG, c + 1].clone(), local[sl, c + 1].clone()
-                buf[j:j + nG, :c + 2] = alphaS[:, :c + 2]
                 eng.run('backward', plan, _engine.F_RAW_POSTERIOR, T=c + 2, B=nG, program=sw['program'], lo=s0 + j,
+                        alpha_src=alphaS, src_stride=T * G,  # out of place: the group's filtering rows are read in place
                         alpha_seq=buf[j:j + nG], seq_stride=T * G, row_scale=rowScale[j:j + nG], row_stride=T,
                         local_evidence=local[sl], log_evidence=logE[sl], alive=alive[sl], **base, **window(0))
                 buf[j:j + nG, c + 1] = sw['saveRow']

@@ -792,6 +792,8 @@ int fill_args(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint32
     a.row_scale = (flags & BLG_F_RAW_POSTERIOR) ? out->row_scale : nullptr;
     a.seq_stride = out->seq_stride > 0 ? out->seq_stride : in->T * (long long)pl->dev.G;
     a.row_stride = out->row_stride > 0 ? out->row_stride : in->T;
+    a.alpha_src = in->alpha_src;
+    a.src_stride = in->src_stride > 0 ? in->src_stride : in->T * (long long)pl->dev.G;
     if (a.seq_stride < in->T * (long long)pl->dev.G || a.row_stride < in->T) return fail("seq_stride / row_stride smaller than one sequence");
     a.steps = pl->d_steps;
     a.flags = flags;
@@ -917,7 +919,7 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     }
     Layout lay;
     const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && a.seq_stride % 2 == 0 &&
-                             !pl->opt.no_bulk;
+                             (!in->alpha_src || ((uintptr_t)in->alpha_src % 16 == 0 && a.src_stride % 2 == 0)) && !pl->opt.no_bulk;
     {
         int wsM = 0;
         if (alignedRows && !acc && fast1d_ws_layout(pl, in->prog, true, a, lay, wsM)) {
@@ -1062,19 +1064,20 @@ int blg_time_average(blg_plan *pl, const double *seq, int64_t T, double *out, vo
 }
 
 int blg_share_apply(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, const double *ratio, int64_t ratio_stride,
-                    void *stream) {
-    if (!pl || !in || !out || !ratio || !out->alpha_seq || !out->row_scale) return fail("null argument");
+                    int64_t n_groups, const int32_t *cp_step, void *stream) {
+    if (!pl || !in || !out || !ratio || !cp_step || !out->alpha_seq || !out->row_scale) return fail("null argument");
     if (in->B <= 0 || in->T <= 0) return 0;
+    if (n_groups <= 0 || in->B % n_groups != 0) return fail("B must be n_cp * n_groups");
     cudaStream_t st = (cudaStream_t)stream;
     const DevProblem &d = pl->dev;
-    const long long rowBytes = (long long)d.G;
-    const long long seqStride = out->seq_stride > 0 ? out->seq_stride : in->T * rowBytes;
+    const long long row = (long long)d.G;
+    const long long seqStride = out->seq_stride > 0 ? out->seq_stride : in->T * row;
     const long long rowStride = out->row_stride > 0 ? out->row_stride : in->T;
-    const long long ratioStride = ratio_stride > 0 ? ratio_stride : in->T * rowBytes;
+    const long long ratioStride = ratio_stride > 0 ? ratio_stride : in->T * row;
     const double *lik = in->lik_table;
-    if (d.om_kind != BLG_OM_TABLE) {  // likelihood rows of the window: the plan's shared table
+    if (d.om_kind != BLG_OM_TABLE) {  // likelihood rows of the series: the plan's shared table
         if (prep_steps(pl, in, st)) return -1;
-        const long long count = in->T * rowBytes;
+        const long long count = in->T * row;
         if (count > pl->lik_cap) {
             if (pl->d_lik) CUDA_TRY(cudaFree(pl->d_lik));
             pl->d_lik = nullptr;
@@ -1088,11 +1091,15 @@ int blg_share_apply(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, 
     } else if (!lik) {
         return fail("lik_table required for BLG_OM_TABLE");
     }
-    if (in->B * in->T > 2147483647LL) return fail("too many rows for one blg_share_apply call");
-    share_apply_kernel<<<(unsigned)(in->B * in->T), 256, 0, st>>>(out->alpha_seq, seqStride, ratio, ratioStride, lik, in->T,
-                                                                  d.G, d.lc_prod, out->row_scale, out->local_evidence,
-                                                                  rowStride, out->alive);
-    ++g_launches;
+    if (n_groups * in->T > 2147483647LL) return fail("too many rows for one blg_share_apply call");
+    const int nCp = (int)(in->B / n_groups);
+    for (int k0 = 0; k0 < nCp; k0 += kShareK) {
+        const int nK = nCp - k0 < kShareK ? nCp - k0 : kShareK;
+        share_apply_kernel<<<(unsigned)(n_groups * in->T), 256, 0, st>>>(out->alpha_seq, seqStride, ratio, ratioStride, lik, in->T,
+                                                                         d.G, d.lc_prod, out->row_scale, out->local_evidence,
+                                                                         rowStride, out->alive, n_groups, cp_step, k0, nK);
+        ++g_launches;
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

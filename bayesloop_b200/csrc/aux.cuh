@@ -215,37 +215,64 @@ __global__ void time_average_kernel(const double *__restrict__ seq, long long T,
     out[g] = s / (double)T;
 }
 
-// One CTA per (combo, row): u = alpha * ratio in place, row_scale = 1 / sum(u), local evidence from sum(u / lik).
-// `lik`: likelihood table of the window ([T][G]); grid = B * T blocks.
+// Change-point prefix sharing: one CTA per (group g, row t).  The backward message ratio[g][t][.] and the likelihood
+// row lik[t][.] are read once; for every change-point k of the call with cp[k] < t the row of combo k * nG + g becomes
+// u = alpha * ratio in place, row_scale = 1 / sum(u), local evidence from sum(u / lik).  Up to kShareK change-points
+// per launch (per-thread partial sums live in registers).
+constexpr int kShareK = 12;
 __global__ void __launch_bounds__(256) share_apply_kernel(double *__restrict__ seq, long long seqStride,
                                                           const double *__restrict__ ratio, long long ratioStride,
                                                           const double *__restrict__ lik, long long T, int G, double lcProd,
                                                           double *__restrict__ rowScale, double *__restrict__ local,
-                                                          long long rowStride, int *__restrict__ alive) {
+                                                          long long rowStride, int *__restrict__ alive, long long nG,
+                                                          const int *__restrict__ cp, int k0, int nK) {
     __shared__ double scratch[6 * kMaxWarps];
     RedScratch rs;
     rs.buf = scratch;
     rs.phase = 0;
-    const long long b = blockIdx.x / T, t = blockIdx.x - b * T;
-    if (alive && alive[b] != 1) return;
-    double *row = seq + b * seqStride + t * G;
-    const double *rr = ratio + b * ratioStride + t * G, *lk = lik + t * (long long)G;
-    double s = 0.0, q = 0.0;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        const double u = row[g] * __ldcs(rr + g);
-        row[g] = u;
-        s += u;
-        q += fast_div(u, __ldg(lk + g));  // core.py:463 (0 / 0 = NaN like the reference: alpha carries the likelihood)
+    const long long g = blockIdx.x / T, t = blockIdx.x - g * T;
+    bool on[kShareK];
+    int any = 0;
+#pragma unroll
+    for (int k = 0; k < kShareK; ++k) {
+        on[k] = k < nK && __ldg(cp + k0 + k) < t && (!alive || alive[(k0 + k) * nG + g] == 1);
+        any |= on[k];
     }
-    block_sum2(s, q, rs);
-    if (threadIdx.x == 0) {
-        if (!(s > 0.0)) {  // core.py:440-452
-            if (alive) alive[b] = -1;
-            return;
+    if (!any) return;
+    const double *rr = ratio + g * ratioStride + t * G, *lk = lik + t * (long long)G;
+    double s[kShareK], q[kShareK];
+#pragma unroll
+    for (int k = 0; k < kShareK; ++k) s[k] = q[k] = 0.0;
+    for (int cell = threadIdx.x; cell < G; cell += blockDim.x) {
+        const double r = __ldcs(rr + cell), l = __ldg(lk + cell);
+        const bool small = l < 1e-290;  // core.py:463 without a division per change-point (see fast_div_pos)
+        const double rl = fast_rcp(small ? l * 0x1p600 : l);
+#pragma unroll
+        for (int k = 0; k < kShareK; ++k)
+            if (on[k]) {
+                double *row = seq + ((k0 + k) * nG + g) * seqStride + t * G;
+                const double u = row[cell] * r;
+                row[cell] = u;
+                s[k] += u;
+                const double qv = u * rl;
+                q[k] += small ? qv * 0x1p600 : qv;
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < kShareK; ++k)
+        if (on[k]) {  // uniform over the block
+            double sk = s[k], qk = q[k];
+            block_sum2(sk, qk, rs);
+            if (threadIdx.x == 0) {
+                const long long b = (k0 + k) * nG + g;
+                if (!(sk > 0.0)) {  // core.py:440-452
+                    if (alive) alive[b] = -1;
+                } else {
+                    rowScale[b * rowStride + t] = 1.0 / sk;
+                    if (local) local[b * rowStride + t] = sk / (qk * lcProd);
+                }
+            }
         }
-        rowScale[b * rowStride + t] = 1.0 / s;
-        if (local) local[b * rowStride + t] = s / (q * lcProd);
-    }
 }
 
 __global__ void fill_kernel(double *__restrict__ x, long long count, double value) {

@@ -839,13 +839,15 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
     uint64_t *bar = reinterpret_cast<uint64_t *>(c2_misc(a) + kC2Mbar);
     uint32_t phase = 0;
     double *seq = a.alpha_seq + b * a.seq_stride + (size_t)s.r0 * n1;
+    // filtering rows (out-of-place smoothing when alpha_src is given)
+    const double *src = a.alpha_src ? a.alpha_src + b * a.src_stride + (size_t)s.r0 * n1 : seq;
     const uint32_t bandBytes = (uint32_t)(s.cnt * sizeof(double));
     {
         const int total = a.c2_x_doubles;
         for (int e = threadIdx.x; e < total; e += kC2Threads) c2_X(a)[e] = 0.0;
         c2_init_barriers(a, bar);
         __syncthreads();
-        if (threadIdx.x == 0) bulk_load(c2_S(a), seq + (T - 1) * (long long)G, bandBytes, bar);
+        if (threadIdx.x == 0) bulk_load(c2_S(a), src + (T - 1) * (long long)G, bandBytes, bar);
     }
     c2_arrive();
     c2_wait();
@@ -970,7 +972,7 @@ __global__ void __launch_bounds__(NT, 1) bwd_cluster2d_kernel(const PassArgs a) 
         auto issueAlpha = [&]() {
             if (alphaPending && threadIdx.x == 0) {
                 bulk_wait_read<0>();
-                bulk_load(c2_S(a), seq + (i - 1) * (long long)G, bandBytes, bar);
+                bulk_load(c2_S(a), src + (i - 1) * (long long)G, bandBytes, bar);
                 if (pb.om_kind == BLG_OM_TABLE && i >= 2)
                     c2_prefetch_l2(a.lik_table + (i - 2) * (long long)G + (size_t)s.r0 * n1, bandBytes);
             }

@@ -63,6 +63,8 @@ struct PassArgs {
     double *logE, *local, *alpha_seq, *avg, *final_state;
     double *row_scale;   // [B][T] normalising factor of each smoothed row (BLG_F_RAW_POSTERIOR) or NULL
     long long seq_stride;  // doubles between consecutive combos in alpha_seq (T * G when packed)
+    const double *alpha_src;  // backward: filtering rows are read here (out-of-place smoothing) or NULL = alpha_seq
+    long long src_stride;
     long long row_stride;  // doubles between consecutive combos in local / row_scale (T when packed)
     int *alive;
     const StepC *steps;  // [T][ncols_eff]

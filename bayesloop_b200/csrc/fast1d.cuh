@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
     const double wgt = acc ? exp(a.log_weight[b]) : 0.0;
     double *cur = s.buf0, *nxt = s.buf1;
     double *seq = a.alpha_seq + b * a.seq_stride;
+    const double *src = a.alpha_src ? a.alpha_src + b * a.src_stride : seq;  // filtering rows (out-of-place smoothing)
     const bool staged = a.use_bulk != 0;
     double *S[2] = {sm + a.off_stage, sm + a.off_stage + a.Gp};  // alpha[t] staging ring
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
@@ -350,8 +351,8 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
         }
         __syncthreads();
         if (service) {
-            bulk_load(S[(T - 1) & 1], seq + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) & 1]);
-            if (T >= 2) bulk_load(S[(T - 2) & 1], seq + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) & 1]);
+            bulk_load(S[(T - 1) & 1], src + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) & 1]);
+            if (T >= 2) bulk_load(S[(T - 2) & 1], src + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) & 1]);
         }
     }
     const int nce = pb.ncols_eff;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
             ph[sb] ^= 1u;
             A = S[sb];
         } else {
-            A = seq + i * (long long)n;
+            A = src + i * (long long)n;
         }
         double pu[M];
         double spu = 0.0, sbeta = 0.0, sql = 0.0;
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_fast1d_kernel(const PassArgs a) 
             break;
         }
         if (staged && service && i >= 2)  // everybody is past the barrier: the staging slot is free again
-            bulk_load(S[sb], seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
+            bulk_load(S[sb], src + (i - 2) * (long long)n, rowBytes, &bars[sb]);
         const double inv = fast_rcp(spu);  // posterior = alpha*beta / sum(alpha*beta)   core.py:439-441
         kb = fast_rcp(sbeta);              // core.py:470, applied lazily (beta only enters scale-free expressions)
         if (owner) {

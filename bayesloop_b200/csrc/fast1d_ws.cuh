@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
     volatile double *ctl = sm + a.ws_ctl;
     volatile int *deadFlag = reinterpret_cast<volatile int *>(sm + a.ws_ctl + 2);
     double *seq = a.alpha_seq + b * a.seq_stride;
+    const double *src = a.alpha_src ? a.alpha_src + b * a.src_stride : seq;  // filtering rows (out-of-place smoothing)
     double *const S0 = sm + a.off_stage;  // alpha[t] ring: 2 slots of Gp doubles; overwritten in place by alpha*beta
     const int Gp = a.Gp;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
@@ -459,8 +460,8 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
         // ------------------------------------------------------------------ service warp
         const bool raw = rawRows;
         if (r.lane == 0) {
-            bulk_load(S0 + ((T - 1) & 1) * Gp, seq + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) & 1]);
-            if (T >= 2) bulk_load(S0 + ((T - 2) & 1) * Gp, seq + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) & 1]);
+            bulk_load(S0 + ((T - 1) & 1) * Gp, src + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) & 1]);
+            if (T >= 2) bulk_load(S0 + ((T - 2) & 1) * Gp, src + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) & 1]);
         }
         bool dead = false;
         long long i = T - 1;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
                 if (raw) bulk_wait_read<0>();
                 if (i >= 2) {  // the slot is free again: prefetch alpha[i-2] into it
                     fence_proxy_async();
-                    bulk_load(P, seq + (i - 2) * (long long)n, rowBytes, &bars[sb]);
+                    bulk_load(P, src + (i - 2) * (long long)n, rowBytes, &bars[sb]);
                 }
             }
         }

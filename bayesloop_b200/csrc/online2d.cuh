@@ -43,11 +43,13 @@ struct O2Geom {
     double *partial;     // [H][tiles][2]: sum(v * lik), sum(v)
     O2Hyp *hyp;          // [H]
     int *counter;        // work queue: next unit (zeroed before the launch)
+    int chunk;           // tiles per unit: kO2Chunk, halved while the launch has fewer than ~6 units per CTA (few hypotheses
+                         // per GPU under sharding: the tail of the queue would leave SMs idle)
     int pipelined;       // 1: the output tile has a shared-memory buffer of its own, so the next tile's loads overlap
                          //    the axis-1 pass and the epilogue; 0 (radii too wide for that): it reuses `in`
 };
 
-constexpr int kO2Chunk = 8;  // tiles of one hypothesis handed out per queue access (weights are built once per unit)
+constexpr int kO2Chunk = 8;  // most tiles of one hypothesis handed out per queue access (weights are built once per unit)
 
 struct O2Lik {
     const PassArgs &a;
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const Pa
     __shared__ int unitSh;
     const DevProblem &pb = a.pb;
     const int tiles = geo.tilesY * geo.tilesX;
-    const int chunksPerHyp = (tiles + kO2Chunk - 1) / kO2Chunk;
+    const int chunk = geo.chunk;
+    const int chunksPerHyp = (tiles + chunk - 1) / chunk;
     const long long units = a.B * (long long)chunksPerHyp;
     double *in = sm;
     double *mid = in + (size_t)geo.inRowsMax * geo.P;
@@ -146,8 +149,8 @@ __global__ void __launch_bounds__(o2::kThreads, 1) online2d_tile_kernel(const Pa
         const long long u = unitSh;
         if (u >= units) break;
         const long long h = u / chunksPerHyp;
-        const int first = (int)(u - h * chunksPerHyp) * kO2Chunk;
-        const int count = min(kO2Chunk, tiles - first);
+        const int first = (int)(u - h * chunksPerHyp) * chunk;
+        const int count = min(chunk, tiles - first);
         const O2Hyp hp = geo.hyp[h];
         const bool clamp = hp.clamp != 0;
         const double *src = a.init_state + h * (long long)pb.G;

@@ -47,7 +47,10 @@ int online2d_run(const PassArgs &a, const O2Launch &L, double *scratch, cudaStre
     e = cudaFuncSetAttribute(tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smemBytes);
     if (e != cudaSuccess) return (int)e;
     const long long tiles = (long long)L.tilesY * L.tilesX;
-    const long long units = a.B * ((tiles + kO2Chunk - 1) / kO2Chunk);
+    int chunk = kO2Chunk;
+    while (chunk > 1 && a.B * ((tiles + chunk - 1) / chunk) < 6LL * a.num_sms) chunk /= 2;
+    geo.chunk = chunk;
+    const long long units = a.B * ((tiles + chunk - 1) / chunk);
     const long long grid = units < a.num_sms ? units : a.num_sms;
     tile<<<(unsigned)grid, o2::kThreads, L.smemBytes, st>>>(a, geo);
     e = cudaGetLastError();

@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
     for (int g = threadIdx.x; g < G; g += blockDim.x) r.cur[g] = beta0;
 
     double *seq = a.alpha_seq + b * a.seq_stride;
+    const double *src = a.alpha_src ? a.alpha_src + b * a.src_stride : seq;  // filtering rows (out-of-place smoothing)
     const bool staged = !STREAM && a.off_stage >= 0 && a.use_bulk;
     double *S[2] = {sm + (staged ? a.off_stage : 0), sm + (staged ? a.off_stage + a.Gp : 0)};
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
@@ -371,8 +372,8 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            bulk_load(S[(T - 1) & 1], seq + (T - 1) * (long long)G, rowBytes, &bars[(T - 1) & 1]);
-            if (T >= 2) bulk_load(S[(T - 2) & 1], seq + (T - 2) * (long long)G, rowBytes, &bars[(T - 2) & 1]);
+            bulk_load(S[(T - 1) & 1], src + (T - 1) * (long long)G, rowBytes, &bars[(T - 1) & 1]);
+            if (T >= 2) bulk_load(S[(T - 2) & 1], src + (T - 2) * (long long)G, rowBytes, &bars[(T - 2) & 1]);
         }
     } else {
         __syncthreads();
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
             ph[sb] ^= 1u;
             A = S[sb];
         } else {
-            A = seq + i * (long long)G;
+            A = src + i * (long long)G;
         }
         // posterior ~ alpha * beta                                  core.py:436-441
         double part = 0.0;
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(NT, MINB) bwd_resident_kernel(const PassArgs a
         }
         q = block_sum(q, r.rs);
         if (staged && threadIdx.x == 0 && i >= 2)  // everybody is past the barrier: S[sb] is free again
-            bulk_load(S[sb], seq + (i - 2) * (long long)G, rowBytes, &bars[sb]);
+            bulk_load(S[sb], src + (i - 2) * (long long)G, rowBytes, &bars[sb]);
         if (threadIdx.x == 0 && a.local) a.local[b * a.row_stride + i] = 1.0 / (q * pb.lc_prod);
         apply_ops<STREAM>(a, r, i, true, b, sm);
         part = 0.0;

@@ -51,7 +51,8 @@ class _Program(ctypes.Structure):
 class _Inputs(ctypes.Structure):
     _fields_ = [('T', ctypes.c_int64), ('B', ctypes.c_int64), ('data', ctypes.c_void_p), ('prior', ctypes.c_void_p),
                 ('reset_base', ctypes.c_void_p), ('lik_table', ctypes.c_void_p), ('prog', _Program),
-                ('log_weight', ctypes.c_void_p), ('init_state', ctypes.c_void_p)]
+                ('log_weight', ctypes.c_void_p), ('init_state', ctypes.c_void_p), ('alpha_src', ctypes.c_void_p),
+                ('src_stride', ctypes.c_int64)]
 
 
 class _Outputs(ctypes.Structure):
@@ -214,7 +215,7 @@ class Engine:
         L.blg_rebase.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p]
         L.blg_share_apply.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Inputs), ctypes.POINTER(_Outputs), ctypes.c_void_p,
-                                      ctypes.c_int64, ctypes.c_void_p]
+                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
         L.blg_marginal.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
                                    ctypes.c_void_p]
         L.blg_time_average.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
@@ -343,12 +344,14 @@ class Engine:
         return plan
 
     def _io(self, T, B, data, prior, reset_base, lik_table, program, lo, log_weight, init_state, log_evidence,
-            local_evidence, alive, alpha_seq, avg, final_state, row_scale=None, seq_stride=0, row_stride=0):
+            local_evidence, alive, alpha_seq, avg, final_state, row_scale=None, seq_stride=0, row_stride=0, alpha_src=None,
+            src_stride=0):
         i = _Inputs()
         i.T, i.B = int(T), int(B)
         i.data, i.prior, i.reset_base, i.lik_table = _ptr(data), _ptr(prior), _ptr(reset_base), _ptr(lik_table)
         i.prog = program.struct(lo, lo + B)
         i.log_weight, i.init_state = _ptr(log_weight), _ptr(init_state)
+        i.alpha_src, i.src_stride = _ptr(alpha_src), int(src_stride or 0)
         o = _Outputs()
         o.log_evidence, o.local_evidence, o.alive = _ptr(log_evidence), _ptr(local_evidence), _ptr(alive)
         o.alpha_seq, o.avg, o.final_state = _ptr(alpha_seq), _ptr(avg), _ptr(final_state)
@@ -361,7 +364,7 @@ class Engine:
         (tensors on self.device) plus `program` and `lo` (first combo row of the program used by this call)."""
         names = ('T', 'B', 'data', 'prior', 'reset_base', 'lik_table', 'program', 'lo', 'log_weight', 'init_state',
                  'log_evidence', 'local_evidence', 'alive', 'alpha_seq', 'avg', 'final_state', 'row_scale', 'seq_stride',
-                 'row_stride')
+                 'row_stride', 'alpha_src', 'src_stride')
         args = [kw.get(k) for k in names]
         args[7] = args[7] or 0
         i, o = self._io(*args)
@@ -386,16 +389,16 @@ class Engine:
         self._check(self.lib.blg_rebase(plan.handle, _ptr(x), int(count), _ptr(shift_from), _ptr(shift_to),
                                         self.stream()))
 
-    def share_apply(self, plan, ratio, ratio_stride, **kw):
+    def share_apply(self, plan, ratio, ratio_stride, n_groups, cp_step, **kw):
         """blg_share_apply: keyword arguments as in run() (T, B, data / lik_table, program, alpha_seq window, strides ...)."""
         names = ('T', 'B', 'data', 'prior', 'reset_base', 'lik_table', 'program', 'lo', 'log_weight', 'init_state',
                  'log_evidence', 'local_evidence', 'alive', 'alpha_seq', 'avg', 'final_state', 'row_scale', 'seq_stride',
-                 'row_stride')
+                 'row_stride', 'alpha_src', 'src_stride')
         args = [kw.get(k) for k in names]
         args[7] = args[7] or 0
         i, o = self._io(*args)
         self._check(self.lib.blg_share_apply(plan.handle, ctypes.byref(i), ctypes.byref(o), _ptr(ratio), int(ratio_stride),
-                                             self.stream()))
+                                             int(n_groups), _ptr(cp_step), self.stream()))
 
     def marginal(self, plan, seq, T, axis, out):
         self._check(self.lib.blg_marginal(plan.handle, _ptr(seq), int(T), int(axis), _ptr(out), self.stream()))

@@ -125,6 +125,9 @@ typedef struct blg_inputs {
     blg_program prog;
     const double *log_weight; /* device [B] backward+ACCUMULATE: logE_b + log hyperprior_b - shift                 */
     const double *init_state; /* device [B][G], only with BLG_F_INIT_STATE                                        */
+    const double *alpha_src;  /* blg_backward, optional: read the filtering rows HERE ([B] sequences src_stride doubles */
+    int64_t src_stride;       /*   apart, 0 = T * G) and write the smoothed rows to alpha_seq -- the out-of-place form,   */
+                              /*   for filtering rows that several calls share (change-point prefix sharing)            */
 } blg_inputs;
 
 typedef struct blg_outputs {
@@ -208,16 +211,17 @@ int blg_time_average(blg_plan *plan, const double *seq, int64_t T, double *out, 
  * (transitionModels.py:300-312), so all combinations that differ only in tChange share the filtering recursion BEFORE
  * it and the backward message AFTER it: both come from ONE change-point-free run per group of combinations.
  * The message itself needs no new pass: blg_backward on a sequence of ONES returns alpha * beta = beta row by row.
- *   blg_share_apply   rows t < in->T of the B combos of the call (a WINDOW of their sequences: pointer offsets +
- *                     seq_stride / row_stride): u = alpha_seq[b][t][g] * ratio[b][t][g] in place -- the smoothed
- *                     row up to its scale, which goes to row_scale[b][t] = 1 / sum(u) -- and
- *                     local_evidence[b][t] = 1 / (sum(post / lik) * prod(lattice))  (core.py:436-441, :463).
- *                     ratio: device, the backward message (any positive factor per row) of B sequences
- *                     `ratio_stride` doubles apart, same window.  in->data (or
- *                     in->lik_table) point at the first time step of the window.  Combos with alive[b] != 1 are
- *                     skipped; a zero row sum sets alive[b] = -1 (core.py:440-452). */
+ *   blg_share_apply   the B = n_cp * n_groups combos of the call are laid out change-point-major (combo k * n_groups + g
+ *                     = group g with its reset after step cp_step[k]).  For every row t > cp_step[k] of every combo:
+ *                     u = alpha_seq[b][t][.] * ratio[g][t][.] in place -- the smoothed row up to its scale, which
+ *                     goes to row_scale[b][t] = 1 / sum(u) -- and local_evidence[b][t] = 1 / (sum(post / lik) *
+ *                     prod(lattice))  (core.py:436-441, :463).  ratio: device, the backward message (any positive
+ *                     factor per row) of the n_groups change-point-free runs, `ratio_stride` doubles apart
+ *                     (0 = T * G); the message and the likelihood row of (g, t) are read ONCE for all change-points.
+ *                     cp_step: device [n_cp] int32.  Combos with alive[b] != 1 are skipped; a zero row sum sets
+ *                     alive[b] = -1 (core.py:440-452). */
 int blg_share_apply(blg_plan *plan, const blg_inputs *in, const blg_outputs *out, const double *ratio,
-                    int64_t ratio_stride, void *stream);
+                    int64_t ratio_stride, int64_t n_groups, const int32_t *cp_step, void *stream);
 
 /* Weighted sum of K rows: out[j] = sum_k weight[k] * state[k][j], j < n.  Used for the OnlineStudy
  * marginalisations (core.py:2195-2197, :2212; n = G) and for the averaged local evidence of a HyperStudy
