@@ -1093,11 +1093,18 @@ int blg_share_apply(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, 
     }
     if (n_groups * in->T > 2147483647LL) return fail("too many rows for one blg_share_apply call");
     const int nCp = (int)(in->B / n_groups);
+    const bool vec = d.G % 2 == 0 && seqStride % 2 == 0 && ratioStride % 2 == 0 && (uintptr_t)out->alpha_seq % 16 == 0 &&
+                     (uintptr_t)ratio % 16 == 0 && (uintptr_t)lik % 16 == 0;
     for (int k0 = 0; k0 < nCp; k0 += kShareK) {
         const int nK = nCp - k0 < kShareK ? nCp - k0 : kShareK;
-        share_apply_kernel<<<(unsigned)(n_groups * in->T), 256, 0, st>>>(out->alpha_seq, seqStride, ratio, ratioStride, lik, in->T,
-                                                                         d.G, d.lc_prod, out->row_scale, out->local_evidence,
-                                                                         rowStride, out->alive, n_groups, cp_step, k0, nK);
+        if (vec)
+            share_apply_kernel<true><<<(unsigned)(n_groups * in->T), 256, 0, st>>>(
+                out->alpha_seq, seqStride, ratio, ratioStride, lik, in->T, d.G, d.lc_prod, out->row_scale, out->local_evidence,
+                rowStride, out->alive, n_groups, cp_step, k0, nK);
+        else
+            share_apply_kernel<false><<<(unsigned)(n_groups * in->T), 256, 0, st>>>(
+                out->alpha_seq, seqStride, ratio, ratioStride, lik, in->T, d.G, d.lc_prod, out->row_scale, out->local_evidence,
+                rowStride, out->alive, n_groups, cp_step, k0, nK);
         ++g_launches;
     }
     CUDA_TRY(cudaGetLastError());

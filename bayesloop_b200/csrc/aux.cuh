@@ -219,48 +219,71 @@ __global__ void time_average_kernel(const double *__restrict__ seq, long long T,
 // row lik[t][.] are read once; for every change-point k of the call with cp[k] < t the row of combo k * nG + g becomes
 // u = alpha * ratio in place, row_scale = 1 / sum(u), local evidence from sum(u / lik).  Up to kShareK change-points
 // per launch (per-thread partial sums live in registers).
-constexpr int kShareK = 12;
-__global__ void __launch_bounds__(256) share_apply_kernel(double *__restrict__ seq, long long seqStride,
-                                                          const double *__restrict__ ratio, long long ratioStride,
-                                                          const double *__restrict__ lik, long long T, int G, double lcProd,
-                                                          double *__restrict__ rowScale, double *__restrict__ local,
-                                                          long long rowStride, int *__restrict__ alive, long long nG,
-                                                          const int *__restrict__ cp, int k0, int nK) {
+constexpr int kShareK = 8;
+template <bool VEC>  // VEC: G even and 16-byte aligned rows -> double2 accesses (twice the bytes in flight per request)
+__global__ void __launch_bounds__(256, 2) share_apply_kernel(double *__restrict__ seq, long long seqStride,
+                                                             const double *__restrict__ ratio, long long ratioStride,
+                                                             const double *__restrict__ lik, long long T, int G,
+                                                             double lcProd, double *__restrict__ rowScale,
+                                                             double *__restrict__ local, long long rowStride,
+                                                             int *__restrict__ alive, long long nG,
+                                                             const int *__restrict__ cp, int k0, int nK) {
     __shared__ double scratch[6 * kMaxWarps];
     RedScratch rs;
     rs.buf = scratch;
     rs.phase = 0;
     const long long g = blockIdx.x / T, t = blockIdx.x - g * T;
-    bool on[kShareK];
-    int any = 0;
-#pragma unroll
-    for (int k = 0; k < kShareK; ++k) {
-        on[k] = k < nK && __ldg(cp + k0 + k) < t && (!alive || alive[(k0 + k) * nG + g] == 1);
-        any |= on[k];
-    }
-    if (!any) return;
+    unsigned on = 0u;  // bit k: change-point k0 + k lies before row t and its combo is alive
+    for (int k = 0; k < nK; ++k)
+        if (__ldg(cp + k0 + k) < t && (!alive || alive[(k0 + k) * nG + g] == 1)) on |= 1u << k;
+    if (!on) return;
     const double *rr = ratio + g * ratioStride + t * G, *lk = lik + t * (long long)G;
+    double *rows = seq + (k0 * nG + g) * seqStride + t * G;  // row of change-point k0; the next one is nG sequences on
+    const long long kStride = nG * seqStride;
     double s[kShareK], q[kShareK];
 #pragma unroll
     for (int k = 0; k < kShareK; ++k) s[k] = q[k] = 0.0;
-    for (int cell = threadIdx.x; cell < G; cell += blockDim.x) {
-        const double r = __ldcs(rr + cell), l = __ldg(lk + cell);
-        const bool small = l < 1e-290;  // core.py:463 without a division per change-point (see fast_div_pos)
+    // core.py:463 without a division per change-point: one reciprocal of the likelihood per cell (see fast_div_pos)
+    auto cell = [&](double r, double l, double &x, int k) {
+        const bool small = l < 1e-290;
         const double rl = fast_rcp(small ? l * 0x1p600 : l);
+        const double u = x * r;
+        x = u;
+        s[k] += u;
+        const double qv = u * rl;
+        q[k] += small ? qv * 0x1p600 : qv;
+    };
+    if (VEC) {
+        for (int c2 = threadIdx.x; c2 < G / 2; c2 += blockDim.x) {
+            const double2 r = __ldcs(reinterpret_cast<const double2 *>(rr) + c2);
+            const double2 l = __ldg(reinterpret_cast<const double2 *>(lk) + c2);
+            double2 v[kShareK];
 #pragma unroll
-        for (int k = 0; k < kShareK; ++k)
-            if (on[k]) {
-                double *row = seq + ((k0 + k) * nG + g) * seqStride + t * G;
-                const double u = row[cell] * r;
-                row[cell] = u;
-                s[k] += u;
-                const double qv = u * rl;
-                q[k] += small ? qv * 0x1p600 : qv;
-            }
+            for (int k = 0; k < kShareK; ++k)
+                if (on >> k & 1u) v[k] = reinterpret_cast<const double2 *>(rows + k * kStride)[c2];
+#pragma unroll
+            for (int k = 0; k < kShareK; ++k)
+                if (on >> k & 1u) {
+                    cell(r.x, l.x, v[k].x, k);
+                    cell(r.y, l.y, v[k].y, k);
+                    reinterpret_cast<double2 *>(rows + k * kStride)[c2] = v[k];
+                }
+        }
+    } else {
+        for (int c = threadIdx.x; c < G; c += blockDim.x) {
+            const double r = __ldcs(rr + c), l = __ldg(lk + c);
+#pragma unroll
+            for (int k = 0; k < kShareK; ++k)
+                if (on >> k & 1u) {
+                    double x = rows[k * kStride + c];
+                    cell(r, l, x, k);
+                    rows[k * kStride + c] = x;
+                }
+        }
     }
 #pragma unroll
     for (int k = 0; k < kShareK; ++k)
-        if (on[k]) {  // uniform over the block
+        if (on >> k & 1u) {  // uniform over the block
             double sk = s[k], qk = q[k];
             block_sum2(sk, qk, rs);
             if (threadIdx.x == 0) {

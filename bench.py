@@ -326,8 +326,9 @@ def measure_sweep(wl, bl, eng, torch, td, world, steps, warmup, local_rank, e2e=
         torch.cuda.synchronize()
 
     timers = Timers(torch)
-    plain_run = eng.run
+    plain_run, plain_apply = eng.run, eng.share_apply
     eng.run = timers.wrap(lambda which, *a, **kw: which, plain_run, name_of=eng.last_kernel)
+    eng.share_apply = timers.wrap('share_apply', plain_apply)
     plain = {k: getattr(dist, k) for k in ('rebase_and_reduce', 'gather_rows', 'reduce_sum')}
     for k, fn in plain.items():
         setattr(dist, k, timers.wrap('collective:' + k, fn))
@@ -378,7 +379,7 @@ def measure_sweep(wl, bl, eng, torch, td, world, steps, warmup, local_rank, e2e=
             del S2
             torch.cuda.empty_cache()
     finally:
-        eng.run = plain_run
+        eng.run, eng.share_apply = plain_run, plain_apply
         for k, fn in plain.items():
             setattr(dist, k, fn)
     times = torch.tensor([dev_ms, e2e_ms or 0.0], dtype=torch.float64, device='cuda')
@@ -411,6 +412,11 @@ def sweep_report(wl, m, peak, peak_src, world):
             kern[name] = {'ms': total, 'launches_per_step': len(m['ms'][which]) // m['steps'], 'GBps': gbs, 'frac': gbs / peak,
                           'bytes_per_cell': BYTES_PER_CELL[which]}
     coll = {k.split(':', 1)[1]: float(np.sum(v)) / m['steps'] for k, v in m['ms'].items() if k.startswith('collective:')}
+    if 'share_apply' in m['ms']:  # prefix sharing: own rows x shared backward message, 16 B per suffix cell
+        total = float(np.sum(m['ms']['share_apply'])) / m['steps']
+        kern['share_apply_kernel'] = {'ms': total, 'launches_per_step': len(m['ms']['share_apply']) // m['steps'],
+                                      'GBps': 16.0 * executed / 4.0 / (total * 1e-3) / 1e9,
+                                      'frac': 16.0 * executed / 4.0 / (total * 1e-3) / 1e9 / peak, 'bytes_per_cell': 16.0}
     dominant = max(kern, key=lambda k: kern[k]['ms'])
     kernel_ms = sum(v['ms'] for v in kern.values())
     coll_ms = sum(coll.values())
