@@ -58,6 +58,11 @@ struct Opts {
     int serpentine = 1;      // alternate the block -> combo mapping per wave of SMs
     int verbose = 0;         // print the launch geometry to stderr
     int ws_m = 0, ws_nt = 0; // warp-specialised 1-D kernels: force (cells per thread, threads); 0 = by grid size
+    int ws_ml = 0;           // ... cells per thread of the last compute warp (0 = ws_m)
+    int ws_even = 0;         // ... same number of cells per thread in every compute warp (no uneven split)
+    int ws_pace_every = 4;   // ... chains of an SM publish their step count every N steps (power of two) ...
+    int ws_pace_skew = 0;    // ... and hold back when more than this many steps ahead of a peer (0 = no pacing, the
+                             // default: lock-step chains measured no faster, profiles/r2u_ws_pacing.txt)
     char trace[256] = {0};   // per-CTA trace files <trace>.<kernel>.<n>.csv (debugging aid)
 };
 
@@ -83,6 +88,10 @@ const OptName kOptNames[] = {
     {"verbose", "BLG_VERBOSE", &Opts::verbose},
     {"ws_m", "BLG_WS_M", &Opts::ws_m},
     {"ws_nt", "BLG_WS_NT", &Opts::ws_nt},
+    {"ws_ml", "BLG_WS_ML", &Opts::ws_ml},
+    {"ws_even", "BLG_WS_EVEN", &Opts::ws_even},
+    {"ws_pace_every", "BLG_WS_PACE_EVERY", &Opts::ws_pace_every},
+    {"ws_pace_skew", "BLG_WS_PACE_SKEW", &Opts::ws_pace_skew},
 };
 
 void opts_from_env(Opts &o) {
@@ -316,7 +325,8 @@ int ensure_w(blg_plan *pl, long long count) {
 // Shared likelihood table: worth it as soon as a few combos share it; bounded so it never competes with alpha_seq.
 // permM > 0: "owner order" of the warp-specialised 1-D kernels (rows of permM planes x permNC entries, see
 // lik_table_perm_kernel); a caller-supplied table (BLG_OM_TABLE) is permuted into the same scratch.
-int prep_lik_table(blg_plan *pl, const blg_inputs *in, PassArgs &a, cudaStream_t st, int permM = 0, int permNC = 0) {
+int prep_lik_table(blg_plan *pl, const blg_inputs *in, PassArgs &a, cudaStream_t st, int permM = 0, int permML = 0,
+                   int permNC = 0) {
     const DevProblem &d = pl->dev;
     a.lik_pitch = d.G;
     if (!permM && (d.om_kind == BLG_OM_TABLE || pl->opt.no_lik_table)) return 0;
@@ -337,7 +347,7 @@ int prep_lik_table(blg_plan *pl, const blg_inputs *in, PassArgs &a, cudaStream_t
     const int nt = 256;
     if (permM)
         lik_table_perm_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(
-            d, pl->d_steps, d.om_kind == BLG_OM_TABLE ? in->lik_table : nullptr, in->T, permM, permNC, pl->d_lik);
+            d, pl->d_steps, d.om_kind == BLG_OM_TABLE ? in->lik_table : nullptr, in->T, permM, permML, permNC, pl->d_lik);
     else
         lik_table_kernel<<<(unsigned)((count + nt - 1) / nt), nt, 0, st>>>(d, pl->d_steps, in->T, pl->d_lik);
     ++g_launches;
@@ -444,28 +454,41 @@ bool fast1d_layout(const blg_plan *pl, const blg_program &pg, bool backward, int
 
 // Warp-specialised fast path (fast1d_ws.cuh): same shapes as fast1d_layout; chooses (M, threads) so that the compute
 // warps (threads/32 - 1) cover the grid with M cells per thread.
-bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, PassArgs &a, Layout &lay, int &M) {
+bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, PassArgs &a, Layout &lay, int &M, int &ML) {
     const DevProblem &d = pl->dev;
     if (pl->opt.no_fast1d || pl->opt.no_ws || pl->opt.force_stream) return false;
     if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW) return false;
-    // 4 compute warps (one per SM sub-partition) + the service warp = 160 threads, M = smallest odd cell count per
-    // thread that covers the grid; beyond 128 * 11 cells 8 compute warps (two per sub-partition) = 288 threads.
-    // Round 2, per-warp trace profiles/r2d_ws_trace.txt: with 3 compute warps per chain the busiest sub-partition
-    // carried 1.6x the mean convolution load (the chain's pace is set by it); with 4 the load is level (0.93).
-    int nt = 160;
-    M = 0;
-    for (int m = 3; m <= 11 && !M; m += 2)
-        if (128 * m >= d.G) M = m;
-    if (!M) {
-        nt = 288;
-        for (int m = 7; m <= 11 && !M; m += 2)
-            if (256 * m >= d.G) M = m;
+    // 4 compute warps (one per SM sub-partition) + the service warp = 160 threads; beyond 128 * 11 cells 8 compute warps
+    // (two per sub-partition) = 288 threads.  Round 2, per-warp trace profiles/r2d_ws_trace.txt: with 3 compute warps
+    // per chain the busiest sub-partition carried 1.6x the mean convolution load (the chain's pace is set by it); with 4
+    // the load is level (0.93).  Among the compiled geometries {M cells per thread, ML in the last compute warp} the
+    // one with the fewest cell slots that cover the grid wins (every slot costs its DFMAs, owned or not): G = 1000 ->
+    // 3 x 32 x 9 + 32 x 5 = 1024 slots instead of 4 x 32 x 9 = 1152.
+    int nt = 0;
+    M = ML = 0;
+    for (int pass = 0; pass < 2 && !M; ++pass) {
+        const int want = pass ? 288 : 160;
+        long long best = 0;
+        for (const int *g = fast1d_ws_geometries(); g[0]; g += 3) {
+            if (g[2] != want || (pl->opt.ws_even && g[0] != g[1])) continue;
+            const long long slots = (long long)(want - 64) * g[0] + 32LL * g[1];
+            if (slots >= d.G && (!M || slots < best)) {
+                M = g[0];
+                ML = g[1];
+                nt = want;
+                best = slots;
+            }
+        }
     }
     if (!M) return false;
-    if (pl->opt.ws_m > 0 && pl->opt.ws_nt > 0 && (pl->opt.ws_nt / 32 - 1) * 32 * pl->opt.ws_m >= d.G &&
-        fwd_fast1d_ws_entry(pl->opt.ws_m, pl->opt.ws_nt)) {  // tuning override: (cells per thread, threads)
-        M = pl->opt.ws_m;
-        nt = pl->opt.ws_nt;
+    if (pl->opt.ws_m > 0 && pl->opt.ws_nt > 0) {  // tuning override: (cells per thread [, in the last warp], threads)
+        const int ml = pl->opt.ws_ml > 0 ? pl->opt.ws_ml : pl->opt.ws_m;
+        if ((long long)(pl->opt.ws_nt - 64) * pl->opt.ws_m + 32LL * ml >= d.G &&
+            fwd_fast1d_ws_entry(pl->opt.ws_m, ml, pl->opt.ws_nt)) {
+            M = pl->opt.ws_m;
+            ML = ml;
+            nt = pl->opt.ws_nt;
+        }
     }
     const int halo = even_up(pg.max_radius[0] + 2 * M);
     if (halo > d.G) return false;
@@ -486,6 +509,9 @@ bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, 
     a.pg.w_off[0] = 0;
     a.pg.w_len[0] = ((taps + M - 1) / M + 1) * (M + 1);  // chunk-padded layout of conv_item (fast1d.cuh)
     off += a.pg.w_len[0];
+    a.ws_w2 = off;
+    a.ws_w2_len = ML != M ? ((taps + ML - 1) / ML + 1) * (ML + 1) : 0;  // the same weights in chunks of ML
+    off += a.ws_w2_len;
     a.off_misc = even_up(off);
     off = a.off_misc + kMiscDoubles;
     a.ws_part = off;
@@ -692,7 +718,7 @@ int prep_sm_assign(blg_plan *pl, const blg_inputs *in, PassArgs &a, long long &g
     grid = in->B;
     if (!pg.sm_assign || pg.sm_count != pl->num_sms || pg.sm_slots < 1 || pl->opt.no_sm_assign) return 0;
     if ((long long)pg.sm_count * pg.sm_slots < in->B) return 0;
-    const long long need = pg.sm_count + in->B;
+    const long long need = pg.sm_count + 2 * in->B;  // arrival counters, claim flags, progress (ws_pace)
     if (need > pl->sm_state_cap) {
         if (pl->d_sm_state) CUDA_TRY(cudaFree(pl->d_sm_state));
         pl->d_sm_state = nullptr;
@@ -700,7 +726,15 @@ int prep_sm_assign(blg_plan *pl, const blg_inputs *in, PassArgs &a, long long &g
         CUDA_TRY(cudaMalloc(&pl->d_sm_state, (size_t)need * sizeof(int)));
         pl->sm_state_cap = need;
     }
-    CUDA_TRY(cudaMemsetAsync(pl->d_sm_state, 0, (size_t)need * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(pl->d_sm_state, 0, (size_t)(pg.sm_count + in->B) * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(pl->d_sm_state + pg.sm_count + in->B, 0xff, (size_t)in->B * sizeof(int), st));  // -1: not started
+    a.ws_progress = pl->d_sm_state + pg.sm_count + in->B;
+    {   // pacing of the chains of an SM (fast1d_ws.cuh): publish / check every 2^k steps, hold back beyond `skew` steps
+        int every = pl->opt.ws_pace_every;
+        while (every & (every - 1)) every &= every - 1;  // power of two (0 = off)
+        a.pace_every = pl->opt.ws_pace_skew > 0 ? every : 0;
+        a.pace_skew = pl->opt.ws_pace_skew;
+    }
     a.sm_assign = pg.sm_assign;
     a.sm_state = pl->d_sm_state;
     a.sm_count = pg.sm_count;
@@ -824,15 +858,15 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && a.seq_stride % 2 == 0 &&
                         !pl->opt.no_bulk;
     {
-        int wsM = 0;
-        if (fast1d_ws_layout(pl, in->prog, false, a, lay, wsM)) {
-            const int rc = prep_lik_table(pl, in, a, st, wsM, lay.nt - 32);
+        int wsM = 0, wsML = 0;
+        if (fast1d_ws_layout(pl, in->prog, false, a, lay, wsM, wsML)) {
+            const int rc = prep_lik_table(pl, in, a, st, wsM, wsML, lay.nt - 32);
             if (rc < 0) return -1;
             if (rc == 0) {
                 a.use_bulk = bulkOk ? 1 : 0;
                 long long grid = in->B;
                 if (prep_sm_assign(pl, in, a, grid, st)) return -1;
-                if (PassKernel k = fwd_fast1d_ws_entry(wsM, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "fwd_fast1d_ws");
+                if (PassKernel k = fwd_fast1d_ws_entry(wsM, wsML, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "fwd_fast1d_ws");
                 return fail("warp-specialised forward kernel missing");
             }
         }
@@ -921,15 +955,15 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && a.seq_stride % 2 == 0 &&
                              (!in->alpha_src || ((uintptr_t)in->alpha_src % 16 == 0 && a.src_stride % 2 == 0)) && !pl->opt.no_bulk;
     {
-        int wsM = 0;
-        if (alignedRows && !acc && fast1d_ws_layout(pl, in->prog, true, a, lay, wsM)) {
-            const int rc = prep_lik_table(pl, in, a, st, wsM, lay.nt - 32);
+        int wsM = 0, wsML = 0;
+        if (alignedRows && !acc && fast1d_ws_layout(pl, in->prog, true, a, lay, wsM, wsML)) {
+            const int rc = prep_lik_table(pl, in, a, st, wsM, wsML, lay.nt - 32);
             if (rc < 0) return -1;
             if (rc == 0) {
                 a.use_bulk = 1;
                 long long grid = in->B;
                 if (prep_sm_assign(pl, in, a, grid, st)) return -1;
-                if (PassKernel k = bwd_fast1d_ws_entry(wsM, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "bwd_fast1d_ws");
+                if (PassKernel k = bwd_fast1d_ws_entry(wsM, wsML, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "bwd_fast1d_ws");
                 return fail("warp-specialised backward kernel missing");
             }
         }

@@ -59,17 +59,20 @@ __global__ void lik_table_kernel(DevProblem pb, const StepC *__restrict__ steps,
 }
 
 // The same table in "owner order" for the warp-specialised 1-D kernels (fast1d_ws.cuh): row t holds M planes of NC
-// entries, plane m entry c = likelihood of cell c*M + m (0 beyond the grid), so the M loads of compute thread c are
-// coalesced across the warp.  `src` != NULL: permute a caller-supplied table (BLG_OM_TABLE) instead of evaluating.
+// entries, plane m entry c = likelihood of the m-th cell of compute thread c (0 beyond the grid or beyond the
+// thread's cells), so the loads of a compute thread are coalesced across the warp.  Threads own M consecutive cells,
+// those of the last warp (c >= NC - 32) ML <= M cells (uneven split).  `src` != NULL: permute a caller-supplied table
+// (BLG_OM_TABLE) instead of evaluating.
 __global__ void lik_table_perm_kernel(DevProblem pb, const StepC *__restrict__ steps, const double *__restrict__ src,
-                                      long long T, int M, int NC, double *__restrict__ table) {
+                                      long long T, int M, int ML, int NC, double *__restrict__ table) {
     const long long pitch = (long long)M * NC;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= T * pitch) return;
     const long long t = e / pitch;
     const int q = (int)(e - t * pitch);
     const int m = q / NC, c = q - m * NC;
-    const int g = c * M + m;
+    const int cs = NC - 32;  // first thread of the short warp
+    const int g = c < cs ? c * M + m : (m < ML ? cs * M + (c - cs) * ML + m : pb.G);
     double v = 0.0;
     if (g < pb.G) {
         if (src) {

@@ -88,6 +88,11 @@ struct PassArgs {
     long long *trace;    // debugging: per-CTA {smid, combo, start, end} or NULL
     int halo;            // fast 1-D kernels: reflected halo cells on each side of the state (0 = generic kernels)
     int ws_part, ws_ctl; // warp-specialised 1-D kernels: offsets (doubles) of the partial sums / control block
+    int ws_w2, ws_w2_len;  // ... and of the weights in the chunk layout of the short last compute warp (uneven split)
+    // ... pacing of the chains that share an SM (ws_pace in fast1d_ws.cuh): device [B] steps done per combo (-1: not
+    // started, INT_MAX: finished) or NULL; a chain holds back while it is more than pace_skew steps ahead of a peer
+    int *ws_progress;
+    int pace_every, pace_skew;
     long long lik_pitch; // row pitch (doubles) of lik_table: G, or M*threads for the owner-order table
     // cluster-resident 2-D kernels (cluster2d.cuh): rows per band, halo rows per side, offsets (doubles) of the state
     // buffer and the staging band, size of the state buffer

@@ -47,7 +47,11 @@ __device__ __forceinline__ void conv_item(const double *__restrict__ line, int i
         acc[m] = 0.0;
     }
     p += M;
-    const int chunks = (2 * R + M) / M;  // ceil((2R+1)/M)
+    // exact tap count: full chunks of M taps, then a guarded remainder (the zero-padded last chunk cost ~6 % of the
+    // DFMAs of a reference-like sweep: (M-1)/2 of 2R+1 ~ 70 taps on average); adding w = 0 taps changes nothing, so
+    // the results are bit-identical either way
+    const int taps = 2 * R + 1;
+    const int chunks = taps / M, rem = taps - chunks * M;
     const double *wc = W;
     for (int c = 0; c < chunks; ++c) {
         double w[M];
@@ -67,17 +71,35 @@ __device__ __forceinline__ void conv_item(const double *__restrict__ line, int i
         p += M;
         wc += MP;
     }
+    if (rem > 0) {
+        double w[M];
+#pragma unroll
+        for (int k = 0; k < M / 2; ++k) {
+            const double2 t = reinterpret_cast<const double2 *>(wc)[k];
+            w[2 * k] = t.x;
+            w[2 * k + 1] = t.y;
+        }
+        w[M - 1] = wc[M - 1];
+#pragma unroll
+        for (int u = 0; u < M - 1; ++u) {
+            if (u >= rem) break;  // uniform over the CTA
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc[m] = fma(w[u], win[(u + m) % M], acc[m]);
+            if (u + 1 < rem) win[u] = p[u];
+        }
+    }
 }
 
 // Gaussian weights in the chunk-padded layout of conv_item (see build_weights in common.cuh for the formula).
+// Returns the normalising factor 1/sum (1 for the identity kernel).
 template <int M>
-__device__ __forceinline__ void build_weights_chunked(double *W, int len, double sigma, int R, RedScratch &rs) {
+__device__ __forceinline__ double build_weights_chunked(double *W, int len, double sigma, int R, RedScratch &rs) {
     constexpr int MP = M + 1;
     double part = 0.0;
     if (!(sigma > 0.0) || R <= 0) {  // transitionModels.py:110-113: identity
         for (int q = threadIdx.x; q < len; q += blockDim.x) W[q] = q == 0 ? 1.0 : 0.0;
         __syncthreads();
-        return;
+        return 1.0;
     }
     const double h = -0.5 / (sigma * sigma);
     for (int q = threadIdx.x; q < len; q += blockDim.x) {
@@ -92,6 +114,28 @@ __device__ __forceinline__ void build_weights_chunked(double *W, int len, double
     }
     const double inv = 1.0 / block_sum(part, rs);
     for (int q = threadIdx.x; q < len; q += blockDim.x) W[q] *= inv;
+    __syncthreads();
+    return inv;
+}
+
+// The same weights in the chunk layout of another M, normalised with the factor build_weights_chunked returned: the two
+// tables hold bit-identical values (uneven split of the warp-specialised kernels, fast1d_ws.cuh).
+template <int M>
+__device__ __forceinline__ void copy_weights_chunked(double *W, int len, double sigma, int R, double inv) {
+    constexpr int MP = M + 1;
+    const bool identity = !(sigma > 0.0) || R <= 0;
+    const double h = identity ? 0.0 : -0.5 / (sigma * sigma);
+    for (int q = threadIdx.x; q < len; q += blockDim.x) {
+        const int c = q / MP, u = q - c * MP, j = c * M + u;
+        double v = 0.0;
+        if (identity) {
+            v = q == 0 ? 1.0 : 0.0;
+        } else if (u < M && j <= 2 * R) {
+            const double x = (double)(j - R);
+            v = exp(h * x * x) * inv;
+        }
+        W[q] = v;
+    }
     __syncthreads();
 }
 

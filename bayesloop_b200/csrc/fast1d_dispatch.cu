@@ -25,28 +25,42 @@ PassKernel bwd_fast1d_entry(int M, int nt) {
 }
 
 // warp-specialised kernels (fast1d_ws_inst.cu): 4 compute warps + 1 service warp (160 threads) or 8 + 1 (288), so
-// that every SM sub-partition carries the same number of compute warps of every chain
-#define BLG_WS_ALL(X) X(3, 160) X(5, 160) X(7, 160) X(9, 160) X(11, 160) X(7, 288) X(9, 288) X(11, 288)
-#define BLG_WS(M, NT)                          \
-    PassKernel fwd_fast1d_ws_m##M##_nt##NT(); \
-    PassKernel bwd_fast1d_ws_m##M##_nt##NT();
+// that every SM sub-partition carries the same number of compute warps of every chain; M cells per thread, ML in the
+// last compute warp (uneven split: fewer FP64 lanes spent on cells beyond the grid).  Keep in step with
+// __graft_entry__.WS_UNITS.
+#define BLG_WS_ALL(X)                                                                                     \
+    X(3, 3, 160) X(5, 3, 160) X(5, 5, 160) X(7, 3, 160) X(7, 7, 160) X(9, 5, 160) X(9, 9, 160) X(11, 7, 160) \
+    X(11, 11, 160) X(7, 7, 288) X(9, 9, 288) X(11, 11, 288)
+#define BLG_WS(M, ML, NT)                              \
+    PassKernel fwd_fast1d_ws_m##M##_l##ML##_nt##NT(); \
+    PassKernel bwd_fast1d_ws_m##M##_l##ML##_nt##NT();
 BLG_WS_ALL(BLG_WS)
 #undef BLG_WS
 
-PassKernel fwd_fast1d_ws_entry(int M, int nt) {
-#define BLG_WS(MM, NT) \
-    if (nt == NT && M == MM) return fwd_fast1d_ws_m##MM##_nt##NT();
+PassKernel fwd_fast1d_ws_entry(int M, int ML, int nt) {
+#define BLG_WS(MM, LL, NT) \
+    if (nt == NT && M == MM && ML == LL) return fwd_fast1d_ws_m##MM##_l##LL##_nt##NT();
     BLG_WS_ALL(BLG_WS)
 #undef BLG_WS
     return nullptr;
 }
 
-PassKernel bwd_fast1d_ws_entry(int M, int nt) {
-#define BLG_WS(MM, NT) \
-    if (nt == NT && M == MM) return bwd_fast1d_ws_m##MM##_nt##NT();
+PassKernel bwd_fast1d_ws_entry(int M, int ML, int nt) {
+#define BLG_WS(MM, LL, NT) \
+    if (nt == NT && M == MM && ML == LL) return bwd_fast1d_ws_m##MM##_l##LL##_nt##NT();
     BLG_WS_ALL(BLG_WS)
 #undef BLG_WS
     return nullptr;
+}
+
+// the geometries above, for the layout search in api.cu: {M, ML, threads}, terminated by M = 0
+const int *fast1d_ws_geometries() {
+    static const int table[] = {
+#define BLG_WS(MM, LL, NT) MM, LL, NT,
+        BLG_WS_ALL(BLG_WS)
+#undef BLG_WS
+        0, 0, 0};
+    return table;
 }
 
 }  // namespace blg

@@ -31,11 +31,11 @@ __device__ __forceinline__ void named_arrive(int id, int count) {
 }
 
 // combo of this CTA (see combo_of_sm in common.cuh) plus the CTA's arrival index on its SM
-__device__ __forceinline__ long long combo_and_slot(const PassArgs &a, int *sh, int &slot) {
+__device__ __forceinline__ long long combo_and_slot(const PassArgs &a, int *sh, int &slot, int &sm) {
     if (threadIdx.x == 0) {
         int b = -1, k = 0;
+        unsigned smid = 0xffffffffu;
         if (a.sm_assign) {
-            unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             int *counters = a.sm_state, *claimed = a.sm_state + a.sm_count;
             b = -2;
@@ -63,10 +63,67 @@ __device__ __forceinline__ long long combo_and_slot(const PassArgs &a, int *sh, 
         }
         sh[0] = b;
         sh[1] = k;
+        sh[2] = (a.sm_assign && (int)smid < a.sm_count) ? (int)smid : -1;
     }
     __syncthreads();
     slot = sh[1];
+    sm = sh[2];
     return sh[0];
+}
+
+// PACING (round 2).  The per-CTA trace of a C2 sweep (profiles/r2s_sm_timeline.txt) showed that the chains sharing an SM
+// do NOT advance together: the warp schedulers favour some warps, one chain of an SM finishes after 45 % of the kernel,
+// the next after 60 %, and the last one runs alone for a third of the time -- with a single chain resident the FP64
+// pipe idles during every epilogue and barrier (16 % of all SM-time had one active chain, 17 % two).  Every chain now
+// publishes its step count (one global store by the service warp every pace_every steps) and holds back -- the service
+// warp delays its arrival at the step barrier -- while it is more than pace_skew steps ahead of a chain of the same
+// SM's list that has started.  The chain with the least progress never waits, so there is no deadlock; a chain that
+// has not started (-1) or has finished (INT_MAX) never blocks anybody; a bounded number of polls is a safety net
+// (pacing only shapes the schedule, results do not depend on it).
+struct WsPace {
+    int *progress;  // NULL: off
+    int peer;       // this lane's peer combo or -1
+    int every, skew;
+    bool tired;     // gave up waiting once: stop pacing
+};
+
+__device__ __forceinline__ WsPace ws_pace_init(const PassArgs &a, long long b, int sm, int lane) {
+    WsPace p;
+    p.progress = (a.ws_progress && a.sm_assign && sm >= 0 && a.pace_every > 0) ? a.ws_progress : nullptr;
+    p.peer = -1;
+    p.every = a.pace_every;
+    p.skew = a.pace_skew;
+    p.tired = false;
+    if (p.progress && lane < a.sm_slots) {
+        const int q = a.sm_assign[sm * a.sm_slots + lane];
+        if (q >= 0 && q != (int)b) p.peer = q;
+    }
+    return p;
+}
+
+__device__ __forceinline__ void ws_pace_done(const PassArgs &a, long long b) {
+    if (a.ws_progress) *reinterpret_cast<volatile int *>(a.ws_progress + b) = 0x7fffffff;
+}
+
+// called by the whole service warp in front of the barrier of step `step` (steps done so far)
+__device__ __forceinline__ void ws_pace(WsPace &p, long long b, long long step, int lane) {
+    if (!p.progress || p.tired || ((int)step & (p.every - 1)) != 0) return;  // every = power of two
+    if (lane == 0) *reinterpret_cast<volatile int *>(p.progress + b) = (int)step;
+    bool gaveUp = false;
+    if (p.peer >= 0) {
+        const int need = (int)step - p.skew;
+        const volatile int *q = p.progress + p.peer;
+        for (int polls = 0;; ++polls) {
+            const int v = *q;
+            if (v < 0 || v >= need) break;
+            if (polls > 20000) {  // ~10 ms: something is wrong with the peer; never hang on a scheduling hint
+                gaveUp = true;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    if (__any_sync(0xffffffffu, gaveUp)) p.tired = true;
 }
 
 // v[0..M) -> cells i0.. of a haloed line, plus their mirror images inside the halo (halo <= n)
@@ -98,12 +155,17 @@ __device__ __forceinline__ void trace_end_lane0(const PassArgs &a, int lane) {
 
 struct WsRoles {
     int lane, warp, rot, ct, i0;
-    bool service, owner;
+    bool service, owner, shortw;
 };
 
-template <int M, int NT>
+// UNEVEN SPLIT (round 2).  Every compute warp issues its DFMAs for 32 lanes x (cells per thread) whether the lanes own
+// grid cells or not: at G = 1000 four warps x 9 cells cover 1152 slots, 13 % of the FP64 work is spent on cells beyond
+// the grid.  With ML < M the LAST compute warp owns ML cells per thread (its own chunk layout of the weights, its own
+// instantiation of the per-step body): 3 x 32 x 9 + 32 x 5 = 1024 slots.  The CTAs of an SM start on different
+// sub-partitions (5 warps per CTA), so the short warps of the resident chains spread over the four sub-partitions.
+template <int M, int ML, int NT>
 __device__ __forceinline__ WsRoles ws_roles(int slot, int n) {
-    constexpr int NW = NT / 32;
+    constexpr int NW = NT / 32, NCW = NW - 1;
     WsRoles r;
     r.lane = threadIdx.x & 31;
     r.warp = threadIdx.x >> 5;
@@ -114,7 +176,8 @@ __device__ __forceinline__ WsRoles ws_roles(int slot, int n) {
     r.service = r.warp == r.rot;
     const int cw = r.warp - (r.warp > r.rot ? 1 : 0);
     r.ct = cw * 32 + r.lane;
-    r.i0 = r.ct * M;
+    r.shortw = (ML != M) && cw == NCW - 1;
+    r.i0 = r.shortw ? (NCW - 1) * 32 * M + r.lane * ML : r.ct * M;
     r.owner = !r.service && r.i0 < n;
     return r;
 }
@@ -142,21 +205,96 @@ __device__ __forceinline__ double lagged_scale(double s) {  // s^(-3/4) to a few
 }
 
 // ------------------------------------------------------------------------------------------------ K1w forward
-template <int M, int NT>
+// The per-step loop of one compute warp with MM cells per thread (MM = M, or ML for the short last warp); NCOMP =
+// compute threads of the CTA = pitch of one plane of the owner-order likelihood table.
+template <int MM, int NT>
+__device__ __forceinline__ void ws_fwd_compute(const PassArgs &a, const Fast1dSetup &s, const WsRoles &r, const double *W,
+                                               double *PP, volatile double *ctl, volatile int *deadFlag, bool rawRows,
+                                               bool first) {
+    constexpr int NCOMP = (NT / 32 - 1) * 32;
+    const int n = a.pb.G, halo = a.halo;
+    const long long T = a.T;
+    double *cur = s.buf0, *nxt = s.buf1;
+    const double *likp = a.lik_table + r.ct;
+    const long long pitch = a.lik_pitch;
+    double lk[MM];  // likelihood of this thread's cells, fetched one step ahead (right after the previous use)
+    if (r.owner) {
+#pragma unroll
+        for (int m = 0; m < MM; ++m) lk[m] = __ldg(likp + m * NCOMP);
+    }
+    // debugging aid (BLG_TRACE): cycles this warp spends in the convolution / the epilogue / waiting at the barrier
+    const bool prof = a.trace != nullptr;
+    long long cConv = 0, cEpi = 0, cBar = 0;
+    for (long long t = 0; t < T; ++t) {
+        double v[MM];
+        const bool trans = (t > 0 || first) && (t - 1 >= s.f_lo) && (t - 1 < s.f_hi);
+        const long long p0 = prof ? clock64() : 0;
+        if (r.owner) {
+            if (trans && s.R > 0) {
+                conv_item<MM>(cur, r.i0, s.R, W, v);  // transitionModels.py:111
+            } else {
+#pragma unroll
+                for (int m = 0; m < MM; ++m) v[m] = cur[r.i0 + m];
+            }
+        }
+        const long long p1 = prof ? clock64() : 0;
+        // lagged scale k_t: written by the service warp before it arrived at the barrier of step t-1
+        const double kappa = t >= 2 ? ctl[t & 1] : 1.0;
+        if (r.owner) {
+            // alpha <- prior * likelihood (core.py:375-382); cells beyond the grid carry lik = 0
+#pragma unroll
+            for (int m = 0; m < MM; ++m) v[m] *= kappa * lk[m];
+            if (t + 1 < T) {
+#pragma unroll
+                for (int m = 0; m < MM; ++m) lk[m] = __ldg(likp + (t + 1) * pitch + m * NCOMP);
+            }
+            store_cells_mirrored<MM>(nxt, r.i0, n, halo, v);
+            PP[(t & 1) * NCOMP + r.ct] = tree_sum<MM>(v);
+        }
+        if (rawRows) fence_proxy_async();  // the new state is read by the service warp's bulk-async row store
+        const long long p2 = prof ? clock64() : 0;
+        named_sync(1, NT);  // new state and its partial sums are visible to everybody
+        if (prof) {
+            cConv += p1 - p0;
+            cEpi += p2 - p1;
+            cBar += clock64() - p2;
+        }
+        {   // a zero norm found by the service warp behind the barrier of an EARLIER step ends the chain here; the
+            // flag carries the step so that both roles leave after the same number of barriers
+            const int ds = *deadFlag;
+            if (ds >= 0 && ds < t) break;
+        }
+        double *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+    if (prof && r.lane == 0) {
+        unsigned wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        long long *w = a.trace + 4 * (long long)gridDim.x + ((long long)blockIdx.x * 8 + r.warp) * 4;
+        w[0] = cConv;
+        w[1] = cEpi;
+        w[2] = cBar;
+        w[3] = wid;
+    }
+}
+
+template <int M, int ML, int NT>
 __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(const PassArgs a) {
+    static_assert(ML <= M, "the short warp owns at most M cells per thread");
     constexpr int NW = NT / 32, NCOMP = (NW - 1) * 32;
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    int slot;
-    const long long b = combo_and_slot(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6), slot);
+    int slot, smid;
+    const long long b = combo_and_slot(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6), slot, smid);
     if (b < 0) return;
     trace_begin(a, b);
-    const int n = pb.G, halo = a.halo;
+    const int n = pb.G;
     const long long T = a.T;
     Fast1dSetup s;
     // weights, windows (fast1d_setup without the per-cell likelihood tables: the table is always shared here)
-    s.buf0 = sm + halo;
-    s.buf1 = sm + (a.Gp + 2 * halo) + halo;
+    s.buf0 = sm + a.halo;
+    s.buf1 = sm + (a.Gp + 2 * a.halo) + a.halo;
     s.rs.buf = sm + a.off_misc;
     s.rs.phase = 0;
     s.W = sm + a.off_w;
@@ -168,21 +306,24 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
         s.f_hi = win[1];
     }
     if (!(s.sigma > 0.0) || s.R <= 0) s.R = 0;
-    if ((2 * s.R + M) / M * (M + 1) > a.pg.w_len[0]) {  // radius beyond blg_program.max_radius
-        if (threadIdx.x == 0) {
+    if ((2 * s.R + M) / M * (M + 1) > a.pg.w_len[0] || (ML != M && (2 * s.R + ML) / ML * (ML + 1) > a.ws_w2_len)) {
+        if (threadIdx.x == 0) {  // radius beyond blg_program.max_radius
             a.logE[b] = NAN;
             if (a.alive) a.alive[b] = -2;
+            ws_pace_done(a, b);
         }
         return;
     }
-    build_weights_chunked<M>(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
-    const WsRoles r = ws_roles<M, NT>(slot, n);
+    const double wInv = build_weights_chunked<M>(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
+    double *const WL = sm + a.ws_w2;  // the same weights in the chunk layout of the short warp
+    if (ML != M) copy_weights_chunked<ML>(WL, a.ws_w2_len, s.sigma, s.R, wInv);
+    const WsRoles r = ws_roles<M, ML, NT>(slot, n);
     double *PP = sm + a.ws_part;
     volatile double *ctl = sm + a.ws_ctl;
     volatile int *deadFlag = reinterpret_cast<volatile int *>(sm + a.ws_ctl + 2);
     {
         const double *init = (a.flags & BLG_F_INIT_STATE) ? a.init_state + b * (long long)n : a.prior;
-        for (int g = threadIdx.x; g < n; g += NT) store_mirrored(s.buf0, g, n, halo, init[g]);
+        for (int g = threadIdx.x; g < n; g += NT) store_mirrored(s.buf0, g, n, a.halo, init[g]);
         for (int j = threadIdx.x; j < 2 * NCOMP; j += NT) PP[j] = 0.0;  // threads without cells never write their slots
         if (threadIdx.x == 0) *deadFlag = -1;
     }
@@ -194,69 +335,10 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
 
     if (!r.service) {
         // ------------------------------------------------------------------ compute warps
-        double *cur = s.buf0, *nxt = s.buf1;
-        const double *likp = a.lik_table + r.ct;
-        const long long pitch = a.lik_pitch;
-        double lk[M];  // likelihood of this thread's cells, fetched one step ahead (right after the previous use)
-        if (r.owner) {
-#pragma unroll
-            for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + m * NCOMP);
-        }
-        // debugging aid (BLG_TRACE): cycles this warp spends in the convolution / the epilogue / waiting at the barrier
-        const bool prof = a.trace != nullptr;
-        long long cConv = 0, cEpi = 0, cBar = 0;
-        for (long long t = 0; t < T; ++t) {
-            double v[M];
-            const bool trans = (t > 0 || first) && (t - 1 >= s.f_lo) && (t - 1 < s.f_hi);
-            const long long p0 = prof ? clock64() : 0;
-            if (r.owner) {
-                if (trans && s.R > 0) {
-                    conv_item<M>(cur, r.i0, s.R, s.W, v);  // transitionModels.py:111
-                } else {
-#pragma unroll
-                    for (int m = 0; m < M; ++m) v[m] = cur[r.i0 + m];
-                }
-            }
-            const long long p1 = prof ? clock64() : 0;
-            // lagged scale k_t: written by the service warp before it arrived at the barrier of step t-1
-            const double kappa = t >= 2 ? ctl[t & 1] : 1.0;
-            if (r.owner) {
-                // alpha <- prior * likelihood (core.py:375-382); cells beyond the grid carry lik = 0
-#pragma unroll
-                for (int m = 0; m < M; ++m) v[m] *= kappa * lk[m];
-                if (t + 1 < T) {
-#pragma unroll
-                    for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + (t + 1) * pitch + m * NCOMP);
-                }
-                store_cells_mirrored<M>(nxt, r.i0, n, halo, v);
-                PP[(t & 1) * NCOMP + r.ct] = tree_sum<M>(v);
-            }
-            if (rawRows) fence_proxy_async();  // the new state is read by the service warp's bulk-async row store
-            const long long p2 = prof ? clock64() : 0;
-            named_sync(1, NT);  // new state and its partial sums are visible to everybody
-            if (prof) {
-                cConv += p1 - p0;
-                cEpi += p2 - p1;
-                cBar += clock64() - p2;
-            }
-            {   // a zero norm found by the service warp behind the barrier of an EARLIER step ends the chain here; the
-                // flag carries the step so that both roles leave after the same number of barriers
-                const int ds = *deadFlag;
-                if (ds >= 0 && ds < t) break;
-            }
-            double *tmp = cur;
-            cur = nxt;
-            nxt = tmp;
-        }
-        if (prof && r.lane == 0) {
-            unsigned wid;
-            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-            long long *w = a.trace + 4 * (long long)gridDim.x + ((long long)blockIdx.x * 8 + r.warp) * 4;
-            w[0] = cConv;
-            w[1] = cEpi;
-            w[2] = cBar;
-            w[3] = wid;
-        }
+        if (ML != M && r.shortw)
+            ws_fwd_compute<ML, NT>(a, s, r, WL, PP, ctl, deadFlag, rawRows, first);
+        else
+            ws_fwd_compute<M, NT>(a, s, r, s.W, PP, ctl, deadFlag, rawRows, first);
     } else {
         // ------------------------------------------------------------------ service warp
         double *seq = store ? a.alpha_seq + b * a.seq_stride : nullptr;
@@ -268,7 +350,9 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
         bool dead = false;
         double sPrev = 1.0;            // s_{t-1}; the initial state enters as it is (core.py:363, :382)
         double kNow = 1.0, kNext = 1.0;  // k_t, k_{t+1}
+        WsPace pace = ws_pace_init(a, b, smid, r.lane);
         for (long long t = 0; t < T; ++t) {
+            ws_pace(pace, b, t, r.lane);
             named_sync(1, NT);
             if (dead) break;  // the compute warps see the flag behind this barrier
             double part = 0.0;
@@ -328,27 +412,113 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_ws_kernel(con
                 logE += log(pb.lc_prod);  // core.py:417
             a.logE[b] = logE;
             if (a.alive) a.alive[b] = dead ? 0 : 1;
+            ws_pace_done(a, b);
         }
         trace_end_lane0(a, r.lane);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ K2w backward
-template <int M, int NT>
+template <int MM, int NT>
+__device__ __forceinline__ void ws_bwd_compute(const PassArgs &a, const Fast1dSetup &s, const WsRoles &r, const double *W,
+                                               double *PP, volatile double *ctl, volatile int *deadFlag, bool rawRows,
+                                               double *S0, uint64_t *bars) {
+    constexpr int NCOMP = (NT / 32 - 1) * 32;
+    const int n = a.pb.G, halo = a.halo, Gp = a.Gp;
+    const long long T = a.T;
+    double *cur = s.buf0, *nxt = s.buf1;
+    const double *likp = a.lik_table + r.ct;
+    const long long pitch = a.lik_pitch;
+    uint32_t phases = 0u;  // bit s = parity of the next completion of ring slot s
+    double beta[MM];
+#pragma unroll
+    for (int m = 0; m < MM; ++m) beta[m] = (r.owner && r.i0 + m < n) ? 1.0 / (double)n : 0.0;  // core.py:424-425
+    double lk[MM];  // likelihood of this thread's cells, fetched one step ahead (right after the previous use)
+    if (r.owner) {
+#pragma unroll
+        for (int m = 0; m < MM; ++m) lk[m] = __ldg(likp + (T - 1) * pitch + m * NCOMP);
+    }
+    for (long long i = T - 1; i >= 0; --i) {
+        const int sb = (int)(i & 1);
+        if (i < T - 1) {
+            const bool trans = (i + 1 >= s.b_lo) && (i + 1 < s.b_hi);
+            if (r.owner) {
+                if (trans && s.R > 0) {
+                    conv_item<MM>(cur, r.i0, s.R, W, beta);  // transitionModels.py:117-118
+                } else {
+#pragma unroll
+                    for (int m = 0; m < MM; ++m) beta[m] = cur[r.i0 + m];
+                }
+#pragma unroll
+                for (int m = 0; m < MM; ++m)
+                    if (r.i0 + m >= n) beta[m] = 0.0;
+            }
+        }
+        // keeps the (scale-free) beta recursion in range: lagged power of sum(beta) two steps back (see lagged_scale)
+        const double kb = i <= T - 3 ? ctl[i & 1] : 1.0;
+        mbar_wait(&bars[sb], (phases >> sb) & 1u);
+        phases ^= 1u << sb;
+        double *A = S0 + sb * Gp;
+        if (r.owner) {
+            double st[MM];
+            double spu0 = 0.0, spu1 = 0.0, sql0 = 0.0, sql1 = 0.0;  // two chains each: short dependency paths
+#pragma unroll
+            for (int m = 0; m < MM; ++m) {
+                const int li = r.i0 + m;
+                const double al = li < n ? A[li] : 0.0;
+                const double pu = al * beta[m];                            // posterior ~ alpha*beta   core.py:436
+                const double ql = li < n ? fast_div_pos(pu, lk[m]) : 0.0;  // core.py:463
+                st[m] = beta[m] * kb * lk[m];                              // beta*likelihood          core.py:467
+                if (li < n) A[li] = pu;
+                if (m & 1) {
+                    spu1 += pu;
+                    sql1 += ql;
+                } else {
+                    spu0 += pu;
+                    sql0 += ql;
+                }
+            }
+            if (i > 0) {
+#pragma unroll
+                for (int m = 0; m < MM; ++m) lk[m] = __ldg(likp + (i - 1) * pitch + m * NCOMP);
+            }
+            store_cells_mirrored<MM>(nxt, r.i0, n, halo, st);
+            double *pp = PP + sb * 3 * NCOMP;
+            pp[r.ct] = spu0 + spu1;
+            pp[NCOMP + r.ct] = tree_sum<MM>(st);  // sum of the new state (magnitude control only)
+            pp[2 * NCOMP + r.ct] = sql0 + sql1;
+        }
+        if (rawRows) fence_proxy_async();  // alpha * beta in the ring slot is read by the bulk-async row store
+        named_sync(1, NT);
+        {
+            const int ds = *deadFlag;  // step at which the service warp found a zero norm (rows run downwards)
+            if (ds >= 0 && ds > i) break;
+        }
+        double *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+}
+
+template <int M, int ML, int NT>
 __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(const PassArgs a) {
+    static_assert(ML <= M, "the short warp owns at most M cells per thread");
     constexpr int NW = NT / 32, NCOMP = (NW - 1) * 32;
     extern __shared__ __align__(16) double sm[];
     const DevProblem &pb = a.pb;
-    int slot;
-    const long long b = combo_and_slot(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6), slot);
+    int slot, smid;
+    const long long b = combo_and_slot(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6), slot, smid);
     if (b < 0) return;
     trace_begin(a, b);
-    if (a.alive && a.alive[b] != 1) return;  // the forward pass aborted (core.py:400)
-    const int n = pb.G, halo = a.halo;
+    if (a.alive && a.alive[b] != 1) {  // the forward pass aborted (core.py:400)
+        if (threadIdx.x == 0) ws_pace_done(a, b);
+        return;
+    }
+    const int n = pb.G;
     const long long T = a.T;
     Fast1dSetup s;
-    s.buf0 = sm + halo;
-    s.buf1 = sm + (a.Gp + 2 * halo) + halo;
+    s.buf0 = sm + a.halo;
+    s.buf1 = sm + (a.Gp + 2 * a.halo) + a.halo;
     s.rs.buf = sm + a.off_misc;
     s.rs.phase = 0;
     s.W = sm + a.off_w;
@@ -360,9 +530,14 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
         s.b_hi = win[3];
     }
     if (!(s.sigma > 0.0) || s.R <= 0) s.R = 0;
-    if ((2 * s.R + M) / M * (M + 1) > a.pg.w_len[0]) return;
-    build_weights_chunked<M>(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
-    const WsRoles r = ws_roles<M, NT>(slot, n);
+    if ((2 * s.R + M) / M * (M + 1) > a.pg.w_len[0] || (ML != M && (2 * s.R + ML) / ML * (ML + 1) > a.ws_w2_len)) {
+        if (threadIdx.x == 0) ws_pace_done(a, b);
+        return;
+    }
+    const double wInv = build_weights_chunked<M>(s.W, a.pg.w_len[0], s.sigma, s.R, s.rs);
+    double *const WL = sm + a.ws_w2;  // the same weights in the chunk layout of the short warp
+    if (ML != M) copy_weights_chunked<ML>(WL, a.ws_w2_len, s.sigma, s.R, wInv);
+    const WsRoles r = ws_roles<M, ML, NT>(slot, n);
     double *PP = sm + a.ws_part;  // [3][NCOMP]
     volatile double *ctl = sm + a.ws_ctl;
     volatile int *deadFlag = reinterpret_cast<volatile int *>(sm + a.ws_ctl + 2);
@@ -384,78 +559,10 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
 
     if (!r.service) {
         // ------------------------------------------------------------------ compute warps
-        double *cur = s.buf0, *nxt = s.buf1;
-        const double *likp = a.lik_table + r.ct;
-        const long long pitch = a.lik_pitch;
-        uint32_t phases = 0u;  // bit s = parity of the next completion of ring slot s
-        double beta[M];
-#pragma unroll
-        for (int m = 0; m < M; ++m) beta[m] = (r.owner && r.i0 + m < n) ? 1.0 / (double)n : 0.0;  // core.py:424-425
-        double lk[M];  // likelihood of this thread's cells, fetched one step ahead (right after the previous use)
-        if (r.owner) {
-#pragma unroll
-            for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + (T - 1) * pitch + m * NCOMP);
-        }
-        for (long long i = T - 1; i >= 0; --i) {
-            const int sb = (int)(i & 1);
-            if (i < T - 1) {
-                const bool trans = (i + 1 >= s.b_lo) && (i + 1 < s.b_hi);
-                if (r.owner) {
-                    if (trans && s.R > 0) {
-                        conv_item<M>(cur, r.i0, s.R, s.W, beta);  // transitionModels.py:117-118
-                    } else {
-#pragma unroll
-                        for (int m = 0; m < M; ++m) beta[m] = cur[r.i0 + m];
-                    }
-#pragma unroll
-                    for (int m = 0; m < M; ++m)
-                        if (r.i0 + m >= n) beta[m] = 0.0;
-                }
-            }
-            // keeps the (scale-free) beta recursion in range: lagged power of sum(beta) two steps back (see lagged_scale)
-            const double kb = i <= T - 3 ? ctl[i & 1] : 1.0;
-            mbar_wait(&bars[sb], (phases >> sb) & 1u);
-            phases ^= 1u << sb;
-            double *A = S0 + sb * Gp;
-            if (r.owner) {
-                double st[M];
-                double spu0 = 0.0, spu1 = 0.0, sql0 = 0.0, sql1 = 0.0;  // two chains each: short dependency paths
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    const int li = r.i0 + m;
-                    const double al = li < n ? A[li] : 0.0;
-                    const double pu = al * beta[m];                            // posterior ~ alpha*beta   core.py:436
-                    const double ql = li < n ? fast_div_pos(pu, lk[m]) : 0.0;  // core.py:463
-                    st[m] = beta[m] * kb * lk[m];                              // beta*likelihood          core.py:467
-                    if (li < n) A[li] = pu;
-                    if (m & 1) {
-                        spu1 += pu;
-                        sql1 += ql;
-                    } else {
-                        spu0 += pu;
-                        sql0 += ql;
-                    }
-                }
-                if (i > 0) {
-#pragma unroll
-                    for (int m = 0; m < M; ++m) lk[m] = __ldg(likp + (i - 1) * pitch + m * NCOMP);
-                }
-                store_cells_mirrored<M>(nxt, r.i0, n, halo, st);
-                double *pp = PP + sb * 3 * NCOMP;
-                pp[r.ct] = spu0 + spu1;
-                pp[NCOMP + r.ct] = tree_sum<M>(st);  // sum of the new state (magnitude control only)
-                pp[2 * NCOMP + r.ct] = sql0 + sql1;
-            }
-            if (rawRows) fence_proxy_async();  // alpha * beta in the ring slot is read by the bulk-async row store
-            named_sync(1, NT);
-            {
-                const int ds = *deadFlag;  // step at which the service warp found a zero norm (rows run downwards)
-                if (ds >= 0 && ds > i) break;
-            }
-            double *tmp = cur;
-            cur = nxt;
-            nxt = tmp;
-        }
+        if (ML != M && r.shortw)
+            ws_bwd_compute<ML, NT>(a, s, r, WL, PP, ctl, deadFlag, rawRows, S0, bars);
+        else
+            ws_bwd_compute<M, NT>(a, s, r, s.W, PP, ctl, deadFlag, rawRows, S0, bars);
     } else {
         // ------------------------------------------------------------------ service warp
         const bool raw = rawRows;
@@ -465,8 +572,10 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
         }
         bool dead = false;
         long long i = T - 1;
+        WsPace pace = ws_pace_init(a, b, smid, r.lane);
         for (; i >= 0; --i) {
             const int sb = (int)(i & 1);
+            ws_pace(pace, b, T - 1 - i, r.lane);
             named_sync(1, NT);
             if (dead) break;
             double spu = 0.0, sstate = 0.0, sql = 0.0;
@@ -528,6 +637,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_ws_kernel(con
             }
         }
         if (raw && r.lane == 0) bulk_wait_all();
+        if (r.lane == 0) ws_pace_done(a, b);
         trace_end_lane0(a, r.lane);
     }
 }

@@ -14,10 +14,12 @@ using PassKernel = void (*)(const PassArgs);
 PassKernel fwd_fast1d_entry(int M, int nt);
 PassKernel bwd_fast1d_entry(int M, int nt);
 
-// warp-specialised fast 1-D kernels (fast1d_ws.cuh): nt = 160 (4 compute warps, M in {3,5,7,9,11}) or 288 (8 compute
-// warps, M in {7,9,11}); the compute warps own M cells per thread, one service warp normalises / stores / prefetches
-PassKernel fwd_fast1d_ws_entry(int M, int nt);
-PassKernel bwd_fast1d_ws_entry(int M, int nt);
+// warp-specialised fast 1-D kernels (fast1d_ws.cuh): nt = 160 (4 compute warps) or 288 (8 compute warps); the compute
+// warps own M cells per thread (ML <= M in the last one), one service warp normalises / stores / prefetches.
+// fast1d_ws_geometries: the compiled {M, ML, nt} triples, terminated by M = 0.
+PassKernel fwd_fast1d_ws_entry(int M, int ML, int nt);
+PassKernel bwd_fast1d_ws_entry(int M, int ML, int nt);
+const int *fast1d_ws_geometries();
 
 // generic resident kernels (resident.cuh): nt in {256, 512, 1024}; stream = state in global scratch (1024 threads)
 PassKernel fwd_resident_entry(int nt, bool stream);
