@@ -60,6 +60,7 @@ struct Opts {
     int ws_m = 0, ws_nt = 0; // warp-specialised 1-D kernels: force (cells per thread, threads); 0 = by grid size
     int ws_ml = 0;           // ... cells per thread of the last compute warp (0 = ws_m)
     int ws_even = 0;         // ... same number of cells per thread in every compute warp (no uneven split)
+    int no_mma = 0;          // ... convolution with DFMAs (fast1d_ws.cuh) instead of FP64 matrix instructions (fast1d_mma.cuh)
     int ws_pace_every = 4;   // ... chains of an SM publish their step count every N steps (power of two) ...
     int ws_pace_skew = 0;    // ... and hold back when more than this many steps ahead of a peer (0 = no pacing, the
                              // default: lock-step chains measured no faster, profiles/r2u_ws_pacing.txt)
@@ -90,6 +91,7 @@ const OptName kOptNames[] = {
     {"ws_nt", "BLG_WS_NT", &Opts::ws_nt},
     {"ws_ml", "BLG_WS_ML", &Opts::ws_ml},
     {"ws_even", "BLG_WS_EVEN", &Opts::ws_even},
+    {"no_mma", "BLG_NO_MMA", &Opts::no_mma},
     {"ws_pace_every", "BLG_WS_PACE_EVERY", &Opts::ws_pace_every},
     {"ws_pace_skew", "BLG_WS_PACE_SKEW", &Opts::ws_pace_skew},
 };
@@ -326,21 +328,21 @@ int ensure_w(blg_plan *pl, long long count) {
 // permM > 0: "owner order" of the warp-specialised 1-D kernels (rows of permM planes x permNC entries, see
 // lik_table_perm_kernel); a caller-supplied table (BLG_OM_TABLE) is permuted into the same scratch.
 int prep_lik_table(blg_plan *pl, const blg_inputs *in, PassArgs &a, cudaStream_t st, int permM = 0, int permML = 0,
-                   int permNC = 0) {
+                   int permNC = 0, bool force = false) {
     const DevProblem &d = pl->dev;
     a.lik_pitch = d.G;
-    if (!permM && (d.om_kind == BLG_OM_TABLE || pl->opt.no_lik_table)) return 0;
+    if (!permM && (d.om_kind == BLG_OM_TABLE || (pl->opt.no_lik_table && !force))) return 0;
     const long long pitch = permM ? (long long)permM * permNC : (long long)d.G;
     const long long count = in->T * pitch;
-    if (!permM && in->B < 4) return 0;
-    if (count * 8 > (6LL << 30)) return permM ? 1 : 0;
+    if (!permM && !force && in->B < 4) return 0;
+    if (count * 8 > (6LL << 30)) return (permM || force) ? 1 : 0;
     if (count > pl->lik_cap) {
         if (pl->d_lik) CUDA_TRY(cudaFree(pl->d_lik));
         pl->d_lik = nullptr;
         pl->lik_cap = 0;
         if (cudaMalloc(&pl->d_lik, (size_t)count * sizeof(double)) != cudaSuccess) {
             cudaGetLastError();
-            return permM ? 1 : 0;  // no room: keep evaluating the likelihood in the passes
+            return (permM || force) ? 1 : 0;  // no room: keep evaluating the likelihood in the passes
         }
         pl->lik_cap = count;
     }
@@ -512,6 +514,51 @@ bool fast1d_ws_layout(const blg_plan *pl, const blg_program &pg, bool backward, 
     a.ws_w2 = off;
     a.ws_w2_len = ML != M ? ((taps + ML - 1) / ML + 1) * (ML + 1) : 0;  // the same weights in chunks of ML
     off += a.ws_w2_len;
+    a.off_misc = even_up(off);
+    off = a.off_misc + kMiscDoubles;
+    a.ws_part = off;
+    off += 6 * (nt - 32);  // partial sums: [2 parities][3 sums][compute threads]
+    a.ws_ctl = off;
+    off += 4;
+    lay.bytes = (size_t)off * sizeof(double);
+    lay.nt = nt;
+    return lay.bytes <= kSmemLimit;
+}
+
+// DMMA variant of the warp-specialised 1-D kernels (fast1d_mma.cuh): tiles of 64 cells, swizzled state buffers.
+bool fast1d_mma_layout(const blg_plan *pl, const blg_program &pg, bool backward, PassArgs &a, Layout &lay, int &tpw) {
+    const DevProblem &d = pl->dev;
+    if (pl->opt.no_fast1d || pl->opt.no_ws || pl->opt.no_mma || pl->opt.force_stream) return false;
+    if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW || d.G % 2) return false;
+    const int ntiles = (d.G + 63) / 64;
+    int nt = 160;
+    tpw = (ntiles + 3) / 4;
+    if (tpw > 6) {
+        nt = 288;
+        tpw = (ntiles + 7) / 8;
+        if (tpw < 4) tpw = 4;
+    }
+    if (tpw > 6 || !fwd_fast1d_mma_entry(tpw, nt)) return false;
+    const int halo = (pg.max_radius[0] + 3 + 7) & ~7;  // mma_halo(): multiple of 8
+    if (halo > d.G) return false;
+    a.halo = halo;
+    a.Gp = even_up(d.G);
+    a.n0p = even_up(d.n0);
+    a.n1p = 2;
+    a.mma_pitch = halo + 64 * ntiles + halo + 8;
+    int off = 2 * a.mma_pitch;
+    a.off_stage = -1;
+    if (backward) {
+        a.off_stage = off;
+        off += 2 * a.Gp;
+    }
+    a.off_tab = -1;
+    a.off_w = off;
+    a.pg.w_off[0] = 0;
+    a.pg.w_len[0] = even_up(2 * pg.max_radius[0] + 1 + 2 * 12);  // kMmaWPad zeros on both sides
+    off += a.pg.w_len[0];
+    a.ws_w2 = off;
+    a.ws_w2_len = 0;
     a.off_misc = even_up(off);
     off = a.off_misc + kMiscDoubles;
     a.ws_part = off;
@@ -857,6 +904,24 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
     Layout lay;
     const bool bulkOk = store && (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && a.seq_stride % 2 == 0 &&
                         !pl->opt.no_bulk;
+    {   // DMMA kernels: rows leave by 16-byte stores from registers, the likelihood arrives by 16-byte loads
+        int tpw = 0;
+        const bool rowsOk = !store || bulkOk;
+        const bool tabOk = pl->dev.om_kind != BLG_OM_TABLE || (uintptr_t)in->lik_table % 16 == 0;
+        if (rowsOk && tabOk && fast1d_mma_layout(pl, in->prog, false, a, lay, tpw)) {
+            const int rc = prep_lik_table(pl, in, a, st, 0, 0, 0, true);
+            if (rc < 0) return -1;
+            if (rc == 0) {
+                a.use_bulk = bulkOk ? 1 : 0;
+                long long grid = in->B;
+                if (prep_sm_assign(pl, in, a, grid, st)) return -1;
+                if (PassKernel k = fwd_fast1d_mma_entry(tpw, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "fwd_fast1d_mma");
+                return fail("DMMA forward kernel missing");
+            }
+        }
+        a.pb.om_kind = pl->dev.om_kind;
+        a.lik_table = in->lik_table;
+    }
     {
         int wsM = 0, wsML = 0;
         if (fast1d_ws_layout(pl, in->prog, false, a, lay, wsM, wsML)) {
@@ -955,6 +1020,21 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     const bool alignedRows = (pl->dev.G % 2 == 0) && ((uintptr_t)out->alpha_seq % 16 == 0) && a.seq_stride % 2 == 0 &&
                              (!in->alpha_src || ((uintptr_t)in->alpha_src % 16 == 0 && a.src_stride % 2 == 0)) && !pl->opt.no_bulk;
     {
+        int tpw = 0;
+        const bool tabOk = pl->dev.om_kind != BLG_OM_TABLE || (uintptr_t)in->lik_table % 16 == 0;
+        if (alignedRows && !acc && tabOk && fast1d_mma_layout(pl, in->prog, true, a, lay, tpw)) {
+            const int rc = prep_lik_table(pl, in, a, st, 0, 0, 0, true);
+            if (rc < 0) return -1;
+            if (rc == 0) {
+                a.use_bulk = 1;
+                long long grid = in->B;
+                if (prep_sm_assign(pl, in, a, grid, st)) return -1;
+                if (PassKernel k = bwd_fast1d_mma_entry(tpw, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "bwd_fast1d_mma");
+                return fail("DMMA backward kernel missing");
+            }
+            a.pb.om_kind = pl->dev.om_kind;
+            a.lik_table = in->lik_table;
+        }
         int wsM = 0, wsML = 0;
         if (alignedRows && !acc && fast1d_ws_layout(pl, in->prog, true, a, lay, wsM, wsML)) {
             const int rc = prep_lik_table(pl, in, a, st, wsM, wsML, lay.nt - 32);

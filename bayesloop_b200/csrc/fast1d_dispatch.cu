@@ -63,4 +63,29 @@ const int *fast1d_ws_geometries() {
     return table;
 }
 
+// DMMA kernels (fast1d_mma_inst.cu): tiles of 64 cells per compute warp x threads.  Keep in step with
+// __graft_entry__.MMA_UNITS.
+#define BLG_MMA_ALL(X) X(1, 160) X(2, 160) X(3, 160) X(4, 160) X(5, 160) X(6, 160) X(4, 288) X(5, 288) X(6, 288)
+#define BLG_MMA(TPW, NT)                       \
+    PassKernel fwd_fast1d_mma_t##TPW##_nt##NT(); \
+    PassKernel bwd_fast1d_mma_t##TPW##_nt##NT();
+BLG_MMA_ALL(BLG_MMA)
+#undef BLG_MMA
+
+PassKernel fwd_fast1d_mma_entry(int tpw, int nt) {
+#define BLG_MMA(TPW, NT) \
+    if (nt == NT && tpw == TPW) return fwd_fast1d_mma_t##TPW##_nt##NT();
+    BLG_MMA_ALL(BLG_MMA)
+#undef BLG_MMA
+    return nullptr;
+}
+
+PassKernel bwd_fast1d_mma_entry(int tpw, int nt) {
+#define BLG_MMA(TPW, NT) \
+    if (nt == NT && tpw == TPW) return bwd_fast1d_mma_t##TPW##_nt##NT();
+    BLG_MMA_ALL(BLG_MMA)
+#undef BLG_MMA
+    return nullptr;
+}
+
 }  // namespace blg

@@ -1,0 +1,629 @@
+// fast1d_mma.cuh -- K1m/K2m: the warp-specialised fast 1-D kernels (fast1d_ws.cuh) with the GaussianRandomWalk
+// convolution issued as FP64 matrix instructions (mma.sync.m8n8k4.f64, "DMMA").
+//
+// Why (B200, profiles/r2s_dmma_mix.txt, r2v_regions.txt): the convolution is FP64-FMA work on either path -- DMMA and DFMA
+// share the FP64 units (a mix of the two never exceeds the faster one) -- but
+//   * a warp of DFMAs reaches 54-57 MAC/clk/SM in isolation, DMMA 63.8 (the full 64 lanes), and
+//   * in the real kernel the DFMA loop keeps the pipe only ~62 % busy: with 3-4 compute warps per SM sub-partition the
+//     schedulers spend their cycles on the 2-cycle issue cadence, operand-collector waits and the LDS -> DFMA
+//     dependencies of 81-instruction chunks (stall_wait 29 %, selected 20 %, math 13 %, short scoreboard 8 % of the
+//     samples inside the loop).  One DMMA is 256 MACs = 16 cycles of pipe time per instruction: two resident warps
+//     saturate the pipe and the instruction count of the loop drops 8x.
+//
+// The convolution as a matrix product (no reshaping of the problem: the band of a Toeplitz matrix):
+//     y[c] = sum_k w[k] x[c - R + k]            (transitionModels.py:111; reflect boundary = mirrored halo cells)
+//   one 8 x 8 tile of outputs  Y[a][r] = y[tile + 8a + r]  accumulates, per "k-step" s = 4q,
+//     A[a][u] = x[tile + 8a + s + u]   (8 x 4: one LDS.64 per lane),
+//     B[u][r] = w[s + u - r + R]       (4 x 8 Toeplitz block, 0 outside 0..2R; the same for every tile),
+//   over s from 4*floor(-R/4) to 4*floor((R+7)/4): 2R + 11 taps on average instead of 2R + 1 (the 7 extra taps are the
+//   price of sharing one input window between 8 neighbouring outputs).  A compute warp owns TPW tiles (64 cells each),
+//   i.e. a lane owns the cell PAIRS (tile + 8*(lane/4) + 2*(lane%4), +1) of its tiles -- the accumulator fragment of the
+//   instruction -- so likelihood loads, state stores and row stores are 16-byte accesses, 512 contiguous bytes per warp:
+//   the rows go to HBM straight from the registers of the compute warps (no service-warp copy, no bulk store).
+//   The state buffers are XOR-swizzled (cell i lives at i ^ ((i >> 2) & 4): every other 16-cell block has its two
+//   4-cell halves swapped), which makes the 8-rows-by-4 fragment loads conflict free; pairs stay adjacent.
+//
+// Everything else -- roles, lagged scale, one named barrier per step, evidence bookkeeping, alpha ring of the backward
+// pass, zero-norm protocol -- is fast1d_ws.cuh.  Semantics: core.py:372-417, :424-470; transitionModels.py:96-118.
+#pragma once
+
+#include "fast1d_ws.cuh"
+
+namespace blg {
+
+constexpr int kMmaWPad = 12;  // zero weights in front of / behind the 2R+1 taps (the Toeplitz blocks reach 10 beyond)
+
+__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 2) & 4); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// halo cells on each side of the state: the k-steps reach R + 3 below the first and R + 10 beyond the last valid cell;
+// only [-halo, n + halo) holds mirrored values, the rest of the buffer stays zero (read with zero weights only)
+__host__ __device__ __forceinline__ int mma_halo(int R) { return (R + 3 + 7) & ~7; }
+
+// zero-padded weights Wz[k + kMmaWPad] = w[k] (build_weights in common.cuh), normalised; len >= 2R + 1 + 2*kMmaWPad
+__device__ __forceinline__ void mma_build_weights(double *Wz, int len, double sigma, int R, RedScratch &rs) {
+    if (!(sigma > 0.0) || R <= 0) {  // transitionModels.py:110-113: identity (never read: R = 0 skips the convolution)
+        for (int q = threadIdx.x; q < len; q += blockDim.x) Wz[q] = q == kMmaWPad ? 1.0 : 0.0;
+        __syncthreads();
+        return;
+    }
+    const double h = -0.5 / (sigma * sigma);
+    double part = 0.0;
+    for (int q = threadIdx.x; q < len; q += blockDim.x) {
+        const int k = q - kMmaWPad;
+        double v = 0.0;
+        if (k >= 0 && k <= 2 * R) {
+            const double x = (double)(k - R);
+            v = exp(h * x * x);
+        }
+        Wz[q] = v;
+        part += v;
+    }
+    const double inv = 1.0 / block_sum(part, rs);
+    for (int q = threadIdx.x; q < len; q += blockDim.x) Wz[q] *= inv;
+    __syncthreads();
+}
+
+// LEAN SERVICE WARP.  The step barrier counts the service warp, so a chain cannot step faster than the service warp's
+// loop -- and that loop was a chain of ~50 DEPENDENT FP64 instructions (rsqrt + sqrt for the lagged scale, the division
+// for the evidence increment, two frexp for the running product), each of which queues for the FP64 pipe behind the
+// matrix instructions of the compute warps of every chain on the sub-partition.  The per-warp trace showed it: every
+// chain took 5 300 - 6 600 cycles per step whatever its radius (profiles/r2d_ws_trace.txt), and an SM's throughput did
+// not depend on how many chains were running (profiles/r2u_ws_pacing.txt).  Here:
+//   * the lagged scale is a POWER OF TWO applied on demand (ondemand_scale): integer instructions only, multiplying by it
+//     is exact, and on most steps it is 1 and skipped;
+//   * the log-evidence telescopes: sum_t log norm_t = log s_{T-1} - sum_t log k_t = log s_{T-1} - ln 2 * (sum of the
+//     integer exponents) -- one log() at the end, no per-step division, and more accurate than a sum of T logs;
+//   * the per-step outputs that do need a division (local evidence, row scale) are parked in the lane t mod 32 and
+//     written every 32 steps by the whole warp at once (32 independent divisions instead of 32 dependent ones).
+// Rescaling ON DEMAND: the factor for step t+2 is 1 unless the binary exponent e of the sum after step t has left
+// [-kScaleBits, kScaleBits]; then it is 2^-e, and the sum of the next step (still uncorrected) is not looked at.  The
+// compute warps skip the multiplication on the steps whose factor is 1 -- all but one in ~30 for a typical series.
+constexpr int kScaleBits = 100;
+__device__ __forceinline__ double ondemand_scale(double s, int &hold, int &ke) {
+    ke = 0;
+    if (hold > 0) {
+        --hold;
+        return 1.0;
+    }
+    const int e = ((__double2hiint(s) >> 20) & 0x7ff) - 1023;  // floor(log2 s) for a normal positive s
+    if (e >= -kScaleBits && e <= kScaleBits) return 1.0;
+    ke = -e;
+    hold = 1;
+    return __hiloint2double((1023 + ke) << 20, 0);
+}
+
+__device__ __forceinline__ double times_pow2(double x, int ke) {  // exact unless the result leaves the normal range
+    return x * __hiloint2double((1023 + ke) << 20, 0);
+}
+
+struct MmaRoles {
+    int lane, warp, ct;
+    bool service;
+    int ntw;  // tiles of this compute warp that hold grid cells (warp-uniform)
+};
+
+template <int TPW, int NT>
+__device__ __forceinline__ MmaRoles mma_roles(int n) {
+    constexpr int NW = NT / 32, NCW = NW - 1;
+    MmaRoles r;
+    r.lane = threadIdx.x & 31;
+    r.warp = threadIdx.x >> 5;
+    r.service = r.warp == NW - 1;  // 5 or 9 warps per CTA: the hardware's slot allocation rotates the sub-partitions
+    r.ct = r.warp * 32 + r.lane;
+    const int ntiles = (n + 63) >> 6;
+    // warp w owns tiles w, w + NCW, w + 2 NCW ... (the partial and the absent tiles spread over the warps)
+    r.ntw = r.service ? 0 : (ntiles - r.warp + NCW - 1) / NCW;
+    if (r.ntw > TPW) r.ntw = TPW;
+    if (r.ntw < 0) r.ntw = 0;
+    return r;
+}
+
+// acc[k] = convolution outputs of the lane's cell pair in tile k (see the header); line = interior pointer of a swizzled
+// state buffer, base[k] = tile_k + 8*(lane/4) + (lane%4), wz = Wz + (lane%4) - (lane/4) + R + kMmaWPad
+template <int TPW, bool FULL>
+__device__ __forceinline__ void mma_conv_body(const double *__restrict__ line, const int (&base)[TPW], int ntw, int R,
+                                              const double *__restrict__ wz, double2 (&acc)[TPW]) {
+#pragma unroll
+    for (int k = 0; k < TPW; ++k) acc[k] = make_double2(0.0, 0.0);
+    const int qlo = -((R + 3) >> 2), qhi = (R + 7) >> 2;
+    // software pipeline: the fragments of k-step q+1 are loaded before the matrix instructions of k-step q are issued
+    // (the loads behind the last k-step read 4 cells / weights further, inside the buffers, and are not used)
+    double bw = wz[4 * qlo];
+    double av[TPW];
+#pragma unroll
+    for (int k = 0; k < TPW; ++k) av[k] = (FULL || k < ntw) ? line[swz(base[k] + 4 * qlo)] : 0.0;
+#pragma unroll 2
+    for (int q = qlo; q <= qhi; ++q) {
+        const int s1 = 4 * q + 4;
+        const double bwn = wz[s1];
+        double avn[TPW];
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) avn[k] = (FULL || k < ntw) ? line[swz(base[k] + s1)] : 0.0;
+#pragma unroll
+        for (int k = 0; k < TPW; ++k)
+            if (FULL || k < ntw) dmma884(acc[k].x, acc[k].y, av[k], bw);
+        bw = bwn;
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) av[k] = avn[k];
+    }
+}
+
+template <int TPW>
+__device__ __forceinline__ void mma_conv(const double *__restrict__ line, const int (&base)[TPW], int ntw, int R,
+                                         const double *__restrict__ wz, double2 (&acc)[TPW]) {
+    if (ntw == TPW)  // warp-uniform: no predicates around the matrix instructions of a warp whose tiles all hold cells
+        mma_conv_body<TPW, true>(line, base, ntw, R, wz, acc);
+    else
+        mma_conv_body<TPW, false>(line, base, ntw, R, wz, acc);
+}
+
+// the lane's pair (v.x, v.y) = cells (c, c+1), c even, into a swizzled haloed line plus the mirror images inside the
+// halo (halo <= n, n even): the mirrored pair is (c+1, c) at -2-c / 2n-2-c, again an aligned pair
+__device__ __forceinline__ void mma_store_pair(double *line, int c, int n, int halo, double2 v) {
+    *reinterpret_cast<double2 *>(line + swz(c)) = v;
+    if (c < halo) *reinterpret_cast<double2 *>(line + swz(-2 - c)) = make_double2(v.y, v.x);
+    if (c + 2 > n - halo) *reinterpret_cast<double2 *>(line + swz(2 * n - 2 - c)) = make_double2(v.y, v.x);
+}
+
+// ------------------------------------------------------------------------------------------------ K1m forward
+template <int TPW, int NT>
+__global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_mma_kernel(const PassArgs a) {
+    constexpr int NW = NT / 32, NCW = NW - 1, NCOMP = NCW * 32;
+    extern __shared__ __align__(16) double sm[];  // the base of the dynamic window is 1 KB aligned in practice
+    const DevProblem &pb = a.pb;
+    int slot, smid;
+    const long long b = combo_and_slot(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6), slot, smid);
+    if (b < 0) return;
+    trace_begin(a, b);
+    const int n = pb.G, halo = a.halo;
+    const long long T = a.T;
+    double *const buf0 = sm + halo, *const buf1 = sm + a.mma_pitch + halo;  // interior pointers, 128-byte aligned
+    RedScratch rs;
+    rs.buf = sm + a.off_misc;
+    rs.phase = 0;
+    double *const Wz = sm + a.off_w;
+    const double sigma = a.pg.param[b];
+    int R = a.pg.radius[b];
+    const int f_lo = a.pg.window[b * 4 + 0], f_hi = a.pg.window[b * 4 + 1];
+    if (!(sigma > 0.0) || R <= 0) R = 0;
+    if (2 * R + 1 + 2 * kMmaWPad > a.pg.w_len[0] || mma_halo(R) > halo) {  // radius beyond blg_program.max_radius
+        if (threadIdx.x == 0) {
+            a.logE[b] = NAN;
+            if (a.alive) a.alive[b] = -2;
+            ws_pace_done(a, b);
+        }
+        return;
+    }
+    // both buffers start as zeros: the cells beyond the mirrored halo are read (with zero weights) and never written
+    for (int j = threadIdx.x; j < 2 * a.mma_pitch; j += NT) sm[j] = 0.0;
+    mma_build_weights(Wz, a.pg.w_len[0], sigma, R, rs);  // ends with a CTA barrier
+    const MmaRoles r = mma_roles<TPW, NT>(n);
+    double *PP = sm + a.ws_part;
+    volatile double *ctl = sm + a.ws_ctl;
+    volatile int *deadFlag = reinterpret_cast<volatile int *>(sm + a.ws_ctl + 2);
+    {
+        const double *init = (a.flags & BLG_F_INIT_STATE) ? a.init_state + b * (long long)n : a.prior;
+        for (int g = threadIdx.x; g < n; g += NT) {
+            const double v = init[g];
+            buf0[swz(g)] = v;
+            if (g < halo) buf0[swz(-1 - g)] = v;
+            if (g >= n - halo) buf0[swz(2 * n - 1 - g)] = v;
+        }
+        for (int j = threadIdx.x; j < 2 * NCOMP; j += NT) PP[j] = 0.0;  // lanes without cells never write their slots
+        if (threadIdx.x == 0) *deadFlag = -1;
+    }
+    __syncthreads();
+    const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
+    const bool first = (a.flags & BLG_F_TRANSITION_FIRST) != 0;
+    // a backward pass follows (it is scale-free per row): rows leave unnormalised, straight from the registers
+    const bool rawRows = store && (a.flags & BLG_F_RAW_ALPHA);
+    double *seq = store ? a.alpha_seq + b * a.seq_stride : nullptr;
+
+    if (!r.service) {
+        // ------------------------------------------------------------------ compute warps
+        const int g8 = r.lane >> 2, u = r.lane & 3;
+        int base[TPW], c0[TPW];
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            const int tile = (r.warp + k * NCW) * 64;
+            base[k] = tile + 8 * g8 + u;
+            c0[k] = tile + 8 * g8 + 2 * u;
+        }
+        const double *wz = Wz + (u - g8 + R + kMmaWPad);
+        double *cur = buf0, *nxt = buf1;
+        const double *likp = a.lik_table;
+        const long long pitch = a.lik_pitch;
+        double2 lk[TPW];  // likelihood of the lane's cell pairs, fetched one step ahead
+#pragma unroll
+        for (int k = 0; k < TPW; ++k)
+            lk[k] = c0[k] < n ? __ldg(reinterpret_cast<const double2 *>(likp + c0[k])) : make_double2(0.0, 0.0);
+        const bool prof = a.trace != nullptr;
+        long long cConv = 0, cEpi = 0, cBar = 0;
+        for (long long t = 0; t < T; ++t) {
+            double2 v[TPW];
+            const bool trans = (t > 0 || first) && (t - 1 >= f_lo) && (t - 1 < f_hi);
+            const long long p0 = prof ? clock64() : 0;
+            if (trans && R > 0) {
+                mma_conv<TPW>(cur, base, r.ntw, R, wz, v);  // transitionModels.py:111
+            } else {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k)
+                    v[k] = c0[k] < n ? *reinterpret_cast<const double2 *>(cur + swz(c0[k])) : make_double2(0.0, 0.0);
+            }
+            const long long p1 = prof ? clock64() : 0;
+            // lagged scale k_t: written by the service warp before it arrived at the barrier of step t-1
+            const double kappa = t >= 2 ? ctl[t & 1] : 1.0;
+            // alpha <- prior * likelihood (core.py:375-382); cells beyond the grid carry lik = 0.  The factor is a power of
+            // two and 1 on most steps (the service warp rescales on demand): one multiply per cell
+            if (kappa == 1.0) {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) {
+                    v[k].x *= lk[k].x;
+                    v[k].y *= lk[k].y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) {
+                    v[k].x *= kappa * lk[k].x;
+                    v[k].y *= kappa * lk[k].y;
+                }
+            }
+            if (t + 1 < T) {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k)
+                    if (c0[k] < n) lk[k] = __ldg(reinterpret_cast<const double2 *>(likp + (t + 1) * pitch + c0[k]));
+            }
+            double ps[TPW];
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) {
+                ps[k] = 0.0;
+                if (c0[k] < n) {
+                    mma_store_pair(nxt, c0[k], n, halo, v[k]);
+                    if (rawRows) __stcs(reinterpret_cast<double2 *>(seq + t * (long long)n + c0[k]), v[k]);
+                    ps[k] = v[k].x + v[k].y;
+                }
+            }
+            const double part = tree_sum<TPW>(ps);
+            PP[(t & 1) * NCOMP + r.ct] = part;
+            const long long p2 = prof ? clock64() : 0;
+            named_sync(1, NT);  // new state and its partial sums are visible to everybody
+            if (prof) {
+                cConv += p1 - p0;
+                cEpi += p2 - p1;
+                cBar += clock64() - p2;
+            }
+            {   // a zero norm found by the service warp behind the barrier of an EARLIER step ends the chain here
+                const int ds = *deadFlag;
+                if (ds >= 0 && ds < t) break;
+            }
+            double *tmp = cur;
+            cur = nxt;
+            nxt = tmp;
+        }
+        if (prof && r.lane == 0 && r.warp < 8) {
+            unsigned wid;
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+            long long *w = a.trace + 4 * (long long)gridDim.x + ((long long)blockIdx.x * 8 + r.warp) * 4;
+            w[0] = cConv;
+            w[1] = cEpi;
+            w[2] = cBar;
+            w[3] = wid;
+        }
+    } else {
+        // ------------------------------------------------------------------ service warp
+        bool dead = false;
+        double sPrev = 1.0, sLast = 1.0;  // s_{t-1}; the initial state enters as it is (core.py:363, :382)
+        int keNow = 0, keNext = 0;        // binary exponents of k_t, k_{t+1}
+        int hold = 0;
+        long long keSum = 0;              // sum of the exponents of the factors applied so far
+        double myS = 1.0, myPrev = 1.0;   // lane t mod 32 parks step t for the deferred local evidence
+        int myKe = 0;
+        double *const local = a.local ? a.local + b * a.row_stride : nullptr;
+        // local evidence of the parked steps [t0, t0 + count): norm_t = s_t / (k_t s_{t-1})   core.py:385, :404
+        auto flush = [&](long long t0, int count) {
+            if (local && r.lane < count) local[t0 + r.lane] = fast_div(myS, times_pow2(myPrev, myKe)) * pb.lc_prod;
+        };
+        WsPace pace = ws_pace_init(a, b, smid, r.lane);
+        for (long long t = 0; t < T; ++t) {
+            ws_pace(pace, b, t, r.lane);
+            named_sync(1, NT);
+            if (dead) break;  // the compute warps see the flag behind this barrier
+            double part = 0.0;
+#pragma unroll
+            for (int j = 0; j < NCOMP / 32; ++j) part += PP[(t & 1) * NCOMP + j * 32 + r.lane];
+            const double st_sum = warp_sum(part);
+            int keAfter;
+            const double kAfter = ondemand_scale(st_sum, hold, keAfter);  // k_{t+2}
+            if (r.lane == 0) ctl[t & 1] = kAfter;
+            if (!(st_sum > 0.0) || isinf(st_sum)) {  // core.py:388-400
+                dead = true;
+                if (r.lane == 0) *deadFlag = (int)t;
+                flush(t & ~31LL, (int)(t & 31));
+                continue;  // one more barrier: the compute warps read the flag behind it
+            }
+            keSum += keNow;
+            if (r.lane == (int)(t & 31)) {
+                myS = st_sum;
+                myPrev = sPrev;
+                myKe = keNow;
+            }
+            if ((t & 31) == 31 || t == T - 1) flush(t & ~31LL, (int)(t & 31) + 1);
+            const double *st = (t & 1) ? buf0 : buf1;  // the buffer the compute warps just filled
+            if (store && !rawRows) {  // core.py:389, :408 -- normalised filtering distribution
+                const double inv = fast_rcp(st_sum);
+                double *row = seq + t * (long long)n;
+                if (a.use_bulk) {  // rows are 16-byte aligned
+                    for (int j = 2 * r.lane; j < n; j += 64) {
+                        double2 x = *reinterpret_cast<const double2 *>(st + swz(j));
+                        x.x *= inv;
+                        x.y *= inv;
+                        __stcs(reinterpret_cast<double2 *>(row + j), x);
+                    }
+                } else {
+                    for (int j = r.lane; j < n; j += 32) __stcs(row + j, st[swz(j)] * inv);
+                }
+            }
+            if ((a.flags & BLG_F_SAVE_STATE) && a.final_state && t == T - 1) {
+                const double inv = fast_rcp(st_sum);
+                double *fs = a.final_state + b * (long long)n;
+                for (int j = r.lane; j < n; j += 32) fs[j] = st[swz(j)] * inv;
+            }
+            sPrev = st_sum;
+            sLast = st_sum;
+            keNow = keNext;
+            keNext = keAfter;
+        }
+        if (r.lane == 0) {
+            // sum_t log(norm_t) = log(s_{T-1}) - sum_t log(k_t)   (core.py:403)
+            double logE = log(sLast) - (double)keSum * 0.693147180559945309417232121458;
+            if (dead)
+                logE = -INFINITY;
+            else if (!(a.flags & BLG_F_INIT_STATE))
+                logE += log(pb.lc_prod);  // core.py:417
+            a.logE[b] = logE;
+            if (a.alive) a.alive[b] = dead ? 0 : 1;
+            ws_pace_done(a, b);
+        }
+        trace_end_lane0(a, r.lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K2m backward
+template <int TPW, int NT>
+__global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_mma_kernel(const PassArgs a) {
+    constexpr int NW = NT / 32, NCW = NW - 1, NCOMP = NCW * 32;
+    extern __shared__ __align__(16) double sm[];  // the base of the dynamic window is 1 KB aligned in practice
+    const DevProblem &pb = a.pb;
+    int slot, smid;
+    const long long b = combo_and_slot(a, reinterpret_cast<int *>(sm + a.off_misc + kMiscBarrierOffset + 6), slot, smid);
+    if (b < 0) return;
+    trace_begin(a, b);
+    if (a.alive && a.alive[b] != 1) {  // the forward pass aborted (core.py:400)
+        if (threadIdx.x == 0) ws_pace_done(a, b);
+        return;
+    }
+    const int n = pb.G, halo = a.halo;
+    const long long T = a.T;
+    double *const buf0 = sm + halo, *const buf1 = sm + a.mma_pitch + halo;
+    RedScratch rs;
+    rs.buf = sm + a.off_misc;
+    rs.phase = 0;
+    double *const Wz = sm + a.off_w;
+    const double sigma = a.pg.param[b];
+    int R = a.pg.radius[b];
+    const int b_lo = a.pg.window[b * 4 + 2], b_hi = a.pg.window[b * 4 + 3];
+    if (!(sigma > 0.0) || R <= 0) R = 0;
+    if (2 * R + 1 + 2 * kMmaWPad > a.pg.w_len[0] || mma_halo(R) > halo) {
+        if (threadIdx.x == 0) ws_pace_done(a, b);
+        return;
+    }
+    for (int j = threadIdx.x; j < 2 * a.mma_pitch; j += NT) sm[j] = 0.0;
+    mma_build_weights(Wz, a.pg.w_len[0], sigma, R, rs);
+    const MmaRoles r = mma_roles<TPW, NT>(n);
+    double *PP = sm + a.ws_part;  // [2 parities][3][NCOMP]
+    volatile double *ctl = sm + a.ws_ctl;
+    volatile int *deadFlag = reinterpret_cast<volatile int *>(sm + a.ws_ctl + 2);
+    double *seq = a.alpha_seq + b * a.seq_stride;
+    const double *src = a.alpha_src ? a.alpha_src + b * a.src_stride : seq;  // filtering rows (out-of-place smoothing)
+    double *const S0 = sm + a.off_stage;  // alpha[t] ring: 2 slots of Gp doubles (natural order); alpha*beta in place
+    const int Gp = a.Gp;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + a.off_misc + kMiscBarrierOffset);
+    const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
+    for (int j = threadIdx.x; j < 6 * NCOMP; j += NT) PP[j] = 0.0;
+    if (threadIdx.x == 0) {
+        *deadFlag = -1;
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+    const bool rawRows = a.row_scale != nullptr;  // BLG_F_RAW_POSTERIOR: rows leave unnormalised + their factor
+
+    if (!r.service) {
+        // ------------------------------------------------------------------ compute warps
+        const int g8 = r.lane >> 2, u = r.lane & 3;
+        int base[TPW], c0[TPW];
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            const int tile = (r.warp + k * NCW) * 64;
+            base[k] = tile + 8 * g8 + u;
+            c0[k] = tile + 8 * g8 + 2 * u;
+        }
+        const double *wz = Wz + (u - g8 + R + kMmaWPad);
+        double *cur = buf0, *nxt = buf1;
+        const double *likp = a.lik_table;
+        const long long pitch = a.lik_pitch;
+        uint32_t phases = 0u;  // bit s = parity of the next completion of ring slot s
+        double2 beta[TPW];
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            const double v = c0[k] < n ? 1.0 / (double)n : 0.0;  // core.py:424-425
+            beta[k] = make_double2(v, v);
+        }
+        double2 lk[TPW];
+#pragma unroll
+        for (int k = 0; k < TPW; ++k)
+            lk[k] = c0[k] < n ? __ldg(reinterpret_cast<const double2 *>(likp + (T - 1) * pitch + c0[k])) : make_double2(1.0, 1.0);
+        for (long long i = T - 1; i >= 0; --i) {
+            const int sb = (int)(i & 1);
+            if (i < T - 1) {
+                const bool trans = (i + 1 >= b_lo) && (i + 1 < b_hi);
+                if (trans && R > 0) {
+                    mma_conv<TPW>(cur, base, r.ntw, R, wz, beta);  // transitionModels.py:117-118
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TPW; ++k)
+                        if (c0[k] < n) beta[k] = *reinterpret_cast<const double2 *>(cur + swz(c0[k]));
+                }
+#pragma unroll
+                for (int k = 0; k < TPW; ++k)
+                    if (c0[k] >= n) beta[k] = make_double2(0.0, 0.0);
+            }
+            // keeps the (scale-free) beta recursion in range: lagged power of sum(beta) two steps back (see lagged_scale)
+            const double kb = i <= T - 3 ? ctl[i & 1] : 1.0;
+            mbar_wait(&bars[sb], (phases >> sb) & 1u);
+            phases ^= 1u << sb;
+            double *A = S0 + sb * Gp;
+            double pspu[TPW], psst[TPW], psql[TPW];
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) {
+                pspu[k] = psst[k] = psql[k] = 0.0;
+                if (c0[k] < n) {
+                    const double2 al = *reinterpret_cast<const double2 *>(A + c0[k]);
+                    double2 pu, st;
+                    pu.x = al.x * beta[k].x;  // posterior ~ alpha*beta   core.py:436
+                    pu.y = al.y * beta[k].y;
+                    psql[k] = fast_div_pos(pu.x, lk[k].x) + fast_div_pos(pu.y, lk[k].y);  // core.py:463
+                    st.x = beta[k].x * lk[k].x;  // beta*likelihood          core.py:467
+                    st.y = beta[k].y * lk[k].y;
+                    if (kb != 1.0) {  // power of two, 1 on most steps
+                        st.x *= kb;
+                        st.y *= kb;
+                    }
+                    *reinterpret_cast<double2 *>(A + c0[k]) = pu;
+                    mma_store_pair(nxt, c0[k], n, halo, st);
+                    pspu[k] = pu.x + pu.y;
+                    psst[k] = st.x + st.y;
+                }
+            }
+            const double spu = tree_sum<TPW>(pspu), sst = tree_sum<TPW>(psst), sql = tree_sum<TPW>(psql);
+            if (i > 0) {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k)
+                    if (c0[k] < n) lk[k] = __ldg(reinterpret_cast<const double2 *>(likp + (i - 1) * pitch + c0[k]));
+            }
+            double *pp = PP + sb * 3 * NCOMP;
+            pp[r.ct] = spu;
+            pp[NCOMP + r.ct] = sst;  // sum of the new state (magnitude control only)
+            pp[2 * NCOMP + r.ct] = sql;
+            if (rawRows) fence_proxy_async();  // alpha * beta in the ring slot is read by the bulk-async row store
+            named_sync(1, NT);
+            {
+                const int ds = *deadFlag;  // step at which the service warp found a zero norm (rows run downwards)
+                if (ds >= 0 && ds > i) break;
+            }
+            double *tmp = cur;
+            cur = nxt;
+            nxt = tmp;
+        }
+    } else {
+        // ------------------------------------------------------------------ service warp
+        const bool raw = rawRows;
+        if (r.lane == 0) {
+            bulk_load(S0 + ((T - 1) & 1) * Gp, src + (T - 1) * (long long)n, rowBytes, &bars[(T - 1) & 1]);
+            if (T >= 2) bulk_load(S0 + ((T - 2) & 1) * Gp, src + (T - 2) * (long long)n, rowBytes, &bars[(T - 2) & 1]);
+        }
+        bool dead = false;
+        long long i = T - 1;
+        double mySpu = 1.0, mySql = 1.0;  // lane (T-1-i) mod 32 parks row i for the deferred divisions
+        int hold = 0;
+        double *const local = a.local ? a.local + b * a.row_stride : nullptr;
+        double *const rscale = raw ? a.row_scale + b * a.row_stride : nullptr;
+        // rows [iLow, iLow + count): lane j holds row iLow + count - 1 - j
+        auto flush = [&](long long iLow, int count) {
+            if (r.lane < count) {
+                const long long row = iLow + count - 1 - r.lane;
+                if (rscale) rscale[row] = fast_rcp(mySpu);  // posterior = alpha*beta / sum(alpha*beta)   core.py:439-441
+                if (local) local[row] = fast_div(mySpu, mySql * pb.lc_prod);  // 1/(sum(post/lik)*lc)     core.py:463
+            }
+        };
+        WsPace pace = ws_pace_init(a, b, smid, r.lane);
+        for (; i >= 0; --i) {
+            const int sb = (int)(i & 1);
+            const long long done = T - 1 - i;  // rows finished so far
+            ws_pace(pace, b, done, r.lane);
+            named_sync(1, NT);
+            if (dead) break;
+            double spu = 0.0, sstate = 0.0, sql = 0.0;
+            const double *pp = PP + sb * 3 * NCOMP;
+#pragma unroll
+            for (int j = 0; j < NCOMP / 32; ++j) {
+                spu += pp[j * 32 + r.lane];
+                sstate += pp[NCOMP + j * 32 + r.lane];
+                sql += pp[2 * NCOMP + j * 32 + r.lane];
+            }
+            spu = warp_sum(spu);
+            sstate = warp_sum(sstate);
+            sql = warp_sum(sql);
+            int ke;
+            const double kAfter = ondemand_scale(sstate, hold, ke);
+            if (r.lane == 0) ctl[i & 1] = kAfter;  // used by step i-2
+            if (!(spu > 0.0) || !(sstate > 0.0) || isinf(sstate)) {  // core.py:440-452
+                dead = true;
+                if (r.lane == 0) *deadFlag = (int)i;
+                flush(i + 1, (int)(done & 31));
+                continue;
+            }
+            if (r.lane == (int)(done & 31)) {
+                mySpu = spu;
+                mySql = sql;
+            }
+            if ((done & 31) == 31 || i == 0) flush(i, (int)(done & 31) + 1);
+            double *row = seq + i * (long long)n;
+            double *P = S0 + sb * Gp;
+            if (raw) {
+                if (r.lane == 0) {
+                    fence_proxy_async();
+                    bulk_store(row, P, rowBytes);
+                }
+            } else {
+                const double inv = fast_rcp(spu);
+                for (int j = 2 * r.lane; j < n; j += 64) {
+                    double2 x = *reinterpret_cast<const double2 *>(P + j);
+                    x.x *= inv;
+                    x.y *= inv;
+                    __stcs(reinterpret_cast<double2 *>(row + j), x);
+                }
+            }
+            __syncwarp();
+            if (r.lane == 0) {
+                if (raw) bulk_wait_read<0>();
+                if (i >= 2) {  // the slot is free again: prefetch alpha[i-2] into it
+                    fence_proxy_async();
+                    bulk_load(P, src + (i - 2) * (long long)n, rowBytes, &bars[sb]);
+                }
+            }
+        }
+        if (dead) {
+            // drain the prefetch that is still in flight before the CTA's shared memory is released (see fast1d_ws.cuh)
+            const long long died = i + 1;
+            if (died >= 1) {
+                const long long rr = died - 1;
+                mbar_wait(&bars[rr & 1], (uint32_t)(((T - 1 - rr) >> 1) & 1));
+            }
+            if (r.lane == 0) {
+                a.logE[b] = -INFINITY;
+                if (a.alive) a.alive[b] = -1;
+            }
+        }
+        if (raw && r.lane == 0) bulk_wait_all();
+        if (r.lane == 0) ws_pace_done(a, b);
+        trace_end_lane0(a, r.lane);
+    }
+}
+
+}  // namespace blg

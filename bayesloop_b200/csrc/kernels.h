@@ -21,6 +21,11 @@ PassKernel fwd_fast1d_ws_entry(int M, int ML, int nt);
 PassKernel bwd_fast1d_ws_entry(int M, int ML, int nt);
 const int *fast1d_ws_geometries();
 
+// the same kernels with the convolution on FP64 matrix instructions (fast1d_mma.cuh): tpw tiles of 64 cells per compute
+// warp (1..6), nt = 160 (4 compute warps) or 288 (8, tpw >= 4)
+PassKernel fwd_fast1d_mma_entry(int tpw, int nt);
+PassKernel bwd_fast1d_mma_entry(int tpw, int nt);
+
 // generic resident kernels (resident.cuh): nt in {256, 512, 1024}; stream = state in global scratch (1024 threads)
 PassKernel fwd_resident_entry(int nt, bool stream);
 PassKernel bwd_resident_entry(int nt, bool stream);

@@ -93,7 +93,7 @@ CONFIGS = {
 
 # default dispatch of the shapes behind BASELINE.json configs[1] (1-D grid, one GaussianRandomWalk: warp-specialised
 # fused kernels) and configs[2]/[3] (2-D grids beyond one SM's shared memory: cluster-resident kernels)
-EXPECTED_FAMILY = {'poisson_c2_small': 'fast1d_ws', 'poisson_wide_kernels': 'fast1d_ws',
+EXPECTED_FAMILY = {'poisson_c2_small': 'fast1d_mma', 'poisson_wide_kernels': 'fast1d_mma',
                    'poisson_regime': 'resident'}
 
 
