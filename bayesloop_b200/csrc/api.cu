@@ -60,6 +60,7 @@ struct Opts {
     int ws_m = 0, ws_nt = 0; // warp-specialised 1-D kernels: force (cells per thread, threads); 0 = by grid size
     int ws_ml = 0;           // ... cells per thread of the last compute warp (0 = ws_m)
     int ws_even = 0;         // ... same number of cells per thread in every compute warp (no uneven split)
+    int mma_nt = 0;          // ... 288: 8 compute warps per chain where 4 would do (0 = by grid size)
     int no_mma = 0;          // ... convolution with DFMAs (fast1d_ws.cuh) instead of FP64 matrix instructions (fast1d_mma.cuh)
     int ws_pace_every = 4;   // ... chains of an SM publish their step count every N steps (power of two) ...
     int ws_pace_skew = 0;    // ... and hold back when more than this many steps ahead of a peer (0 = no pacing, the
@@ -92,6 +93,7 @@ const OptName kOptNames[] = {
     {"ws_ml", "BLG_WS_ML", &Opts::ws_ml},
     {"ws_even", "BLG_WS_EVEN", &Opts::ws_even},
     {"no_mma", "BLG_NO_MMA", &Opts::no_mma},
+    {"mma_nt", "BLG_MMA_NT", &Opts::mma_nt},
     {"ws_pace_every", "BLG_WS_PACE_EVERY", &Opts::ws_pace_every},
     {"ws_pace_skew", "BLG_WS_PACE_SKEW", &Opts::ws_pace_skew},
 };
@@ -533,13 +535,13 @@ bool fast1d_mma_layout(const blg_plan *pl, const blg_program &pg, bool backward,
     const int ntiles = (d.G + 63) / 64;
     int nt = 160;
     tpw = (ntiles + 3) / 4;
-    if (tpw > 6) {
+    if (tpw > 6 || (pl->opt.mma_nt == 288 && ntiles > 4)) {  // 8 compute warps (two per sub-partition)
         nt = 288;
         tpw = (ntiles + 7) / 8;
-        if (tpw < 4) tpw = 4;
+        if (tpw == 3) tpw = 4;  // compiled: 1, 2 (56 registers, 4 chains per SM), 4, 5, 6 (2 chains per SM)
     }
     if (tpw > 6 || !fwd_fast1d_mma_entry(tpw, nt)) return false;
-    const int halo = (pg.max_radius[0] + 3 + 7) & ~7;  // mma_halo(): multiple of 8
+    const int halo = (pg.max_radius[0] + 7 + 7) & ~7;  // mma_halo(): multiple of 8
     if (halo > d.G) return false;
     a.halo = halo;
     a.Gp = even_up(d.G);
@@ -555,7 +557,7 @@ bool fast1d_mma_layout(const blg_plan *pl, const blg_program &pg, bool backward,
     a.off_tab = -1;
     a.off_w = off;
     a.pg.w_off[0] = 0;
-    a.pg.w_len[0] = even_up(2 * pg.max_radius[0] + 1 + 2 * 12);  // kMmaWPad zeros on both sides
+    a.pg.w_len[0] = even_up(2 * pg.max_radius[0] + 1 + 2 * 16);  // kMmaWPad zeros on both sides
     off += a.pg.w_len[0];
     a.ws_w2 = off;
     a.ws_w2_len = 0;
@@ -808,15 +810,17 @@ int launch_resident(const blg_plan *pl, PassKernel kernel, const PassArgs &a, co
     PassArgs a2 = a;
     if (pl->opt.trace[0]) {  // debugging aid: per-CTA {smid, combo, start, end} (globaltimer ns), dumped as CSV
         // + per warp {convolution, epilogue, barrier cycles, hardware warp id} (warp-specialised forward kernel)
-        CUDA_TRY(cudaMalloc(&trace, (size_t)B * 36 * sizeof(long long)));
-        CUDA_TRY(cudaMemset(trace, 0, (size_t)B * 36 * sizeof(long long)));
+        // + per warp and step (32 steps in the middle of the series) the SM clock at {convolution start, convolution
+        //   issued, epilogue done, barrier passed} (DMMA forward kernel): [B][4 warps][32 steps][4]
+        CUDA_TRY(cudaMalloc(&trace, (size_t)B * (36 + 512) * sizeof(long long)));
+        CUDA_TRY(cudaMemset(trace, 0, (size_t)B * (36 + 512) * sizeof(long long)));
         a2.trace = trace;
     }
     kernel<<<(unsigned)B, lay.nt, lay.bytes, st>>>(a2);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     if (trace) {
-        std::vector<long long> h((size_t)B * 36);
+        std::vector<long long> h((size_t)B * (36 + 512));
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(trace);
@@ -832,6 +836,19 @@ int launch_resident(const blg_plan *pl, PassKernel kernel, const PassArgs &a, co
                 for (int k = 0; k < 32; ++k) fprintf(f, ",%lld", h[4 * B + 32 * i + k]);
                 fprintf(f, "\n");
             }
+            fclose(f);
+        }
+        bool any = false;
+        for (size_t k = (size_t)36 * B; k < h.size() && !any; ++k) any = h[k] != 0;
+        snprintf(path, sizeof path, "%s.%s.%d.events.csv", pl->opt.trace, name, seq - 1);
+        if (FILE *f = any ? fopen(path, "w") : nullptr) {
+            fprintf(f, "block,warp,step,conv_start,conv_issued,epi_done,bar_passed\n");
+            for (long long i = 0; i < B; ++i)
+                for (int w = 0; w < 4; ++w)
+                    for (int q = 0; q < 32; ++q) {
+                        const long long *e = &h[(size_t)36 * B + ((size_t)(i * 4 + w) * 32 + q) * 4];
+                        if (e[0]) fprintf(f, "%lld,%d,%d,%lld,%lld,%lld,%lld\n", i, w, q, e[0], e[1], e[2], e[3]);
+                    }
             fclose(f);
         }
     }

@@ -65,7 +65,8 @@ const int *fast1d_ws_geometries() {
 
 // DMMA kernels (fast1d_mma_inst.cu): tiles of 64 cells per compute warp x threads.  Keep in step with
 // __graft_entry__.MMA_UNITS.
-#define BLG_MMA_ALL(X) X(1, 160) X(2, 160) X(3, 160) X(4, 160) X(5, 160) X(6, 160) X(4, 288) X(5, 288) X(6, 288)
+#define BLG_MMA_ALL(X) \
+    X(1, 160) X(2, 160) X(3, 160) X(4, 160) X(5, 160) X(6, 160) X(1, 288) X(2, 288) X(4, 288) X(5, 288) X(6, 288)
 #define BLG_MMA(TPW, NT)                       \
     PassKernel fwd_fast1d_mma_t##TPW##_nt##NT(); \
     PassKernel bwd_fast1d_mma_t##TPW##_nt##NT();

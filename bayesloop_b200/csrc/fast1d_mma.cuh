@@ -12,16 +12,19 @@
 //
 // The convolution as a matrix product (no reshaping of the problem: the band of a Toeplitz matrix):
 //     y[c] = sum_k w[k] x[c - R + k]            (transitionModels.py:111; reflect boundary = mirrored halo cells)
-//   one 8 x 8 tile of outputs  Y[a][r] = y[tile + 8a + r]  accumulates, per "k-step" s = 4q,
-//     A[a][u] = x[tile + 8a + s + u]   (8 x 4: one LDS.64 per lane),
-//     B[u][r] = w[s + u - r + R]       (4 x 8 Toeplitz block, 0 outside 0..2R; the same for every tile),
-//   over s from 4*floor(-R/4) to 4*floor((R+7)/4): 2R + 11 taps on average instead of 2R + 1 (the 7 extra taps are the
-//   price of sharing one input window between 8 neighbouring outputs).  A compute warp owns TPW tiles (64 cells each),
+//   one 8 x 8 tile of outputs  Y[a][r] = y[tile + 8a + r]  accumulates, per group of 8 input offsets s = 8j .. 8j+7, TWO
+//   instructions (even and odd offsets):
+//     A[a][u] = x[tile + 8a + 8j + 2u (+1)]   (8 x 4: ONE 16-byte LDS per lane feeds both -- 512 contiguous bytes per
+//                                              warp, conflict free in the natural layout, address = pointer + constant),
+//     B[u][r] = w[8j + 2u (+1) - r + R]       (4 x 8 Toeplitz block, 0 outside 0..2R; the same for every tile),
+//   over j from floor(-R/8) to floor((R+7)/8): 2R + 15 taps on average instead of 2R + 1 (7 of the extra taps are the
+//   price of sharing one input window between 8 neighbouring outputs, the rest is the granularity of 8).  A first
+//   version used k-steps of 4 offsets on an XOR-swizzled state (2R + 11 taps): 12 instructions per DMMA, most of them
+//   address arithmetic, issue slots 47 % busy and the matrix pipe 63 % (profiles/r2z_*); here it is ~2 per DMMA.
+//   A compute warp owns TPW tiles (64 cells each),
 //   i.e. a lane owns the cell PAIRS (tile + 8*(lane/4) + 2*(lane%4), +1) of its tiles -- the accumulator fragment of the
 //   instruction -- so likelihood loads, state stores and row stores are 16-byte accesses, 512 contiguous bytes per warp:
 //   the rows go to HBM straight from the registers of the compute warps (no service-warp copy, no bulk store).
-//   The state buffers are XOR-swizzled (cell i lives at i ^ ((i >> 2) & 4): every other 16-cell block has its two
-//   4-cell halves swapped), which makes the 8-rows-by-4 fragment loads conflict free; pairs stay adjacent.
 //
 // Everything else -- roles, lagged scale, one named barrier per step, evidence bookkeeping, alpha ring of the backward
 // pass, zero-norm protocol -- is fast1d_ws.cuh.  Semantics: core.py:372-417, :424-470; transitionModels.py:96-118.
@@ -31,17 +34,18 @@
 
 namespace blg {
 
-constexpr int kMmaWPad = 12;  // zero weights in front of / behind the 2R+1 taps (the Toeplitz blocks reach 10 beyond)
+constexpr int kMmaWPad = 16;  // zero weights in front of / behind the 2R+1 taps (the Toeplitz blocks reach 14 beyond)
 
-__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 2) & 4); }
+__device__ __forceinline__ int swz(int i) { return i; }  // natural layout (an XOR swizzle lived here, see the header)
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    // volatile: keeps the issue order chosen in mma_conv_body (independent accumulators between dependent instructions)
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// halo cells on each side of the state: the k-steps reach R + 3 below the first and R + 10 beyond the last valid cell;
+// halo cells on each side of the state: the groups reach R + 7 below the first and R + 14 beyond the last valid cell;
 // only [-halo, n + halo) holds mirrored values, the rest of the buffer stays zero (read with zero weights only)
-__host__ __device__ __forceinline__ int mma_halo(int R) { return (R + 3 + 7) & ~7; }
+__host__ __device__ __forceinline__ int mma_halo(int R) { return (R + 7 + 7) & ~7; }
 
 // zero-padded weights Wz[k + kMmaWPad] = w[k] (build_weights in common.cuh), normalised; len >= 2R + 1 + 2*kMmaWPad
 __device__ __forceinline__ void mma_build_weights(double *Wz, int len, double sigma, int R, RedScratch &rs) {
@@ -122,33 +126,31 @@ __device__ __forceinline__ MmaRoles mma_roles(int n) {
     return r;
 }
 
-// acc[k] = convolution outputs of the lane's cell pair in tile k (see the header); line = interior pointer of a swizzled
-// state buffer, base[k] = tile_k + 8*(lane/4) + (lane%4), wz = Wz + (lane%4) - (lane/4) + R + kMmaWPad
+// acc[k] = convolution outputs of the lane's cell pair in tile k (see the header); line = interior pointer of a state
+// buffer, base[k] = tile_k + 8*(lane/4) + 2*(lane%4), wz = Wz + 2*(lane%4) - (lane/4) + R + kMmaWPad
 template <int TPW, bool FULL>
 __device__ __forceinline__ void mma_conv_body(const double *__restrict__ line, const int (&base)[TPW], int ntw, int R,
                                               const double *__restrict__ wz, double2 (&acc)[TPW]) {
 #pragma unroll
     for (int k = 0; k < TPW; ++k) acc[k] = make_double2(0.0, 0.0);
-    const int qlo = -((R + 3) >> 2), qhi = (R + 7) >> 2;
-    // software pipeline: the fragments of k-step q+1 are loaded before the matrix instructions of k-step q are issued
-    // (the loads behind the last k-step read 4 cells / weights further, inside the buffers, and are not used)
-    double bw = wz[4 * qlo];
-    double av[TPW];
-#pragma unroll
-    for (int k = 0; k < TPW; ++k) av[k] = (FULL || k < ntw) ? line[swz(base[k] + 4 * qlo)] : 0.0;
+    const int jlo = -((R + 7) >> 3), jhi = (R + 7) >> 3;
+    const double *x0 = line + base[0] + 8 * jlo;  // the tiles of a warp are a compile-time distance apart
+    const double *w = wz + 8 * jlo;
 #pragma unroll 2
-    for (int q = qlo; q <= qhi; ++q) {
-        const int s1 = 4 * q + 4;
-        const double bwn = wz[s1];
-        double avn[TPW];
-#pragma unroll
-        for (int k = 0; k < TPW; ++k) avn[k] = (FULL || k < ntw) ? line[swz(base[k] + s1)] : 0.0;
+    for (int j = jlo; j <= jhi; ++j) {
+        const double b0 = w[0], b1 = w[1];
+        double2 av[TPW];
 #pragma unroll
         for (int k = 0; k < TPW; ++k)
-            if (FULL || k < ntw) dmma884(acc[k].x, acc[k].y, av[k], bw);
-        bw = bwn;
+            if (FULL || k < ntw) av[k] = *reinterpret_cast<const double2 *>(x0 + (base[k] - base[0]));
 #pragma unroll
-        for (int k = 0; k < TPW; ++k) av[k] = avn[k];
+        for (int k = 0; k < TPW; ++k)  // even offsets of every tile, then the odd ones: TPW instructions between
+            if (FULL || k < ntw) dmma884(acc[k].x, acc[k].y, av[k].x, b0);  // two that use the same accumulator
+#pragma unroll
+        for (int k = 0; k < TPW; ++k)
+            if (FULL || k < ntw) dmma884(acc[k].x, acc[k].y, av[k].y, b1);
+        x0 += 8;
+        w += 8;
     }
 }
 
@@ -171,7 +173,7 @@ __device__ __forceinline__ void mma_store_pair(double *line, int c, int n, int h
 
 // ------------------------------------------------------------------------------------------------ K1m forward
 template <int TPW, int NT>
-__global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_mma_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) fwd_fast1d_mma_kernel(const PassArgs a) {
     constexpr int NW = NT / 32, NCW = NW - 1, NCOMP = NCW * 32;
     extern __shared__ __align__(16) double sm[];  // the base of the dynamic window is 1 KB aligned in practice
     const DevProblem &pb = a.pb;
@@ -230,10 +232,10 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_mma_kernel(co
 #pragma unroll
         for (int k = 0; k < TPW; ++k) {
             const int tile = (r.warp + k * NCW) * 64;
-            base[k] = tile + 8 * g8 + u;
+            base[k] = tile + 8 * g8 + 2 * u;
             c0[k] = tile + 8 * g8 + 2 * u;
         }
-        const double *wz = Wz + (u - g8 + R + kMmaWPad);
+        const double *wz = Wz + (2 * u - g8 + R + kMmaWPad);
         double *cur = buf0, *nxt = buf1;
         const double *likp = a.lik_table;
         const long long pitch = a.lik_pitch;
@@ -292,9 +294,18 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_mma_kernel(co
             const long long p2 = prof ? clock64() : 0;
             named_sync(1, NT);  // new state and its partial sums are visible to everybody
             if (prof) {
+                const long long p3 = clock64();
                 cConv += p1 - p0;
                 cEpi += p2 - p1;
-                cBar += clock64() - p2;
+                cBar += p3 - p2;
+                const long long q = t - (T >> 1);  // 32 steps in the middle of the series, per warp: the SM clock
+                if (q >= 0 && q < 32 && r.lane == 0 && r.warp < 4) {
+                    long long *e = a.trace + 36LL * gridDim.x + (((long long)blockIdx.x * 4 + r.warp) * 32 + q) * 4;
+                    e[0] = p0;
+                    e[1] = p1;
+                    e[2] = p2;
+                    e[3] = p3;
+                }
             }
             {   // a zero norm found by the service warp behind the barrier of an EARLIER step ends the chain here
                 const int ds = *deadFlag;
@@ -394,7 +405,7 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) fwd_fast1d_mma_kernel(co
 
 // ------------------------------------------------------------------------------------------------ K2m backward
 template <int TPW, int NT>
-__global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_mma_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) bwd_fast1d_mma_kernel(const PassArgs a) {
     constexpr int NW = NT / 32, NCW = NW - 1, NCOMP = NCW * 32;
     extern __shared__ __align__(16) double sm[];  // the base of the dynamic window is 1 KB aligned in practice
     const DevProblem &pb = a.pb;
@@ -450,10 +461,10 @@ __global__ void __launch_bounds__(NT, NT > 192 ? 2 : 4) bwd_fast1d_mma_kernel(co
 #pragma unroll
         for (int k = 0; k < TPW; ++k) {
             const int tile = (r.warp + k * NCW) * 64;
-            base[k] = tile + 8 * g8 + u;
+            base[k] = tile + 8 * g8 + 2 * u;
             c0[k] = tile + 8 * g8 + 2 * u;
         }
-        const double *wz = Wz + (u - g8 + R + kMmaWPad);
+        const double *wz = Wz + (2 * u - g8 + R + kMmaWPad);
         double *cur = buf0, *nxt = buf1;
         const double *likp = a.lik_table;
         const long long pitch = a.lik_pitch;

@@ -122,10 +122,9 @@ class Program:
 
     def _assignment(self, lo, hi, sms, slots=4):
         """Combos of one call pre-assigned to SMs: longest-processing-time-first into `sms` bins of `slots`
-        entries.  Cost model fitted to a per-CTA trace of the warp-specialised kernels on B200 (tools/trace_c2.py,
-        BLG_TRACE; 1000-cell grid): all CTAs of an SM finish together and the SM's time per step is
-        ~0.08 us per resident CTA + 0.02 us per convolution tap -- the convolution dominates, the fixed per-step
-        work of a chain is hidden by the service warp."""
+        entries.  Cost model fitted to a per-CTA trace of the 1-D kernels on B200 (tools/trace_c2.py, BLG_TRACE;
+        1000-cell grid): an SM's time per step grows with the number of resident chains and with the convolution
+        work of all of them."""
         if hi - lo > sms * slots:
             return None
         key = (lo, hi, sms, slots)
@@ -134,8 +133,10 @@ class Program:
             if memo in _ASSIGNMENTS:  # same sweep fitted again (new data, same hyper-grid): reuse the host table
                 self._orders[key] = self._engine.to_device(_ASSIGNMENTS[memo])
                 return self._orders[key]
-            taps = (2 * self.host['radius'][lo:hi] + 1).sum(axis=1).astype(float)
-            cost = 0.08 + 0.02 * taps
+            # round 2 (DMMA kernels, fast1d_mma.cuh): the convolution costs 2 * ((R + 7) // 8) + 1 groups of matrix
+            # instructions per tile; per-SM trace of a C2 sweep: time ~ 0.17 ms * (chains + groups) per 2000 steps
+            groups = (2 * ((self.host['radius'][lo:hi] + 7) // 8) + 1).sum(axis=1).astype(float)
+            cost = 1.0 + groups
             table = np.full((sms, slots), -1, dtype=np.int32)
             load = np.zeros(sms)
             fill = np.zeros(sms, dtype=np.int64)
