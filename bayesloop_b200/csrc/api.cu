@@ -61,10 +61,10 @@ struct Opts {
     int ws_ml = 0;           // ... cells per thread of the last compute warp (0 = ws_m)
     int ws_even = 0;         // ... same number of cells per thread in every compute warp (no uneven split)
     int mma_nt = 0;          // ... 288: 8 compute warps per chain where 4 would do (0 = by grid size)
+    int il = 0;              // ... the chains of an SM interleaved in one CTA (fast1d_il.cuh; measured slower, opt-in)
     int no_mma = 0;          // ... convolution with DFMAs (fast1d_ws.cuh) instead of FP64 matrix instructions (fast1d_mma.cuh)
     int ws_pace_every = 4;   // ... chains of an SM publish their step count every N steps (power of two) ...
-    int ws_pace_skew = 0;    // ... and hold back when more than this many steps ahead of a peer (0 = no pacing, the
-                             // default: lock-step chains measured no faster, profiles/r2u_ws_pacing.txt)
+    int ws_pace_skew = 8;    // ... and hold back when more than this many steps ahead of a peer (0 = no pacing)
     char trace[256] = {0};   // per-CTA trace files <trace>.<kernel>.<n>.csv (debugging aid)
 };
 
@@ -93,6 +93,7 @@ const OptName kOptNames[] = {
     {"ws_ml", "BLG_WS_ML", &Opts::ws_ml},
     {"ws_even", "BLG_WS_EVEN", &Opts::ws_even},
     {"no_mma", "BLG_NO_MMA", &Opts::no_mma},
+    {"il", "BLG_IL", &Opts::il},
     {"mma_nt", "BLG_MMA_NT", &Opts::mma_nt},
     {"ws_pace_every", "BLG_WS_PACE_EVERY", &Opts::ws_pace_every},
     {"ws_pace_skew", "BLG_WS_PACE_SKEW", &Opts::ws_pace_skew},
@@ -572,6 +573,52 @@ bool fast1d_mma_layout(const blg_plan *pl, const blg_program &pg, bool backward,
     return lay.bytes <= kSmemLimit;
 }
 
+// Interleaved variant (fast1d_il.cuh): one CTA per SM works through the SM's list of up to 4 chains.
+bool fast1d_il_layout(const blg_plan *pl, const blg_inputs *in, bool backward, PassArgs &a, Layout &lay, int &tpw) {
+    const DevProblem &d = pl->dev;
+    const blg_program &pg = in->prog;
+    if (pl->opt.no_fast1d || pl->opt.no_ws || pl->opt.no_mma || !pl->opt.il || pl->opt.force_stream) return false;
+    if (d.ndim != 1 || pg.n_ops != 1 || pg.kind[0] != BLG_OP_GRW || d.G % 2) return false;
+    if (!pg.sm_assign || pg.sm_count != pl->num_sms || pg.sm_slots < 1 || pg.sm_slots > 4 || pl->opt.no_sm_assign) return false;
+    if ((long long)pg.sm_count * pg.sm_slots < in->B) return false;
+    const int ntiles = (d.G + 63) / 64;
+    tpw = (ntiles + 15) / 16;
+    if (tpw > 2 || !(backward ? bwd_fast1d_il_entry(tpw) : fwd_fast1d_il_entry(tpw))) return false;
+    const int halo = (pg.max_radius[0] + 7 + 7) & ~7;  // mma_halo()
+    if (halo > d.G) return false;
+    a.halo = halo;
+    a.Gp = even_up(d.G);
+    a.n0p = even_up(d.n0);
+    a.n1p = 2;
+    a.mma_pitch = halo + 64 * ntiles + halo + 8;
+    int off = 2 * a.mma_pitch;  // offsets inside a chain slot
+    a.off_stage = -1;
+    if (backward) {
+        a.off_stage = off;
+        off += 2 * a.Gp;
+    }
+    a.off_tab = -1;
+    a.off_w = off;
+    a.pg.w_off[0] = 0;
+    a.pg.w_len[0] = even_up(2 * pg.max_radius[0] + 1 + 2 * 16);
+    off += a.pg.w_len[0];
+    a.il_stride = even_up(off);
+    off = 4 * a.il_stride;
+    a.off_misc = off;
+    off += kMiscDoubles;
+    a.ws_part = off;
+    off += 4 * 2 * 3 * 16;  // kIlChains * kIlPP
+    a.il_ctl = off;
+    off += 4 * 8;           // kIlChains * kIlCtlDoubles
+    a.ws_ctl = off;         // mbarriers of the alpha rings (backward): [4 chains][2 slots]
+    off += 8;
+    a.ws_w2 = 0;
+    a.ws_w2_len = 0;
+    lay.bytes = (size_t)off * sizeof(double);
+    lay.nt = 17 * 32;
+    return lay.bytes <= kSmemLimit;
+}
+
 // Stream kernels (grids that do not fit in shared memory): state in global scratch, convolution tiles in smem.
 bool stream_layout(const blg_plan *pl, const blg_program &pg, PassArgs &a, Layout &lay, int chunkM = 0) {
     const DevProblem &d = pl->dev;
@@ -925,6 +972,18 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
         int tpw = 0;
         const bool rowsOk = !store || bulkOk;
         const bool tabOk = pl->dev.om_kind != BLG_OM_TABLE || (uintptr_t)in->lik_table % 16 == 0;
+        if (rowsOk && tabOk && fast1d_il_layout(pl, in, false, a, lay, tpw)) {  // the chains of an SM in one CTA
+            const int rc = prep_lik_table(pl, in, a, st, 0, 0, 0, true);
+            if (rc < 0) return -1;
+            if (rc == 0) {
+                a.use_bulk = bulkOk ? 1 : 0;
+                long long grid = in->B;
+                if (prep_sm_assign(pl, in, a, grid, st)) return -1;
+                return launch_resident(pl, fwd_fast1d_il_entry(tpw), a, lay, a.sm_count, st, "fwd_fast1d_il");
+            }
+            a.pb.om_kind = pl->dev.om_kind;
+            a.lik_table = in->lik_table;
+        }
         if (rowsOk && tabOk && fast1d_mma_layout(pl, in->prog, false, a, lay, tpw)) {
             const int rc = prep_lik_table(pl, in, a, st, 0, 0, 0, true);
             if (rc < 0) return -1;
@@ -1039,6 +1098,18 @@ int blg_backward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uin
     {
         int tpw = 0;
         const bool tabOk = pl->dev.om_kind != BLG_OM_TABLE || (uintptr_t)in->lik_table % 16 == 0;
+        if (alignedRows && !acc && tabOk && fast1d_il_layout(pl, in, true, a, lay, tpw)) {  // the chains of an SM in one CTA
+            const int rc = prep_lik_table(pl, in, a, st, 0, 0, 0, true);
+            if (rc < 0) return -1;
+            if (rc == 0) {
+                a.use_bulk = 1;
+                long long grid = in->B;
+                if (prep_sm_assign(pl, in, a, grid, st)) return -1;
+                return launch_resident(pl, bwd_fast1d_il_entry(tpw), a, lay, a.sm_count, st, "bwd_fast1d_il");
+            }
+            a.pb.om_kind = pl->dev.om_kind;
+            a.lik_table = in->lik_table;
+        }
         if (alignedRows && !acc && tabOk && fast1d_mma_layout(pl, in->prog, true, a, lay, tpw)) {
             const int rc = prep_lik_table(pl, in, a, st, 0, 0, 0, true);
             if (rc < 0) return -1;

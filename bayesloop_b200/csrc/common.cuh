@@ -93,6 +93,7 @@ struct PassArgs {
     // started, INT_MAX: finished) or NULL; a chain holds back while it is more than pace_skew steps ahead of a peer
     int *ws_progress;
     int pace_every, pace_skew;
+    int il_stride, il_ctl;  // interleaved 1-D kernels (fast1d_il.cuh): doubles per chain slot, offset of the control blocks
     int mma_pitch;       // DMMA 1-D kernels (fast1d_mma.cuh): doubles per swizzled state buffer (halo + tiles + halo + 8)
     long long lik_pitch; // row pitch (doubles) of lik_table: G, or M*threads for the owner-order table
     // cluster-resident 2-D kernels (cluster2d.cuh): rows per band, halo rows per side, offsets (doubles) of the state

@@ -89,4 +89,16 @@ PassKernel bwd_fast1d_mma_entry(int tpw, int nt) {
     return nullptr;
 }
 
+// interleaved kernels (fast1d_il_inst.cu): tiles of 64 cells per compute warp and chain (16 compute warps)
+PassKernel fwd_fast1d_il_t1();
+PassKernel fwd_fast1d_il_t2();
+PassKernel bwd_fast1d_il_t1();
+PassKernel bwd_fast1d_il_t2();
+
+PassKernel fwd_fast1d_il_entry(int tpw) { return tpw == 1 ? fwd_fast1d_il_t1() : tpw == 2 ? fwd_fast1d_il_t2() : nullptr; }
+
+PassKernel bwd_fast1d_il_entry(int tpw) {
+    return tpw == 1 ? bwd_fast1d_il_t1() : tpw == 2 ? bwd_fast1d_il_t2() : nullptr;
+}
+
 }  // namespace blg

@@ -26,6 +26,11 @@ const int *fast1d_ws_geometries();
 PassKernel fwd_fast1d_mma_entry(int tpw, int nt);
 PassKernel bwd_fast1d_mma_entry(int tpw, int nt);
 
+// ... and with the chains of an SM interleaved inside one CTA of 16 compute warps + 1 service warp (fast1d_il.cuh):
+// tpw tiles per compute warp and chain (1: grids up to 1024 cells, 2: up to 2048); grid = one CTA per sm_assign list
+PassKernel fwd_fast1d_il_entry(int tpw);
+PassKernel bwd_fast1d_il_entry(int tpw);
+
 // generic resident kernels (resident.cuh): nt in {256, 512, 1024}; stream = state in global scratch (1024 threads)
 PassKernel fwd_resident_entry(int nt, bool stream);
 PassKernel bwd_resident_entry(int nt, bool stream);

@@ -81,6 +81,9 @@ def _gauss2d(bl, engine, n0, n1, T, hb, seed=2):
 CONFIGS = {
     'poisson_c2_small': lambda bl, e: _poisson(bl, e, B=24, T=300, G=1000, smax=0.2),
     'poisson_wide_kernels': lambda bl, e: _poisson(bl, e, B=6, T=60, G=1000, smax=1.0),
+    # more chains than SMs, plan option il = 1: the chains of an SM interleaved inside one CTA (fast1d_il.cuh), 3-4 / 1-2 per SM
+    'poisson_c2_interleaved': lambda bl, e: _poisson(bl, e, B=500, T=70, G=1000, smax=0.2),
+    'poisson_interleaved_small_grid': lambda bl, e: _poisson(bl, e, B=200, T=90, G=200, smax=0.5),
     'poisson_regime': lambda bl, e: _poisson(bl, e, B=8, T=200, G=500, smax=0.1,
                                              extra=lambda bl: bl.tm.RegimeSwitch('p', -5)),
     'poisson_odd_grid': lambda bl, e: _poisson(bl, e, B=5, T=100, G=333, smax=0.3),
@@ -94,7 +97,11 @@ CONFIGS = {
 # default dispatch of the shapes behind BASELINE.json configs[1] (1-D grid, one GaussianRandomWalk: warp-specialised
 # fused kernels) and configs[2]/[3] (2-D grids beyond one SM's shared memory: cluster-resident kernels)
 EXPECTED_FAMILY = {'poisson_c2_small': 'fast1d_mma', 'poisson_wide_kernels': 'fast1d_mma',
+                   'poisson_c2_interleaved': 'fast1d_il', 'poisson_interleaved_small_grid': 'fast1d_il',
                    'poisson_regime': 'resident'}
+
+
+PLAN_OPTIONS = {'poisson_c2_interleaved': {'il': 1}, 'poisson_interleaved_small_grid': {'il': 1}}
 
 
 @pytest.mark.parametrize('name', sorted(CONFIGS))
@@ -102,7 +109,8 @@ EXPECTED_FAMILY = {'poisson_c2_small': 'fast1d_mma', 'poisson_wide_kernels': 'fa
 def test_cuda_matches_cpu_oracle(name, mode, cuda_engine, oracle_engine):
     import bayesloop_b200 as bl
     kw = dict(forwardOnly=(mode == 'forwardOnly'), evidenceOnly=(mode == 'evidenceOnly'))
-    got = helpers.abi_sweep(cuda_engine, CONFIGS[name](bl, cuda_engine), **kw)
+    with cuda_engine.options(**PLAN_OPTIONS.get(name, {})):
+        got = helpers.abi_sweep(cuda_engine, CONFIGS[name](bl, cuda_engine), **kw)
     if name in EXPECTED_FAMILY:  # the kernels that carry the performance claims must be the ones that ran
         assert cuda_engine.last_kernel() == ('bwd_' if mode == 'full' else 'fwd_') + EXPECTED_FAMILY[name]
     want = helpers.abi_sweep(oracle_engine, CONFIGS[name](bl, oracle_engine), **kw)

@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
 # C2 (headline): forward + backward + accumulate of one timed sweep at the bench shape (3 warm-up sweeps skipped)
-ncu --set full --clock-control none --import-source on -k regex:'fast1d_ws|accumulate_kernel' --launch-skip 9 -c 3 \
+ncu --set full --clock-control none --import-source on -k regex:'fast1d_il|fast1d_mma|fast1d_ws|accumulate_kernel' --launch-skip 9 -c 3 \
     -f -o gpurun_out/${TAG}_c2_ws python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${TAG}_ncu_c2.log 2>&1
 # C3: cluster-resident 2-D kernels, 8 x 8 of the hyper-grid, window of 200 steps
 ncu --set full --clock-control none --import-source on -k regex:cluster2d --launch-skip 6 -c 2 \
