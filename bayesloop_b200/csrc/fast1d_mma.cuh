@@ -261,17 +261,23 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) fwd_fast1d_
             const double kappa = t >= 2 ? ctl[t & 1] : 1.0;
             // alpha <- prior * likelihood (core.py:375-382); cells beyond the grid carry lik = 0.  The factor is a power of
             // two and 1 on most steps (the service warp rescales on demand): one multiply per cell
-            if (kappa == 1.0) {
+            // (the test is an integer compare of the high word: an FP64 compare would queue for the FP64 pipe behind the
+            //  matrix instructions of every chain on the sub-partition, like every dependent FP64 level of this epilogue)
+            double ps[TPW];
+            if (__double2hiint(kappa) == 0x3ff00000) {
 #pragma unroll
                 for (int k = 0; k < TPW; ++k) {
-                    v[k].x *= lk[k].x;
-                    v[k].y *= lk[k].y;
+                    const double ax = v[k].x, ay = v[k].y;
+                    v[k].x = ax * lk[k].x;
+                    v[k].y = ay * lk[k].y;
+                    ps[k] = fma(ay, lk[k].y, v[k].x);  // v.x + v.y one level earlier
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < TPW; ++k) {
                     v[k].x *= kappa * lk[k].x;
                     v[k].y *= kappa * lk[k].y;
+                    ps[k] = v[k].x + v[k].y;
                 }
             }
             if (t + 1 < T) {
@@ -279,14 +285,13 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) fwd_fast1d_
                 for (int k = 0; k < TPW; ++k)
                     if (c0[k] < n) lk[k] = __ldg(reinterpret_cast<const double2 *>(likp + (t + 1) * pitch + c0[k]));
             }
-            double ps[TPW];
 #pragma unroll
             for (int k = 0; k < TPW; ++k) {
-                ps[k] = 0.0;
                 if (c0[k] < n) {
                     mma_store_pair(nxt, c0[k], n, halo, v[k]);
                     if (rawRows) __stcs(reinterpret_cast<double2 *>(seq + t * (long long)n + c0[k]), v[k]);
-                    ps[k] = v[k].x + v[k].y;
+                } else {
+                    ps[k] = 0.0;
                 }
             }
             const double part = tree_sum<TPW>(ps);
@@ -499,6 +504,7 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) bwd_fast1d_
             mbar_wait(&bars[sb], (phases >> sb) & 1u);
             phases ^= 1u << sb;
             double *A = S0 + sb * Gp;
+            const bool unit = __double2hiint(kb) == 0x3ff00000;  // integer compare: no FP64 instruction in front of the sweep
             double pspu[TPW], psst[TPW], psql[TPW];
 #pragma unroll
             for (int k = 0; k < TPW; ++k) {
@@ -511,7 +517,7 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) bwd_fast1d_
                     psql[k] = fast_div_pos(pu.x, lk[k].x) + fast_div_pos(pu.y, lk[k].y);  // core.py:463
                     st.x = beta[k].x * lk[k].x;  // beta*likelihood          core.py:467
                     st.y = beta[k].y * lk[k].y;
-                    if (kb != 1.0) {  // power of two, 1 on most steps
+                    if (!unit) {  // power of two, 1 on most steps
                         st.x *= kb;
                         st.y *= kb;
                     }

@@ -41,7 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
-FP64_LANES = 58.5          # tools/micro/dfma_bench.cu on B200: DFMA lanes / clk / SM
+FP64_LANES = 63.8          # tools/micro/dmma_mix_bench.cu on B200: FP64 MACs / clk / SM of mma.m8n8k4.f64 (DFMA: 56.9)
 BYTES_PER_CELL = {'forward': 8.0, 'backward': 16.0, 'accumulate': 8.0}  # algorithmic HBM bytes
 
 
@@ -423,7 +423,8 @@ def sweep_report(wl, m, peak, peak_src, world):
     fp64_peak = FP64_LANES * 148 * 1.965e9 * 2 / 1e12
     flop_pass = 2.0 * T * G * float(m['taps'].sum())
     fp64 = {'peak_tflops': fp64_peak,
-            'peak_source': 'measured: tools/micro/dfma_bench.cu (58.5 DFMA lanes/clk/SM x 148 SMs x 1.965 GHz)',
+            'peak_source': 'measured: tools/micro/dmma_mix_bench.cu (63.8 FP64 MAC/clk/SM with mma.m8n8k4.f64 x 148 SMs x 1.965 GHz; '
+                           'profiles/r2s_dmma_mix.txt)',
             'convolution_flop_per_pass': flop_pass, 'mean_taps': float(m['taps'].mean()) if len(m['taps']) else 0.0,
             'kernels': {name: {'tflops': flop_pass / (v['ms'] * 1e-3) / 1e12,
                                'frac': flop_pass / (v['ms'] * 1e-3) / 1e12 / fp64_peak}

@@ -24,6 +24,8 @@ METRICS = {
     'sm__throughput.avg.pct_of_peak_sustained_elapsed': 'sm_throughput_pct',
     'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active': 'fp64_pipe_pct_of_active',
     'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed': 'fp64_pipe_pct_of_elapsed',
+    # mma.m8n8k4.f64 (DMMA) is counted on the tensor pipe, not on the FP64 pipe
+    'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active': 'dmma_pipe_pct_of_active',
     'smsp__issue_active.avg.pct_of_peak_sustained_active': 'issue_active_pct',
     'sm__warps_active.avg.pct_of_peak_sustained_active': 'warps_active_pct',
     'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed': 'smem_pipe_pct',
