@@ -607,11 +607,11 @@ bool fast1d_il_layout(const blg_plan *pl, const blg_inputs *in, bool backward, P
     a.off_misc = off;
     off += kMiscDoubles;
     a.ws_part = off;
-    off += 4 * 2 * 3 * 16;  // kIlChains * kIlPP
+    off += 4 * 2 * 3 * 16 * 16;  // kIlChains * kIlPP
     a.il_ctl = off;
     off += 4 * 8;           // kIlChains * kIlCtlDoubles
-    a.ws_ctl = off;         // mbarriers of the alpha rings (backward): [4 chains][2 slots]
-    off += 8;
+    a.ws_ctl = off;         // mbarriers: alpha rings (backward) [4 chains][2 slots], then one per chain (step done)
+    off += 12;
     a.ws_w2 = 0;
     a.ws_w2_len = 0;
     lay.bytes = (size_t)off * sizeof(double);

@@ -30,7 +30,8 @@ constexpr int kIlChains = 4;                   // chains interleaved per CTA (= 
 constexpr int kIlCW = 16;                      // compute warps
 constexpr int kIlNT = (kIlCW + 1) * 32;        // + the service warp
 constexpr int kIlCtlDoubles = 8;               // control block per chain, see IlCtl
-constexpr int kIlPP = 2 * 3 * kIlCW;           // partial sums per chain: [2 parities][3 sums][compute warps]
+constexpr int kIlPL = kIlCW * 16;               // partial sums of one kind per chain-step: 16 per compute warp (lane pairs)
+constexpr int kIlPP = 2 * 3 * kIlPL;           // partial sums per chain: [2 parities][3 sums][kIlPL]
 
 // control block of one chain (shared memory, 8 doubles)
 struct IlCtl {
@@ -53,23 +54,45 @@ __device__ __forceinline__ void il_wait_ge(const int *p, int want) {
     __threadfence_block();
 }
 
-// the warp publishes "one more step part done": its earlier shared-memory writes are visible to whoever sees the count
-__device__ __forceinline__ void il_signal(int *p, int lane) {
+// the warp publishes "my part of this step is done": one arrival on the chain's mbarrier (the other compute warps wait
+// on it with mbarrier.try_wait, which suspends the warp instead of spinning in the issue slots of the sub-partition) and
+// one count for the service warp (which may lag more than one phase behind, where a parity wait would be ambiguous)
+__device__ __forceinline__ void il_signal(int *p, uint64_t *bar, int lane) {
     __syncwarp();
     if (lane == 0) {
         __threadfence_block();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
         atomicAdd(p, 1);
     }
+}
+
+// the compute warps leave 16 partial sums each (one shuffle level); the service warp adds the 256 of a chain-step
+// (four independent chains of adds, then the warp reduction)
+__device__ __forceinline__ void il_partial(double *pp, double v, int warp, int lane) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (lane < 16) pp[warp * 16 + lane] = v;
+}
+
+__device__ __forceinline__ double il_reduce(const double *pp, int lane) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int j = 0; j < kIlPL / 32; j += 4) {
+        s0 += pp[j * 32 + lane];
+        s1 += pp[(j + 1) * 32 + lane];
+        s2 += pp[(j + 2) * 32 + lane];
+        s3 += pp[(j + 3) * 32 + lane];
+    }
+    return warp_sum((s0 + s1) + (s2 + s3));
 }
 
 template <int TPW>
 __device__ __forceinline__ void il_conv(const double *__restrict__ line, const int (&base)[TPW], int ntw, int R,
                                         const double *__restrict__ wz, double2 (&acc)[TPW]) {
-    // separate accumulators for the even and the odd offsets of a group: with one tile per warp there is nothing else
-    // between two matrix instructions that use the same accumulator
-    double2 ae[TPW], ao[TPW];
+    // one accumulator per tile: consecutive matrix instructions of a warp depend on each other, the other three warps of
+    // the sub-partition fill the pipe meanwhile (a split into even / odd accumulators costs a dependent FP64 add in the
+    // epilogue, which is what this kernel cannot afford: every dependent FP64 level queues behind the matrix pipe)
 #pragma unroll
-    for (int k = 0; k < TPW; ++k) ae[k] = ao[k] = make_double2(0.0, 0.0);
+    for (int k = 0; k < TPW; ++k) acc[k] = make_double2(0.0, 0.0);
     const int jlo = -((R + 7) >> 3), jhi = (R + 7) >> 3;
     const double *x0 = line + base[0] + 8 * jlo;
     const double *w = wz + 8 * jlo;
@@ -80,15 +103,13 @@ __device__ __forceinline__ void il_conv(const double *__restrict__ line, const i
         for (int k = 0; k < TPW; ++k) {
             if (k < ntw) {
                 const double2 av = *reinterpret_cast<const double2 *>(x0 + (base[k] - base[0]));
-                dmma884(ae[k].x, ae[k].y, av.x, b0);
-                dmma884(ao[k].x, ao[k].y, av.y, b1);
+                dmma884(acc[k].x, acc[k].y, av.x, b0);
+                dmma884(acc[k].x, acc[k].y, av.y, b1);
             }
         }
         x0 += 8;
         w += 8;
     }
-#pragma unroll
-    for (int k = 0; k < TPW; ++k) acc[k] = make_double2(ae[k].x + ao[k].x, ae[k].y + ao[k].y);
 }
 
 // common set-up of both passes: the CTA's chain list, zeroed state buffers, weights; returns the number of list entries
@@ -156,6 +177,11 @@ __global__ void __launch_bounds__(kIlNT, 1) fwd_fast1d_il_kernel(const PassArgs 
     const bool store = !(a.flags & BLG_F_EVIDENCE_ONLY);
     const bool first = (a.flags & BLG_F_TRANSITION_FIRST) != 0;
     const bool rawRows = store && (a.flags & BLG_F_RAW_ALPHA);
+    uint64_t *ready = reinterpret_cast<uint64_t *>(sm + a.ws_ctl) + 2 * kIlChains;  // one mbarrier per chain: 16 arrivals
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < kIlChains; ++c) mbar_init(&ready[c], kIlCW);
+        fence_proxy_async();
+    }
     // initial state of every chain (core.py:363)
     for (int c = 0; c < nc; ++c) {
         const int b = ctl[c].combo;
@@ -210,7 +236,7 @@ __global__ void __launch_bounds__(kIlNT, 1) fwd_fast1d_il_kernel(const PassArgs 
             for (int c = 0; c < kIlChains; ++c) {
                 if (!live[c]) continue;
                 IlCtl &q = ctl[c];
-                if (t >= 1) il_wait_ge(&q.done, kIlCW * (int)t);           // every warp has finished step t-1 of this chain
+                if (t >= 1) mbar_wait(&ready[c], (uint32_t)((t - 1) & 1));  // every warp has finished step t-1 of this chain
                 if (t >= 2) il_wait_ge(&q.svc_done, (int)t - 1);            // ... and the service warp step t-2
                 {
                     const int ds = ld_volatile_s32(&q.dead);
@@ -257,9 +283,8 @@ __global__ void __launch_bounds__(kIlNT, 1) fwd_fast1d_il_kernel(const PassArgs 
                         part += v[k].x + v[k].y;
                     }
                 }
-                part = warp_sum(part);
-                if (lane == 0) PPall[c * kIlPP + (t & 1) * 3 * kIlCW + warp] = part;
-                il_signal(&q.done, lane);
+                il_partial(PPall + c * kIlPP + (int)(t & 1) * 3 * kIlPL, part, warp, lane);  // reduced by the service warp
+                il_signal(&q.done, &ready[c], lane);
             }
 #pragma unroll
             for (int k = 0; k < TPW; ++k) lk[k] = lkn[k];
@@ -290,7 +315,7 @@ __global__ void __launch_bounds__(kIlNT, 1) fwd_fast1d_il_kernel(const PassArgs 
                     if (local && lane < count) local[t0 + lane] = fast_div(myS[c], times_pow2(myPrev[c], myKe[c])) * pb.lc_prod;
                 };
                 il_wait_ge(&q.done, kIlCW * ((int)t + 1));
-                const double st_sum = warp_sum(lane < kIlCW ? PPall[c * kIlPP + (t & 1) * 3 * kIlCW + lane] : 0.0);
+                const double st_sum = il_reduce(PPall + c * kIlPP + (int)(t & 1) * 3 * kIlPL, lane);
                 int keAfter;
                 const double kAfter = ondemand_scale(st_sum, hold[c], keAfter);  // k_{t+2}
                 if (lane == 0) *reinterpret_cast<volatile double *>(&q.kappa[t & 1]) = kAfter;
@@ -374,8 +399,10 @@ __global__ void __launch_bounds__(kIlNT, 1) bwd_fast1d_il_kernel(const PassArgs 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool rawRows = a.row_scale != nullptr;  // BLG_F_RAW_POSTERIOR: rows leave unnormalised + their factor
     const uint32_t rowBytes = (uint32_t)(n * sizeof(double));
+    uint64_t *ready = bars + 2 * kIlChains;  // one mbarrier per chain: 16 arrivals per step
     if (threadIdx.x == 0) {
         for (int j = 0; j < 2 * kIlChains; ++j) mbar_init(&bars[j], 1);
+        for (int c = 0; c < kIlChains; ++c) mbar_init(&ready[c], kIlCW);
         fence_proxy_async();
     }
     __syncthreads();
@@ -423,7 +450,7 @@ __global__ void __launch_bounds__(kIlNT, 1) bwd_fast1d_il_kernel(const PassArgs 
             for (int c = 0; c < kIlChains; ++c) {
                 if (!live[c]) continue;
                 IlCtl &q = ctl[c];
-                if (s >= 1) il_wait_ge(&q.done, kIlCW * (int)s);
+                if (s >= 1) mbar_wait(&ready[c], (uint32_t)((s - 1) & 1));
                 if (s >= 2) il_wait_ge(&q.svc_done, (int)s - 1);
                 {
                     const int ds = ld_volatile_s32(&q.dead);
@@ -482,17 +509,14 @@ __global__ void __launch_bounds__(kIlNT, 1) bwd_fast1d_il_kernel(const PassArgs 
                         sst += st.x + st.y;
                     }
                 }
-                spu = warp_sum(spu);
-                sst = warp_sum(sst);
-                sql = warp_sum(sql);
-                if (lane == 0) {
-                    double *pp = PPall + c * kIlPP + (int)(s & 1) * 3 * kIlCW;
-                    pp[warp] = spu;
-                    pp[kIlCW + warp] = sst;  // sum of the new state (magnitude control only)
-                    pp[2 * kIlCW + warp] = sql;
+                {
+                    double *pp = PPall + c * kIlPP + (int)(s & 1) * 3 * kIlPL;
+                    il_partial(pp, spu, warp, lane);
+                    il_partial(pp + kIlPL, sst, warp, lane);  // sum of the new state (magnitude control only)
+                    il_partial(pp + 2 * kIlPL, sql, warp, lane);
                 }
                 fence_proxy_async();  // alpha * beta in the ring slot is read by the bulk-async row store
-                il_signal(&q.done, lane);
+                il_signal(&q.done, &ready[c], lane);
             }
 #pragma unroll
             for (int k = 0; k < TPW; ++k) lk[k] = lkn[k];
@@ -535,10 +559,10 @@ __global__ void __launch_bounds__(kIlNT, 1) bwd_fast1d_il_kernel(const PassArgs 
                     }
                 };
                 il_wait_ge(&q.done, kIlCW * ((int)s + 1));
-                const double *pp = PPall + c * kIlPP + (int)(s & 1) * 3 * kIlCW;
-                const double spu = warp_sum(lane < kIlCW ? pp[lane] : 0.0);
-                const double sstate = warp_sum(lane < kIlCW ? pp[kIlCW + lane] : 0.0);
-                const double sql = warp_sum(lane < kIlCW ? pp[2 * kIlCW + lane] : 0.0);
+                const double *pp = PPall + c * kIlPP + (int)(s & 1) * 3 * kIlPL;
+                const double spu = il_reduce(pp, lane);
+                const double sstate = il_reduce(pp + kIlPL, lane);
+                const double sql = il_reduce(pp + 2 * kIlPL, lane);
                 int ke;
                 const double kAfter = ondemand_scale(sstate, hold[c], ke);
                 if (lane == 0) *reinterpret_cast<volatile double *>(&q.kappa[s & 1]) = kAfter;  // used by step s+2
