@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kIlNT, 1) bwd_fast1d_il_kernel(const PassArgs 
                         double2 pu, st;
                         pu.x = al.x * beta[k].x;  // posterior ~ alpha*beta   core.py:436
                         pu.y = al.y * beta[k].y;
-                        sql += fast_div_pos(pu.x, lk[k].x) + fast_div_pos(pu.y, lk[k].y);  // core.py:463
+                        sql += fast_div_pos1(pu.x, lk[k].x) + fast_div_pos1(pu.y, lk[k].y);  // core.py:463
                         st.x = beta[k].x * lk[k].x;  // beta*likelihood          core.py:467
                         st.y = beta[k].y * lk[k].y;
                         if (!unit) {

@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) bwd_fast1d_
                     double2 pu, st;
                     pu.x = al.x * beta[k].x;  // posterior ~ alpha*beta   core.py:436
                     pu.y = al.y * beta[k].y;
-                    psql[k] = fast_div_pos(pu.x, lk[k].x) + fast_div_pos(pu.y, lk[k].y);  // core.py:463
+                    psql[k] = fast_div_pos1(pu.x, lk[k].x) + fast_div_pos1(pu.y, lk[k].y);  // core.py:463
                     st.x = beta[k].x * lk[k].x;  // beta*likelihood          core.py:467
                     st.y = beta[k].y * lk[k].y;
                     if (!unit) {  // power of two, 1 on most steps
