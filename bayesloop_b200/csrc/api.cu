@@ -991,7 +991,7 @@ int blg_forward(blg_plan *pl, const blg_inputs *in, const blg_outputs *out, uint
                 a.use_bulk = bulkOk ? 1 : 0;
                 long long grid = in->B;
                 if (prep_sm_assign(pl, in, a, grid, st)) return -1;
-                if (PassKernel k = fwd_fast1d_mma_entry(tpw, lay.nt)) return launch_resident(pl, k, a, lay, grid, st, "fwd_fast1d_mma");
+                if (PassKernel k = fwd_fast1d_mma_entry(tpw, lay.nt, pl->opt.trace[0] != 0)) return launch_resident(pl, k, a, lay, grid, st, "fwd_fast1d_mma");
                 return fail("DMMA forward kernel missing");
             }
         }

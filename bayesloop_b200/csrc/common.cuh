@@ -265,14 +265,22 @@ __device__ __forceinline__ double fast_div_pos(double a, double b) {
 // The same with ONE Newton step on the hardware seed (rcp.approx.ftz.f64, ~2^-20): relative error ~1e-12, two dependent
 // FP64 instructions fewer per cell.  For sum(post / lik), which only feeds the local evidence of the backward pass
 // (core.py:463; the reference's own tests pin it to 5 decimals).
-__device__ __forceinline__ double fast_div_pos1(double a, double b) {
-    const bool small = b < 1e-290;
-    const double x = small ? b * 0x1p600 : b;
+__device__ __forceinline__ double fast_rcp_pos1(double b) {  // 1 / b for b >= 0 (inf for b below ~1e-290: see the caller)
     double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(r, fma(-x, r, 1.0), r);
-    const double q = a * r;
-    return small ? q * 0x1p600 : q;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    return fma(r, fma(-b, r, 1.0), r);
+}
+
+__device__ __forceinline__ double fast_rcp_pos(double b) {  // 1 / b with the range handling of fast_div_pos1
+    if (__double2hiint(b) >= 0x03d00000) return fast_rcp_pos1(b);
+    return fast_rcp_pos1(b * 0x1p600) * 0x1p600;
+}
+
+__device__ __forceinline__ double fast_div_pos1(double a, double b) {
+    // the range test is an INTEGER compare of the high word (b >= 0): FP64 compares and selects would go through the FP64
+    // pipe like the arithmetic; operands below the range of the hardware seed take the rescaled path (rare, divergent)
+    if (__double2hiint(b) >= 0x03d00000) return a * fast_rcp_pos1(b);
+    return a * fast_rcp_pos1(b * 0x1p600) * 0x1p600;
 }
 
 // ------------------------------------------------------------------------------------------------ log-evidence

@@ -67,15 +67,15 @@ const int *fast1d_ws_geometries() {
 // __graft_entry__.MMA_UNITS.
 #define BLG_MMA_ALL(X) \
     X(1, 160) X(2, 160) X(3, 160) X(4, 160) X(5, 160) X(6, 160) X(1, 288) X(2, 288) X(4, 288) X(5, 288) X(6, 288)
-#define BLG_MMA(TPW, NT)                       \
-    PassKernel fwd_fast1d_mma_t##TPW##_nt##NT(); \
+#define BLG_MMA(TPW, NT)                           \
+    PassKernel fwd_fast1d_mma_t##TPW##_nt##NT(bool); \
     PassKernel bwd_fast1d_mma_t##TPW##_nt##NT();
 BLG_MMA_ALL(BLG_MMA)
 #undef BLG_MMA
 
-PassKernel fwd_fast1d_mma_entry(int tpw, int nt) {
+PassKernel fwd_fast1d_mma_entry(int tpw, int nt, bool prof) {
 #define BLG_MMA(TPW, NT) \
-    if (nt == NT && tpw == TPW) return fwd_fast1d_mma_t##TPW##_nt##NT();
+    if (nt == NT && tpw == TPW) return fwd_fast1d_mma_t##TPW##_nt##NT(prof);
     BLG_MMA_ALL(BLG_MMA)
 #undef BLG_MMA
     return nullptr;

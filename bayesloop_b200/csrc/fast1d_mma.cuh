@@ -30,6 +30,8 @@
 // pass, zero-norm protocol -- is fast1d_ws.cuh.  Semantics: core.py:372-417, :424-470; transitionModels.py:96-118.
 #pragma once
 
+#include <type_traits>
+
 #include "fast1d_ws.cuh"
 
 namespace blg {
@@ -172,7 +174,7 @@ __device__ __forceinline__ void mma_store_pair(double *line, int c, int n, int h
 }
 
 // ------------------------------------------------------------------------------------------------ K1m forward
-template <int TPW, int NT>
+template <int TPW, int NT, bool PROF>
 __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) fwd_fast1d_mma_kernel(const PassArgs a) {
     constexpr int NW = NT / 32, NCW = NW - 1, NCOMP = NCW * 32;
     extern __shared__ __align__(16) double sm[];  // the base of the dynamic window is 1 KB aligned in practice
@@ -227,50 +229,62 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) fwd_fast1d_
 
     if (!r.service) {
         // ------------------------------------------------------------------ compute warps
+        // The chains of a sub-partition run their convolutions in a common window and their epilogues in the gap behind it
+        // (DESIGN.md section 6), all at once, on ONE issue port: the gap is as long as the instructions the four warps
+        // execute between their last and their next matrix instruction.  Hence the shape of this loop: the tiles of a
+        // warp sit a compile-time distance apart (one running pointer per array, constant offsets), guards and mirror
+        // stores exist only in the warps / tiles that need them (warp-uniform flags), counters are 32-bit, the trace is a
+        // template parameter.
         const int g8 = r.lane >> 2, u = r.lane & 3;
-        int base[TPW], c0[TPW];
+        constexpr int TS = NCW * 64;  // cells between two tiles of a warp
+        const int c00 = r.warp * 64 + 8 * g8 + 2 * u;  // the lane's cell pair in the warp's first tile
+        int base[TPW];
 #pragma unroll
-        for (int k = 0; k < TPW; ++k) {
-            const int tile = (r.warp + k * NCW) * 64;
-            base[k] = tile + 8 * g8 + 2 * u;
-            c0[k] = tile + 8 * g8 + 2 * u;
-        }
+        for (int k = 0; k < TPW; ++k) base[k] = c00 + k * TS;
+        // warp-uniform: every tile of the warp lies inside the grid, and only its first tile can touch the left halo, only
+        // its last one the right halo (halo <= the distance between two tiles of a warp) -> the short store path
+        const int tileFirst = r.warp * 64, tileLast = (r.warp + (TPW - 1) * NCW) * 64, cLast = c00 + (TPW - 1) * TS;
+        const bool fast = tileLast + 64 <= n && halo <= TS && (TPW == 1 || tileLast - TS + 64 <= n - halo);
+        const bool mirFirst = tileFirst < halo, mirLast = tileLast + 64 > n - halo;
         const double *wz = Wz + (2 * u - g8 + R + kMmaWPad);
-        double *cur = buf0, *nxt = buf1;
-        const double *likp = a.lik_table;
+        double *cur = buf0 + c00, *nxt = buf1 + c00;  // the lane's pair in the first tile of either buffer
         const long long pitch = a.lik_pitch;
+        const double *likq = a.lik_table + c00;      // likelihood row of the NEXT step
+        double *rowp = rawRows ? seq + c00 : nullptr;  // alpha row of this step
         double2 lk[TPW];  // likelihood of the lane's cell pairs, fetched one step ahead
 #pragma unroll
         for (int k = 0; k < TPW; ++k)
-            lk[k] = c0[k] < n ? __ldg(reinterpret_cast<const double2 *>(likp + c0[k])) : make_double2(0.0, 0.0);
-        const bool prof = a.trace != nullptr;
+            lk[k] = base[k] < n ? __ldg(reinterpret_cast<const double2 *>(likq + k * TS)) : make_double2(0.0, 0.0);
+        likq += pitch;
+        const int Ti = (int)T;
         long long cConv = 0, cEpi = 0, cBar = 0;
-        for (long long t = 0; t < T; ++t) {
+        double *pp = PP + r.ct;
+        for (int t = 0; t < Ti; ++t) {
             double2 v[TPW];
-            const bool trans = (t > 0 || first) && (t - 1 >= f_lo) && (t - 1 < f_hi);
-            const long long p0 = prof ? clock64() : 0;
+            const bool trans = (t > 0 || first) && t - 1 >= f_lo && t - 1 < f_hi;
+            // lagged scale k_t: written by the service warp before it arrived at the barrier of step t-1.  A power of two,
+            // 1 on most steps (integer test of the high word: an FP64 compare would queue for the FP64 pipe); read
+            // in front of the convolution, off the gap between two windows
+            const double kappa = t >= 2 ? ctl[t & 1] : 1.0;
+            const bool unit = __double2hiint(kappa) == 0x3ff00000;
+            const long long p0 = PROF ? clock64() : 0;
             if (trans && R > 0) {
-                mma_conv<TPW>(cur, base, r.ntw, R, wz, v);  // transitionModels.py:111
+                mma_conv<TPW>(cur - c00, base, r.ntw, R, wz, v);  // transitionModels.py:111
             } else {
 #pragma unroll
                 for (int k = 0; k < TPW; ++k)
-                    v[k] = c0[k] < n ? *reinterpret_cast<const double2 *>(cur + swz(c0[k])) : make_double2(0.0, 0.0);
+                    v[k] = base[k] < n ? *reinterpret_cast<const double2 *>(cur + k * TS) : make_double2(0.0, 0.0);
             }
-            const long long p1 = prof ? clock64() : 0;
-            // lagged scale k_t: written by the service warp before it arrived at the barrier of step t-1
-            const double kappa = t >= 2 ? ctl[t & 1] : 1.0;
-            // alpha <- prior * likelihood (core.py:375-382); cells beyond the grid carry lik = 0.  The factor is a power of
-            // two and 1 on most steps (the service warp rescales on demand): one multiply per cell
-            // (the test is an integer compare of the high word: an FP64 compare would queue for the FP64 pipe behind the
-            //  matrix instructions of every chain on the sub-partition, like every dependent FP64 level of this epilogue)
+            const long long p1 = PROF ? clock64() : 0;
             double ps[TPW];
-            if (__double2hiint(kappa) == 0x3ff00000) {
+            // alpha <- prior * likelihood (core.py:375-382); cells beyond the grid carry lik = 0
+            if (unit) {
 #pragma unroll
                 for (int k = 0; k < TPW; ++k) {
                     const double ax = v[k].x, ay = v[k].y;
                     v[k].x = ax * lk[k].x;
                     v[k].y = ay * lk[k].y;
-                    ps[k] = fma(ay, lk[k].y, v[k].x);  // v.x + v.y one level earlier
+                    ps[k] = fma(ay, lk[k].y, v[k].x);  // v.x + v.y one dependent level earlier
                 }
             } else {
 #pragma unroll
@@ -280,30 +294,42 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) fwd_fast1d_
                     ps[k] = v[k].x + v[k].y;
                 }
             }
-            if (t + 1 < T) {
+            if (fast) {  // warp-uniform: every tile inside the grid, mirrors at most from the first / the last tile
 #pragma unroll
-                for (int k = 0; k < TPW; ++k)
-                    if (c0[k] < n) lk[k] = __ldg(reinterpret_cast<const double2 *>(likp + (t + 1) * pitch + c0[k]));
-            }
+                for (int k = 0; k < TPW; ++k) {
+                    *reinterpret_cast<double2 *>(nxt + k * TS) = v[k];
+                    if (rawRows) __stcs(reinterpret_cast<double2 *>(rowp + k * TS), v[k]);
+                }
+                if (t + 1 < Ti) {
 #pragma unroll
-            for (int k = 0; k < TPW; ++k) {
-                if (c0[k] < n) {
-                    mma_store_pair(nxt, c0[k], n, halo, v[k]);
-                    if (rawRows) __stcs(reinterpret_cast<double2 *>(seq + t * (long long)n + c0[k]), v[k]);
-                } else {
-                    ps[k] = 0.0;
+                    for (int k = 0; k < TPW; ++k) lk[k] = __ldg(reinterpret_cast<const double2 *>(likq + k * TS));
+                }
+                if (mirFirst && c00 < halo) *reinterpret_cast<double2 *>(nxt - 2 * c00 - 2) = make_double2(v[0].y, v[0].x);
+                if (mirLast && cLast + 2 > n - halo)
+                    *reinterpret_cast<double2 *>(nxt - c00 + 2 * n - 2 - cLast) = make_double2(v[TPW - 1].y, v[TPW - 1].x);
+            } else {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) {
+                    if (base[k] < n) {
+                        mma_store_pair(nxt - c00, base[k], n, halo, v[k]);
+                        if (rawRows) __stcs(reinterpret_cast<double2 *>(rowp + k * TS), v[k]);
+                        if (t + 1 < Ti) lk[k] = __ldg(reinterpret_cast<const double2 *>(likq + k * TS));
+                    } else {
+                        ps[k] = 0.0;
+                    }
                 }
             }
-            const double part = tree_sum<TPW>(ps);
-            PP[(t & 1) * NCOMP + r.ct] = part;
-            const long long p2 = prof ? clock64() : 0;
+            pp[(t & 1) * NCOMP] = tree_sum<TPW>(ps);
+            likq += pitch;
+            if (rawRows) rowp += n;
+            const long long p2 = PROF ? clock64() : 0;
             named_sync(1, NT);  // new state and its partial sums are visible to everybody
-            if (prof) {
+            if (PROF) {
                 const long long p3 = clock64();
                 cConv += p1 - p0;
                 cEpi += p2 - p1;
                 cBar += p3 - p2;
-                const long long q = t - (T >> 1);  // 32 steps in the middle of the series, per warp: the SM clock
+                const int q = t - (Ti >> 1);  // 32 steps in the middle of the series, per warp: the SM clock
                 if (q >= 0 && q < 32 && r.lane == 0 && r.warp < 4) {
                     long long *e = a.trace + 36LL * gridDim.x + (((long long)blockIdx.x * 4 + r.warp) * 32 + q) * 4;
                     e[0] = p0;
@@ -320,7 +346,7 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) fwd_fast1d_
             cur = nxt;
             nxt = tmp;
         }
-        if (prof && r.lane == 0 && r.warp < 8) {
+        if (PROF && r.lane == 0 && r.warp < 8) {
             unsigned wid;
             asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
             long long *w = a.trace + 4 * (long long)gridDim.x + ((long long)blockIdx.x * 8 + r.warp) * 4;
@@ -460,83 +486,109 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) bwd_fast1d_
     const bool rawRows = a.row_scale != nullptr;  // BLG_F_RAW_POSTERIOR: rows leave unnormalised + their factor
 
     if (!r.service) {
-        // ------------------------------------------------------------------ compute warps
+        // ------------------------------------------------------------------ compute warps (lean loop: see the forward kernel)
         const int g8 = r.lane >> 2, u = r.lane & 3;
-        int base[TPW], c0[TPW];
+        constexpr int TS = NCW * 64;  // cells between two tiles of a warp
+        const int c00 = r.warp * 64 + 8 * g8 + 2 * u;
+        int base[TPW];
 #pragma unroll
-        for (int k = 0; k < TPW; ++k) {
-            const int tile = (r.warp + k * NCW) * 64;
-            base[k] = tile + 8 * g8 + 2 * u;
-            c0[k] = tile + 8 * g8 + 2 * u;
-        }
+        for (int k = 0; k < TPW; ++k) base[k] = c00 + k * TS;
+        const int tileFirst = r.warp * 64, tileLast = (r.warp + (TPW - 1) * NCW) * 64, cLast = c00 + (TPW - 1) * TS;
+        const bool full = tileLast + 64 <= n;  // warp-uniform: all tiles of the warp inside the grid
+        const bool fast = full && halo <= TS && (TPW == 1 || tileLast - TS + 64 <= n - halo);
+        const bool mirFirst = tileFirst < halo, mirLast = tileLast + 64 > n - halo;
         const double *wz = Wz + (2 * u - g8 + R + kMmaWPad);
-        double *cur = buf0, *nxt = buf1;
-        const double *likp = a.lik_table;
+        double *cur = buf0 + c00, *nxt = buf1 + c00;
         const long long pitch = a.lik_pitch;
+        const int Ti = (int)T;
+        const double *likq = a.lik_table + (long long)(Ti - 1) * pitch + c00;  // likelihood row fetched next
         uint32_t phases = 0u;  // bit s = parity of the next completion of ring slot s
         double2 beta[TPW];
 #pragma unroll
         for (int k = 0; k < TPW; ++k) {
-            const double v = c0[k] < n ? 1.0 / (double)n : 0.0;  // core.py:424-425
+            const double v = base[k] < n ? 1.0 / (double)n : 0.0;  // core.py:424-425
             beta[k] = make_double2(v, v);
         }
         double2 lk[TPW];
 #pragma unroll
         for (int k = 0; k < TPW; ++k)
-            lk[k] = c0[k] < n ? __ldg(reinterpret_cast<const double2 *>(likp + (T - 1) * pitch + c0[k])) : make_double2(1.0, 1.0);
-        for (long long i = T - 1; i >= 0; --i) {
-            const int sb = (int)(i & 1);
-            if (i < T - 1) {
+            lk[k] = base[k] < n ? __ldg(reinterpret_cast<const double2 *>(likq + k * TS)) : make_double2(1.0, 1.0);
+        likq -= pitch;
+        double *pp = PP + r.ct;
+        double *const S0c = S0 + c00;
+        for (int i = Ti - 1; i >= 0; --i) {
+            const int sb = i & 1;
+            if (i < Ti - 1) {
                 const bool trans = (i + 1 >= b_lo) && (i + 1 < b_hi);
                 if (trans && R > 0) {
-                    mma_conv<TPW>(cur, base, r.ntw, R, wz, beta);  // transitionModels.py:117-118
+                    mma_conv<TPW>(cur - c00, base, r.ntw, R, wz, beta);  // transitionModels.py:117-118
                 } else {
 #pragma unroll
                     for (int k = 0; k < TPW; ++k)
-                        if (c0[k] < n) beta[k] = *reinterpret_cast<const double2 *>(cur + swz(c0[k]));
+                        if (base[k] < n) beta[k] = *reinterpret_cast<const double2 *>(cur + k * TS);
                 }
+                if (!full) {
 #pragma unroll
-                for (int k = 0; k < TPW; ++k)
-                    if (c0[k] >= n) beta[k] = make_double2(0.0, 0.0);
+                    for (int k = 0; k < TPW; ++k)
+                        if (base[k] >= n) beta[k] = make_double2(0.0, 0.0);
+                }
             }
-            // keeps the (scale-free) beta recursion in range: lagged power of sum(beta) two steps back (see lagged_scale)
-            const double kb = i <= T - 3 ? ctl[i & 1] : 1.0;
+            // keeps the (scale-free) beta recursion in range: a power of two, 1 on most steps (ondemand_scale)
+            const double kb = i <= Ti - 3 ? ctl[i & 1] : 1.0;
+            const bool unit = __double2hiint(kb) == 0x3ff00000;  // integer compare: no FP64 instruction in front of the sweep
             mbar_wait(&bars[sb], (phases >> sb) & 1u);
             phases ^= 1u << sb;
-            double *A = S0 + sb * Gp;
-            const bool unit = __double2hiint(kb) == 0x3ff00000;  // integer compare: no FP64 instruction in front of the sweep
-            double pspu[TPW], psst[TPW], psql[TPW];
-#pragma unroll
-            for (int k = 0; k < TPW; ++k) {
-                pspu[k] = psst[k] = psql[k] = 0.0;
-                if (c0[k] < n) {
-                    const double2 al = *reinterpret_cast<const double2 *>(A + c0[k]);
-                    double2 pu, st;
-                    pu.x = al.x * beta[k].x;  // posterior ~ alpha*beta   core.py:436
-                    pu.y = al.y * beta[k].y;
-                    psql[k] = fast_div_pos1(pu.x, lk[k].x) + fast_div_pos1(pu.y, lk[k].y);  // core.py:463
-                    st.x = beta[k].x * lk[k].x;  // beta*likelihood          core.py:467
-                    st.y = beta[k].y * lk[k].y;
-                    if (!unit) {  // power of two, 1 on most steps
-                        st.x *= kb;
-                        st.y *= kb;
-                    }
-                    *reinterpret_cast<double2 *>(A + c0[k]) = pu;
-                    mma_store_pair(nxt, c0[k], n, halo, st);
-                    pspu[k] = pu.x + pu.y;
-                    psst[k] = st.x + st.y;
+            double *A = S0c + sb * Gp;  // alpha[i], the lane's pair of the first tile
+            // tile by tile with three running sums (few live registers: the gap between two convolution windows is
+            // issue bound, spills and register moves are instructions too)
+            double spu = 0.0, sst = 0.0, sql = 0.0;
+            // one tile: posterior product into the ring slot, new state (+ mirrors), the three sums, next likelihood
+            auto tile = [&](int k, auto fastPath) {
+                constexpr bool FAST = decltype(fastPath)::value;
+                const double2 al = *reinterpret_cast<const double2 *>(A + k * TS);
+                double2 pu, st;
+                pu.x = al.x * beta[k].x;  // posterior ~ alpha*beta   core.py:436
+                pu.y = al.y * beta[k].y;
+                *reinterpret_cast<double2 *>(A + k * TS) = pu;
+                st.x = beta[k].x * lk[k].x;  // beta*likelihood          core.py:467
+                st.y = beta[k].y * lk[k].y;
+                if (!unit) {
+                    st.x *= kb;
+                    st.y *= kb;
                 }
-            }
-            const double spu = tree_sum<TPW>(pspu), sst = tree_sum<TPW>(psst), sql = tree_sum<TPW>(psql);
-            if (i > 0) {
+                if (FAST) {  // mirrors at most from the first / the last tile of the warp
+                    *reinterpret_cast<double2 *>(nxt + k * TS) = st;
+                    if (k == 0 && mirFirst && c00 < halo) *reinterpret_cast<double2 *>(nxt - 2 * c00 - 2) = make_double2(st.y, st.x);
+                    if (k == TPW - 1 && mirLast && cLast + 2 > n - halo)
+                        *reinterpret_cast<double2 *>(nxt - c00 + 2 * n - 2 - cLast) = make_double2(st.y, st.x);
+                } else {
+                    mma_store_pair(nxt - c00, base[k], n, halo, st);
+                }
+                // sum(post / lik), core.py:463.  Likelihoods inside the range of the hardware reciprocal seed (all but
+                // pathological rows; warp-uniform test on the high words) take two Newton-corrected reciprocals
+                // (the vote needs the whole warp: short path only, where no lane is masked off)
+                const int lo = min(__double2hiint(lk[k].x), __double2hiint(lk[k].y));
+                if (FAST && !__any_sync(0xffffffffu, lo < 0x03d00000))
+                    sql += fma(pu.y, fast_rcp_pos1(lk[k].y), pu.x * fast_rcp_pos1(lk[k].x));
+                else
+                    sql += fast_div_pos(pu.x, lk[k].x) + fast_div_pos(pu.y, lk[k].y);
+                spu += pu.x + pu.y;
+                sst += st.x + st.y;
+                if (i > 0) lk[k] = __ldg(reinterpret_cast<const double2 *>(likq + k * TS));
+            };
+            if (fast) {  // warp-uniform
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) tile(k, std::true_type{});
+            } else {
 #pragma unroll
                 for (int k = 0; k < TPW; ++k)
-                    if (c0[k] < n) lk[k] = __ldg(reinterpret_cast<const double2 *>(likp + (i - 1) * pitch + c0[k]));
+                    if (base[k] < n) tile(k, std::false_type{});
             }
-            double *pp = PP + sb * 3 * NCOMP;
-            pp[r.ct] = spu;
-            pp[NCOMP + r.ct] = sst;  // sum of the new state (magnitude control only)
-            pp[2 * NCOMP + r.ct] = sql;
+            likq -= pitch;
+            double *q = pp + sb * 3 * NCOMP;
+            q[0] = spu;
+            q[NCOMP] = sst;  // sum of the new state (magnitude control only)
+            q[2 * NCOMP] = sql;
             if (rawRows) fence_proxy_async();  // alpha * beta in the ring slot is read by the bulk-async row store
             named_sync(1, NT);
             {
@@ -575,6 +627,12 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) bwd_fast1d_
             ws_pace(pace, b, done, r.lane);
             named_sync(1, NT);
             if (dead) break;
+            double *row = seq + i * (long long)n;
+            double *P = S0 + sb * Gp;
+            if (raw && r.lane == 0) {  // the unnormalised row leaves first: the copy engine reads the slot while this warp adds
+                fence_proxy_async();
+                bulk_store(row, P, rowBytes);
+            }
             double spu = 0.0, sstate = 0.0, sql = 0.0;
             const double *pp = PP + sb * 3 * NCOMP;
 #pragma unroll
@@ -600,14 +658,7 @@ __global__ void __launch_bounds__(NT, (NT > 192 && TPW > 2) ? 2 : 4) bwd_fast1d_
                 mySql = sql;
             }
             if ((done & 31) == 31 || i == 0) flush(i, (int)(done & 31) + 1);
-            double *row = seq + i * (long long)n;
-            double *P = S0 + sb * Gp;
-            if (raw) {
-                if (r.lane == 0) {
-                    fence_proxy_async();
-                    bulk_store(row, P, rowBytes);
-                }
-            } else {
+            if (!raw) {
                 const double inv = fast_rcp(spu);
                 for (int j = 2 * r.lane; j < n; j += 64) {
                     double2 x = *reinterpret_cast<const double2 *>(P + j);

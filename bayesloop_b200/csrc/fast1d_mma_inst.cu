@@ -15,7 +15,10 @@ namespace blg {
 #if BLG_INST_BWD
 PassKernel BLG_CAT4(bwd_fast1d_mma_t, BLG_INST_TPW, _nt, BLG_INST_NT)() { return bwd_fast1d_mma_kernel<BLG_INST_TPW, BLG_INST_NT>; }
 #else
-PassKernel BLG_CAT4(fwd_fast1d_mma_t, BLG_INST_TPW, _nt, BLG_INST_NT)() { return fwd_fast1d_mma_kernel<BLG_INST_TPW, BLG_INST_NT>; }
+// prof: per-warp phase counters and the per-step event trace into PassArgs::trace (plan option trace)
+PassKernel BLG_CAT4(fwd_fast1d_mma_t, BLG_INST_TPW, _nt, BLG_INST_NT)(bool prof) {
+    return prof ? fwd_fast1d_mma_kernel<BLG_INST_TPW, BLG_INST_NT, true> : fwd_fast1d_mma_kernel<BLG_INST_TPW, BLG_INST_NT, false>;
+}
 #endif
 
 }  // namespace blg

@@ -23,7 +23,7 @@ const int *fast1d_ws_geometries();
 
 // the same kernels with the convolution on FP64 matrix instructions (fast1d_mma.cuh): tpw tiles of 64 cells per compute
 // warp (1..6), nt = 160 (4 compute warps) or 288 (8, tpw >= 4)
-PassKernel fwd_fast1d_mma_entry(int tpw, int nt);
+PassKernel fwd_fast1d_mma_entry(int tpw, int nt, bool prof = false);
 PassKernel bwd_fast1d_mma_entry(int tpw, int nt);
 
 // ... and with the chains of an SM interleaved inside one CTA of 16 compute warps + 1 service warp (fast1d_il.cuh):
