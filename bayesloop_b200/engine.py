@@ -227,6 +227,7 @@ class Engine:
         self._pinned = {}
         self._plans = collections.OrderedDict()  # problem signature -> Plan (scratch and tables stay allocated)
         self._options = {}  # dispatch options applied to every plan this engine creates (blg_plan_set_option)
+        self._free_probe = None  # (torch reservation, driver-reported free bytes) of the last cudaMemGetInfo
 
     # ---------------------------------------------------------------------------------------------- memory
     def to_device(self, array, pinned=False):
@@ -272,8 +273,13 @@ class Engine:
         using it (the buffers of the previous fit live there: without them a second fit in the same process would size
         its waves for a nearly full device)."""
         if self.device.type == 'cuda':
-            cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
-            return torch.cuda.mem_get_info(self.device)[0] + max(0, cached)
+            reserved = torch.cuda.memory_reserved(self.device)
+            cached = reserved - torch.cuda.memory_allocated(self.device)
+            # cudaMemGetInfo costs 2 - 20 ms with tens of GB allocated (tools/e2e_breakdown.py: the largest host-side item
+            # of a repeated fit): the driver's figure is only asked again when torch's reservation has changed
+            if self._free_probe is None or self._free_probe[0] != reserved:
+                self._free_probe = (reserved, torch.cuda.mem_get_info(self.device)[0])
+            return self._free_probe[1] + max(0, cached)
         return 8 << 30
 
     def stream(self):
