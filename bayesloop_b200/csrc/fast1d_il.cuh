@@ -93,11 +93,11 @@ __device__ __forceinline__ void il_conv(const double *__restrict__ line, const i
     // epilogue, which is what this kernel cannot afford: every dependent FP64 level queues behind the matrix pipe)
 #pragma unroll
     for (int k = 0; k < TPW; ++k) acc[k] = make_double2(0.0, 0.0);
-    const int jlo = -((R + 7) >> 3), jhi = (R + 7) >> 3;
-    const double *x0 = line + base[0] + 8 * jlo;
-    const double *w = wz + 8 * jlo;
+    const int s0 = -(R + (R & 1)), groups = (2 * R + 15 + (R & 1)) >> 3;  // see mma_conv_body
+    const double *x0 = line + base[0] + s0;
+    const double *w = wz + s0;
 #pragma unroll 4
-    for (int j = jlo; j <= jhi; ++j) {
+    for (int j = 0; j < groups; ++j) {
         const double b0 = w[0], b1 = w[1];
 #pragma unroll
         for (int k = 0; k < TPW; ++k) {
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kIlNT, 1) fwd_fast1d_il_kernel(const PassArgs 
 #pragma unroll
         for (int c = 0; c < kIlChains; ++c) {
             live[c] = c < nc && ctl[c].R >= 0;
-            if (live[c]) est += (2 * ((ctl[c].R + 7) >> 3) + 1) * 128 * TPW + 500;
+            if (live[c]) est += ((2 * ctl[c].R + 15 + (ctl[c].R & 1)) >> 3) * 128 * TPW + 500;
         }
         {   // the four warps of a sub-partition (warp mod 4) start a quarter of a round apart
             const long long until = clock64() + (long long)(warp >> 2) * (est >> 2);
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(kIlNT, 1) bwd_fast1d_il_kernel(const PassArgs 
         for (int c = 0; c < kIlChains; ++c) {
             live[c] = c < nc && ctl[c].R >= 0;
             phases[c] = 0u;
-            if (live[c]) est += (2 * ((ctl[c].R + 7) >> 3) + 1) * 128 * TPW + 700;
+            if (live[c]) est += ((2 * ctl[c].R + 15 + (ctl[c].R & 1)) >> 3) * 128 * TPW + 700;
         }
         {   // the four warps of a sub-partition (warp mod 4) start a quarter of a round apart
             const long long until = clock64() + (long long)(warp >> 2) * (est >> 2);

@@ -17,8 +17,8 @@
 //     A[a][u] = x[tile + 8a + 8j + 2u (+1)]   (8 x 4: ONE 16-byte LDS per lane feeds both -- 512 contiguous bytes per
 //                                              warp, conflict free in the natural layout, address = pointer + constant),
 //     B[u][r] = w[8j + 2u (+1) - r + R]       (4 x 8 Toeplitz block, 0 outside 0..2R; the same for every tile),
-//   over j from floor(-R/8) to floor((R+7)/8): 2R + 15 taps on average instead of 2R + 1 (7 of the extra taps are the
-//   price of sharing one input window between 8 neighbouring outputs, the rest is the granularity of 8).  A first
+//   over ceil((2R + 8) / 8) groups starting at offset -R: 2R + 11.5 taps on average instead of 2R + 1 (7 of the extra
+//   taps are the price of sharing one input window between 8 neighbouring outputs, the rest is the granularity of 8).  A first
 //   version used k-steps of 4 offsets on an XOR-swizzled state (2R + 11 taps): 12 instructions per DMMA, most of them
 //   address arithmetic, issue slots 47 % busy and the matrix pipe 63 % (profiles/r2z_*); here it is ~2 per DMMA.
 //   A compute warp owns TPW tiles (64 cells each),
@@ -135,11 +135,14 @@ __device__ __forceinline__ void mma_conv_body(const double *__restrict__ line, c
                                               const double *__restrict__ wz, double2 (&acc)[TPW]) {
 #pragma unroll
     for (int k = 0; k < TPW; ++k) acc[k] = make_double2(0.0, 0.0);
-    const int jlo = -((R + 7) >> 3), jhi = (R + 7) >> 3;
-    const double *x0 = line + base[0] + 8 * jlo;  // the tiles of a warp are a compile-time distance apart
-    const double *w = wz + 8 * jlo;
+    // the 8 outputs of a fragment row need the input offsets -R .. R+7: groups of 8 starting at the (even) offset
+    // s0 = -R or -R-1, ceil((2R + 8 + (R & 1)) / 8) of them -- half a group fewer on average than groups aligned at
+    // multiples of 8 (2 ceil(R/8) + 1)
+    const int s0 = -(R + (R & 1)), groups = (2 * R + 15 + (R & 1)) >> 3;
+    const double *x0 = line + base[0] + s0;  // the tiles of a warp are a compile-time distance apart
+    const double *w = wz + s0;
 #pragma unroll 2
-    for (int j = jlo; j <= jhi; ++j) {
+    for (int j = 0; j < groups; ++j) {
         const double b0 = w[0], b1 = w[1];
         double2 av[TPW];
 #pragma unroll

@@ -133,9 +133,10 @@ class Program:
             if memo in _ASSIGNMENTS:  # same sweep fitted again (new data, same hyper-grid): reuse the host table
                 self._orders[key] = self._engine.to_device(_ASSIGNMENTS[memo])
                 return self._orders[key]
-            # round 2 (DMMA kernels, fast1d_mma.cuh): the convolution costs 2 * ((R + 7) // 8) + 1 groups of matrix
+            # round 2 (DMMA kernels, fast1d_mma.cuh): the convolution costs ceil((2R + 8 + (R & 1)) / 8) groups of matrix
             # instructions per tile; per-SM trace of a C2 sweep: time ~ 0.17 ms * (chains + groups) per 2000 steps
-            groups = (2 * ((self.host['radius'][lo:hi] + 7) // 8) + 1).sum(axis=1).astype(float)
+            rad = self.host['radius'][lo:hi]
+            groups = ((2 * rad + 15 + (rad & 1)) // 8).sum(axis=1).astype(float)
             cost = 1.0 + groups
             table = np.full((sms, slots), -1, dtype=np.int32)
             load = np.zeros(sms)
