@@ -1,7 +1,7 @@
 // fast1d_mma.cuh -- K1m/K2m: the warp-specialised fast 1-D kernels (fast1d_ws.cuh) with the GaussianRandomWalk
 // convolution issued as FP64 matrix instructions (mma.sync.m8n8k4.f64, "DMMA").
 //
-// Why (B200, profiles/r2s_dmma_mix.txt, r2v_regions.txt): the convolution is FP64-FMA work on either path -- DMMA and DFMA
+// Why (B200, profiles/r2s_dmma_mix.txt, r2v_regions_c2_ws.txt): the convolution is FP64-FMA work on either path -- DMMA and DFMA
 // share the FP64 units (a mix of the two never exceeds the faster one) -- but
 //   * a warp of DFMAs reaches 54-57 MAC/clk/SM in isolation, DMMA 63.8 (the full 64 lanes), and
 //   * in the real kernel the DFMA loop keeps the pipe only ~62 % busy: with 3-4 compute warps per SM sub-partition the
@@ -12,22 +12,23 @@
 //
 // The convolution as a matrix product (no reshaping of the problem: the band of a Toeplitz matrix):
 //     y[c] = sum_k w[k] x[c - R + k]            (transitionModels.py:111; reflect boundary = mirrored halo cells)
-//   one 8 x 8 tile of outputs  Y[a][r] = y[tile + 8a + r]  accumulates, per group of 8 input offsets s = 8j .. 8j+7, TWO
-//   instructions (even and odd offsets):
-//     A[a][u] = x[tile + 8a + 8j + 2u (+1)]   (8 x 4: ONE 16-byte LDS per lane feeds both -- 512 contiguous bytes per
-//                                              warp, conflict free in the natural layout, address = pointer + constant),
-//     B[u][r] = w[8j + 2u (+1) - r + R]       (4 x 8 Toeplitz block, 0 outside 0..2R; the same for every tile),
-//   over ceil((2R + 8) / 8) groups starting at offset -R: 2R + 11.5 taps on average instead of 2R + 1 (7 of the extra
-//   taps are the price of sharing one input window between 8 neighbouring outputs, the rest is the granularity of 8).  A first
-//   version used k-steps of 4 offsets on an XOR-swizzled state (2R + 11 taps): 12 instructions per DMMA, most of them
-//   address arithmetic, issue slots 47 % busy and the matrix pipe 63 % (profiles/r2z_*); here it is ~2 per DMMA.
-//   A compute warp owns TPW tiles (64 cells each),
-//   i.e. a lane owns the cell PAIRS (tile + 8*(lane/4) + 2*(lane%4), +1) of its tiles -- the accumulator fragment of the
-//   instruction -- so likelihood loads, state stores and row stores are 16-byte accesses, 512 contiguous bytes per warp:
-//   the rows go to HBM straight from the registers of the compute warps (no service-warp copy, no bulk store).
+//   one 8 x 8 tile of outputs  Y[a][r] = y[tile + 8a + r]  accumulates, per group of 8 input offsets s = s0 + 8j .. + 7
+//   (s0 = -R rounded down to an even number), TWO instructions (even and odd offsets):
+//     A[a][u] = x[tile + 8a + s0 + 8j + 2u (+1)]   (8 x 4: ONE 16-byte LDS per lane feeds both -- 512 contiguous bytes per
+//                                                   warp, conflict free, address = running pointer + constant),
+//     B[u][r] = w[s0 + 8j + 2u (+1) - r + R]       (4 x 8 Toeplitz block, 0 outside 0..2R; the same for every tile),
+//   over ceil((2R + 8) / 8) groups (the 8 outputs of a row need the offsets -R .. R+7): 2R + 11.5 taps on average
+//   instead of 2R + 1 -- 7 of the extra taps are the price of sharing one input window between 8 neighbouring outputs,
+//   the rest is the granularity of 8.  A first version used k-steps of 4 offsets on an XOR-swizzled state (2R + 11
+//   taps): 12 instructions per DMMA, most of them address arithmetic, issue slots 47 % busy and the matrix pipe 63 %
+//   (profiles/r2_dmma_variants.txt); here it is ~2 per DMMA and the pipe 75 % busy in the forward pass.
+//   A compute warp owns TPW tiles (64 cells each, a compile-time distance apart), i.e. a lane owns the cell PAIRS
+//   (tile + 8*(lane/4) + 2*(lane%4), +1) of its tiles -- the accumulator fragment of the instruction -- so likelihood
+//   loads, state stores and row stores are 16-byte accesses, 512 contiguous bytes per warp: the forward rows go to HBM
+//   straight from the registers of the compute warps (no service-warp copy, no bulk store).
 //
-// Everything else -- roles, lagged scale, one named barrier per step, evidence bookkeeping, alpha ring of the backward
-// pass, zero-norm protocol -- is fast1d_ws.cuh.  Semantics: core.py:372-417, :424-470; transitionModels.py:96-118.
+// Roles, one named barrier per step, alpha ring of the backward pass and zero-norm protocol are those of fast1d_ws.cuh;
+// the service warp is lean (see below), the chains of an SM are paced (ws_pace).  Semantics: core.py:372-417, :424-470; transitionModels.py:96-118.
 #pragma once
 
 #include <type_traits>
