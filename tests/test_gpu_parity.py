@@ -84,6 +84,10 @@ CONFIGS = {
     # more chains than SMs, plan option il = 1: the chains of an SM interleaved inside one CTA (fast1d_il.cuh), 3-4 / 1-2 per SM
     'poisson_c2_interleaved': lambda bl, e: _poisson(bl, e, B=500, T=70, G=1000, smax=0.2),
     'poisson_interleaved_small_grid': lambda bl, e: _poisson(bl, e, B=200, T=90, G=200, smax=0.5),
+    # the other geometries of the DMMA kernels: 6 tiles per warp (4 compute warps), 8 compute warps x 4 tiles, 1 tile per warp
+    'poisson_grid_1500': lambda bl, e: _poisson(bl, e, B=5, T=40, G=1500, smax=0.3),
+    'poisson_grid_2000': lambda bl, e: _poisson(bl, e, B=5, T=40, G=2000, smax=0.4),
+    'poisson_grid_250': lambda bl, e: _poisson(bl, e, B=7, T=60, G=250, smax=0.6),
     'poisson_regime': lambda bl, e: _poisson(bl, e, B=8, T=200, G=500, smax=0.1,
                                              extra=lambda bl: bl.tm.RegimeSwitch('p', -5)),
     'poisson_odd_grid': lambda bl, e: _poisson(bl, e, B=5, T=100, G=333, smax=0.3),
@@ -98,6 +102,7 @@ CONFIGS = {
 # fused kernels) and configs[2]/[3] (2-D grids beyond one SM's shared memory: cluster-resident kernels)
 EXPECTED_FAMILY = {'poisson_c2_small': 'fast1d_mma', 'poisson_wide_kernels': 'fast1d_mma',
                    'poisson_c2_interleaved': 'fast1d_il', 'poisson_interleaved_small_grid': 'fast1d_il',
+                   'poisson_grid_1500': 'fast1d_mma', 'poisson_grid_2000': 'fast1d_mma', 'poisson_grid_250': 'fast1d_mma',
                    'poisson_regime': 'resident'}
 
 
