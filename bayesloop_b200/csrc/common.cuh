@@ -271,11 +271,6 @@ __device__ __forceinline__ double fast_rcp_pos1(double b) {  // 1 / b for b >= 0
     return fma(r, fma(-b, r, 1.0), r);
 }
 
-__device__ __forceinline__ double fast_rcp_pos(double b) {  // 1 / b with the range handling of fast_div_pos1
-    if (__double2hiint(b) >= 0x03d00000) return fast_rcp_pos1(b);
-    return fast_rcp_pos1(b * 0x1p600) * 0x1p600;
-}
-
 __device__ __forceinline__ double fast_div_pos1(double a, double b) {
     // the range test is an INTEGER compare of the high word (b >= 0): FP64 compares and selects would go through the FP64
     // pipe like the arithmetic; operands below the range of the hardware seed take the rescaled path (rare, divergent)
