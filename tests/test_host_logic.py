@@ -207,3 +207,27 @@ def test_prefix_sharing_only_where_the_history_is_erased(use_oracle):
     assert structure(bl.tm.CombinedTransitionModel(bl.tm.Independent(), grw('s', [0.1, 0.2, 0.3, 0.4], target='rate')),
                      cls=bl.HyperStudy) is None
     assert structure(grw('s', [0.1, 0.2, 0.3, 0.4], target='rate'), cls=bl.HyperStudy) is None
+
+
+def test_sm_assignment_table_of_a_c2_like_sweep(oracle_engine):
+    """Program._assignment: the per-SM chain lists of the 1-D kernels (blg_program.sm_assign).  Every combo exactly once,
+    at most 4 per SM, filled slots form a prefix of every list (the interleaved kernel reads them in order), and the
+    predicted cost (chains + DMMA groups, engine.py) is level to a few per cent for the sigma sweep of BASELINE configs[1]."""
+    import numpy as np
+    from bayesloop_b200.engine import Program
+    B, sms = 512, 148
+    sigma_n = np.linspace(0, 0.2, B) / (12.0 / 1001)  # cint(0, 0.2, 512) on oint(0, 12, 1000)
+    radius = (4.0 * sigma_n + 0.5).astype(np.int32)
+    ops = [dict(kind=1, axis=0, param=sigma_n, radius=radius, window=np.tile(np.array([0, 1 << 30, 0, 1 << 30], np.int32), (B, 1)))]
+    prog = Program(oracle_engine, ops, B)
+    table = prog._assignment(0, B, sms).cpu().numpy()
+    assert table.shape == (sms, 4)
+    used = table[table >= 0]
+    assert sorted(used.tolist()) == list(range(B))
+    for row in table:
+        filled = np.flatnonzero(row >= 0)
+        assert list(filled) == list(range(len(filled)))
+    groups = (2 * radius + 15 + (radius & 1)) // 8
+    cost = np.array([sum(1.0 + groups[b] for b in row if b >= 0) for row in table])
+    assert cost.max() <= 1.06 * cost.mean()
+    assert prog._assignment(0, B, sms // 4) is None  # more combos than 4 per SM: the hardware places the CTAs
