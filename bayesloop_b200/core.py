@@ -88,6 +88,49 @@ def _share_structure(ops, T):
     return dict(k=k, group=group, cidx=cidx, cvals=cvals.astype(np.int64), nG=nG, nC=nC)
 
 
+def _deal_shared(share, ops, size, slots, fits_all_groups):
+    """How a (groups) x (change-points) sweep is dealt over `size` ranks: 'groups' (whole groups, every change-point),
+    'changepoints' (every group, a subset of the change-points) or None (no sharing: plain round-robin deal).  The
+    answer depends only on its arguments, which are the same on every rank.
+
+    A shared sweep launches one forward and one backward pass per change-point with B = (groups of the rank) combos
+    (HyperStudy._executeSharedSweep), plus two full-length passes of the change-point-free run of every group of the
+    rank.  With `slots` combos resident on the device at a time a launch takes the makespan of its combos on
+    the slots: a launch with few combos is as long as its costliest combo and leaves slots idle.  Dealing GROUPS
+    shrinks every launch (C4 on 8 GPUs: 12-13 combos on 15 resident clusters, the launches as long as the widest
+    random walk: 5.5 x one GPU measured, profiles/r2Y2_bench_n8.json); dealing CHANGE-POINTS keeps the launches of the
+    single-GPU run and the ranks balanced ((T - c) + (c + 2) executed steps per combo whatever c), at the price of
+    every rank repeating the change-point-free runs (2 of 2 + nC/size pass-equivalents) and holding the two shared
+    sequences of ALL groups (`fits_all_groups`)."""
+    nG, nC = share['nG'], share['nC']
+    rep = np.full(nG, -1, dtype=np.int64)
+    rep[share['group']] = np.arange(len(share['group']))  # one representative combo per group
+    cost = np.full(nG, 18.0)  # elementwise work of a step in units of one convolution tap (DESIGN.md 6: 46 FMA at 28 taps)
+    for op in ops:
+        radius = np.asarray(op['radius'], dtype=np.int64).reshape(len(share['group']), -1)[rep]
+        cost += np.where(radius > 0, 2 * radius + 1, 0).sum(axis=1)
+
+    def launch(sel):  # makespan of one launch: combos by descending cost onto the least loaded of `slots` slots
+        c = np.sort(cost[sel])[::-1]
+        if len(c) <= slots:
+            return float(c[0])
+        load = np.zeros(int(slots))
+        for x in c:
+            load[np.argmin(load)] += x
+        return float(load.max())
+
+    cand = {}
+    if nC // size >= 2 and (fits_all_groups or size == 1):
+        cand['changepoints'] = launch(np.arange(nG)) * (2 + -(-nC // size))
+    if nG >= size:
+        cand['groups'] = max(launch(np.arange(r, nG, size)) for r in range(size)) * (2 + nC)
+    if size == 1:
+        return 'groups' if cand else None  # one rank: the two deals are the same thing
+    if not cand:
+        return None
+    return min(sorted(cand), key=cand.get)  # ties: 'changepoints' (balanced whatever the groups cost)
+
+
 class _Session:
     """Device-side constants of one fit: plan, data series, prior, likelihood table."""
 
@@ -703,6 +746,8 @@ class HyperStudy(Study):
     (reference: core.py:1118-1495).  The sweep is the batch axis of the device kernels and, under
     torch.distributed, is sharded across ranks/GPUs (bayesloop_b200/distributed.py)."""
 
+    shareDeal = None  # under torch.distributed: 'groups' / 'changepoints' instead of the choice of _deal_shared
+
     def __init__(self, silent=False, engine=None):
         super(HyperStudy, self).__init__(silent=silent, engine=engine)
         self.hyperGrid = []
@@ -817,17 +862,27 @@ class HyperStudy(Study):
         if share is None:
             rows = dist.shard_rows(Ball)
         else:
-            # groups (or, with fewer groups than ranks, change-points) dealt round-robin over the ranks; this rank's
-            # combinations are laid out change-point-major: slot = (change-point index) * nG + (group index)
+            # whole groups or whole change-points dealt round-robin over the ranks (_deal_shared picks the cheaper deal)
             rank, size = dist.world()
-            gsel = np.arange(rank, share['nG'], size) if share['nG'] >= size else np.arange(share['nG'])
-            csel = np.arange(share['nC']) if share['nG'] >= size else np.arange(rank, share['nC'], size)
-            where = np.full((share['nC'], share['nG']), -1, dtype=np.int64)
-            where[share['cidx'], share['group']] = np.arange(Ball)
-            rows = where[np.ix_(csel, gsel)].reshape(-1)
-            share = dict(share, nG=len(gsel), nC=len(csel), cvals=share['cvals'][csel])
-            if share['nG'] == 0 or share['nC'] < 2:
+            deal = 'groups' if size == 1 else self.shareDeal
+            if deal is None:
+                # the decision must be the same on every rank: smallest free memory of the ranks, grid-level slot count
+                free = dist.min_over_ranks(eng, eng.free_bytes())
+                fits = 2 * share['nG'] * T * G * 8 <= (int(free * 0.85) - T * G * 8) // 2
+                slots = 15 if G * 8 > 200 * 1024 else 4 * max(eng.sm_count(), 148)  # clusters of 8 SMs / chains per SM
+                deal = _deal_shared(share, ctx.ops, size, slots, fits)
+            elif (deal == 'groups' and share['nG'] < size) or (deal == 'changepoints' and share['nC'] // size < 2):
+                deal = None
+            if deal is None:
                 share, rows = None, dist.shard_rows(Ball)
+            else:
+                # this rank's combinations are laid out change-point-major: slot = (change-point index) * nG + (group index)
+                gsel = np.arange(rank, share['nG'], size) if deal == 'groups' else np.arange(share['nG'])
+                csel = np.arange(share['nC']) if deal == 'groups' else np.arange(rank, share['nC'], size)
+                where = np.full((share['nC'], share['nG']), -1, dtype=np.int64)
+                where[share['cidx'], share['group']] = np.arange(Ball)
+                rows = where[np.ix_(csel, gsel)].reshape(-1)
+                share = dict(share, nG=len(gsel), nC=len(csel), cvals=share['cvals'][csel], deal=deal)
         B = len(rows)
         hp = np.asarray(self.flatHyperPriorValues, dtype=float)[rows]
         ops = [dict(op, param=np.asarray(op['param'])[rows], radius=np.asarray(op['radius'])[rows],
@@ -988,7 +1043,7 @@ class HyperStudy(Study):
         logEAll, aliveAll = dist.gather_rows(eng, logE[:B], alive[:B], sw['Ball'], rows=sw['rows'])
         logEAll = np.where(aliveAll == 1, logEAll, -np.inf)
         self.sweepStats = dict(waves=waves, wave=sw['wave'], rows=sw['rows'], launches=eng.launch_count(), shared=True,
-                               executed_updates=int(executed) * G, nominal_updates=2 * int(B) * T * G)
+                               deal=share.get('deal'), executed_updates=int(executed) * G, nominal_updates=2 * int(B) * T * G)
         return eng, logEAll, aliveAll, localEv, avg, sw['means']
 
     def _executeSweep(self, sw):

@@ -90,6 +90,15 @@ def gather_dealt(eng, mine, total):
     return out
 
 
+def min_over_ranks(eng, value):
+    """Smallest `value` (a host scalar) of the ranks: for decisions every rank must take alike."""
+    if world()[1] == 1:
+        return value
+    t = torch.tensor([float(value)], dtype=torch.float64, device=eng.device)
+    td.all_reduce(t, op=td.ReduceOp.MIN)
+    return float(t.item())
+
+
 def reduce_sum(eng, tensor):
     if world()[1] > 1:
         td.all_reduce(tensor, op=td.ReduceOp.SUM)

@@ -445,7 +445,7 @@ def sweep_report(wl, m, peak, peak_src, world):
         # NOMINAL updates (what the reference executes for this study); the rooflines above count the executed ones.
         out['sharing'] = {'what': 'change-point prefix sharing (history erased at tChange, transitionModels.py:300-312)',
                           'nominal_updates_per_rank': nominal, 'executed_updates_per_rank': executed,
-                          'executed_over_nominal': executed / nominal,
+                          'executed_over_nominal': executed / nominal, 'dealt_by': m['stats'].get('deal'),
                           'value_executed': updates * (executed / nominal) / (m['dev_ms'] * 1e-3)}
     if m['e2e_ms']:
         n_local = wl.B // world

@@ -7,12 +7,13 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, out_dir):
+def _worker(rank, world, port, name, out_dir, deal=None):
     import torch.distributed as td
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -24,9 +25,12 @@ def _worker(rank, world, port, name, out_dir):
     from bayesloop_b200 import engine
     from conftest import ORACLE_SO
     engine.set_default_engine(engine.Engine(ORACLE_SO, 'cpu'))
+    bl.HyperStudy.shareDeal = deal
     S, got = parity.run_case(name, bl)
     shard = S._dev['rows'] if type(S).__name__ == 'OnlineStudy' else S.sweepStats['rows']
-    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), shard=np.array(shard), **got)
+    stats = getattr(S, 'sweepStats', {})
+    np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), shard=np.array(shard), deal=str(stats.get('deal')),
+             shared=bool(stats.get('shared')), **got)
     td.destroy_process_group()
 
 
@@ -36,11 +40,16 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(name, tmp_path, world=2):
+def _run(name, tmp_path, world=2, deal=None, keep_stats=False):
     from conftest import build_oracle
     build_oracle()
-    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
-    return [dict(np.load(os.path.join(str(tmp_path), 'rank%d.npz' % r))) for r in range(world)]
+    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path), deal), nprocs=world, join=True)
+    ranks = [dict(np.load(os.path.join(str(tmp_path), 'rank%d.npz' % r))) for r in range(world)]
+    for r in ranks:
+        stats = {k: r.pop(k) for k in ('deal', 'shared')}
+        if keep_stats:
+            r['stats'] = stats
+    return ranks
 
 
 def test_two_ranks_reproduce_the_golden_hyperstudy(tmp_path):
@@ -104,5 +113,31 @@ def test_more_ranks_than_hypotheses(tmp_path):
     want = load_golden(name)
     assert [list(r['shard']) for r in ranks] == [[0], []]
     for r in ranks:
+        r.pop('shard')
+        parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)
+
+
+@pytest.mark.parametrize('world,deal,want_deal,first_rows', [
+    (2, None, 'changepoints', [0, 1, 2, 3, 4, 5, 12, 13]),   # the cost model: 6 groups never fill a launch, so deal change-points
+    (2, 'groups', 'groups', [0, 2, 4, 6, 8, 10, 12, 14]),
+    (3, 'changepoints', 'changepoints', [0, 1, 2, 3, 4, 5, 18, 19]),
+    (3, 'groups', 'groups', [0, 3, 6, 9, 12, 15, 18, 21]),
+    (5, 'changepoints', 'None', [0, 5, 10, 15, 20, 25, 30, 35]),  # 8 change-points over 5 ranks: < 2 each -> plain deal
+])
+def test_changepoint_study_with_prefix_sharing_dealt_by_groups_or_by_changepoints(tmp_path, world, deal, want_deal, first_rows):
+    """C4 in miniature (8 change-points x 6 groups of random-walk widths) with the change-point prefix sharing under
+    torch.distributed: whole groups or whole change-points per rank (core._deal_shared), every rank's merged result
+    equal to the golden of the unsharded reference run, every combination owned by exactly one rank."""
+    import parity
+    from conftest import load_golden
+    name = 'syn_cps_gauss_2d'
+    ranks = _run(name, tmp_path, world=world, deal=deal, keep_stats=True)
+    want = load_golden(name)
+    owned = np.sort(np.concatenate([r['shard'] for r in ranks]))
+    assert list(owned) == list(range(48))
+    assert list(ranks[0]['shard'][:8]) == first_rows
+    for r in ranks:
+        stats = r.pop('stats')
+        assert str(stats['deal']) == want_deal and bool(stats['shared']) == (want_deal != 'None')
         r.pop('shard')
         parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)
