@@ -79,15 +79,14 @@ def gather_dealt(eng, mine, total):
     if size == 1:
         return eng.to_host(mine)
     width = -(-int(total) // size)
-    send = torch.zeros((width,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+    tail = tuple(mine.shape[1:])
+    send = torch.zeros((width,) + tail, dtype=mine.dtype, device=mine.device)
     send[:mine.shape[0]] = mine
-    recv = [torch.empty_like(send) for _ in range(size)]
-    td.all_gather(recv, send)
-    out = np.empty((int(total),) + tuple(mine.shape[1:]), dtype=eng.to_host(send[:0]).dtype)
-    for r, block in enumerate(recv):
-        rows = shard_rows(total, r, size)
-        out[rows] = eng.to_host(block[:len(rows)])
-    return out
+    recv = torch.empty((size, width) + tail, dtype=mine.dtype, device=mine.device)
+    td.all_gather(list(recv.unbind(0)), send)  # views of one buffer (gloo's all_gather_into_tensor wants a flat one)
+    # ONE device -> host copy per call (an OnlineStudy calls this every step); global row r + size * k sits at [r][k]
+    host = np.asarray(eng.to_host(recv))
+    return np.swapaxes(host, 0, 1).reshape((width * size,) + tail)[:int(total)].copy()
 
 
 def min_over_ranks(eng, value):
