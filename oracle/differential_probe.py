@@ -7,7 +7,9 @@ outcomes are compared -- same exception type, or same log-evidence / means / gri
 Known, deliberate differences (documented in tests/test_host_logic.py and DESIGN.md): Poisson counts > 170 overflow the
 reference's factorial (OverflowError) where the product evaluates lgamma; an unknown `target` raises
 ConfigurationError instead of a bare ValueError; timestamps of the wrong length fall back to the integer range (the
-reference leaves them unset and crashes later).
+reference leaves them unset and crashes later); an ndarray prior is never written to by the filter (the reference's
+forward loop multiplies the likelihood into the user's array, so resets and later combinations of a sweep start from
+whatever it holds by then: those probes compare with the reference given the same prior as a callable).
 """
 import contextlib
 import io
@@ -159,9 +161,122 @@ def main():
             'm', bl.cint(-2, 2, 20), 's', bl.oint(0, 2, 20),
             prior=[stats.Normal('a', 0, 1), stats.Exponential('b', 1)]), static), std),
     }
+    # ---- second batch: fit modes, time stamps, priors / hyper-priors of every kind, irregular grids, dead combinations
+    seq = std + [lambda S: S.posteriorSequence, lambda S: S.localEvidence]
+    P60 = lambda bl: bl.om.Poisson('r', bl.oint(0, 8, 60))  # noqa: E731
+    tsf = [0.5 * i for i in range(15)]
+    tsn = [0., 1., 2.5, 2.75, 4., 7., 8., 8.5, 9., 12., 13., 14., 20., 21., 22.]
+
+    def refit(bl):  # fit, exchange the transition model, fit again on the same study object
+        S = bl.Study()
+        S.loadData(np.array(xc))
+        S.set(P60(bl), bl.tm.Static())
+        S.fit()
+        S.setTM(bl.tm.GaussianRandomWalk('s', 0.3, target='r'))
+        S.fit()
+        return S
+
+    def online_hp(bl):
+        S = bl.OnlineStudy(storeHistory=False)
+        S.setOM(G2(bl))
+        S.add('w', bl.tm.GaussianRandomWalk('s', [0.05, 0.1, 0.2], target='m', prior=lambda s: 1. / s))
+        S.add('r', bl.tm.RegimeSwitch('p', [-6, -3], prior=np.array([1., 3.])))
+        for d in xs:
+            S.step(d)
+        return S
+
+    probes.update({
+        'study: forwardOnly': (generic('Study', xc, P60, lambda bl: grw(bl, 0.3), forwardOnly=True), seq),
+        'study: evidenceOnly': (generic('Study', xc, P60, lambda bl: grw(bl, 0.3), evidenceOnly=True),
+                                [lambda S: S.logEvidence, lambda S: S.localEvidence]),
+        'study: fit, new transition model, fit again': (refit, seq),
+        'study: integer data': (generic('Study', np.asarray(xc, dtype=np.int64), P60, lambda bl: grw(bl, 0.2)), seq),
+        'change-point on a fractional time stamp': (generic('Study', xc, P60, lambda bl: bl.tm.ChangePoint('t', 3.5), ts=tsf), seq),
+        'change-point between two time stamps (never fires)': (generic('Study', xc, P60, lambda bl: bl.tm.ChangePoint('t', 3.3),
+                                                                        ts=tsf), seq),
+        'break-point between irregular time stamps': (generic(
+            'Study', xc, P60, lambda bl: bl.tm.SerialTransitionModel(grw(bl, 0.5), bl.tm.BreakPoint('b', 7.5), bl.tm.Static()),
+            ts=tsn), seq),
+        'changepoint study: all, irregular time stamps': (generic('ChangepointStudy', xc, P60,
+                                                                  lambda bl: bl.tm.ChangePoint('t', 'all'), ts=tsn), hyp),
+        'random walk of width zero': (generic('Study', xc, P60, lambda bl: grw(bl, 0.0)), seq),
+        'random walk of negative width': (generic('Study', xc, P60, lambda bl: grw(bl, -0.2)), seq),
+        'two random walks on the same parameter': (generic(
+            'Study', xc, P60, lambda bl: bl.tm.CombinedTransitionModel(grw(bl, 0.2), bl.tm.GaussianRandomWalk('s2', 0.4, target='r'))),
+            seq),
+        'regime switch with a floor of 1e-300': (generic('Study', xc, P60, lambda bl: bl.tm.RegimeSwitch('p', -300)), seq),
+        'regime switch with a floor above the flat level': (generic('Study', xc, P60, lambda bl: bl.tm.RegimeSwitch('p', 1)), seq),
+        'independent observations': (generic('Study', xc, P60, lambda bl: bl.tm.Independent()), seq),
+        'static inside a combined model': (generic(
+            'Study', xc, P60, lambda bl: bl.tm.CombinedTransitionModel(bl.tm.Static(), grw(bl, 0.3), bl.tm.Static())), seq),
+        'irregular (categorical) grid with a random walk': (generic(
+            'Study', xc, lambda bl: bl.om.Poisson('r', [0.5, 1., 2., 3., 3.5, 5., 8.]), lambda bl: grw(bl, 1.2)), seq),
+        '2-D grid, one irregular axis': (generic(
+            'Study', xs, lambda bl: bl.om.Gaussian('m', bl.cint(-2, 2, 12), 's', [0.2, 0.5, 0.6, 1., 2.]),
+            lambda bl: bl.tm.GaussianRandomWalk('w', 0.3, target='m')), seq),
+        'callable prior on a 2-D grid': (generic('Study', xs, lambda bl: bl.om.Gaussian(
+            'm', bl.cint(-2, 2, 16), 's', bl.oint(0, 2, 14), prior=lambda m, s: 1. / s ** 3), static), seq),
+        'SymPy prior, one parameter': (generic('Study', xc, lambda bl: bl.om.Poisson(
+            'r', bl.oint(0, 8, 60), prior=stats.Exponential('e', 0.5)), lambda bl: grw(bl, 0.2)), seq),
+        'prior array that sums to one': (generic('Study', xc, lambda bl: bl.om.Poisson(
+            'r', bl.oint(0, 8, 60), prior=np.ones(60) / 60.), static), seq),
+        # the reference's forward loop works IN PLACE on the array _computePrior returned (core.py:362, :385): with an
+        # ndarray prior that is the user's array itself, so a later reset (transitionModels.py:303-304, :352-353)
+        # "restores" whatever the filter has written into it by then.  The product keeps the prior the user gave;
+        # the reference run it is compared with gets the same values through a callable (core.py:224-235), which the
+        # reference evaluates afresh at every reset
+        'prior array with a zero region and a change-point': (
+            generic('Study', xc, lambda bl: bl.om.Poisson('r', bl.oint(0, 8, 60), prior=np.concatenate([np.zeros(10), np.ones(50)])),
+                    lambda bl: bl.tm.ChangePoint('t', 6)), seq,
+            generic('Study', xc, lambda bl: bl.om.Poisson('r', bl.oint(0, 8, 60), prior=lambda r: 1. * (np.arange(60) >= 10)),
+                    lambda bl: bl.tm.ChangePoint('t', 6))),
+        'prior array and independent observations': (
+            generic('Study', xc, lambda bl: bl.om.Poisson('r', bl.oint(0, 8, 60), prior=np.linspace(1., 3., 60)),
+                    lambda bl: bl.tm.Independent()), seq,
+            generic('Study', xc, lambda bl: bl.om.Poisson('r', bl.oint(0, 8, 60), prior=lambda r: np.linspace(1., 3., 60)),
+                    lambda bl: bl.tm.Independent())),
+        'hyper: prior array (every combination starts from it)': (
+            generic('HyperStudy', xc, lambda bl: bl.om.Poisson('r', bl.oint(0, 8, 60), prior=np.linspace(1., 3., 60)),
+                    lambda bl: grw(bl, [0.1, 0.3])), hyp + [lambda S: S.posteriorSequence],
+            generic('HyperStudy', xc, lambda bl: bl.om.Poisson('r', bl.oint(0, 8, 60), prior=lambda r: np.linspace(1., 3., 60)),
+                    lambda bl: grw(bl, [0.1, 0.3]))),
+        'count the likelihood cannot explain (dead fit)': (generic(
+            'Study', [1., 2., 900., 1.], lambda bl: bl.om.Gaussian('m', bl.cint(-2, 2, 16), 's', bl.oint(0, 0.5, 10)), static),
+            [lambda S: S.logEvidence]),
+        'hyper: one dead combination of three': (generic(
+            'HyperStudy', [0.1, 0.2, 30., 0.1], lambda bl: bl.om.Gaussian('m', bl.cint(-1, 1, 16), 's', bl.oint(0, 0.4, 8)),
+            lambda bl: bl.tm.GaussianRandomWalk('w', [0., 0.01, 4.], target='m')),
+            [lambda S: S.logEvidence, lambda S: S.hyperParameterDistribution, lambda S: np.asarray(S.logEvidenceList)]),
+        'hyper: callable hyper-prior': (generic('HyperStudy', xc, P60, lambda bl: bl.tm.GaussianRandomWalk(
+            's', [0.1, 0.2, 0.4], target='r', prior=lambda s: 1. / s)), hyp + [lambda S: S.posteriorSequence]),
+        'hyper: hyper-prior array': (generic('HyperStudy', xc, P60, lambda bl: bl.tm.GaussianRandomWalk(
+            's', [0.1, 0.2, 0.4], target='r', prior=np.array([3., 2., 1.]))), hyp),
+        'hyper: SymPy hyper-prior': (generic('HyperStudy', xc, P60, lambda bl: bl.tm.GaussianRandomWalk(
+            's', bl.cint(0.1, 0.5, 5), target='r', prior=stats.Exponential('e', 4.))), hyp),
+        'hyper: irregular hyper-parameter values': (generic('HyperStudy', xc, P60, lambda bl: bl.tm.GaussianRandomWalk(
+            's', [0.1, 0.15, 0.4, 1.0], target='r')), hyp + [lambda S: S.localEvidence]),
+        'hyper: break-point all inside a hyper-study': (generic('HyperStudy', xc, P60, lambda bl: bl.tm.SerialTransitionModel(
+            bl.tm.Static(), bl.tm.BreakPoint('b', 'all'), grw(bl, [0.1, 0.3]))), hyp),
+        'changepoint study: hyper-prior on the change-point': (generic(
+            'ChangepointStudy', xc, P60, lambda bl: bl.tm.ChangePoint('t', 'all', prior=lambda t: 1. + t)), hyp),
+        'changepoint study: change-point x walk widths (shared prefixes)': (generic(
+            'ChangepointStudy', xc, P60, lambda bl: bl.tm.CombinedTransitionModel(
+                bl.tm.ChangePoint('t', 'all'), grw(bl, [0.1, 0.2, 0.4]))), hyp + [lambda S: S.posteriorSequence,
+                                                                                   lambda S: S.localEvidence]),
+        'online: hyper-priors, no history': (online_hp, [lambda S: S.logEvidence, lambda S: S.marginalizedPosterior,
+                                                         lambda S: S.transitionModelDistribution,
+                                                         lambda S: np.concatenate(S.hyperParameterDistribution)]),
+        'online: segment of two, first point only waits': (
+            lambda bl: [S for S in [bl.OnlineStudy()] if not (S.setOM(ar(bl)), S.add('a', bl.tm.Static()), S.step(0.3))][0],
+            [lambda S: float(len(S.formattedTimestamps))]),
+        'missing value in a segment of two': (generic('Study', xn, ar, static), seq),
+        'Bernoulli with a value outside {0, 1}': (generic('Study', [0, 1, 2, 1], lambda bl: bl.om.Bernoulli('p', bl.oint(0, 1, 20)),
+                                                          static), std),
+    })
     diffs = 0
-    for name, (build, attrs) in probes.items():
-        r, o = run(ref, build, attrs), run(ours, build, attrs)
+    for name, probe in probes.items():
+        build, attrs = probe[:2]
+        r, o = run(ref, probe[2] if len(probe) > 2 else build, attrs), run(ours, build, attrs)
         if r[0] != o[0]:
             same = False
         elif r[0] == 'exc':

@@ -91,6 +91,44 @@ def test_online_study_checkpoint_resume(use_oracle):
         np.testing.assert_array_equal(a, c)
 
 
+def test_array_prior_is_never_written_to_by_the_filter(use_oracle):
+    """The reference's forward loop multiplies the likelihood INTO the array _computePrior returned (core.py:362,
+    :385); for an ndarray prior that is the user's own array, so a ChangePoint / Independent reset
+    (transitionModels.py:303-304, :352-353) restores whatever the filter wrote into it, and every later combination of
+    a sweep starts from it (found by oracle/differential_probe.py).  The product normalises the array in place like
+    core.py:212-213 and then leaves it alone: an array prior gives exactly what the same values give as a callable
+    (core.py:224-235), which is also what the reference computes for the callable."""
+    import bayesloop_b200 as bl
+    rng = np.random.default_rng(5)
+    rng.normal(0.3, 0.8, 15)  # the probe script draws its Gaussian series first
+    counts = rng.poisson(3, 15)
+    values = np.concatenate([np.zeros(10), np.ones(50)])
+
+    def fit(prior, cls, tm):
+        S = cls(silent=True)
+        S.loadData(counts, silent=True)
+        S.set(bl.om.Poisson('r', bl.oint(0, 8, 60), prior=prior), tm, silent=True)
+        S.fit(silent=True)
+        return S
+
+    models = [(bl.Study, lambda: bl.tm.ChangePoint('t', 6)), (bl.Study, lambda: bl.tm.Independent()),
+              (bl.HyperStudy, lambda: bl.tm.GaussianRandomWalk('s', [0.1, 0.3], target='r')),
+              (bl.ChangepointStudy, lambda: bl.tm.CombinedTransitionModel(
+                  bl.tm.ChangePoint('t', 'all'), bl.tm.GaussianRandomWalk('s', [0.1, 0.3], target='r')))]
+    for cls, tm in models:
+        array = values.copy()
+        A = fit(array, cls, tm())
+        C = fit(lambda r: values.copy(), cls, tm())
+        lattice = 8. / 61.
+        np.testing.assert_allclose(array, values / values.sum() / lattice, rtol=1e-14)  # normalised in place, nothing else
+        assert abs(A.logEvidence - C.logEvidence) <= 1e-12 * abs(C.logEvidence)
+        np.testing.assert_allclose(A.posteriorSequence, C.posteriorSequence, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(A.localEvidence, C.localEvidence, rtol=1e-12)
+    # the reference, given the callable, on the first model of the list (reference value computed in the build container
+    # by oracle/differential_probe.py: 'prior array with a zero region and a change-point')
+    assert abs(fit(values.copy(), bl.Study, bl.tm.ChangePoint('t', 6)).logEvidence - (-31.911321254878697)) < 1e-10
+
+
 def test_edge_cases_behave_like_the_reference(use_oracle):
     """Probed against the unmodified reference in the build container (it cannot travel): a series shorter than one
     segment gives empty sequences and logE = log(prod(latticeConstant)) (the loops of core.py:372-470 never run,
