@@ -273,6 +273,108 @@ def main():
         'Bernoulli with a value outside {0, 1}': (generic('Study', [0, 1, 2, 1], lambda bl: bl.om.Bernoulli('p', bl.oint(0, 1, 20)),
                                                           static), std),
     })
+    # ---- third batch: OnlineStudy with history and odd models, optimize / simulate, accessors, wider sweeps
+    def online_full(models, data=xs, om=G2, prior=None):
+        def build(bl):
+            S = bl.OnlineStudy(storeHistory=True)
+            S.setOM(om(bl))
+            for n, m in models(bl):
+                S.add(n, m)
+            if prior is not None:
+                S.setTransitionModelPrior(prior)
+            for d in data:
+                S.step(d)
+            return S
+        return build
+
+    hist = [lambda S: S.logEvidence, lambda S: np.asarray(S.posteriorSequence), lambda S: np.asarray(S.posteriorMeanValues),
+            lambda S: np.asarray(S.transitionModelSequence), lambda S: np.asarray(S.localTransitionModelSequence),
+            lambda S: np.concatenate([np.concatenate(h) for h in S.hyperParameterSequence])]
+    two = lambda bl: [('w', bl.tm.CombinedTransitionModel(  # noqa: E731
+        bl.tm.GaussianRandomWalk('a', [0.05, 0.2], target='m'), bl.tm.GaussianRandomWalk('b', [0.02, 0.1, 0.3], target='s'))),
+        ('r', bl.tm.RegimeSwitch('p', [-6, -2])), ('i', bl.tm.Independent()), ('n', bl.tm.NotEqual('q', -3.))]  # (an integer exponent makes the reference's 10**q raise)
+
+    def online_set(bl):  # transition model given through set(), not add()
+        S = bl.OnlineStudy(storeHistory=True)
+        S.set(G2(bl), bl.tm.GaussianRandomWalk('s', 0.1, target='m'))
+        for d in xs:
+            S.step(d)
+        return S
+
+    def optimized(bl):
+        S = bl.Study()
+        S.loadData(np.array(xc))
+        S.set(P60(bl), bl.tm.GaussianRandomWalk('s', 0.5, target='r'))
+        S.optimize(tol=1e-6)
+        return S
+
+    def custom_grid(bl):
+        S = bl.HyperStudy()
+        S.loadData(np.array(xc))
+        S.set(P60(bl), bl.tm.CombinedTransitionModel(grw(bl, [0.1, 0.2]), bl.tm.RegimeSwitch('p', [-7, -4])))
+        S._createHyperGrid()
+        S.hyperGridValues = np.array([[0.1, -7.], [0.15, -5.], [0.3, -4.]])
+        S.flatHyperPriorValues = np.array([0.2, 0.5, 0.3])
+        S.hyperGridConstant = [1., 1.]
+        S.fit(customHyperGrid=True)
+        return S
+
+    fitted = lambda bl: generic('HyperStudy', xc, P60, lambda b: grw(b, [0.1, 0.2, 0.4]))(bl)  # noqa: E731
+    fitted1 = lambda bl: generic('Study', xc, P60, lambda b: grw(b, 0.3))(bl)  # noqa: E731
+    cps2 = lambda bl: generic('ChangepointStudy', [1, 2, 1, 6, 7, 6, 2, 1, 1, 2], P, lambda b: b.tm.SerialTransitionModel(  # noqa: E731
+        b.tm.Static(), b.tm.ChangePoint('t1', 'all'), grw(b, [0.1, 0.3]), b.tm.ChangePoint('t2', 'all'), b.tm.Static()))(bl)
+    probes.update({
+        'online: history of four hypotheses families': (online_full(two), hist),
+        'online: model prior and history': (online_full(two, prior=[0.1, 0.2, 0.3, 0.4]), hist),
+        'online: transition model through set()': (online_set, hist[:3]),
+        'online: change-point at time -1 (t is always -1)': (online_full(
+            lambda bl: [('c', bl.tm.ChangePoint('t', -1)), ('s', bl.tm.Static())]), hist[:5]),
+        'online: serial model (t is always -1)': (online_full(
+            lambda bl: [('x', bl.tm.SerialTransitionModel(bl.tm.Static(), bl.tm.BreakPoint('b', 5),
+                                                          bl.tm.GaussianRandomWalk('s', 0.2, target='m')))]), hist[:3]),
+        'online: Poisson, one parameter': (online_full(
+            lambda bl: [('w', bl.tm.GaussianRandomWalk('s', [0.1, 0.3], target='r')), ('r', bl.tm.RegimeSwitch('p', -5))],
+            data=xc, om=P60), hist),
+        'online: segment of two': (online_full(
+            lambda bl: [('w', bl.tm.GaussianRandomWalk('s', [0.05, 0.1], target='rho')), ('s', bl.tm.Static())], om=ar), hist),
+        'online: two data columns per step': (online_full(
+            lambda bl: [('w', bl.tm.GaussianRandomWalk('s', [0.1, 0.3], target='r'))],
+            data=[[1, 2], [2, 3], [3, 1], [0, 2]], om=P60), hist[:3]),
+        'optimize one hyper-parameter': (optimized, [lambda S: S.logEvidence, lambda S: S.getHyperParameterValue('s'),
+                                                     lambda S: S.posteriorMeanValues]),
+        'hyper: custom hyper-grid': (custom_grid, hyp + [lambda S: S.posteriorSequence]),
+        'hyper: three hyper-parameters': (generic('HyperStudy', xs, G2, lambda bl: bl.tm.CombinedTransitionModel(
+            bl.tm.GaussianRandomWalk('a', [0.05, 0.2], target='m'), bl.tm.GaussianRandomWalk('b', [0.02, 0.1], target='s'),
+            bl.tm.RegimeSwitch('p', [-6, -3, -1]))), hyp + [lambda S: S.posteriorSequence, lambda S: S.localEvidence]),
+        'hyper: NotEqual sweep': (generic('HyperStudy', xs, G2, lambda bl: bl.tm.NotEqual('q', [-5., -3., -1.])), hyp),
+        'hyper: every combination dead': (generic(
+            'HyperStudy', [0.1, 50., 0.1], lambda bl: bl.om.Gaussian('m', bl.cint(-1, 1, 16), 's', bl.oint(0, 0.3, 8)),
+            lambda bl: bl.tm.GaussianRandomWalk('w', [0., 0.01], target='m')), [lambda S: S.logEvidence]),
+        'hyper: change-point values in a plain hyper-study': (generic('HyperStudy', xc, P60, lambda bl: bl.tm.CombinedTransitionModel(
+            bl.tm.ChangePoint('t', [3, 6, 9]), grw(bl, [0.1, 0.3]))), hyp + [lambda S: S.posteriorSequence]),
+        'changepoint study: evidenceOnly': (generic('ChangepointStudy', xc, P60, lambda bl: bl.tm.ChangePoint('t', 'all'),
+                                                    evidenceOnly=True), [lambda S: S.logEvidence, lambda S: S.hyperParameterDistribution]),
+        'changepoint study: two change-points around a random walk': (cps2, hyp + [lambda S: S.posteriorSequence]),
+        'accessor: getParameterMeanValues': (fitted, [lambda S: S.getParameterMeanValues('r')]),
+        # (getParameterDistribution(s) of the reference compare an ndarray with [] and raise under NumPy 2: core.py:880, :950)
+        'accessor: getHyperParameterDistribution': (fitted, [lambda S: S.getHyperParameterDistribution('s')[0],
+                                                             lambda S: S.getHyperParameterDistribution('s')[1]]),
+        'accessor: getJointHyperParameterDistribution': (
+            generic('HyperStudy', xc, P60, lambda bl: bl.tm.CombinedTransitionModel(grw(bl, [0.1, 0.2, 0.3]),
+                                                                                   bl.tm.RegimeSwitch('p', [-7, -4]))),
+            [lambda S: S.getJointHyperParameterDistribution(['s', 'p'])[2]]),
+        'accessor: getDurationDistribution': (cps2, [lambda S: S.getDurationDistribution(['t1', 't2'])[0],
+                                                      lambda S: S.getDurationDistribution(['t1', 't2'])[1]]),
+        'accessor: unknown parameter name': (fitted, [lambda S: S.getParameterMeanValues('nope')]),
+        'accessor: online current distributions': (online_full(two), [
+            lambda S: S.getCurrentParameterDistribution('m')[1], lambda S: S.getCurrentTransitionModelDistribution(),
+            lambda S: S.getCurrentTransitionModelProbability('r'), lambda S: S.getCurrentParameterMeanValue('s'),
+            lambda S: S.getCurrentHyperParameterDistribution('a')[1], lambda S: S.getCurrentHyperParameterMeanValue('b'),
+            lambda S: S.getTransitionModelProbabilities('w'), lambda S: S.getParameterMeanValues('m'),
+            lambda S: S.getHyperParameterMeanValues('p'), lambda S: S.getParameterDistribution(3, 's')[1],
+            lambda S: S.getHyperParameterDistribution(5, 'b')[1]]),
+        'simulate: Poisson predictions': (fitted1, [lambda S: np.asarray(S.simulate(np.arange(0, 12), t=5, density=False))[1]]),
+    })
     diffs = 0
     for name, probe in probes.items():
         build, attrs = probe[:2]
