@@ -76,6 +76,10 @@ def _share_structure(ops, T):
         w = np.asarray(op['window'])
         if j != k and not np.all(w == w[0]):
             return None  # another operator's activity depends on the combination (Serial models): not shareable
+        if j != k and not (np.all(w[:, 0] <= 0) and np.all(w[:, 1] >= T) and np.all(w[:, 2] <= 0) and np.all(w[:, 3] >= T)):
+            # an operator that is active on a RANGE of steps only (a segment of a Serial model next to the change-point):
+            # the shared schedule runs the passes on windows of the sequence, whose step indices start at 0 again
+            return None
         keys.append(np.asarray(op['param'], dtype=float).reshape(B, 1))
         keys.append(np.asarray(op['radius'], dtype=float).reshape(B, 1))
     _, group = np.unique(np.hstack(keys), axis=0, return_inverse=True)

@@ -245,6 +245,35 @@ def test_prefix_sharing_only_where_the_history_is_erased(use_oracle):
     assert structure(bl.tm.CombinedTransitionModel(bl.tm.Independent(), grw('s', [0.1, 0.2, 0.3, 0.4], target='rate')),
                      cls=bl.HyperStudy) is None
     assert structure(grw('s', [0.1, 0.2, 0.3, 0.4], target='rate'), cls=bl.HyperStudy) is None
+    # a change-point next to a Serial model whose segments are active on RANGES of steps: the passes of the shared
+    # schedule run on windows of the sequence (step indices start at 0 again), so such a sweep keeps the plain schedule
+    ranged = bl.tm.CombinedTransitionModel(
+        bl.tm.ChangePoint('t', [2, 4]),
+        bl.tm.SerialTransitionModel(bl.tm.NotEqual('q', -4.), bl.tm.BreakPoint('b', 3), bl.tm.RegimeSwitch('p', [-7., -4.])))
+    assert structure(ranged, cls=bl.HyperStudy) is None
+
+
+def test_changepoint_sweep_next_to_a_serial_model_matches_the_reference(use_oracle):
+    """Found by oracle/fuzz_lowering.py (seeds 22257, 22726, 25252 of 8 000): a HyperStudy over the time of a
+    change-point combined with a Serial model (NotEqual before, RegimeSwitch after a FIXED break-point) was run with
+    prefix sharing, whose windowed passes shifted the Serial model's segments.  Expected values: the unmodified
+    reference in the build container (core.py:1349-1419 over transitionModels.py:289-314, :756-818)."""
+    import bayesloop_b200 as bl
+    S = bl.HyperStudy(silent=True)
+    S.loadData(np.array([2., 4, 2, 3, 5, 1, 1, 2]), silent=True)
+    S.set(bl.om.Poisson('r', bl.oint(0, 8, 12)),
+          bl.tm.CombinedTransitionModel(
+              bl.tm.ChangePoint('t', [2, 4]),
+              bl.tm.SerialTransitionModel(bl.tm.NotEqual('q4', -4.), bl.tm.BreakPoint('b6', 3),
+                                          bl.tm.RegimeSwitch('p5', [-7., -4.]))), silent=True)
+    S.fit(silent=True)
+    assert not S.sweepStats['shared']
+    np.testing.assert_allclose(S.logEvidenceList, [-15.92795686903254, -15.927738811661808, -14.397293915094128,
+                                                   -14.397330652637821], rtol=1e-10)
+    assert abs(S.logEvidence - (-14.894547565491354)) < 1e-9
+    np.testing.assert_allclose(S.posteriorMeanValues[0], [
+        1.826368071727187, 5.256682591927492, 1.864359256320257, 4.250236184533213, 4.249751692782431, 1.707450557414314,
+        1.7074487137590055, 1.707457673995852], rtol=1e-9)
 
 
 def test_sm_assignment_table_of_a_c2_like_sweep(oracle_engine):
