@@ -1038,6 +1038,11 @@ class HyperStudy(Study):
             eng.run('accumulate', plan, 0, T=T, B=nb, program=sw['program'], lo=s0, log_weight=weights[s0:s0 + nb], avg=avg,
                     alpha_seq=buf, row_scale=rowScale, alive=alive[s0:s0 + nb], log_evidence=logE[s0:s0 + nb], **base,
                     **window(0))
+        if not bool((alive[:B] == 1).all()):
+            # a combination died on the way (zero norm, core.py:388-400, :440-452): the reference leaves the local
+            # evidences of its forward pass in the rows the backward pass never reached (core.py:1356 keeps them) --
+            # the plain sweep reproduces exactly that, the windowed passes do not
+            return None
         part = sw['part']
         part.zero_()
         eng.mix(plan, local, sw['hpDev'], B, T, part)

@@ -253,6 +253,33 @@ def test_prefix_sharing_only_where_the_history_is_erased(use_oracle):
     assert structure(ranged, cls=bl.HyperStudy) is None
 
 
+def test_shared_sweep_with_a_dead_combination_falls_back_to_the_plain_schedule(use_oracle):
+    """A NotEqual model turns a flat distribution into 0/0: with a missing value right behind the change-point the
+    combination dies (zero / NaN norm, core.py:388-400, :440-452).  The reference keeps the local evidences of the
+    forward pass in the rows the backward pass never reached (core.py:1356); the plain sweep reproduces that, so a
+    shared sweep in which a combination died is run again with the plain schedule."""
+    import bayesloop_b200 as bl
+    data = np.array([0.84, -0.15, 0.26, 0.53, 0.69, -0.89, 0.47, -0.02, -0.60, -0.68, -0.23, np.nan, -1.46, 0.06, 0.77, -0.24])
+
+    def fit(share):
+        S = bl.HyperStudy(silent=True)
+        S.loadData(data, silent=True)
+        S.set(bl.om.ScaledAR1('rho', bl.oint(-1, 1, 10), 'sig', bl.oint(0, 3, 10)),
+              bl.tm.CombinedTransitionModel(bl.tm.NotEqual('q', [-3., -2., -1.]), bl.tm.ChangePoint('t', list(range(1, 15)))),
+              silent=True)
+        S.shareChangepoints = share
+        S.fit(silent=True)
+        return S
+
+    shared, plain = fit(True), fit(False)
+    dead = ~np.isfinite(np.asarray(plain.logEvidenceList))
+    assert dead.any() and not dead.all()
+    assert not shared.sweepStats['shared']
+    np.testing.assert_array_equal(np.asarray(shared.logEvidenceList), np.asarray(plain.logEvidenceList))
+    np.testing.assert_array_equal(np.asarray(shared.localEvidence), np.asarray(plain.localEvidence))
+    np.testing.assert_allclose(shared.posteriorSequence, plain.posteriorSequence, rtol=1e-12)  # other summation order
+
+
 def test_changepoint_sweep_next_to_a_serial_model_matches_the_reference(use_oracle):
     """Found by oracle/fuzz_lowering.py (seeds 22257, 22726, 25252 of 8 000): a HyperStudy over the time of a
     change-point combined with a Serial model (NotEqual before, RegimeSwitch after a FIXED break-point) was run with
