@@ -14,8 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 needs_reference = pytest.mark.skipif(not os.path.isdir('/root/reference/bayesloop'), reason='needs /root/reference')
 
 
-def _run(script):
-    return subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', script)], capture_output=True, text=True,
+def _run(script, *args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', script)] + list(args), capture_output=True, text=True,
                           timeout=900, cwd=ROOT)
 
 
@@ -41,3 +41,15 @@ def test_the_references_own_test_files_pass_against_the_product():
                       'test_transitionmodels.py::TestBuiltin::test_bivariaterandomwalk',
                       'test_transitionmodels.py::TestBuiltin::test_deterministic'], out[-3000:]
     assert re.search(r'3 failed, 46 passed', out), out[-500:]
+
+
+@needs_reference
+@pytest.mark.parametrize('script,args', [('fuzz_lowering.py', ('150', '0')), ('fuzz_lowering.py', ('150', '22200')),
+                                         ('fuzz_sharing.py', ('150', '0'))])
+def test_randomised_sweeps_agree_with_the_reference(script, args):
+    """Random model trees (oracle/fuzz_lowering.py; the second range holds seed 22257, one of the three sweeps that
+    exposed the shared schedule next to a Serial model) and random (change-points) x (hyper-parameters) sweeps with the
+    shared and the plain schedule (oracle/fuzz_sharing.py) against the unmodified reference."""
+    run = _run(script, *args)
+    tail = run.stdout.strip().splitlines()[-1] if run.stdout.strip() else run.stderr[-500:]
+    assert run.returncode == 0 and re.search(r'\b0 differ', tail), run.stdout[-2000:]
