@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY (build container; needs /root/reference).  Randomised differential test of the change-point
 prefix sharing: random (change-points) x (hyper-parameter lists) sweeps -- Poisson / Gaussian /
-ScaledAR1 grids, one or two random walks, optional RegimeSwitch / NotEqual / Static in any order, missing values, time
+ScaledAR1 grids, one or two random walks, optional RegimeSwitch / NotEqual / Static in any order, hyper-priors of every
+kind (none / callable / array / SymPy random variable), missing values, time
 stamps with an offset, forwardOnly / evidenceOnly, random wave caps -- fitted by the unmodified reference, by the product
 with the shared schedule and by the product with the plain schedule (host logic -> C ABI -> CPU oracle); log-evidences,
 hyper-parameter distributions, posterior means, averaged posterior sequences and local evidences must agree to 1e-8.
@@ -69,6 +70,21 @@ def draw(seed):
     if rng.random() < 0.2:
         parts.append(('static',))
     parts = [parts[i] for i in rng.permutation(len(parts))]
+    # hyper-prior of every part that has hyper-parameters: none / callable / array / SymPy random variable
+    # (core.py:1183-1240; the array is normalised in place there, so each build gets a fresh one)
+    prior_kinds = [str(rng.choice(['none', 'none', 'callable', 'array', 'sympy'])) for _ in parts]
+    prior_seeds = [int(rng.integers(0, 2 ** 31)) for _ in parts]
+
+    def hyper_prior(k, values):
+        import sympy.stats
+        kind = prior_kinds[k]
+        if kind == 'none' or isinstance(values, str):
+            return {}
+        if kind == 'callable':
+            return {'prior': lambda x: 1. / (1. + np.abs(x))}
+        if kind == 'array':
+            return {'prior': 0.25 + np.random.default_rng(prior_seeds[k]).random(len(values))}
+        return {'prior': sympy.stats.Normal('h%d' % k, float(np.mean(values)), 1. + float(np.ptp(values)))}
     wave = None if rng.random() < 0.5 else int(rng.integers(1, 9))
     kw, r = {}, rng.random()
     if r < 0.15:
@@ -80,11 +96,11 @@ def draw(seed):
         models = []
         for k, p in enumerate(parts):
             if p[0] == 'cp':
-                models.append(bl.tm.ChangePoint('t', p[1]))
+                models.append(bl.tm.ChangePoint('t', p[1], **hyper_prior(k, p[1])))
             elif p[0] == 'grw':
-                models.append(bl.tm.GaussianRandomWalk('s%d' % k, p[2], target=p[1]))
+                models.append(bl.tm.GaussianRandomWalk('s%d' % k, p[2], target=p[1], **hyper_prior(k, p[2])))
             elif p[0] == 'rs':
-                models.append(bl.tm.RegimeSwitch('p%d' % k, p[1]))
+                models.append(bl.tm.RegimeSwitch('p%d' % k, p[1], **hyper_prior(k, p[1])))
             elif p[0] == 'ne':
                 models.append(bl.tm.NotEqual('q%d' % k, p[1]))
             else:
@@ -102,7 +118,7 @@ def draw(seed):
             S.shareChangepoints, S.maxWave = share, wave
         S.fit(**kw)
         return S
-    return build, '%s/%s T=%d %s wave=%s %s' % (cls, which, T, [p[0] for p in parts], wave, kw)
+    return build, '%s/%s T=%d %s priors %s wave=%s %s' % (cls, which, T, [p[0] for p in parts], prior_kinds, wave, kw)
 
 
 def extract(S, evidence_only):
