@@ -1192,7 +1192,8 @@ class HyperStudy(Study):
         top = np.amax(logDist)
         dist = np.exp(logDist - top)
         self.hyperParameterDistribution = dist / np.sum(dist) / np.prod(self.hyperGridConstant)
-        self.logEvidence = float(top + np.log(np.sum(dist))) if np.isfinite(top) else -np.inf
+        # scipy's logsumexp (core.py:1405) hands back a non-finite maximum as it is: -inf (every combination dead), NaN, +inf
+        self.logEvidence = float(top + np.log(np.sum(dist))) if np.isfinite(top) else float(top)
         self.localEvidence = localEv
         if not silent:
             print('    + Computed hyper-parameter distribution')
