@@ -92,9 +92,22 @@ def _share_structure(ops, T):
     return dict(k=k, group=group, cidx=cidx, cvals=cvals.astype(np.int64), nG=nG, nC=nC)
 
 
+def _combo_cost(ops, B, T):
+    """Predicted cost of one time step of every combination, in units of one convolution tap per cell: the elementwise
+    work of a step (~18: DESIGN.md 6 counts 46 FMA per update at 28 taps) plus 2 R + 1 taps per random-walk operator,
+    weighted with the share of the steps on which the operator is active (segments of Serial models)."""
+    cost = np.full(int(B), 18.0)
+    for op in ops:
+        radius = np.asarray(op['radius'], dtype=np.int64).reshape(int(B))
+        w = np.asarray(op['window'], dtype=np.int64).reshape(int(B), 4)
+        active = np.clip(np.minimum(w[:, 1], T) - np.maximum(w[:, 0], 0), 0, T) / float(max(T, 1))
+        cost += np.where(radius > 0, 2 * radius + 1, 0) * active
+    return cost
+
+
 def _deal_shared(share, ops, size, slots, fits_all_groups):
     """How a (groups) x (change-points) sweep is dealt over `size` ranks: 'groups' (whole groups, every change-point),
-    'changepoints' (every group, a subset of the change-points) or None (no sharing: plain round-robin deal).  The
+    'changepoints' (every group, a subset of the change-points) or None (no sharing: rows dealt by predicted cost).  The
     answer depends only on its arguments, which are the same on every rank.
 
     A shared sweep launches one forward and one backward pass per change-point with B = (groups of the rank) combos
@@ -109,10 +122,7 @@ def _deal_shared(share, ops, size, slots, fits_all_groups):
     nG, nC = share['nG'], share['nC']
     rep = np.full(nG, -1, dtype=np.int64)
     rep[share['group']] = np.arange(len(share['group']))  # one representative combo per group
-    cost = np.full(nG, 18.0)  # elementwise work of a step in units of one convolution tap (46 FMA at 28 taps)
-    for op in ops:
-        radius = np.asarray(op['radius'], dtype=np.int64).reshape(len(share['group']), -1)[rep]
-        cost += np.where(radius > 0, 2 * radius + 1, 0).sum(axis=1)
+    cost = _combo_cost(ops, len(share['group']), 1 << 30)[rep]  # (the operators next to a shared reset are always active)
 
     def launch(sel):  # makespan of one launch: combos by descending cost onto the least loaded of `slots` slots
         c = np.sort(cost[sel])[::-1]
@@ -864,7 +874,7 @@ class HyperStudy(Study):
         if self.shareChangepoints and not (forwardOnly or evidenceOnly):
             share = _share_structure(ctx.ops, T)
         if share is None:
-            rows = dist.shard_rows(Ball)
+            rows = dist.deal_by_cost(_combo_cost(ctx.ops, Ball, T))
         else:
             # whole groups or whole change-points dealt round-robin over the ranks (_deal_shared picks the cheaper deal)
             rank, size = dist.world()
@@ -878,7 +888,7 @@ class HyperStudy(Study):
             elif (deal == 'groups' and share['nG'] < size) or (deal == 'changepoints' and share['nC'] // size < 2):
                 deal = None
             if deal is None:
-                share, rows = None, dist.shard_rows(Ball)
+                share, rows = None, dist.deal_by_cost(_combo_cost(ctx.ops, Ball, T))
             else:
                 # this rank's combinations are laid out change-point-major: slot = (change-point index) * nG + (group index)
                 gsel = np.arange(rank, share['nG'], size) if deal == 'groups' else np.arange(share['nG'])

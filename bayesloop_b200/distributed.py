@@ -1,17 +1,18 @@
 """Multi-GPU sharding of the hyper-parameter sweep: one process per GPU, torch.distributed for the plumbing.
 
 The sweep is embarrassingly parallel over hyper-parameter combinations (the reference itself splits this axis over
-processes, core.py:1463-1465).  Rows of hyperGridValues are dealt round-robin (row i -> rank i % world): the cost of
-a combination grows with its random-walk width, which varies smoothly along the grid axes, so interleaving gives
-every rank the same cost mix (a contiguous np.array_split hands one rank all the wide kernels: measured 82 %
-scaling efficiency at 2 GPUs).  Every rank runs its own waves with NO per-step communication; merge once:
+processes, core.py:1463-1465).  Rows of hyperGridValues are dealt BY PREDICTED COST (deal_by_cost: descending cost,
+laps of alternating direction): the cost of a combination grows with its random-walk widths, so a contiguous
+np.array_split hands one rank all the wide kernels (measured 82 % scaling efficiency at 2 GPUs) and plain round-robin
+still gives every rank a fixed residue of the inner grid index (3 - 5 % at 8 GPUs on a 64 x 64 hyper-grid).  Every rank
+runs its own waves with NO per-step communication; merge once:
 
   * all-gather of the per-combo log-evidence / alive flags (B doubles)                        -- core.py:1336
   * all-reduce(sum) of the per-rank partial local evidence [T]                                 -- core.py:1337,1410
   * all-reduce(max) of the per-rank reference log-weight, local re-base by exp(m_r - M), then
     all-reduce(sum) of the running average [T x G] over NCCL / NVLink                          -- core.py:1339-1340
 
-OnlineStudy shards its hypotheses the same way (row h of the concatenated hypothesis list -> rank h % world): every
+OnlineStudy deals its hypotheses round-robin (row h of the concatenated hypothesis list -> rank h % world): every
 rank filters its own rows of the [H x G] state; per step one all-gather of the H evidence increments (H doubles)
 keeps the O(H) bookkeeping of core.py:2171-2215 identical on all ranks, and the marginalised posterior is an
 all-reduce(sum) of the per-rank weighted row sums [G] when somebody reads it.
@@ -36,6 +37,23 @@ def shard_rows(B, rank=None, size=None):
     if rank is None:
         rank, size = world()
     return np.arange(rank, int(B), size)
+
+
+def deal_by_cost(cost, rank=None, size=None):
+    """Row indices owned by a rank when the rows are dealt by predicted cost: rows in descending cost, handed out in
+    laps 0 .. size-1, size-1 .. 0, ... (every rank gets one row of each lap, the direction alternates), returned in
+    ascending order.  Plain round-robin puts row i on rank i % size, which on a Cartesian hyper-grid whose inner axis
+    length is a multiple of the world size gives every rank a fixed residue of the inner index: at C3 (64 x 64 widths
+    on 8 GPUs) the last rank owns the widest random walks of every block of 8 (7 % more work than the first; the ranks
+    were seen to wait 4.7 % of the fit in the first collective, profiles/r2Y2_bench_n8.json)."""
+    if rank is None:
+        rank, size = world()
+    cost = np.asarray(cost, dtype=float)
+    order = np.argsort(-cost, kind='stable')
+    pos = np.arange(len(order))
+    lap, k = pos // size, pos % size
+    owner = np.where(lap % 2 == 0, k, size - 1 - k)
+    return np.sort(order[owner == rank])
 
 
 def gather_rows(eng, logE, alive, Ball, rows=None):

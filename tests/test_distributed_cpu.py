@@ -58,7 +58,8 @@ def test_two_ranks_reproduce_the_golden_hyperstudy(tmp_path):
     name = 'syn_hyper_poisson_sweep'
     ranks = _run(name, tmp_path)
     want = load_golden(name)
-    assert [list(r['shard']) for r in ranks] == [[0, 2, 4, 6, 8, 10], [1, 3, 5, 7, 9, 11]]
+    # 12 widths of growing cost, dealt by predicted cost in laps of alternating direction (distributed.deal_by_cost)
+    assert [list(r['shard']) for r in ranks] == [[0, 3, 4, 7, 8, 11], [1, 2, 5, 6, 9, 10]]
     for r in ranks:
         r.pop('shard')
         parity.compare(name, r, want, rtol=2e-9, atol_post=1e-13)
@@ -122,7 +123,7 @@ def test_more_ranks_than_hypotheses(tmp_path):
     (2, 'groups', 'groups', [0, 2, 4, 6, 8, 10, 12, 14]),
     (3, 'changepoints', 'changepoints', [0, 1, 2, 3, 4, 5, 18, 19]),
     (3, 'groups', 'groups', [0, 3, 6, 9, 12, 15, 18, 21]),
-    (5, 'changepoints', 'None', [0, 5, 10, 15, 20, 25, 30, 35]),  # 8 change-points over 5 ranks: < 2 each -> plain deal
+    (5, 'changepoints', 'None', None),  # 8 change-points over 5 ranks: < 2 each -> plain deal (by predicted cost)
 ])
 def test_changepoint_study_with_prefix_sharing_dealt_by_groups_or_by_changepoints(tmp_path, world, deal, want_deal, first_rows):
     """C4 in miniature (8 change-points x 6 groups of random-walk widths) with the change-point prefix sharing under
@@ -135,7 +136,10 @@ def test_changepoint_study_with_prefix_sharing_dealt_by_groups_or_by_changepoint
     want = load_golden(name)
     owned = np.sort(np.concatenate([r['shard'] for r in ranks]))
     assert list(owned) == list(range(48))
-    assert list(ranks[0]['shard'][:8]) == first_rows
+    if first_rows is not None:
+        assert list(ranks[0]['shard'][:8]) == first_rows
+    else:
+        assert sorted(len(r['shard']) for r in ranks) == [9, 9, 10, 10, 10]
     for r in ranks:
         stats = r.pop('stats')
         assert str(stats['deal']) == want_deal and bool(stats['shared']) == (want_deal != 'None')
