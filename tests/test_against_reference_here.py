@@ -46,13 +46,13 @@ def test_the_references_own_test_files_pass_against_the_product():
 @needs_reference
 @pytest.mark.parametrize('script,args', [('fuzz_lowering.py', ('150', '0')), ('fuzz_lowering.py', ('150', '22200')),
                                          ('fuzz_sharing.py', ('150', '0')), ('fuzz_models.py', ('150', '0')),
-                                         ('fuzz_online.py', ('150', '0'))])
+                                         ('fuzz_online.py', ('150', '0')), ('fuzz_timestamps.py', ('150', '0'))])
 def test_randomised_sweeps_agree_with_the_reference(script, args):
     """Random model trees (oracle/fuzz_lowering.py; the second range holds seed 22257, one of the three sweeps that
     exposed the shared schedule next to a Serial model) and random (change-points) x (hyper-parameters) sweeps with the
     shared and the plain schedule (oracle/fuzz_sharing.py), random observation models x priors x data shapes
-    (oracle/fuzz_models.py), random OnlineStudy hypotheses with hyper-priors and model priors (oracle/fuzz_online.py)
-    against the unmodified reference."""
+    (oracle/fuzz_models.py), random OnlineStudy hypotheses with hyper-priors and model priors (oracle/fuzz_online.py),
+    Serial models on irregular time stamps (oracle/fuzz_timestamps.py) against the unmodified reference."""
     run = _run(script, *args)
     tail = run.stdout.strip().splitlines()[-1] if run.stdout.strip() else run.stderr[-500:]
     assert run.returncode == 0 and re.search(r'\b0 differ', tail), run.stdout[-2000:]
