@@ -573,6 +573,18 @@ def _cpu_worker(job):
         return cpu_port_sample(*job)
 
 
+def _cpu_worker_warm(_):
+    """Imports of a worker process (torch, the package, the port), kept out of the timed steps whatever --warmup is."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    with contextlib.redirect_stdout(io.StringIO()):
+        import bayesloop_b200  # noqa: F401
+        import helpers  # noqa: F401
+        import np_oracle  # noqa: F401
+    time.sleep(0.2)  # long enough for every worker of the pool to take one of these
+    return 0
+
+
 CPU_SAMPLE = {'c2': (24, 4000), 'c3': (6, 40), 'c4': (6, 40), 'c5': (8, 12)}  # (combos, time steps) of the 1-core sample
 
 
@@ -602,6 +614,7 @@ def run_reference(args, rank, world):
     ctx = mp.get_context('spawn')
     times = []
     with ctx.Pool(workers) as pool:
+        pool.map(_cpu_worker_warm, range(4 * workers), chunksize=1)
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             res = pool.map(_cpu_worker, jobs)
