@@ -68,6 +68,16 @@ def test_cuda_library_contains_sm100a_sass_with_bulk_copies():
     assert any('LDGSTS' in b for b in tiles)
     for b in tiles:
         assert 'DFMA' in b and ' LDL' not in b and ' STL' not in b, 'register spill in the tile kernel'
+    # headline kernels of the bench (C2: grid 1000 = 4 tiles of 64 cells per compute warp, 160 threads): the convolution
+    # is issued as FP64 matrix instructions, the backward pass stages its rows with bulk copies, nothing spills
+    # (profiles/r2_sass_resources.txt)
+    headline = [b for b in blocks if b.startswith(('_ZN3blg21fwd_fast1d_mma_kernelILi4ELi160ELb0E',
+                                                   '_ZN3blg21bwd_fast1d_mma_kernelILi4ELi160E'))]
+    assert len(headline) == 2
+    for b in headline:
+        assert 'DMMA' in b, 'FP64 matrix instructions missing from a headline kernel'
+        assert 'UBLKCP' in b or 'fwd_fast1d' in b[:40], 'bulk copies missing from the backward headline kernel'
+        assert ' LDL' not in b and ' STL' not in b, 'register spill in a headline kernel'
 
 
 def test_product_fails_loudly_without_cuda(monkeypatch):
