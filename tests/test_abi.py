@@ -104,6 +104,27 @@ def test_ctypes_structs_match_the_header(tmp_path):
     assert got == want
 
 
+def test_integration_stub_declares_the_same_structures_as_the_binding():
+    """The ctypes stub INTEGRATION.md shows a bayesloop maintainer is executable documentation: its four structures must
+    have the field names, order and sizes of the binding the product uses (bayesloop_b200/engine.py), which the test
+    above ties to include/blgrid.h."""
+    import re
+    from bayesloop_b200 import engine
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    block = text[text.index('class Problem(ctypes.Structure):'):text.index('def fit_on_gpu')]
+    scope = {'ctypes': ctypes}
+    exec(block, scope)  # class definitions only
+    for name, ours in (('Problem', engine._Problem), ('Program', engine._Program), ('Inputs', engine._Inputs),
+                       ('Outputs', engine._Outputs)):
+        stub = scope[name]
+        assert [f[0] for f in stub._fields_] == [f[0] for f in ours._fields_], name
+        assert ctypes.sizeof(stub) == ctypes.sizeof(ours), name
+        assert [getattr(stub, f[0]).offset for f in stub._fields_] == [getattr(ours, f[0]).offset for f in ours._fields_], name
+    # every entry point the stub calls is declared by the header
+    called = set(re.findall(r'_lib\.(blg_[a-z_]+)', text))
+    assert called and called <= set(declared_symbols()), called - set(declared_symbols())
+
+
 def test_python_constants_match_the_header_enums():
     """Flags, operator codes and observation-model codes are duplicated in the binding (engine.py,
     transitionModels.py, observationModels.py): they must be the values of include/blgrid.h."""
